@@ -1,0 +1,945 @@
+// oracle/hb_oracle.cpp — CPU restatement of hydrobricks' per-time-step solve (ModelHydro::Run()).
+//
+// TEST INFRASTRUCTURE ONLY (see hb_oracle.h). Plain C++, flat arrays, no virtual dispatch. Every
+// function cites the reference file:line (under /root/reference/core/src) it restates. The
+// arithmetic keeps the reference's operation order and its float32-parameter promotions, so that on
+// the same compiler flags it reproduces the compiled reference (oracle/_ref) bit for bit.
+//
+// Parity status: PINNED (tests/test_oracle_kat.py: SolverTest / ModelSocontTest known-answer vectors;
+// tests/test_oracle_vs_ref.py: bit-exact against oracle/_ref where that library is present;
+// tests/golden/*.npz: vectors generated from the reference by tools/make_goldens.py).
+#include "hb_oracle.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <limits>
+#include <string>
+#include <vector>
+
+namespace {
+
+// base/NumericConstants.h:21-34
+const double EPSILON_D = std::numeric_limits<double>::epsilon();
+const double EPSILON_F = std::numeric_limits<float>::epsilon();
+const double PRECISION = 0.00000001;
+
+inline bool NearlyEqual(double a, double b, double tol) { return std::fabs(a - b) <= tol; }
+inline bool NearlyZero(double v, double tol) { return std::fabs(v) <= tol; }
+inline bool GreaterThan(double a, double b, double tol) { return a > b + tol; }
+inline bool LessThanOrEqual(double a, double b, double tol) { return a <= b + tol; }
+
+struct Flux {  // fluxes/Flux.h:133-153
+    int kind;
+    double amount = 0;
+    double* changeRate = nullptr;
+    bool isStatic = false;
+    bool needsWeighting = false;
+    double fractionUnitArea = 1.0;
+    double fractionLandCover = 1.0;
+    double fractionTotal = 1.0;
+    int targetContainer = -1;
+    int forcingVar = -1;
+    int unit = -1;
+};
+
+struct Container {  // containers/WaterContainer.h:342-353
+    int brick;
+    int contentKind;
+    double content = 0, dyn = 0, stat = 0, initial = 0;
+    bool hasCapacity = false;
+    float capacity = 0;
+    bool infinite = false;
+    bool noMeltWhenSnowCover = false;
+    int relatedSnowpackBrick = -1;
+    int overflowProcess = -1;
+    std::vector<int> inputs;
+};
+
+struct Process {
+    int brick, type, container;
+    float params[4] = {0, 0, 0, 0};
+    int targetBrick = -1;
+    double unitArea = 0;
+    float slope = 0;
+    std::vector<int> outputs;
+    std::vector<double> rates;
+};
+
+struct Brick {
+    int kind, unit;
+    bool needsSolver;
+    int parent = -1;
+    double areaFraction = 1.0;
+    int water = -1, second = -1;  // second: snow (snowpack) or ice (glacier)
+    std::vector<int> processes;
+};
+
+struct Splitter {
+    int unit, type;
+    float params[4] = {0, 0, 1, 1};
+    std::vector<int> inputs, outputs;
+};
+
+struct Record {
+    int kind, id;
+};
+
+}  // namespace
+
+struct hbo_model {
+    int nUnits, nSteps, solver, spinupSteps;
+    double dt;
+    int cursor = 0;
+    std::vector<Flux> fluxes;
+    std::vector<Container> containers;
+    std::vector<Process> processes;
+    std::vector<Brick> bricks;
+    std::vector<Splitter> splitters;
+    std::vector<std::vector<int>> unitBricks, unitSplitters;
+    std::vector<int> basinBricks;
+    std::vector<int> outletFluxes;
+    std::vector<Record> records;
+    const double* forcing[3] = {nullptr, nullptr, nullptr};
+    std::vector<double> forcingStore[3];
+    double outletTotal = 0;
+    // Processor state (base/Processor.h)
+    std::vector<int> iterableBricks;
+    std::vector<double*> stateVariableChanges;
+    std::vector<double> changeRatesNoSolver, ratesBeforeSweep;
+    std::vector<double> k1, k2, k3, k4, combined, state;
+    int solvableConnectionCount = 0, directConnectionCount = 0;
+    long unconverged = 0;
+    std::string error;
+
+    double Forcing(int var, int unit) const {  // base/Forcing.cpp:12-16, TimeSeriesData.cpp:57-60
+        return forcing[var][static_cast<size_t>(cursor) * nUnits + unit];
+    }
+};
+
+namespace {
+
+struct Fail {
+    std::string msg;
+};
+
+// ---- containers -------------------------------------------------------------------------------
+
+// WaterContainer.h:151-157
+double ContentWithChanges(const Container& c) {
+    if (c.infinite) return INFINITY;
+    return c.content + c.dyn + c.stat;
+}
+// WaterContainer.h:164-170
+double ContentWithDynamicChanges(const Container& c) {
+    if (c.infinite) return INFINITY;
+    return c.content + c.dyn;
+}
+// WaterContainer.h:228-231
+bool IsNotEmpty(const Container& c) {
+    double content = ContentWithChanges(c);
+    return GreaterThan(content, 0, EPSILON_F) && GreaterThan(content, 0, PRECISION);
+}
+// WaterContainer.cpp:245-248
+double TargetFillingRatio(const Container& c) {
+    return std::max(0.0, std::min(1.0, ContentWithChanges(c) / static_cast<double>(c.capacity)));
+}
+// Snowpack.cpp:139-141
+bool HasSnow(const hbo_model& m, int snowpackBrick) { return IsNotEmpty(m.containers[m.bricks[snowpackBrick].second]); }
+
+// WaterContainer.cpp:237-239, IceContainer.cpp:22-32
+bool ContentAccessible(const hbo_model& m, const Container& c) {
+    if (c.contentKind == HBO_ICE && c.noMeltWhenSnowCover) {
+        if (c.relatedSnowpackBrick < 0) throw Fail{"No snowpack provided for the glacier melt limitation."};
+        if (HasSnow(m, c.relatedSnowpackBrick)) return false;
+    }
+    return ContentWithChanges(c) > 0;
+}
+
+// ---- fluxes -----------------------------------------------------------------------------------
+
+// FluxForcing.cpp:11-14, FluxToBrickInstantaneous.cpp:13-15, others return _amount
+double FluxGetAmount(hbo_model& m, Flux& f) {
+    if (f.kind == HBO_F_FORCING) {
+        f.amount = m.Forcing(f.forcingVar, f.unit);
+        return f.amount;
+    }
+    if (f.kind == HBO_F_TO_BRICK_INSTANT) return 0;
+    return f.amount;
+}
+
+// Flux.cpp:20-26, FluxToBrick.cpp:17-24, FluxToBrickInstantaneous.cpp:21-38, FluxSimple.cpp:14-17
+void FluxUpdate(hbo_model& m, Flux& f, double amount) {
+    if (f.kind == HBO_F_SIMPLE) {
+        f.amount = amount;
+        return;
+    }
+    if (f.kind == HBO_F_TO_BRICK_INSTANT) {
+        if (f.fractionTotal != 1.0) {
+            f.amount = amount * f.fractionTotal;
+        } else {
+            f.amount = amount;
+        }
+        Container& c = m.containers[f.targetContainer];
+        if (!c.infinite) c.stat += f.amount;  // WaterContainer.cpp:50-53
+        return;
+    }
+    if (f.fractionTotal < 1.0) {
+        f.amount = amount * f.fractionTotal;
+    } else {
+        f.amount = amount;
+    }
+}
+
+// WaterContainer.cpp:228-235
+double SumIncomingFluxes(hbo_model& m, Container& c) {
+    double sum = 0;
+    for (int i : c.inputs) sum += FluxGetAmount(m, m.fluxes[i]);
+    return sum;
+}
+
+// ---- flux-constraint step ---------------------------------------------------------------------
+
+// WaterContainer.cpp:177-194
+void SetOutgoingRatesToZero(hbo_model& m, Container& c, int containerId) {
+    for (int ip : m.bricks[c.brick].processes) {
+        Process& p = m.processes[ip];
+        if (p.container != containerId) continue;
+        for (int io : p.outputs) {
+            double* r = m.fluxes[io].changeRate;
+            if (r) *r = 0;
+        }
+    }
+}
+
+// WaterContainer.cpp:55-175 (+ IceContainer.cpp:10-20)
+void ApplyConstraints(hbo_model& m, int containerId, double timeStep) {
+    Container& c = m.containers[containerId];
+    if (c.contentKind == HBO_ICE && c.noMeltWhenSnowCover) {
+        if (c.relatedSnowpackBrick < 0) throw Fail{"No snowpack provided for the glacier melt limitation."};
+        if (HasSnow(m, c.relatedSnowpackBrick)) SetOutgoingRatesToZero(m, c, containerId);
+    }
+    if (c.infinite) return;
+
+    std::vector<double*> outgoingRates;
+    double outputs = 0;
+    for (int ip : m.bricks[c.brick].processes) {
+        Process& p = m.processes[ip];
+        if (p.container != containerId) continue;
+        for (int io : p.outputs) {
+            double* changeRate = m.fluxes[io].changeRate;
+            if (changeRate == nullptr) continue;
+            if (*changeRate < 0) {
+                *changeRate = 0;
+            } else if (*changeRate > 10000) {
+                throw Fail{"Change rate is too high."};
+            }
+            outgoingRates.push_back(changeRate);
+            outputs += *changeRate;
+        }
+    }
+
+    std::vector<double*> incomingRates;
+    double inputs = 0;
+    double inputsStatic = 0;
+    for (int ii : c.inputs) {
+        Flux& in = m.fluxes[ii];
+        if (in.kind == HBO_F_TO_BRICK_INSTANT) {
+            inputsStatic += in.amount;  // GetRealAmount()
+            continue;
+        }
+        if (in.kind == HBO_F_FORCING || in.isStatic) {
+            inputsStatic += FluxGetAmount(m, in);
+            continue;
+        }
+        double* changeRate = in.changeRate;
+        if (changeRate == nullptr) continue;
+        if (*changeRate < 0) *changeRate = 0;
+        incomingRates.push_back(changeRate);
+        inputs += *changeRate;
+    }
+
+    double change = inputs - outputs;
+    double content = ContentWithDynamicChanges(c);
+
+    // Avoid negative content
+    if (change < 0 && content + inputsStatic + change * timeStep < 0) {
+        double diff = (content + inputsStatic + change * timeStep) / timeStep;
+        for (double* rate : outgoingRates) {
+            if (NearlyZero(*rate, EPSILON_D)) continue;
+            if (NearlyEqual(diff, change, PRECISION)) {
+                *rate = 0;
+                continue;
+            }
+            *rate += diff * std::abs((*rate) / outputs);
+        }
+    }
+
+    // Enforce maximum capacity
+    if (c.hasCapacity) {
+        if (content + inputsStatic + change * timeStep > c.capacity) {
+            double diff = (content + inputsStatic + change * timeStep - c.capacity) / timeStep;
+            if (c.overflowProcess >= 0) {
+                double* r = m.fluxes[m.processes[c.overflowProcess].outputs[0]].changeRate;
+                if (r != nullptr) {
+                    *r = diff;
+                    return;
+                }
+                throw Fail{"Overflow exists but has no change rate pointer"};
+            }
+            if (content + inputsStatic > c.capacity) {
+                throw Fail{"Forcing is coming directly into a brick with limited capacity and no overflow."};
+            }
+            for (double* rate : incomingRates) {
+                if (NearlyZero(*rate, EPSILON_D)) continue;
+                *rate -= diff * std::abs((*rate) / inputs);
+            }
+        }
+    }
+}
+
+// WaterContainer.cpp:196-216
+void FinalizeContainer(Container& c) {
+    if (c.infinite) return;
+    c.content += c.dyn + c.stat;
+    c.dyn = 0;
+    c.stat = 0;
+    if (NearlyZero(c.content, PRECISION)) {
+        c.content = 0;
+        return;
+    }
+    if (c.content < 0 - PRECISION) c.content = 0;  // logged as an error in the reference
+}
+
+// ---- bricks -----------------------------------------------------------------------------------
+
+// LandCover.h:91-93, SurfaceComponent.cpp:31-40, Brick.h:170
+bool IsNull(const hbo_model& m, const Brick& b) {
+    if (b.kind == HBO_BRICK_GENERIC_LAND_COVER || b.kind == HBO_BRICK_GLACIER) {
+        return NearlyZero(b.areaFraction, PRECISION);
+    }
+    if (b.kind == HBO_BRICK_SNOWPACK) {
+        if (NearlyZero(b.areaFraction, PRECISION)) return true;
+        if (b.parent >= 0 && IsNull(m, m.bricks[b.parent])) return true;
+        return false;
+    }
+    return false;
+}
+
+// Brick.cpp:166-168, Snowpack.cpp:109-112, Glacier.cpp:116-119
+void UpdateContentFromInputs(hbo_model& m, Brick& b) {
+    if (b.kind == HBO_BRICK_SNOWPACK) {
+        Container& snow = m.containers[b.second];
+        double s = SumIncomingFluxes(m, snow);
+        if (!snow.infinite) snow.stat += s;
+    } else if (b.kind == HBO_BRICK_GLACIER) {
+        Container& ice = m.containers[b.second];
+        double s = SumIncomingFluxes(m, ice);
+        if (!ice.infinite) ice.dyn += s;
+    }
+    Container& w = m.containers[b.water];
+    double s = SumIncomingFluxes(m, w);
+    if (!w.infinite) w.dyn += s;
+}
+
+// Brick.cpp:170-172, Snowpack.cpp:114-117, Glacier.cpp:121-124
+void BrickApplyConstraints(hbo_model& m, Brick& b, double dt) {
+    if (b.second >= 0) ApplyConstraints(m, b.second, dt);
+    ApplyConstraints(m, b.water, dt);
+}
+
+// Brick.cpp:127-135, Snowpack.cpp:58-67, Glacier.cpp:71-74
+void BrickFinalize(hbo_model& m, Brick& b) {
+    if (b.second >= 0) FinalizeContainer(m.containers[b.second]);
+    FinalizeContainer(m.containers[b.water]);
+}
+
+// ---- processes --------------------------------------------------------------------------------
+
+void StoreRates1(Process& p, double v) { p.rates.assign(1, v); }
+
+void GetRates(hbo_model& m, Process& p) {
+    Container& c = m.containers[p.container];
+    const int unit = m.bricks[p.brick].unit;
+    switch (p.type) {
+        case HBO_P_MELT_DEGREE_DAY: {  // ProcessMeltDegreeDay.cpp:49-60
+            if (!ContentAccessible(m, c)) {
+                StoreRates1(p, 0);
+                return;
+            }
+            double melt = 0;
+            const float ddf = p.params[0], tm = p.params[1];
+            double t = m.Forcing(HBO_V_TEMPERATURE, unit);
+            if (t >= tm) melt = (t - tm) * ddf;
+            StoreRates1(p, melt);
+            return;
+        }
+        case HBO_P_ET_SOCONT: {  // ProcessETSocont.cpp:35-38 (exponent is a float member = 0.5)
+            const float exponent = 0.5f;
+            StoreRates1(p, m.Forcing(HBO_V_PET, unit) * pow(TargetFillingRatio(c), exponent));
+            return;
+        }
+        case HBO_P_INFILTRATION_SOCONT: {  // ProcessInfiltrationSocont.cpp:17-23, ProcessInfiltration.cpp:35-45
+            Container& target = m.containers[m.bricks[p.targetBrick].water];
+            if (static_cast<double>(target.capacity) <= 0) {
+                StoreRates1(p, 0);
+                return;
+            }
+            StoreRates1(p, ContentWithChanges(c) * (1 - pow(TargetFillingRatio(target), 2)));
+            return;
+        }
+        case HBO_P_RUNOFF_SOCONT: {  // ProcessRunoffSocont.cpp:41-56
+            double storageShape = 2.0;
+            const double dt = 86400;
+            const double exponent = 5.0 / 3.0;
+            const float beta = p.params[0];
+            double area = p.unitArea;  // surface_runoff is a storage: no area fraction (ProcessRunoffSocont.cpp:33-39)
+            double h = ContentWithChanges(c) * storageShape / 1000;
+            double qQuick = beta * pow(p.slope, 0.5) * pow(h, exponent) / area;
+            double dh = qQuick * storageShape * dt;
+            double runoff = (dh / storageShape) * 1000;
+            StoreRates1(p, std::min(runoff, ContentWithChanges(c)));
+            return;
+        }
+        case HBO_P_OUTFLOW_LINEAR: {  // ProcessOutflowLinear.cpp:19-21
+            const float k = p.params[0];
+            StoreRates1(p, k * ContentWithChanges(c));
+            return;
+        }
+        case HBO_P_OUTFLOW_DIRECT:  // ProcessOutflowDirect.cpp:42-44
+            StoreRates1(p, std::max(ContentWithChanges(c), 0.0));
+            return;
+        case HBO_P_OUTFLOW_REST: {  // ProcessOutflowRest.cpp:13-41
+            double rest = ContentWithChanges(c);
+            Brick& b = m.bricks[p.brick];
+            if (b.needsSolver) {
+                for (int ip : b.processes) {
+                    Process& other = m.processes[ip];
+                    if (&other == &p) continue;
+                    for (int io : other.outputs) {
+                        double* rate = m.fluxes[io].changeRate;
+                        if (rate != nullptr) rest -= *rate;
+                    }
+                }
+            }
+            StoreRates1(p, std::max(rest, 0.0));
+            return;
+        }
+        case HBO_P_OVERFLOW:  // ProcessOutflowOverflow.cpp:17-19
+            StoreRates1(p, 0);
+            return;
+        case HBO_P_PERCOLATION_CONSTANT: {  // ProcessPercolationConstant.cpp:23-25
+            const float r = p.params[0];
+            StoreRates1(p, r);
+            return;
+        }
+        default:
+            throw Fail{"unknown process type"};
+    }
+}
+
+// Process.cpp:480-487
+const std::vector<double>& GetChangeRates(hbo_model& m, Process& p) {
+    if (LessThanOrEqual(ContentWithChanges(m.containers[p.container]), 0, PRECISION)) {
+        p.rates.assign(p.outputs.size(), 0.0);
+        return p.rates;
+    }
+    GetRates(m, p);
+    return p.rates;
+}
+
+// Process.cpp:489-493, ProcessOutflowOverflow.cpp:21-26
+void StoreInOutgoingFlux(hbo_model& m, Process& p, double* rate, int index) {
+    if (p.type == HBO_P_OVERFLOW) *rate = 0;
+    m.fluxes[p.outputs[index]].changeRate = rate;
+}
+
+// Process.cpp:495-508
+void ApplyChange(hbo_model& m, Process& p, int connectionIndex, double rate, double dt) {
+    if (rate < 0) rate = 0;
+    Flux& f = m.fluxes[p.outputs[connectionIndex]];
+    if (GreaterThan(rate, 0, PRECISION)) {
+        FluxUpdate(m, f, rate * dt);
+        Container& c = m.containers[p.container];
+        if (!c.infinite) c.dyn -= rate * dt;  // WaterContainer.cpp:40-43
+    } else {
+        FluxUpdate(m, f, 0);
+    }
+}
+
+// ---- splitters --------------------------------------------------------------------------------
+
+void SplitterCompute(hbo_model& m, Splitter& s) {
+    switch (s.type) {
+        case HBO_S_SNOW_RAIN_LINEAR: {  // SplitterSnowRainLinear.cpp:49-64
+            const float t0 = s.params[0], t1 = s.params[1];
+            double precip = m.Forcing(HBO_V_PRECIPITATION, s.unit);
+            double temp = m.Forcing(HBO_V_TEMPERATURE, s.unit);
+            double rcf = s.params[2];
+            double scf = s.params[3];
+            if (temp <= t0) {
+                FluxUpdate(m, m.fluxes[s.outputs[0]], 0);
+                FluxUpdate(m, m.fluxes[s.outputs[1]], precip * scf);
+            } else if (temp >= t1) {
+                FluxUpdate(m, m.fluxes[s.outputs[0]], precip * rcf);
+                FluxUpdate(m, m.fluxes[s.outputs[1]], 0);
+            } else {
+                double rainFraction = (temp - t0) / (t1 - t0);  // (t1 - t0) in float32
+                FluxUpdate(m, m.fluxes[s.outputs[0]], precip * rainFraction * rcf);
+                FluxUpdate(m, m.fluxes[s.outputs[1]], precip * (1 - rainFraction) * scf);
+            }
+            return;
+        }
+        case HBO_S_SNOW_RAIN_THRESHOLD: {  // SplitterSnowRainThreshold.cpp:45-54
+            const float thr = s.params[0];
+            double precip = m.Forcing(HBO_V_PRECIPITATION, s.unit);
+            double temp = m.Forcing(HBO_V_TEMPERATURE, s.unit);
+            double rcf = s.params[2];
+            double scf = s.params[3];
+            if (temp <= thr) {
+                FluxUpdate(m, m.fluxes[s.outputs[0]], 0);
+                FluxUpdate(m, m.fluxes[s.outputs[1]], precip * scf);
+            } else {
+                FluxUpdate(m, m.fluxes[s.outputs[0]], precip * rcf);
+                FluxUpdate(m, m.fluxes[s.outputs[1]], 0);
+            }
+            return;
+        }
+        case HBO_S_RAIN: {  // SplitterRain.cpp:37-39
+            double rcf = s.params[2];
+            FluxUpdate(m, m.fluxes[s.outputs[0]], m.Forcing(HBO_V_PRECIPITATION, s.unit) * rcf);
+            return;
+        }
+        case HBO_S_MULTI_FLUXES: {  // SplitterMultiFluxes.cpp:35-40
+            for (int io : s.outputs) FluxUpdate(m, m.fluxes[io], FluxGetAmount(m, m.fluxes[s.inputs[0]]));
+            return;
+        }
+        default:
+            throw Fail{"unknown splitter type"};
+    }
+}
+
+// ---- processor --------------------------------------------------------------------------------
+
+int ConnectionCount(const hbo_model& m, const Brick& b) {
+    int n = 0;
+    for (int ip : b.processes) n += static_cast<int>(m.processes[ip].outputs.size());
+    return n;
+}
+
+// Processor.cpp:58-112
+void ConnectToElementsToSolve(hbo_model& m) {
+    m.iterableBricks.clear();
+    m.stateVariableChanges.clear();
+    m.solvableConnectionCount = m.directConnectionCount = 0;
+    for (int u = 0; u < m.nUnits; ++u) {
+        for (int ib : m.unitBricks[u]) {
+            Brick& b = m.bricks[ib];
+            if (b.needsSolver) {
+                m.iterableBricks.push_back(ib);
+                // Brick.cpp:178-180 / Snowpack.cpp:119-129 / Glacier.cpp:126-136: water first, then second
+                m.stateVariableChanges.push_back(&m.containers[b.water].dyn);
+                if (b.second >= 0) m.stateVariableChanges.push_back(&m.containers[b.second].dyn);
+                m.solvableConnectionCount += ConnectionCount(m, b);
+            } else {
+                m.directConnectionCount += ConnectionCount(m, b);
+            }
+        }
+    }
+    for (int ib : m.basinBricks) {
+        Brick& b = m.bricks[ib];
+        m.iterableBricks.push_back(ib);
+        m.stateVariableChanges.push_back(&m.containers[b.water].dyn);
+        if (b.second >= 0) m.stateVariableChanges.push_back(&m.containers[b.second].dyn);
+        m.solvableConnectionCount += ConnectionCount(m, b);
+    }
+}
+
+// Processor.cpp:191-209
+void EnforceConstraints(hbo_model& m, std::vector<double>& rates, double dt) {
+    const int maxSweeps = 10;
+    for (int sweep = 0; sweep < maxSweeps; ++sweep) {
+        m.ratesBeforeSweep = rates;
+        for (int ib : m.iterableBricks) BrickApplyConstraints(m, m.bricks[ib], dt);
+        bool stable = true;
+        for (size_t i = 0; i < rates.size(); ++i) {
+            if (!(std::fabs(rates[i] - m.ratesBeforeSweep[i]) <= PRECISION)) {
+                stable = false;
+                break;
+            }
+        }
+        if (stable) return;
+    }
+    m.unconverged++;
+}
+
+// Processor.cpp:146-172
+void EvaluateRates(hbo_model& m, std::vector<double>& rates, double dt, bool applyConstraints = true) {
+    int iRate = 0;
+    for (int ib : m.iterableBricks) {
+        for (int ip : m.bricks[ib].processes) {
+            Process& p = m.processes[ip];
+            const std::vector<double>& processRates = GetChangeRates(m, p);
+            for (size_t j = 0; j < processRates.size(); ++j) {
+                rates[iRate] = processRates[j];
+                if (applyConstraints) StoreInOutgoingFlux(m, p, &rates[iRate], static_cast<int>(j));
+                iRate++;
+            }
+        }
+    }
+    if (applyConstraints) EnforceConstraints(m, rates, dt);
+}
+
+// Processor.cpp:174-189
+void ConstrainRates(hbo_model& m, std::vector<double>& rates, double dt) {
+    int iRate = 0;
+    for (int ib : m.iterableBricks) {
+        for (int ip : m.bricks[ib].processes) {
+            Process& p = m.processes[ip];
+            for (size_t j = 0; j < p.outputs.size(); ++j) {
+                StoreInOutgoingFlux(m, p, &rates[iRate], static_cast<int>(j));
+                iRate++;
+            }
+        }
+    }
+    EnforceConstraints(m, rates, dt);
+}
+
+// Processor.cpp:211-226
+void ApplyRates(hbo_model& m, const std::vector<double>& rates, double dt) {
+    int iRate = 0;
+    for (int ib : m.iterableBricks) {
+        Brick& b = m.bricks[ib];
+        if (IsNull(m, b)) continue;
+        UpdateContentFromInputs(m, b);
+        for (int ip : b.processes) {
+            Process& p = m.processes[ip];
+            for (size_t ic = 0; ic < p.outputs.size(); ++ic) {
+                ApplyChange(m, p, static_cast<int>(ic), rates[iRate], dt);
+                iRate++;
+            }
+        }
+    }
+}
+
+// Processor.cpp:228-235
+void FinalizeTimeStep(hbo_model& m) {
+    for (int ib : m.iterableBricks) {
+        Brick& b = m.bricks[ib];
+        if (IsNull(m, b)) continue;
+        BrickFinalize(m, b);
+    }
+}
+
+void ResetState(hbo_model& m) {  // Processor.cpp:140-144
+    for (double* v : m.stateVariableChanges) *v = 0;
+}
+void HalveState(hbo_model& m) {  // SolverRK4.cpp:26-29 (Gather, *= 0.5, Scatter)
+    for (size_t i = 0; i < m.stateVariableChanges.size(); ++i) m.state[i] = *m.stateVariableChanges[i];
+    for (size_t i = 0; i < m.state.size(); ++i) m.state[i] *= 0.5;
+    for (size_t i = 0; i < m.stateVariableChanges.size(); ++i) *m.stateVariableChanges[i] = m.state[i];
+}
+
+// SolverEulerExplicit.cpp:13-22
+void SolveEuler(hbo_model& m, double dt) {
+    EvaluateRates(m, m.k1, dt);
+    ApplyRates(m, m.k1, dt);
+    FinalizeTimeStep(m);
+}
+
+// SolverHeunExplicit.cpp:16-38
+void SolveHeun(hbo_model& m, double dt) {
+    EvaluateRates(m, m.k1, dt);
+    ApplyRates(m, m.k1, dt);
+    EvaluateRates(m, m.k2, dt, false);
+    ResetState(m);
+    for (size_t i = 0; i < m.combined.size(); ++i) m.combined[i] = (m.k1[i] + m.k2[i]) / 2;
+    ConstrainRates(m, m.combined, dt);
+    ApplyRates(m, m.combined, dt);
+    FinalizeTimeStep(m);
+}
+
+// SolverRK4.cpp:19-63
+void SolveRK4(hbo_model& m, double dt) {
+    EvaluateRates(m, m.k1, dt);
+    ApplyRates(m, m.k1, dt);
+    HalveState(m);
+
+    EvaluateRates(m, m.k2, dt, false);
+    ResetState(m);
+    ConstrainRates(m, m.k2, dt);
+    ApplyRates(m, m.k2, dt);
+    HalveState(m);
+
+    EvaluateRates(m, m.k3, dt, false);
+    ResetState(m);
+    ConstrainRates(m, m.k3, dt);
+    ApplyRates(m, m.k3, dt);
+
+    EvaluateRates(m, m.k4, dt, false);
+    ResetState(m);
+    for (size_t i = 0; i < m.combined.size(); ++i) {
+        m.combined[i] = (m.k1[i] + 2 * m.k2[i] + 2 * m.k3[i] + m.k4[i]) / 6;
+    }
+    ConstrainRates(m, m.combined, dt);
+    ApplyRates(m, m.combined, dt);
+    FinalizeTimeStep(m);
+}
+
+// Processor.cpp:278-323
+void ApplyDirectChanges(hbo_model& m, Brick& b, int& ptIndex, double dt) {
+    UpdateContentFromInputs(m, b);
+
+    int iRate = ptIndex;
+    for (int ip : b.processes) {
+        Process& p = m.processes[ip];
+        for (size_t j = 0; j < p.outputs.size(); ++j) {
+            m.changeRatesNoSolver[iRate] = 0;
+            StoreInOutgoingFlux(m, p, &m.changeRatesNoSolver[iRate], static_cast<int>(j));
+            iRate++;
+        }
+    }
+
+    iRate = ptIndex;
+    for (int ip : b.processes) {
+        Process& p = m.processes[ip];
+        const std::vector<double>& rates = GetChangeRates(m, p);
+        int iRateCopy = iRate;
+        for (double rate : rates) {
+            m.changeRatesNoSolver[iRateCopy] = rate;
+            iRateCopy++;
+        }
+        ApplyConstraints(m, p.container, dt);
+        for (size_t j = 0; j < rates.size(); ++j) {
+            ApplyChange(m, p, static_cast<int>(j), m.changeRatesNoSolver[iRate], dt);
+            m.changeRatesNoSolver[iRate] = 0;
+            iRate++;
+            ptIndex++;
+        }
+    }
+    BrickFinalize(m, b);
+}
+
+// Processor.cpp:237-276, SubBasin.cpp:322-329
+void ProcessTimeStep(hbo_model& m, double dt) {
+    int ptIndex = 0;
+    for (int u = 0; u < m.nUnits; ++u) {
+        for (int is : m.unitSplitters[u]) SplitterCompute(m, m.splitters[is]);
+        for (int ib : m.unitBricks[u]) {
+            Brick& b = m.bricks[ib];
+            if (b.needsSolver) continue;
+            if (IsNull(m, b)) continue;
+            ApplyDirectChanges(m, b, ptIndex, dt);
+        }
+    }
+    switch (m.solver) {
+        case HBO_SOLVER_EULER: SolveEuler(m, dt); break;
+        case HBO_SOLVER_HEUN: SolveHeun(m, dt); break;
+        default: SolveRK4(m, dt); break;
+    }
+    m.outletTotal = 0;
+    for (int io : m.outletFluxes) m.outletTotal += FluxGetAmount(m, m.fluxes[io]);
+}
+
+double RecordValue(const hbo_model& m, const Record& r) {
+    switch (r.kind) {
+        case HBO_REC_CONTAINER: return m.containers[r.id].content;
+        case HBO_REC_FLUX: return m.fluxes[r.id].amount;
+        case HBO_REC_FRACTION: return m.bricks[r.id].areaFraction;
+        default: return m.outletTotal;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+hbo_model* hbo_create(int n_units, int n_steps, double dt_days, int solver, int spinup_steps) {
+    auto* m = new hbo_model();
+    m->nUnits = n_units;
+    m->nSteps = n_steps;
+    m->dt = dt_days;
+    m->solver = solver;
+    m->spinupSteps = std::min(spinup_steps, n_steps);  // ModelHydro.cpp:52-53
+    m->unitBricks.resize(n_units);
+    m->unitSplitters.resize(n_units);
+    return m;
+}
+
+void hbo_destroy(hbo_model* m) { delete m; }
+
+int hbo_add_brick(hbo_model* m, int kind, int unit, int needs_solver, int parent_brick) {
+    Brick b;
+    b.kind = kind;
+    b.unit = unit;
+    b.needsSolver = needs_solver != 0;
+    b.parent = parent_brick;
+    m->bricks.push_back(b);
+    int id = static_cast<int>(m->bricks.size()) - 1;
+    if (unit >= 0) {
+        m->unitBricks[unit].push_back(id);
+    } else {
+        m->basinBricks.push_back(id);
+    }
+    return id;
+}
+
+void hbo_set_area_fraction(hbo_model* m, int brick, double fraction) { m->bricks[brick].areaFraction = fraction; }
+void hbo_set_parent(hbo_model* m, int brick, int parent_brick) { m->bricks[brick].parent = parent_brick; }
+void hbo_set_target_brick(hbo_model* m, int process, int target_brick) { m->processes[process].targetBrick = target_brick; }
+
+int hbo_add_container(hbo_model* m, int brick, int content_kind, float capacity, int infinite_storage,
+                      int no_melt_when_snow_cover, double initial_state) {
+    Container c;
+    c.brick = brick;
+    c.contentKind = content_kind;
+    c.hasCapacity = !std::isnan(capacity);
+    c.capacity = c.hasCapacity ? capacity : 0.0f;
+    c.infinite = infinite_storage != 0;
+    c.noMeltWhenSnowCover = no_melt_when_snow_cover != 0;
+    c.initial = initial_state;
+    m->containers.push_back(c);
+    int id = static_cast<int>(m->containers.size()) - 1;
+    if (content_kind == HBO_WATER) {
+        m->bricks[brick].water = id;
+    } else {
+        m->bricks[brick].second = id;
+    }
+    return id;
+}
+
+void hbo_set_related_snowpack(hbo_model* m, int ice_container, int snowpack_brick) {
+    m->containers[ice_container].relatedSnowpackBrick = snowpack_brick;
+}
+
+int hbo_add_process(hbo_model* m, int brick, int type, int container, const float* params, int n_params,
+                    int target_brick, double unit_area, float slope) {
+    Process p;
+    p.brick = brick;
+    p.type = type;
+    p.container = container;
+    for (int i = 0; i < n_params && i < 4; ++i) p.params[i] = params[i];
+    p.targetBrick = target_brick;
+    p.unitArea = unit_area;
+    p.slope = slope;
+    m->processes.push_back(p);
+    int id = static_cast<int>(m->processes.size()) - 1;
+    m->bricks[brick].processes.push_back(id);
+    if (type == HBO_P_OVERFLOW) m->containers[m->bricks[brick].water].overflowProcess = id;  // ModelBuilder.cpp:236-238
+    return id;
+}
+
+int hbo_add_flux(hbo_model* m, int kind, int is_static, int needs_weighting, double fraction_unit_area,
+                 int target_container, int forcing_var, int unit) {
+    Flux f;
+    f.kind = kind;
+    f.isStatic = is_static != 0;
+    f.needsWeighting = needs_weighting != 0;
+    f.fractionUnitArea = fraction_unit_area;
+    f.fractionTotal = f.fractionUnitArea * f.fractionLandCover;
+    f.targetContainer = target_container;
+    f.forcingVar = forcing_var;
+    f.unit = unit;
+    m->fluxes.push_back(f);
+    return static_cast<int>(m->fluxes.size()) - 1;
+}
+
+void hbo_process_add_output(hbo_model* m, int process, int flux) { m->processes[process].outputs.push_back(flux); }
+void hbo_container_add_input(hbo_model* m, int container, int flux) { m->containers[container].inputs.push_back(flux); }
+
+int hbo_add_splitter(hbo_model* m, int unit, int type, const float* params, int n_params) {
+    Splitter s;
+    s.unit = unit;
+    s.type = type;
+    for (int i = 0; i < n_params && i < 4; ++i) s.params[i] = params[i];
+    m->splitters.push_back(s);
+    int id = static_cast<int>(m->splitters.size()) - 1;
+    m->unitSplitters[unit].push_back(id);
+    return id;
+}
+
+void hbo_splitter_add_output(hbo_model* m, int splitter, int flux) { m->splitters[splitter].outputs.push_back(flux); }
+void hbo_splitter_add_input(hbo_model* m, int splitter, int flux) { m->splitters[splitter].inputs.push_back(flux); }
+void hbo_add_outlet_flux(hbo_model* m, int flux) { m->outletFluxes.push_back(flux); }
+
+void hbo_set_forcing(hbo_model* m, int var, const double* data) {
+    m->forcingStore[var].assign(data, data + static_cast<size_t>(m->nSteps) * m->nUnits);
+    m->forcing[var] = m->forcingStore[var].data();
+}
+
+int hbo_add_record(hbo_model* m, int kind, int id) {
+    m->records.push_back(Record{kind, id});
+    return static_cast<int>(m->records.size()) - 1;
+}
+
+// LandCover.cpp:27-37, SurfaceComponent.cpp:12-24
+void hbo_finalize_graph(hbo_model* m) {
+    for (Brick& b : m->bricks) {
+        if (b.kind == HBO_BRICK_STORAGE) continue;
+        double value = b.areaFraction;
+        for (int ip : b.processes) {
+            for (int io : m->processes[ip].outputs) {
+                Flux& f = m->fluxes[io];
+                if (!f.needsWeighting) continue;
+                if (b.kind == HBO_BRICK_SNOWPACK) {
+                    value *= m->bricks[b.parent].areaFraction;
+                }
+                f.fractionLandCover = value;
+                f.fractionTotal = f.fractionUnitArea * f.fractionLandCover;
+            }
+        }
+    }
+}
+
+int hbo_run(hbo_model* m, double* outlet, double* records) {
+    try {
+        ConnectToElementsToSolve(*m);
+        m->changeRatesNoSolver.assign(m->directConnectionCount, 0.0);
+        const int n = m->solvableConnectionCount;
+        m->k1.assign(n, 0.0);
+        m->k2.assign(n, 0.0);
+        m->k3.assign(n, 0.0);
+        m->k4.assign(n, 0.0);
+        m->combined.assign(n, 0.0);
+        m->state.assign(m->stateVariableChanges.size(), 0.0);
+        // ModelHydro::Reset (ModelHydro.cpp:183-193): containers to their initial state, fluxes to 0.
+        for (Container& c : m->containers) {
+            c.content = c.initial;
+            c.dyn = 0;
+            c.stat = 0;
+        }
+        for (Flux& f : m->fluxes) {
+            f.amount = 0;
+            f.changeRate = nullptr;
+        }
+        for (int v = 0; v < 3; ++v) {
+            if (!m->forcing[v]) {
+                m->forcingStore[v].assign(static_cast<size_t>(m->nSteps) * m->nUnits, 0.0);
+                m->forcing[v] = m->forcingStore[v].data();
+            }
+        }
+        // RunSpinup (ModelHydro.cpp:135-181): replay the first steps unlogged, then rewind the clock.
+        m->cursor = 0;
+        for (int i = 0; i < m->spinupSteps; ++i) {
+            ProcessTimeStep(*m, m->dt);
+            m->cursor++;
+        }
+        m->cursor = 0;
+        const size_t nrec = m->records.size();
+        for (int t = 0; t < m->nSteps; ++t) {
+            ProcessTimeStep(*m, m->dt);
+            if (outlet) outlet[t] = m->outletTotal;
+            for (size_t r = 0; r < nrec; ++r) records[r * m->nSteps + t] = RecordValue(*m, m->records[r]);
+            m->cursor++;
+        }
+    } catch (const Fail& f) {
+        m->error = f.msg;
+        return -1;
+    }
+    return 0;
+}
+
+const char* hbo_last_error(hbo_model* m) { return m->error.c_str(); }
+long hbo_unconverged_sweeps(hbo_model* m) { return m->unconverged; }
+
+}  // extern "C"

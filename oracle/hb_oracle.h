@@ -1,0 +1,82 @@
+/* oracle/hb_oracle.h — C API of the CPU restatement of hydrobricks' ModelHydro::Run() hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY. Nothing under hydrobricks_b200/ may include, link or call this; only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it, as the
+ * checker. See hb_oracle.cpp for the reference file:line each function follows.
+ *
+ * Parity status: PINNED — checked bit-for-bit against the compiled reference core (oracle/_ref) and
+ * against the reference's own known-answer tests (tests/test_oracle_*.py, tests/golden/).
+ *
+ * The model is a flat graph assembled by the caller (oracle/hb_oracle.py mirrors
+ * core/src/base/ModelBuilder.cpp for that): containers, bricks, processes, fluxes, splitters.
+ * All ids are indices returned by the hbo_add_* calls.
+ */
+#ifndef HB_ORACLE_H
+#define HB_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hbo_model hbo_model;
+
+enum { HBO_WATER = 0, HBO_SNOW = 1, HBO_ICE = 2 };
+enum { HBO_BRICK_STORAGE = 0, HBO_BRICK_GENERIC_LAND_COVER = 1, HBO_BRICK_GLACIER = 2, HBO_BRICK_SNOWPACK = 3 };
+enum {
+    HBO_P_MELT_DEGREE_DAY = 0, /* params: degree_day_factor, melting_temperature; forcing temperature */
+    HBO_P_ET_SOCONT = 1,       /* forcing pet */
+    HBO_P_INFILTRATION_SOCONT = 2,
+    HBO_P_RUNOFF_SOCONT = 3,   /* params: beta */
+    HBO_P_OUTFLOW_LINEAR = 4,  /* params: response_factor */
+    HBO_P_OUTFLOW_DIRECT = 5,
+    HBO_P_OUTFLOW_REST = 6,
+    HBO_P_OVERFLOW = 7,
+    HBO_P_PERCOLATION_CONSTANT = 8 /* params: percolation_rate */
+};
+enum {
+    HBO_F_TO_BRICK = 0, HBO_F_TO_BRICK_INSTANT = 1, HBO_F_TO_OUTLET = 2, HBO_F_TO_ATMOSPHERE = 3,
+    HBO_F_SIMPLE = 4, HBO_F_FORCING = 5
+};
+enum { HBO_S_SNOW_RAIN_LINEAR = 0, HBO_S_MULTI_FLUXES = 1, HBO_S_RAIN = 2, HBO_S_SNOW_RAIN_THRESHOLD = 3 };
+enum { HBO_V_PRECIPITATION = 0, HBO_V_TEMPERATURE = 1, HBO_V_PET = 2 };
+enum { HBO_SOLVER_EULER = 0, HBO_SOLVER_HEUN = 1, HBO_SOLVER_RK4 = 2 };
+enum { HBO_REC_CONTAINER = 0, HBO_REC_FLUX = 1, HBO_REC_OUTLET = 2, HBO_REC_FRACTION = 3 };
+
+hbo_model* hbo_create(int n_units, int n_steps, double dt_days, int solver, int spinup_steps);
+void hbo_destroy(hbo_model* m);
+
+int hbo_add_brick(hbo_model* m, int kind, int unit /* -1 = sub-basin */, int needs_solver, int parent_brick);
+void hbo_set_area_fraction(hbo_model* m, int brick, double fraction);
+void hbo_set_parent(hbo_model* m, int brick, int parent_brick);
+void hbo_set_target_brick(hbo_model* m, int process, int target_brick);
+/* capacity: NaN = no capacity. related_snow_container: -1 = none. */
+int hbo_add_container(hbo_model* m, int brick, int content_kind, float capacity, int infinite_storage,
+                      int no_melt_when_snow_cover, double initial_state);
+void hbo_set_related_snowpack(hbo_model* m, int ice_container, int snowpack_brick);
+int hbo_add_process(hbo_model* m, int brick, int type, int container, const float* params, int n_params,
+                    int target_brick, double unit_area, float slope);
+int hbo_add_flux(hbo_model* m, int kind, int is_static, int needs_weighting, double fraction_unit_area,
+                 int target_container /* -1 */, int forcing_var /* -1 */, int unit /* -1 */);
+void hbo_process_add_output(hbo_model* m, int process, int flux);
+void hbo_container_add_input(hbo_model* m, int container, int flux);
+int hbo_add_splitter(hbo_model* m, int unit, int type, const float* params, int n_params);
+void hbo_splitter_add_output(hbo_model* m, int splitter, int flux);
+void hbo_splitter_add_input(hbo_model* m, int splitter, int flux);
+void hbo_add_outlet_flux(hbo_model* m, int flux);
+/* data[T][U], row-major */
+void hbo_set_forcing(hbo_model* m, int var, const double* data);
+int hbo_add_record(hbo_model* m, int kind, int id);
+
+/* Re-applies the land-cover fractions to the weighted fluxes (LandCover::SetAreaFraction). */
+void hbo_finalize_graph(hbo_model* m);
+
+/* Runs the model; outlet[T]; records[n_records][T]. Returns 0, or <0 with hbo_last_error(). */
+int hbo_run(hbo_model* m, double* outlet, double* records);
+const char* hbo_last_error(hbo_model* m);
+/* Number of constraint sweeps that hit the 10-sweep limit (Processor.cpp:208 warning). */
+long hbo_unconverged_sweeps(hbo_model* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -224,6 +224,11 @@ PYBIND11_MODULE(_hydrobricks, m) {
         .def("add_process_parameter", &SettingsModel::AddProcessParameter, "name"_a, "value"_a, "kind"_a = "constant")
         .def("add_process_forcing", &SettingsModel::AddProcessForcing, "name"_a)
         .def("add_brick_parameter", &SettingsModel::AddBrickParameter, "name"_a, "value"_a, "kind"_a = "constant")
+        // Not in the reference module; used by tools/make_goldens.py to rebuild the C++ test fixtures
+        // (core/tests/src/SolverTest.cpp:117-146, helpers.cpp:9-107).
+        .def("add_brick_forcing", &SettingsModel::AddBrickForcing, "name"_a)
+        .def("set_process_parameter_value", &SettingsModel::SetProcessParameterValue, "name"_a, "value"_a,
+             "kind"_a = "constant")
         .def("set_current_brick_computed_directly", &SettingsModel::SetCurrentBrickComputedDirectly)
         .def("set_parameter_value", &SettingsModel::SetParameterValue, "component"_a, "name"_a, "value"_a)
         .def("generate_precipitation_splitters", &SettingsModel::GeneratePrecipitationSplitters, "with_snow"_a = true,

@@ -1,0 +1,179 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref + the reference Python layer).
+
+Run in the build container only:   python tools/make_goldens.py
+Each bundle holds: meta (JSON: structures as exported by SettingsModel.get_structure() with parameter
+values, basin-ordered units, solver, labels), the forcing handed to ModelHydro::CreateTimeSeries
+[T x U], the outlet discharge [T] and every recorded hydro-unit series [T x U] of the reference run.
+The committed bundles are what tests/ compare the oracle restatement and the CUDA engine against on
+machines where /root/reference does not exist.
+"""
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+import ref_cases  # noqa: E402
+import refpy  # noqa: E402
+
+OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
+
+
+def save(name, meta, forcing, outlet, records, extra=None):
+    OUT.mkdir(parents=True, exist_ok=True)
+    arrays = {"meta": np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8), "outlet": np.asarray(outlet)}
+    for k, v in forcing.items():
+        arrays["forcing_" + k] = np.asarray(v, dtype=np.float64)
+    for i, label in enumerate(meta["labels"]):
+        arrays[f"rec_{i}"] = np.asarray(records[label])
+    for k, v in (extra or {}).items():
+        arrays[k] = np.asarray(v)
+    np.savez_compressed(OUT / f"{name}.npz", **arrays)
+    print(f"{name}: T={len(outlet)} labels={len(meta['labels'])} "
+          f"{(OUT / (name + '.npz')).stat().st_size / 1024:.0f} KiB")
+
+
+def run_ref_module(ref, settings, units, forcing, labels_from_model=True):
+    """Drive the reference core directly (no Python layer): init_with_basin, time series, run."""
+    basin = ref.SettingsBasin()
+    for u in units:
+        basin.add_hydro_unit(u["id"], u["area"], u.get("elevation", -9999))
+        if u.get("slope"):
+            basin.add_hydro_unit_property_double("slope", u["slope"][0], u["slope"][1])
+        for name, frac in u["land_covers"]:
+            basin.add_land_cover(name, "", frac)
+    model = ref.ModelHydro()
+    model.init_with_basin(settings, basin)
+    n = len(next(iter(forcing.values())))
+    t = settings.get_timer()
+    import pandas as pd
+
+    mjd0 = (pd.Timestamp(t["start"]) - pd.Timestamp("1858-11-17")).days
+    time = np.arange(n, dtype=np.float64) + mjd0
+    ids = np.array([u["id"] for u in units], dtype=np.int32)
+    for k, v in forcing.items():
+        assert model.create_time_series(k, time, ids, np.asarray(v, dtype=np.float64))
+    assert model.attach_time_series_to_hydro_units()
+    model.run()
+    rec = {label: model.get_hydro_unit_values(label) for label in model.get_recorded_hydro_unit_labels()}
+    return model.get_outlet_discharge(), rec
+
+
+def kat_linear_storage(ref, solver):
+    """core/tests/src/SolverTest.cpp:117-244 (fixture SolverLinearStorage)."""
+    s = ref.SettingsModel()
+    s.set_solver(solver)
+    s.set_timer("2020-01-01", "2020-01-20", 1, "day")
+    s.add_hydro_unit_brick("storage", "storage")
+    s.add_brick_forcing("precipitation")
+    s.add_brick_logging("water_content")
+    s.add_brick_process("outflow", "outflow:linear")
+    s.set_process_parameter_value("response_factor", 0.3)
+    s.add_process_logging("output")
+    s.add_process_output("outlet")
+    s.add_logging_to("outlet")
+    units = [{"id": 1, "area": 100.0, "elevation": -9999, "slope": None, "land_covers": []}]
+    precip = np.array([0.0, 10.0, 10.0, 10.0] + [0.0] * 16).reshape(20, 1)
+    forcing = {"precipitation": precip}
+    q, rec = run_ref_module(ref, s, units, forcing)
+    meta = {"structures": s.get_structure(), "units": units, "solver": solver, "labels": list(rec),
+            "source": "core/tests/src/SolverTest.cpp:117-244"}
+    return meta, forcing, q, rec
+
+
+def kat_socont_quick(ref):
+    """core/tests/src/ModelSocontTest.cpp:536-626 (QuickDischargeIsCorrect) with the structure of
+    core/tests/src/helpers.cpp:9-107 (GenerateStructureSocont, 1 soil store, socont_runoff)."""
+    s = ref.SettingsModel()
+    s.log_all(True)
+    s.set_solver("runge_kutta")
+    s.set_timer("2020-01-01", "2020-01-10", 1, "day")
+    s.generate_precipitation_splitters(True)
+    s.add_land_cover_brick("ground", "generic_land_cover")
+    s.generate_snowpacks("melt:degree_day")
+    s.add_sub_basin_brick("glacier_area_rain_snowmelt_storage", "storage")
+    s.add_brick_process("outflow", "outflow:linear", "outlet")
+    s.add_sub_basin_brick("glacier_area_icemelt_storage", "storage")
+    s.add_brick_process("outflow", "outflow:linear", "outlet")
+    s.select_hydro_unit_brick("ground")
+    s.add_brick_process("infiltration", "infiltration:socont", "slow_reservoir")
+    s.add_brick_process("runoff", "outflow:rest", "surface_runoff")
+    s.set_process_outputs_as_static()
+    s.add_hydro_unit_brick("slow_reservoir", "storage")
+    s.add_brick_parameter("capacity", 200.0)
+    s.add_brick_process("et", "et:socont")
+    s.add_brick_process("outflow", "outflow:linear", "outlet")
+    s.add_brick_process("overflow", "overflow", "outlet")
+    s.add_hydro_unit_brick("surface_runoff", "storage")
+    s.add_brick_process("runoff", "runoff:socont", "outlet")
+    s.add_logging_to("outlet")
+    s.set_parameter_value("surface_runoff", "beta", 301)
+    s.set_parameter_value("slow_reservoir", "capacity", 0)
+    units = [{"id": 1, "area": 38.9 * 1000000, "elevation": -9999, "slope": (0.3, "m/m"),
+              "land_covers": [("ground", 1.0)]}]
+    forcing = {
+        "precipitation": np.array([0.0, 13.8, 59.3, 34.2, 13.7, 26.1, 9.8, 0.0, 0.0, 0.0]).reshape(10, 1),
+        "temperature": np.full((10, 1), 5.0),
+        "pet": np.zeros((10, 1)),
+    }
+    q, rec = run_ref_module(ref, s, units, forcing)
+    meta = {"structures": s.get_structure(), "units": units, "solver": "rk4", "labels": list(rec),
+            "source": "core/tests/src/ModelSocontTest.cpp:536-626"}
+    return meta, forcing, q, rec
+
+
+def main():
+    hb = refpy.load_reference_python("ref")
+    ref = sys.modules["hydrobricks._hydrobricks"]
+
+    for solver in ["euler_explicit", "heun_explicit", "runge_kutta"]:
+        save(f"kat_linear_storage_{solver}", *kat_linear_storage(ref, solver))
+    save("kat_socont_quick_rk4", *kat_socont_quick(ref))
+
+    def bundle(name, model, hu, forcing, n_years_note):
+        structures, units, fdata, q, rec = ref_cases.collect(model, hu, forcing)
+        meta = {"structures": structures, "units": units, "solver": model.solver, "labels": list(rec),
+                "source": n_years_note}
+        save(name, meta, fdata, q, rec)
+
+    # RK4 (the headline solver) gets every structure variant; Heun/Euler a representative subset, to keep
+    # the committed fixtures small.
+    for solver in ["rk4", "heun_explicit", "euler_explicit"]:
+        full = solver == "rk4"
+        for nb in (1, 2) if full else (1,):
+            m, hu, f, _ = ref_cases.sitter_socont(hb, solver=solver, soil_storage_nb=nb, end_date="1981-12-31")
+            bundle(f"socont_sitter_{solver}_{nb}store", m, hu, f,
+                   "reference Python layer, ch_sitter_appenzell 35 bands, 1981, linear_storage, record_all")
+        variants = [("glacier_1store", dict(soil_storage_nb=1)),
+                    ("glacier_2store", dict(soil_storage_nb=2)),
+                    ("noglacier_1store", dict(soil_storage_nb=1, with_glacier=False)),
+                    ("glacier_finite_1store", dict(soil_storage_nb=1, infinite_storage=False)),
+                    ("glacier_linear_1store", dict(soil_storage_nb=1, surface_runoff="linear_storage"))]
+        for tag, kw in variants if full else [variants[1], variants[3]]:
+            m, hu, f, _ = ref_cases.gsm_socont(hb, solver=solver, end_date="1982-12-31", n_units=10, **kw)
+            bundle(f"gsm_socont_{solver}_{tag}", m, hu, f,
+                   "reference Python layer, 10 synthetic bands with slope/glacier, Rhone-Gletsch meteo 1981-1982")
+
+    # C1: full bundled catchment, 1981-2020, outlet + station series only (fused spatialisation input).
+    m, hu, f, params = ref_cases.sitter_socont(hb, solver="rk4", soil_storage_nb=1, end_date="2020-12-31")
+    structures, units, fdata, q, rec = ref_cases.collect(m, hu, f)
+    station = {str(n): np.asarray(d) for n, d in zip(f.data1D.data_name, f.data1D.data)}
+    meta = {"structures": structures, "units": units, "solver": "rk4", "labels": [],
+            "spatialisation": {"temperature": {"method": "additive_elevation_gradient", "ref_elevation": 1250,
+                                               "gradient": -0.6},
+                               "precipitation": {"method": "multiplicative_elevation_gradient",
+                                                 "ref_elevation": 1250, "gradient": 0.05,
+                                                 "correction_factor": 1},
+                               "pet": {"method": "constant"}},
+            "source": "reference Python layer, ch_sitter_appenzell 35 bands, 1981-2020 (BASELINE config C1)"}
+    # spot-check columns of the spatialised forcing so the fused path can be verified without 12 MB
+    extra = {"station_" + k: v for k, v in station.items()}
+    for k, v in fdata.items():
+        extra["spatial_first_" + k] = v[:, 0]
+        extra["spatial_last_" + k] = v[:, -1]
+    save("c1_sitter_rk4_full", meta, {}, q, {}, extra=extra)
+
+
+if __name__ == "__main__":
+    main()
