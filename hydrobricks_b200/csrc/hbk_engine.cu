@@ -1,0 +1,1018 @@
+// hbk_engine.cu — B200 (sm_100a) batched simulation engine behind the C-ABI of include/hbk.h.
+//
+// Replaces ModelHydro::Run() (reference core/src/base/ModelHydro.cpp:100-133) for Socont-family
+// structures: ONE launch integrates every (parameter set, hydro unit) pair over a whole time segment.
+//
+//  * one thread per (parameter set p, hydro unit u); storages live in registers, the time loop is inside
+//    the kernel (hbk_device.cuh holds the per-step arithmetic);
+//  * a block covers PB parameter sets x UB units. PB = 32 puts the parameter axis on the lanes (calibration
+//    ensembles: every lane of a warp reads the same forcing value -> shared-memory broadcast);
+//    PB = 1 puts the unit axis on the lanes (large distributed basins);
+//  * forcing is staged per block in chunks of TC steps by TMA bulk copies (cp.async.bulk + mbarrier),
+//    double buffered: either the block's tile of pre-spatialised per-unit series, or the station series
+//    with the elevation lapse rates applied in registers (fused spatialisation, forcing.py:1061-1113);
+//  * the per-step outlet contributions (and the glacier deposits into the two sub-basin stores) are kept
+//    in shared memory for a chunk and reduced over the block's units in a fixed order, then written once;
+//  * the two sub-basin linear stores (glacier_area_*_storage) only depend on the per-step deposit sums, so
+//    a second tiny kernel integrates them per parameter set after the unit pass;
+//  * state is spilled to a struct-of-arrays in HBM at segment boundaries, which is where dated actions
+//    (glacier evolution, land-cover change) get applied by their own kernels.
+//
+// There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/hbk.h"
+#include "hbk_device.cuh"
+
+namespace hbk {
+
+constexpr int kBlock = 256;
+constexpr int kNH = 4;  // per-unit constants: area fraction of basin, area [m2], pow(slope,0.5), elevation
+
+struct KArgs {
+    int P, U, tBegin, tEnd, PB, UB, TC, nUTiles;
+    Flags flags;
+    double dt;
+    const float* params;  // [HBK_N_PARAMS][ldp]
+    int ldp;
+    const double* hru;  // [kNH][ldu]
+    const int* hruFlags;
+    int ldu;
+    const double* frac;  // [2][fracLd]: ground, glacier
+    long long fracLd;
+    int fracPerSet;
+    int forcingMode;            // 0: tiled per-unit series, 1: station series + fused spatialisation
+    const double* forcing[3];   // mode 0: [nUTiles][tld][UB]; mode 1: [tld]
+    long long tld;
+    const double* gradT;  // per set or nullptr
+    const double* gradP;
+    const double* corrP;
+    double gradTs, gradPs, corrPs, zrefT, zrefP;
+    double* state;  // [HBK_N_STATES][lds]
+    long long lds;
+    double* outQ;  // [nUTiles][P][ldt]
+    double* outD1;
+    double* outD2;
+    long long ldt;
+    int writeOutputs;
+    unsigned long long recordMask;
+    double* rec;  // [popcount][P][T][U]
+    int T;
+    int* err;
+    unsigned long long* unconverged;
+};
+
+// ---- TMA bulk copy + mbarrier (PTX) ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smemAddr(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy completing on an mbarrier (SASS: UBLKCP). 16-byte aligned, size % 16 == 0.
+__device__ __forceinline__ void tmaLoad1D(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smemAddr(dst)),
+                 "l"(src), "r"(bytes), "r"(smemAddr(bar))
+                 : "memory");
+}
+
+// ---- main kernel ------------------------------------------------------------------------------------
+template <int SOLVER, int NSOIL, bool GLACIER>
+__global__ void __launch_bounds__(kBlock) hbkRunUnits(const KArgs a) {
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    constexpr int NQ = GLACIER ? 3 : 1;
+    const int tid = threadIdx.x;
+    const int ut = blockIdx.x % a.nUTiles;
+    const int pg = blockIdx.x / a.nUTiles;
+    const int pl = tid % a.PB;
+    const int ul = tid / a.PB;
+    const int p = pg * a.PB + pl;
+    const int u = ut * a.UB + ul;
+    const bool valid = (p < a.P) && (u < a.U);
+
+    // shared memory carve-up
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smemRaw);  // 2 mbarriers
+    const int fRow = (a.forcingMode == 0) ? a.TC * a.UB : (a.TC + 2);  // doubles per variable per stage
+    double* fbuf = reinterpret_cast<double*>(smemRaw + 128);             // [2][3][fRow]
+    double* qbuf = fbuf + 2 * 3 * fRow;                                  // [NQ][TC][kBlock]
+
+    // per-thread constants
+    Par par;
+    Hru h;
+    double fa = 0, area = 1, elev = 0, fG = 1, fGl = 0;
+    bool glacierVariant = false;
+    double cT = 0, mP = 1, corr = 1;
+    if (valid) {
+        const float* pp = a.params + p;
+        const float t0f = pp[HBK_P_TRANSITION_START * a.ldp], t1f = pp[HBK_P_TRANSITION_END * a.ldp];
+        par.t0 = t0f;
+        par.t1 = t1f;
+        par.span = (double)(t1f - t0f);
+        par.rcf = pp[HBK_P_RAIN_CORRECTION * a.ldp];
+        par.scf = pp[HBK_P_SNOW_CORRECTION * a.ldp];
+        par.ddfG = pp[HBK_P_GROUND_SNOW_DDF * a.ldp];
+        par.tmG = pp[HBK_P_GROUND_SNOW_TMELT * a.ldp];
+        par.ddfGl = pp[HBK_P_GLACIER_SNOW_DDF * a.ldp];
+        par.tmGl = pp[HBK_P_GLACIER_SNOW_TMELT * a.ldp];
+        par.ddfIce = pp[HBK_P_ICE_DDF * a.ldp];
+        par.tmIce = pp[HBK_P_ICE_TMELT * a.ldp];
+        par.A = pp[HBK_P_CAPACITY * a.ldp];
+        par.k1 = pp[HBK_P_K_SLOW_1 * a.ldp];
+        par.perc = pp[HBK_P_PERCOLATION * a.ldp];
+        par.k2 = pp[HBK_P_K_SLOW_2 * a.ldp];
+        fa = a.hru[0 * a.ldu + u];
+        area = a.hru[1 * a.ldu + u];
+        const double slopeTerm = a.hru[2 * a.ldu + u];
+        elev = a.hru[3 * a.ldu + u];
+        const double quick = pp[HBK_P_QUICK * a.ldp];
+        par.quick = (a.flags.quickKind == 0) ? quick * slopeTerm : quick;
+        glacierVariant = GLACIER && (a.hruFlags[u] & 1);
+        const long long fi = a.fracPerSet ? ((long long)p * a.U + u) : u;
+        fG = a.frac[fi];
+        fGl = a.frac[a.fracLd + fi];
+        const long long si = (long long)p * a.U + u;
+        h.snowG = a.state[HBK_S_GROUND_SNOW * a.lds + si];
+        h.snowGl = a.state[HBK_S_GLACIER_SNOW * a.lds + si];
+        h.wG = a.state[HBK_S_GROUND_WATER * a.lds + si];
+        h.wGl = a.state[HBK_S_GLACIER_WATER * a.lds + si];
+        h.ice = a.state[HBK_S_ICE * a.lds + si];
+        h.slow = a.state[HBK_S_SLOW * a.lds + si];
+        h.slow2 = a.state[HBK_S_SLOW2 * a.lds + si];
+        h.quick = a.state[HBK_S_QUICK * a.lds + si];
+        h.amtInfil = a.state[HBK_S_AMT_INFILTRATION * a.lds + si];
+        h.amtRest = a.state[HBK_S_AMT_REST * a.lds + si];
+        h.amtMeltG = a.state[HBK_S_AMT_MELT_GROUND * a.lds + si];
+        h.amtMeltGl = a.state[HBK_S_AMT_MELT_GLACIER * a.lds + si];
+        h.amtDep1 = a.state[HBK_S_AMT_DEPOSIT_RAIN_SNOWMELT * a.lds + si];
+        h.amtDep2 = a.state[HBK_S_AMT_DEPOSIT_ICEMELT * a.lds + si];
+        if (a.forcingMode == 1) {
+            // forcing.py:1073-1075 / 1104-1106: g*(z - zref) -> /100 -> (1 + ...) -> x * ...
+            const double gT = a.gradT ? a.gradT[p] : a.gradTs;
+            const double gP = a.gradP ? a.gradP[p] : a.gradPs;
+            corr = a.corrP ? a.corrP[p] : a.corrPs;
+            cT = gT * (elev - a.zrefT) / 100;
+            mP = 1 + gP * (elev - a.zrefP) / 100;
+        }
+    }
+
+    const int nSteps = a.tEnd - a.tBegin;
+    const int nChunks = (nSteps + a.TC - 1) / a.TC;
+
+    auto issueLoad = [&](int c) {
+        const int stage = c & 1;
+        const int t0 = a.tBegin + c * a.TC;
+        const int n = min(a.TC, a.tEnd - t0);
+        double* dst = fbuf + (size_t)stage * 3 * fRow;
+        if (a.forcingMode == 0) {
+            const uint32_t bytes = (uint32_t)(n * a.UB * sizeof(double));
+            mbarExpectTx(&bars[stage], 3 * bytes);
+            for (int v = 0; v < 3; ++v) {
+                const double* src = a.forcing[v] + ((size_t)ut * a.tld + t0) * a.UB;
+                tmaLoad1D(dst + (size_t)v * fRow, src, bytes, &bars[stage]);
+            }
+        } else {
+            const int t0a = t0 & ~1;  // 16-byte aligned source
+            const uint32_t bytes = (uint32_t)((a.TC + 2) * sizeof(double));
+            mbarExpectTx(&bars[stage], 3 * bytes);
+            for (int v = 0; v < 3; ++v) tmaLoad1D(dst + (size_t)v * fRow, a.forcing[v] + t0a, bytes, &bars[stage]);
+        }
+    };
+
+    if (tid == 0) {
+        mbarInit(&bars[0], 1);
+        mbarInit(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0 && nChunks > 0) issueLoad(0);
+
+    int err = 0;
+    int unconverged = 0;
+    const int nRec = __popcll(a.recordMask);
+
+    for (int c = 0; c < nChunks; ++c) {
+        const int stage = c & 1;
+        const int t0 = a.tBegin + c * a.TC;
+        const int n = min(a.TC, a.tEnd - t0);
+        if (tid == 0 && c + 1 < nChunks) issueLoad(c + 1);
+        mbarWait(&bars[stage], (c >> 1) & 1);
+        const double* fs = fbuf + (size_t)stage * 3 * fRow;
+        const int off = (a.forcingMode == 1) ? (t0 & 1) : 0;
+
+        for (int tc = 0; tc < n; ++tc) {
+            StepOut o;
+            o.q = 0.0;
+            o.dep1 = 0.0;
+            o.dep2 = 0.0;
+            if (valid) {
+                double precip, temp, pet;
+                if (a.forcingMode == 0) {
+                    precip = fs[0 * fRow + tc * a.UB + ul];
+                    temp = fs[1 * fRow + tc * a.UB + ul];
+                    pet = fs[2 * fRow + tc * a.UB + ul];
+                } else {
+                    const double xp = fs[0 * fRow + tc + off];
+                    const double xt = fs[1 * fRow + tc + off];
+                    const double xe = fs[2 * fRow + tc + off];
+                    temp = xt + cT;
+                    precip = (xp * corr) * mP;
+                    precip = (precip < 0.0) ? 0.0 : precip;
+                    pet = (xe < 0.0) ? 0.0 : xe;
+                }
+                directPhase<GLACIER>(h, par, precip, temp, a.dt, fa, fG, fGl, glacierVariant, a.flags, o, err);
+                solveUnit<SOLVER, NSOIL>(h, par, pet, area, fa, a.dt, a.flags, o, err, unconverged);
+
+                if (nRec && a.writeOutputs) {
+                    // Logger::Record (Logger.cpp:93-120): contents after Finalize and flux amounts
+                    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+                    const bool gv = glacierVariant;
+                    double* base = a.rec + ((size_t)p * a.T + (t0 + tc)) * a.U + u;
+                    const size_t stride = (size_t)a.P * a.T * a.U;
+                    int k = 0;
+#define HBK_REC(slot, value)                                   \
+    if (a.recordMask & (1ull << (slot))) {                     \
+        base[(size_t)k * stride] = (value);                    \
+        ++k;                                                   \
+    }
+                    HBK_REC(HBK_R_GROUND_WATER, h.wG)
+                    HBK_REC(HBK_R_GROUND_INFILTRATION, h.amtInfil)
+                    HBK_REC(HBK_R_GROUND_RUNOFF, h.amtRest)
+                    HBK_REC(HBK_R_GLACIER_WATER, gv ? h.wGl : nan)
+                    HBK_REC(HBK_R_GLACIER_ICE, gv ? h.ice : nan)
+                    HBK_REC(HBK_R_GLACIER_OUTFLOW, gv ? h.amtDep1 : nan)
+                    HBK_REC(HBK_R_GLACIER_MELT, gv ? h.amtDep2 : nan)
+                    HBK_REC(HBK_R_GROUND_SNOWPACK_WATER, 0.0)
+                    HBK_REC(HBK_R_GROUND_SNOWPACK_SNOW, h.snowG)
+                    HBK_REC(HBK_R_GROUND_SNOWPACK_MELT, h.amtMeltG)
+                    HBK_REC(HBK_R_GLACIER_SNOWPACK_WATER, gv ? 0.0 : nan)
+                    HBK_REC(HBK_R_GLACIER_SNOWPACK_SNOW, gv ? h.snowGl : nan)
+                    HBK_REC(HBK_R_GLACIER_SNOWPACK_MELT, gv ? h.amtMeltGl : nan)
+                    HBK_REC(HBK_R_SLOW_WATER, h.slow)
+                    HBK_REC(HBK_R_SLOW_ET, o.amtEt)
+                    HBK_REC(HBK_R_SLOW_OUTFLOW, o.amtOut)
+                    HBK_REC(HBK_R_SLOW_OVERFLOW, o.amtOvf)
+                    HBK_REC(HBK_R_SLOW_PERCOLATION, o.amtPerc)
+                    HBK_REC(HBK_R_SLOW2_WATER, h.slow2)
+                    HBK_REC(HBK_R_SLOW2_OUTFLOW, o.amtOut2)
+                    HBK_REC(HBK_R_QUICK_WATER, h.quick)
+                    HBK_REC(HBK_R_QUICK_RUNOFF, o.amtQ)
+#undef HBK_REC
+                }
+            }
+            qbuf[(size_t)tc * kBlock + tid] = o.q;
+            if (GLACIER) {
+                qbuf[(size_t)(a.TC + tc) * kBlock + tid] = o.dep1;
+                qbuf[(size_t)(2 * a.TC + tc) * kBlock + tid] = o.dep2;
+            }
+        }
+        __syncthreads();
+        // SubBasin::ComputeOutletDischarge (SubBasin.cpp:322-329): sum the block's units in unit order.
+        if (a.writeOutputs || GLACIER) {  // the deposits feed the sub-basin stores even during spin-up
+            for (int idx = tid; idx < NQ * n * a.PB; idx += kBlock) {
+                const int qi = idx / (n * a.PB);
+                if (qi == 0 && !a.writeOutputs) continue;
+                const int rem = idx - qi * n * a.PB;
+                const int tc = rem / a.PB;
+                const int lp = rem - tc * a.PB;
+                const int gp = pg * a.PB + lp;
+                if (gp >= a.P) continue;
+                const double* src = qbuf + ((size_t)qi * a.TC + tc) * kBlock + lp;
+                double s = 0.0;
+                for (int k = 0; k < a.UB; ++k) s += src[(size_t)k * a.PB];
+                double* dst = (qi == 0) ? a.outQ : (qi == 1 ? a.outD1 : a.outD2);
+                dst[((size_t)ut * a.P + gp) * a.ldt + (t0 + tc)] = s;
+            }
+        }
+        __syncthreads();
+    }
+
+    if (valid) {
+        const long long si = (long long)p * a.U + u;
+        a.state[HBK_S_GROUND_SNOW * a.lds + si] = h.snowG;
+        a.state[HBK_S_GLACIER_SNOW * a.lds + si] = h.snowGl;
+        a.state[HBK_S_GROUND_WATER * a.lds + si] = h.wG;
+        a.state[HBK_S_GLACIER_WATER * a.lds + si] = h.wGl;
+        a.state[HBK_S_ICE * a.lds + si] = h.ice;
+        a.state[HBK_S_SLOW * a.lds + si] = h.slow;
+        a.state[HBK_S_SLOW2 * a.lds + si] = h.slow2;
+        a.state[HBK_S_QUICK * a.lds + si] = h.quick;
+        a.state[HBK_S_AMT_INFILTRATION * a.lds + si] = h.amtInfil;
+        a.state[HBK_S_AMT_REST * a.lds + si] = h.amtRest;
+        a.state[HBK_S_AMT_MELT_GROUND * a.lds + si] = h.amtMeltG;
+        a.state[HBK_S_AMT_MELT_GLACIER * a.lds + si] = h.amtMeltGl;
+        a.state[HBK_S_AMT_DEPOSIT_RAIN_SNOWMELT * a.lds + si] = h.amtDep1;
+        a.state[HBK_S_AMT_DEPOSIT_ICEMELT * a.lds + si] = h.amtDep2;
+    }
+    if (err) atomicOr(a.err, err);
+    if (unconverged) atomicAdd(a.unconverged, (unsigned long long)unconverged);
+}
+
+// Sum the unit-tile partials in tile order: out[p][t] = sum_tiles part[tile][p][t]  (only when nUTiles > 1).
+__global__ void hbkReduceTiles(const double* __restrict__ part, double* __restrict__ out, int nTiles, int P,
+                               long long ldt, int tBegin, int tEnd) {
+    const long long n = (long long)P * (tEnd - tBegin);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(i / (tEnd - tBegin));
+        const int t = tBegin + (int)(i - (long long)p * (tEnd - tBegin));
+        double s = 0.0;
+        for (int k = 0; k < nTiles; ++k) s += part[((size_t)k * P + p) * ldt + t];
+        out[(size_t)p * ldt + t] = s;
+    }
+}
+
+// The two sub-basin linear stores, one thread per parameter set, sequential in time
+// (modules/glacier.py:108-131; solved with the same solver as the units, Processor.cpp:94-111).
+template <int SOLVER>
+__global__ void hbkBasinStores(const float* params, int ldp, int P, long long ldt, int tBegin, int tEnd, double dt,
+                               const double* d1, const double* d2, const double* stale, double* outlet,
+                               double* basinState, int writeOutputs, int* errFlags, unsigned long long* unconv) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const double kSnow = params[HBK_P_K_SNOW * ldp + p];
+    const double kIce = params[HBK_P_K_ICE * ldp + p];
+    double c1 = basinState[2 * p], c2 = basinState[2 * p + 1];
+    const double st1 = stale ? stale[2 * p] : 0.0, st2 = stale ? stale[2 * p + 1] : 0.0;
+    int err = 0, unc = 0;
+    for (int t = tBegin; t < tEnd; ++t) {
+        const double dep1 = d1[(size_t)p * ldt + t], dep2 = d2[(size_t)p * ldt + t];
+        const double o1 = basinStoreStep<SOLVER>(c1, kSnow, dep1, dep1 + st1, dt, err, unc);
+        const double o2 = basinStoreStep<SOLVER>(c2, kIce, dep2, dep2 + st2, dt, err, unc);
+        if (writeOutputs) outlet[(size_t)p * ldt + t] = (o1 + o2) + outlet[(size_t)p * ldt + t];
+    }
+    basinState[2 * p] = c1;
+    basinState[2 * p + 1] = c2;
+    if (err) atomicOr(errFlags, err);
+    if (unc) atomicAdd(unconv, (unsigned long long)unc);
+}
+
+// [T][U] (API layout of ModelHydro::CreateTimeSeries) -> [tile][tld][UB] so that a block's chunk is contiguous.
+__global__ void hbkTileForcing(const double* __restrict__ src, double* __restrict__ dst, int T, int U, int UB,
+                               long long tld, int nTiles) {
+    const long long n = (long long)nTiles * T * UB;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int ul = (int)(i % UB);
+        const long long r = i / UB;
+        const int t = (int)(r % T);
+        const int tile = (int)(r / T);
+        const int u = tile * UB + ul;
+        dst[((size_t)tile * tld + t) * UB + ul] = (u < U) ? src[(size_t)t * U + u] : 0.0;
+    }
+}
+
+__global__ void hbkBroadcastState(double* dst, const double* perUnit, double value, int P, int U) {
+    const long long n = (long long)P * U;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = perUnit ? perUnit[i % U] : value;
+}
+
+}  // namespace hbk
+
+// =====================================================================================================
+// Host side
+// =====================================================================================================
+using namespace hbk;
+
+struct hbk_engine {
+    hbk_structure st{};
+    int U = 0, T = 0, P = 0, device = 0;
+    int PB = 32, UB = 8, TC = 16, nUTiles = 1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string error;
+    // device buffers
+    float* dParams = nullptr;
+    int ldp = 0;
+    double* dHru = nullptr;
+    int* dHruFlags = nullptr;
+    int ldu = 0;
+    double* dFrac = nullptr;      // [2][U] (per unit) or [2][P*U]
+    double* dFracInit = nullptr;  // initial fractions [2][U]
+    int fracPerSet = 0;
+    double* dForcingRaw[3] = {nullptr, nullptr, nullptr};    // [T][U]
+    double* dForcingTiled[3] = {nullptr, nullptr, nullptr};  // [nUTiles][tld][UB]
+    double* dStation[3] = {nullptr, nullptr, nullptr};       // [tld]
+    bool haveRaw[3] = {false, false, false}, haveStation[3] = {false, false, false};
+    int tiledUB = 0;
+    double* dGradT = nullptr;
+    double* dGradP = nullptr;
+    double* dCorrP = nullptr;
+    double gradTs = 0, gradPs = 0, corrPs = 1, zrefT = 0, zrefP = 0;
+    long long tld = 0;
+    double* dState = nullptr;      // [HBK_N_STATES][P*U]
+    double* dInitUnit = nullptr;   // [HBK_N_STATES][U] initial state per unit (broadcast over sets)
+    bool initPerSet = false;
+    double* dInitFull = nullptr;   // [HBK_N_STATES][P*U] after save_as_initial_state
+    double* dBasinState = nullptr; // [P][2]
+    double* dBasinInit = nullptr;
+    double* dOutlet = nullptr;     // [P][ldt]
+    double* dPartQ = nullptr;      // [nUTiles][P][ldt] (nUTiles > 1)
+    double* dD1 = nullptr;         // [P][ldt]
+    double* dD2 = nullptr;
+    double* dPartD1 = nullptr;
+    double* dPartD2 = nullptr;
+    long long ldt = 0;
+    uint64_t recordMask = 0;
+    double* dRec = nullptr;
+    size_t recBytes = 0;
+    int* dErr = nullptr;
+    unsigned long long* dUnconv = nullptr;
+    int spinupSteps = 0;
+    bool unitsSet = false, ran = false;
+    size_t allocP = 0;
+    // stats
+    double lastMs = 0;
+    int lastLaunches = 0;
+    long long lastUnconverged = 0;
+    std::vector<double> hFracG, hFracGl;
+    std::vector<int> hGlacierVariant;
+};
+
+namespace {
+
+int fail(hbk_engine* e, int code, const std::string& msg) {
+    if (e) e->error = msg;
+    return code;
+}
+
+#define HBK_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t _err = (call);                                                                  \
+        if (_err != cudaSuccess)                                                                    \
+            return fail(e, HBK_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(_err));      \
+    } while (0)
+
+template <class T>
+void freeDev(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+// Thread-block shape: parameter axis on the lanes when there are enough sets, else the unit axis.
+void chooseShape(hbk_engine* e) {
+    int pb = 1;
+    while (pb < 32 && pb < e->P) pb *= 2;
+    e->PB = pb;
+    e->UB = kBlock / pb;
+    e->nUTiles = (e->U + e->UB - 1) / e->UB;
+    const int nq = e->st.has_glacier ? 3 : 1;
+    // chunk length: keep forcing stages + reduction buffer under ~100 KB so two blocks fit on an SM
+    int tc = 16;
+    for (;;) {
+        const size_t fRow = (e->haveRaw[0] ? (size_t)tc * e->UB : (size_t)tc + 2);
+        const size_t bytes = 128 + 2 * 3 * fRow * 8 + (size_t)nq * tc * kBlock * 8;
+        if (bytes <= 100 * 1024 || tc == 2) break;
+        tc /= 2;
+    }
+    e->TC = tc;
+}
+
+size_t smemBytes(const hbk_engine* e, bool tiled) {
+    const int nq = e->st.has_glacier ? 3 : 1;
+    const size_t fRow = tiled ? (size_t)e->TC * e->UB : (size_t)e->TC + 2;
+    return 128 + 2 * 3 * fRow * 8 + (size_t)nq * e->TC * kBlock * 8;
+}
+
+using KernelFn = void (*)(const KArgs);
+
+template <int SOLVER, int NSOIL>
+KernelFn pickGlacier(bool glacier) {
+    return glacier ? (KernelFn)hbkRunUnits<SOLVER, NSOIL, true> : (KernelFn)hbkRunUnits<SOLVER, NSOIL, false>;
+}
+template <int SOLVER>
+KernelFn pickSoil(int nSoil, bool glacier) {
+    return nSoil == 2 ? pickGlacier<SOLVER, 2>(glacier) : pickGlacier<SOLVER, 1>(glacier);
+}
+// "Device functions selected from a per-structure process table": the table (hbk_structure) picks the
+// template instantiation.
+KernelFn pickKernel(const hbk_structure& st) {
+    switch (st.solver) {
+        case HBK_SOLVER_EULER: return pickSoil<0>(st.n_soil_stores, st.has_glacier != 0);
+        case HBK_SOLVER_HEUN: return pickSoil<1>(st.n_soil_stores, st.has_glacier != 0);
+        default: return pickSoil<2>(st.n_soil_stores, st.has_glacier != 0);
+    }
+}
+
+int ensureSetBuffers(hbk_engine* e, int P) {
+    if ((size_t)P == e->allocP) return HBK_OK;
+    freeDev(e->dParams);
+    freeDev(e->dState);
+    freeDev(e->dInitFull);
+    freeDev(e->dBasinState);
+    freeDev(e->dBasinInit);
+    freeDev(e->dOutlet);
+    freeDev(e->dPartQ);
+    freeDev(e->dD1);
+    freeDev(e->dD2);
+    freeDev(e->dPartD1);
+    freeDev(e->dPartD2);
+    freeDev(e->dRec);
+    freeDev(e->dGradT);
+    freeDev(e->dGradP);
+    freeDev(e->dCorrP);
+    e->recBytes = 0;
+    e->initPerSet = false;
+    e->P = P;
+    e->ldp = (P + 31) / 32 * 32;
+    e->ldt = (e->T + 15) / 16 * 16;
+    HBK_CUDA(cudaMalloc(&e->dParams, sizeof(float) * HBK_N_PARAMS * e->ldp));
+    HBK_CUDA(cudaMalloc(&e->dState, sizeof(double) * HBK_N_STATES * (size_t)P * e->U));
+    HBK_CUDA(cudaMalloc(&e->dBasinState, sizeof(double) * 2 * P));
+    HBK_CUDA(cudaMalloc(&e->dBasinInit, sizeof(double) * 2 * P));
+    HBK_CUDA(cudaMemsetAsync(e->dBasinInit, 0, sizeof(double) * 2 * P, e->stream));
+    HBK_CUDA(cudaMalloc(&e->dOutlet, sizeof(double) * (size_t)P * e->ldt));
+    e->allocP = P;
+    return HBK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hbk_engine_create(const hbk_structure* st, int32_t n_units, int32_t n_steps, int32_t device, hbk_engine** out) {
+    if (!st || !out || n_units <= 0 || n_steps <= 0) return HBK_E_ARG;
+    *out = nullptr;
+    auto* e = new hbk_engine();
+    e->st = *st;
+    e->U = n_units;
+    e->T = n_steps;
+    e->device = device;
+    auto bail = [&](int code, const std::string& msg) {
+        std::fprintf(stderr, "hbk_engine_create: %s\n", msg.c_str());
+        delete e;
+        return code;
+    };
+    if (st->solver < 0 || st->solver > 2) return bail(HBK_E_ARG, "unknown solver");
+    if (st->n_soil_stores != 1 && st->n_soil_stores != 2) return bail(HBK_E_UNSUPPORTED, "n_soil_stores must be 1 or 2");
+    if (!(st->time_step_days > 0)) return bail(HBK_E_ARG, "time_step_days must be > 0");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0)
+        return bail(HBK_E_CUDA, "no CUDA device available (this engine has no CPU fallback)");
+    if (device < 0 || device >= count) return bail(HBK_E_ARG, "bad device index");
+    if (cudaSetDevice(device) != cudaSuccess) return bail(HBK_E_CUDA, "cudaSetDevice failed");
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(HBK_E_CUDA, "cudaStreamCreate failed");
+    cudaEventCreate(&e->ev0);
+    cudaEventCreate(&e->ev1);
+    e->ldu = (n_units + 31) / 32 * 32;
+    e->tld = (n_steps + 15) / 16 * 16 + 32;
+    bool ok = cudaMalloc(&e->dHru, sizeof(double) * kNH * e->ldu) == cudaSuccess &&
+              cudaMalloc(&e->dHruFlags, sizeof(int) * e->ldu) == cudaSuccess &&
+              cudaMalloc(&e->dFrac, sizeof(double) * 2 * n_units) == cudaSuccess &&
+              cudaMalloc(&e->dFracInit, sizeof(double) * 2 * n_units) == cudaSuccess &&
+              cudaMalloc(&e->dInitUnit, sizeof(double) * HBK_N_STATES * n_units) == cudaSuccess &&
+              cudaMalloc(&e->dErr, sizeof(int)) == cudaSuccess &&
+              cudaMalloc(&e->dUnconv, sizeof(unsigned long long)) == cudaSuccess;
+    if (!ok) return bail(HBK_E_CUDA, "device allocation failed");
+    cudaMemset(e->dInitUnit, 0, sizeof(double) * HBK_N_STATES * n_units);
+    *out = e;
+    return HBK_OK;
+}
+
+void hbk_engine_destroy(hbk_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    freeDev(e->dParams);
+    freeDev(e->dHru);
+    freeDev(e->dHruFlags);
+    freeDev(e->dFrac);
+    freeDev(e->dFracInit);
+    for (int v = 0; v < 3; ++v) {
+        freeDev(e->dForcingRaw[v]);
+        freeDev(e->dForcingTiled[v]);
+        freeDev(e->dStation[v]);
+    }
+    freeDev(e->dGradT);
+    freeDev(e->dGradP);
+    freeDev(e->dCorrP);
+    freeDev(e->dState);
+    freeDev(e->dInitUnit);
+    freeDev(e->dInitFull);
+    freeDev(e->dBasinState);
+    freeDev(e->dBasinInit);
+    freeDev(e->dOutlet);
+    freeDev(e->dPartQ);
+    freeDev(e->dD1);
+    freeDev(e->dD2);
+    freeDev(e->dPartD1);
+    freeDev(e->dPartD2);
+    freeDev(e->dRec);
+    freeDev(e->dErr);
+    freeDev(e->dUnconv);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+const char* hbk_last_error(const hbk_engine* e) { return e ? e->error.c_str() : "null engine"; }
+
+int hbk_set_units(hbk_engine* e, const double* area, const double* elevation, const float* slope,
+                  const int32_t* glacier_variant, const double* frac_ground, const double* frac_glacier) {
+    if (!e || !area) return HBK_E_ARG;
+    if (e->st.quick_kind == HBK_QUICK_SOCONT && !slope)
+        return fail(e, HBK_E_ARG, "runoff:socont needs the 'slope' property of every hydro unit");
+    HBK_CUDA(cudaSetDevice(e->device));
+    const int U = e->U;
+    double basinArea = 0;  // SubBasin::AddHydroUnit (SubBasin.cpp:173): running sum in unit order
+    for (int u = 0; u < U; ++u) basinArea += area[u];
+    std::vector<double> hru((size_t)kNH * e->ldu, 0.0);
+    std::vector<int> flags(e->ldu, 0);
+    e->hFracG.assign(U, 1.0);
+    e->hFracGl.assign(U, 0.0);
+    e->hGlacierVariant.assign(U, 0);
+    for (int u = 0; u < U; ++u) {
+        hru[0 * e->ldu + u] = area[u] / basinArea;  // ModelBuilder.cpp:468
+        hru[1 * e->ldu + u] = area[u];
+        // pow(_slope, 0.5) of ProcessRunoffSocont.cpp:51 with _slope float32, evaluated with the host libm
+        hru[2 * e->ldu + u] = slope ? std::pow((double)slope[u], 0.5) : 0.0;
+        hru[3 * e->ldu + u] = elevation ? elevation[u] : 0.0;
+        flags[u] = (glacier_variant && glacier_variant[u]) ? 1 : 0;
+        e->hGlacierVariant[u] = flags[u];
+        if (frac_ground) e->hFracG[u] = frac_ground[u];
+        if (frac_glacier) e->hFracGl[u] = frac_glacier[u];
+    }
+    std::vector<double> frac(2 * (size_t)U);
+    for (int u = 0; u < U; ++u) {
+        frac[u] = e->hFracG[u];
+        frac[U + u] = e->hFracGl[u];
+    }
+    HBK_CUDA(cudaMemcpy(e->dHru, hru.data(), sizeof(double) * hru.size(), cudaMemcpyHostToDevice));
+    HBK_CUDA(cudaMemcpy(e->dHruFlags, flags.data(), sizeof(int) * flags.size(), cudaMemcpyHostToDevice));
+    HBK_CUDA(cudaMemcpy(e->dFracInit, frac.data(), sizeof(double) * frac.size(), cudaMemcpyHostToDevice));
+    HBK_CUDA(cudaMemcpy(e->dFrac, frac.data(), sizeof(double) * frac.size(), cudaMemcpyHostToDevice));
+    e->unitsSet = true;
+    return HBK_OK;
+}
+
+int hbk_set_parameters(hbk_engine* e, int32_t n_sets, const float* values) {
+    if (!e || n_sets <= 0 || !values) return HBK_E_ARG;
+    HBK_CUDA(cudaSetDevice(e->device));
+    int rc = ensureSetBuffers(e, n_sets);
+    if (rc) return rc;
+    // [n_sets][N] -> [N][ldp]: the parameter axis is the fastest one on the device
+    std::vector<float> t((size_t)HBK_N_PARAMS * e->ldp, 0.0f);
+    for (int p = 0; p < n_sets; ++p)
+        for (int k = 0; k < HBK_N_PARAMS; ++k) t[(size_t)k * e->ldp + p] = values[(size_t)p * HBK_N_PARAMS + k];
+    HBK_CUDA(cudaMemcpyAsync(e->dParams, t.data(), sizeof(float) * t.size(), cudaMemcpyHostToDevice, e->stream));
+    HBK_CUDA(cudaStreamSynchronize(e->stream));
+    return HBK_OK;
+}
+
+int hbk_set_forcing(hbk_engine* e, int32_t var, const double* data) {
+    if (!e || var < 0 || var > 2 || !data) return HBK_E_ARG;
+    HBK_CUDA(cudaSetDevice(e->device));
+    const size_t n = (size_t)e->T * e->U;
+    if (!e->dForcingRaw[var]) HBK_CUDA(cudaMalloc(&e->dForcingRaw[var], sizeof(double) * n));
+    HBK_CUDA(cudaMemcpyAsync(e->dForcingRaw[var], data, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+    HBK_CUDA(cudaStreamSynchronize(e->stream));
+    e->haveRaw[var] = true;
+    e->haveStation[var] = false;
+    e->tiledUB = 0;  // re-tile on the next run
+    return HBK_OK;
+}
+
+int hbk_set_station_forcing(hbk_engine* e, int32_t var, const double* series, double ref_elevation, double gradient,
+                            const double* gradient_per_set, double correction, const double* correction_per_set) {
+    if (!e || var < 0 || var > 2 || !series) return HBK_E_ARG;
+    HBK_CUDA(cudaSetDevice(e->device));
+    if ((gradient_per_set || correction_per_set) && e->P == 0)
+        return fail(e, HBK_E_STATE, "set the parameters before per-set spatialisation gradients");
+    if (!e->dStation[var]) {
+        HBK_CUDA(cudaMalloc(&e->dStation[var], sizeof(double) * e->tld));
+    }
+    HBK_CUDA(cudaMemsetAsync(e->dStation[var], 0, sizeof(double) * e->tld, e->stream));
+    HBK_CUDA(cudaMemcpyAsync(e->dStation[var], series, sizeof(double) * e->T, cudaMemcpyHostToDevice, e->stream));
+    auto perSet = [&](double*& dst, const double* src) -> int {
+        if (!src) {
+            freeDev(dst);
+            return HBK_OK;
+        }
+        if (!dst) HBK_CUDA(cudaMalloc(&dst, sizeof(double) * e->P));
+        HBK_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * e->P, cudaMemcpyHostToDevice, e->stream));
+        return HBK_OK;
+    };
+    int rc = HBK_OK;
+    if (var == HBK_VAR_TEMPERATURE) {
+        e->gradTs = gradient;
+        e->zrefT = ref_elevation;
+        rc = perSet(e->dGradT, gradient_per_set);
+    } else if (var == HBK_VAR_PRECIPITATION) {
+        e->gradPs = gradient;
+        e->zrefP = ref_elevation;
+        e->corrPs = correction;
+        rc = perSet(e->dGradP, gradient_per_set);
+        if (!rc) rc = perSet(e->dCorrP, correction_per_set);
+    }
+    if (rc) return rc;
+    HBK_CUDA(cudaStreamSynchronize(e->stream));
+    e->haveStation[var] = true;
+    e->haveRaw[var] = false;
+    return HBK_OK;
+}
+
+int hbk_set_initial_state(hbk_engine* e, int32_t slot, const double* values) {
+    if (!e || slot < 0 || slot >= HBK_N_STATES) return HBK_E_ARG;
+    HBK_CUDA(cudaSetDevice(e->device));
+    if (values) {
+        HBK_CUDA(cudaMemcpy(e->dInitUnit + (size_t)slot * e->U, values, sizeof(double) * e->U, cudaMemcpyHostToDevice));
+    } else {
+        HBK_CUDA(cudaMemset(e->dInitUnit + (size_t)slot * e->U, 0, sizeof(double) * e->U));
+    }
+    e->initPerSet = false;
+    return HBK_OK;
+}
+
+int hbk_save_as_initial_state(hbk_engine* e) {
+    if (!e || !e->ran) return fail(e, HBK_E_STATE, "save_as_initial_state needs a completed run");
+    HBK_CUDA(cudaSetDevice(e->device));
+    const size_t n = sizeof(double) * HBK_N_STATES * (size_t)e->P * e->U;
+    if (!e->dInitFull) HBK_CUDA(cudaMalloc(&e->dInitFull, n));
+    HBK_CUDA(cudaMemcpy(e->dInitFull, e->dState, n, cudaMemcpyDeviceToDevice));
+    HBK_CUDA(cudaMemcpy(e->dBasinInit, e->dBasinState, sizeof(double) * 2 * e->P, cudaMemcpyDeviceToDevice));
+    e->initPerSet = true;
+    return HBK_OK;
+}
+
+int hbk_set_spinup_steps(hbk_engine* e, int32_t n) {
+    if (!e || n < 0) return HBK_E_ARG;
+    e->spinupSteps = std::min<int>(n, e->T);  // ModelHydro.cpp:52-53
+    return HBK_OK;
+}
+
+int hbk_set_record_mask(hbk_engine* e, uint64_t mask) {
+    if (!e) return HBK_E_ARG;
+    e->recordMask = mask & ((1ull << HBK_N_RECORDS) - 1);
+    return HBK_OK;
+}
+
+static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs) {
+    const bool tiled = e->haveRaw[0];
+    KArgs a{};
+    a.P = e->P;
+    a.U = e->U;
+    a.tBegin = tBegin;
+    a.tEnd = tEnd;
+    a.PB = e->PB;
+    a.UB = e->UB;
+    a.TC = e->TC;
+    a.nUTiles = e->nUTiles;
+    a.flags.quickKind = e->st.quick_kind;
+    a.flags.slowOrder = e->st.slow_process_order;
+    a.flags.splitKind = e->st.splitter_kind;
+    a.flags.iceInfinite = e->st.glacier_infinite_storage;
+    a.flags.noMeltWhenSnow = e->st.glacier_no_melt_when_snow_cover;
+    a.dt = e->st.time_step_days;
+    a.params = e->dParams;
+    a.ldp = e->ldp;
+    a.hru = e->dHru;
+    a.hruFlags = e->dHruFlags;
+    a.ldu = e->ldu;
+    a.frac = e->dFrac;
+    a.fracPerSet = e->fracPerSet;
+    a.fracLd = e->fracPerSet ? (long long)e->P * e->U : e->U;
+    a.forcingMode = tiled ? 0 : 1;
+    for (int v = 0; v < 3; ++v) a.forcing[v] = tiled ? e->dForcingTiled[v] : e->dStation[v];
+    a.tld = e->tld;
+    a.gradT = e->dGradT;
+    a.gradP = e->dGradP;
+    a.corrP = e->dCorrP;
+    a.gradTs = e->gradTs;
+    a.gradPs = e->gradPs;
+    a.corrPs = e->corrPs;
+    a.zrefT = e->zrefT;
+    a.zrefP = e->zrefP;
+    a.state = e->dState;
+    a.lds = (long long)e->P * e->U;
+    const bool multi = e->nUTiles > 1;
+    a.outQ = multi ? e->dPartQ : e->dOutlet;
+    a.outD1 = multi ? e->dPartD1 : e->dD1;
+    a.outD2 = multi ? e->dPartD2 : e->dD2;
+    a.ldt = e->ldt;
+    a.writeOutputs = writeOutputs ? 1 : 0;
+    a.recordMask = e->recordMask;
+    a.rec = e->dRec;
+    a.T = e->T;
+    a.err = e->dErr;
+    a.unconverged = e->dUnconv;
+
+    KernelFn fn = pickKernel(e->st);
+    const size_t smem = smemBytes(e, tiled);
+    HBK_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int nPGroups = (e->P + e->PB - 1) / e->PB;
+    const long long grid = (long long)nPGroups * e->nUTiles;
+    if (grid > 2147483647LL) return fail(e, HBK_E_UNSUPPORTED, "grid too large");
+    void* args[] = {(void*)&a};
+    HBK_CUDA(cudaLaunchKernel((const void*)fn, dim3((unsigned)grid), dim3(kBlock), args, smem, e->stream));
+    e->lastLaunches++;
+
+    if (writeOutputs && multi) {
+        const long long n = (long long)e->P * (tEnd - tBegin);
+        const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+        hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartQ, e->dOutlet, e->nUTiles, e->P, e->ldt, tBegin, tEnd);
+        e->lastLaunches++;
+        if (e->st.has_glacier) {
+            hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD1, e->dD1, e->nUTiles, e->P, e->ldt, tBegin, tEnd);
+            hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD2, e->dD2, e->nUTiles, e->P, e->ldt, tBegin, tEnd);
+            e->lastLaunches += 2;
+        }
+    } else if (!writeOutputs && multi && e->st.has_glacier) {
+        // spin-up: the deposits are still needed by the sub-basin stores
+        const long long n = (long long)e->P * (tEnd - tBegin);
+        const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+        hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD1, e->dD1, e->nUTiles, e->P, e->ldt, tBegin, tEnd);
+        hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD2, e->dD2, e->nUTiles, e->P, e->ldt, tBegin, tEnd);
+        e->lastLaunches += 2;
+    }
+    if (e->st.has_glacier) {
+        const int blocks = (e->P + 127) / 128;
+        const double dt = e->st.time_step_days;
+        switch (e->st.solver) {
+            case HBK_SOLVER_EULER:
+                hbkBasinStores<0><<<blocks, 128, 0, e->stream>>>(e->dParams, e->ldp, e->P, e->ldt, tBegin, tEnd, dt, e->dD1,
+                                                               e->dD2, nullptr, e->dOutlet, e->dBasinState,
+                                                               writeOutputs ? 1 : 0, e->dErr, e->dUnconv);
+                break;
+            case HBK_SOLVER_HEUN:
+                hbkBasinStores<1><<<blocks, 128, 0, e->stream>>>(e->dParams, e->ldp, e->P, e->ldt, tBegin, tEnd, dt, e->dD1,
+                                                               e->dD2, nullptr, e->dOutlet, e->dBasinState,
+                                                               writeOutputs ? 1 : 0, e->dErr, e->dUnconv);
+                break;
+            default:
+                hbkBasinStores<2><<<blocks, 128, 0, e->stream>>>(e->dParams, e->ldp, e->P, e->ldt, tBegin, tEnd, dt, e->dD1,
+                                                               e->dD2, nullptr, e->dOutlet, e->dBasinState,
+                                                               writeOutputs ? 1 : 0, e->dErr, e->dUnconv);
+                break;
+        }
+        e->lastLaunches++;
+    }
+    HBK_CUDA(cudaGetLastError());
+    return HBK_OK;
+}
+
+int hbk_run(hbk_engine* e) {
+    if (!e) return HBK_E_ARG;
+    if (!e->unitsSet) return fail(e, HBK_E_STATE, "hbk_set_units has not been called");
+    if (e->P <= 0) return fail(e, HBK_E_STATE, "hbk_set_parameters has not been called");
+    const bool tiled = e->haveRaw[0] && e->haveRaw[1] && e->haveRaw[2];
+    const bool station = e->haveStation[0] && e->haveStation[1] && e->haveStation[2];
+    if (!tiled && !station)
+        return fail(e, HBK_E_STATE, "forcing incomplete: precipitation, temperature and pet are all required, "
+                                    "either all per unit or all as station series");
+    HBK_CUDA(cudaSetDevice(e->device));
+    chooseShape(e);
+    e->lastLaunches = 0;
+
+    // (re)allocate shape-dependent buffers
+    const bool multi = e->nUTiles > 1;
+    const size_t outN = (size_t)e->P * e->ldt;
+    if (multi && !e->dPartQ) HBK_CUDA(cudaMalloc(&e->dPartQ, sizeof(double) * outN * e->nUTiles));
+    if (e->st.has_glacier) {
+        if (!e->dD1) HBK_CUDA(cudaMalloc(&e->dD1, sizeof(double) * outN));
+        if (!e->dD2) HBK_CUDA(cudaMalloc(&e->dD2, sizeof(double) * outN));
+        if (multi && !e->dPartD1) HBK_CUDA(cudaMalloc(&e->dPartD1, sizeof(double) * outN * e->nUTiles));
+        if (multi && !e->dPartD2) HBK_CUDA(cudaMalloc(&e->dPartD2, sizeof(double) * outN * e->nUTiles));
+    }
+    const int nRec = __builtin_popcountll(e->recordMask);
+    const size_t recBytes = sizeof(double) * (size_t)nRec * e->P * e->T * e->U;
+    if (recBytes != e->recBytes) {
+        freeDev(e->dRec);
+        if (recBytes) HBK_CUDA(cudaMalloc(&e->dRec, recBytes));
+        e->recBytes = recBytes;
+    }
+    if (tiled && e->tiledUB != e->UB) {
+        for (int v = 0; v < 3; ++v) {
+            freeDev(e->dForcingTiled[v]);
+            const size_t n = (size_t)e->nUTiles * e->tld * e->UB;
+            HBK_CUDA(cudaMalloc(&e->dForcingTiled[v], sizeof(double) * n));
+            HBK_CUDA(cudaMemsetAsync(e->dForcingTiled[v], 0, sizeof(double) * n, e->stream));
+            hbkTileForcing<<<148 * 4, 256, 0, e->stream>>>(e->dForcingRaw[v], e->dForcingTiled[v], e->T, e->U, e->UB, e->tld,
+                                                           e->nUTiles);
+        }
+        HBK_CUDA(cudaGetLastError());
+        e->tiledUB = e->UB;
+    }
+
+    HBK_CUDA(cudaEventRecord(e->ev0, e->stream));
+    // ModelHydro::Reset (ModelHydro.cpp:183-193): containers back to their initial state, fluxes to 0.
+    const size_t nPU = (size_t)e->P * e->U;
+    if (e->initPerSet) {
+        HBK_CUDA(cudaMemcpyAsync(e->dState, e->dInitFull, sizeof(double) * HBK_N_STATES * nPU, cudaMemcpyDeviceToDevice,
+                                 e->stream));
+        HBK_CUDA(cudaMemsetAsync(e->dState + (size_t)HBK_S_AMT_INFILTRATION * nPU, 0,
+                                 sizeof(double) * (HBK_N_STATES - HBK_S_AMT_INFILTRATION) * nPU, e->stream));
+    } else {
+        for (int s = 0; s < HBK_N_STATES; ++s) {
+            const bool storage = s < HBK_S_AMT_INFILTRATION;
+            hbkBroadcastState<<<148 * 2, 256, 0, e->stream>>>(e->dState + (size_t)s * nPU,
+                                                              storage ? e->dInitUnit + (size_t)s * e->U : nullptr, 0.0,
+                                                              e->P, e->U);
+        }
+        e->lastLaunches += HBK_N_STATES;
+    }
+    HBK_CUDA(cudaMemcpyAsync(e->dBasinState, e->dBasinInit, sizeof(double) * 2 * e->P, cudaMemcpyDeviceToDevice, e->stream));
+    HBK_CUDA(cudaMemcpyAsync(e->dFrac, e->dFracInit, sizeof(double) * 2 * e->U, cudaMemcpyDeviceToDevice, e->stream));
+    HBK_CUDA(cudaMemsetAsync(e->dErr, 0, sizeof(int), e->stream));
+    HBK_CUDA(cudaMemsetAsync(e->dUnconv, 0, sizeof(unsigned long long), e->stream));
+
+    int rc;
+    if (e->spinupSteps > 0) {  // ModelHydro::RunSpinup (ModelHydro.cpp:135-181)
+        rc = launchSegment(e, 0, e->spinupSteps, false);
+        if (rc) return rc;
+    }
+    rc = launchSegment(e, 0, e->T, true);
+    if (rc) return rc;
+    HBK_CUDA(cudaEventRecord(e->ev1, e->stream));
+    HBK_CUDA(cudaStreamSynchronize(e->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    e->lastMs = ms;
+    int err = 0;
+    unsigned long long unc = 0;
+    HBK_CUDA(cudaMemcpy(&err, e->dErr, sizeof(int), cudaMemcpyDeviceToHost));
+    HBK_CUDA(cudaMemcpy(&unc, e->dUnconv, sizeof(unc), cudaMemcpyDeviceToHost));
+    e->lastUnconverged = (long long)unc;
+    e->ran = true;
+    if (err & kErrRateTooHigh)  // WaterContainer.cpp:83-86 throws; ModelHydro::Run fails
+        return fail(e, HBK_E_MODEL, "a change rate exceeded 10000 (WaterContainer::ApplyConstraints)");
+    return HBK_OK;
+}
+
+int hbk_get_outlet(hbk_engine* e, int32_t first, int32_t n, double* out) {
+    if (!e || !out || first < 0 || n <= 0 || first + n > e->P) return HBK_E_ARG;
+    if (!e->ran) return fail(e, HBK_E_STATE, "no completed run");
+    HBK_CUDA(cudaSetDevice(e->device));
+    HBK_CUDA(cudaMemcpy2D(out, sizeof(double) * e->T, e->dOutlet + (size_t)first * e->ldt, sizeof(double) * e->ldt,
+                          sizeof(double) * e->T, n, cudaMemcpyDeviceToHost));
+    return HBK_OK;
+}
+
+int hbk_get_recorded(hbk_engine* e, int32_t slot, int32_t set, double* out) {
+    if (!e || !out || slot < 0 || slot >= HBK_N_RECORDS || set < 0 || set >= e->P) return HBK_E_ARG;
+    if (!e->ran) return fail(e, HBK_E_STATE, "no completed run");
+    if (!(e->recordMask & (1ull << slot))) return fail(e, HBK_E_ARG, "this item was not recorded (record mask)");
+    HBK_CUDA(cudaSetDevice(e->device));
+    const int k = __builtin_popcountll(e->recordMask & ((1ull << slot) - 1));
+    const size_t n = (size_t)e->T * e->U;
+    HBK_CUDA(cudaMemcpy(out, e->dRec + ((size_t)k * e->P + set) * n, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return HBK_OK;
+}
+
+int hbk_get_state(hbk_engine* e, int32_t slot, double* out) {
+    if (!e || !out || slot < 0 || slot >= HBK_N_STATES) return HBK_E_ARG;
+    if (!e->ran) return fail(e, HBK_E_STATE, "no completed run");
+    HBK_CUDA(cudaSetDevice(e->device));
+    const size_t n = (size_t)e->P * e->U;
+    HBK_CUDA(cudaMemcpy(out, e->dState + (size_t)slot * n, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return HBK_OK;
+}
+
+int hbk_get_basin_state(hbk_engine* e, double* out) {
+    if (!e || !out) return HBK_E_ARG;
+    if (!e->ran) return fail(e, HBK_E_STATE, "no completed run");
+    HBK_CUDA(cudaSetDevice(e->device));
+    HBK_CUDA(cudaMemcpy(out, e->dBasinState, sizeof(double) * 2 * e->P, cudaMemcpyDeviceToHost));
+    return HBK_OK;
+}
+
+int hbk_outlet_dev(hbk_engine* e, const double** ptr, int64_t* ld) {
+    if (!e || !ptr || !ld) return HBK_E_ARG;
+    *ptr = e->dOutlet;
+    *ld = e->ldt;
+    return HBK_OK;
+}
+
+int hbk_last_run_stats(hbk_engine* e, double* ms, int32_t* launches, int64_t* unconverged) {
+    if (!e) return HBK_E_ARG;
+    if (ms) *ms = e->lastMs;
+    if (launches) *launches = e->lastLaunches;
+    if (unconverged) *unconverged = e->lastUnconverged;
+    return HBK_OK;
+}
+
+void* hbk_stream(hbk_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+}  // extern "C"

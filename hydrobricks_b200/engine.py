@@ -1,0 +1,227 @@
+"""ctypes binding of the C-ABI in include/hbk.h (libhbk.so, CUDA sm_100a).
+
+This is product code: it never imports anything from oracle/ and it raises when the CUDA library or a
+CUDA device is missing — there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "libhbk.so"
+
+# enums of include/hbk.h
+SOLVER = {"euler_explicit": 0, "heun_explicit": 1, "rk4": 2, "runge_kutta": 2}
+QUICK_SOCONT, QUICK_LINEAR = 0, 1
+SPLIT_LINEAR, SPLIT_THRESHOLD = 0, 1
+VAR = {"precipitation": 0, "p": 0, "temperature": 1, "t": 1, "pet": 2}
+PARAM_SLOTS = [
+    "transition_start", "transition_end", "rain_correction", "snow_correction", "ground_snow_ddf",
+    "ground_snow_tmelt", "glacier_snow_ddf", "glacier_snow_tmelt", "ice_ddf", "ice_tmelt", "capacity", "k_slow_1",
+    "percolation", "k_slow_2", "quick", "k_snow", "k_ice",
+]
+N_PARAMS = len(PARAM_SLOTS)
+RECORD_SLOTS = [
+    "ground_water", "ground_infiltration", "ground_runoff", "glacier_water", "glacier_ice", "glacier_outflow",
+    "glacier_melt", "ground_snowpack_water", "ground_snowpack_snow", "ground_snowpack_melt",
+    "glacier_snowpack_water", "glacier_snowpack_snow", "glacier_snowpack_melt", "slow_water", "slow_et",
+    "slow_outflow", "slow_overflow", "slow_percolation", "slow2_water", "slow2_outflow", "quick_water",
+    "quick_runoff",
+]
+STATE_SLOTS = [
+    "ground_snow", "glacier_snow", "ground_water", "glacier_water", "ice", "slow", "slow2", "quick",
+    "amt_infiltration", "amt_rest", "amt_melt_ground", "amt_melt_glacier", "amt_deposit_rain_snowmelt",
+    "amt_deposit_icemelt",
+]
+
+
+class HbkStructure(ctypes.Structure):
+    _fields_ = [
+        ("solver", ctypes.c_int32),
+        ("n_soil_stores", ctypes.c_int32),
+        ("quick_kind", ctypes.c_int32),
+        ("slow_process_order", ctypes.c_int32),
+        ("splitter_kind", ctypes.c_int32),
+        ("has_glacier", ctypes.c_int32),
+        ("glacier_infinite_storage", ctypes.c_int32),
+        ("glacier_no_melt_when_snow_cover", ctypes.c_int32),
+        ("time_step_days", ctypes.c_double),
+    ]
+
+
+class HbkError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"hbk error {code}: {message}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library():
+    """Load libhbk.so; fail loudly when it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python __graft_entry__.py build` "
+                          "(nvcc, sm_100a). hydrobricks_b200 has no CPU fallback.")
+    L = ctypes.CDLL(str(LIB_PATH))
+    vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
+    dp, fp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)
+    L.hbk_engine_create.argtypes = [ctypes.POINTER(HbkStructure), i32, i32, i32, ctypes.POINTER(vp)]
+    L.hbk_engine_destroy.argtypes = [vp]
+    L.hbk_engine_destroy.restype = None
+    L.hbk_last_error.argtypes = [vp]
+    L.hbk_last_error.restype = ctypes.c_char_p
+    L.hbk_set_units.argtypes = [vp, dp, dp, fp, ip, dp, dp]
+    L.hbk_set_parameters.argtypes = [vp, i32, fp]
+    L.hbk_set_forcing.argtypes = [vp, i32, dp]
+    L.hbk_set_station_forcing.argtypes = [vp, i32, dp, dbl, dbl, dp, dbl, dp]
+    L.hbk_set_initial_state.argtypes = [vp, i32, dp]
+    L.hbk_save_as_initial_state.argtypes = [vp]
+    L.hbk_set_spinup_steps.argtypes = [vp, i32]
+    L.hbk_set_record_mask.argtypes = [vp, ctypes.c_uint64]
+    L.hbk_run.argtypes = [vp]
+    L.hbk_get_outlet.argtypes = [vp, i32, i32, dp]
+    L.hbk_get_recorded.argtypes = [vp, i32, i32, dp]
+    L.hbk_get_state.argtypes = [vp, i32, dp]
+    L.hbk_get_basin_state.argtypes = [vp, dp]
+    L.hbk_outlet_dev.argtypes = [vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(i64)]
+    L.hbk_last_run_stats.argtypes = [vp, dp, ip, ctypes.POINTER(i64)]
+    L.hbk_stream.argtypes = [vp]
+    L.hbk_stream.restype = ctypes.c_void_p
+    _lib = L
+    return L
+
+
+def _dptr(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) if a is not None else None
+
+
+class Engine:
+    """One engine = one structure + basin + time axis on one CUDA device."""
+
+    def __init__(self, structure: HbkStructure, n_units: int, n_steps: int, device: int = 0):
+        self.L = load_library()
+        self.h = ctypes.c_void_p()
+        self.n_units, self.n_steps, self.n_sets = int(n_units), int(n_steps), 0
+        rc = self.L.hbk_engine_create(ctypes.byref(structure), self.n_units, self.n_steps, int(device),
+                                      ctypes.byref(self.h))
+        if rc != 0:
+            raise HbkError(rc, "hbk_engine_create failed (is a CUDA device present? there is no CPU fallback)")
+        self.structure = structure
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.hbk_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise HbkError(rc, self.L.hbk_last_error(self.h).decode())
+
+    def set_units(self, area, elevation=None, slope=None, glacier_variant=None, fraction_ground=None,
+                  fraction_glacier=None):
+        f64 = lambda x: None if x is None else np.ascontiguousarray(x, dtype=np.float64)  # noqa: E731
+        area, elevation, fg, fgl = f64(area), f64(elevation), f64(fraction_ground), f64(fraction_glacier)
+        slope = None if slope is None else np.ascontiguousarray(slope, dtype=np.float32)
+        gv = None if glacier_variant is None else np.ascontiguousarray(glacier_variant, dtype=np.int32)
+        assert area.shape == (self.n_units,)
+        self._check(self.L.hbk_set_units(
+            self.h, _dptr(area), _dptr(elevation),
+            slope.ctypes.data_as(ctypes.POINTER(ctypes.c_float)) if slope is not None else None,
+            gv.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)) if gv is not None else None, _dptr(fg), _dptr(fgl)))
+
+    def set_parameters(self, values):
+        v = np.ascontiguousarray(values, dtype=np.float32)
+        if v.ndim == 1:
+            v = v[None, :]
+        assert v.shape[1] == N_PARAMS, v.shape
+        self.n_sets = v.shape[0]
+        self._check(self.L.hbk_set_parameters(self.h, self.n_sets, v.ctypes.data_as(ctypes.POINTER(ctypes.c_float))))
+
+    def set_forcing(self, variable, data):
+        a = np.ascontiguousarray(data, dtype=np.float64)
+        assert a.shape == (self.n_steps, self.n_units), a.shape
+        self._check(self.L.hbk_set_forcing(self.h, VAR[variable] if isinstance(variable, str) else variable, _dptr(a)))
+
+    def set_station_forcing(self, variable, series, ref_elevation=0.0, gradient=0.0, correction=1.0):
+        s = np.ascontiguousarray(series, dtype=np.float64)
+        assert s.shape == (self.n_steps,)
+        g_set = c_set = None
+        if np.ndim(gradient) > 0:
+            g_set = np.ascontiguousarray(gradient, dtype=np.float64)
+            assert g_set.shape == (self.n_sets,)
+            gradient = 0.0
+        if np.ndim(correction) > 0:
+            c_set = np.ascontiguousarray(correction, dtype=np.float64)
+            assert c_set.shape == (self.n_sets,)
+            correction = 1.0
+        self._check(self.L.hbk_set_station_forcing(self.h, VAR[variable] if isinstance(variable, str) else variable,
+                                                   _dptr(s), float(ref_elevation), float(gradient), _dptr(g_set),
+                                                   float(correction), _dptr(c_set)))
+
+    def set_initial_state(self, slot, values=None):
+        v = None if values is None else np.ascontiguousarray(values, dtype=np.float64)
+        self._check(self.L.hbk_set_initial_state(self.h, STATE_SLOTS.index(slot) if isinstance(slot, str) else slot,
+                                                 _dptr(v)))
+
+    def save_as_initial_state(self):
+        self._check(self.L.hbk_save_as_initial_state(self.h))
+
+    def set_spinup_steps(self, n):
+        self._check(self.L.hbk_set_spinup_steps(self.h, int(n)))
+
+    def set_record_mask(self, slots):
+        mask = 0
+        for s in slots:
+            mask |= 1 << (RECORD_SLOTS.index(s) if isinstance(s, str) else int(s))
+        self._check(self.L.hbk_set_record_mask(self.h, mask))
+
+    def run(self):
+        self._check(self.L.hbk_run(self.h))
+
+    def get_outlet(self, first=0, n=None):
+        n = self.n_sets - first if n is None else n
+        out = np.empty((n, self.n_steps), dtype=np.float64)
+        self._check(self.L.hbk_get_outlet(self.h, int(first), int(n), _dptr(out)))
+        return out
+
+    def get_recorded(self, slot, set_index=0):
+        out = np.empty((self.n_steps, self.n_units), dtype=np.float64)
+        self._check(self.L.hbk_get_recorded(self.h, RECORD_SLOTS.index(slot) if isinstance(slot, str) else slot,
+                                            int(set_index), _dptr(out)))
+        return out
+
+    def get_state(self, slot):
+        out = np.empty((self.n_sets, self.n_units), dtype=np.float64)
+        self._check(self.L.hbk_get_state(self.h, STATE_SLOTS.index(slot) if isinstance(slot, str) else slot, _dptr(out)))
+        return out
+
+    def get_basin_state(self):
+        out = np.empty((self.n_sets, 2), dtype=np.float64)
+        self._check(self.L.hbk_get_basin_state(self.h, _dptr(out)))
+        return out
+
+    def outlet_device_pointer(self):
+        ptr, ld = ctypes.c_void_p(), ctypes.c_int64()
+        self._check(self.L.hbk_outlet_dev(self.h, ctypes.byref(ptr), ctypes.byref(ld)))
+        return ptr.value, ld.value
+
+    def last_run_stats(self):
+        ms, n, unc = ctypes.c_double(), ctypes.c_int32(), ctypes.c_int64()
+        self._check(self.L.hbk_last_run_stats(self.h, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(unc)))
+        return {"kernel_ms": ms.value, "launches": n.value, "unconverged_sweeps": unc.value}
+
+    def stream(self):
+        return self.L.hbk_stream(self.h)

@@ -1,0 +1,357 @@
+"""Structure compiler: model-structure description -> the engine's per-structure process table.
+
+Input is the list of structure-variant dicts that `SettingsModel.get_structure()` exports
+(reference core/bindings/Binding.cpp:119-160, with the parameter values of every element). The compiler
+recognises the Socont family (python/src/hydrobricks/models/socont.py:111-215, modules/glacier.py:87-131,
+core/tests/src/helpers.cpp:9-107) by the ROLE of each brick, not by its name:
+
+  snow_rain_transition splitter (snow_rain:linear | snow_rain:threshold) -> rain / snow multi_fluxes splitters
+  one generic land cover     {infiltration:socont -> S, outflow:rest -> Q}            (direct brick)
+  optional glacier land cover {outflow:direct -> B1 (instantaneous), melt:degree_day -> B2 (instantaneous)}
+  one snowpack per cover      {melt:degree_day -> cover}
+  S  storage, capacity        {et:socont, outflow:linear -> outlet, overflow -> outlet, [percolation:constant -> S2]}
+  S2 storage                  {outflow:linear -> outlet}
+  Q  storage                  {runoff:socont -> outlet | outflow:linear -> outlet}
+  B1, B2 sub-basin storages   {outflow:linear -> outlet}
+
+and emits (i) the hbk_structure flags that select the kernel instantiation, (ii) the float32 parameter
+vector in HBK_P_* slot order, (iii) the label -> recorder-slot map. Anything else raises
+UnsupportedStructure: the engine never silently computes something different from the reference.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import engine as _e
+
+PRECISION = 1e-8
+
+
+class UnsupportedStructure(ValueError):
+    pass
+
+
+def _params(elem):
+    return {p["name"]: np.float32(p["value"]) for p in elem.get("parameters", [])}
+
+
+def _proc_kinds(brick):
+    return [p["kind"] for p in brick["processes"]]
+
+
+def _target(proc):
+    outs = proc.get("outputs", [])
+    return outs[0]["target"] if outs else None
+
+
+class CompiledStructure:
+    def __init__(self, structures, solver: str, time_step_days: float = 1.0):
+        if solver not in _e.SOLVER:
+            raise UnsupportedStructure(
+                f"solver {solver!r}: only euler_explicit, heun_explicit and rk4/runge_kutta run on the device")
+        self.solver = solver
+        self.structures = structures
+        self.labels = {}
+        self.params = np.zeros(_e.N_PARAMS, dtype=np.float32)
+        self.param_index = {}  # (component, parameter name) -> slot
+        self._compile(structures, time_step_days)
+
+    # ------------------------------------------------------------------------------------------------
+    def _set(self, slot, component, name, value):
+        i = _e.PARAM_SLOTS.index(slot)
+        self.params[i] = np.float32(value)
+        self.param_index[(component, name)] = i
+
+    def _compile(self, structures, dt):
+        if not structures:
+            raise UnsupportedStructure("empty structure")
+        by_id = {s["id"]: s for s in structures}
+        base = by_id[1]
+        glacier_st = None
+        for s in structures:
+            if any(b["kind"] == "glacier" for b in s["hydro_unit_bricks"]):
+                glacier_st = s
+        if len(structures) > 2:
+            raise UnsupportedStructure("more than two structure variants")
+        full = glacier_st or base  # the variant that carries every brick
+        self.glacier_structure_id = glacier_st["id"] if glacier_st else None
+        self.variant_covers = {s["id"]: {b["name"] for b in s["hydro_unit_bricks"] if b["is_land_cover"]}
+                               for s in structures}
+
+        bricks = {b["name"]: b for b in full["hydro_unit_bricks"]}
+        basin_bricks = {b["name"]: b for b in base["sub_basin_bricks"]}
+        splitters = {s["name"]: s for s in full["hydro_unit_splitters"]}
+
+        st = _e.HbkStructure()
+        st.solver = _e.SOLVER[self.solver]
+        st.time_step_days = float(dt)
+
+        # --- splitters
+        if base["sub_basin_splitters"]:
+            raise UnsupportedStructure("sub-basin splitters")
+        tr = [s for s in splitters.values() if s["kind"] in ("snow_rain:linear", "snow_rain:threshold")]
+        multi = [s for s in splitters.values() if s["kind"] == "multi_fluxes"]
+        if len(tr) != 1 or len(multi) != 2 or len(splitters) != 3:
+            raise UnsupportedStructure("expected snow_rain_transition + rain/snow multi_fluxes splitters")
+        tr = tr[0]
+        sp = _params(tr)
+        if tr["kind"] == "snow_rain:linear":
+            st.splitter_kind = _e.SPLIT_LINEAR
+            self._set("transition_start", tr["name"], "transition_start", sp["transition_start"])
+            self._set("transition_end", tr["name"], "transition_end", sp["transition_end"])
+        else:
+            st.splitter_kind = _e.SPLIT_THRESHOLD
+            self._set("transition_start", tr["name"], "threshold", sp["threshold"])
+        self._set("rain_correction", tr["name"], "rain_correction_factor", sp.get("rain_correction_factor", 1.0))
+        self._set("snow_correction", tr["name"], "snow_correction_factor", sp.get("snow_correction_factor", 1.0))
+        self.splitter_name = tr["name"]
+        rain_targets = snow_targets = None
+        for out in tr["outputs"]:
+            tgt = splitters.get(out["target"])
+            if tgt is None or tgt["kind"] != "multi_fluxes":
+                raise UnsupportedStructure("snow_rain_transition must feed multi_fluxes splitters")
+            names = [o["target"] for o in tgt["outputs"]]
+            if out["flux_type"] == "snow":
+                snow_targets = names
+            else:
+                rain_targets = names
+
+        # --- land covers
+        covers = [b for b in full["hydro_unit_bricks"] if b["is_land_cover"]]
+        ground = [b for b in covers if b["kind"] == "generic_land_cover"]
+        glacier = [b for b in covers if b["kind"] == "glacier"]
+        if len(ground) != 1 or len(glacier) > 1 or len(ground) + len(glacier) != len(covers):
+            raise UnsupportedStructure("expected one generic land cover and at most one glacier cover")
+        ground = ground[0]
+        glacier = glacier[0] if glacier else None
+        self.ground_name = ground["name"]
+        self.glacier_name = glacier["name"] if glacier else None
+        if sorted(rain_targets or []) != sorted(c["name"] for c in covers):
+            raise UnsupportedStructure("rain must go to every land cover")
+        if _proc_kinds(ground) != ["infiltration:socont", "outflow:rest"]:
+            raise UnsupportedStructure(f"land cover {ground['name']}: expected infiltration:socont + outflow:rest")
+        slow_name = _target(ground["processes"][0])
+        quick_name = _target(ground["processes"][1])
+        if not ground["processes"][1]["outputs"][0]["static"]:
+            raise UnsupportedStructure("outflow:rest output must be static")
+        g = self.ground_name
+        self.labels.update({f"{g}:water_content": "ground_water",
+                            f"{g}:{ground['processes'][0]['name']}:output": "ground_infiltration",
+                            f"{g}:{ground['processes'][1]['name']}:output": "ground_runoff"})
+
+        # --- snowpacks
+        def snowpack_of(cover):
+            sps = [b for b in full["hydro_unit_bricks"] if b["kind"] == "snowpack" and b.get("parent") == cover["name"]]
+            if len(sps) != 1 or _proc_kinds(sps[0]) != ["melt:degree_day"] or _target(sps[0]["processes"][0]) != cover["name"]:
+                raise UnsupportedStructure(f"cover {cover['name']}: expected one snowpack with melt:degree_day")
+            return sps[0]
+
+        gsp = snowpack_of(ground)
+        pp = _params(gsp["processes"][0])
+        self._set("ground_snow_ddf", gsp["name"], "degree_day_factor", pp["degree_day_factor"])
+        self._set("ground_snow_tmelt", gsp["name"], "melting_temperature", pp["melting_temperature"])
+        self.labels.update({f"{gsp['name']}:water_content": "ground_snowpack_water",
+                            f"{gsp['name']}:snow_content": "ground_snowpack_snow",
+                            f"{gsp['name']}:{gsp['processes'][0]['name']}:output": "ground_snowpack_melt"})
+        snowpacks = [gsp["name"]]
+
+        # --- glacier
+        st.has_glacier = 0
+        b1 = b2 = None
+        if glacier is not None:
+            st.has_glacier = 1
+            if _proc_kinds(glacier) != ["outflow:direct", "melt:degree_day"]:
+                raise UnsupportedStructure("glacier cover: expected outflow:direct + melt:degree_day")
+            for proc in glacier["processes"]:
+                if not proc["outputs"][0]["instantaneous"]:
+                    raise UnsupportedStructure("glacier outputs must be instantaneous")
+            b1, b2 = _target(glacier["processes"][0]), _target(glacier["processes"][1])
+            gp = _params(glacier)
+            st.glacier_infinite_storage = int("infinite_storage" in gp and abs(float(gp["infinite_storage"])) > np.finfo(np.float32).eps)
+            st.glacier_no_melt_when_snow_cover = int("no_melt_when_snow_cover" in gp and float(gp["no_melt_when_snow_cover"]) > 0)
+            mp = _params(glacier["processes"][1])
+            self._set("ice_ddf", glacier["name"], "degree_day_factor", mp["degree_day_factor"])
+            self._set("ice_tmelt", glacier["name"], "melting_temperature", mp["melting_temperature"])
+            glsp = snowpack_of(glacier)
+            pp = _params(glsp["processes"][0])
+            self._set("glacier_snow_ddf", glsp["name"], "degree_day_factor", pp["degree_day_factor"])
+            self._set("glacier_snow_tmelt", glsp["name"], "melting_temperature", pp["melting_temperature"])
+            n = glacier["name"]
+            self.labels.update({f"{n}:water_content": "glacier_water", f"{n}:ice_content": "glacier_ice",
+                                f"{n}:{glacier['processes'][0]['name']}:output": "glacier_outflow",
+                                f"{n}:{glacier['processes'][1]['name']}:output": "glacier_melt",
+                                f"{glsp['name']}:water_content": "glacier_snowpack_water",
+                                f"{glsp['name']}:snow_content": "glacier_snowpack_snow",
+                                f"{glsp['name']}:{glsp['processes'][0]['name']}:output": "glacier_snowpack_melt"})
+            snowpacks.append(glsp["name"])
+            for name, slot in ((b1, "k_snow"), (b2, "k_ice")):
+                bb = basin_bricks.get(name)
+                if bb is None or bb["kind"] != "storage" or _proc_kinds(bb) != ["outflow:linear"] or \
+                        _target(bb["processes"][0]) != "outlet":
+                    raise UnsupportedStructure(f"sub-basin store {name}: expected storage with outflow:linear -> outlet")
+                self._set(slot, name, "response_factor", _params(bb["processes"][0])["response_factor"])
+        if sorted(snow_targets or []) != sorted(snowpacks):
+            raise UnsupportedStructure("snow must go to the snowpack of every land cover")
+        self.basin_store_names = (b1, b2)
+        # sub-basin bricks that no glacier feeds stay empty forever (helpers.cpp:55-59): ignore them, but
+        # only if they are plain linear stores to the outlet.
+        for name, bb in basin_bricks.items():
+            if name in (b1, b2):
+                continue
+            if bb["kind"] != "storage" or _proc_kinds(bb) != ["outflow:linear"] or _target(bb["processes"][0]) != "outlet":
+                raise UnsupportedStructure(f"sub-basin brick {name}")
+
+        # --- slow reservoir(s)
+        slow = bricks.get(slow_name)
+        if slow is None or slow["kind"] != "storage" or slow.get("computed_directly"):
+            raise UnsupportedStructure("infiltration target must be a storage solved by the ODE solver")
+        kinds = _proc_kinds(slow)
+        norm = ["overflow" if k in ("overflow", "outflow:overflow") else k for k in kinds]
+        if norm == ["et:socont", "outflow:linear", "overflow"]:
+            st.n_soil_stores, st.slow_process_order = 1, 0
+        elif norm == ["et:socont", "outflow:linear", "overflow", "percolation:constant"]:
+            st.n_soil_stores, st.slow_process_order = 2, 0
+        elif norm == ["et:socont", "outflow:linear", "percolation:constant", "overflow"]:
+            st.n_soil_stores, st.slow_process_order = 2, 1
+        else:
+            raise UnsupportedStructure(f"slow reservoir processes {kinds}")
+        sparams = _params(slow)
+        if "capacity" not in sparams:
+            raise UnsupportedStructure("slow reservoir needs a capacity")
+        self._set("capacity", slow_name, "capacity", sparams["capacity"])
+        label_of = {"et:socont": "slow_et", "outflow:linear": "slow_outflow", "overflow": "slow_overflow",
+                    "percolation:constant": "slow_percolation"}
+        self.labels[f"{slow_name}:water_content"] = "slow_water"
+        slow2_name = None
+        for proc, k in zip(slow["processes"], norm):
+            self.labels[f"{slow_name}:{proc['name']}:output"] = label_of[k]
+            if k == "outflow:linear":
+                if _target(proc) != "outlet":
+                    raise UnsupportedStructure("slow reservoir outflow must go to the outlet")
+                self._set("k_slow_1", slow_name, "response_factor", _params(proc)["response_factor"])
+            elif k == "overflow" and _target(proc) != "outlet":
+                raise UnsupportedStructure("slow reservoir overflow must go to the outlet")
+            elif k == "percolation:constant":
+                slow2_name = _target(proc)
+                pv = _params(proc)
+                self._set("percolation", slow_name, "percolation_rate", pv.get("percolation_rate", pv.get("rate", 0)))
+        if st.n_soil_stores == 2:
+            s2 = bricks.get(slow2_name)
+            if s2 is None or s2["kind"] != "storage" or _proc_kinds(s2) != ["outflow:linear"] or \
+                    _target(s2["processes"][0]) != "outlet" or _params(s2).get("capacity") is not None:
+                raise UnsupportedStructure("second soil store: expected storage with outflow:linear -> outlet")
+            self._set("k_slow_2", slow2_name, "response_factor", _params(s2["processes"][0])["response_factor"])
+            self.labels[f"{slow2_name}:water_content"] = "slow2_water"
+            self.labels[f"{slow2_name}:{s2['processes'][0]['name']}:output"] = "slow2_outflow"
+
+        # --- quick store
+        quick = bricks.get(quick_name)
+        if quick is None or quick["kind"] != "storage" or len(quick["processes"]) != 1 or \
+                _target(quick["processes"][0]) != "outlet" or _params(quick).get("capacity") is not None:
+            raise UnsupportedStructure("surface runoff store: expected one process to the outlet")
+        qp = quick["processes"][0]
+        if qp["kind"] == "runoff:socont":
+            st.quick_kind = _e.QUICK_SOCONT
+            self._set("quick", quick_name, "beta", _params(qp)["beta"])
+        elif qp["kind"] == "outflow:linear":
+            st.quick_kind = _e.QUICK_LINEAR
+            self._set("quick", quick_name, "response_factor", _params(qp)["response_factor"])
+        else:
+            raise UnsupportedStructure(f"surface runoff process {qp['kind']}")
+        self.labels[f"{quick_name}:water_content"] = "quick_water"
+        self.labels[f"{quick_name}:{qp['name']}:output"] = "quick_runoff"
+
+        known = {self.ground_name, gsp["name"], slow_name, quick_name}
+        if glacier is not None:
+            known |= {glacier["name"], snowpacks[1]}
+        if slow2_name:
+            known.add(slow2_name)
+        extra = set(bricks) - known
+        if extra:
+            raise UnsupportedStructure(f"bricks outside the Socont family: {sorted(extra)}")
+        for b in full["hydro_unit_bricks"]:
+            if b.get("forcing"):
+                raise UnsupportedStructure("brick-level forcing")
+        self.names = {"slow": slow_name, "slow2": slow2_name, "quick": quick_name}
+        self.hbk = st
+
+    # ------------------------------------------------------------------------------------------------
+    def assign_structure_variants(self, unit_land_covers):
+        """ModelBuilder::AssignHydroUnitStructures (ModelBuilder.cpp:36-97) -> glacier_variant flag per unit."""
+        out = []
+        ids = sorted(self.variant_covers)
+        for covers in unit_land_covers:
+            if len(ids) <= 1:
+                sid = ids[0]
+            else:
+                present = {n for n, f in covers if abs(f) > PRECISION}
+                sid = next((i for i in ids if self.variant_covers[i] == present), -1)
+                if sid < 0:
+                    sup = [(len(self.variant_covers[i]), i) for i in ids if self.variant_covers[i] >= present]
+                    if sup:
+                        sid = min(sup)[1]
+                    else:
+                        size = max(len(c) for c in self.variant_covers.values())
+                        sid = min(i for i in ids if len(self.variant_covers[i]) == size)
+            out.append(1 if sid == self.glacier_structure_id else 0)
+        return out
+
+    def parameter_vector(self, overrides=None):
+        """Parameter slots with optional {(component, name): value} overrides (SetParameterValue)."""
+        v = self.params.copy()
+        for (component, name), value in (overrides or {}).items():
+            for comp in [c.strip() for c in component.split(",")]:
+                v[self.resolve(comp, name)] = np.float32(value)
+        return v
+
+    def resolve(self, component, name):
+        if (component, name) in self.param_index:
+            return self.param_index[(component, name)]
+        raise KeyError(f"parameter {component}:{name} is not part of this structure")
+
+    def resolve_all(self, component, name):
+        """SettingsModel::SetParameterValue target resolution incl. 'type:' components and lists."""
+        slots = []
+        for comp in [c.strip() for c in component.split(",") if c.strip()]:
+            if comp.startswith("type:"):
+                kind = comp.split(":", 1)[1]
+                for st in self.structures:
+                    for b in st["hydro_unit_bricks"] + st["sub_basin_bricks"]:
+                        if b["kind"] == kind or (kind == "land_cover" and b["kind"] in ("generic_land_cover", "glacier")):
+                            if (b["name"], name) in self.param_index:
+                                slots.append(self.param_index[(b["name"], name)])
+            elif (comp, name) in self.param_index:
+                slots.append(self.param_index[(comp, name)])
+        return sorted(set(slots))
+
+    def record_slots(self, labels):
+        return [self.labels[label] for label in labels]
+
+
+def slope_m_per_m(value: float, unit: str) -> np.float32:
+    """HydroUnitProperty::GetValue(..., "m/m") + the float32 cast of HydroUnit::GetPropertyFloat
+    (HydroUnitProperty.cpp:19-49, HydroUnit.cpp:146-148)."""
+    if unit in ("m/m", "m_per_m"):
+        return np.float32(value)
+    if unit in ("degrees", "degree", "deg", "°"):
+        return np.float32(math.tan(value * 3.1415926535897932384626433832795 / 180.0))
+    raise ValueError(f"unsupported slope unit {unit!r}")
+
+
+def build_engine(structures, units, solver, n_steps, device=0, time_step_days=1.0):
+    """Compile + create an engine + upload the basin. `units` as in tests/golden (basin order)."""
+    cs = CompiledStructure(structures, solver, time_step_days)
+    eng = _e.Engine(cs.hbk, len(units), n_steps, device)
+    area = [u["area"] for u in units]
+    elev = [u.get("elevation", 0.0) for u in units]
+    slope = None
+    if cs.hbk.quick_kind == _e.QUICK_SOCONT:
+        slope = [slope_m_per_m(*u["slope"]) for u in units]
+    covers = [u["land_covers"] for u in units]
+    gv = cs.assign_structure_variants(covers)
+    fg = [dict(c).get(cs.ground_name, 1.0) for c in covers]
+    fgl = [dict(c).get(cs.glacier_name, 0.0) if cs.glacier_name else 0.0 for c in covers]
+    eng.set_units(area, elev, slope, gv, fg, fgl)
+    return cs, eng

@@ -1,0 +1,158 @@
+/* include/hbk.h — C-ABI of the B200-native batched simulation engine for hydrobricks.
+ *
+ * Drop-in scope: the per-time-step solve behind ModelHydro::Run() (reference
+ * core/src/base/ModelHydro.cpp:100-133 and callees) for Socont-family structures
+ * with the explicit solvers, batched over (parameter set x hydro unit). The reference has no FFI of
+ * its own for this path (its boundary is the pybind11 module core/bindings/Binding.cpp:308-360);
+ * each entry point below names the ModelHydro / SettingsModel member it replaces. The pybind11
+ * module `_hydrobricks` of this repo (hydrobricks_b200/csrc/hb_binding.cpp) re-implements those
+ * classes on top of this ABI; INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions: every call returns 0 on success or a negative HBK_E_* code; hbk_last_error() gives the
+ * message. Handles are opaque. All buffers are caller-owned HOST memory unless the name says `_dev`.
+ * One engine per CUDA device; an engine is not thread-safe, distinct engines are independent.
+ * There is NO CPU fallback: every call fails with HBK_E_CUDA when no CUDA device is usable.
+ */
+#ifndef HBK_H
+#define HBK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hbk_engine hbk_engine;
+
+enum { HBK_OK = 0, HBK_E_ARG = -1, HBK_E_CUDA = -2, HBK_E_STATE = -3, HBK_E_MODEL = -4, HBK_E_UNSUPPORTED = -5 };
+
+/* Solver::Factory names (core/src/base/Solver.cpp:42-64): euler_explicit, heun_explicit, rk4|runge_kutta */
+enum { HBK_SOLVER_EULER = 0, HBK_SOLVER_HEUN = 1, HBK_SOLVER_RK4 = 2 };
+/* surface_runoff brick process: runoff:socont (ProcessRunoffSocont.cpp:41-56) | outflow:linear */
+enum { HBK_QUICK_SOCONT = 0, HBK_QUICK_LINEAR = 1 };
+/* snow_rain_transition splitter: snow_rain:linear | snow_rain:threshold */
+enum { HBK_SPLIT_LINEAR = 0, HBK_SPLIT_THRESHOLD = 1 };
+/* order of the slow_reservoir processes = rate-vector layout (Processor.cpp:146-172) */
+enum { HBK_SLOW_ORDER_ET_OUT_OVF_PERC = 0 /* models/socont.py:171-190 */,
+       HBK_SLOW_ORDER_ET_OUT_PERC_OVF = 1 /* core/tests/src/helpers.cpp:74-86 */ };
+enum { HBK_VAR_PRECIPITATION = 0, HBK_VAR_TEMPERATURE = 1, HBK_VAR_PET = 2 };
+
+/* The per-structure process table for the Socont family, as the structure compiler
+ * (hydrobricks_b200/csrc/hb_host.cpp) derives it from a SettingsModel. */
+typedef struct {
+    int32_t solver;
+    int32_t n_soil_stores;            /* 1 | 2 (slow_reservoir [+ percolation -> slow_reservoir_2]) */
+    int32_t quick_kind;               /* HBK_QUICK_* */
+    int32_t slow_process_order;       /* HBK_SLOW_ORDER_* */
+    int32_t splitter_kind;            /* HBK_SPLIT_* */
+    int32_t has_glacier;              /* a structure variant with a glacier land cover exists */
+    int32_t glacier_infinite_storage; /* Glacier.cpp:21-33 */
+    int32_t glacier_no_melt_when_snow_cover;
+    double time_step_days;            /* TimeMachine time step in days */
+} hbk_structure;
+
+/* Parameter slots of one parameter set: float32 like the reference (Parameter.h:121). */
+enum {
+    HBK_P_TRANSITION_START = 0, /* snow_rain_transition:transition_start (or :threshold) */
+    HBK_P_TRANSITION_END,
+    HBK_P_RAIN_CORRECTION,
+    HBK_P_SNOW_CORRECTION,
+    HBK_P_GROUND_SNOW_DDF, /* <cover>_snowpack:degree_day_factor */
+    HBK_P_GROUND_SNOW_TMELT,
+    HBK_P_GLACIER_SNOW_DDF,
+    HBK_P_GLACIER_SNOW_TMELT,
+    HBK_P_ICE_DDF, /* glacier:degree_day_factor */
+    HBK_P_ICE_TMELT,
+    HBK_P_CAPACITY,   /* slow_reservoir:capacity (A) */
+    HBK_P_K_SLOW_1,   /* slow_reservoir:response_factor */
+    HBK_P_PERCOLATION,/* slow_reservoir:percolation_rate */
+    HBK_P_K_SLOW_2,   /* slow_reservoir_2:response_factor */
+    HBK_P_QUICK,      /* surface_runoff:beta or :response_factor */
+    HBK_P_K_SNOW,     /* glacier_area_rain_snowmelt_storage:response_factor */
+    HBK_P_K_ICE,      /* glacier_area_icemelt_storage:response_factor */
+    HBK_N_PARAMS
+};
+
+/* Recorder slots = hydro-unit log labels (SettingsModel.cpp:808-841, Logger.cpp:93-120). */
+enum {
+    HBK_R_GROUND_WATER = 0, HBK_R_GROUND_INFILTRATION, HBK_R_GROUND_RUNOFF,
+    HBK_R_GLACIER_WATER, HBK_R_GLACIER_ICE, HBK_R_GLACIER_OUTFLOW, HBK_R_GLACIER_MELT,
+    HBK_R_GROUND_SNOWPACK_WATER, HBK_R_GROUND_SNOWPACK_SNOW, HBK_R_GROUND_SNOWPACK_MELT,
+    HBK_R_GLACIER_SNOWPACK_WATER, HBK_R_GLACIER_SNOWPACK_SNOW, HBK_R_GLACIER_SNOWPACK_MELT,
+    HBK_R_SLOW_WATER, HBK_R_SLOW_ET, HBK_R_SLOW_OUTFLOW, HBK_R_SLOW_OVERFLOW, HBK_R_SLOW_PERCOLATION,
+    HBK_R_SLOW2_WATER, HBK_R_SLOW2_OUTFLOW,
+    HBK_R_QUICK_WATER, HBK_R_QUICK_RUNOFF,
+    HBK_N_RECORDS
+};
+
+/* Storages that can be given an initial content / read back (WaterContainer::SetInitialState). */
+enum {
+    HBK_S_GROUND_SNOW = 0, HBK_S_GLACIER_SNOW, HBK_S_GROUND_WATER, HBK_S_GLACIER_WATER, HBK_S_ICE,
+    HBK_S_SLOW, HBK_S_SLOW2, HBK_S_QUICK,
+    HBK_S_AMT_INFILTRATION, HBK_S_AMT_REST, HBK_S_AMT_MELT_GROUND, HBK_S_AMT_MELT_GLACIER,
+    HBK_S_AMT_DEPOSIT_RAIN_SNOWMELT, HBK_S_AMT_DEPOSIT_ICEMELT,
+    HBK_N_STATES
+};
+
+/* ModelHydro::InitializeWithBasin (ModelHydro.cpp:20-74): structure + time axis. */
+int hbk_engine_create(const hbk_structure* structure, int32_t n_units, int32_t n_steps, int32_t device,
+                      hbk_engine** out);
+void hbk_engine_destroy(hbk_engine* e);
+const char* hbk_last_error(const hbk_engine* e);
+
+/* SubBasin::BuildBasin + AssignFractions (SubBasin.cpp:28-101), units in basin order.
+ * slope: float(tan(deg*pi/180)) as HydroUnit::GetPropertyFloat returns it (HydroUnit.cpp:146-148);
+ * may be NULL when quick_kind is linear. glacier_variant[u] != 0: the unit was assigned the structure
+ * variant that carries the glacier bricks (ModelBuilder.cpp:36-97). fractions: land-cover area fractions. */
+int hbk_set_units(hbk_engine* e, const double* area_m2, const double* elevation_m, const float* slope_m_per_m,
+                  const int32_t* glacier_variant, const double* fraction_ground, const double* fraction_glacier);
+
+/* SettingsModel::SetParameterValue + ModelHydro::UpdateParameters (ModelHydro.cpp:76-84), batched:
+ * values[n_sets][HBK_N_PARAMS] float32. */
+int hbk_set_parameters(hbk_engine* e, int32_t n_sets, const float* values);
+
+/* ModelHydro::CreateTimeSeries + AttachTimeSeriesToHydroUnits (ModelHydro.cpp:306-346):
+ * data[n_steps][n_units] float64, columns in basin order, shared by all parameter sets. */
+int hbk_set_forcing(hbk_engine* e, int32_t variable, const double* data);
+
+/* Fused forcing spatialisation (python forcing.py:1061-1113): station series[n_steps]; per unit
+ *   temperature: x + g*(z - z_ref)/100;  precipitation: max(0, (x*corr) * (1 + g*(z - z_ref)/100));
+ *   pet: x.   gradient / correction may be per parameter set ([n_sets], NULL -> scalar). */
+int hbk_set_station_forcing(hbk_engine* e, int32_t variable, const double* series, double ref_elevation,
+                            double gradient, const double* gradient_per_set, double correction,
+                            const double* correction_per_set);
+
+/* WaterContainer::SetInitialState for every (set, unit): values[n_units] broadcast over sets, NULL = 0. */
+int hbk_set_initial_state(hbk_engine* e, int32_t state_slot, const double* values);
+/* ModelHydro::SaveAsInitialState (ModelHydro.cpp:195-197): end-of-run contents become the initial state. */
+int hbk_save_as_initial_state(hbk_engine* e);
+/* SettingsModel::SetSpinupDays (ModelHydro.cpp:48-53, 135-181). */
+int hbk_set_spinup_steps(hbk_engine* e, int32_t n_steps);
+/* Selective recorder: bit i of mask = HBK_R_* slot i (Logger.cpp:93-120). Memory = popcount*P*T*U*8 B. */
+int hbk_set_record_mask(hbk_engine* e, uint64_t mask);
+
+/* ModelHydro::Reset + Run (ModelHydro.cpp:100-133, 183-193) for all parameter sets. */
+int hbk_run(hbk_engine* e);
+
+/* ModelHydro::GetOutletDischarge (ModelHydro.cpp:203-205): out[n_sets][n_steps]. */
+int hbk_get_outlet(hbk_engine* e, int32_t first_set, int32_t n_sets, double* out);
+/* ModelHydro::GetHydroUnitValues(label) (ModelHydro.cpp:227-236) for one set: out[n_steps][n_units];
+ * NaN where the unit's structure variant has no such brick. */
+int hbk_get_recorded(hbk_engine* e, int32_t record_slot, int32_t set, double* out);
+/* End-of-run storage contents: out[n_sets][n_units]. */
+int hbk_get_state(hbk_engine* e, int32_t state_slot, double* out);
+/* Sub-basin stores (glacier_area_*_storage) end-of-run contents: out[n_sets][2]. */
+int hbk_get_basin_state(hbk_engine* e, double* out);
+
+/* Device-resident access for callers that keep data on the GPU (bench `value`, multi-GPU gather):
+ * pointer to outlet[n_sets][ld] float64 and its leading dimension. */
+int hbk_outlet_dev(hbk_engine* e, const double** ptr, int64_t* ld);
+/* Device time of the last hbk_run (CUDA events on the engine's stream), and kernel launch count. */
+int hbk_last_run_stats(hbk_engine* e, double* kernel_ms, int32_t* n_launches, int64_t* unconverged_sweeps);
+/* Raw CUDA stream handle (cudaStream_t) the engine launches on, for callers timing with events. */
+void* hbk_stream(hbk_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HBK_H */
