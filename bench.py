@@ -1,0 +1,460 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path: Socont RK4 calibration ensemble (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            this repo's engine (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU implementation of the path
+                                                             (oracle/_ref = unmodified core compiled here, else the
+                                                             oracle port) on all host cores, rank 0 only
+
+A "step" = one pass of the hot path over one batch: ModelHydro::Run() for P parameter sets x U hydro units x T
+daily steps (engine: one hbk_run). metric = HRU*timesteps/s (whole job, all ranks); evals_per_s = parameter
+sets/s. Workload: P=100000 random parameter sets in the reference ranges, U=50 elevation
+bands with slopes, T=10957 (1981-2010), Socont 1 soil store + runoff:socont, station forcing with elevation
+gradients. Scaling is weak: every rank integrates its own P sets (parameter axis sharded, no communication on
+the hot path; one NCCL all_gather of per-set scores per step).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+U_DEFAULT, T_DEFAULT, P_DEFAULT = 50, 10957, 100000
+START, END = "1981-01-01", "2010-12-31"
+# Executed FP64 work of the dominant kernel per HRU*timestep, from the ncu instruction-mix capture of this same
+# workload (profiles/): flops = DADD + DMUL + 2*DFMA thread instructions / (P*U*T). Updated per round.
+FP64_FLOPS_PER_HRU_STEP = 1000.0
+FP64_FLOPS_SOURCE = "provisional hand count (SURVEY.md §8d: 600-900 FP64 instr); replaced by ncu instruction mix"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# synthetic workload
+# ---------------------------------------------------------------------------------------------------------
+def station_series(T, seed=42):
+    rng = np.random.Generator(np.random.MT19937(seed))
+    t = np.arange(T, dtype=np.float64)
+    doy = np.fmod(t, 365.25) / 365.25
+    u1, u2, u3 = rng.random(T), rng.random(T), rng.random(T)
+    temp = 5 - 12 * np.cos(2 * np.pi * doy) + 4 * (u1 - 0.5)
+    precip = np.where(u2 < 0.4, -8 * np.log(1 - u3), 0.0)
+    pet = np.maximum(0.0, 2 - 2 * np.cos(2 * np.pi * doy))
+    return precip, temp, pet
+
+
+def hydro_units(U, seed=43):
+    rng = np.random.Generator(np.random.MT19937(seed))
+    step = 2400.0 / U
+    elev = 800 + step * (np.arange(U) + 0.5)
+    slope = rng.uniform(5, 35, U)
+    return [{"id": i + 1, "area": 1.0e6, "elevation": float(elev[i]), "slope": (float(slope[i]), "deg"),
+             "land_covers": [("ground", 1.0)]} for i in range(U)]
+
+
+def parameter_sets(P, seed=44):
+    """Uniform in the reference ranges (parameters.py:66-174, 736-738), transition_start < transition_end."""
+    rng = np.random.Generator(np.random.MT19937(seed))
+    t0 = rng.uniform(-2, 2, P)
+    t1 = rng.uniform(0, 4, P)
+    bad = t0 >= t1
+    while bad.any():
+        t0[bad], t1[bad] = rng.uniform(-2, 2, bad.sum()), rng.uniform(0, 4, bad.sum())
+        bad = t0 >= t1
+    return {"a_snow": rng.uniform(2, 20, P), "A": rng.uniform(0, 3000, P), "k_slow_1": rng.uniform(1e-4, 1, P),
+            "beta": rng.uniform(100, 30000, P), "prec_t_start": t0, "prec_t_end": t1}
+
+
+SPATIAL = {"zref": 1250.0, "grad_t": -0.6, "grad_p": 0.05}
+
+
+def spatialise(units, precip, temp, pet):
+    """forcing.py:1061-1113 in numpy: the pre-spatialised [T x U] arrays the reference core is given."""
+    z = np.array([u["elevation"] for u in units])
+    t2 = temp[:, None] + SPATIAL["grad_t"] * (z - SPATIAL["zref"]) / 100
+    p2 = precip[:, None] * (1 + SPATIAL["grad_p"] * (z - SPATIAL["zref"]) / 100)
+    p2[p2 < 0] = 0
+    e2 = np.repeat(pet[:, None], len(z), axis=1)
+    return p2, t2, e2
+
+
+def mjd_axis(T):
+    return np.arange(T, dtype=np.float64) + 44605.0  # 1981-01-01
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation on all host cores
+# ---------------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _load_ref_backend():
+    cands = sorted((ROOT / "oracle" / "_ref").glob("_hydrobricks*.so"))
+    if not cands:
+        return None
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_hydrobricks", cands[0])
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _ref_worker_init(U, T):
+    from hydrobricks_b200 import models
+
+    ref = _load_ref_backend()
+    units = hydro_units(U)
+    precip, temp, pet = station_series(T)
+    if ref is not None:
+        ref.init()
+        try:
+            ref.set_message_log_level()
+        except Exception:
+            pass
+        m = models.Socont(solver="rk4", soil_storage_nb=1, surface_runoff="socont_runoff",
+                          land_cover_names=["ground"], land_cover_types=["ground"], backend=ref)
+        m.setup(units, START, "2010-12-31" if T == T_DEFAULT else str(np.datetime64(START) + np.timedelta64(T - 1, "D")))
+        p2, t2, e2 = spatialise(m.units, precip, temp, pet)
+        m.set_forcing(mjd_axis(T), p2, t2, e2)
+        _W["kind"], _W["model"] = "reference", m
+    else:  # oracle port (the restatement) when the compiled reference did not travel
+        from hydrobricks_b200 import _hydrobricks as mirror
+        from oracle import hb_oracle
+
+        m = models.Socont(solver="rk4", soil_storage_nb=1, surface_runoff="socont_runoff",
+                          land_cover_names=["ground"], land_cover_types=["ground"], backend=mirror)
+        m.units = sorted(units, key=lambda u: -u["elevation"])
+        _W["kind"], _W["model"], _W["oracle"] = "port", m, hb_oracle
+        _W["forcing"] = spatialise(m.units, precip, temp, pet)
+    _W["T"], _W["U"] = T, U
+
+
+def _ref_worker_run(sets):
+    m, T = _W["model"], _W["T"]
+    t_run = 0.0
+    q = np.zeros(1)
+    for values in sets:
+        if _W["kind"] == "reference":
+            m.set_parameters(values)
+            m.model.reset()
+            t0 = time.perf_counter()
+            m.model.run()
+            t_run += time.perf_counter() - t0
+            q = m.model.get_outlet_discharge()
+        else:
+            for alias, v in values.items():
+                comp, name = m.aliases[alias]
+                m.settings.set_parameter_value(comp, name, v)
+            om = _W["oracle"].OracleModel(m.settings.get_structure(), m.units, "rk4", T)
+            for k, v in zip(("precipitation", "temperature", "pet"), _W["forcing"]):
+                om.set_forcing(k, v)
+            t0 = time.perf_counter()
+            q = om.run()
+            t_run += time.perf_counter() - t0
+    return t_run, float(np.sum(q))
+
+
+def run_reference_arm(args, sets_per_core=None, quiet=False):
+    import multiprocessing as mp
+
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    U, T = args.units, args.timesteps
+    n_per_core = sets_per_core or args.ref_sets_per_core
+    ps = parameter_sets(cores * n_per_core * (args.steps + args.warmup) + 1)
+    chunks = []
+    k = 0
+    for _ in range(args.steps + args.warmup):
+        step = []
+        for _c in range(cores):
+            step.append([{a: float(ps[a][k + j]) for a in ps} for j in range(n_per_core)])
+            k += n_per_core
+        chunks.append(step)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_ref_worker_init, initargs=(U, T)) as pool:
+        pool.map(_ref_worker_run, [[] for _ in range(cores)])  # make sure every worker is initialised
+        times = []
+        kind = "reference" if _load_ref_backend() is not None else "port"
+        for i, step in enumerate(chunks):
+            t0 = time.perf_counter()
+            res = pool.map(_ref_worker_run, step, chunksize=1)
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                times.append((dt, max(r[0] for r in res)))
+    wall = sum(t[0] for t in times)
+    n_sets = cores * n_per_core * len(times)
+    value = n_sets * U * T / wall
+    line = {
+        "metric": "hru_timesteps_per_s", "value": value, "unit": "HRU*timesteps/s", "impl": "reference",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "evals_per_s": n_sets / wall,
+        "config": {"workload": "C2 Socont-RK4 calibration ensemble (bounded CPU sample)", "sets_per_step": cores * n_per_core,
+                   "hydro_units": U, "timesteps": T, "solver": "rk4", "structure": "socont 1 soil store, runoff:socont",
+                   "forcing": "pre-spatialised per-unit series (station + elevation gradients)"},
+        "cpu_baseline": {"value": value, "unit": "HRU*timesteps/s", "cores": cores, "kind": kind,
+                         "sample": f"{cores * n_per_core} parameter sets per step ({n_per_core} per core) x {U} units x "
+                                   f"{T} steps, one model instance per core, wall time incl. parameter update"},
+        "e2e": {"value": value, "unit": "HRU*timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    if not quiet:
+        print(json.dumps(line), flush=True)
+    return line
+
+
+# ---------------------------------------------------------------------------------------------------------
+# engine arm
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 8 and r[4 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+class DeviceArray:
+    """Zero-copy view of engine-owned device memory for torch (CUDA array interface)."""
+
+    def __init__(self, ptr, shape, strides):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f8", "data": (ptr, False), "version": 3,
+                                         "strides": strides}
+
+
+def run_engine_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from hydrobricks_b200 import engine as hbk_engine
+    from hydrobricks_b200 import models
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1 (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (engine arm) needs a CUDA device; there is no CPU fallback")
+
+    # cpu_baseline: rank 0, N=1 only, in a child process BEFORE this process touches CUDA
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                              "--units", str(args.units), "--timesteps", str(args.timesteps),
+                              "--ref-sets-per-core", str(args.ref_sets_per_core)], capture_output=True, text=True)
+        for ln in out.stdout.splitlines():
+            if ln.startswith("{"):
+                cpu_baseline = json.loads(ln)["cpu_baseline"]
+        if cpu_baseline is None:
+            cpu_baseline = {"value": None, "unit": "HRU*timesteps/s", "cores": 0, "kind": "port",
+                            "sample": "failed: " + out.stderr[-300:]}
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    P, U, T = args.sets, args.units, args.timesteps
+    units = hydro_units(U)
+    precip, temp, pet = station_series(T)
+    ps = parameter_sets(P, seed=44 + rank)  # every rank its own shard of the ensemble (weak scaling)
+
+    m = models.Socont(solver="rk4", soil_storage_nb=1, surface_runoff="socont_runoff", land_cover_names=["ground"],
+                      land_cover_types=["ground"])
+    end = END if T == T_DEFAULT else str(np.datetime64(START) + np.timedelta64(T - 1, "D"))
+    m.setup(units, START, end, device=local)
+    matrix = m.parameter_matrix(ps, P)
+    eng = m.model._engine
+
+    # pinned host staging: the step's inputs and its result
+    pin_params = torch.from_numpy(matrix).pin_memory()
+    pin_forcing = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in (precip, temp, pet)]
+    pin_out = torch.empty((P, T), dtype=torch.float64).pin_memory()
+    out_ptr = ctypes.cast(pin_out.data_ptr(), ctypes.POINTER(ctypes.c_double))
+
+    def upload():
+        eng.set_parameters(pin_params.numpy())
+        eng.set_station_forcing("precipitation", pin_forcing[0].numpy(), SPATIAL["zref"], SPATIAL["grad_p"], 1.0)
+        eng.set_station_forcing("temperature", pin_forcing[1].numpy(), SPATIAL["zref"], SPATIAL["grad_t"], 1.0)
+        eng.set_station_forcing("pet", pin_forcing[2].numpy())
+
+    upload()
+    stream = torch.cuda.ExternalStream(eng.stream())
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
+    scores_all = torch.empty(world * P, dtype=torch.float64, device="cuda") if world > 1 else None
+
+    def scores():
+        ptr, ld = eng.outlet_device_pointer()
+        q = torch.as_tensor(DeviceArray(ptr, (P, T), (ld * 8, 8)), device="cuda")
+        s = q.mean(dim=1)
+        if world > 1:  # the only collective of the job: final gather of the per-set scores
+            dist.all_gather_into_tensor(scores_all, s)
+        return s
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def resident_step():
+        eng.run()
+        scores()
+
+    def e2e_step():
+        upload()
+        eng.run()
+        eng._check(eng.L.hbk_get_outlet(eng.h, 0, P, out_ptr))
+
+    peak_fp64 = hbk_engine.measure_fp64_peak(local)
+
+    # ---- resident (value) ----
+    for _ in range(args.warmup):
+        resident_step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    kernel_ms, launches = [], 0
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations (256 MiB write > 126 MB L2), outside the step's events
+        torch.cuda.synchronize()
+        ev[i][0].record(stream)
+        resident_step()
+        ev[i][1].record(stream)
+        st = eng.last_run_stats()
+        kernel_ms.append(st["kernel_ms"])
+        launches += st["launches"]
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([dev_ms, wall * 1e3, sum(kernel_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms, kern_ms = t.tolist()
+    units_done = world * P * U * T * args.steps
+    value = units_done / (dev_ms * 1e-3)
+
+    # ---- end to end: pinned host inputs -> device -> run -> full outlet back to pinned host ----
+    for _ in range(min(args.warmup, 1)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = units_done / t.item()
+    h2d = pin_params.numel() * 4 + sum(x.numel() * 8 for x in pin_forcing)
+    d2h = P * T * 8
+
+    if rank == 0:
+        main_ms = kern_ms / args.steps  # device time of one hbk_run (state reset + unit kernel), CUDA events
+        flops = FP64_FLOPS_PER_HRU_STEP * P * U * T
+        achieved = flops / (main_ms * 1e-3) / 1e12
+        hbm_bytes = P * T * 8 + 3 * T * 8 + P * hbk_engine.N_PARAMS * 4
+        try:
+            hbm_peak = json.load(open(ROOT / "MEASURED_PEAKS.json"))["hbm_gbs"]
+            hbm_src = "MEASURED_PEAKS.json"
+        except Exception:
+            hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+        line = {
+            "metric": "hru_timesteps_per_s", "value": value, "unit": "HRU*timesteps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "evals_per_s": world * P * args.steps / (dev_ms * 1e-3),
+            "config": {"workload": "C2 Socont-RK4 calibration ensemble", "sets_per_gpu": P, "hydro_units": U,
+                       "timesteps": T, "solver": "rk4", "structure": "socont 1 soil store, runoff:socont",
+                       "forcing": "station series + fused elevation-gradient spatialisation",
+                       "l2": "256 MiB flush between timed iterations; per-step output 8.8 GB >> L2",
+                       "block_shape": {"PB": 32 if P >= 32 else None, "threads": 256}},
+            "wall_ms_per_step": wall_ms / args.steps,
+            "e2e": {"value": e2e_value, "unit": "HRU*timesteps/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "note": "pinned host params+station series -> device, run, full "
+                    "outlet[P x T] -> pinned host, through the C-ABI"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_fp64, "unit": "TFLOP/s",
+                         "frac": achieved / peak_fp64 if peak_fp64 else None, "traffic": None,
+                         "kernel": "hbkRunUnits<RK4,1 soil store,no glacier>", "kernel_ms": main_ms,
+                         "flops_per_hru_step": FP64_FLOPS_PER_HRU_STEP, "flops_source": FP64_FLOPS_SOURCE,
+                         "peak_source": "DFMA micro-benchmark measured in this run (hbk_measure_fp64_peak); "
+                                        "MEASURED_PEAKS.json has no FP64 figure",
+                         "note": "not a dense contraction: neither HBM nor tensor binds, the FP64 pipe does "
+                                 "(SURVEY.md §8d); the HBM fraction is listed for completeness",
+                         "hbm": {"achieved": hbm_bytes / (main_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": hbm_bytes / (main_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                                 "algorithmic_bytes_per_launch": int(hbm_bytes)}},
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sets", type=int, default=P_DEFAULT, help="parameter sets per GPU")
+    ap.add_argument("--units", type=int, default=U_DEFAULT)
+    ap.add_argument("--timesteps", type=int, default=T_DEFAULT)
+    ap.add_argument("--ref-sets-per-core", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        run_reference_arm(args)
+    else:
+        run_engine_arm(args)
+
+
+if __name__ == "__main__":
+    main()

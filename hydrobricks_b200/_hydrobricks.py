@@ -1,0 +1,769 @@
+"""Host-side mirror of the reference's `_hydrobricks` extension module (core/bindings/Binding.cpp:164-413)
+for the ModelHydro::Run() hot path, on top of the C-ABI of include/hbk.h.
+
+Same class names, method names, argument meaning and error behaviour as the pybind11 module the
+reference Python layer imports (`from hydrobricks._hydrobricks import ModelHydro, ...`,
+python/src/hydrobricks/models/model.py:13), so `hb.models.Socont(...).setup/run/get_outlet_discharge` work
+unchanged with this module injected as `hydrobricks._hydrobricks` (tools/refpy.py, backend "b200").
+Batched extras the reference does not have: ModelHydro.run_batch / get_outlet_discharge_batch.
+
+SettingsModel / SettingsBasin are declarative (cold path); ModelHydro.init_with_basin compiles them with
+structure.CompiledStructure and creates the CUDA engine. Structures outside the Socont family raise
+ValueError there — nothing is ever computed on the CPU.
+"""
+from __future__ import annotations
+
+import copy
+
+import numpy as np
+
+from . import engine as _engine
+from . import structure as _structure
+
+_FORCING_NAMES = {"precipitation", "pet", "temperature", "temperature_min", "temperature_max", "solar_radiation",
+                  "r_solar"}
+
+# Process::RegisterSettings of the reference (core/src/processes/Process*.cpp RegisterProcessSettings):
+# default parameters and forcing of every process type the engine runs.
+_PROCESS_REGISTRY = {
+    "melt:degree_day": ([("degree_day_factor", 3.0), ("melting_temperature", 0.0)], ["temperature"]),
+    "et:socont": ([], ["pet"]),
+    "infiltration:socont": ([], []),
+    "runoff:socont": ([("beta", 500.0)], []),
+    "outflow:linear": ([("response_factor", 0.2)], []),
+    "outflow:direct": ([], []),
+    "outflow:rest": ([], []),
+    "overflow": ([], []),
+    "outflow:overflow": ([], []),
+    "percolation:constant": ([("percolation_rate", 0.1)], []),
+}
+
+_log_level = "message"
+
+
+def init():
+    """InitHydrobricksForPython (Utils.h:16)."""
+    return True
+
+
+def init_log(path):
+    return None
+
+
+def close_log():
+    return None
+
+
+def set_max_log_level():
+    global _log_level
+    _log_level = "max"
+
+
+def set_debug_log_level():
+    global _log_level
+    _log_level = "debug"
+
+
+def set_message_log_level():
+    global _log_level
+    _log_level = "message"
+
+
+class LogNull:
+    pass
+
+
+class Parameter:
+    """base/Parameter.h: name + float32 value."""
+
+    def __init__(self, name, value):
+        self.name = name
+        self.value = float(np.float32(value))
+
+    def get_name(self):
+        return self.name
+
+    def set_name(self, name):
+        self.name = name
+
+    def get_value(self):
+        return self.value
+
+    def set_value(self, value):
+        self.value = float(np.float32(value))
+
+    def __repr__(self):
+        return f"<_hydrobricks.Parameter named '{self.name}'>"
+
+
+def _param(name, value):
+    return {"name": name, "value": float(np.float32(value))}
+
+
+class SettingsModel:
+    """base/SettingsModel.{h,cpp}: select-then-add builder of the model structure."""
+
+    def __init__(self):
+        self._log_all = False
+        self._record_fractions = False
+        self._structures = [self._new_structure(1)]
+        self._sel_structure = self._structures[0]
+        self._sel_brick = None
+        self._sel_process = None
+        self._sel_splitter = None
+        self.solver = ""
+        self.timer = {"start": "", "end": "", "time_step": 1, "time_step_unit": "", "spinup_days": 0}
+
+    @staticmethod
+    def _new_structure(sid):
+        return {"id": sid, "log_items": [], "hydro_unit_bricks": [], "sub_basin_bricks": [],
+                "hydro_unit_splitters": [], "sub_basin_splitters": []}
+
+    # -- options -------------------------------------------------------------------------------------
+    def log_all(self, log_all=True):
+        self._log_all = bool(log_all)
+
+    def record_fractions(self, record=True):
+        self._record_fractions = bool(record)
+
+    def set_solver(self, name):
+        self.solver = name
+
+    def set_timer(self, start_date, end_date, time_step, time_step_unit):
+        self.timer.update(start=start_date, end=end_date, time_step=int(time_step), time_step_unit=time_step_unit)
+
+    def set_spinup_days(self, days):
+        if days < 0:
+            raise ValueError("The spin-up duration cannot be negative.")  # SettingsModel.cpp:38-43
+        self.timer["spinup_days"] = int(days)
+
+    def get_solver_name(self):
+        return self.solver
+
+    def get_timer(self):
+        return dict(self.timer)
+
+    # -- structures ----------------------------------------------------------------------------------
+    def add_structure(self):
+        sid = max(s["id"] for s in self._structures) + 1
+        self._structures.append(self._new_structure(sid))
+        self._sel_structure = self._structures[-1]
+        self._sel_brick = self._sel_process = self._sel_splitter = None
+        return sid
+
+    def select_structure(self, sid):
+        for s in self._structures:
+            if s["id"] == sid:
+                self._sel_structure = s
+                self._sel_brick = s["hydro_unit_bricks"][0] if s["hydro_unit_bricks"] else None
+                return True
+        return False
+
+    # -- bricks --------------------------------------------------------------------------------------
+    def _add_brick(self, where, name, kind, attach):
+        brick = {"name": name, "kind": kind, "parent": None, "attach": attach, "computed_directly": False,
+                 "is_land_cover": False, "is_surface_component": False, "forcing": [], "parameters": [],
+                 "log_items": [], "processes": []}
+        self._sel_structure[where].append(brick)
+        self._sel_brick = brick
+        if self._log_all:  # SettingsModel.cpp:55-62
+            self.add_brick_logging("water_content")
+            if kind == "glacier":
+                self.add_brick_logging("ice_content")
+            elif kind == "snowpack":
+                self.add_brick_logging("snow_content")
+        return brick
+
+    def add_hydro_unit_brick(self, name, kind="storage"):
+        self._add_brick("hydro_unit_bricks", name, kind, "hydro_unit")
+
+    def add_sub_basin_brick(self, name, kind="storage"):
+        self._add_brick("sub_basin_bricks", name, kind, "sub_basin")
+
+    def add_land_cover_brick(self, name, kind):
+        brick = self._add_brick("hydro_unit_bricks", name, kind, "hydro_unit")
+        brick["is_land_cover"] = True
+        if self._select_splitter_if_found("rain_splitter"):  # SettingsModel.cpp:85-94
+            self._add_splitter_output(name)
+
+    def _add_surface_component_brick(self, name, kind):
+        brick = self._add_brick("hydro_unit_bricks", name, kind, "hydro_unit")
+        brick["is_surface_component"] = True
+
+    def select_hydro_unit_brick(self, name):
+        for b in self._sel_structure["hydro_unit_bricks"]:
+            if b["name"] == name:
+                self._sel_brick, self._sel_process = b, None
+                return
+        raise RuntimeError(f"The hydro unit brick '{name}' was not found")
+
+    def add_brick_parameter(self, name, value, kind="constant"):
+        if kind != "constant":
+            raise NotImplementedError(f"SettingsModel::AddBrickParameter - Parameter type '{kind}' not supported")
+        self._sel_brick["parameters"].append(_param(name, value))
+
+    def add_brick_forcing(self, name):
+        if name not in _FORCING_NAMES:
+            raise ValueError(f"The provided forcing '{name}' is not yet supported.")
+        self._sel_brick["forcing"].append(name)
+
+    def set_current_brick_computed_directly(self):
+        self._sel_brick["computed_directly"] = True
+
+    def add_brick_logging(self, name):
+        if name not in self._sel_brick["log_items"]:
+            self._sel_brick["log_items"].append(name)
+
+    def add_logging_to(self, name):
+        if name not in self._sel_structure["log_items"]:
+            self._sel_structure["log_items"].append(name)
+
+    # -- processes -----------------------------------------------------------------------------------
+    def add_brick_process(self, name, kind, target="", log=False):
+        if kind not in _PROCESS_REGISTRY:
+            raise RuntimeError(
+                f"Process type '{kind}' is not available in the B200 engine (Socont family only: "
+                f"{', '.join(sorted(_PROCESS_REGISTRY))}).")
+        proc = {"name": name, "kind": kind, "forcing": [], "outputs": [], "parameters": [], "log_items": []}
+        self._sel_brick["processes"].append(proc)
+        self._sel_process = proc
+        if target:
+            if ":" in target:  # "brick:content" (SettingsModel.cpp:186-193)
+                tgt, flux_type = target.split(":", 1)
+                self.add_process_output(tgt, flux_type)
+            else:
+                self.add_process_output(target)
+        if (log or self._log_all) and "transport:" not in kind:
+            self.add_process_logging("output")
+        params, forcing = _PROCESS_REGISTRY[kind]
+        for pname, pvalue in params:
+            self.add_process_parameter(pname, pvalue)
+        for f in forcing:
+            self.add_process_forcing(f)
+
+    def select_process(self, name):
+        for p in self._sel_brick["processes"]:
+            if p["name"] == name:
+                self._sel_process = p
+                return
+        raise RuntimeError(f"The process '{name}' was not found.")
+
+    def add_process_output(self, target, flux_type="water"):
+        self._sel_process["outputs"].append({"target": target, "flux_type": flux_type, "instantaneous": False,
+                                             "static": False})
+
+    def add_process_parameter(self, name, value, kind="constant"):
+        if kind != "constant":
+            raise NotImplementedError(f"SettingsModel::AddProcessParameter - Parameter type '{kind}' not supported")
+        for p in self._sel_process["parameters"]:
+            if p["name"] == name:
+                p["value"] = float(np.float32(value))
+                return
+        self._sel_process["parameters"].append(_param(name, value))
+
+    def set_process_parameter_value(self, name, value, kind="constant"):
+        for p in self._sel_process["parameters"]:
+            if p["name"] == name:
+                p["value"] = float(np.float32(value))
+                return
+        raise RuntimeError(f"SettingsModel::SetProcessParameterValue - Parameter '{name}' not found")
+
+    def add_process_forcing(self, name):
+        if name not in _FORCING_NAMES:
+            raise ValueError(f"The provided forcing '{name}' is not yet supported.")
+        self._sel_process["forcing"].append(name)
+
+    def add_process_logging(self, name):
+        if name not in self._sel_process["log_items"]:
+            self._sel_process["log_items"].append(name)
+
+    def set_process_outputs_as_instantaneous(self):
+        for o in self._sel_process["outputs"]:
+            o["instantaneous"] = True
+
+    def set_process_outputs_as_static(self):
+        for o in self._sel_process["outputs"]:
+            o["static"] = True
+
+    # -- splitters -----------------------------------------------------------------------------------
+    def _add_hydro_unit_splitter(self, name, kind):
+        s = {"name": name, "kind": kind, "attach": "hydro_unit", "forcing": [], "outputs": [], "parameters": [],
+             "log_items": []}
+        self._sel_structure["hydro_unit_splitters"].append(s)
+        self._sel_splitter = s
+
+    def _select_splitter_if_found(self, name):
+        for s in self._sel_structure["hydro_unit_splitters"]:
+            if s["name"] == name:
+                self._sel_splitter = s
+                return True
+        return False
+
+    def _add_splitter_output(self, target, flux_type="water"):
+        self._sel_splitter["outputs"].append({"target": target, "flux_type": flux_type, "instantaneous": False,
+                                              "static": False})
+
+    def generate_precipitation_splitters(self, with_snow=True, splitter_type="snow_rain:linear"):
+        """SettingsModel::GeneratePrecipitationSplitters (SettingsModel.cpp:491-530)."""
+        if not with_snow:
+            raise RuntimeError("The B200 engine needs the snow routine (with_snow=True) of the Socont family.")
+        if splitter_type not in ("snow_rain:linear", "snow_rain:threshold"):
+            raise RuntimeError(f"Splitter type '{splitter_type}' is not available in the B200 engine.")
+        self._add_hydro_unit_splitter("snow_rain_transition", splitter_type)
+        self._sel_splitter["forcing"] += ["precipitation", "temperature"]
+        self._add_splitter_output("rain_splitter")
+        self._add_splitter_output("snow_splitter", "snow")
+        if splitter_type == "snow_rain:threshold":
+            self._sel_splitter["parameters"].append(_param("threshold", 0.0))
+        else:
+            self._sel_splitter["parameters"].append(_param("transition_start", 0.0))
+            self._sel_splitter["parameters"].append(_param("transition_end", 2.0))
+        self._sel_splitter["parameters"].append(_param("rain_correction_factor", 1.0))
+        self._sel_splitter["parameters"].append(_param("snow_correction_factor", 1.0))
+        self._add_hydro_unit_splitter("snow_splitter", "multi_fluxes")
+        self._add_hydro_unit_splitter("rain_splitter", "multi_fluxes")
+
+    def generate_snowpacks(self, snow_melt_process):
+        """SettingsModel::GenerateSnowpacks (SettingsModel.cpp:532-545)."""
+        covers = [b["name"] for b in self._sel_structure["hydro_unit_bricks"] if b["is_land_cover"]]
+        for cover in covers:
+            if not self._select_splitter_if_found("snow_splitter"):
+                raise RuntimeError("The hydro unit splitter 'snow_splitter' was not found")
+            self._add_splitter_output(cover + "_snowpack", "snow")
+            self._add_surface_component_brick(cover + "_snowpack", "snowpack")
+            self._sel_brick["parent"] = cover
+            self.add_brick_process("melt", snow_melt_process, cover)
+
+    def _unsupported(self, what):
+        raise RuntimeError(f"{what} is not available in the B200 engine (SURVEY.md §8f lists it as next).")
+
+    def generate_snowpacks_with_water_retention(self, *a, **k):
+        self._unsupported("snowpack water retention")
+
+    def generate_canopy_interception(self, *a, **k):
+        self._unsupported("canopy interception")
+
+    def add_snowpack_refreezing(self, *a, **k):
+        self._unsupported("snowpack refreezing")
+
+    def add_snowpack_sublimation(self, *a, **k):
+        self._unsupported("snowpack sublimation")
+
+    def add_snow_ice_transformation(self, *a, **k):
+        self._unsupported("snow to ice transformation process")
+
+    def add_snow_redistribution(self, *a, **k):
+        self._unsupported("snow redistribution")
+
+    # -- parameters ----------------------------------------------------------------------------------
+    def set_parameter_value(self, component, name, value):
+        """SettingsModel::SetParameterValue (SettingsModel.cpp:923-1031)."""
+        if "," in component:
+            for c in [c.strip() for c in component.split(",") if c.strip()]:
+                if not self.set_parameter_value(c, name, value):
+                    return False
+            return True
+        value = float(np.float32(value))
+        found = False
+
+        def set_in_brick(brick):
+            for p in brick["parameters"]:
+                if p["name"] == name:
+                    p["value"] = value
+                    return
+            for proc in brick["processes"]:
+                for p in proc["parameters"]:
+                    if p["name"] == name:
+                        p["value"] = value
+                        return
+            raise RuntimeError(f"The parameter '{name}' was not found.")
+
+        for st in self._structures:
+            bricks = {b["name"]: b for b in st["hydro_unit_bricks"] + st["sub_basin_bricks"]}
+            splitters = {s["name"]: s for s in st["hydro_unit_splitters"] + st["sub_basin_splitters"]}
+            if component in bricks:
+                set_in_brick(bricks[component])
+                found = True
+            elif component in splitters:
+                for p in splitters[component]["parameters"]:
+                    if p["name"] == name:
+                        p["value"] = value
+                        break
+                else:
+                    raise RuntimeError(f"SettingsModel::SetSplitterParameterValue - Parameter '{name}' not found")
+                found = True
+            elif "type:" in component:
+                kind = component.split(":", 1)[1]
+                for b in st["hydro_unit_bricks"] + st["sub_basin_bricks"]:
+                    if b["kind"] == kind or (kind == "land_cover" and b["kind"] in ("generic_land_cover", "glacier")):
+                        set_in_brick(b)
+        return found
+
+    # -- export --------------------------------------------------------------------------------------
+    def get_structure(self):
+        """Binding.cpp:119-160 (plus "parameters"/"log_items" per element)."""
+        return copy.deepcopy(self._structures)
+
+    def get_hydro_unit_log_labels(self):
+        """SettingsModel::GetHydroUnitLogLabels (SettingsModel.cpp:808-841): union over variants, in order."""
+        labels = []
+        for st in self._structures:
+            for b in st["hydro_unit_bricks"]:
+                for item in b["log_items"]:
+                    labels.append(f"{b['name']}:{item}")
+                for p in b["processes"]:
+                    for item in p["log_items"]:
+                        labels.append(f"{b['name']}:{p['name']}:{item}")
+        return list(dict.fromkeys(labels))
+
+    def get_land_cover_names(self):
+        names = []
+        for st in self._structures:
+            names += [b["name"] for b in st["hydro_unit_bricks"] if b["is_land_cover"]]
+        return list(dict.fromkeys(names))
+
+
+class SettingsBasin:
+    """base/SettingsBasin.{h,cpp}."""
+
+    def __init__(self):
+        self.units = []
+
+    def add_hydro_unit(self, id, area, elevation=-9999):  # noqa: A002
+        self.units.append({"id": int(id), "area": float(area), "elevation": float(elevation), "slope": None,
+                           "properties": {}, "land_covers": []})
+
+    def add_land_cover(self, name, kind, fraction):
+        self.units[-1]["land_covers"].append((name, float(fraction)))
+
+    def add_hydro_unit_property_str(self, name, value):
+        self.units[-1]["properties"][name] = value
+
+    def add_hydro_unit_property_double(self, name, value, unit):
+        self.units[-1]["properties"][name] = (float(value), unit)
+        if name == "slope":
+            self.units[-1]["slope"] = (float(value), unit)
+
+    def add_lateral_connection(self, *a, **k):
+        raise RuntimeError("Lateral connections are not available in the B200 engine (SURVEY.md §8f).")
+
+    def get_lateral_connection_count(self):
+        return 0
+
+    def clear(self):
+        self.units = []
+
+
+class SubBasin:
+    def __init__(self):
+        self.settings = None
+
+    def init(self, spatial_structure):
+        if not spatial_structure.units:
+            raise ValueError("Basin initialization failed: no hydro unit")
+        self.settings = spatial_structure
+
+
+class TimeSeries:
+    def __init__(self, name, time, ids, data):
+        self.name, self.time, self.ids, self.data = name, time, ids, data
+
+    @staticmethod
+    def create(data_name, time, ids, data):
+        return TimeSeries(data_name, np.asarray(time, dtype=np.float64), np.asarray(ids, dtype=np.int32),
+                          np.asarray(data, dtype=np.float64))
+
+
+def _parse_date_mjd(text):
+    """UtilsDateTime: 'YYYY-MM-DD' -> modified Julian date."""
+    d = np.datetime64(text[:10], "D")
+    return float((d - np.datetime64("1858-11-17", "D")).astype(int))
+
+
+class Action:
+    def __init__(self):
+        pass
+
+
+class ModelHydro:
+    """base/ModelHydro.{h,cpp} on the CUDA engine. One instance = one structure + basin + period; `run` is
+    the reference's single-parameter-set call, `run_batch` integrates many parameter sets in one launch."""
+
+    def __init__(self):
+        self._engine = None
+        self._cs = None
+        self._settings = None
+        self._units = None
+        self._series = {}
+        self._forcing_loaded = False
+        self._actions = []
+        self._n_steps = 0
+        self._labels = []
+        self._ran = False
+        self._mjd0 = 0.0
+        self._device = 0
+        self._pending_sets = None
+
+    # -- setup ---------------------------------------------------------------------------------------
+    def init_with_basin(self, model_settings, basin_settings, device=0):
+        try:
+            t = model_settings.timer
+            if not model_settings.solver:
+                raise ValueError("Model settings are not valid.")  # SettingsModel::IsValid
+            if t["time_step_unit"] not in ("day", "days", "d"):
+                raise _structure.UnsupportedStructure("only daily time steps (time_step_unit='day')")
+            self._mjd0 = _parse_date_mjd(t["start"])
+            dt = float(t["time_step"])
+            # TimeMachine::GetTimeStepCount (TimeMachine.cpp:61-64): 1 + (end - start) / dt
+            self._n_steps = int(1 + (_parse_date_mjd(t["end"]) - self._mjd0) / dt)
+            self._settings = model_settings
+            self._units = [dict(u) for u in basin_settings.units]
+            self._cs, self._engine = _structure.build_engine(model_settings.get_structure(), self._units,
+                                                             model_settings.solver, self._n_steps, device, dt)
+            self._engine.set_spinup_steps(int(t["spinup_days"] / dt))
+            self._labels = [l for l in model_settings.get_hydro_unit_log_labels()]
+            self._device = device
+        except (_structure.UnsupportedStructure, KeyError) as err:
+            raise ValueError(f"Model initialization failed: {err}") from err
+
+    def is_valid(self):
+        return self._engine is not None
+
+    # -- actions (dated state edits, applied between kernel segments) -----------------------------------
+    def add_action(self, action):
+        self._actions.append(action)
+        return True
+
+    def get_action_count(self):
+        return len(self._actions)
+
+    def get_sporadic_action_item_count(self):
+        return sum(getattr(a, "get_change_count", lambda: 0)() for a in self._actions)
+
+    # -- forcing -------------------------------------------------------------------------------------
+    def add_time_series(self, ts):
+        return self.create_time_series(ts.name, ts.time, ts.ids, ts.data)
+
+    def create_time_series(self, data_name, time, ids, data):
+        """ModelHydro::CreateTimeSeries (ModelHydro.cpp:306-322): data[T x U] float64, one column per id."""
+        data = np.asarray(data, dtype=np.float64)
+        time = np.asarray(time, dtype=np.float64)
+        ids = np.asarray(ids).astype(np.int64).ravel()
+        if data.ndim != 2 or data.shape != (len(time), len(ids)):
+            return False
+        key = data_name.lower()
+        if key not in _engine.VAR:
+            raise ValueError(f"Unknown forcing variable '{data_name}'")
+        self._series[_engine.VAR[key]] = (time, ids, data)
+        return True
+
+    def clear_time_series(self):
+        self._series = {}
+        self._forcing_loaded = False
+
+    def attach_time_series_to_hydro_units(self):
+        """ModelHydro::AttachTimeSeriesToHydroUnits (ModelHydro.cpp:324-346): match columns to units by id and
+        align the series start with the modelling period (TimeSeriesData cursor, ModelHydro.cpp:348-357)."""
+        unit_ids = np.array([u["id"] for u in self._units])
+        for var, (time, ids, data) in self._series.items():
+            pos = {int(i): k for k, i in enumerate(ids)}
+            try:
+                cols = [pos[int(i)] for i in unit_ids]
+            except KeyError:
+                return False
+            start = int(round(self._mjd0 - time[0]))
+            if start < 0 or start + self._n_steps > len(time):
+                raise ValueError("The forcing data do not cover the modelling period.")
+            self._engine.set_forcing(var, np.ascontiguousarray(data[start:start + self._n_steps][:, cols]))
+        self._forcing_loaded = len(self._series) > 0
+        return True
+
+    def forcing_loaded(self):
+        return self._forcing_loaded
+
+    def set_station_forcing(self, variable, series, ref_elevation=0.0, gradient=0.0, correction=1.0):
+        """Batched extra: station series + fused elevation-gradient spatialisation (forcing.py:1061-1113);
+        gradient / correction may be arrays with one value per parameter set (set the parameter sets first)."""
+        if np.ndim(gradient) > 0 or np.ndim(correction) > 0:
+            if self._pending_sets is None:
+                raise ValueError("set_parameter_sets() must precede per-set spatialisation gradients")
+            self._engine.set_parameters(self._pending_sets)
+        self._engine.set_station_forcing(variable.lower(), series, ref_elevation, gradient, correction)
+        self._station = getattr(self, "_station", set()) | {_engine.VAR[variable.lower()]}
+        self._forcing_loaded = len(self._station) == 3
+
+    # -- parameters ----------------------------------------------------------------------------------
+    def update_parameters(self, model_settings):
+        """ModelHydro::UpdateParameters (ModelHydro.cpp:76-84): re-read every parameter value."""
+        cs = _structure.CompiledStructure(model_settings.get_structure(), model_settings.solver,
+                                          self._cs.hbk.time_step_days)
+        self._cs.params = cs.params
+        self._pending_sets = cs.params[None, :].copy()
+
+    def set_parameter_sets(self, values):
+        """Batched extra: values[n_sets][HBK_N_PARAMS] float32 in engine.PARAM_SLOTS order."""
+        self._pending_sets = np.ascontiguousarray(values, dtype=np.float32)
+
+    def parameter_slot(self, component, name):
+        return self._cs.resolve_all(component, name)
+
+    # -- run -----------------------------------------------------------------------------------------
+    def reset(self):
+        self._ran = False
+
+    def save_as_initial_state(self):
+        self._engine.save_as_initial_state()
+
+    def run(self):
+        if not self._forcing_loaded:
+            raise ValueError("Time step processing failed: no forcing attached.")
+        if self._actions:
+            raise ValueError("Dated actions (glacier evolution, land-cover change) are not yet wired into the "
+                             "B200 engine's segment loop; refusing to run without them.")
+        if self._pending_sets is None:
+            self._pending_sets = self._cs.params[None, :].copy()
+        try:
+            self._engine.set_parameters(self._pending_sets)
+            self._engine.set_record_mask([self._cs.labels[l] for l in self._labels if l in self._cs.labels])
+            self._engine.run()
+        except _engine.HbkError as err:
+            raise ValueError(str(err)) from err
+        self._ran = True
+
+    def run_batch(self, parameter_sets, record=False):
+        """Integrate n parameter sets in one launch; returns outlet[n_sets][T]."""
+        self.set_parameter_sets(parameter_sets)
+        labels, self._labels = self._labels, (self._labels if record else [])
+        try:
+            self.run()
+        finally:
+            self._labels = labels
+        return self._engine.get_outlet()
+
+    # -- results -------------------------------------------------------------------------------------
+    def get_outlet_discharge(self):
+        return self._engine.get_outlet(0, 1)[0]
+
+    def get_outlet_discharge_batch(self):
+        return self._engine.get_outlet()
+
+    def get_total_outlet_discharge(self):
+        return float(self.get_outlet_discharge().sum())
+
+    def get_recorded_hydro_unit_labels(self):
+        return list(self._labels)
+
+    def get_recorded_hydro_unit_fraction_labels(self):
+        return self._settings.get_land_cover_names() if self._settings._log_all or self._settings._record_fractions else []
+
+    def get_hydro_unit_values(self, label):
+        if label not in self._cs.labels:
+            raise RuntimeError(f"Label '{label}' is not recorded.")
+        return self._engine.get_recorded(self._cs.labels[label], 0)
+
+    def get_hydro_unit_fractions(self, label):
+        frac = {self._cs.ground_name: [dict(u["land_covers"]).get(self._cs.ground_name, 1.0) for u in self._units]}
+        if self._cs.glacier_name:
+            frac[self._cs.glacier_name] = [dict(u["land_covers"]).get(self._cs.glacier_name, 0.0) for u in self._units]
+        return np.repeat(np.asarray(frac[label], dtype=np.float64)[None, :], self._n_steps, axis=0)
+
+    def get_hydro_unit_ids(self):
+        return [u["id"] for u in self._units]
+
+    def get_hydro_unit_areas(self):
+        return np.array([u["area"] for u in self._units], dtype=np.float64)
+
+    def _fractions(self):
+        g = np.array([dict(u["land_covers"]).get(self._cs.ground_name, 1.0) for u in self._units])
+        gl = np.array([dict(u["land_covers"]).get(self._cs.glacier_name, 0.0) if self._cs.glacier_name else 0.0
+                       for u in self._units])
+        return g, gl
+
+    def get_total_et(self):
+        """Logger::GetTotalET (Logger.cpp:168-216): area-weighted sum of the ET flux records."""
+        areas = self.get_hydro_unit_areas()
+        et = self._engine.get_recorded("slow_et", 0)
+        return float((np.nan_to_num(et) * (areas / areas.sum())[None, :]).sum())
+
+    def _storage_total(self, slots_with_fraction):
+        areas = self.get_hydro_unit_areas()
+        w = areas / areas.sum()
+        total = 0.0
+        for slot, frac in slots_with_fraction:
+            end = self._engine.get_state(slot)[0]
+            total += float((end * frac * w).sum())
+        return total
+
+    def get_total_water_storage_changes(self):
+        """Logger::GetTotalWaterStorageChanges (Logger.cpp:220-290): final - initial (initial = 0 here unless
+        an initial state was saved) of every water container, land-cover stores weighted by their fraction."""
+        g, gl = self._fractions()
+        one = np.ones_like(g)
+        total = self._storage_total([("ground_water", g), ("glacier_water", gl), ("slow", one), ("slow2", one),
+                                     ("quick", one)])
+        if self._cs.hbk.has_glacier:
+            total += float(self._engine.get_basin_state()[0].sum())
+        return total
+
+    def get_total_snow_storage_changes(self):
+        g, gl = self._fractions()
+        return self._storage_total([("ground_snow", g), ("glacier_snow", gl)])
+
+    def get_total_glacier_storage_changes(self):
+        g, gl = self._fractions()
+        return self._storage_total([("ice", gl)])
+
+    def dump_outputs(self, path):
+        raise RuntimeError("dump_outputs (netCDF) is outside the hot path and not available in the B200 engine.")
+
+
+class ActionLandCoverChange(Action):
+    def __init__(self):
+        super().__init__()
+        self.changes = []
+
+    def add_change(self, date, hydro_unit_id, land_cover, area):
+        self.changes.append((float(date), int(hydro_unit_id), land_cover, float(area)))
+
+    def get_change_count(self):
+        return len(self.changes)
+
+    def get_land_cover_count(self):
+        return len({c[2] for c in self.changes})
+
+
+class ActionGlacierEvolutionDeltaH(Action):
+    def __init__(self):
+        super().__init__()
+        self.month = 10
+        self.land_cover = ""
+        self.hu_ids = np.zeros(0, dtype=np.int32)
+        self.areas = np.zeros((0, 0))
+        self.volumes = np.zeros((0, 0))
+
+    def add_lookup_tables(self, month_num, land_cover, hu_ids, areas, volumes):
+        self.month, self.land_cover = int(month_num), land_cover
+        self.hu_ids = np.asarray(hu_ids, dtype=np.int32)
+        self.areas = np.asarray(areas, dtype=np.float64)
+        self.volumes = np.asarray(volumes, dtype=np.float64)
+
+    def get_land_cover_name(self):
+        return self.land_cover
+
+    def get_hydro_unit_ids(self):
+        return self.hu_ids
+
+    def get_lookup_table_area(self):
+        return self.areas
+
+    def get_lookup_table_volume(self):
+        return self.volumes
+
+
+class ActionGlacierSnowToIceTransformation(Action):
+    def __init__(self, month, day, land_cover):
+        super().__init__()
+        self.month, self.day, self.land_cover = int(month), int(day), land_cover
+
+    def get_land_cover_name(self):
+        return self.land_cover

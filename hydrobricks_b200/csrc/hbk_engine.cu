@@ -388,6 +388,25 @@ __global__ void hbkBroadcastState(double* dst, const double* perUnit, double val
         dst[i] = perUnit ? perUnit[i % U] : value;
 }
 
+// FP64 roofline denominator: 8 independent DFMA chains per thread (2 flops per DFMA).
+__global__ void hbkFp64Peak(double* out, int iters, double seed) {
+    double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6,
+           a7 = seed + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c);
+        a1 = fma(a1, m, c);
+        a2 = fma(a2, m, c);
+        a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c);
+        a5 = fma(a5, m, c);
+        a6 = fma(a6, m, c);
+        a7 = fma(a7, m, c);
+    }
+    const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 123.456) out[0] = s;  // keep the chains alive
+}
+
 }  // namespace hbk
 
 // =====================================================================================================
@@ -1014,5 +1033,35 @@ int hbk_last_run_stats(hbk_engine* e, double* ms, int32_t* launches, int64_t* un
 }
 
 void* hbk_stream(hbk_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+int hbk_measure_fp64_peak(int32_t device, double* tflops) {
+    if (!tflops) return HBK_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return HBK_E_CUDA;
+    double* d = nullptr;
+    if (cudaMalloc(&d, sizeof(double)) != cudaSuccess) return HBK_E_CUDA;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    const int iters = 1 << 16, blocks = 148 * 8, threads = 256;
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(a);
+        hbkFp64Peak<<<blocks, threads>>>(d, iters, 1.0 + rep);
+        cudaEventRecord(b);
+        if (cudaEventSynchronize(b) != cudaSuccess) {
+            cudaFree(d);
+            return HBK_E_CUDA;
+        }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        const double flops = 2.0 * 8.0 * iters * (double)blocks * threads;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    *tflops = best;
+    return HBK_OK;
+}
 
 }  // extern "C"

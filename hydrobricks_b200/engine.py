@@ -94,8 +94,18 @@ def load_library():
     L.hbk_last_run_stats.argtypes = [vp, dp, ip, ctypes.POINTER(i64)]
     L.hbk_stream.argtypes = [vp]
     L.hbk_stream.restype = ctypes.c_void_p
+    L.hbk_measure_fp64_peak.argtypes = [i32, dp]
     _lib = L
     return L
+
+
+def measure_fp64_peak(device=0):
+    """Measured DFMA throughput [TFLOP/s] (roofline denominator for the compute-bound configurations)."""
+    out = ctypes.c_double()
+    rc = load_library().hbk_measure_fp64_peak(int(device), ctypes.byref(out))
+    if rc != 0:
+        raise HbkError(rc, "hbk_measure_fp64_peak failed")
+    return out.value
 
 
 def _dptr(a):

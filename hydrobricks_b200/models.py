@@ -1,0 +1,198 @@
+"""Host mirror of the reference's model classes for the hot path: `Socont` with the option names, parameter
+aliases and structure-generation call sequence of python/src/hydrobricks/models/socont.py:111-215,
+models/model.py:1040-1105, models/model_settings.py:130-347 and modules/glacier.py:87-131, driving any
+`_hydrobricks`-compatible backend module (this package's, or the compiled reference in tests).
+
+It exists so that the engine can be used — and benchmarked, and tested on the GPU box — without the
+reference's Python package; with that package installed, inject hydrobricks_b200._hydrobricks instead and use
+hb.models.Socont unchanged.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _hydrobricks as _backend_default
+
+RAIN_SNOWMELT_STORAGE = "glacier_area_rain_snowmelt_storage"
+ICEMELT_STORAGE = "glacier_area_icemelt_storage"
+
+
+class Socont:
+    def __init__(self, solver="crank_nicolson", soil_storage_nb=1, surface_runoff="socont_runoff",
+                 land_cover_names=None, land_cover_types=None, record_all=False, glacier_infinite_storage=True,
+                 snow_melt_process="melt:degree_day", backend=None):
+        self.backend = backend or _backend_default
+        self.solver = solver
+        self.options = {"soil_storage_nb": soil_storage_nb, "surface_runoff": surface_runoff,
+                        "snow_melt_process": snow_melt_process, "glacier_infinite_storage": glacier_infinite_storage}
+        self.land_cover_names = list(land_cover_names or ["open"])
+        self.land_cover_types = list(land_cover_types or ["open"])
+        self.record_all = record_all
+        if soil_storage_nb not in (1, 2):
+            raise ValueError("There can be only one or two groundwater storages.")
+        if surface_runoff not in ("socont_runoff", "linear_storage"):
+            raise ValueError(f"The surface runoff option {surface_runoff} is not recognised in Socont.")
+        self.settings = self.backend.SettingsModel()
+        self.settings.log_all(record_all)
+        self.settings.set_solver(solver)
+        self.model = None
+        self._define_structure()
+        self._generate_structure()
+        self._define_parameter_aliases()
+
+    # models/socont.py:111-215 + modules/glacier.py:87-131
+    def _define_structure(self):
+        st = {}
+        glaciers = [n for n, t in zip(self.land_cover_names, self.land_cover_types) if t == "glacier"]
+        for name in glaciers:
+            st[name] = {"attach_to": "hydro_unit", "kind": "land_cover",
+                        "parameters": {"no_melt_when_snow_cover": True,
+                                       "infinite_storage": self.options["glacier_infinite_storage"]},
+                        "processes": {
+                            "outflow_rain_snowmelt": {"kind": "outflow:direct", "target": RAIN_SNOWMELT_STORAGE,
+                                                      "instantaneous": True},
+                            "melt": {"kind": self.options["snow_melt_process"], "target": ICEMELT_STORAGE,
+                                     "instantaneous": True}}}
+        if glaciers:
+            for name in (RAIN_SNOWMELT_STORAGE, ICEMELT_STORAGE):
+                st[name] = {"attach_to": "sub_basin", "kind": "storage",
+                            "processes": {"outflow": {"kind": "outflow:linear", "target": "outlet"}}}
+        soil = next((n for n, t in zip(self.land_cover_names, self.land_cover_types) if t != "glacier"), "open")
+        st[soil] = {"attach_to": "hydro_unit", "kind": "land_cover",
+                    "processes": {"infiltration": {"kind": "infiltration:socont", "target": "slow_reservoir"},
+                                  "runoff": {"kind": "outflow:rest", "target": "surface_runoff"}}}
+        st["slow_reservoir"] = {"attach_to": "hydro_unit", "kind": "storage", "parameters": {"capacity": 200},
+                                "processes": {"et": {"kind": "et:socont"},
+                                              "outflow": {"kind": "outflow:linear", "target": "outlet"},
+                                              "overflow": {"kind": "overflow", "target": "outlet"}}}
+        if self.options["soil_storage_nb"] == 2:
+            st["slow_reservoir"]["processes"]["percolation"] = {"kind": "percolation:constant",
+                                                                "target": "slow_reservoir_2"}
+            st["slow_reservoir_2"] = {"attach_to": "hydro_unit", "kind": "storage",
+                                      "processes": {"outflow": {"kind": "outflow:linear", "target": "outlet"}}}
+        kind = "runoff:socont" if self.options["surface_runoff"] == "socont_runoff" else "outflow:linear"
+        st["surface_runoff"] = {"attach_to": "hydro_unit", "kind": "storage",
+                                "processes": {"runoff": {"kind": kind, "target": "outlet"}}}
+        self.structure = st
+        self._glacier_names = glaciers
+
+    def _variants(self):  # models/model.py:1129-1168
+        if not self._glacier_names:
+            return [(self.land_cover_names, self.land_cover_types, self.structure)]
+        names = [n for n, t in zip(self.land_cover_names, self.land_cover_types) if t != "glacier"]
+        types = [t for t in self.land_cover_types if t != "glacier"]
+        base = {k: v for k, v in self.structure.items() if k not in self._glacier_names}
+        return [(names, types, base), (self.land_cover_names, self.land_cover_types, self.structure)]
+
+    def _generate_structure(self):  # models/model.py:1040-1105, model_settings.py:130-347
+        s = self.settings
+        for i, (names, types, structure) in enumerate(self._variants()):
+            if i > 0:
+                s.add_structure()
+            s.generate_precipitation_splitters(True, "snow_rain:linear")
+            for t, n in zip(types, names):
+                s.add_land_cover_brick(n, "generic_land_cover" if t in ("ground", "generic_land_cover", "open",
+                                                                        "forest", "lake") else t)
+            s.generate_snowpacks(self.options["snow_melt_process"])
+            for key, brick in structure.items():
+                if brick["kind"] == "land_cover":
+                    s.select_hydro_unit_brick(key)
+                elif brick["attach_to"] == "hydro_unit":
+                    s.add_hydro_unit_brick(key, brick["kind"])
+                else:
+                    s.add_sub_basin_brick(key, brick["kind"])
+                for pname, value in brick.get("parameters", {}).items():
+                    s.add_brick_parameter(pname, value)
+                for pname, pd in brick.get("processes", {}).items():
+                    s.add_brick_process(pname, pd["kind"], pd.get("target", ""), False)
+                    if pd["kind"] in ("outflow:direct", "outflow:rest"):
+                        s.set_process_outputs_as_static()
+                    if pd.get("instantaneous"):
+                        s.set_process_outputs_as_instantaneous()
+            s.add_logging_to("outlet")
+
+    def _define_parameter_aliases(self):
+        """models/socont.py:217-262 + parameters.py aliases: alias -> (component, parameter name)."""
+        soil = next((n for n, t in zip(self.land_cover_names, self.land_cover_types) if t != "glacier"), "open")
+        a = {"A": ("slow_reservoir", "capacity"), "k_slow": ("slow_reservoir", "response_factor"),
+             "k_slow_1": ("slow_reservoir", "response_factor"), "k_slow_2": ("slow_reservoir_2", "response_factor"),
+             "percol": ("slow_reservoir", "percolation_rate"), "k_quick": ("surface_runoff", "response_factor"),
+             "beta": ("surface_runoff", "beta"), "a_snow": ("type:snowpack", "degree_day_factor"),
+             "melt_t_snow": ("type:snowpack", "melting_temperature"),
+             "prec_t_start": ("snow_rain_transition", "transition_start"),
+             "prec_t_end": ("snow_rain_transition", "transition_end")}
+        if self._glacier_names:
+            a.update({"a_ice": (",".join(self._glacier_names), "degree_day_factor"),
+                      "k_snow": (RAIN_SNOWMELT_STORAGE, "response_factor"),
+                      "k_ice": (ICEMELT_STORAGE, "response_factor")})
+        self.aliases = a
+        self.soil_cover = soil
+
+    # -- the reference's Model surface (models/model.py:118-332, 450-600) ----------------------------------
+    def setup(self, units, start_date, end_date, spinup_days=0, device=0):
+        """units: list of dicts {"id","area","elevation","slope":(value,unit)|None,"land_covers":[(name,frac)]}
+        in any order; sorted by descending elevation like HydroUnits (hydro_units.py:693-736)."""
+        self.units = sorted(units, key=lambda u: -u["elevation"])
+        self.settings.set_timer(start_date, end_date, 1, "day")
+        if spinup_days:
+            self.settings.set_spinup_days(spinup_days)
+        basin = self.backend.SettingsBasin()
+        for u in self.units:
+            basin.add_hydro_unit(u["id"], u["area"], u["elevation"])
+            if u.get("slope"):
+                basin.add_hydro_unit_property_double("slope", u["slope"][0], u["slope"][1])
+            for name, frac in u["land_covers"]:
+                basin.add_land_cover(name, "", frac)
+        self.model = self.backend.ModelHydro()
+        try:
+            self.model.init_with_basin(self.settings, basin, device)
+        except TypeError:
+            self.model.init_with_basin(self.settings, basin)
+        self._basin = basin
+
+    def set_parameters(self, values: dict):
+        for alias, value in values.items():
+            component, name = self.aliases.get(alias, (None, None))
+            if component is None:
+                component, name = alias.split(":", 1)
+            if not self.settings.set_parameter_value(component, name, value):
+                raise ValueError(f"Failed setting parameter {alias}")
+        self.model.update_parameters(self.settings)
+
+    def set_forcing(self, time_mjd, precipitation, temperature, pet):
+        """Pre-spatialised forcing [T x U] in the basin order of self.units (model.py:354-384)."""
+        ids = np.array([u["id"] for u in self.units], dtype=np.int32)
+        self.model.clear_time_series()
+        for name, data in (("precipitation", precipitation), ("temperature", temperature), ("pet", pet)):
+            if not self.model.create_time_series(name, np.asarray(time_mjd, dtype=np.float64), ids, data):
+                raise ValueError("Failed adding time series.")
+        if not self.model.attach_time_series_to_hydro_units():
+            raise ValueError("Attaching time series failed.")
+
+    def run(self, parameters: dict | None = None):
+        if parameters:
+            self.set_parameters(parameters)
+        self.model.reset()
+        self.model.run()
+
+    def get_outlet_discharge(self):
+        return self.model.get_outlet_discharge()
+
+    # -- batched extras --------------------------------------------------------------------------------
+    def parameter_matrix(self, sets: dict, n_sets: int):
+        """{alias: array[n_sets] | scalar} -> float32 [n_sets][HBK_N_PARAMS] (engine.PARAM_SLOTS order)."""
+        base = self.model._cs.params.copy()
+        m = np.repeat(base[None, :], n_sets, axis=0)
+        for alias, values in sets.items():
+            component, name = self.aliases.get(alias, (None, None))
+            if component is None:
+                component, name = alias.split(":", 1)
+            slots = self.model.parameter_slot(component, name)
+            if not slots:
+                raise ValueError(f"parameter {alias} is not part of this structure")
+            for slot in slots:
+                m[:, slot] = np.asarray(values, dtype=np.float32)
+        return m
+
+    def run_batch(self, matrix):
+        return self.model.run_batch(matrix)

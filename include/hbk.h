@@ -152,6 +152,10 @@ int hbk_last_run_stats(hbk_engine* e, double* kernel_ms, int32_t* n_launches, in
 /* Raw CUDA stream handle (cudaStream_t) the engine launches on, for callers timing with events. */
 void* hbk_stream(hbk_engine* e);
 
+/* Measured FP64 (non-tensor) DFMA throughput of the device in TFLOP/s: the roofline denominator of the
+ * compute-bound ensemble configurations (MEASURED_PEAKS.json has no FP64 figure). */
+int hbk_measure_fp64_peak(int32_t device, double* tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,92 @@
+"""Host logic (CPU): the SettingsModel / Socont mirrors must emit exactly the structure the reference's own
+SettingsModel emits for the same calls (golden structures recorded from the reference), the structure compiler
+must map it to the right process table, and unsupported structures must be refused loudly."""
+import copy
+
+import numpy as np
+import pytest
+
+import golden_utils as gu
+from hydrobricks_b200 import _hydrobricks as hbk_mod
+from hydrobricks_b200 import models, structure
+
+
+def strip(structs):
+    out = copy.deepcopy(structs)
+    for s in out:
+        s.pop("log_items", None)
+    return out
+
+
+CASES = {
+    "socont_sitter_rk4_1store": dict(soil_storage_nb=1, surface_runoff="linear_storage"),
+    "socont_sitter_rk4_2store": dict(soil_storage_nb=2, surface_runoff="linear_storage"),
+    "gsm_socont_rk4_glacier_1store": dict(soil_storage_nb=1, land_cover_names=["ground", "glacier"],
+                                          land_cover_types=["ground", "glacier"]),
+    "gsm_socont_rk4_glacier_2store": dict(soil_storage_nb=2, land_cover_names=["ground", "glacier"],
+                                          land_cover_types=["ground", "glacier"]),
+    "gsm_socont_rk4_glacier_finite_1store": dict(soil_storage_nb=1, land_cover_names=["ground", "glacier"],
+                                                 land_cover_types=["ground", "glacier"],
+                                                 glacier_infinite_storage=False),
+    "gsm_socont_rk4_noglacier_1store": dict(soil_storage_nb=1, land_cover_names=["ground"],
+                                            land_cover_types=["ground"]),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_socont_mirror_emits_reference_structure(name):
+    meta, _, _, _, _ = gu.load(name)
+    m = models.Socont(solver="rk4", record_all=True, **CASES[name])
+    mine = strip(m.settings.get_structure())
+    ref = strip(meta["structures"])
+    # parameter VALUES differ (the golden run had its own parameter set); compare them after resetting
+    def blank(structs):
+        for s in structs:
+            for group in ("hydro_unit_bricks", "sub_basin_bricks", "hydro_unit_splitters", "sub_basin_splitters"):
+                for el in s[group]:
+                    for p in el.get("parameters", []):
+                        p["value"] = 0.0
+                    for proc in el.get("processes", []):
+                        for p in proc.get("parameters", []):
+                            p["value"] = 0.0
+        return structs
+    assert blank(mine) == blank(ref)
+
+
+def test_set_parameter_value_matches_reference_values():
+    meta, _, _, _, _ = gu.load("gsm_socont_rk4_glacier_2store")
+    m = models.Socont(solver="rk4", record_all=True, soil_storage_nb=2, land_cover_names=["ground", "glacier"],
+                      land_cover_types=["ground", "glacier"])
+    s = m.settings
+    # the values tools/ref_cases.py::gsm_socont used, through the same aliases
+    for comp, name, v in [("type:snowpack", "degree_day_factor", 4.5), ("slow_reservoir", "capacity", 120),
+                          ("slow_reservoir", "response_factor", 0.02), ("surface_runoff", "beta", 800),
+                          ("glacier", "degree_day_factor", 7.0),
+                          ("glacier_area_rain_snowmelt_storage", "response_factor", 0.2),
+                          ("glacier_area_icemelt_storage", "response_factor", 0.35),
+                          ("slow_reservoir", "percolation_rate", 0.8), ("slow_reservoir_2", "response_factor", 0.006)]:
+        s.set_parameter_value(comp, name, v)
+    a = structure.CompiledStructure(s.get_structure(), "rk4").params
+    b = structure.CompiledStructure(meta["structures"], "rk4").params
+    assert np.array_equal(a, b)
+
+
+def test_unsupported_structures_are_refused():
+    s = hbk_mod.SettingsModel()
+    with pytest.raises(RuntimeError):
+        s.add_hydro_unit_brick("x", "storage")
+        s.add_brick_process("p", "et:hbv")
+    meta, _, _, _, _ = gu.load("kat_linear_storage_runge_kutta")
+    with pytest.raises(structure.UnsupportedStructure):
+        structure.CompiledStructure(meta["structures"], "rk4")
+    meta, _, _, _, _ = gu.load("socont_sitter_rk4_1store")
+    with pytest.raises(structure.UnsupportedStructure):
+        structure.CompiledStructure(meta["structures"], "crank_nicolson")
+
+
+def test_structure_variant_assignment():
+    meta, _, _, _, _ = gu.load("gsm_socont_rk4_glacier_1store")
+    cs = structure.CompiledStructure(meta["structures"], "rk4")
+    gv = cs.assign_structure_variants([u["land_covers"] for u in meta["units"]])
+    expect = [1 if dict(u["land_covers"]).get("glacier", 0) > 1e-8 else 0 for u in meta["units"]]
+    assert gv == expect and 0 < sum(gv) < len(gv)

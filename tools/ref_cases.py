@@ -74,14 +74,14 @@ def synthetic_units_csv(path, n_units=12, seed=3, with_glacier=True, area=1.0e6)
     areas = area * rng.uniform(0.4, 1.6, n_units)
     with open(path, "w") as f:
         if with_glacier:
-            f.write("id,fraction-ground,fraction-glacier,elevation,area,slope\n-,fraction,fraction,m,m2,deg\n")
+            f.write("id,elevation,area_ground,area_glacier,slope\n-,m,m2,m2,deg\n")
         else:
             f.write("id,fraction-ground,elevation,area,slope\n-,fraction,m,m2,deg\n")
         for i in range(n_units):
             g = float(np.clip((elev[i] - 2400) / 800 * 0.8, 0, 0.8)) if with_glacier else 0.0
             g = round(g, 4)
             if with_glacier:
-                f.write(f"{i + 1},{1 - g:.4f},{g:.4f},{elev[i]:.1f},{areas[i]:.1f},{slope[i]:.3f}\n")
+                f.write(f"{i + 1},{elev[i]:.1f},{areas[i] * (1 - g):.1f},{areas[i] * g:.1f},{slope[i]:.3f}\n")
             else:
                 f.write(f"{i + 1},1,{elev[i]:.1f},{areas[i]:.1f},{slope[i]:.3f}\n")
 
@@ -116,8 +116,13 @@ def gsm_socont(hb, solver="rk4", soil_storage_nb=1, surface_runoff="socont_runof
     parameters.add_data_parameter("precip_gradient", 0.04)
     parameters.add_data_parameter("temp_gradients", -0.55)
     hydro_units = hb.HydroUnits(land_cover_types=types, land_cover_names=names)
-    hydro_units.load_from_csv(csv, column_elevation="elevation", column_area="area",
-                              other_columns={"slope": "slope"})
+    if with_glacier:
+        hydro_units.load_from_csv(csv, column_elevation="elevation",
+                                  columns_areas={"ground": "area_ground", "glacier": "area_glacier"},
+                                  other_columns={"slope": "slope"})
+    else:
+        hydro_units.load_from_csv(csv, column_elevation="elevation", column_area="area",
+                                  other_columns={"slope": "slope"})
     forcing = hb.Forcing(hydro_units)
     forcing.load_station_data_from_csv(
         CATCH / "ch_rhone_gletsch" / "meteo.csv", column_time="date", time_format="%d/%m/%Y",
