@@ -32,8 +32,8 @@ U_DEFAULT, T_DEFAULT, P_DEFAULT = 50, 10957, 100000
 START, END = "1981-01-01", "2010-12-31"
 # Executed FP64 work of the dominant kernel per HRU*timestep, from the ncu instruction-mix capture of this same
 # workload (profiles/): flops = DADD + DMUL + 2*DFMA thread instructions / (P*U*T). Updated per round.
-FP64_FLOPS_PER_HRU_STEP = 1000.0
-FP64_FLOPS_SOURCE = "provisional hand count (SURVEY.md §8d: 600-900 FP64 instr); replaced by ncu instruction mix"
+FP64_FLOPS_PER_HRU_STEP = 535.8
+FP64_FLOPS_SOURCE = "profiles/r01a_instmix.csv: (DADD + DMUL + 2*DFMA) thread instructions / HRU*timesteps of the faithful r01a kernel"
 
 
 # ---------------------------------------------------------------------------------------------------------
