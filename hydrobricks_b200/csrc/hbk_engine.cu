@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kBlock) hbkRunUnits(const KArgs a) {
         const float t0f = pp[HBK_P_TRANSITION_START * a.ldp], t1f = pp[HBK_P_TRANSITION_END * a.ldp];
         par.t0 = t0f;
         par.t1 = t1f;
-        par.span = (double)(t1f - t0f);
+        par.invSpan = 1.0 / (double)(t1f - t0f);
         par.rcf = pp[HBK_P_RAIN_CORRECTION * a.ldp];
         par.scf = pp[HBK_P_SNOW_CORRECTION * a.ldp];
         par.ddfG = pp[HBK_P_GROUND_SNOW_DDF * a.ldp];
@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(kBlock) hbkRunUnits(const KArgs a) {
         par.ddfIce = pp[HBK_P_ICE_DDF * a.ldp];
         par.tmIce = pp[HBK_P_ICE_TMELT * a.ldp];
         par.A = pp[HBK_P_CAPACITY * a.ldp];
+        par.invA = 1.0 / par.A;
         par.k1 = pp[HBK_P_K_SLOW_1 * a.ldp];
         par.perc = pp[HBK_P_PERCOLATION * a.ldp];
         par.k2 = pp[HBK_P_K_SLOW_2 * a.ldp];
@@ -148,7 +149,9 @@ __global__ void __launch_bounds__(kBlock) hbkRunUnits(const KArgs a) {
         const double slopeTerm = a.hru[2 * a.ldu + u];
         elev = a.hru[3 * a.ldu + u];
         const double quick = pp[HBK_P_QUICK * a.ldp];
-        par.quick = (a.flags.quickKind == 0) ? quick * slopeTerm : quick;
+        // runoff:socont folded: beta*sqrt(slope)/area * (2/1000)^(5/3) * 86400 * 1000  (ProcessRunoffSocont.cpp:41-56)
+        const double socontUnit = 3.1748021039363989e-05 * 86400.0 * 1000.0;  // 0.002^(5/3) = 3.1748021039363989e-05
+        par.quick = (a.flags.quickKind == 0) ? quick * slopeTerm / area * socontUnit : quick;
         glacierVariant = GLACIER && (a.hruFlags[u] & 1);
         const long long fi = a.fracPerSet ? ((long long)p * a.U + u) : u;
         fG = a.frac[fi];
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(kBlock) hbkRunUnits(const KArgs a) {
                     pet = (xe < 0.0) ? 0.0 : xe;
                 }
                 directPhase<GLACIER>(h, par, precip, temp, a.dt, fa, fG, fGl, glacierVariant, a.flags, o, err);
-                solveUnit<SOLVER, NSOIL>(h, par, pet, area, fa, a.dt, a.flags, o, err, unconverged);
+                solveUnit<SOLVER, NSOIL>(h, par, pet, fa, a.dt, a.flags, o, err, unconverged);
 
                 if (nRec && a.writeOutputs) {
                     // Logger::Record (Logger.cpp:93-120): contents after Finalize and flux amounts
@@ -498,7 +501,7 @@ void chooseShape(hbk_engine* e) {
     e->nUTiles = (e->U + e->UB - 1) / e->UB;
     const int nq = e->st.has_glacier ? 3 : 1;
     // chunk length: keep forcing stages + reduction buffer under ~100 KB so two blocks fit on an SM
-    int tc = 16;
+    int tc = 32;
     for (;;) {
         const size_t fRow = (e->haveRaw[0] ? (size_t)tc * e->UB : (size_t)tc + 2);
         const size_t bytes = 128 + 2 * 3 * fRow * 8 + (size_t)nq * tc * kBlock * 8;
