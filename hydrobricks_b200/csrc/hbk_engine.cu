@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -33,11 +34,17 @@
 
 namespace hbk {
 
-constexpr int kBlock = 256;
+#ifndef HBK_MAX_THREADS
+#define HBK_MAX_THREADS 128  // largest block the host may launch (PB * UB); 128 x 6 blocks = 24 warps/SM measured best
+#endif
+#ifndef HBK_MIN_BLOCKS
+#define HBK_MIN_BLOCKS 6  // register budget = 65536 / (HBK_MAX_THREADS * HBK_MIN_BLOCKS)
+#endif
+constexpr int kBlock = HBK_MAX_THREADS;
 constexpr int kNH = 4;  // per-unit constants: area fraction of basin, area [m2], pow(slope,0.5), elevation
 
 struct KArgs {
-    int P, U, tBegin, tEnd, PB, UB, TC, nUTiles;
+    int P, U, tBegin, tEnd, PB, UB, TC, nUTiles, G, nGroups;
     Flags flags;
     double dt;
     const float* params;  // [HBK_N_PARAMS][ldp]
@@ -55,8 +62,8 @@ struct KArgs {
     const double* gradP;
     const double* corrP;
     double gradTs, gradPs, corrPs, zrefT, zrefP;
-    double* state;  // [HBK_N_STATES][lds]
-    long long lds;
+    double* state;  // [HBK_N_STATES][lds], element (p, u) at p*sP + u*sU
+    long long lds, sP, sU;
     double* outQ;  // [nUTiles][P][ldt]
     double* outD1;
     double* outD2;
@@ -100,32 +107,38 @@ __device__ __forceinline__ void tmaLoad1D(void* dst, const void* src, uint32_t b
 }
 
 // ---- main kernel ------------------------------------------------------------------------------------
+// Block = PB parameter sets x UB units (threads), time-multiplexed over a GROUP of G consecutive unit tiles:
+//   for each chunk of TC steps: for each tile of the group: [load state] TC steps [store state], add the tile's
+//   outlet contributions to the chunk accumulator; after the last tile write outlet[p][t0..t0+TC).
+// With G = all tiles (ensembles) one block sums every unit of its parameter sets in unit order: no partial
+// buffers, no second pass. With G = 1 (few sets, many units) the state never leaves the registers.
 template <int SOLVER, int NSOIL, bool GLACIER>
-__global__ void __launch_bounds__(kBlock) hbkRunUnits(const KArgs a) {
+__global__ void __launch_bounds__(HBK_MAX_THREADS, HBK_MIN_BLOCKS) hbkRunUnits(const KArgs a) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     constexpr int NQ = GLACIER ? 3 : 1;
     const int tid = threadIdx.x;
-    const int ut = blockIdx.x % a.nUTiles;
-    const int pg = blockIdx.x / a.nUTiles;
+    const int nThreads = blockDim.x;  // PB * UB
+    const int grp = blockIdx.x % a.nGroups;
+    const int pg = blockIdx.x / a.nGroups;
     const int pl = tid % a.PB;
     const int ul = tid / a.PB;
     const int p = pg * a.PB + pl;
-    const int u = ut * a.UB + ul;
-    const bool valid = (p < a.P) && (u < a.U);
+    const bool validP = p < a.P;
+    const int tileBegin = grp * a.G;
+    const int tileEnd = min(tileBegin + a.G, a.nUTiles);
+    const bool multi = a.G > 1;
 
     // shared memory carve-up
     uint64_t* bars = reinterpret_cast<uint64_t*>(smemRaw);  // 2 mbarriers
     const int fRow = (a.forcingMode == 0) ? a.TC * a.UB : (a.TC + 2);  // doubles per variable per stage
     double* fbuf = reinterpret_cast<double*>(smemRaw + 128);             // [2][3][fRow]
-    double* qbuf = fbuf + 2 * 3 * fRow;                                  // [NQ][TC][kBlock]
+    double* qbuf = fbuf + 2 * 3 * fRow;                                  // [NQ][TC][nThreads]
+    double* accb = qbuf + (size_t)NQ * a.TC * nThreads;                  // [NQ][TC][PB]
 
-    // per-thread constants
+    // per-thread, per-parameter-set constants
     Par par;
-    Hru h;
-    double fa = 0, area = 1, elev = 0, fG = 1, fGl = 0;
-    bool glacierVariant = false;
-    double cT = 0, mP = 1, corr = 1;
-    if (valid) {
+    double quickBase = 0, gT = 0, gP = 0, corr = 1;
+    if (validP) {
         const float* pp = a.params + p;
         const float t0f = pp[HBK_P_TRANSITION_START * a.ldp], t1f = pp[HBK_P_TRANSITION_END * a.ldp];
         par.t0 = t0f;
@@ -144,59 +157,100 @@ __global__ void __launch_bounds__(kBlock) hbkRunUnits(const KArgs a) {
         par.k1 = pp[HBK_P_K_SLOW_1 * a.ldp];
         par.perc = pp[HBK_P_PERCOLATION * a.ldp];
         par.k2 = pp[HBK_P_K_SLOW_2 * a.ldp];
+        quickBase = pp[HBK_P_QUICK * a.ldp];
+        par.quick = quickBase;
+        if (a.forcingMode == 1) {
+            gT = a.gradT ? a.gradT[p] : a.gradTs;
+            gP = a.gradP ? a.gradP[p] : a.gradPs;
+            corr = a.corrP ? a.corrP[p] : a.corrPs;
+        }
+    }
+
+    // per-(set, unit) values, (re)loaded per tile when the block time-multiplexes several tiles
+    Hru h;
+    double fa = 0, fG = 1, fGl = 0, cT = 0, mP = 1;
+    bool glacierVariant = false;
+    auto loadUnit = [&](int u) {
         fa = a.hru[0 * a.ldu + u];
-        area = a.hru[1 * a.ldu + u];
+        const double area = a.hru[1 * a.ldu + u];
         const double slopeTerm = a.hru[2 * a.ldu + u];
-        elev = a.hru[3 * a.ldu + u];
-        const double quick = pp[HBK_P_QUICK * a.ldp];
-        // runoff:socont folded: beta*sqrt(slope)/area * (2/1000)^(5/3) * 86400 * 1000  (ProcessRunoffSocont.cpp:41-56)
-        const double socontUnit = 3.1748021039363989e-05 * 86400.0 * 1000.0;  // 0.002^(5/3) = 3.1748021039363989e-05
-        par.quick = (a.flags.quickKind == 0) ? quick * slopeTerm / area * socontUnit : quick;
+        const double elev = a.hru[3 * a.ldu + u];
+        // runoff:socont folded: beta*sqrt(slope)/area * (2/1000)^(5/3) * 86400 * 1000 (ProcessRunoffSocont.cpp:41-56)
+        const double socontUnit = 3.174802103936398e-05 * 86400.0 * 1000.0;
+        par.quick = (a.flags.quickKind == 0) ? quickBase * slopeTerm / area * socontUnit : quickBase;
         glacierVariant = GLACIER && (a.hruFlags[u] & 1);
         const long long fi = a.fracPerSet ? ((long long)p * a.U + u) : u;
         fG = a.frac[fi];
         fGl = a.frac[a.fracLd + fi];
-        const long long si = (long long)p * a.U + u;
+        if (a.forcingMode == 1) {
+            // forcing.py:1073-1075 / 1104-1106: g*(z - zref) -> /100 -> (1 + ...) -> x * ...
+            cT = gT * (elev - a.zrefT) / 100;
+            mP = 1 + gP * (elev - a.zrefP) / 100;
+        }
+    };
+    auto loadState = [&](int u) {
+        const long long si = (long long)p * a.sP + (long long)u * a.sU;
         h.snowG = a.state[HBK_S_GROUND_SNOW * a.lds + si];
-        h.snowGl = a.state[HBK_S_GLACIER_SNOW * a.lds + si];
         h.wG = a.state[HBK_S_GROUND_WATER * a.lds + si];
-        h.wGl = a.state[HBK_S_GLACIER_WATER * a.lds + si];
-        h.ice = a.state[HBK_S_ICE * a.lds + si];
         h.slow = a.state[HBK_S_SLOW * a.lds + si];
-        h.slow2 = a.state[HBK_S_SLOW2 * a.lds + si];
+        h.slow2 = (NSOIL == 2) ? a.state[HBK_S_SLOW2 * a.lds + si] : 0.0;
         h.quick = a.state[HBK_S_QUICK * a.lds + si];
         h.amtInfil = a.state[HBK_S_AMT_INFILTRATION * a.lds + si];
         h.amtRest = a.state[HBK_S_AMT_REST * a.lds + si];
         h.amtMeltG = a.state[HBK_S_AMT_MELT_GROUND * a.lds + si];
-        h.amtMeltGl = a.state[HBK_S_AMT_MELT_GLACIER * a.lds + si];
-        h.amtDep1 = a.state[HBK_S_AMT_DEPOSIT_RAIN_SNOWMELT * a.lds + si];
-        h.amtDep2 = a.state[HBK_S_AMT_DEPOSIT_ICEMELT * a.lds + si];
-        if (a.forcingMode == 1) {
-            // forcing.py:1073-1075 / 1104-1106: g*(z - zref) -> /100 -> (1 + ...) -> x * ...
-            const double gT = a.gradT ? a.gradT[p] : a.gradTs;
-            const double gP = a.gradP ? a.gradP[p] : a.gradPs;
-            corr = a.corrP ? a.corrP[p] : a.corrPs;
-            cT = gT * (elev - a.zrefT) / 100;
-            mP = 1 + gP * (elev - a.zrefP) / 100;
+        if (GLACIER) {
+            h.snowGl = a.state[HBK_S_GLACIER_SNOW * a.lds + si];
+            h.wGl = a.state[HBK_S_GLACIER_WATER * a.lds + si];
+            h.ice = a.state[HBK_S_ICE * a.lds + si];
+            h.amtMeltGl = a.state[HBK_S_AMT_MELT_GLACIER * a.lds + si];
+            h.amtDep1 = a.state[HBK_S_AMT_DEPOSIT_RAIN_SNOWMELT * a.lds + si];
+            h.amtDep2 = a.state[HBK_S_AMT_DEPOSIT_ICEMELT * a.lds + si];
+        } else {
+            h.snowGl = h.wGl = h.ice = h.amtMeltGl = h.amtDep1 = h.amtDep2 = 0.0;
         }
-    }
+    };
+    auto storeState = [&](int u) {
+        const long long si = (long long)p * a.sP + (long long)u * a.sU;
+        a.state[HBK_S_GROUND_SNOW * a.lds + si] = h.snowG;
+        a.state[HBK_S_GROUND_WATER * a.lds + si] = h.wG;
+        a.state[HBK_S_SLOW * a.lds + si] = h.slow;
+        if (NSOIL == 2) a.state[HBK_S_SLOW2 * a.lds + si] = h.slow2;
+        a.state[HBK_S_QUICK * a.lds + si] = h.quick;
+        a.state[HBK_S_AMT_INFILTRATION * a.lds + si] = h.amtInfil;
+        a.state[HBK_S_AMT_REST * a.lds + si] = h.amtRest;
+        a.state[HBK_S_AMT_MELT_GROUND * a.lds + si] = h.amtMeltG;
+        if (GLACIER) {
+            a.state[HBK_S_GLACIER_SNOW * a.lds + si] = h.snowGl;
+            a.state[HBK_S_GLACIER_WATER * a.lds + si] = h.wGl;
+            a.state[HBK_S_ICE * a.lds + si] = h.ice;
+            a.state[HBK_S_AMT_MELT_GLACIER * a.lds + si] = h.amtMeltGl;
+            a.state[HBK_S_AMT_DEPOSIT_RAIN_SNOWMELT * a.lds + si] = h.amtDep1;
+            a.state[HBK_S_AMT_DEPOSIT_ICEMELT * a.lds + si] = h.amtDep2;
+        }
+    };
 
+    const double invDt = 1.0 / a.dt;
     const int nSteps = a.tEnd - a.tBegin;
     const int nChunks = (nSteps + a.TC - 1) / a.TC;
+    const int nTilesHere = tileEnd - tileBegin;
+    // forcing pipeline: one load per chunk (station series) or per (chunk, tile) (per-unit series)
+    const int nLoads = (a.forcingMode == 0) ? nChunks * nTilesHere : nChunks;
 
-    auto issueLoad = [&](int c) {
-        const int stage = c & 1;
-        const int t0 = a.tBegin + c * a.TC;
-        const int n = min(a.TC, a.tEnd - t0);
+    auto issueLoad = [&](int seq) {
+        const int stage = seq & 1;
         double* dst = fbuf + (size_t)stage * 3 * fRow;
         if (a.forcingMode == 0) {
+            const int c = seq / nTilesHere, tile = tileBegin + seq % nTilesHere;
+            const int t0 = a.tBegin + c * a.TC;
+            const int n = min(a.TC, a.tEnd - t0);
             const uint32_t bytes = (uint32_t)(n * a.UB * sizeof(double));
             mbarExpectTx(&bars[stage], 3 * bytes);
             for (int v = 0; v < 3; ++v) {
-                const double* src = a.forcing[v] + ((size_t)ut * a.tld + t0) * a.UB;
+                const double* src = a.forcing[v] + ((size_t)tile * a.tld + t0) * a.UB;
                 tmaLoad1D(dst + (size_t)v * fRow, src, bytes, &bars[stage]);
             }
         } else {
+            const int t0 = a.tBegin + seq * a.TC;
             const int t0a = t0 & ~1;  // 16-byte aligned source
             const uint32_t bytes = (uint32_t)((a.TC + 2) * sizeof(double));
             mbarExpectTx(&bars[stage], 3 * bytes);
@@ -210,124 +264,131 @@ __global__ void __launch_bounds__(kBlock) hbkRunUnits(const KArgs a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid == 0 && nChunks > 0) issueLoad(0);
+    if (tid == 0 && nLoads > 0) issueLoad(0);
 
     int err = 0;
     int unconverged = 0;
     const int nRec = __popcll(a.recordMask);
+    bool loaded = false;
 
     for (int c = 0; c < nChunks; ++c) {
-        const int stage = c & 1;
         const int t0 = a.tBegin + c * a.TC;
         const int n = min(a.TC, a.tEnd - t0);
-        if (tid == 0 && c + 1 < nChunks) issueLoad(c + 1);
-        mbarWait(&bars[stage], (c >> 1) & 1);
-        const double* fs = fbuf + (size_t)stage * 3 * fRow;
         const int off = (a.forcingMode == 1) ? (t0 & 1) : 0;
+        for (int tl = 0; tl < nTilesHere; ++tl) {
+            const int tile = tileBegin + tl;
+            const int u = tile * a.UB + ul;
+            const bool valid = validP && (u < a.U);
+            // ---- forcing for this (chunk, tile) ----
+            const int seq = (a.forcingMode == 0) ? c * nTilesHere + tl : c;
+            if (a.forcingMode == 0 || tl == 0) {
+                if (tid == 0 && seq + 1 < nLoads) issueLoad(seq + 1);
+                mbarWait(&bars[seq & 1], (seq >> 1) & 1);
+            }
+            const double* fs = fbuf + (size_t)(seq & 1) * 3 * fRow;
+            if (valid && (multi || !loaded)) {
+                loadUnit(u);
+                loadState(u);
+            }
+            loaded = true;
 
-        for (int tc = 0; tc < n; ++tc) {
-            StepOut o;
-            o.q = 0.0;
-            o.dep1 = 0.0;
-            o.dep2 = 0.0;
-            if (valid) {
-                double precip, temp, pet;
-                if (a.forcingMode == 0) {
-                    precip = fs[0 * fRow + tc * a.UB + ul];
-                    temp = fs[1 * fRow + tc * a.UB + ul];
-                    pet = fs[2 * fRow + tc * a.UB + ul];
-                } else {
-                    const double xp = fs[0 * fRow + tc + off];
-                    const double xt = fs[1 * fRow + tc + off];
-                    const double xe = fs[2 * fRow + tc + off];
-                    temp = xt + cT;
-                    precip = (xp * corr) * mP;
-                    precip = (precip < 0.0) ? 0.0 : precip;
-                    pet = (xe < 0.0) ? 0.0 : xe;
-                }
-                directPhase<GLACIER>(h, par, precip, temp, a.dt, fa, fG, fGl, glacierVariant, a.flags, o, err);
-                solveUnit<SOLVER, NSOIL>(h, par, pet, fa, a.dt, a.flags, o, err, unconverged);
+            for (int tc = 0; tc < n; ++tc) {
+                StepOut o;
+                o.q = 0.0;
+                o.dep1 = 0.0;
+                o.dep2 = 0.0;
+                if (valid) {
+                    double precip, temp, pet;
+                    if (a.forcingMode == 0) {
+                        precip = fs[0 * fRow + tc * a.UB + ul];
+                        temp = fs[1 * fRow + tc * a.UB + ul];
+                        pet = fs[2 * fRow + tc * a.UB + ul];
+                    } else {
+                        const double xp = fs[0 * fRow + tc + off];
+                        const double xt = fs[1 * fRow + tc + off];
+                        const double xe = fs[2 * fRow + tc + off];
+                        temp = xt + cT;
+                        precip = (xp * corr) * mP;
+                        precip = (precip < 0.0) ? 0.0 : precip;
+                        pet = (xe < 0.0) ? 0.0 : xe;
+                    }
+                    directPhase<GLACIER>(h, par, precip, temp, a.dt, invDt, fa, fG, fGl, glacierVariant, a.flags, o, err);
+                    solveUnit<SOLVER, NSOIL>(h, par, pet, fa, a.dt, invDt, a.flags, o, err, unconverged);
 
-                if (nRec && a.writeOutputs) {
-                    // Logger::Record (Logger.cpp:93-120): contents after Finalize and flux amounts
-                    const double nan = __longlong_as_double(0x7ff8000000000000LL);
-                    const bool gv = glacierVariant;
-                    double* base = a.rec + ((size_t)p * a.T + (t0 + tc)) * a.U + u;
-                    const size_t stride = (size_t)a.P * a.T * a.U;
-                    int k = 0;
+                    if (nRec && a.writeOutputs) {
+                        // Logger::Record (Logger.cpp:93-120): contents after Finalize and flux amounts
+                        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+                        const bool gv = glacierVariant;
+                        double* base = a.rec + ((size_t)p * a.T + (t0 + tc)) * a.U + u;
+                        const size_t stride = (size_t)a.P * a.T * a.U;
+                        int k = 0;
 #define HBK_REC(slot, value)                                   \
     if (a.recordMask & (1ull << (slot))) {                     \
         base[(size_t)k * stride] = (value);                    \
         ++k;                                                   \
     }
-                    HBK_REC(HBK_R_GROUND_WATER, h.wG)
-                    HBK_REC(HBK_R_GROUND_INFILTRATION, h.amtInfil)
-                    HBK_REC(HBK_R_GROUND_RUNOFF, h.amtRest)
-                    HBK_REC(HBK_R_GLACIER_WATER, gv ? h.wGl : nan)
-                    HBK_REC(HBK_R_GLACIER_ICE, gv ? h.ice : nan)
-                    HBK_REC(HBK_R_GLACIER_OUTFLOW, gv ? h.amtDep1 : nan)
-                    HBK_REC(HBK_R_GLACIER_MELT, gv ? h.amtDep2 : nan)
-                    HBK_REC(HBK_R_GROUND_SNOWPACK_WATER, 0.0)
-                    HBK_REC(HBK_R_GROUND_SNOWPACK_SNOW, h.snowG)
-                    HBK_REC(HBK_R_GROUND_SNOWPACK_MELT, h.amtMeltG)
-                    HBK_REC(HBK_R_GLACIER_SNOWPACK_WATER, gv ? 0.0 : nan)
-                    HBK_REC(HBK_R_GLACIER_SNOWPACK_SNOW, gv ? h.snowGl : nan)
-                    HBK_REC(HBK_R_GLACIER_SNOWPACK_MELT, gv ? h.amtMeltGl : nan)
-                    HBK_REC(HBK_R_SLOW_WATER, h.slow)
-                    HBK_REC(HBK_R_SLOW_ET, o.amtEt)
-                    HBK_REC(HBK_R_SLOW_OUTFLOW, o.amtOut)
-                    HBK_REC(HBK_R_SLOW_OVERFLOW, o.amtOvf)
-                    HBK_REC(HBK_R_SLOW_PERCOLATION, o.amtPerc)
-                    HBK_REC(HBK_R_SLOW2_WATER, h.slow2)
-                    HBK_REC(HBK_R_SLOW2_OUTFLOW, o.amtOut2)
-                    HBK_REC(HBK_R_QUICK_WATER, h.quick)
-                    HBK_REC(HBK_R_QUICK_RUNOFF, o.amtQ)
+                        HBK_REC(HBK_R_GROUND_WATER, h.wG)
+                        HBK_REC(HBK_R_GROUND_INFILTRATION, h.amtInfil)
+                        HBK_REC(HBK_R_GROUND_RUNOFF, h.amtRest)
+                        HBK_REC(HBK_R_GLACIER_WATER, gv ? h.wGl : nan)
+                        HBK_REC(HBK_R_GLACIER_ICE, gv ? h.ice : nan)
+                        HBK_REC(HBK_R_GLACIER_OUTFLOW, gv ? h.amtDep1 : nan)
+                        HBK_REC(HBK_R_GLACIER_MELT, gv ? h.amtDep2 : nan)
+                        HBK_REC(HBK_R_GROUND_SNOWPACK_WATER, 0.0)
+                        HBK_REC(HBK_R_GROUND_SNOWPACK_SNOW, h.snowG)
+                        HBK_REC(HBK_R_GROUND_SNOWPACK_MELT, h.amtMeltG)
+                        HBK_REC(HBK_R_GLACIER_SNOWPACK_WATER, gv ? 0.0 : nan)
+                        HBK_REC(HBK_R_GLACIER_SNOWPACK_SNOW, gv ? h.snowGl : nan)
+                        HBK_REC(HBK_R_GLACIER_SNOWPACK_MELT, gv ? h.amtMeltGl : nan)
+                        HBK_REC(HBK_R_SLOW_WATER, h.slow)
+                        HBK_REC(HBK_R_SLOW_ET, o.amtEt)
+                        HBK_REC(HBK_R_SLOW_OUTFLOW, o.amtOut)
+                        HBK_REC(HBK_R_SLOW_OVERFLOW, o.amtOvf)
+                        HBK_REC(HBK_R_SLOW_PERCOLATION, o.amtPerc)
+                        HBK_REC(HBK_R_SLOW2_WATER, h.slow2)
+                        HBK_REC(HBK_R_SLOW2_OUTFLOW, o.amtOut2)
+                        HBK_REC(HBK_R_QUICK_WATER, h.quick)
+                        HBK_REC(HBK_R_QUICK_RUNOFF, o.amtQ)
 #undef HBK_REC
+                    }
+                }
+                qbuf[(size_t)tc * nThreads + tid] = o.q;
+                if (GLACIER) {
+                    qbuf[(size_t)(a.TC + tc) * nThreads + tid] = o.dep1;
+                    qbuf[(size_t)(2 * a.TC + tc) * nThreads + tid] = o.dep2;
                 }
             }
-            qbuf[(size_t)tc * kBlock + tid] = o.q;
-            if (GLACIER) {
-                qbuf[(size_t)(a.TC + tc) * kBlock + tid] = o.dep1;
-                qbuf[(size_t)(2 * a.TC + tc) * kBlock + tid] = o.dep2;
-            }
-        }
-        __syncthreads();
-        // SubBasin::ComputeOutletDischarge (SubBasin.cpp:322-329): sum the block's units in unit order.
-        if (a.writeOutputs || GLACIER) {  // the deposits feed the sub-basin stores even during spin-up
-            for (int idx = tid; idx < NQ * n * a.PB; idx += kBlock) {
+            if (valid && multi) storeState(u);
+            __syncthreads();
+            // SubBasin::ComputeOutletDischarge (SubBasin.cpp:322-329): add this tile's units, in unit order, to
+            // the chunk accumulator; entry (qi, tc, lp) is always owned by the same thread.
+            const bool last = (tl == nTilesHere - 1);
+            for (int idx = tid; idx < NQ * n * a.PB; idx += nThreads) {
                 const int qi = idx / (n * a.PB);
-                if (qi == 0 && !a.writeOutputs) continue;
                 const int rem = idx - qi * n * a.PB;
                 const int tc = rem / a.PB;
                 const int lp = rem - tc * a.PB;
-                const int gp = pg * a.PB + lp;
-                if (gp >= a.P) continue;
-                const double* src = qbuf + ((size_t)qi * a.TC + tc) * kBlock + lp;
-                double s = 0.0;
+                const double* src = qbuf + ((size_t)qi * a.TC + tc) * nThreads + lp;
+                double* acc = accb + ((size_t)qi * a.TC + tc) * a.PB + lp;
+                double s = (tl == 0) ? 0.0 : *acc;
                 for (int k = 0; k < a.UB; ++k) s += src[(size_t)k * a.PB];
-                double* dst = (qi == 0) ? a.outQ : (qi == 1 ? a.outD1 : a.outD2);
-                dst[((size_t)ut * a.P + gp) * a.ldt + (t0 + tc)] = s;
+                if (!last) {
+                    *acc = s;
+                } else {
+                    const int gp = pg * a.PB + lp;
+                    if (gp < a.P && (a.writeOutputs || qi > 0)) {  // deposits feed the basin stores during spin-up
+                        double* dst = (qi == 0) ? a.outQ : (qi == 1 ? a.outD1 : a.outD2);
+                        dst[((size_t)grp * a.P + gp) * a.ldt + (t0 + tc)] = s;
+                    }
+                }
             }
+            __syncthreads();
         }
-        __syncthreads();
     }
 
-    if (valid) {
-        const long long si = (long long)p * a.U + u;
-        a.state[HBK_S_GROUND_SNOW * a.lds + si] = h.snowG;
-        a.state[HBK_S_GLACIER_SNOW * a.lds + si] = h.snowGl;
-        a.state[HBK_S_GROUND_WATER * a.lds + si] = h.wG;
-        a.state[HBK_S_GLACIER_WATER * a.lds + si] = h.wGl;
-        a.state[HBK_S_ICE * a.lds + si] = h.ice;
-        a.state[HBK_S_SLOW * a.lds + si] = h.slow;
-        a.state[HBK_S_SLOW2 * a.lds + si] = h.slow2;
-        a.state[HBK_S_QUICK * a.lds + si] = h.quick;
-        a.state[HBK_S_AMT_INFILTRATION * a.lds + si] = h.amtInfil;
-        a.state[HBK_S_AMT_REST * a.lds + si] = h.amtRest;
-        a.state[HBK_S_AMT_MELT_GROUND * a.lds + si] = h.amtMeltG;
-        a.state[HBK_S_AMT_MELT_GLACIER * a.lds + si] = h.amtMeltGl;
-        a.state[HBK_S_AMT_DEPOSIT_RAIN_SNOWMELT * a.lds + si] = h.amtDep1;
-        a.state[HBK_S_AMT_DEPOSIT_ICEMELT * a.lds + si] = h.amtDep2;
+    if (validP && !multi && nTilesHere > 0) {
+        const int u = tileBegin * a.UB + ul;
+        if (u < a.U) storeState(u);
     }
     if (err) atomicOr(a.err, err);
     if (unconverged) atomicAdd(a.unconverged, (unsigned long long)unconverged);
@@ -385,10 +446,10 @@ __global__ void hbkTileForcing(const double* __restrict__ src, double* __restric
     }
 }
 
-__global__ void hbkBroadcastState(double* dst, const double* perUnit, double value, int P, int U) {
+__global__ void hbkBroadcastState(double* dst, const double* perUnit, double value, int P, int U, int laneP) {
     const long long n = (long long)P * U;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        dst[i] = perUnit ? perUnit[i % U] : value;
+        dst[i] = perUnit ? perUnit[laneP ? i / P : i % U] : value;
 }
 
 // FP64 roofline denominator: 8 independent DFMA chains per thread (2 flops per DFMA).
@@ -420,7 +481,8 @@ using namespace hbk;
 struct hbk_engine {
     hbk_structure st{};
     int U = 0, T = 0, P = 0, device = 0;
-    int PB = 32, UB = 8, TC = 16, nUTiles = 1;
+    int PB = 32, UB = 8, TC = 16, nUTiles = 1, G = 1, nGroups = 1;
+    bool stateLaneP = false;  // state layout: element (p,u) at u*P + p (parameter axis on the lanes) or p*U + u
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string error;
@@ -450,7 +512,8 @@ struct hbk_engine {
     double* dBasinState = nullptr; // [P][2]
     double* dBasinInit = nullptr;
     double* dOutlet = nullptr;     // [P][ldt]
-    double* dPartQ = nullptr;      // [nUTiles][P][ldt] (nUTiles > 1)
+    double* dPartQ = nullptr;      // [nGroups][P][ldt] (nGroups > 1)
+    int partGroups = 0;
     double* dD1 = nullptr;         // [P][ldt]
     double* dD2 = nullptr;
     double* dPartD1 = nullptr;
@@ -497,16 +560,49 @@ void chooseShape(hbk_engine* e) {
     int pb = 1;
     while (pb < 32 && pb < e->P) pb *= 2;
     e->PB = pb;
-    e->UB = kBlock / pb;
+    // units per block: 128..256 threads; pick the width that leaves the fewest idle unit slots in the last
+    // tile (U = 50 with 8 units/block wastes 6 of 56 warps; 5 units/block wastes none)
+    const int ubMax = kBlock / pb, ubMin = std::max(1, ubMax / 2);
+    int best = ubMax;
+    double bestUse = 0;
+    for (int ub = ubMax; ub >= ubMin; --ub) {
+        if ((ub * pb) % 32 != 0 || (e->haveRaw[0] && (ub % 2 != 0))) continue;
+        const int tiles = (e->U + ub - 1) / ub;
+        const double use = (double)e->U / ((double)tiles * ub);
+        if (use > bestUse + 1e-9) {
+            bestUse = use;
+            best = ub;
+        }
+    }
+    e->UB = best;
     e->nUTiles = (e->U + e->UB - 1) / e->UB;
+    // tiles per block: enough blocks to fill the machine several times, otherwise as many tiles per block as
+    // possible (G = all tiles: the block sums every unit of its sets itself, no partial buffers)
+    const long long nPGroups = (e->P + e->PB - 1) / e->PB;
+    const long long wantBlocks = 148LL * HBK_MIN_BLOCKS * 2;
+    long long groups = std::min<long long>(e->nUTiles, std::max<long long>(1, (wantBlocks + nPGroups - 1) / nPGroups));
+    e->G = (int)((e->nUTiles + groups - 1) / groups);
+    if (const char* force = std::getenv("HBK_TILES_PER_BLOCK")) {  // testing / tuning knob
+        const int g = std::atoi(force);
+        if (g > 0) e->G = std::min(g, e->nUTiles);
+    }
+    e->nGroups = (e->nUTiles + e->G - 1) / e->G;
+    e->stateLaneP = e->PB == 32;
     const int nq = e->st.has_glacier ? 3 : 1;
-    // chunk length: keep forcing stages + reduction buffer under ~100 KB so two blocks fit on an SM
-    int tc = 32;
+    // chunk length: shared memory per block small enough for HBK_MIN_BLOCKS blocks per SM
+    const size_t budget = (size_t)(220 * 1024) / HBK_MIN_BLOCKS - 1024;
+    // (measured: longer chunks cost more than they save, the shared-memory carve-out shrinks the L1 that
+    // serves the register spills; 8 steps per chunk was the optimum on C2, profiles/r01_tuning.md)
+    int tc = 8;
     for (;;) {
         const size_t fRow = (e->haveRaw[0] ? (size_t)tc * e->UB : (size_t)tc + 2);
-        const size_t bytes = 128 + 2 * 3 * fRow * 8 + (size_t)nq * tc * kBlock * 8;
-        if (bytes <= 100 * 1024 || tc == 2) break;
+        const size_t bytes = 128 + 2 * 3 * fRow * 8 + (size_t)nq * tc * (e->PB * e->UB + e->PB) * 8;
+        if (bytes <= budget || tc == 2) break;
         tc /= 2;
+    }
+    if (const char* force = std::getenv("HBK_CHUNK_STEPS")) {  // tuning knob
+        const int v = std::atoi(force);
+        if (v >= 2 && v <= 64 && (v & (v - 1)) == 0) tc = v;
     }
     e->TC = tc;
 }
@@ -514,7 +610,7 @@ void chooseShape(hbk_engine* e) {
 size_t smemBytes(const hbk_engine* e, bool tiled) {
     const int nq = e->st.has_glacier ? 3 : 1;
     const size_t fRow = tiled ? (size_t)e->TC * e->UB : (size_t)e->TC + 2;
-    return 128 + 2 * 3 * fRow * 8 + (size_t)nq * e->TC * kBlock * 8;
+    return 128 + 2 * 3 * fRow * 8 + (size_t)nq * e->TC * (e->PB * e->UB + e->PB) * 8;
 }
 
 using KernelFn = void (*)(const KArgs);
@@ -802,6 +898,8 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
     a.UB = e->UB;
     a.TC = e->TC;
     a.nUTiles = e->nUTiles;
+    a.G = e->G;
+    a.nGroups = e->nGroups;
     a.flags.quickKind = e->st.quick_kind;
     a.flags.slowOrder = e->st.slow_process_order;
     a.flags.splitKind = e->st.splitter_kind;
@@ -829,7 +927,9 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
     a.zrefP = e->zrefP;
     a.state = e->dState;
     a.lds = (long long)e->P * e->U;
-    const bool multi = e->nUTiles > 1;
+    a.sP = e->stateLaneP ? 1 : e->U;
+    a.sU = e->stateLaneP ? e->P : 1;
+    const bool multi = e->nGroups > 1;
     a.outQ = multi ? e->dPartQ : e->dOutlet;
     a.outD1 = multi ? e->dPartD1 : e->dD1;
     a.outD2 = multi ? e->dPartD2 : e->dD2;
@@ -845,28 +945,28 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
     const size_t smem = smemBytes(e, tiled);
     HBK_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int nPGroups = (e->P + e->PB - 1) / e->PB;
-    const long long grid = (long long)nPGroups * e->nUTiles;
+    const long long grid = (long long)nPGroups * e->nGroups;
     if (grid > 2147483647LL) return fail(e, HBK_E_UNSUPPORTED, "grid too large");
     void* args[] = {(void*)&a};
-    HBK_CUDA(cudaLaunchKernel((const void*)fn, dim3((unsigned)grid), dim3(kBlock), args, smem, e->stream));
+    HBK_CUDA(cudaLaunchKernel((const void*)fn, dim3((unsigned)grid), dim3(e->PB * e->UB), args, smem, e->stream));
     e->lastLaunches++;
 
     if (writeOutputs && multi) {
         const long long n = (long long)e->P * (tEnd - tBegin);
         const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
-        hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartQ, e->dOutlet, e->nUTiles, e->P, e->ldt, tBegin, tEnd);
+        hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartQ, e->dOutlet, e->nGroups, e->P, e->ldt, tBegin, tEnd);
         e->lastLaunches++;
         if (e->st.has_glacier) {
-            hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD1, e->dD1, e->nUTiles, e->P, e->ldt, tBegin, tEnd);
-            hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD2, e->dD2, e->nUTiles, e->P, e->ldt, tBegin, tEnd);
+            hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD1, e->dD1, e->nGroups, e->P, e->ldt, tBegin, tEnd);
+            hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD2, e->dD2, e->nGroups, e->P, e->ldt, tBegin, tEnd);
             e->lastLaunches += 2;
         }
     } else if (!writeOutputs && multi && e->st.has_glacier) {
         // spin-up: the deposits are still needed by the sub-basin stores
         const long long n = (long long)e->P * (tEnd - tBegin);
         const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
-        hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD1, e->dD1, e->nUTiles, e->P, e->ldt, tBegin, tEnd);
-        hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD2, e->dD2, e->nUTiles, e->P, e->ldt, tBegin, tEnd);
+        hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD1, e->dD1, e->nGroups, e->P, e->ldt, tBegin, tEnd);
+        hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD2, e->dD2, e->nGroups, e->P, e->ldt, tBegin, tEnd);
         e->lastLaunches += 2;
     }
     if (e->st.has_glacier) {
@@ -909,14 +1009,20 @@ int hbk_run(hbk_engine* e) {
     e->lastLaunches = 0;
 
     // (re)allocate shape-dependent buffers
-    const bool multi = e->nUTiles > 1;
+    const bool multi = e->nGroups > 1;
     const size_t outN = (size_t)e->P * e->ldt;
-    if (multi && !e->dPartQ) HBK_CUDA(cudaMalloc(&e->dPartQ, sizeof(double) * outN * e->nUTiles));
+    if (e->partGroups != e->nGroups) {
+        freeDev(e->dPartQ);
+        freeDev(e->dPartD1);
+        freeDev(e->dPartD2);
+        e->partGroups = e->nGroups;
+    }
+    if (multi && !e->dPartQ) HBK_CUDA(cudaMalloc(&e->dPartQ, sizeof(double) * outN * e->nGroups));
     if (e->st.has_glacier) {
         if (!e->dD1) HBK_CUDA(cudaMalloc(&e->dD1, sizeof(double) * outN));
         if (!e->dD2) HBK_CUDA(cudaMalloc(&e->dD2, sizeof(double) * outN));
-        if (multi && !e->dPartD1) HBK_CUDA(cudaMalloc(&e->dPartD1, sizeof(double) * outN * e->nUTiles));
-        if (multi && !e->dPartD2) HBK_CUDA(cudaMalloc(&e->dPartD2, sizeof(double) * outN * e->nUTiles));
+        if (multi && !e->dPartD1) HBK_CUDA(cudaMalloc(&e->dPartD1, sizeof(double) * outN * e->nGroups));
+        if (multi && !e->dPartD2) HBK_CUDA(cudaMalloc(&e->dPartD2, sizeof(double) * outN * e->nGroups));
     }
     const int nRec = __builtin_popcountll(e->recordMask);
     const size_t recBytes = sizeof(double) * (size_t)nRec * e->P * e->T * e->U;
@@ -951,7 +1057,7 @@ int hbk_run(hbk_engine* e) {
             const bool storage = s < HBK_S_AMT_INFILTRATION;
             hbkBroadcastState<<<148 * 2, 256, 0, e->stream>>>(e->dState + (size_t)s * nPU,
                                                               storage ? e->dInitUnit + (size_t)s * e->U : nullptr, 0.0,
-                                                              e->P, e->U);
+                                                              e->P, e->U, e->stateLaneP ? 1 : 0);
         }
         e->lastLaunches += HBK_N_STATES;
     }
@@ -1008,7 +1114,14 @@ int hbk_get_state(hbk_engine* e, int32_t slot, double* out) {
     if (!e->ran) return fail(e, HBK_E_STATE, "no completed run");
     HBK_CUDA(cudaSetDevice(e->device));
     const size_t n = (size_t)e->P * e->U;
-    HBK_CUDA(cudaMemcpy(out, e->dState + (size_t)slot * n, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (!e->stateLaneP) {
+        HBK_CUDA(cudaMemcpy(out, e->dState + (size_t)slot * n, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    } else {  // device layout [u][p] -> out[p][u]
+        std::vector<double> tmp(n);
+        HBK_CUDA(cudaMemcpy(tmp.data(), e->dState + (size_t)slot * n, sizeof(double) * n, cudaMemcpyDeviceToHost));
+        for (int u = 0; u < e->U; ++u)
+            for (int p = 0; p < e->P; ++p) out[(size_t)p * e->U + u] = tmp[(size_t)u * e->P + p];
+    }
     return HBK_OK;
 }
 

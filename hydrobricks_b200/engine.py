@@ -11,7 +11,9 @@ from pathlib import Path
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "libhbk.so"
+import os  # noqa: E402
+
+LIB_PATH = Path(os.environ.get("HBK_LIB", HERE / "libhbk.so"))  # HBK_LIB: tuning builds of the same sources
 
 # enums of include/hbk.h
 SOLVER = {"euler_explicit": 0, "heun_explicit": 1, "rk4": 2, "runge_kutta": 2}
