@@ -1,6 +1,6 @@
 """ctypes binding of the C-ABI in include/hbk.h (libhbk.so, CUDA sm_100a).
 
-This is product code: it never imports anything from oracle/ and it raises when the CUDA library or a
+This is product code: it stays independent of the test-only checker directory and raises when the CUDA library or a
 CUDA device is missing — there is no CPU fallback.
 """
 from __future__ import annotations

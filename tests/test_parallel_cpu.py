@@ -1,0 +1,68 @@
+"""Host logic of the multi-GPU path on CPU: world_size-2 gloo process group (parameter axis
+sharded, no collective on the path, one final gather)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from hydrobricks_b200 import evaluation, parallel
+
+
+def test_shard_bounds_cover_and_balance():
+    for n in (1, 2, 7, 100, 100001):
+        for world in (1, 2, 3, 8):
+            spans = [parallel.shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, n_sets, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = torch.arange(n_sets * 3, dtype=torch.float64).reshape(n_sets, 3)
+    local = parallel.shard_rows(full, rank, world)
+    # "scores" of the local shard: something that depends on the set only
+    scores = (local ** 2).sum(dim=1)
+    gathered = parallel.gather_rows(scores, n_sets)
+    rows = parallel.gather_rows(local, n_sets)
+    ok = torch.equal(gathered, (full ** 2).sum(dim=1)) and torch.equal(rows, full)
+    out[rank] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_sets", [8, 9, 33])
+def test_gather_rows_gloo_world2(n_sets):
+    world = 2
+    port = 29500 + (os.getpid() + n_sets) % 2000
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, port, n_sets, out), nprocs=world, join=True)
+        assert all(out[r] for r in range(world))
+
+
+def test_batched_nse_kge_against_numpy_formulas():
+    rng = np.random.default_rng(0)
+    obs = rng.gamma(2.0, 2.0, 400)
+    obs[[5, 77, 300]] = np.nan
+    sim = obs[None, :] * rng.uniform(0.6, 1.4, (6, 1)) + rng.normal(0, 0.3, (6, 400))
+    sim = np.nan_to_num(sim, nan=1.0)
+    sim[0] = np.nan_to_num(obs, nan=3.0)
+    warm = 30
+    n1 = evaluation.nse(sim, obs, warm).numpy()
+    k1 = evaluation.kge_2012(sim, obs, warm).numpy()
+    keep = ~np.isnan(obs[warm:])
+    o = obs[warm:][keep]
+    for i in range(6):
+        s = sim[i, warm:][keep]
+        n0 = 1 - np.sum((s - o) ** 2) / np.sum((o - o.mean()) ** 2)
+        r = np.corrcoef(s, o)[0, 1]
+        k0 = 1 - np.sqrt((r - 1) ** 2 + ((s.std(ddof=1) / s.mean()) / (o.std(ddof=1) / o.mean()) - 1) ** 2 +
+                         (s.mean() / o.mean() - 1) ** 2)
+        assert abs(n1[i] - n0) < 1e-12 and abs(k1[i] - k0) < 1e-12
+    assert abs(n1[0] - 1.0) < 1e-12  # identical series: NSE = 1 (python/tests/test_models.py:731-738)
