@@ -70,7 +70,10 @@ struct Brick {
     int kind, unit;
     bool needsSolver;
     int parent = -1;
+    int genericCover = -1;  // the unit's generic (soil) land cover, for land covers (HydroUnit::GetGenericLandCover)
+    int snowpack = -1;      // '<cover>_snowpack' brick of a land cover
     double areaFraction = 1.0;
+    double initialAreaFraction = 1.0;
     int water = -1, second = -1;  // second: snow (snowpack) or ice (glacier)
     std::vector<int> processes;
 };
@@ -83,6 +86,11 @@ struct Splitter {
 
 struct Record {
     int kind, id;
+};
+
+struct Event {
+    int step, kind, brick;
+    double value;
 };
 
 }  // namespace
@@ -100,6 +108,12 @@ struct hbo_model {
     std::vector<int> basinBricks;
     std::vector<int> outletFluxes;
     std::vector<Record> records;
+    std::vector<Event> events;
+    std::vector<std::pair<int, int>> snowToIce;  // (glacier brick, snowpack brick)
+    std::vector<int> dhBricks;
+    std::vector<double> dhUnitAreas, dhAreas, dhVolumes;
+    int dhRows = 0, dhLastRow = 0;
+    double dhInitialWE = 0;
     const double* forcing[3] = {nullptr, nullptr, nullptr};
     std::vector<double> forcingStore[3];
     double outletTotal = 0;
@@ -741,6 +755,199 @@ void ProcessTimeStep(hbo_model& m, double dt) {
     for (int io : m.outletFluxes) m.outletTotal += FluxGetAmount(m, m.fluxes[io]);
 }
 
+// ---- actions ------------------------------------------------------------------------------------
+
+// LandCover::SetAreaFraction (LandCover.cpp:27-37): push the fraction into the weighted out-fluxes.
+void SetAreaFraction(hbo_model& m, Brick& b, double value) {
+    b.areaFraction = value;
+    for (int ip : b.processes) {
+        for (int io : m.processes[ip].outputs) {
+            Flux& f = m.fluxes[io];
+            if (f.needsWeighting) {
+                f.fractionLandCover = value;
+                f.fractionTotal = f.fractionUnitArea * f.fractionLandCover;
+            }
+        }
+    }
+}
+
+struct Slot {  // HydroUnit.cpp:12-52 (GetContentSlots): role 0 SelfWater, 1 SelfIce, 2 Snow, 3 SnowpackWater
+    int container, role;
+};
+
+std::vector<Slot> ContentSlots(hbo_model& m, const Brick& cover) {
+    std::vector<Slot> slots;
+    auto add = [&](int c, int role) {
+        if (c >= 0 && !m.containers[c].infinite) slots.push_back({c, role});
+    };
+    add(cover.water, 0);
+    if (cover.kind == HBO_BRICK_GLACIER) add(cover.second, 1);
+    if (cover.snowpack >= 0) {
+        add(m.bricks[cover.snowpack].second, 2);
+        add(m.bricks[cover.snowpack].water, 3);
+    }
+    return slots;
+}
+
+// HydroUnit::TransferLandCoverContent (HydroUnit.cpp:384-451)
+void TransferLandCoverContent(hbo_model& m, Brick& changed, double oldFraction, double newFraction, Brick& generic,
+                              double genericOldFraction, double genericNewFraction) {
+    double delta = newFraction - oldFraction;
+    if (NearlyZero(delta, EPSILON_D)) return;
+    Brick *donor, *receiver;
+    double fReceiverOld, fReceiverNew, fDonorNew, strip;
+    if (delta > 0) {
+        donor = &generic;
+        receiver = &changed;
+        fReceiverOld = oldFraction;
+        fReceiverNew = newFraction;
+        fDonorNew = genericNewFraction;
+        strip = delta;
+    } else {
+        donor = &changed;
+        receiver = &generic;
+        fReceiverOld = genericOldFraction;
+        fReceiverNew = genericNewFraction;
+        fDonorNew = newFraction;
+        strip = -delta;
+    }
+    if (NearlyZero(fReceiverNew, EPSILON_D)) return;
+    std::vector<Slot> receiverSlots = ContentSlots(m, *receiver);
+    std::vector<Slot> donorSlots = ContentSlots(m, *donor);
+    auto hasRole = [](const std::vector<Slot>& v, int role) {
+        for (const Slot& s : v)
+            if (s.role == role) return true;
+        return false;
+    };
+    auto depth = [&](const std::vector<Slot>& v, int role) {
+        for (const Slot& s : v)
+            if (s.role == role) return m.containers[s.container].content;
+        return 0.0;
+    };
+    double unmatchedDonorWater = 0;
+    for (const Slot& s : donorSlots) {
+        if ((s.role == 0 || s.role == 3) && !hasRole(receiverSlots, s.role)) {
+            unmatchedDonorWater += m.containers[s.container].content;
+        }
+    }
+    for (const Slot& s : receiverSlots) {
+        double donorDepth = depth(donorSlots, s.role);
+        if (s.role == 0) donorDepth += unmatchedDonorWater;
+        double receiverDepth = m.containers[s.container].content;
+        double newDepth = (receiverDepth * fReceiverOld + donorDepth * strip) / fReceiverNew;
+        m.containers[s.container].content = newDepth;
+    }
+    if (NearlyZero(fDonorNew, EPSILON_D)) {
+        for (const Slot& s : donorSlots) m.containers[s.container].content = 0;
+    }
+}
+
+// HydroUnit::ChangeLandCoverAreaFraction + FixLandCoverFractionsTotal (HydroUnit.cpp:332-374, 459-490)
+void ChangeLandCoverAreaFraction(hbo_model& m, int brickId, double fraction) {
+    if (fraction < 0 || fraction > 1) throw Fail{"land cover fraction not in [0 .. 1]"};
+    Brick& changed = m.bricks[brickId];
+    if (changed.genericCover >= 0 && changed.genericCover != brickId) {
+        Brick& generic = m.bricks[changed.genericCover];
+        double oldFraction = changed.areaFraction;
+        double delta = fraction - oldFraction;
+        double genericOldFraction = generic.areaFraction;
+        double genericNewFraction = genericOldFraction - delta;
+        if (genericNewFraction < 0 - EPSILON_D) throw Fail{"generic land cover not large enough for the area change"};
+        TransferLandCoverContent(m, changed, oldFraction, fraction, generic, genericOldFraction, genericNewFraction);
+    }
+    SetAreaFraction(m, changed, fraction);
+    // FixLandCoverFractionsTotal: the unit's land covers in brick order
+    int genericId = changed.genericCover >= 0 ? changed.genericCover : brickId;
+    double total = 0;
+    for (int ib : m.unitBricks[changed.unit]) {
+        const Brick& b = m.bricks[ib];
+        if (b.kind == HBO_BRICK_GENERIC_LAND_COVER || b.kind == HBO_BRICK_GLACIER) total += b.areaFraction;
+    }
+    if (!NearlyEqual(total, 1.0, EPSILON_D)) {
+        double diff = total - 1.0;
+        Brick& ground = m.bricks[genericId];
+        if (ground.areaFraction < diff - EPSILON_D) throw Fail{"generic land cover not large enough"};
+        if (ground.areaFraction - diff > 0) {
+            SetAreaFraction(m, ground, ground.areaFraction - diff);
+        } else {
+            SetAreaFraction(m, ground, 0);
+        }
+    }
+}
+
+// Action::CheckLandCoverAreaFraction (Action.cpp:71-91)
+double CheckFraction(double fraction) {
+    if (NearlyZero(fraction, PRECISION)) return 0.0;
+    if (NearlyEqual(1, fraction, PRECISION)) return 1.0;
+    if (fraction < 0 || fraction > 1) throw Fail{"The fraction is not in the range [0 .. 1]"};
+    return fraction;
+}
+
+// ActionGlacierEvolutionDeltaH::Apply (ActionGlacierEvolutionDeltaH.cpp:79-142)
+void ApplyDeltaH(hbo_model& m) {
+    const int n = static_cast<int>(m.dhBricks.size());
+    double glacierWE = 0.0;
+    for (int i = 0; i < n; ++i) {
+        Brick& b = m.bricks[m.dhBricks[i]];
+        if (NearlyZero(b.areaFraction, PRECISION)) continue;
+        double area = b.areaFraction * m.dhUnitAreas[i];
+        double brickGlacierWE = m.containers[b.second].content;
+        glacierWE += area * brickGlacierWE;
+    }
+    double glacierRetreatPc = (m.dhInitialWE - glacierWE) / m.dhInitialWE;
+    glacierRetreatPc = std::max(0.0, glacierRetreatPc);
+    int nRows = m.dhRows;
+    double rowPcIncrement = 1.0 / (nRows - 1);
+    int row = static_cast<int>(glacierRetreatPc / rowPcIncrement);
+    if (row != m.dhLastRow) {
+        for (int i = 0; i < n; ++i) {
+            double fraction = m.dhAreas[static_cast<size_t>(row) * n + i] / m.dhUnitAreas[i];
+            fraction = CheckFraction(fraction);
+            ChangeLandCoverAreaFraction(m, m.dhBricks[i], fraction);
+        }
+        m.dhLastRow = row;
+    }
+    double rowVolumeSum = 0;
+    for (int i = 0; i < n; ++i) rowVolumeSum += m.dhVolumes[static_cast<size_t>(row) * n + i];
+    for (int i = 0; i < n; ++i) {
+        Container& ice = m.containers[m.bricks[m.dhBricks[i]].second];
+        double areaGlacier = m.dhAreas[static_cast<size_t>(row) * n + i];
+        if (NearlyZero(areaGlacier, PRECISION)) {
+            ice.content = 0;
+        } else {
+            double volumeRatio = m.dhVolumes[static_cast<size_t>(row) * n + i] / rowVolumeSum;
+            double iceWE = glacierWE * volumeRatio / areaGlacier;
+            ice.content = iceWE;
+        }
+    }
+}
+
+// ActionGlacierSnowToIceTransformation::Apply (ActionGlacierSnowToIceTransformation.cpp:41-74)
+void ApplySnowToIce(hbo_model& m) {
+    for (auto& pr : m.snowToIce) {
+        Brick& glacier = m.bricks[pr.first];
+        if (NearlyZero(glacier.areaFraction, PRECISION)) continue;
+        Container& snow = m.containers[m.bricks[pr.second].second];
+        double snowWE = snow.content;
+        if (snowWE <= 0) continue;
+        Container& ice = m.containers[glacier.second];
+        if (ice.infinite) throw Fail{"Trying to set the content of an infinite storage."};
+        ice.content = ice.content + snowWE;
+        snow.content = 0;
+    }
+}
+
+void ApplyEvents(hbo_model& m, int step) {
+    for (const Event& e : m.events) {
+        if (e.step != step) continue;
+        switch (e.kind) {
+            case HBO_ACT_LAND_COVER_CHANGE: ChangeLandCoverAreaFraction(m, e.brick, e.value); break;
+            case HBO_ACT_SNOW_TO_ICE: ApplySnowToIce(m); break;
+            case HBO_ACT_DELTA_H: ApplyDeltaH(m); break;
+        }
+    }
+}
+
 double RecordValue(const hbo_model& m, const Record& r) {
     switch (r.kind) {
         case HBO_REC_CONTAINER: return m.containers[r.id].content;
@@ -784,7 +991,31 @@ int hbo_add_brick(hbo_model* m, int kind, int unit, int needs_solver, int parent
     return id;
 }
 
-void hbo_set_area_fraction(hbo_model* m, int brick, double fraction) { m->bricks[brick].areaFraction = fraction; }
+void hbo_set_area_fraction(hbo_model* m, int brick, double fraction) {
+    m->bricks[brick].areaFraction = fraction;
+    m->bricks[brick].initialAreaFraction = fraction;
+}
+void hbo_add_event(hbo_model* m, int step, int kind, int brick, double value) {
+    m->events.push_back(Event{step, kind, brick, value});
+}
+void hbo_add_snow_to_ice_unit(hbo_model* m, int glacier_brick, int snowpack_brick) {
+    m->snowToIce.push_back({glacier_brick, snowpack_brick});
+}
+void hbo_set_delta_h(hbo_model* m, int n_units, const int* glacier_bricks, const double* unit_areas, int n_rows,
+                     const double* areas, const double* volumes) {
+    m->dhBricks.assign(glacier_bricks, glacier_bricks + n_units);
+    m->dhUnitAreas.assign(unit_areas, unit_areas + n_units);
+    m->dhRows = n_rows;
+    m->dhAreas.assign(areas, areas + static_cast<size_t>(n_rows) * n_units);
+    m->dhVolumes.assign(volumes, volumes + static_cast<size_t>(n_rows) * n_units);
+    double initialVolume = 0;  // ActionGlacierEvolutionDeltaH.cpp:17-18
+    for (int i = 0; i < n_units; ++i) initialVolume += volumes[i];
+    m->dhInitialWE = initialVolume * 900.0;
+}
+void hbo_set_cover_links(hbo_model* m, int cover_brick, int generic_cover_brick, int snowpack_brick) {
+    m->bricks[cover_brick].genericCover = generic_cover_brick;
+    m->bricks[cover_brick].snowpack = snowpack_brick;
+}
 void hbo_set_parent(hbo_model* m, int brick, int parent_brick) { m->bricks[brick].parent = parent_brick; }
 void hbo_set_target_brick(hbo_model* m, int process, int target_brick) { m->processes[process].targetBrick = target_brick; }
 
@@ -912,6 +1143,13 @@ int hbo_run(hbo_model* m, double* outlet, double* records) {
             f.amount = 0;
             f.changeRate = nullptr;
         }
+        // LandCover::Reset (LandCover.cpp:13-19): extents back to the initial ones; ActionsManager::Reset
+        for (Brick& b : m->bricks) {
+            if (b.kind == HBO_BRICK_GENERIC_LAND_COVER || b.kind == HBO_BRICK_GLACIER) {
+                SetAreaFraction(*m, b, b.initialAreaFraction);
+            }
+        }
+        m->dhLastRow = 0;
         for (int v = 0; v < 3; ++v) {
             if (!m->forcing[v]) {
                 m->forcingStore[v].assign(static_cast<size_t>(m->nSteps) * m->nUnits, 0.0);
@@ -926,7 +1164,16 @@ int hbo_run(hbo_model* m, double* outlet, double* records) {
         }
         m->cursor = 0;
         const size_t nrec = m->records.size();
+        // RewindAfterSpinup (ModelHydro.cpp:167-181): the extents go back to the declared ones
+        if (m->spinupSteps > 0) {
+            for (Brick& b : m->bricks) {
+                if (b.kind == HBO_BRICK_GENERIC_LAND_COVER || b.kind == HBO_BRICK_GLACIER) {
+                    SetAreaFraction(*m, b, b.initialAreaFraction);
+                }
+            }
+        }
         for (int t = 0; t < m->nSteps; ++t) {
+            if (t > 0) ApplyEvents(*m, t);  // TimeMachine::IncrementTime -> ActionsManager::DateUpdate
             ProcessTimeStep(*m, m->dt);
             if (outlet) outlet[t] = m->outletTotal;
             for (size_t r = 0; r < nrec; ++r) records[r * m->nSteps + t] = RecordValue(*m, m->records[r]);

@@ -67,6 +67,20 @@ void hbo_add_outlet_flux(hbo_model* m, int flux);
 void hbo_set_forcing(hbo_model* m, int var, const double* data);
 int hbo_add_record(hbo_model* m, int kind, int id);
 
+/* Dated actions (ActionsManager::DateUpdate, ActionsManager.cpp:80-104), applied between time steps, before
+ * step `step` (>= 1), in the order added for equal steps. Not applied during spin-up (ModelHydro.cpp:141-147). */
+enum { HBO_ACT_LAND_COVER_CHANGE = 0, HBO_ACT_SNOW_TO_ICE = 1, HBO_ACT_DELTA_H = 2 };
+/* land-cover change: `brick` = the changed land-cover brick, value = new area fraction (already checked/snapped).
+ * snow-to-ice: brick = -1 (all glacier units registered with hbo_add_snow_to_ice_unit). delta-h: brick = -1. */
+void hbo_add_event(hbo_model* m, int step, int kind, int brick, double value);
+void hbo_add_snow_to_ice_unit(hbo_model* m, int glacier_brick, int snowpack_brick);
+/* delta-h lookup tables (ActionGlacierEvolutionDeltaH::AddLookupTables): glacier bricks of the table's units,
+ * unit areas, areas/volumes [n_rows][n_units] row-major. */
+void hbo_set_delta_h(hbo_model* m, int n_units, const int* glacier_bricks, const double* unit_areas, int n_rows,
+                     const double* areas, const double* volumes);
+/* generic (soil) land cover and snowpack bricks of a land cover, for the content transfer of a fraction change */
+void hbo_set_cover_links(hbo_model* m, int cover_brick, int generic_cover_brick, int snowpack_brick);
+
 /* Re-applies the land-cover fractions to the weighted fluxes (LandCover::SetAreaFraction). */
 void hbo_finalize_graph(hbo_model* m);
 

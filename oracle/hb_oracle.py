@@ -83,6 +83,11 @@ def lib():
         L.hbo_add_outlet_flux.argtypes = [c_vp, c_int]
         L.hbo_set_forcing.argtypes = [c_vp, c_int, dp]
         L.hbo_add_record.argtypes = [c_vp, c_int, c_int]
+        ipt = ctypes.POINTER(ctypes.c_int)
+        L.hbo_add_event.argtypes = [c_vp, c_int, c_int, c_int, c_dbl]
+        L.hbo_add_snow_to_ice_unit.argtypes = [c_vp, c_int, c_int]
+        L.hbo_set_delta_h.argtypes = [c_vp, c_int, ipt, dp, c_int, dp, dp]
+        L.hbo_set_cover_links.argtypes = [c_vp, c_int, c_int, c_int]
         L.hbo_finalize_graph.argtypes = [c_vp]
         L.hbo_run.argtypes = [c_vp, dp, dp]
         L.hbo_last_error.restype = ctypes.c_char_p
@@ -290,6 +295,17 @@ class OracleModel:
                     child["parent"] = parent
                     self._set_parent(child, parent)
 
+        # links used by the land-cover-change actions (HydroUnit::GetGenericLandCover, '<cover>_snowpack')
+        for iu, u in enumerate(units):
+            st = st_by_id[st_ids[iu]]
+            covers = [b["name"] for b in st["hydro_unit_bricks"] if b["is_land_cover"]]
+            generic = next((n for n in ("open", "ground", "generic", "generic_land_cover") if n in covers), None)
+            for name in covers:
+                sp = self._bricks.get((name + "_snowpack", iu))
+                L.hbo_set_cover_links(h, self._bricks[(name, iu)]["id"],
+                                      self._bricks[(generic, iu)]["id"] if generic else -1, sp["id"] if sp else -1)
+        self._units = units
+
         # Land-cover fractions (SubBasin::AssignFractions, SubBasin.cpp:57-101)
         for iu, u in enumerate(units):
             for name, fraction in u["land_covers"]:
@@ -396,6 +412,33 @@ class OracleModel:
                     else:
                         raise ValueError(f"The target {out['target']} to attach the flux was no found")
                 L.hbo_splitter_add_output(h, sp["id"], fl)
+
+    # -- dated actions (applied before time step `step`, step >= 1) --------------------------------
+    def add_land_cover_change(self, step, unit_index, cover, fraction):
+        b = self._bricks[(cover, unit_index)]
+        self.L.hbo_add_event(self.h, int(step), 0, b["id"], float(fraction))
+
+    def add_snow_to_ice(self, cover, steps):
+        if not getattr(self, "_s2i_done", False):
+            for iu in range(self.n_units):
+                if (cover, iu) in self._bricks:
+                    self.L.hbo_add_snow_to_ice_unit(self.h, self._bricks[(cover, iu)]["id"],
+                                                    self._bricks[(cover + "_snowpack", iu)]["id"])
+            self._s2i_done = True
+        for s in steps:
+            self.L.hbo_add_event(self.h, int(s), 1, -1, 0.0)
+
+    def set_delta_h(self, cover, unit_indices, areas, volumes, steps):
+        areas = np.ascontiguousarray(areas, dtype=np.float64)
+        volumes = np.ascontiguousarray(volumes, dtype=np.float64)
+        n = len(unit_indices)
+        bricks = (ctypes.c_int * n)(*[self._bricks[(cover, iu)]["id"] for iu in unit_indices])
+        ua = np.ascontiguousarray([self._units[iu]["area"] for iu in unit_indices], dtype=np.float64)
+        dp = ctypes.POINTER(ctypes.c_double)
+        self.L.hbo_set_delta_h(self.h, n, bricks, ua.ctypes.data_as(dp), areas.shape[0], areas.ctypes.data_as(dp),
+                               volumes.ctypes.data_as(dp))
+        for s in steps:
+            self.L.hbo_add_event(self.h, int(s), 2, -1, 0.0)
 
     # -- recording (Logger.cpp:93-120; label scheme SettingsModel.cpp:808-841) --------------------
     def record(self, label: str):

@@ -9,7 +9,7 @@ import pytest
 
 import golden_utils as gu
 
-CASES = [b for b in gu.bundles() if not b.startswith("c1_")]
+CASES = [b for b in gu.bundles() if not b.startswith(("c1_", "actions_"))]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -72,3 +72,22 @@ def test_c1_sitter_spatialisation_and_outlet():
     assert gu.same(p[:, 0], extra["spatial_first_p"]) and gu.same(p[:, -1], extra["spatial_last_p"])
     om = gu.run_oracle(meta, {"p": p, "t": t, "pet": pet}, labels=[])
     assert gu.same(om.outlet, outlet)
+
+
+ACTION_CASES = [b for b in gu.bundles("actions_")]
+
+
+@pytest.mark.parametrize("name", ACTION_CASES)
+def test_oracle_actions_match_reference_bit_exact(name):
+    """Dated actions (ActionGlacierEvolutionDeltaH, ActionLandCoverChange, ActionGlacierSnowToIceTransformation):
+    oracle restatement + the host scheduler (hydrobricks_b200/schedule.py) against the reference run."""
+    import sys
+
+    sys.path.insert(0, str(gu.GOLDEN.parent.parent / "tools"))
+    import ref_actions_case as rc
+
+    meta, forcing, outlet, records, extra = gu.load(name)
+    om = rc.run_oracle(meta, forcing, extra["spatial_dh_areas"], extra["spatial_dh_volumes"], meta["labels"])
+    assert gu.same(om.outlet, outlet)
+    for label, ref in records.items():
+        assert gu.same(om.records[label], ref), label

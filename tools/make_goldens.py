@@ -155,6 +155,22 @@ def main():
             bundle(f"gsm_socont_{solver}_{tag}", m, hu, f,
                    "reference Python layer, 10 synthetic bands with slope/glacier, Rhone-Gletsch meteo 1981-1982")
 
+    # Dated actions (SURVEY §8 a21, config C4 in small): delta-h glacier evolution, land-cover changes, snow->ice
+    import ref_actions_case as rc
+
+    for solver, flags in [("rk4", (True, True, True)), ("rk4", (True, False, False)), ("rk4", (False, True, False)),
+                          ("heun_explicit", (True, True, True)), ("euler_explicit", (True, True, True))]:
+        meta, forcing, q, rec, frac, areas, volumes = rc.run_reference(ref, solver, *flags)
+        tag = "".join(n for n, f in zip(("dh", "lc", "s2i"), flags) if f)
+        extra = {"spatial_dh_areas": areas, "spatial_dh_volumes": volumes}
+        for k, v in frac.items():
+            extra["spatial_fraction_" + k] = v
+        keep = ["glacier:ice_content", "glacier:water_content", "ground:water_content",
+                "glacier_snowpack:snow_content", "ground_snowpack:snow_content", "slow_reservoir:water_content",
+                "surface_runoff:water_content", "glacier:melt:output", "glacier:outflow_rain_snowmelt:output"]
+        meta["labels"] = keep
+        save(f"actions_{solver}_{tag}", meta, forcing, q, {k: rec[k] for k in keep}, extra=extra)
+
     # C1: full bundled catchment, 1981-2020, outlet + station series only (fused spatialisation input).
     m, hu, f, params = ref_cases.sitter_socont(hb, solver="rk4", soil_storage_nb=1, end_date="2020-12-31")
     structures, units, fdata, q, rec = ref_cases.collect(m, hu, f)
