@@ -18,6 +18,7 @@ import copy
 import numpy as np
 
 from . import engine as _engine
+from . import schedule as _schedule
 from . import structure as _structure
 
 _FORCING_NAMES = {"precipitation", "pet", "temperature", "temperature_min", "temperature_max", "solar_radiation",
@@ -540,6 +541,54 @@ class ModelHydro:
     def get_sporadic_action_item_count(self):
         return sum(getattr(a, "get_change_count", lambda: 0)() for a in self._actions)
 
+    def _schedule_actions(self):
+        """Translate the registered actions into engine events (kernel boundaries): recursive actions in
+        registration order, then the sporadic items in date order (ActionsManager.cpp:24-104)."""
+        eng = self._engine
+        eng.clear_actions()
+        if not self._actions:
+            return
+        dt = self._cs.hbk.time_step_days
+        pos = {u["id"]: i for i, u in enumerate(self._units)}
+        glacier = self._cs.glacier_name
+        events = []  # (step, order, callable)
+        sporadic = []
+        for order, action in enumerate(self._actions):
+            if isinstance(action, ActionGlacierSnowToIceTransformation):
+                if action.land_cover != glacier:
+                    raise ValueError(f"snow-to-ice: land cover '{action.land_cover}' is not the glacier cover")
+                for k in _schedule.recursive_steps(self._mjd0, self._n_steps, action.month, action.day, dt):
+                    events.append((k, order, lambda k=k: eng.add_snow_to_ice(k)))
+            elif isinstance(action, ActionGlacierEvolutionDeltaH):
+                if action.land_cover != glacier:
+                    raise ValueError(f"delta-h: land cover '{action.land_cover}' is not the glacier cover")
+                try:
+                    units = [pos[int(i)] for i in action.hu_ids]
+                except KeyError as err:
+                    raise ValueError(f"The hydro unit {err} was not found") from err
+                eng.set_delta_h_tables(units, action.areas, action.volumes)
+                for k in _schedule.recursive_steps(self._mjd0, self._n_steps, action.month, 1, dt):
+                    events.append((k, order, lambda k=k: eng.add_delta_h_update(k)))
+            elif isinstance(action, ActionLandCoverChange):
+                for date, unit_id, cover, area in action.changes:
+                    sporadic.append((date, order, unit_id, cover, area))
+            else:
+                raise ValueError(f"Action {type(action).__name__} is not available in the B200 engine")
+        for n, (date, order, unit_id, cover, area) in enumerate(sorted(sporadic, key=lambda c: c[0])):
+            if unit_id not in pos:
+                raise ValueError(f"The hydro unit {unit_id} was not found")
+            u = pos[unit_id]
+            if cover != glacier:
+                # changing the generic cover itself is undone by FixLandCoverFractionsTotal (HydroUnit.cpp:459-490)
+                if cover == self._cs.ground_name:
+                    continue
+                raise ValueError(f"Land cover '{cover}' was not found.")
+            fraction = _schedule.check_fraction(area / self._units[u]["area"])
+            k = _schedule.sporadic_step(self._mjd0, date, dt)
+            events.append((k, 10000 + n, lambda k=k, u=u, f=fraction: eng.add_land_cover_change(k, u, f)))
+        for _, _, add in sorted(events, key=lambda e: (e[0], e[1])):
+            add()
+
     # -- forcing -------------------------------------------------------------------------------------
     def add_time_series(self, ts):
         return self.create_time_series(ts.name, ts.time, ts.ids, ts.data)
@@ -617,14 +666,15 @@ class ModelHydro:
     def run(self):
         if not self._forcing_loaded:
             raise ValueError("Time step processing failed: no forcing attached.")
-        if self._actions:
-            raise ValueError("Dated actions (glacier evolution, land-cover change) are not yet wired into the "
-                             "B200 engine's segment loop; refusing to run without them.")
+        self._schedule_actions()
         if self._pending_sets is None:
             self._pending_sets = self._cs.params[None, :].copy()
         try:
             self._engine.set_parameters(self._pending_sets)
-            self._engine.set_record_mask([self._cs.labels[l] for l in self._labels if l in self._cs.labels])
+            slots = [self._cs.labels[l] for l in self._labels if l in self._cs.labels]
+            if self._labels and (self._settings._log_all or self._settings._record_fractions):
+                slots += ["fraction_ground"] + (["fraction_glacier"] if self._cs.glacier_name else [])
+            self._engine.set_record_mask(slots)
             self._engine.run()
         except _engine.HbkError as err:
             raise ValueError(str(err)) from err
@@ -662,10 +712,11 @@ class ModelHydro:
         return self._engine.get_recorded(self._cs.labels[label], 0)
 
     def get_hydro_unit_fractions(self, label):
-        frac = {self._cs.ground_name: [dict(u["land_covers"]).get(self._cs.ground_name, 1.0) for u in self._units]}
-        if self._cs.glacier_name:
-            frac[self._cs.glacier_name] = [dict(u["land_covers"]).get(self._cs.glacier_name, 0.0) for u in self._units]
-        return np.repeat(np.asarray(frac[label], dtype=np.float64)[None, :], self._n_steps, axis=0)
+        """Logger fraction series (Logger.cpp:111-119): recorded per step, so action-driven changes show."""
+        slot = {self._cs.ground_name: "fraction_ground", self._cs.glacier_name: "fraction_glacier"}.get(label)
+        if slot is None:
+            raise RuntimeError(f"Fraction label '{label}' is not recorded.")
+        return self._engine.get_recorded(slot, 0)
 
     def get_hydro_unit_ids(self):
         return [u["id"] for u in self._units]

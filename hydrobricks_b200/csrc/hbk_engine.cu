@@ -349,6 +349,8 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, HBK_MIN_BLOCKS) hbkRunUnits(c
                         HBK_REC(HBK_R_SLOW2_OUTFLOW, o.amtOut2)
                         HBK_REC(HBK_R_QUICK_WATER, h.quick)
                         HBK_REC(HBK_R_QUICK_RUNOFF, o.amtQ)
+                        HBK_REC(HBK_R_FRACTION_GROUND, fG)
+                        HBK_REC(HBK_R_FRACTION_GLACIER, gv ? fGl : nan)
 #undef HBK_REC
                     }
                 }
@@ -452,6 +454,164 @@ __global__ void hbkBroadcastState(double* dst, const double* perUnit, double val
         dst[i] = perUnit ? perUnit[laneP ? i / P : i % U] : value;
 }
 
+// ---- dated actions (kernel boundaries) ------------------------------------------------------------------
+struct ActArgs {
+    int P, U;
+    double* frac;  // [2][P*U] per set: ground, glacier
+    double* state;
+    long long lds, sP, sU;
+    const double* hru;  // unit constants (area at [1][u])
+    const int* hruFlags;
+    int ldu;
+    int iceInfinite;
+    int* err;
+};
+
+__device__ __forceinline__ double& stateAt(const ActArgs& a, int slot, int p, int u) {
+    return a.state[(size_t)slot * a.lds + (long long)p * a.sP + (long long)u * a.sU];
+}
+
+// HydroUnit::ChangeLandCoverAreaFraction for the glacier cover of unit u, parameter set p: the generic (ground)
+// cover absorbs the area difference and the water / snow column of the strip that changes hands moves with it
+// (HydroUnit.cpp:332-374 ChangeLandCoverAreaFraction, :384-451 TransferLandCoverContent, :459-490 FixLandCoverFractionsTotal).
+__device__ void changeGlacierFraction(const ActArgs& a, int p, int u, double fraction) {
+    const size_t fi = (size_t)p * a.U + u;
+    double& fG = a.frac[fi];
+    double& fGl = a.frac[(size_t)a.P * a.U + fi];
+    if (fraction < 0 || fraction > 1 || !(a.hruFlags[u] & 1)) {
+        atomicOr(a.err, kErrActionFraction);
+        return;
+    }
+    const double oldFraction = fGl;
+    const double delta = fraction - oldFraction;
+    const double genericOld = fG;
+    const double genericNew = genericOld - delta;
+    if (genericNew < 0 - kEpsD) {
+        atomicOr(a.err, kErrActionFraction);
+        return;
+    }
+    if (!nearlyZero(delta, kEpsD)) {
+        double& wG = stateAt(a, HBK_S_GROUND_WATER, p, u);
+        double& wGl = stateAt(a, HBK_S_GLACIER_WATER, p, u);
+        double& snowG = stateAt(a, HBK_S_GROUND_SNOW, p, u);
+        double& snowGl = stateAt(a, HBK_S_GLACIER_SNOW, p, u);
+        double& ice = stateAt(a, HBK_S_ICE, p, u);
+        if (delta > 0) {  // the glacier grows, taking land (and its water column) from the generic cover
+            const double fRO = oldFraction, fRN = fraction, fDN = genericNew, strip = delta;
+            if (!nearlyZero(fRN, kEpsD)) {
+                wGl = (wGl * fRO + wG * strip) / fRN;
+                if (!a.iceInfinite) ice = (ice * fRO + 0.0 * strip) / fRN;
+                snowGl = (snowGl * fRO + snowG * strip) / fRN;
+                if (nearlyZero(fDN, kEpsD)) {
+                    wG = 0;
+                    snowG = 0;
+                }
+            }
+        } else {  // the glacier shrinks, giving land to the generic cover; the ice stays with the glacier
+            const double fRO = genericOld, fRN = genericNew, fDN = fraction, strip = -delta;
+            if (!nearlyZero(fRN, kEpsD)) {
+                wG = (wG * fRO + wGl * strip) / fRN;
+                snowG = (snowG * fRO + snowGl * strip) / fRN;
+                if (nearlyZero(fDN, kEpsD)) {
+                    wGl = 0;
+                    if (!a.iceInfinite) ice = 0;
+                    snowGl = 0;
+                }
+            }
+        }
+    }
+    fGl = fraction;
+    double total = 0;
+    total += fG;
+    total += fGl;
+    if (!(fabs(total - 1.0) <= kEpsD)) {
+        const double diff = total - 1.0;
+        if (fG < diff - kEpsD) {
+            atomicOr(a.err, kErrActionFraction);
+            return;
+        }
+        fG = (fG - diff > 0) ? fG - diff : 0.0;
+    }
+}
+
+__global__ void hbkActLandCoverChange(const ActArgs a, int u, double fraction) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < a.P) changeGlacierFraction(a, p, u, fraction);
+}
+
+// ActionGlacierSnowToIceTransformation::Apply (ActionGlacierSnowToIceTransformation.cpp:41-74)
+__global__ void hbkActSnowToIce(const ActArgs a) {
+    const long long n = (long long)a.P * a.U;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(i / a.U), u = (int)(i % a.U);
+        if (!(a.hruFlags[u] & 1)) continue;
+        if (nearlyZero(a.frac[(size_t)a.P * a.U + i], kPrecision)) continue;
+        double& snow = stateAt(a, HBK_S_GLACIER_SNOW, p, u);
+        if (snow <= 0) continue;
+        if (a.iceInfinite) {
+            atomicOr(a.err, kErrActionInfiniteIce);
+            continue;
+        }
+        double& ice = stateAt(a, HBK_S_ICE, p, u);
+        ice = ice + snow;
+        snow = 0;
+    }
+}
+
+// ActionGlacierEvolutionDeltaH::Apply (ActionGlacierEvolutionDeltaH.cpp:79-142): one thread per parameter set.
+__global__ void hbkActDeltaH(const ActArgs a, int n, const int* units, int nRows, const double* areas,
+                             const double* volumes, double initialWE, int* lastRow) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.P) return;
+    double glacierWE = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const int u = units[i];
+        const double f = a.frac[(size_t)a.P * a.U + (size_t)p * a.U + u];
+        if (nearlyZero(f, kPrecision)) continue;
+        const double area = f * a.hru[1 * a.ldu + u];
+        glacierWE += area * stateAt(a, HBK_S_ICE, p, u);
+    }
+    double retreat = (initialWE - glacierWE) / initialWE;
+    retreat = (0.0 < retreat) ? retreat : 0.0;
+    const double rowInc = 1.0 / (nRows - 1);
+    int row = (int)(retreat / rowInc);
+    row = min(row, nRows - 1);
+    if (row != lastRow[p]) {
+        for (int i = 0; i < n; ++i) {
+            const int u = units[i];
+            double fraction = areas[(size_t)row * n + i] / a.hru[1 * a.ldu + u];
+            if (nearlyZero(fraction, kPrecision)) {  // Action::CheckLandCoverAreaFraction (Action.cpp:71-91)
+                fraction = 0.0;
+            } else if (fabs(1 - fraction) <= kPrecision) {
+                fraction = 1.0;
+            }
+            changeGlacierFraction(a, p, u, fraction);
+        }
+        lastRow[p] = row;
+    }
+    double rowVolumeSum = 0;
+    for (int i = 0; i < n; ++i) rowVolumeSum += volumes[(size_t)row * n + i];
+    for (int i = 0; i < n; ++i) {
+        const int u = units[i];
+        const double areaGlacier = areas[(size_t)row * n + i];
+        double& ice = stateAt(a, HBK_S_ICE, p, u);
+        if (nearlyZero(areaGlacier, kPrecision)) {
+            ice = 0;
+        } else {
+            const double volumeRatio = volumes[(size_t)row * n + i] / rowVolumeSum;
+            ice = glacierWE * volumeRatio / areaGlacier;
+        }
+    }
+}
+
+__global__ void hbkBroadcastFractions(double* dst, const double* init, int P, int U) {
+    const long long n = (long long)P * U;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        dst[i] = init[i % U];
+        dst[n + i] = init[U + i % U];
+    }
+}
+
 // FP64 roofline denominator: 8 independent DFMA chains per thread (2 flops per DFMA).
 __global__ void hbkFp64Peak(double* out, int iters, double seed) {
     double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6,
@@ -526,6 +686,20 @@ struct hbk_engine {
     unsigned long long* dUnconv = nullptr;
     int spinupSteps = 0;
     bool unitsSet = false, ran = false;
+    // dated actions
+    struct Event {
+        int step, kind, unit;  // kind 0 land-cover change, 1 snow->ice, 2 delta-h
+        double value;
+    };
+    std::vector<Event> events;
+    double* dFracSet = nullptr;  // [2][P*U]
+    int* dDhUnits = nullptr;
+    double* dDhAreas = nullptr;
+    double* dDhVolumes = nullptr;
+    int* dDhLastRow = nullptr;
+    int dhUnits = 0, dhRows = 0;
+    double dhInitialWE = 0;
+    std::vector<double> hArea;
     size_t allocP = 0;
     // stats
     double lastMs = 0;
@@ -650,6 +824,8 @@ int ensureSetBuffers(hbk_engine* e, int P) {
     freeDev(e->dGradT);
     freeDev(e->dGradP);
     freeDev(e->dCorrP);
+    freeDev(e->dFracSet);
+    freeDev(e->dDhLastRow);
     e->recBytes = 0;
     e->initPerSet = false;
     e->P = P;
@@ -738,6 +914,11 @@ void hbk_engine_destroy(hbk_engine* e) {
     freeDev(e->dPartD1);
     freeDev(e->dPartD2);
     freeDev(e->dRec);
+    freeDev(e->dFracSet);
+    freeDev(e->dDhUnits);
+    freeDev(e->dDhAreas);
+    freeDev(e->dDhVolumes);
+    freeDev(e->dDhLastRow);
     freeDev(e->dErr);
     freeDev(e->dUnconv);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -759,6 +940,7 @@ int hbk_set_units(hbk_engine* e, const double* area, const double* elevation, co
     for (int u = 0; u < U; ++u) basinArea += area[u];
     std::vector<double> hru((size_t)kNH * e->ldu, 0.0);
     std::vector<int> flags(e->ldu, 0);
+    e->hArea.assign(area, area + U);
     e->hFracG.assign(U, 1.0);
     e->hFracGl.assign(U, 0.0);
     e->hGlacierVariant.assign(U, 0);
@@ -887,6 +1069,121 @@ int hbk_set_record_mask(hbk_engine* e, uint64_t mask) {
     return HBK_OK;
 }
 
+int hbk_clear_actions(hbk_engine* e) {
+    if (!e) return HBK_E_ARG;
+    e->events.clear();
+    e->dhUnits = 0;
+    return HBK_OK;
+}
+
+int hbk_add_land_cover_change(hbk_engine* e, int32_t step, int32_t unit, double fraction) {
+    if (!e || unit < 0 || unit >= e->U || step < 1) return HBK_E_ARG;
+    if (!e->st.has_glacier) return fail(e, HBK_E_MODEL, "land-cover change needs a structure with a glacier cover");
+    if (!e->unitsSet || !e->hGlacierVariant[unit])
+        return fail(e, HBK_E_MODEL, "land-cover change on a hydro unit whose structure variant has no glacier cover");
+    if (fraction < 0 || fraction > 1) return fail(e, HBK_E_MODEL, "The fraction is not in the range [0 .. 1]");
+    e->events.push_back({step, 0, unit, fraction});
+    return HBK_OK;
+}
+
+int hbk_add_snow_to_ice(hbk_engine* e, int32_t step) {
+    if (!e || step < 1) return HBK_E_ARG;
+    if (!e->st.has_glacier) return fail(e, HBK_E_MODEL, "snow-to-ice transformation needs a glacier cover");
+    e->events.push_back({step, 1, -1, 0.0});
+    return HBK_OK;
+}
+
+int hbk_add_delta_h_update(hbk_engine* e, int32_t step) {
+    if (!e || step < 1) return HBK_E_ARG;
+    if (e->dhUnits == 0) return fail(e, HBK_E_STATE, "hbk_set_delta_h_tables has not been called");
+    e->events.push_back({step, 2, -1, 0.0});
+    return HBK_OK;
+}
+
+int hbk_set_delta_h_tables(hbk_engine* e, int32_t n, const int32_t* units, int32_t nRows, const double* areas,
+                           const double* volumes) {
+    if (!e || n <= 0 || !units || nRows < 2 || !areas || !volumes) return HBK_E_ARG;
+    if (!e->unitsSet) return fail(e, HBK_E_STATE, "hbk_set_units must precede hbk_set_delta_h_tables");
+    if (!e->st.has_glacier || e->st.glacier_infinite_storage)
+        return fail(e, HBK_E_MODEL, "glacier evolution needs a glacier cover with a finite ice storage");
+    HBK_CUDA(cudaSetDevice(e->device));
+    // ActionGlacierEvolutionDeltaH::Init (ActionGlacierEvolutionDeltaH.cpp:21-70)
+    std::vector<double> ice(e->U, 0.0);
+    HBK_CUDA(cudaMemcpy(ice.data(), e->dInitUnit + (size_t)HBK_S_ICE * e->U, sizeof(double) * e->U, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) {
+        const int u = units[i];
+        if (u < 0 || u >= e->U) return fail(e, HBK_E_ARG, "delta-h: hydro unit index out of range");
+        if (!e->hGlacierVariant[u]) return fail(e, HBK_E_MODEL, "delta-h: the land cover was not found in a hydro unit");
+        const double areaRef = areas[i];
+        const double areaInModel = e->hFracGl[u] * e->hArea[u];
+        if (std::fabs(areaInModel) <= 1e-8) {
+            double fraction = areaRef / e->hArea[u];
+            if (std::fabs(fraction) <= 1e-8) fraction = 0.0;
+            if (std::fabs(1 - fraction) <= 1e-8) fraction = 1.0;
+            if (fraction < 0 || fraction > 1) return fail(e, HBK_E_MODEL, "delta-h: initial fraction not in [0 .. 1]");
+            e->hFracG[u] -= fraction - e->hFracGl[u];
+            e->hFracGl[u] = fraction;
+        } else if (std::fabs(areaInModel - areaRef) > 1e-8) {
+            return fail(e, HBK_E_MODEL, "The glacier area fraction of a hydro unit does not match the lookup table "
+                                        "initial area.");
+        }
+        ice[u] = volumes[i] * 900.0 / areaRef;  // constants::iceDensity (GlobVars.h:8)
+    }
+    std::vector<double> frac(2 * (size_t)e->U);
+    for (int u = 0; u < e->U; ++u) {
+        frac[u] = e->hFracG[u];
+        frac[e->U + u] = e->hFracGl[u];
+    }
+    HBK_CUDA(cudaMemcpy(e->dFracInit, frac.data(), sizeof(double) * frac.size(), cudaMemcpyHostToDevice));
+    HBK_CUDA(cudaMemcpy(e->dInitUnit + (size_t)HBK_S_ICE * e->U, ice.data(), sizeof(double) * e->U, cudaMemcpyHostToDevice));
+    freeDev(e->dDhUnits);
+    freeDev(e->dDhAreas);
+    freeDev(e->dDhVolumes);
+    HBK_CUDA(cudaMalloc(&e->dDhUnits, sizeof(int) * n));
+    HBK_CUDA(cudaMalloc(&e->dDhAreas, sizeof(double) * (size_t)n * nRows));
+    HBK_CUDA(cudaMalloc(&e->dDhVolumes, sizeof(double) * (size_t)n * nRows));
+    HBK_CUDA(cudaMemcpy(e->dDhUnits, units, sizeof(int) * n, cudaMemcpyHostToDevice));
+    HBK_CUDA(cudaMemcpy(e->dDhAreas, areas, sizeof(double) * (size_t)n * nRows, cudaMemcpyHostToDevice));
+    HBK_CUDA(cudaMemcpy(e->dDhVolumes, volumes, sizeof(double) * (size_t)n * nRows, cudaMemcpyHostToDevice));
+    e->dhUnits = n;
+    e->dhRows = nRows;
+    double initialVolume = 0;
+    for (int i = 0; i < n; ++i) initialVolume += volumes[i];
+    e->dhInitialWE = initialVolume * 900.0;
+    return HBK_OK;
+}
+
+static int applyEvents(hbk_engine* e, int step) {
+    ActArgs a{};
+    a.P = e->P;
+    a.U = e->U;
+    a.frac = e->dFracSet;
+    a.state = e->dState;
+    a.lds = (long long)e->P * e->U;
+    a.sP = e->stateLaneP ? 1 : e->U;
+    a.sU = e->stateLaneP ? e->P : 1;
+    a.hru = e->dHru;
+    a.hruFlags = e->dHruFlags;
+    a.ldu = e->ldu;
+    a.iceInfinite = e->st.glacier_infinite_storage;
+    a.err = e->dErr;
+    const int pBlocks = (e->P + 127) / 128;
+    for (const auto& ev : e->events) {
+        if (ev.step != step) continue;
+        if (ev.kind == 0) {
+            hbkActLandCoverChange<<<pBlocks, 128, 0, e->stream>>>(a, ev.unit, ev.value);
+        } else if (ev.kind == 1) {
+            hbkActSnowToIce<<<148 * 2, 256, 0, e->stream>>>(a);
+        } else {
+            hbkActDeltaH<<<pBlocks, 128, 0, e->stream>>>(a, e->dhUnits, e->dDhUnits, e->dhRows, e->dDhAreas, e->dDhVolumes,
+                                                         e->dhInitialWE, e->dDhLastRow);
+        }
+        e->lastLaunches++;
+    }
+    HBK_CUDA(cudaGetLastError());
+    return HBK_OK;
+}
+
 static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs) {
     const bool tiled = e->haveRaw[0];
     KArgs a{};
@@ -911,7 +1208,7 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
     a.hru = e->dHru;
     a.hruFlags = e->dHruFlags;
     a.ldu = e->ldu;
-    a.frac = e->dFrac;
+    a.frac = e->fracPerSet ? e->dFracSet : e->dFrac;
     a.fracPerSet = e->fracPerSet;
     a.fracLd = e->fracPerSet ? (long long)e->P * e->U : e->U;
     a.forcingMode = tiled ? 0 : 1;
@@ -1063,6 +1360,14 @@ int hbk_run(hbk_engine* e) {
     }
     HBK_CUDA(cudaMemcpyAsync(e->dBasinState, e->dBasinInit, sizeof(double) * 2 * e->P, cudaMemcpyDeviceToDevice, e->stream));
     HBK_CUDA(cudaMemcpyAsync(e->dFrac, e->dFracInit, sizeof(double) * 2 * e->U, cudaMemcpyDeviceToDevice, e->stream));
+    e->fracPerSet = e->events.empty() ? 0 : 1;
+    if (e->fracPerSet) {  // LandCover::Reset + ActionsManager::Reset: initial extents, lookup-table row 0
+        if (!e->dFracSet) HBK_CUDA(cudaMalloc(&e->dFracSet, sizeof(double) * 2 * nPU));
+        if (!e->dDhLastRow) HBK_CUDA(cudaMalloc(&e->dDhLastRow, sizeof(int) * e->P));
+        hbkBroadcastFractions<<<148 * 2, 256, 0, e->stream>>>(e->dFracSet, e->dFracInit, e->P, e->U);
+        HBK_CUDA(cudaMemsetAsync(e->dDhLastRow, 0, sizeof(int) * e->P, e->stream));
+        e->lastLaunches++;
+    }
     HBK_CUDA(cudaMemsetAsync(e->dErr, 0, sizeof(int), e->stream));
     HBK_CUDA(cudaMemsetAsync(e->dUnconv, 0, sizeof(unsigned long long), e->stream));
 
@@ -1071,8 +1376,27 @@ int hbk_run(hbk_engine* e) {
         rc = launchSegment(e, 0, e->spinupSteps, false);
         if (rc) return rc;
     }
-    rc = launchSegment(e, 0, e->T, true);
-    if (rc) return rc;
+    if (e->events.empty()) {
+        rc = launchSegment(e, 0, e->T, true);
+        if (rc) return rc;
+    } else {
+        // kernel boundaries at the action dates (ActionsManager::DateUpdate between two time steps)
+        std::vector<int> steps;
+        for (const auto& ev : e->events)
+            if (ev.step >= 1 && ev.step < e->T) steps.push_back(ev.step);
+        std::sort(steps.begin(), steps.end());
+        steps.erase(std::unique(steps.begin(), steps.end()), steps.end());
+        int t = 0;
+        for (int k : steps) {
+            rc = launchSegment(e, t, k, true);
+            if (rc) return rc;
+            rc = applyEvents(e, k);
+            if (rc) return rc;
+            t = k;
+        }
+        rc = launchSegment(e, t, e->T, true);
+        if (rc) return rc;
+    }
     HBK_CUDA(cudaEventRecord(e->ev1, e->stream));
     HBK_CUDA(cudaStreamSynchronize(e->stream));
     float ms = 0;
@@ -1086,6 +1410,11 @@ int hbk_run(hbk_engine* e) {
     e->ran = true;
     if (err & kErrRateTooHigh)  // WaterContainer.cpp:83-86 throws; ModelHydro::Run fails
         return fail(e, HBK_E_MODEL, "a change rate exceeded 10000 (WaterContainer::ApplyConstraints)");
+    if (err & kErrActionFraction)
+        return fail(e, HBK_E_MODEL, "Application of an action failed: land-cover fraction outside [0 .. 1] or the "
+                                    "generic land cover cannot absorb the area change");
+    if (err & kErrActionInfiniteIce)
+        return fail(e, HBK_E_MODEL, "Trying to set the content of an infinite storage (snow-to-ice on infinite glacier ice)");
     return HBK_OK;
 }
 

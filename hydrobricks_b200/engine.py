@@ -31,7 +31,7 @@ RECORD_SLOTS = [
     "glacier_melt", "ground_snowpack_water", "ground_snowpack_snow", "ground_snowpack_melt",
     "glacier_snowpack_water", "glacier_snowpack_snow", "glacier_snowpack_melt", "slow_water", "slow_et",
     "slow_outflow", "slow_overflow", "slow_percolation", "slow2_water", "slow2_outflow", "quick_water",
-    "quick_runoff",
+    "quick_runoff", "fraction_ground", "fraction_glacier",
 ]
 STATE_SLOTS = [
     "ground_snow", "glacier_snow", "ground_water", "glacier_water", "ice", "slow", "slow2", "quick",
@@ -87,6 +87,11 @@ def load_library():
     L.hbk_save_as_initial_state.argtypes = [vp]
     L.hbk_set_spinup_steps.argtypes = [vp, i32]
     L.hbk_set_record_mask.argtypes = [vp, ctypes.c_uint64]
+    L.hbk_clear_actions.argtypes = [vp]
+    L.hbk_add_land_cover_change.argtypes = [vp, i32, i32, dbl]
+    L.hbk_add_snow_to_ice.argtypes = [vp, i32]
+    L.hbk_set_delta_h_tables.argtypes = [vp, i32, ip, i32, dp, dp]
+    L.hbk_add_delta_h_update.argtypes = [vp, i32]
     L.hbk_run.argtypes = [vp]
     L.hbk_get_outlet.argtypes = [vp, i32, i32, dp]
     L.hbk_get_recorded.argtypes = [vp, i32, i32, dp]
@@ -199,6 +204,27 @@ class Engine:
         for s in slots:
             mask |= 1 << (RECORD_SLOTS.index(s) if isinstance(s, str) else int(s))
         self._check(self.L.hbk_set_record_mask(self.h, mask))
+
+    # dated actions: events fire before time step `step` (>= 1), same-step events in the order added
+    def clear_actions(self):
+        self._check(self.L.hbk_clear_actions(self.h))
+
+    def add_land_cover_change(self, step, unit, glacier_fraction):
+        self._check(self.L.hbk_add_land_cover_change(self.h, int(step), int(unit), float(glacier_fraction)))
+
+    def add_snow_to_ice(self, step):
+        self._check(self.L.hbk_add_snow_to_ice(self.h, int(step)))
+
+    def set_delta_h_tables(self, units, areas, volumes):
+        u = np.ascontiguousarray(units, dtype=np.int32)
+        a = np.ascontiguousarray(areas, dtype=np.float64)
+        v = np.ascontiguousarray(volumes, dtype=np.float64)
+        assert a.shape == v.shape == (a.shape[0], len(u))
+        self._check(self.L.hbk_set_delta_h_tables(self.h, len(u), u.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                                  a.shape[0], _dptr(a), _dptr(v)))
+
+    def add_delta_h_update(self, step):
+        self._check(self.L.hbk_add_delta_h_update(self.h, int(step)))
 
     def run(self):
         self._check(self.L.hbk_run(self.h))

@@ -82,6 +82,7 @@ enum {
     HBK_R_SLOW_WATER, HBK_R_SLOW_ET, HBK_R_SLOW_OUTFLOW, HBK_R_SLOW_OVERFLOW, HBK_R_SLOW_PERCOLATION,
     HBK_R_SLOW2_WATER, HBK_R_SLOW2_OUTFLOW,
     HBK_R_QUICK_WATER, HBK_R_QUICK_RUNOFF,
+    HBK_R_FRACTION_GROUND, HBK_R_FRACTION_GLACIER, /* land-cover fraction series (Logger::RecordFractions) */
     HBK_N_RECORDS
 };
 
@@ -130,6 +131,24 @@ int hbk_save_as_initial_state(hbk_engine* e);
 int hbk_set_spinup_steps(hbk_engine* e, int32_t n_steps);
 /* Selective recorder: bit i of mask = HBK_R_* slot i (Logger.cpp:93-120). Memory = popcount*P*T*U*8 B. */
 int hbk_set_record_mask(hbk_engine* e, uint64_t mask);
+
+/* Dated actions = kernel boundaries (TimeMachine::IncrementTime -> ActionsManager::DateUpdate,
+ * TimeMachine.cpp:49-59, ActionsManager.cpp:80-104). An event fires between time steps, BEFORE step `step`
+ * (1 <= step < n_steps); events of the same step fire in the order they were added (the host adds recursive
+ * actions in registration order, then sporadic items in date order). Not applied during spin-up.
+ *  - land-cover change: ActionLandCoverChange::Apply -> HydroUnit::ChangeLandCoverAreaFraction
+ *    (ActionLandCoverChange.cpp:25-39, HydroUnit.cpp:332-490): new glacier fraction of one unit, the generic
+ *    cover absorbs the difference, the water/snow column of the strip changes hands;
+ *  - snow to ice: ActionGlacierSnowToIceTransformation::Apply (…SnowToIceTransformation.cpp:41-74);
+ *  - delta-h: ActionGlacierEvolutionDeltaH::Apply (…DeltaH.cpp:79-142) with the lookup tables
+ *    areas/volumes[n_rows][n_units] (row-major) of hbk_set_delta_h_tables, which also performs Init
+ *    (…DeltaH.cpp:21-70): checks the initial glacier areas and sets the initial ice content. */
+int hbk_clear_actions(hbk_engine* e);
+int hbk_add_land_cover_change(hbk_engine* e, int32_t step, int32_t unit, double glacier_fraction);
+int hbk_add_snow_to_ice(hbk_engine* e, int32_t step);
+int hbk_set_delta_h_tables(hbk_engine* e, int32_t n_units, const int32_t* units, int32_t n_rows, const double* areas,
+                           const double* volumes);
+int hbk_add_delta_h_update(hbk_engine* e, int32_t step);
 
 /* ModelHydro::Reset + Run (ModelHydro.cpp:100-133, 183-193) for all parameter sets. */
 int hbk_run(hbk_engine* e);
