@@ -398,6 +398,7 @@ class SettingsModel:
                 for b in st["hydro_unit_bricks"] + st["sub_basin_bricks"]:
                     if b["kind"] == kind or (kind == "land_cover" and b["kind"] in ("generic_land_cover", "glacier")):
                         set_in_brick(b)
+                found = True  # SetParameterValueInSelectedStructure falls through to `return true`
         return found
 
     # -- export --------------------------------------------------------------------------------------
@@ -559,6 +560,8 @@ class ModelHydro:
                     raise ValueError(f"snow-to-ice: land cover '{action.land_cover}' is not the glacier cover")
                 for k in _schedule.recursive_steps(self._mjd0, self._n_steps, action.month, action.day, dt):
                     events.append((k, order, lambda k=k: eng.add_snow_to_ice(k)))
+            elif isinstance(action, ActionGlacierEvolutionAreaScaling):
+                raise ValueError("ActionGlacierEvolutionAreaScaling is not available in the B200 engine")
             elif isinstance(action, ActionGlacierEvolutionDeltaH):
                 if action.land_cover != glacier:
                     raise ValueError(f"delta-h: land cover '{action.land_cover}' is not the glacier cover")
@@ -809,6 +812,18 @@ class ActionGlacierEvolutionDeltaH(Action):
 
     def get_lookup_table_volume(self):
         return self.volumes
+
+
+class ActionGlacierEvolutionAreaScaling(ActionGlacierEvolutionDeltaH):
+    """Same table interface as the delta-h action (ActionGlacierEvolutionAreaScaling.h:23-24); its Apply rule is
+    outside the engine's scope and ModelHydro.run() refuses it."""
+
+
+class ParameterModifier:
+    """Time-varying parameters (base/ParameterModifier.h) are outside the engine's scope."""
+
+    def __init__(self, *a, **k):
+        raise RuntimeError("ParameterModifier (time-varying parameters) is not available in the B200 engine.")
 
 
 class ActionGlacierSnowToIceTransformation(Action):

@@ -154,7 +154,7 @@ def set_parameter(structures, component: str, name: str, value) -> bool:
             for b in st["hydro_unit_bricks"] + st["sub_basin_bricks"]:
                 if b["kind"] == kind or (kind == "land_cover" and b["kind"] in ("generic_land_cover", "glacier")):
                     set_in_brick(b)
-            # the reference reports success only through other branches; keep that
+            found = True  # SetParameterValueInSelectedStructure falls through to `return true`
     return found
 
 

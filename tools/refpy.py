@@ -91,7 +91,9 @@ def load_extension(backend):
     if backend == "ref":
         cands = sorted((REPO / "oracle" / "_ref").glob("_hydrobricks*.so"))
     elif backend == "b200":
-        cands = sorted((REPO / "hydrobricks_b200").glob("_hydrobricks*.so"))
+        if str(REPO) not in sys.path:
+            sys.path.insert(0, str(REPO))
+        return importlib.import_module("hydrobricks_b200._hydrobricks")
     else:
         raise ValueError(backend)
     if not cands:
