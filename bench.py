@@ -50,13 +50,33 @@ def station_series(T, seed=42):
     return precip, temp, pet
 
 
-def hydro_units(U, seed=43):
+def hydro_units(U, seed=43, area=1.0e6, glacier=False):
     rng = np.random.Generator(np.random.MT19937(seed))
     step = 2400.0 / U
     elev = 800 + step * (np.arange(U) + 0.5)
     slope = rng.uniform(5, 35, U)
-    return [{"id": i + 1, "area": 1.0e6, "elevation": float(elev[i]), "slope": (float(slope[i]), "deg"),
-             "land_covers": [("ground", 1.0)]} for i in range(U)]
+    units = []
+    for i in range(U):
+        covers = [("ground", 1.0)]
+        if glacier:  # 0 below 2400 m, ramp to 0.8 at 3200 m
+            g = float(np.clip((elev[i] - 2400) / 800 * 0.8, 0, 0.8))
+            covers = [("ground", 1.0 - g), ("glacier", g)]
+        units.append({"id": i + 1, "area": area, "elevation": float(elev[i]), "slope": (float(slope[i]), "deg"),
+                      "land_covers": covers})
+    return units
+
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the headline
+    "c2": dict(sets=100000, units=50, timesteps=10957, glacier=False, soil=1, area=1.0e6,
+               name="C2 Socont-RK4 calibration ensemble"),
+    # configs[2]: 1M HRUs (100 m grid) x 40 years, snow + glacier + soil + groundwater bricks, one parameter set
+    "c3": dict(sets=1, units=1000000, timesteps=14610, glacier=True, soil=2, area=1.0e4,
+               name="C3 synthetic distributed basin, 1M HRUs x 40 y, GSM-Socont"),
+    # configs[4]: solver sweep, 10k sets x 1k HRUs x 10 years
+    "c5": dict(sets=10000, units=1000, timesteps=3653, glacier=False, soil=1, area=1.0e6,
+               name="C5 solver sweep, 10k sets x 1k HRUs x 10 y"),
+}
 
 
 def parameter_sets(P, seed=44):
@@ -279,7 +299,7 @@ def run_engine_arm(args):
 
     # cpu_baseline: rank 0, N=1 only, in a child process BEFORE this process touches CUDA
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.workload == "c2":
         out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
                               "--units", str(args.units), "--timesteps", str(args.timesteps),
                               "--ref-sets-per-core", str(args.ref_sets_per_core)], capture_output=True, text=True)
@@ -295,12 +315,21 @@ def run_engine_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     P, U, T = args.sets, args.units, args.timesteps
-    units = hydro_units(U)
+    wl = WORKLOADS[args.workload]
+    units = hydro_units(U, area=wl["area"], glacier=wl["glacier"])
     precip, temp, pet = station_series(T)
     ps = parameter_sets(P, seed=44 + rank)  # every rank its own shard of the ensemble (weak scaling)
+    if wl["glacier"]:
+        rng = np.random.Generator(np.random.MT19937(91 + rank))
+        ps.update({"a_ice": ps["a_snow"] + rng.uniform(0.5, 6, P), "k_snow": rng.uniform(0.05, 0.6, P),
+                   "k_ice": rng.uniform(0.05, 0.6, P)})
+    if wl["soil"] == 2:
+        rng = np.random.Generator(np.random.MT19937(92 + rank))
+        ps.update({"percol": rng.uniform(0, 10, P), "k_slow_2": ps["k_slow_1"] * rng.uniform(0.05, 0.9, P)})
 
-    m = models.Socont(solver="rk4", soil_storage_nb=1, surface_runoff="socont_runoff", land_cover_names=["ground"],
-                      land_cover_types=["ground"])
+    covers = ["ground", "glacier"] if wl["glacier"] else ["ground"]
+    m = models.Socont(solver=args.solver, soil_storage_nb=wl["soil"], surface_runoff="socont_runoff",
+                      land_cover_names=covers, land_cover_types=covers)
     end = END if T == T_DEFAULT else str(np.datetime64(START) + np.timedelta64(T - 1, "D"))
     m.setup(units, START, end, device=local)
     matrix = m.parameter_matrix(ps, P)
@@ -407,8 +436,9 @@ def run_engine_arm(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "evals_per_s": world * P * args.steps / (dev_ms * 1e-3),
-            "config": {"workload": "C2 Socont-RK4 calibration ensemble", "sets_per_gpu": P, "hydro_units": U,
-                       "timesteps": T, "solver": "rk4", "structure": "socont 1 soil store, runoff:socont",
+            "config": {"workload": wl["name"], "sets_per_gpu": P, "hydro_units": U,
+                       "timesteps": T, "solver": args.solver,
+                       "structure": f"socont {wl['soil']} soil store(s), runoff:socont" + (", glacier (GSM)" if wl["glacier"] else ""),
                        "forcing": "station series + fused elevation-gradient spatialisation",
                        "l2": "256 MiB flush between timed iterations; per-step output 8.8 GB >> L2",
                        "block_shape": "32 parameter sets (lanes) x 4 units per block, all unit tiles time-multiplexed "
@@ -421,7 +451,8 @@ def run_engine_arm(args):
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_fp64, "unit": "TFLOP/s",
                          "frac": achieved / peak_fp64 if peak_fp64 else None, "traffic": None,
-                         "kernel": "hbkRunUnits<RK4,1 soil store,no glacier>", "kernel_ms": main_ms,
+                         "kernel": f"hbkRunUnits<{args.solver},{wl['soil']} soil store(s),{'glacier' if wl['glacier'] else 'no glacier'}>",
+                         "kernel_ms": main_ms,
                          "flops_per_hru_step": FP64_FLOPS_PER_HRU_STEP, "flops_source": FP64_FLOPS_SOURCE,
                          "peak_source": "DFMA micro-benchmark measured in this run (hbk_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 figure",
@@ -443,12 +474,17 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--sets", type=int, default=P_DEFAULT, help="parameter sets per GPU")
-    ap.add_argument("--units", type=int, default=U_DEFAULT)
-    ap.add_argument("--timesteps", type=int, default=T_DEFAULT)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--solver", default="rk4", choices=["rk4", "heun_explicit", "euler_explicit"])
+    ap.add_argument("--sets", type=int, default=None, help="parameter sets per GPU")
+    ap.add_argument("--units", type=int, default=None)
+    ap.add_argument("--timesteps", type=int, default=None)
     ap.add_argument("--ref-sets-per-core", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    for key in ("sets", "units", "timesteps"):
+        if getattr(args, key) is None:
+            setattr(args, key, WORKLOADS[args.workload][key])
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
             return
