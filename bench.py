@@ -333,7 +333,7 @@ def run_engine_arm(args):
     end = END if T == T_DEFAULT else str(np.datetime64(START) + np.timedelta64(T - 1, "D"))
     m.setup(units, START, end, device=local)
     matrix = m.parameter_matrix(ps, P)
-    eng = m.model._engine
+    eng = m.engine(P)
 
     # pinned host staging: the step's inputs and its result
     pin_params = torch.from_numpy(matrix).pin_memory()

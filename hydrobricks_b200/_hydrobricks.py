@@ -659,6 +659,16 @@ class ModelHydro:
     def parameter_slot(self, component, name):
         return self._cs.resolve_all(component, name)
 
+    def base_parameters(self):
+        """float32[HBK_N_PARAMS]: the current single-set parameter vector (engine.PARAM_SLOTS order)."""
+        return self._cs.params.copy()
+
+    def engine_handle(self):
+        return self._engine.h.value
+
+    def get_state(self, state_slot):
+        return self._engine.get_state(state_slot)
+
     # -- run -----------------------------------------------------------------------------------------
     def reset(self):
         self._ran = False

@@ -1,0 +1,348 @@
+// hb_binding.cpp — pybind11 module `_hydrobricks` of the B200 engine: the surface of the reference's module
+// (core/bindings/Binding.cpp:164-413) for the ModelHydro::Run() path, over hb_host.hpp / the C-ABI (libhbk.so).
+// numpy via pybind11/numpy.h (no Eigen). Batched extras: set_parameter_sets, run_batch,
+// get_outlet_discharge_batch, set_station_forcing.
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include "hb_host.hpp"
+
+namespace py = pybind11;
+using namespace pybind11::literals;
+using f64arr = py::array_t<double, py::array::c_style | py::array::forcecast>;
+using f32arr = py::array_t<float, py::array::c_style | py::array::forcecast>;
+using i32arr = py::array_t<int, py::array::c_style | py::array::forcecast>;
+
+namespace {
+
+py::list paramList(const std::vector<hb::Param>& v) {
+    py::list l;
+    for (auto& p : v) l.append(py::dict("name"_a = p.name, "value"_a = (double)p.value));
+    return l;
+}
+py::list outputList(const std::vector<hb::Output>& v) {
+    py::list l;
+    for (auto& o : v)
+        l.append(py::dict("target"_a = o.target, "flux_type"_a = o.fluxType, "instantaneous"_a = o.instantaneous,
+                          "static"_a = o.isStatic));
+    return l;
+}
+py::dict brickDict(const hb::Brick& b) {
+    py::dict d;
+    d["name"] = b.name;
+    d["kind"] = b.kind;
+    d["parent"] = b.parent.empty() ? py::object(py::none()) : py::object(py::cast(b.parent));
+    d["attach"] = b.attach;
+    d["computed_directly"] = b.computedDirectly;
+    d["is_land_cover"] = b.isLandCover;
+    d["is_surface_component"] = b.isSurfaceComponent;
+    d["forcing"] = b.forcing;
+    d["parameters"] = paramList(b.parameters);
+    d["log_items"] = b.logItems;
+    py::list procs;
+    for (auto& p : b.processes)
+        procs.append(py::dict("name"_a = p.name, "kind"_a = p.kind, "forcing"_a = p.forcing,
+                              "outputs"_a = outputList(p.outputs), "parameters"_a = paramList(p.parameters),
+                              "log_items"_a = p.logItems));
+    d["processes"] = procs;
+    return d;
+}
+py::list structureList(const hb::SettingsModel& s) {  // Binding.cpp:119-160 + parameters / log items
+    py::list out;
+    for (auto& st : s.Structures()) {
+        py::list hb_, sb, hs, ss;
+        for (auto& b : st.hydroUnitBricks) hb_.append(brickDict(b));
+        for (auto& b : st.subBasinBricks) sb.append(brickDict(b));
+        auto spl = [](const hb::Splitter& sp) {
+            return py::dict("name"_a = sp.name, "kind"_a = sp.kind, "attach"_a = sp.attach, "forcing"_a = sp.forcing,
+                            "outputs"_a = outputList(sp.outputs), "parameters"_a = paramList(sp.parameters),
+                            "log_items"_a = sp.logItems);
+        };
+        for (auto& sp : st.hydroUnitSplitters) hs.append(spl(sp));
+        for (auto& sp : st.subBasinSplitters) ss.append(spl(sp));
+        out.append(py::dict("id"_a = st.id, "log_items"_a = st.logItems, "hydro_unit_bricks"_a = hb_,
+                            "sub_basin_bricks"_a = sb, "hydro_unit_splitters"_a = hs, "sub_basin_splitters"_a = ss));
+    }
+    return out;
+}
+
+int varIndex(std::string name) {
+    std::transform(name.begin(), name.end(), name.begin(), ::tolower);
+    if (name == "precipitation" || name == "p") return HBK_VAR_PRECIPITATION;
+    if (name == "temperature" || name == "t") return HBK_VAR_TEMPERATURE;
+    if (name == "pet") return HBK_VAR_PET;
+    throw py::value_error("Unknown forcing variable '" + name + "'");
+}
+
+struct LogNull {};
+
+}  // namespace
+
+PYBIND11_MODULE(_hydrobricks, m) {
+    m.doc() = "hydrobricks B200 engine: drop-in for the ModelHydro::Run() path of hydrobricks._hydrobricks";
+    m.attr("__hb_b200__") = true;
+    py::register_exception<hb::Unsupported>(m, "UnsupportedStructure", PyExc_ValueError);
+
+    m.def("init", []() { return true; });
+    m.def("init_log", [](const std::string&) {}, "path"_a);
+    m.def("close_log", []() {});
+    m.def("set_max_log_level", []() {});
+    m.def("set_debug_log_level", []() {});
+    m.def("set_message_log_level", []() {});
+
+    py::class_<hb::SettingsModel>(m, "SettingsModel")
+        .def(py::init<>())
+        .def("log_all", &hb::SettingsModel::SetLogAll, "log_all"_a = true)
+        .def("record_fractions", &hb::SettingsModel::SetRecordFractions, "record"_a = true)
+        .def("add_logging_to", &hb::SettingsModel::AddLoggingToItem, "name"_a)
+        .def("add_brick_logging", &hb::SettingsModel::AddBrickLogging, "name"_a)
+        .def("select_process", &hb::SettingsModel::SelectProcess, "name"_a)
+        .def("add_process_logging", &hb::SettingsModel::AddProcessLogging, "name"_a)
+        .def("add_structure", &hb::SettingsModel::AddStructure)
+        .def("set_solver", &hb::SettingsModel::SetSolver, "name"_a)
+        .def("set_timer", &hb::SettingsModel::SetTimer, "start_date"_a, "end_date"_a, "time_step"_a, "time_step_unit"_a)
+        .def("set_spinup_days", &hb::SettingsModel::SetSpinupDays, "days"_a)
+        .def("add_land_cover_brick", &hb::SettingsModel::AddLandCoverBrick, "name"_a, "kind"_a)
+        .def("add_hydro_unit_brick", &hb::SettingsModel::AddHydroUnitBrick, "name"_a, "kind"_a = "storage")
+        .def("add_sub_basin_brick", &hb::SettingsModel::AddSubBasinBrick, "name"_a, "kind"_a = "storage")
+        .def("select_hydro_unit_brick", &hb::SettingsModel::SelectHydroUnitBrickByName, "name"_a)
+        .def("add_brick_process", &hb::SettingsModel::AddBrickProcess, "name"_a, "kind"_a, "target"_a = "", "log"_a = false)
+        .def("add_process_output", [](hb::SettingsModel& s, const std::string& t) { s.AddProcessOutput(t); }, "target"_a)
+        .def("add_process_parameter", &hb::SettingsModel::AddProcessParameter, "name"_a, "value"_a, "kind"_a = "constant")
+        .def("set_process_parameter_value", &hb::SettingsModel::SetProcessParameterValue, "name"_a, "value"_a,
+             "kind"_a = "constant")
+        .def("add_process_forcing", &hb::SettingsModel::AddProcessForcing, "name"_a)
+        .def("add_brick_parameter", &hb::SettingsModel::AddBrickParameter, "name"_a, "value"_a, "kind"_a = "constant")
+        .def("add_brick_forcing", &hb::SettingsModel::AddBrickForcing, "name"_a)
+        .def("set_current_brick_computed_directly", &hb::SettingsModel::SetCurrentBrickComputedDirectly)
+        .def("set_parameter_value", &hb::SettingsModel::SetParameterValue, "component"_a, "name"_a, "value"_a)
+        .def("generate_precipitation_splitters", &hb::SettingsModel::GeneratePrecipitationSplitters, "with_snow"_a = true,
+             "splitter_type"_a = "snow_rain:linear")
+        .def("generate_snowpacks", &hb::SettingsModel::GenerateSnowpacks, "snow_melt_process"_a)
+        .def("generate_snowpacks_with_water_retention",
+             [](hb::SettingsModel& s, py::args, py::kwargs) { s.Unsupported("snowpack water retention"); })
+        .def("generate_canopy_interception",
+             [](hb::SettingsModel& s, py::args, py::kwargs) { s.Unsupported("canopy interception"); })
+        .def("add_snowpack_refreezing", [](hb::SettingsModel& s, py::args, py::kwargs) { s.Unsupported("snowpack refreezing"); })
+        .def("add_snowpack_sublimation", [](hb::SettingsModel& s, py::args, py::kwargs) { s.Unsupported("snowpack sublimation"); })
+        .def("add_snow_ice_transformation",
+             [](hb::SettingsModel& s, py::args, py::kwargs) { s.Unsupported("snow to ice transformation process"); })
+        .def("add_snow_redistribution", [](hb::SettingsModel& s, py::args, py::kwargs) { s.Unsupported("snow redistribution"); })
+        .def("set_process_outputs_as_instantaneous", &hb::SettingsModel::SetProcessOutputsAsInstantaneous)
+        .def("set_process_outputs_as_static", &hb::SettingsModel::SetProcessOutputsAsStatic)
+        .def("get_structure", [](hb::SettingsModel& s) { return structureList(s); })
+        .def("get_solver_name", [](hb::SettingsModel& s) { return s.solver; })
+        .def("get_hydro_unit_log_labels", &hb::SettingsModel::GetHydroUnitLogLabels)
+        .def("get_timer", [](hb::SettingsModel& s) {
+            return py::dict("start"_a = s.timerStart, "end"_a = s.timerEnd, "time_step"_a = s.timeStep,
+                            "time_step_unit"_a = s.timeStepUnit, "spinup_days"_a = s.spinupDays);
+        });
+
+    py::class_<hb::SettingsBasin>(m, "SettingsBasin")
+        .def(py::init<>())
+        .def("add_hydro_unit", &hb::SettingsBasin::AddHydroUnit, "id"_a, "area"_a, "elevation"_a = -9999)
+        .def("add_land_cover", &hb::SettingsBasin::AddLandCover, "name"_a, "kind"_a, "fraction"_a)
+        .def("add_hydro_unit_property_str", &hb::SettingsBasin::AddHydroUnitPropertyString, "name"_a, "value"_a)
+        .def("add_hydro_unit_property_double", &hb::SettingsBasin::AddHydroUnitPropertyDouble, "name"_a, "value"_a, "unit"_a)
+        .def("add_lateral_connection", &hb::SettingsBasin::AddLateralConnection, "giver_hydro_unit_id"_a,
+             "receiver_hydro_unit_id"_a, "fraction"_a, "type"_a = "")
+        .def("get_lateral_connection_count", &hb::SettingsBasin::GetLateralConnectionCount)
+        .def("clear", &hb::SettingsBasin::Clear);
+
+    py::class_<hb::Action>(m, "Action").def(py::init<>());
+    py::class_<hb::ActionLandCoverChange, hb::Action>(m, "ActionLandCoverChange")
+        .def(py::init<>())
+        .def("add_change", &hb::ActionLandCoverChange::AddChange, "date"_a, "hydro_unit_id"_a, "land_cover"_a, "area"_a)
+        .def("get_change_count", &hb::ActionLandCoverChange::GetChangeCount)
+        .def("get_land_cover_count", &hb::ActionLandCoverChange::GetLandCoverCount);
+    auto addTables = [](hb::ActionGlacierEvolutionDeltaH& a, int month, const std::string& cover, const i32arr& ids,
+                        const f64arr& areas, const f64arr& volumes) {
+        if (areas.ndim() != 2 || volumes.ndim() != 2 || areas.shape(1) != ids.size() || volumes.shape(0) != areas.shape(0) ||
+            volumes.shape(1) != areas.shape(1))
+            throw py::value_error("lookup tables must be [rows x units]");
+        a.AddLookupTables(month, cover, std::vector<int>(ids.data(), ids.data() + ids.size()), (int)areas.shape(0),
+                          std::vector<double>(areas.data(), areas.data() + areas.size()),
+                          std::vector<double>(volumes.data(), volumes.data() + volumes.size()));
+    };
+    py::class_<hb::ActionGlacierEvolutionDeltaH, hb::Action>(m, "ActionGlacierEvolutionDeltaH")
+        .def(py::init<>())
+        .def("add_lookup_tables", addTables, "month_num"_a, "land_cover"_a, "hu_ids"_a, "areas"_a, "volumes"_a)
+        .def("get_land_cover_name", [](hb::ActionGlacierEvolutionDeltaH& a) { return a.cover; })
+        .def("get_hydro_unit_ids", [](hb::ActionGlacierEvolutionDeltaH& a) { return i32arr(a.unitIds.size(), a.unitIds.data()); })
+        .def("get_lookup_table_area", [](hb::ActionGlacierEvolutionDeltaH& a) {
+            f64arr out({(py::ssize_t)a.rows, (py::ssize_t)a.unitIds.size()});
+            std::copy(a.areas.begin(), a.areas.end(), out.mutable_data());
+            return out;
+        })
+        .def("get_lookup_table_volume", [](hb::ActionGlacierEvolutionDeltaH& a) {
+            f64arr out({(py::ssize_t)a.rows, (py::ssize_t)a.unitIds.size()});
+            std::copy(a.volumes.begin(), a.volumes.end(), out.mutable_data());
+            return out;
+        });
+    py::class_<hb::ActionGlacierEvolutionAreaScaling, hb::ActionGlacierEvolutionDeltaH>(m, "ActionGlacierEvolutionAreaScaling")
+        .def(py::init<>());
+    py::class_<hb::ActionGlacierSnowToIceTransformation, hb::Action>(m, "ActionGlacierSnowToIceTransformation")
+        .def(py::init<int, int, const std::string&>(), "month"_a, "day"_a, "land_cover"_a)
+        .def("get_land_cover_name", [](hb::ActionGlacierSnowToIceTransformation& a) { return a.cover; });
+
+    py::class_<hb::ModelHydro>(m, "ModelHydro")
+        .def(py::init<>())
+        .def("init_with_basin", &hb::ModelHydro::InitializeWithBasin, "model_settings"_a, "basin_settings"_a, "device"_a = 0,
+             py::keep_alive<1, 2>())
+        .def("is_valid", &hb::ModelHydro::IsValid)
+        .def("add_action", &hb::ModelHydro::AddAction, "action"_a, py::keep_alive<1, 2>())
+        .def("get_action_count", &hb::ModelHydro::GetActionCount)
+        .def("get_sporadic_action_item_count", &hb::ModelHydro::GetSporadicActionItemCount)
+        .def("create_time_series",
+             [](hb::ModelHydro& mh, const std::string& name, const f64arr& time, const i32arr& ids, const f64arr& data) {
+                 if (data.ndim() != 2 || data.shape(0) != time.size() || data.shape(1) != ids.size()) return false;
+                 return mh.CreateTimeSeries(name, time.data(), (int)time.size(), ids.data(), (int)ids.size(), data.data());
+             },
+             "data_name"_a, "time"_a, "ids"_a, "data"_a)
+        .def("clear_time_series", &hb::ModelHydro::ClearTimeSeries)
+        .def("attach_time_series_to_hydro_units", &hb::ModelHydro::AttachTimeSeriesToHydroUnits)
+        .def("forcing_loaded", &hb::ModelHydro::ForcingLoaded)
+        .def("set_station_forcing",
+             [](hb::ModelHydro& mh, const std::string& var, const f64arr& series, double zref, py::object gradient,
+                py::object correction) {
+                 f64arr g, c;
+                 double gs = 0, cs = 1;
+                 const double *gp = nullptr, *cp = nullptr;
+                 if (py::isinstance<py::float_>(gradient) || py::isinstance<py::int_>(gradient)) {
+                     gs = gradient.cast<double>();
+                 } else {
+                     g = gradient.cast<f64arr>();
+                     gp = g.data();
+                 }
+                 if (py::isinstance<py::float_>(correction) || py::isinstance<py::int_>(correction)) {
+                     cs = correction.cast<double>();
+                 } else {
+                     c = correction.cast<f64arr>();
+                     cp = c.data();
+                 }
+                 mh.SetStationForcing(varIndex(var), series.data(), (int)series.size(), zref, gs, gp, cs, cp);
+             },
+             "variable"_a, "series"_a, "ref_elevation"_a = 0.0, "gradient"_a = 0.0, "correction"_a = 1.0)
+        .def("update_parameters", &hb::ModelHydro::UpdateParameters, "model_settings"_a)
+        .def("set_parameter_sets",
+             [](hb::ModelHydro& mh, const f32arr& v) {
+                 if (v.ndim() != 2 || v.shape(1) != HBK_N_PARAMS) throw py::value_error("expected [n_sets x HBK_N_PARAMS]");
+                 mh.SetParameterSets(v.data(), (int)v.shape(0));
+             },
+             "values"_a)
+        .def("parameter_slot", &hb::ModelHydro::ParameterSlot, "component"_a, "name"_a)
+        .def("base_parameters", [](hb::ModelHydro& mh) {
+            auto v = mh.BaseParameters();
+            return f32arr(v.size(), v.data());
+        })
+        .def("reset", &hb::ModelHydro::Reset)
+        .def("save_as_initial_state", &hb::ModelHydro::SaveAsInitialState)
+        .def("run", [](hb::ModelHydro& mh) { mh.Run(true); }, py::call_guard<py::gil_scoped_release>())
+        .def("run_batch",
+             [](hb::ModelHydro& mh, const f32arr& v, bool record) {
+                 if (v.ndim() != 2 || v.shape(1) != HBK_N_PARAMS) throw py::value_error("expected [n_sets x HBK_N_PARAMS]");
+                 mh.SetParameterSets(v.data(), (int)v.shape(0));
+                 {
+                     py::gil_scoped_release nogil;
+                     mh.Run(record);
+                 }
+                 f64arr out({(py::ssize_t)mh.SetCount(), (py::ssize_t)mh.StepCount()});
+                 mh.GetOutlet(0, mh.SetCount(), out.mutable_data());
+                 return out;
+             },
+             "parameter_sets"_a, "record"_a = false)
+        .def("get_outlet_discharge", [](hb::ModelHydro& mh) {
+            f64arr out(mh.StepCount());
+            mh.GetOutlet(0, 1, out.mutable_data());
+            return out;
+        })
+        .def("get_outlet_discharge_batch", [](hb::ModelHydro& mh) {
+            f64arr out({(py::ssize_t)mh.SetCount(), (py::ssize_t)mh.StepCount()});
+            mh.GetOutlet(0, mh.SetCount(), out.mutable_data());
+            return out;
+        })
+        .def("get_total_outlet_discharge", [](hb::ModelHydro& mh) {
+            std::vector<double> q(mh.StepCount());
+            mh.GetOutlet(0, 1, q.data());
+            double s = 0;
+            for (double v : q) s += v;
+            return s;
+        })
+        .def("get_recorded_hydro_unit_labels", &hb::ModelHydro::GetRecordedHydroUnitLabels)
+        .def("get_recorded_hydro_unit_fraction_labels", &hb::ModelHydro::GetRecordedHydroUnitFractionLabels)
+        .def("get_hydro_unit_values", [](hb::ModelHydro& mh, const std::string& label) {
+            f64arr out({(py::ssize_t)mh.StepCount(), (py::ssize_t)mh.UnitCount()});
+            mh.GetHydroUnitValues(label, 0, out.mutable_data());
+            return out;
+        }, "label"_a)
+        .def("get_hydro_unit_fractions", [](hb::ModelHydro& mh, const std::string& label) {
+            f64arr out({(py::ssize_t)mh.StepCount(), (py::ssize_t)mh.UnitCount()});
+            mh.GetHydroUnitFractions(label, out.mutable_data());
+            return out;
+        }, "label"_a)
+        .def("get_hydro_unit_ids", &hb::ModelHydro::GetHydroUnitIds)
+        .def("get_hydro_unit_areas", [](hb::ModelHydro& mh) {
+            auto a = mh.GetHydroUnitAreas();
+            return f64arr(a.size(), a.data());
+        })
+        .def("get_state", [](hb::ModelHydro& mh, int slot) {
+            f64arr out({(py::ssize_t)mh.SetCount(), (py::ssize_t)mh.UnitCount()});
+            mh.GetState(slot, out.mutable_data());
+            return out;
+        }, "state_slot"_a)
+        // water-balance totals (Logger.cpp:168-339): area-weighted ET sum, end-of-run storage contents
+        .def("get_total_et", [](hb::ModelHydro& mh) {
+            const int T = mh.StepCount(), U = mh.UnitCount();
+            std::vector<double> et((size_t)T * U);
+            mh.GetRecorded(HBK_R_SLOW_ET, 0, et.data());
+            auto areas = mh.GetHydroUnitAreas();
+            double total = 0, sum = 0;
+            for (double a : areas) total += a;
+            for (int t = 0; t < T; ++t)
+                for (int u = 0; u < U; ++u) {
+                    double v = et[(size_t)t * U + u];
+                    if (v == v) sum += v * (areas[u] / total);
+                }
+            return sum;
+        })
+        .def("get_total_water_storage_changes", [](hb::ModelHydro& mh) {
+            const int U = mh.UnitCount(), P = mh.SetCount();
+            std::vector<double> g, gl, buf((size_t)P * U);
+            mh.fractions(g, gl);
+            auto areas = mh.GetHydroUnitAreas();
+            double total = 0, sum = 0;
+            for (double a : areas) total += a;
+            const int slots[5] = {HBK_S_GROUND_WATER, HBK_S_GLACIER_WATER, HBK_S_SLOW, HBK_S_SLOW2, HBK_S_QUICK};
+            for (int k = 0; k < 5; ++k) {
+                mh.GetState(slots[k], buf.data());
+                for (int u = 0; u < U; ++u) sum += buf[u] * (k == 0 ? g[u] : (k == 1 ? gl[u] : 1.0)) * (areas[u] / total);
+            }
+            if (mh.compiled().st.has_glacier) {
+                std::vector<double> b((size_t)P * 2);
+                mh.GetBasinState(b.data());
+                sum += b[0] + b[1];
+            }
+            return sum;
+        })
+        .def("get_total_snow_storage_changes", [](hb::ModelHydro& mh) {
+            const int U = mh.UnitCount(), P = mh.SetCount();
+            std::vector<double> g, gl, buf((size_t)P * U);
+            mh.fractions(g, gl);
+            auto areas = mh.GetHydroUnitAreas();
+            double total = 0, sum = 0;
+            for (double a : areas) total += a;
+            mh.GetState(HBK_S_GROUND_SNOW, buf.data());
+            for (int u = 0; u < U; ++u) sum += buf[u] * g[u] * (areas[u] / total);
+            mh.GetState(HBK_S_GLACIER_SNOW, buf.data());
+            for (int u = 0; u < U; ++u) sum += buf[u] * gl[u] * (areas[u] / total);
+            return sum;
+        })
+        .def("dump_outputs", [](hb::ModelHydro&, const std::string&) -> bool {
+            throw std::runtime_error("dump_outputs (netCDF) is outside the hot path and not available in the B200 engine.");
+        }, "path"_a)
+        .def("engine_handle", [](hb::ModelHydro& mh) { return (std::uintptr_t)mh.engine(); },
+             "Raw hbk_engine* (for hydrobricks_b200.engine.Engine.from_handle: device pointers, stream, statistics).");
+
+    py::class_<LogNull>(m, "LogNull").def(py::init<>());
+}

@@ -1,0 +1,1288 @@
+// hb_host.hpp — C++ host side above the C-ABI (include/hbk.h): the classes the reference exposes through its
+// pybind11 module for the ModelHydro::Run() path, re-implemented for the B200 engine.
+//
+//   hb::SettingsModel   base/SettingsModel.{h,cpp}   declarative select-then-add structure builder
+//   hb::SettingsBasin   base/SettingsBasin.{h,cpp}
+//   hb::Compiled        structure compiler: SettingsModel -> per-structure process table (hbk_structure),
+//                       float32 parameter slots, log-label -> recorder-slot map (ModelBuilder.cpp:36-240, 448-727
+//                       is the wiring it recognises)
+//   hb::ModelHydro      base/ModelHydro.{h,cpp} on top of hbk_engine; actions scheduled like
+//                       TimeMachine::IncrementTime -> ActionsManager::DateUpdate (ActionsManager.cpp:80-104)
+// Same method names and error behaviour as the reference classes (std::runtime_error where the reference throws,
+// std::invalid_argument -> ValueError where its binding raises py::value_error). Header-only; hb_binding.cpp wraps
+// it for Python. Nothing here computes hydrology: all arithmetic is in the CUDA engine.
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <cstdio>
+#include <map>
+#include <memory>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/hbk.h"
+
+namespace hb {
+
+using std::string;
+using std::vector;
+
+struct Param {
+    string name;
+    float value;
+};
+struct Output {
+    string target;
+    string fluxType = "water";
+    bool instantaneous = false;
+    bool isStatic = false;
+};
+struct Process {
+    string name, kind;
+    vector<string> forcing, logItems;
+    vector<Output> outputs;
+    vector<Param> parameters;
+};
+struct Brick {
+    string name, kind, parent, attach;
+    bool computedDirectly = false, isLandCover = false, isSurfaceComponent = false;
+    vector<string> forcing, logItems;
+    vector<Param> parameters;
+    vector<Process> processes;
+};
+struct Splitter {
+    string name, kind, attach;
+    vector<string> forcing, logItems;
+    vector<Output> outputs;
+    vector<Param> parameters;
+};
+struct Structure {
+    int id = 1;
+    vector<string> logItems;
+    vector<Brick> hydroUnitBricks, subBasinBricks;
+    vector<Splitter> hydroUnitSplitters, subBasinSplitters;
+};
+
+inline bool isForcingName(const string& n) {
+    static const std::set<string> k = {"precipitation", "pet", "temperature", "temperature_min", "temperature_max",
+                                       "solar_radiation", "r_solar"};
+    return k.count(n) > 0;
+}
+
+// Process::RegisterSettings of the reference (processes/Process*.cpp RegisterProcessSettings): default parameters
+// and forcing of the process types the engine runs.
+struct ProcessDefaults {
+    vector<Param> params;
+    vector<string> forcing;
+};
+inline const std::map<string, ProcessDefaults>& processRegistry() {
+    static const std::map<string, ProcessDefaults> r = {
+        {"melt:degree_day", {{{"degree_day_factor", 3.0f}, {"melting_temperature", 0.0f}}, {"temperature"}}},
+        {"et:socont", {{}, {"pet"}}},
+        {"infiltration:socont", {{}, {}}},
+        {"runoff:socont", {{{"beta", 500.0f}}, {}}},
+        {"outflow:linear", {{{"response_factor", 0.2f}}, {}}},
+        {"outflow:direct", {{}, {}}},
+        {"outflow:rest", {{}, {}}},
+        {"overflow", {{}, {}}},
+        {"outflow:overflow", {{}, {}}},
+        {"percolation:constant", {{{"percolation_rate", 0.1f}}, {}}},
+    };
+    return r;
+}
+
+class SettingsModel {
+  public:
+    SettingsModel() {
+        _structures.emplace_back();
+        _structures.back().id = 1;
+        _selStructure = 0;
+    }
+
+    // ---- options
+    void SetLogAll(bool v = true) { _logAll = v; }
+    void SetRecordFractions(bool v = true) { _recordFractions = v; }
+    bool LogAll() const { return _logAll; }
+    bool RecordsFractions() const { return _recordFractions; }
+    void SetSolver(const string& name) { solver = name; }
+    void SetTimer(const string& start, const string& end, int step, const string& unit) {
+        timerStart = start;
+        timerEnd = end;
+        timeStep = step;
+        timeStepUnit = unit;
+    }
+    void SetSpinupDays(int days) {
+        if (days < 0) throw std::invalid_argument("The spin-up duration cannot be negative.");
+        spinupDays = days;
+    }
+
+    // ---- structures
+    int AddStructure() {
+        int id = 0;
+        for (auto& s : _structures) id = std::max(id, s.id);
+        _structures.emplace_back();
+        _structures.back().id = id + 1;
+        _selStructure = (int)_structures.size() - 1;
+        _selBrick = {-1, -1};
+        _selProcess = -1;
+        _selSplitter = -1;
+        return id + 1;
+    }
+    int GetStructureCount() const { return (int)_structures.size(); }
+    const vector<Structure>& Structures() const { return _structures; }
+
+    // ---- bricks
+    void AddHydroUnitBrick(const string& name, const string& kind = "storage") { addBrick(false, name, kind); }
+    void AddSubBasinBrick(const string& name, const string& kind = "storage") { addBrick(true, name, kind); }
+    void AddLandCoverBrick(const string& name, const string& kind) {
+        addBrick(false, name, kind);
+        brick().isLandCover = true;
+        if (selectSplitterIfFound("rain_splitter")) addSplitterOutput(name, "water");  // SettingsModel.cpp:85-94
+    }
+    void SelectHydroUnitBrickByName(const string& name) {
+        auto& v = sel().hydroUnitBricks;
+        for (int i = 0; i < (int)v.size(); ++i) {
+            if (v[i].name == name) {
+                _selBrick = {0, i};
+                _selProcess = -1;
+                return;
+            }
+        }
+        throw std::runtime_error("The hydro unit brick '" + name + "' was not found");
+    }
+    void AddBrickParameter(const string& name, float value, const string& kind = "constant") {
+        if (kind != "constant")
+            throw std::runtime_error("SettingsModel::AddBrickParameter - Parameter type '" + kind + "' not supported");
+        brick().parameters.push_back({name, value});
+    }
+    void AddBrickForcing(const string& name) {
+        if (!isForcingName(name)) throw std::invalid_argument("The provided forcing '" + name + "' is not yet supported.");
+        brick().forcing.push_back(name);
+    }
+    void SetCurrentBrickComputedDirectly() { brick().computedDirectly = true; }
+    void AddBrickLogging(const string& name) { addUnique(brick().logItems, name); }
+    void AddLoggingToItem(const string& name) { addUnique(sel().logItems, name); }
+
+    // ---- processes
+    void AddBrickProcess(const string& name, const string& kind, const string& target = "", bool log = false) {
+        auto it = processRegistry().find(kind);
+        if (it == processRegistry().end())
+            throw std::runtime_error("Process type '" + kind +
+                                     "' is not available in the B200 engine (Socont family only).");
+        Process p;
+        p.name = name;
+        p.kind = kind;
+        brick().processes.push_back(p);
+        _selProcess = (int)brick().processes.size() - 1;
+        if (!target.empty()) {
+            auto pos = target.find(':');
+            if (pos != string::npos) {
+                AddProcessOutput(target.substr(0, pos), target.substr(pos + 1));
+            } else {
+                AddProcessOutput(target);
+            }
+        }
+        if ((log || _logAll) && kind.find("transport:") == string::npos) AddProcessLogging("output");
+        for (auto& pr : it->second.params) AddProcessParameter(pr.name, pr.value);
+        for (auto& f : it->second.forcing) AddProcessForcing(f);
+    }
+    void SelectProcess(const string& name) {
+        auto& v = brick().processes;
+        for (int i = 0; i < (int)v.size(); ++i) {
+            if (v[i].name == name) {
+                _selProcess = i;
+                return;
+            }
+        }
+        throw std::runtime_error("The process '" + name + "' was not found.");
+    }
+    void AddProcessOutput(const string& target, const string& fluxType = "water") {
+        Output o;
+        o.target = target;
+        o.fluxType = fluxType;
+        process().outputs.push_back(o);
+    }
+    void AddProcessParameter(const string& name, float value, const string& kind = "constant") {
+        if (kind != "constant")
+            throw std::runtime_error("SettingsModel::AddProcessParameter - Parameter type '" + kind + "' not supported");
+        for (auto& p : process().parameters) {
+            if (p.name == name) {
+                p.value = value;
+                return;
+            }
+        }
+        process().parameters.push_back({name, value});
+    }
+    void SetProcessParameterValue(const string& name, float value, const string& = "constant") {
+        for (auto& p : process().parameters) {
+            if (p.name == name) {
+                p.value = value;
+                return;
+            }
+        }
+        throw std::runtime_error("SettingsModel::SetProcessParameterValue - Parameter '" + name + "' not found");
+    }
+    void AddProcessForcing(const string& name) {
+        if (!isForcingName(name)) throw std::invalid_argument("The provided forcing '" + name + "' is not yet supported.");
+        process().forcing.push_back(name);
+    }
+    void AddProcessLogging(const string& name) { addUnique(process().logItems, name); }
+    void SetProcessOutputsAsInstantaneous() {
+        for (auto& o : process().outputs) o.instantaneous = true;
+    }
+    void SetProcessOutputsAsStatic() {
+        for (auto& o : process().outputs) o.isStatic = true;
+    }
+
+    // ---- generators (SettingsModel.cpp:491-545)
+    void GeneratePrecipitationSplitters(bool withSnow = true, const string& type = "snow_rain:linear") {
+        if (!withSnow) throw std::runtime_error("The B200 engine needs the snow routine (with_snow=True).");
+        if (type != "snow_rain:linear" && type != "snow_rain:threshold")
+            throw std::runtime_error("Splitter type '" + type + "' is not available in the B200 engine.");
+        addSplitter("snow_rain_transition", type);
+        splitter().forcing = {"precipitation", "temperature"};
+        addSplitterOutput("rain_splitter", "water");
+        addSplitterOutput("snow_splitter", "snow");
+        if (type == "snow_rain:threshold") {
+            splitter().parameters.push_back({"threshold", 0.0f});
+        } else {
+            splitter().parameters.push_back({"transition_start", 0.0f});
+            splitter().parameters.push_back({"transition_end", 2.0f});
+        }
+        splitter().parameters.push_back({"rain_correction_factor", 1.0f});
+        splitter().parameters.push_back({"snow_correction_factor", 1.0f});
+        addSplitter("snow_splitter", "multi_fluxes");
+        addSplitter("rain_splitter", "multi_fluxes");
+    }
+    void GenerateSnowpacks(const string& meltProcess) {
+        vector<string> covers;
+        for (auto& b : sel().hydroUnitBricks)
+            if (b.isLandCover) covers.push_back(b.name);
+        for (auto& cover : covers) {
+            if (!selectSplitterIfFound("snow_splitter"))
+                throw std::runtime_error("The hydro unit splitter 'snow_splitter' was not found");
+            addSplitterOutput(cover + "_snowpack", "snow");
+            addBrick(false, cover + "_snowpack", "snowpack");
+            brick().isSurfaceComponent = true;
+            brick().parent = cover;
+            AddBrickProcess("melt", meltProcess, cover);
+        }
+    }
+    [[noreturn]] void Unsupported(const string& what) const {
+        throw std::runtime_error(what + " is not available in the B200 engine (SURVEY.md §8f lists it as next).");
+    }
+
+    // ---- parameters (SettingsModel.cpp:923-1031)
+    bool SetParameterValue(const string& component, const string& name, float value) {
+        if (component.find(',') != string::npos) {
+            size_t start = 0;
+            while (start <= component.size()) {
+                size_t end = component.find(',', start);
+                if (end == string::npos) end = component.size();
+                string tok = component.substr(start, end - start);
+                size_t a = tok.find_first_not_of(' '), b = tok.find_last_not_of(' ');
+                if (a != string::npos) {
+                    if (!SetParameterValue(tok.substr(a, b - a + 1), name, value)) return false;
+                }
+                start = end + 1;
+            }
+            return true;
+        }
+        bool found = false;
+        for (auto& st : _structures) {
+            Brick* b = findBrick(st, component);
+            if (b) {
+                setInBrick(*b, name, value);
+                found = true;
+                continue;
+            }
+            Splitter* sp = findSplitter(st, component);
+            if (sp) {
+                bool ok = false;
+                for (auto& p : sp->parameters) {
+                    if (p.name == name) {
+                        p.value = value;
+                        ok = true;
+                        break;
+                    }
+                }
+                if (!ok) throw std::runtime_error("SettingsModel::SetSplitterParameterValue - Parameter '" + name + "' not found");
+                found = true;
+                continue;
+            }
+            if (component.find("type:") != string::npos) {
+                string kind = component.substr(component.find(':') + 1);
+                auto matches = [&](const Brick& br) {
+                    return br.kind == kind ||
+                           (kind == "land_cover" && (br.kind == "generic_land_cover" || br.kind == "glacier"));
+                };
+                for (auto& br : st.hydroUnitBricks)
+                    if (matches(br)) setInBrick(br, name, value);
+                for (auto& br : st.subBasinBricks)
+                    if (matches(br)) setInBrick(br, name, value);
+                found = true;  // SetParameterValueInSelectedStructure falls through to `return true`
+            }
+        }
+        return found;
+    }
+
+    // SettingsModel::GetHydroUnitLogLabels (SettingsModel.cpp:808-841): union over the variants, in order
+    vector<string> GetHydroUnitLogLabels() const {
+        vector<string> labels;
+        std::set<string> seen;
+        auto add = [&](const string& l) {
+            if (seen.insert(l).second) labels.push_back(l);
+        };
+        for (auto& st : _structures) {
+            for (auto& b : st.hydroUnitBricks) {
+                for (auto& item : b.logItems) add(b.name + ":" + item);
+                for (auto& p : b.processes)
+                    for (auto& item : p.logItems) add(b.name + ":" + p.name + ":" + item);
+            }
+        }
+        return labels;
+    }
+    vector<string> GetLandCoverBricksNames() const {
+        vector<string> names;
+        std::set<string> seen;
+        for (auto& st : _structures)
+            for (auto& b : st.hydroUnitBricks)
+                if (b.isLandCover && seen.insert(b.name).second) names.push_back(b.name);
+        return names;
+    }
+
+    string solver, timerStart, timerEnd, timeStepUnit;
+    int timeStep = 1, spinupDays = 0;
+
+  private:
+    bool _logAll = false, _recordFractions = false;
+    vector<Structure> _structures;
+    int _selStructure = 0;
+    std::pair<int, int> _selBrick{-1, -1};  // (0 hydro unit | 1 sub-basin, index)
+    int _selProcess = -1, _selSplitter = -1;
+
+    Structure& sel() { return _structures[_selStructure]; }
+    Brick& brick() {
+        if (_selBrick.second < 0) throw std::runtime_error("No brick selected.");
+        return _selBrick.first == 0 ? sel().hydroUnitBricks[_selBrick.second] : sel().subBasinBricks[_selBrick.second];
+    }
+    Process& process() {
+        if (_selProcess < 0) throw std::runtime_error("No process selected.");
+        return brick().processes[_selProcess];
+    }
+    Splitter& splitter() { return sel().hydroUnitSplitters[_selSplitter]; }
+    static void addUnique(vector<string>& v, const string& s) {
+        if (std::find(v.begin(), v.end(), s) == v.end()) v.push_back(s);
+    }
+    void addBrick(bool subBasin, const string& name, const string& kind) {
+        Brick b;
+        b.name = name;
+        b.kind = kind;
+        b.attach = subBasin ? "sub_basin" : "hydro_unit";
+        auto& v = subBasin ? sel().subBasinBricks : sel().hydroUnitBricks;
+        v.push_back(b);
+        _selBrick = {subBasin ? 1 : 0, (int)v.size() - 1};
+        _selProcess = -1;
+        if (_logAll) {  // SettingsModel.cpp:55-62
+            AddBrickLogging("water_content");
+            if (kind == "glacier") AddBrickLogging("ice_content");
+            if (kind == "snowpack") AddBrickLogging("snow_content");
+        }
+    }
+    void addSplitter(const string& name, const string& kind) {
+        Splitter s;
+        s.name = name;
+        s.kind = kind;
+        s.attach = "hydro_unit";
+        sel().hydroUnitSplitters.push_back(s);
+        _selSplitter = (int)sel().hydroUnitSplitters.size() - 1;
+    }
+    bool selectSplitterIfFound(const string& name) {
+        auto& v = sel().hydroUnitSplitters;
+        for (int i = 0; i < (int)v.size(); ++i) {
+            if (v[i].name == name) {
+                _selSplitter = i;
+                return true;
+            }
+        }
+        return false;
+    }
+    void addSplitterOutput(const string& target, const string& fluxType) {
+        Output o;
+        o.target = target;
+        o.fluxType = fluxType;
+        splitter().outputs.push_back(o);
+    }
+    static Brick* findBrick(Structure& st, const string& name) {
+        for (auto& b : st.hydroUnitBricks)
+            if (b.name == name) return &b;
+        for (auto& b : st.subBasinBricks)
+            if (b.name == name) return &b;
+        return nullptr;
+    }
+    static Splitter* findSplitter(Structure& st, const string& name) {
+        for (auto& s : st.hydroUnitSplitters)
+            if (s.name == name) return &s;
+        for (auto& s : st.subBasinSplitters)
+            if (s.name == name) return &s;
+        return nullptr;
+    }
+    static void setInBrick(Brick& b, const string& name, float value) {
+        for (auto& p : b.parameters) {
+            if (p.name == name) {
+                p.value = value;
+                return;
+            }
+        }
+        for (auto& pr : b.processes) {
+            for (auto& p : pr.parameters) {
+                if (p.name == name) {
+                    p.value = value;
+                    return;
+                }
+            }
+        }
+        throw std::runtime_error("The parameter '" + name + "' was not found.");
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+struct UnitSettings {
+    int id = 0;
+    double area = 0, elevation = -9999;
+    bool hasSlope = false;
+    double slopeValue = 0;
+    string slopeUnit;
+    vector<std::pair<string, double>> landCovers;
+};
+
+class SettingsBasin {
+  public:
+    void AddHydroUnit(int id, double area, double elevation = -9999) {
+        UnitSettings u;
+        u.id = id;
+        u.area = area;
+        u.elevation = elevation;
+        units.push_back(u);
+    }
+    void AddLandCover(const string& name, const string&, double fraction) { last().landCovers.push_back({name, fraction}); }
+    void AddHydroUnitPropertyString(const string&, const string&) {}
+    void AddHydroUnitPropertyDouble(const string& name, double value, const string& unit) {
+        if (name == "slope") {
+            last().hasSlope = true;
+            last().slopeValue = value;
+            last().slopeUnit = unit;
+        }
+    }
+    void AddLateralConnection(int, int, double, const string& = "") {
+        throw std::runtime_error("Lateral connections are not available in the B200 engine (SURVEY.md §8f).");
+    }
+    int GetLateralConnectionCount() const { return 0; }
+    void Clear() { units.clear(); }
+    vector<UnitSettings> units;
+
+  private:
+    UnitSettings& last() {
+        if (units.empty()) throw std::runtime_error("No hydro unit defined.");
+        return units.back();
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+struct Unsupported : std::invalid_argument {
+    using std::invalid_argument::invalid_argument;
+};
+
+inline const std::map<string, int>& recordSlots() {
+    static const std::map<string, int> m = {
+        {"ground_water", HBK_R_GROUND_WATER}, {"ground_infiltration", HBK_R_GROUND_INFILTRATION},
+        {"ground_runoff", HBK_R_GROUND_RUNOFF}, {"glacier_water", HBK_R_GLACIER_WATER},
+        {"glacier_ice", HBK_R_GLACIER_ICE}, {"glacier_outflow", HBK_R_GLACIER_OUTFLOW},
+        {"glacier_melt", HBK_R_GLACIER_MELT}, {"ground_snowpack_water", HBK_R_GROUND_SNOWPACK_WATER},
+        {"ground_snowpack_snow", HBK_R_GROUND_SNOWPACK_SNOW}, {"ground_snowpack_melt", HBK_R_GROUND_SNOWPACK_MELT},
+        {"glacier_snowpack_water", HBK_R_GLACIER_SNOWPACK_WATER}, {"glacier_snowpack_snow", HBK_R_GLACIER_SNOWPACK_SNOW},
+        {"glacier_snowpack_melt", HBK_R_GLACIER_SNOWPACK_MELT}, {"slow_water", HBK_R_SLOW_WATER},
+        {"slow_et", HBK_R_SLOW_ET}, {"slow_outflow", HBK_R_SLOW_OUTFLOW}, {"slow_overflow", HBK_R_SLOW_OVERFLOW},
+        {"slow_percolation", HBK_R_SLOW_PERCOLATION}, {"slow2_water", HBK_R_SLOW2_WATER},
+        {"slow2_outflow", HBK_R_SLOW2_OUTFLOW}, {"quick_water", HBK_R_QUICK_WATER},
+        {"quick_runoff", HBK_R_QUICK_RUNOFF}, {"fraction_ground", HBK_R_FRACTION_GROUND},
+        {"fraction_glacier", HBK_R_FRACTION_GLACIER}};
+    return m;
+}
+
+// Structure compiler: recognises the Socont family by the ROLE of each brick (python/src/hydrobricks/models/
+// socont.py:111-215, modules/glacier.py:87-131, core/tests/src/helpers.cpp:9-107) and refuses anything else.
+struct Compiled {
+    hbk_structure st{};
+    float params[HBK_N_PARAMS] = {};
+    std::map<std::pair<string, string>, int> paramIndex;
+    std::map<string, int> labels;  // log label -> HBK_R_* slot
+    string groundName, glacierName;
+    int glacierStructureId = -1;
+    std::map<int, std::set<string>> variantCovers;
+    vector<std::pair<string, string>> brickKinds;  // (name, kind) over all variants, for "type:" components
+
+    static float paramOf(const vector<Param>& v, const string& name, bool* found = nullptr) {
+        for (auto& p : v) {
+            if (p.name == name) {
+                if (found) *found = true;
+                return p.value;
+            }
+        }
+        if (found) {
+            *found = false;
+            return 0;
+        }
+        throw Unsupported("parameter '" + name + "' missing");
+    }
+    static vector<string> kinds(const Brick& b) {
+        vector<string> k;
+        for (auto& p : b.processes) k.push_back(p.kind == "outflow:overflow" ? "overflow" : p.kind);
+        return k;
+    }
+    static string target(const Process& p) { return p.outputs.empty() ? "" : p.outputs[0].target; }
+    void set(int slot, const string& component, const string& name, float value) {
+        params[slot] = value;
+        paramIndex[{component, name}] = slot;
+    }
+    void label(const string& l, const string& slot) { labels[l] = recordSlots().at(slot); }
+
+    Compiled(const SettingsModel& sm, double dtDays) {
+        const string& solver = sm.solver;
+        if (solver == "euler_explicit") {
+            st.solver = HBK_SOLVER_EULER;
+        } else if (solver == "heun_explicit") {
+            st.solver = HBK_SOLVER_HEUN;
+        } else if (solver == "rk4" || solver == "runge_kutta") {
+            st.solver = HBK_SOLVER_RK4;
+        } else {
+            throw Unsupported("solver '" + solver + "': only euler_explicit, heun_explicit and rk4/runge_kutta run on the device");
+        }
+        st.time_step_days = dtDays;
+        const auto& structures = sm.Structures();
+        if (structures.empty()) throw Unsupported("empty structure");
+        if (structures.size() > 2) throw Unsupported("more than two structure variants");
+        const Structure* base = nullptr;
+        const Structure* glacierSt = nullptr;
+        for (auto& s : structures) {
+            if (s.id == 1) base = &s;
+            for (auto& b : s.hydroUnitBricks) {
+                if (b.kind == "glacier") glacierSt = &s;
+                brickKinds.push_back({b.name, b.kind});
+            }
+            for (auto& b : s.subBasinBricks) brickKinds.push_back({b.name, b.kind});
+            std::set<string> covers;
+            for (auto& b : s.hydroUnitBricks)
+                if (b.isLandCover) covers.insert(b.name);
+            variantCovers[s.id] = covers;
+        }
+        if (!base) throw Unsupported("structure 1 missing");
+        const Structure& full = glacierSt ? *glacierSt : *base;
+        glacierStructureId = glacierSt ? glacierSt->id : -1;
+        auto findBrick = [&](const string& n) -> const Brick* {
+            for (auto& b : full.hydroUnitBricks)
+                if (b.name == n) return &b;
+            return nullptr;
+        };
+        auto findBasinBrick = [&](const string& n) -> const Brick* {
+            for (auto& b : base->subBasinBricks)
+                if (b.name == n) return &b;
+            return nullptr;
+        };
+
+        // splitters
+        if (!base->subBasinSplitters.empty()) throw Unsupported("sub-basin splitters");
+        const Splitter* tr = nullptr;
+        int nMulti = 0;
+        for (auto& s : full.hydroUnitSplitters) {
+            if (s.kind == "snow_rain:linear" || s.kind == "snow_rain:threshold") tr = &s;
+            if (s.kind == "multi_fluxes") nMulti++;
+        }
+        if (!tr || nMulti != 2 || full.hydroUnitSplitters.size() != 3)
+            throw Unsupported("expected snow_rain_transition + rain/snow multi_fluxes splitters");
+        if (tr->kind == "snow_rain:linear") {
+            st.splitter_kind = HBK_SPLIT_LINEAR;
+            set(HBK_P_TRANSITION_START, tr->name, "transition_start", paramOf(tr->parameters, "transition_start"));
+            set(HBK_P_TRANSITION_END, tr->name, "transition_end", paramOf(tr->parameters, "transition_end"));
+        } else {
+            st.splitter_kind = HBK_SPLIT_THRESHOLD;
+            set(HBK_P_TRANSITION_START, tr->name, "threshold", paramOf(tr->parameters, "threshold"));
+        }
+        bool f;
+        float rcf = paramOf(tr->parameters, "rain_correction_factor", &f);
+        set(HBK_P_RAIN_CORRECTION, tr->name, "rain_correction_factor", f ? rcf : 1.0f);
+        float scf = paramOf(tr->parameters, "snow_correction_factor", &f);
+        set(HBK_P_SNOW_CORRECTION, tr->name, "snow_correction_factor", f ? scf : 1.0f);
+        vector<string> rainTargets, snowTargets;
+        for (auto& o : tr->outputs) {
+            const Splitter* tgt = nullptr;
+            for (auto& s : full.hydroUnitSplitters)
+                if (s.name == o.target && s.kind == "multi_fluxes") tgt = &s;
+            if (!tgt) throw Unsupported("snow_rain_transition must feed multi_fluxes splitters");
+            for (auto& oo : tgt->outputs) (o.fluxType == "snow" ? snowTargets : rainTargets).push_back(oo.target);
+        }
+
+        // land covers
+        const Brick* ground = nullptr;
+        const Brick* glacier = nullptr;
+        int nCovers = 0;
+        for (auto& b : full.hydroUnitBricks) {
+            if (!b.isLandCover) continue;
+            nCovers++;
+            if (b.kind == "generic_land_cover") {
+                if (ground) throw Unsupported("more than one generic land cover");
+                ground = &b;
+            } else if (b.kind == "glacier") {
+                if (glacier) throw Unsupported("more than one glacier cover");
+                glacier = &b;
+            }
+        }
+        if (!ground || nCovers != 1 + (glacier ? 1 : 0))
+            throw Unsupported("expected one generic land cover and at most one glacier cover");
+        groundName = ground->name;
+        glacierName = glacier ? glacier->name : "";
+        {
+            vector<string> want = {ground->name};
+            if (glacier) want.push_back(glacier->name);
+            std::sort(want.begin(), want.end());
+            std::sort(rainTargets.begin(), rainTargets.end());
+            if (want != rainTargets) throw Unsupported("rain must go to every land cover");
+        }
+        if (kinds(*ground) != vector<string>{"infiltration:socont", "outflow:rest"})
+            throw Unsupported("land cover " + ground->name + ": expected infiltration:socont + outflow:rest");
+        const string slowName = target(ground->processes[0]), quickName = target(ground->processes[1]);
+        if (!ground->processes[1].outputs[0].isStatic) throw Unsupported("outflow:rest output must be static");
+        label(ground->name + ":water_content", "ground_water");
+        label(ground->name + ":" + ground->processes[0].name + ":output", "ground_infiltration");
+        label(ground->name + ":" + ground->processes[1].name + ":output", "ground_runoff");
+
+        auto snowpackOf = [&](const Brick& cover) -> const Brick& {
+            const Brick* sp = nullptr;
+            for (auto& b : full.hydroUnitBricks) {
+                if (b.kind == "snowpack" && b.parent == cover.name) {
+                    if (sp) throw Unsupported("cover " + cover.name + ": more than one snowpack");
+                    sp = &b;
+                }
+            }
+            if (!sp || kinds(*sp) != vector<string>{"melt:degree_day"} || target(sp->processes[0]) != cover.name)
+                throw Unsupported("cover " + cover.name + ": expected one snowpack with melt:degree_day");
+            return *sp;
+        };
+        const Brick& gsp = snowpackOf(*ground);
+        set(HBK_P_GROUND_SNOW_DDF, gsp.name, "degree_day_factor", paramOf(gsp.processes[0].parameters, "degree_day_factor"));
+        set(HBK_P_GROUND_SNOW_TMELT, gsp.name, "melting_temperature",
+            paramOf(gsp.processes[0].parameters, "melting_temperature"));
+        label(gsp.name + ":water_content", "ground_snowpack_water");
+        label(gsp.name + ":snow_content", "ground_snowpack_snow");
+        label(gsp.name + ":" + gsp.processes[0].name + ":output", "ground_snowpack_melt");
+        vector<string> snowpacks = {gsp.name};
+        std::set<string> known = {ground->name, gsp.name, slowName, quickName};
+
+        string b1, b2;
+        if (glacier) {
+            st.has_glacier = 1;
+            if (kinds(*glacier) != vector<string>{"outflow:direct", "melt:degree_day"})
+                throw Unsupported("glacier cover: expected outflow:direct + melt:degree_day");
+            for (auto& p : glacier->processes)
+                if (p.outputs.empty() || !p.outputs[0].instantaneous) throw Unsupported("glacier outputs must be instantaneous");
+            b1 = target(glacier->processes[0]);
+            b2 = target(glacier->processes[1]);
+            bool hasInf, hasNoMelt;
+            float inf = paramOf(glacier->parameters, "infinite_storage", &hasInf);
+            float noMelt = paramOf(glacier->parameters, "no_melt_when_snow_cover", &hasNoMelt);
+            st.glacier_infinite_storage = hasInf && std::fabs(inf) > 1.1920929e-07f ? 1 : 0;  // Glacier.cpp:23-28
+            st.glacier_no_melt_when_snow_cover = hasNoMelt && noMelt > 0 ? 1 : 0;
+            set(HBK_P_ICE_DDF, glacier->name, "degree_day_factor", paramOf(glacier->processes[1].parameters, "degree_day_factor"));
+            set(HBK_P_ICE_TMELT, glacier->name, "melting_temperature",
+                paramOf(glacier->processes[1].parameters, "melting_temperature"));
+            const Brick& glsp = snowpackOf(*glacier);
+            set(HBK_P_GLACIER_SNOW_DDF, glsp.name, "degree_day_factor",
+                paramOf(glsp.processes[0].parameters, "degree_day_factor"));
+            set(HBK_P_GLACIER_SNOW_TMELT, glsp.name, "melting_temperature",
+                paramOf(glsp.processes[0].parameters, "melting_temperature"));
+            const string& n = glacier->name;
+            label(n + ":water_content", "glacier_water");
+            label(n + ":ice_content", "glacier_ice");
+            label(n + ":" + glacier->processes[0].name + ":output", "glacier_outflow");
+            label(n + ":" + glacier->processes[1].name + ":output", "glacier_melt");
+            label(glsp.name + ":water_content", "glacier_snowpack_water");
+            label(glsp.name + ":snow_content", "glacier_snowpack_snow");
+            label(glsp.name + ":" + glsp.processes[0].name + ":output", "glacier_snowpack_melt");
+            snowpacks.push_back(glsp.name);
+            known.insert(glacier->name);
+            known.insert(glsp.name);
+            int slot[2] = {HBK_P_K_SNOW, HBK_P_K_ICE};
+            const string* names[2] = {&b1, &b2};
+            for (int i = 0; i < 2; ++i) {
+                const Brick* bb = findBasinBrick(*names[i]);
+                if (!bb || bb->kind != "storage" || kinds(*bb) != vector<string>{"outflow:linear"} ||
+                    target(bb->processes[0]) != "outlet")
+                    throw Unsupported("sub-basin store " + *names[i] + ": expected storage with outflow:linear -> outlet");
+                set(slot[i], *names[i], "response_factor", paramOf(bb->processes[0].parameters, "response_factor"));
+            }
+        }
+        {
+            vector<string> a = snowTargets, b = snowpacks;
+            std::sort(a.begin(), a.end());
+            std::sort(b.begin(), b.end());
+            if (a != b) throw Unsupported("snow must go to the snowpack of every land cover");
+        }
+        for (auto& bb : base->subBasinBricks) {
+            if (bb.name == b1 || bb.name == b2) continue;
+            if (bb.kind != "storage" || kinds(bb) != vector<string>{"outflow:linear"} || target(bb.processes[0]) != "outlet")
+                throw Unsupported("sub-basin brick " + bb.name);
+        }
+
+        // slow reservoir(s)
+        const Brick* slow = findBrick(slowName);
+        if (!slow || slow->kind != "storage" || slow->computedDirectly)
+            throw Unsupported("infiltration target must be a storage solved by the ODE solver");
+        vector<string> k = kinds(*slow);
+        if (k == vector<string>{"et:socont", "outflow:linear", "overflow"}) {
+            st.n_soil_stores = 1;
+            st.slow_process_order = 0;
+        } else if (k == vector<string>{"et:socont", "outflow:linear", "overflow", "percolation:constant"}) {
+            st.n_soil_stores = 2;
+            st.slow_process_order = 0;
+        } else if (k == vector<string>{"et:socont", "outflow:linear", "percolation:constant", "overflow"}) {
+            st.n_soil_stores = 2;
+            st.slow_process_order = 1;
+        } else {
+            throw Unsupported("slow reservoir processes are not et:socont, outflow:linear, overflow[, percolation:constant]");
+        }
+        set(HBK_P_CAPACITY, slowName, "capacity", paramOf(slow->parameters, "capacity"));
+        label(slowName + ":water_content", "slow_water");
+        string slow2Name;
+        for (size_t i = 0; i < slow->processes.size(); ++i) {
+            const Process& p = slow->processes[i];
+            static const std::map<string, string> lab = {{"et:socont", "slow_et"}, {"outflow:linear", "slow_outflow"},
+                                                         {"overflow", "slow_overflow"},
+                                                         {"percolation:constant", "slow_percolation"}};
+            label(slowName + ":" + p.name + ":output", lab.at(k[i]));
+            if (k[i] == "outflow:linear") {
+                if (target(p) != "outlet") throw Unsupported("slow reservoir outflow must go to the outlet");
+                set(HBK_P_K_SLOW_1, slowName, "response_factor", paramOf(p.parameters, "response_factor"));
+            } else if (k[i] == "overflow") {
+                if (target(p) != "outlet") throw Unsupported("slow reservoir overflow must go to the outlet");
+            } else if (k[i] == "percolation:constant") {
+                slow2Name = target(p);
+                bool has;
+                float v = paramOf(p.parameters, "percolation_rate", &has);
+                if (!has) v = paramOf(p.parameters, "rate");
+                set(HBK_P_PERCOLATION, slowName, "percolation_rate", v);
+            }
+        }
+        if (st.n_soil_stores == 2) {
+            const Brick* s2 = findBrick(slow2Name);
+            bool hasCap = false;
+            if (s2) paramOf(s2->parameters, "capacity", &hasCap);
+            if (!s2 || s2->kind != "storage" || kinds(*s2) != vector<string>{"outflow:linear"} ||
+                target(s2->processes[0]) != "outlet" || hasCap)
+                throw Unsupported("second soil store: expected storage with outflow:linear -> outlet");
+            set(HBK_P_K_SLOW_2, slow2Name, "response_factor", paramOf(s2->processes[0].parameters, "response_factor"));
+            label(slow2Name + ":water_content", "slow2_water");
+            label(slow2Name + ":" + s2->processes[0].name + ":output", "slow2_outflow");
+            known.insert(slow2Name);
+        }
+
+        // quick store
+        const Brick* quick = findBrick(quickName);
+        bool hasCap = false;
+        if (quick) paramOf(quick->parameters, "capacity", &hasCap);
+        if (!quick || quick->kind != "storage" || quick->processes.size() != 1 || target(quick->processes[0]) != "outlet" || hasCap)
+            throw Unsupported("surface runoff store: expected one process to the outlet");
+        const Process& qp = quick->processes[0];
+        if (qp.kind == "runoff:socont") {
+            st.quick_kind = HBK_QUICK_SOCONT;
+            set(HBK_P_QUICK, quickName, "beta", paramOf(qp.parameters, "beta"));
+        } else if (qp.kind == "outflow:linear") {
+            st.quick_kind = HBK_QUICK_LINEAR;
+            set(HBK_P_QUICK, quickName, "response_factor", paramOf(qp.parameters, "response_factor"));
+        } else {
+            throw Unsupported("surface runoff process " + qp.kind);
+        }
+        label(quickName + ":water_content", "quick_water");
+        label(quickName + ":" + qp.name + ":output", "quick_runoff");
+
+        for (auto& b : full.hydroUnitBricks) {
+            if (!known.count(b.name)) throw Unsupported("brick outside the Socont family: " + b.name);
+            if (!b.forcing.empty()) throw Unsupported("brick-level forcing");
+        }
+    }
+
+    // ModelBuilder::AssignHydroUnitStructures (ModelBuilder.cpp:36-97) -> glacier-variant flag of one unit
+    int glacierVariantOf(const vector<std::pair<string, double>>& covers) const {
+        if (variantCovers.size() <= 1) return variantCovers.begin()->first == glacierStructureId ? 1 : 0;
+        std::set<string> present;
+        for (auto& c : covers)
+            if (std::fabs(c.second) > 1e-8) present.insert(c.first);
+        int sid = -1;
+        for (auto& v : variantCovers) {
+            if (v.second == present) {
+                sid = v.first;
+                break;
+            }
+        }
+        if (sid < 0) {
+            size_t best = SIZE_MAX, largest = 0;
+            int largestId = variantCovers.begin()->first;
+            for (auto& v : variantCovers) {
+                if (v.second.size() > largest) {
+                    largest = v.second.size();
+                    largestId = v.first;
+                }
+                bool superset = std::includes(v.second.begin(), v.second.end(), present.begin(), present.end());
+                if (superset && v.second.size() < best) {
+                    best = v.second.size();
+                    sid = v.first;
+                }
+            }
+            if (sid < 0) sid = largestId;
+        }
+        return sid == glacierStructureId ? 1 : 0;
+    }
+
+    // SettingsModel::SetParameterValue target resolution incl. lists and "type:" components -> slots
+    vector<int> resolveAll(const string& component, const string& name) const {
+        std::set<int> slots;
+        size_t start = 0;
+        while (start <= component.size()) {
+            size_t end = component.find(',', start);
+            if (end == string::npos) end = component.size();
+            string tok = component.substr(start, end - start);
+            size_t a = tok.find_first_not_of(' '), b = tok.find_last_not_of(' ');
+            if (a != string::npos) {
+                tok = tok.substr(a, b - a + 1);
+                if (tok.rfind("type:", 0) == 0) {
+                    string kind = tok.substr(5);
+                    for (auto& bk : brickKinds) {
+                        bool m = bk.second == kind ||
+                                 (kind == "land_cover" && (bk.second == "generic_land_cover" || bk.second == "glacier"));
+                        auto it = paramIndex.find({bk.first, name});
+                        if (m && it != paramIndex.end()) slots.insert(it->second);
+                    }
+                } else {
+                    auto it = paramIndex.find({tok, name});
+                    if (it != paramIndex.end()) slots.insert(it->second);
+                }
+            }
+            start = end + 1;
+        }
+        return vector<int>(slots.begin(), slots.end());
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// dates (UtilsDateTime): proleptic Gregorian <-> modified Julian date
+inline long daysFromCivil(int y, unsigned m, unsigned d) {
+    y -= m <= 2;
+    const long era = (y >= 0 ? y : y - 399) / 400;
+    const unsigned yoe = (unsigned)(y - era * 400);
+    const unsigned doy = (153 * (m + (m > 2 ? -3 : 9)) + 2) / 5 + d - 1;
+    const unsigned doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+    return era * 146097 + (long)doe - 719468;  // days since 1970-01-01
+}
+inline void civilFromDays(long z, int& y, unsigned& m, unsigned& d) {
+    z += 719468;
+    const long era = (z >= 0 ? z : z - 146096) / 146097;
+    const unsigned doe = (unsigned)(z - era * 146097);
+    const unsigned yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+    y = (int)yoe + (int)era * 400;
+    const unsigned doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+    const unsigned mp = (5 * doy + 2) / 153;
+    d = doy - (153 * mp + 2) / 5 + 1;
+    m = mp < 10 ? mp + 3 : mp - 9;
+    y += m <= 2;
+}
+constexpr long kMjdEpochUnixDays = -40587;  // 1858-11-17
+inline double parseDateMjd(const string& text) {
+    int y, mo, d;
+    if (std::sscanf(text.c_str(), "%d-%d-%d", &y, &mo, &d) != 3) throw std::invalid_argument("bad date '" + text + "'");
+    return (double)(daysFromCivil(y, (unsigned)mo, (unsigned)d) - kMjdEpochUnixDays);
+}
+
+// Action dates -> step indices (TimeMachine.cpp:49-59, ActionsManager.cpp:80-104, Action.cpp:18-57)
+inline vector<int> recursiveSteps(double mjdStart, int nSteps, int month, int day, double dt) {
+    static const int dim[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+    if (month < 1 || month > 12) month = 1;
+    day = std::max(1, std::min(day, dim[month - 1]));
+    vector<int> out;
+    for (int k = 1; k < nSteps; ++k) {
+        int y;
+        unsigned m, d;
+        civilFromDays((long)std::floor(mjdStart + k * dt) + kMjdEpochUnixDays, y, m, d);
+        if ((int)m == month && (int)d == day) out.push_back(k);
+    }
+    return out;
+}
+inline int sporadicStep(double mjdStart, double date, double dt) {
+    return std::max(1, (int)std::ceil((date - mjdStart) / dt - 1e-12));
+}
+inline double checkFraction(double f) {  // Action::CheckLandCoverAreaFraction (Action.cpp:71-91)
+    if (std::fabs(f) <= 1e-8) return 0.0;
+    if (std::fabs(1 - f) <= 1e-8) return 1.0;
+    if (f < 0 || f > 1) throw std::invalid_argument("The fraction is not in the range [0 .. 1]");
+    return f;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+struct Action {
+    virtual ~Action() = default;
+};
+struct ActionLandCoverChange : Action {
+    struct Change {
+        double date;
+        int unitId;
+        string cover;
+        double area;
+    };
+    vector<Change> changes;
+    void AddChange(double date, int unitId, const string& cover, double area) { changes.push_back({date, unitId, cover, area}); }
+    int GetChangeCount() const { return (int)changes.size(); }
+    int GetLandCoverCount() const {
+        std::set<string> s;
+        for (auto& c : changes) s.insert(c.cover);
+        return (int)s.size();
+    }
+};
+struct ActionGlacierEvolutionDeltaH : Action {
+    int month = 10;
+    string cover;
+    vector<int> unitIds;
+    int rows = 0;
+    vector<double> areas, volumes;  // [rows][units]
+    void AddLookupTables(int m, const string& c, const vector<int>& ids, int nRows, const vector<double>& a,
+                         const vector<double>& v) {
+        month = m;
+        cover = c;
+        unitIds = ids;
+        rows = nRows;
+        areas = a;
+        volumes = v;
+    }
+};
+struct ActionGlacierEvolutionAreaScaling : ActionGlacierEvolutionDeltaH {};
+struct ActionGlacierSnowToIceTransformation : Action {
+    int month, day;
+    string cover;
+    ActionGlacierSnowToIceTransformation(int m, int d, const string& c) : month(m), day(d), cover(c) {}
+};
+
+inline float slopeMPerM(double value, const string& unit) {
+    // HydroUnitProperty::GetValue(..., "m/m") + float cast of HydroUnit::GetPropertyFloat
+    // (HydroUnitProperty.cpp:19-49, HydroUnit.cpp:146-148)
+    if (unit == "m/m" || unit == "m_per_m") return (float)value;
+    if (unit == "degrees" || unit == "degree" || unit == "deg" || unit == "°")
+        return (float)std::tan(value * 3.1415926535897932384626433832795 / 180.0);
+    throw std::invalid_argument("unsupported slope unit '" + unit + "'");
+}
+
+class ModelHydro {
+  public:
+    ModelHydro() = default;
+    ~ModelHydro() { hbk_engine_destroy(_e); }
+    ModelHydro(const ModelHydro&) = delete;
+    ModelHydro& operator=(const ModelHydro&) = delete;
+
+    void InitializeWithBasin(SettingsModel& ms, SettingsBasin& bs, int device = 0) {
+        if (ms.solver.empty()) throw std::invalid_argument("Model settings are not valid.");
+        if (ms.timeStepUnit != "day" && ms.timeStepUnit != "days" && ms.timeStepUnit != "d")
+            throw std::invalid_argument("Model initialization failed: only daily time steps (time_step_unit='day')");
+        _mjd0 = parseDateMjd(ms.timerStart);
+        _dt = (double)ms.timeStep;
+        _nSteps = (int)(1 + (parseDateMjd(ms.timerEnd) - _mjd0) / _dt);  // TimeMachine.cpp:61-64
+        try {
+            _c.reset(new Compiled(ms, _dt));
+        } catch (const Unsupported& err) {
+            throw std::invalid_argument(string("Model initialization failed: ") + err.what());
+        }
+        _settings = &ms;
+        _units = bs.units;
+        if (_units.empty()) throw std::invalid_argument("Basin initialization failed: no hydro unit");
+        hbk_engine_destroy(_e);
+        _e = nullptr;
+        if (hbk_engine_create(&_c->st, (int)_units.size(), _nSteps, device, &_e) != HBK_OK)
+            throw std::invalid_argument("hbk_engine_create failed: no usable CUDA device (the B200 engine has no CPU fallback)");
+        const int U = (int)_units.size();
+        vector<double> area(U), elev(U), fg(U, 1.0), fgl(U, 0.0);
+        vector<float> slope(U, 0.0f);
+        vector<int32_t> gv(U, 0);
+        for (int u = 0; u < U; ++u) {
+            area[u] = _units[u].area;
+            elev[u] = _units[u].elevation;
+            if (_c->st.quick_kind == HBK_QUICK_SOCONT) {
+                if (!_units[u].hasSlope) throw std::invalid_argument("No property with the name 'slope' was found.");
+                slope[u] = slopeMPerM(_units[u].slopeValue, _units[u].slopeUnit);
+            }
+            gv[u] = _c->glacierVariantOf(_units[u].landCovers);
+            for (auto& lc : _units[u].landCovers) {
+                if (lc.first == _c->groundName) fg[u] = lc.second;
+                if (!_c->glacierName.empty() && lc.first == _c->glacierName) fgl[u] = lc.second;
+            }
+        }
+        check(hbk_set_units(_e, area.data(), elev.data(), _c->st.quick_kind == HBK_QUICK_SOCONT ? slope.data() : nullptr,
+                            gv.data(), fg.data(), fgl.data()));
+        check(hbk_set_spinup_steps(_e, (int)(ms.spinupDays / _dt)));
+        _labels = ms.GetHydroUnitLogLabels();
+        _sets.assign(_c->params, _c->params + HBK_N_PARAMS);
+        _nSets = 1;
+    }
+    bool IsValid() const { return _e != nullptr; }
+
+    // ---- forcing
+    bool CreateTimeSeries(const string& name, const double* time, int nTime, const int* ids, int nIds, const double* data) {
+        string key = name;
+        std::transform(key.begin(), key.end(), key.begin(), ::tolower);
+        int var;
+        if (key == "precipitation" || key == "p") {
+            var = HBK_VAR_PRECIPITATION;
+        } else if (key == "temperature" || key == "t") {
+            var = HBK_VAR_TEMPERATURE;
+        } else if (key == "pet") {
+            var = HBK_VAR_PET;
+        } else {
+            throw std::invalid_argument("Unknown forcing variable '" + name + "'");
+        }
+        Series s;
+        s.time.assign(time, time + nTime);
+        s.ids.assign(ids, ids + nIds);
+        s.data.assign(data, data + (size_t)nTime * nIds);
+        _series[var] = std::move(s);
+        return true;
+    }
+    void ClearTimeSeries() {
+        _series.clear();
+        _forcingLoaded = false;
+        _stationVars.clear();
+    }
+    bool AttachTimeSeriesToHydroUnits() {
+        const int U = (int)_units.size();
+        for (auto& kv : _series) {
+            const Series& s = kv.second;
+            std::map<int, int> pos;
+            for (int i = 0; i < (int)s.ids.size(); ++i) pos[s.ids[i]] = i;
+            vector<int> cols(U);
+            for (int u = 0; u < U; ++u) {
+                auto it = pos.find(_units[u].id);
+                if (it == pos.end()) return false;
+                cols[u] = it->second;
+            }
+            const long start = std::lround(_mjd0 - s.time[0]);
+            if (start < 0 || start + _nSteps > (long)s.time.size())
+                throw std::invalid_argument("The forcing data do not cover the modelling period.");
+            vector<double> buf((size_t)_nSteps * U);
+            const size_t n = s.ids.size();
+            for (int t = 0; t < _nSteps; ++t)
+                for (int u = 0; u < U; ++u) buf[(size_t)t * U + u] = s.data[(size_t)(start + t) * n + cols[u]];
+            check(hbk_set_forcing(_e, kv.first, buf.data()));
+        }
+        _forcingLoaded = !_series.empty();
+        return true;
+    }
+    bool ForcingLoaded() const { return _forcingLoaded; }
+    void SetStationForcing(int var, const double* series, int n, double zref, double gradient, const double* gradSet,
+                           double corr, const double* corrSet) {
+        if (n != _nSteps) throw std::invalid_argument("station series length differs from the modelling period");
+        if (gradSet || corrSet) check(hbk_set_parameters(_e, _nSets, _sets.data()));
+        check(hbk_set_station_forcing(_e, var, series, zref, gradient, gradSet, corr, corrSet));
+        _stationVars.insert(var);
+        _forcingLoaded = _stationVars.size() == 3;
+    }
+
+    // ---- parameters
+    void UpdateParameters(SettingsModel& ms) {
+        Compiled c(ms, _dt);
+        std::memcpy(_c->params, c.params, sizeof(c.params));
+        _sets.assign(c.params, c.params + HBK_N_PARAMS);
+        _nSets = 1;
+    }
+    void SetParameterSets(const float* values, int nSets) {
+        _sets.assign(values, values + (size_t)nSets * HBK_N_PARAMS);
+        _nSets = nSets;
+    }
+    vector<int> ParameterSlot(const string& component, const string& name) const { return _c->resolveAll(component, name); }
+    vector<float> BaseParameters() const { return vector<float>(_c->params, _c->params + HBK_N_PARAMS); }
+
+    // ---- actions
+    bool AddAction(Action* a) {
+        _actions.push_back(a);
+        return true;
+    }
+    int GetActionCount() const { return (int)_actions.size(); }
+    int GetSporadicActionItemCount() const {
+        int n = 0;
+        for (auto* a : _actions)
+            if (auto* lc = dynamic_cast<ActionLandCoverChange*>(a)) n += lc->GetChangeCount();
+        return n;
+    }
+
+    // ---- run
+    void Reset() {}
+    void SaveAsInitialState() { check(hbk_save_as_initial_state(_e)); }
+    void Run(bool record = true) {
+        if (!_forcingLoaded) throw std::invalid_argument("Time step processing failed: no forcing attached.");
+        scheduleActions();
+        check(hbk_set_parameters(_e, _nSets, _sets.data()));
+        uint64_t mask = 0;
+        if (record) {
+            for (auto& l : _labels) {
+                auto it = _c->labels.find(l);
+                if (it != _c->labels.end()) mask |= 1ull << it->second;
+            }
+            if (!_labels.empty() && (_settings->LogAll() || _settings->RecordsFractions())) {
+                mask |= 1ull << HBK_R_FRACTION_GROUND;
+                if (!_c->glacierName.empty()) mask |= 1ull << HBK_R_FRACTION_GLACIER;
+            }
+        }
+        check(hbk_set_record_mask(_e, mask));
+        check(hbk_run(_e));
+    }
+
+    // ---- results
+    int StepCount() const { return _nSteps; }
+    int UnitCount() const { return (int)_units.size(); }
+    int SetCount() const { return _nSets; }
+    void GetOutlet(int first, int n, double* out) { check(hbk_get_outlet(_e, first, n, out)); }
+    vector<string> GetRecordedHydroUnitLabels() const { return _labels; }
+    vector<string> GetRecordedHydroUnitFractionLabels() const {
+        if (_settings && (_settings->LogAll() || _settings->RecordsFractions())) return _settings->GetLandCoverBricksNames();
+        return {};
+    }
+    void GetHydroUnitValues(const string& label, int set, double* out) {
+        auto it = _c->labels.find(label);
+        if (it == _c->labels.end()) throw std::runtime_error("Label '" + label + "' is not recorded.");
+        check(hbk_get_recorded(_e, it->second, set, out));
+    }
+    void GetHydroUnitFractions(const string& label, double* out) {
+        int slot;
+        if (label == _c->groundName) {
+            slot = HBK_R_FRACTION_GROUND;
+        } else if (!_c->glacierName.empty() && label == _c->glacierName) {
+            slot = HBK_R_FRACTION_GLACIER;
+        } else {
+            throw std::runtime_error("Fraction label '" + label + "' is not recorded.");
+        }
+        check(hbk_get_recorded(_e, slot, 0, out));
+    }
+    vector<int> GetHydroUnitIds() const {
+        vector<int> ids;
+        for (auto& u : _units) ids.push_back(u.id);
+        return ids;
+    }
+    vector<double> GetHydroUnitAreas() const {
+        vector<double> a;
+        for (auto& u : _units) a.push_back(u.area);
+        return a;
+    }
+    void GetState(int slot, double* out) { check(hbk_get_state(_e, slot, out)); }
+    void GetBasinState(double* out) { check(hbk_get_basin_state(_e, out)); }
+    void GetRecorded(int slot, int set, double* out) { check(hbk_get_recorded(_e, slot, set, out)); }
+    const Compiled& compiled() const { return *_c; }
+    const vector<UnitSettings>& units() const { return _units; }
+    hbk_engine* engine() { return _e; }
+    void fractions(vector<double>& g, vector<double>& gl) const {
+        g.assign(_units.size(), 1.0);
+        gl.assign(_units.size(), 0.0);
+        for (size_t u = 0; u < _units.size(); ++u)
+            for (auto& lc : _units[u].landCovers) {
+                if (lc.first == _c->groundName) g[u] = lc.second;
+                if (!_c->glacierName.empty() && lc.first == _c->glacierName) gl[u] = lc.second;
+            }
+    }
+
+  private:
+    struct Series {
+        vector<double> time, data;
+        vector<int> ids;
+    };
+    hbk_engine* _e = nullptr;
+    std::unique_ptr<Compiled> _c;
+    SettingsModel* _settings = nullptr;  // non-owning, like Process parameter pointers into the SettingsModel
+    vector<UnitSettings> _units;
+    std::map<int, Series> _series;
+    std::set<int> _stationVars;
+    bool _forcingLoaded = false;
+    vector<Action*> _actions;  // non-owning (ActionsManager.cpp:24-39)
+    vector<string> _labels;
+    vector<float> _sets;
+    int _nSets = 1, _nSteps = 0;
+    double _mjd0 = 0, _dt = 1;
+
+    void check(int rc) {
+        if (rc != HBK_OK) throw std::invalid_argument(string("hbk error ") + std::to_string(rc) + ": " + hbk_last_error(_e));
+    }
+
+    void scheduleActions() {
+        check(hbk_clear_actions(_e));
+        if (_actions.empty()) return;
+        std::map<int, int> pos;
+        for (int i = 0; i < (int)_units.size(); ++i) pos[_units[i].id] = i;
+        struct Ev {
+            int step, order, kind, unit;
+            double value;
+        };
+        vector<Ev> events;
+        struct Sp {
+            double date;
+            int order, unitId;
+            string cover;
+            double area;
+        };
+        vector<Sp> sporadic;
+        for (int order = 0; order < (int)_actions.size(); ++order) {
+            Action* a = _actions[order];
+            if (auto* s2i = dynamic_cast<ActionGlacierSnowToIceTransformation*>(a)) {
+                if (s2i->cover != _c->glacierName) throw std::invalid_argument("snow-to-ice: land cover is not the glacier cover");
+                for (int k : recursiveSteps(_mjd0, _nSteps, s2i->month, s2i->day, _dt)) events.push_back({k, order, 1, -1, 0});
+            } else if (dynamic_cast<ActionGlacierEvolutionAreaScaling*>(a)) {
+                throw std::invalid_argument("ActionGlacierEvolutionAreaScaling is not available in the B200 engine");
+            } else if (auto* dh = dynamic_cast<ActionGlacierEvolutionDeltaH*>(a)) {
+                if (dh->cover != _c->glacierName) throw std::invalid_argument("delta-h: land cover is not the glacier cover");
+                vector<int32_t> units;
+                for (int id : dh->unitIds) {
+                    auto it = pos.find(id);
+                    if (it == pos.end()) throw std::invalid_argument("The hydro unit " + std::to_string(id) + " was not found");
+                    units.push_back(it->second);
+                }
+                check(hbk_set_delta_h_tables(_e, (int)units.size(), units.data(), dh->rows, dh->areas.data(), dh->volumes.data()));
+                for (int k : recursiveSteps(_mjd0, _nSteps, dh->month, 1, _dt)) events.push_back({k, order, 2, -1, 0});
+            } else if (auto* lc = dynamic_cast<ActionLandCoverChange*>(a)) {
+                for (auto& c : lc->changes) sporadic.push_back({c.date, order, c.unitId, c.cover, c.area});
+            } else {
+                throw std::invalid_argument("This action is not available in the B200 engine");
+            }
+        }
+        std::stable_sort(sporadic.begin(), sporadic.end(), [](const Sp& a, const Sp& b) { return a.date < b.date; });
+        int n = 0;
+        for (auto& s : sporadic) {
+            auto it = pos.find(s.unitId);
+            if (it == pos.end()) throw std::invalid_argument("The hydro unit " + std::to_string(s.unitId) + " was not found");
+            if (s.cover != _c->glacierName) {
+                if (s.cover == _c->groundName) continue;  // undone by FixLandCoverFractionsTotal (HydroUnit.cpp:459-490)
+                throw std::invalid_argument("Land cover '" + s.cover + "' was not found.");
+            }
+            double fraction = checkFraction(s.area / _units[it->second].area);
+            events.push_back({sporadicStep(_mjd0, s.date, _dt), 10000 + n++, 0, it->second, fraction});
+        }
+        std::stable_sort(events.begin(), events.end(), [](const Ev& a, const Ev& b) {
+            return a.step != b.step ? a.step < b.step : a.order < b.order;
+        });
+        for (auto& ev : events) {
+            if (ev.kind == 0) {
+                check(hbk_add_land_cover_change(_e, ev.step, ev.unit, ev.value));
+            } else if (ev.kind == 1) {
+                check(hbk_add_snow_to_ice(_e, ev.step));
+            } else {
+                check(hbk_add_delta_h_update(_e, ev.step));
+            }
+        }
+    }
+};
+
+}  // namespace hb

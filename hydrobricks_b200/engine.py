@@ -132,10 +132,20 @@ class Engine:
             raise HbkError(rc, "hbk_engine_create failed (is a CUDA device present? there is no CPU fallback)")
         self.structure = structure
 
+    @classmethod
+    def from_handle(cls, handle, n_units, n_steps, n_sets):
+        """Non-owning view of an engine created elsewhere (the compiled host module's ModelHydro.engine_handle())."""
+        self = cls.__new__(cls)
+        self.L = load_library()
+        self.h = ctypes.c_void_p(handle)
+        self.n_units, self.n_steps, self.n_sets = int(n_units), int(n_steps), int(n_sets)
+        self._borrowed = True
+        return self
+
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and not getattr(self, "_borrowed", False):
             self.L.hbk_engine_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:

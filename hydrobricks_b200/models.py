@@ -11,7 +11,23 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import _hydrobricks as _backend_default
+def default_backend():
+    """The compiled C++/pybind11 host module (hydrobricks_b200/native/_hydrobricks*.so); the pure-Python mirror
+    hydrobricks_b200._hydrobricks offers the same surface (backend="python") — both drive the same C-ABI / CUDA
+    engine, neither computes on the CPU."""
+    from .native import _hydrobricks as native
+
+    return native
+
+
+def resolve_backend(backend):
+    if backend is None or backend == "native":
+        return default_backend()
+    if backend == "python":
+        from . import _hydrobricks as mirror
+
+        return mirror
+    return backend
 
 RAIN_SNOWMELT_STORAGE = "glacier_area_rain_snowmelt_storage"
 ICEMELT_STORAGE = "glacier_area_icemelt_storage"
@@ -21,7 +37,7 @@ class Socont:
     def __init__(self, solver="crank_nicolson", soil_storage_nb=1, surface_runoff="socont_runoff",
                  land_cover_names=None, land_cover_types=None, record_all=False, glacier_infinite_storage=True,
                  snow_melt_process="melt:degree_day", backend=None):
-        self.backend = backend or _backend_default
+        self.backend = resolve_backend(backend)
         self.solver = solver
         self.options = {"soil_storage_nb": soil_storage_nb, "surface_runoff": surface_runoff,
                         "snow_melt_process": snow_melt_process, "glacier_infinite_storage": glacier_infinite_storage}
@@ -149,6 +165,7 @@ class Socont:
         except TypeError:
             self.model.init_with_basin(self.settings, basin)
         self._basin = basin
+        self._n_steps = int((np.datetime64(end_date) - np.datetime64(start_date)).astype(int)) + 1
 
     def set_parameters(self, values: dict):
         for alias, value in values.items():
@@ -181,7 +198,7 @@ class Socont:
     # -- batched extras --------------------------------------------------------------------------------
     def parameter_matrix(self, sets: dict, n_sets: int):
         """{alias: array[n_sets] | scalar} -> float32 [n_sets][HBK_N_PARAMS] (engine.PARAM_SLOTS order)."""
-        base = self.model._cs.params.copy()
+        base = np.asarray(self.model.base_parameters(), dtype=np.float32)
         m = np.repeat(base[None, :], n_sets, axis=0)
         for alias, values in sets.items():
             component, name = self.aliases.get(alias, (None, None))
@@ -196,3 +213,11 @@ class Socont:
 
     def run_batch(self, matrix):
         return self.model.run_batch(matrix)
+
+    def engine(self, n_sets=0):
+        """ctypes view of the underlying hbk_engine (device pointers, stream, statistics) for either backend."""
+        from . import engine as _engine
+
+        if hasattr(self.model, "_engine"):
+            return self.model._engine
+        return _engine.Engine.from_handle(self.model.engine_handle(), len(self.units), self._n_steps, n_sets)

@@ -38,9 +38,10 @@ def _structure(backend, **kw):
     dict(solver="euler_explicit", soil_storage_nb=1, land_cover_names=["ground", "glacier"],
          land_cover_types=["ground", "glacier"], glacier_infinite_storage=False, record_all=True),
 ])
-def test_reference_socont_builds_same_structure_on_both_backends(kw):
+@pytest.mark.parametrize("backend", ["b200", "b200-native"])
+def test_reference_socont_builds_same_structure_on_both_backends(kw, backend):
     ref_st, _ = _structure("ref", **kw)
-    b200_st, socont = _structure("b200", **kw)
+    b200_st, socont = _structure(backend, **kw)
     assert b200_st == ref_st
     # and the parameter plumbing of the reference layer works on the mirror
     params = socont.generate_parameters()
@@ -51,11 +52,12 @@ def test_reference_socont_builds_same_structure_on_both_backends(kw):
         assert socont.settings.set_parameter_value(p["component"], p["name"], p["value"])
 
 
-def test_reference_setup_reaches_the_engine():
+@pytest.mark.parametrize("backend", ["b200", "b200-native"])
+def test_reference_setup_reaches_the_engine(backend):
     import refpy
     import torch
 
-    hb = refpy.load_reference_python("b200")
+    hb = refpy.load_reference_python(backend)
     import hydrobricks.models as models
 
     socont = models.Socont(solver="rk4", soil_storage_nb=1, surface_runoff="linear_storage")

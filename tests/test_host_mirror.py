@@ -33,10 +33,11 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize("backend", ["python", "native"])
 @pytest.mark.parametrize("name", list(CASES))
-def test_socont_mirror_emits_reference_structure(name):
+def test_socont_mirror_emits_reference_structure(name, backend):
     meta, _, _, _, _ = gu.load(name)
-    m = models.Socont(solver="rk4", record_all=True, **CASES[name])
+    m = models.Socont(solver="rk4", record_all=True, backend=backend, **CASES[name])
     mine = strip(m.settings.get_structure())
     ref = strip(meta["structures"])
     # parameter VALUES differ (the golden run had its own parameter set); compare them after resetting
@@ -53,10 +54,11 @@ def test_socont_mirror_emits_reference_structure(name):
     assert blank(mine) == blank(ref)
 
 
-def test_set_parameter_value_matches_reference_values():
+@pytest.mark.parametrize("backend", ["python", "native"])
+def test_set_parameter_value_matches_reference_values(backend):
     meta, _, _, _, _ = gu.load("gsm_socont_rk4_glacier_2store")
     m = models.Socont(solver="rk4", record_all=True, soil_storage_nb=2, land_cover_names=["ground", "glacier"],
-                      land_cover_types=["ground", "glacier"])
+                      land_cover_types=["ground", "glacier"], backend=backend)
     s = m.settings
     # the values tools/ref_cases.py::gsm_socont used, through the same aliases
     for comp, name, v in [("type:snowpack", "degree_day_factor", 4.5), ("slow_reservoir", "capacity", 120),
@@ -72,10 +74,15 @@ def test_set_parameter_value_matches_reference_values():
 
 
 def test_unsupported_structures_are_refused():
-    s = hbk_mod.SettingsModel()
-    with pytest.raises(RuntimeError):
-        s.add_hydro_unit_brick("x", "storage")
-        s.add_brick_process("p", "et:hbv")
+    from hydrobricks_b200.native import _hydrobricks as native
+
+    for mod in (hbk_mod, native):
+        s = mod.SettingsModel()
+        with pytest.raises(RuntimeError):
+            s.add_hydro_unit_brick("x", "storage")
+            s.add_brick_process("p", "et:hbv")
+        with pytest.raises(RuntimeError):
+            s.add_snow_redistribution("transport:snow_slide")
     meta, _, _, _, _ = gu.load("kat_linear_storage_runge_kutta")
     with pytest.raises(structure.UnsupportedStructure):
         structure.CompiledStructure(meta["structures"], "rk4")

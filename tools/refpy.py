@@ -94,6 +94,10 @@ def load_extension(backend):
         if str(REPO) not in sys.path:
             sys.path.insert(0, str(REPO))
         return importlib.import_module("hydrobricks_b200._hydrobricks")
+    elif backend == "b200-native":
+        if str(REPO) not in sys.path:
+            sys.path.insert(0, str(REPO))
+        return importlib.import_module("hydrobricks_b200.native._hydrobricks")
     else:
         raise ValueError(backend)
     if not cands:
