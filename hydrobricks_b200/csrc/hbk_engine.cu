@@ -380,7 +380,8 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, HBK_MIN_BLOCKS) hbkRunUnits(c
                     const int gp = pg * a.PB + lp;
                     if (gp < a.P && (a.writeOutputs || qi > 0)) {  // deposits feed the basin stores during spin-up
                         double* dst = (qi == 0) ? a.outQ : (qi == 1 ? a.outD1 : a.outD2);
-                        dst[((size_t)grp * a.P + gp) * a.ldt + (t0 + tc)] = s;
+                        // streaming store: the 8.8 GB outlet must not evict the L2-resident unit state
+                        __stcs(&dst[((size_t)grp * a.P + gp) * a.ldt + (t0 + tc)], s);
                     }
                 }
             }
@@ -743,7 +744,10 @@ void chooseShape(hbk_engine* e) {
         if ((ub * pb) % 32 != 0 || (e->haveRaw[0] && (ub % 2 != 0))) continue;
         const int tiles = (e->U + ub - 1) / ub;
         const double use = (double)e->U / ((double)tiles * ub);
-        if (use > bestUse + 1e-9) {
+        // prefer wide blocks: fewer resident blocks keep the time-multiplexed state of all resident blocks inside
+        // the 126 MB L2 (888 blocks x 32 sets x 50 units x 8 slots x 8 B = 90 MB); a narrower block must buy
+        // more than 5 % of unit-slot utilisation to win
+        if (use > bestUse + 0.05) {
             bestUse = use;
             best = ub;
         }
