@@ -431,6 +431,13 @@ def run_engine_arm(args):
             hbm_src = "MEASURED_PEAKS.json"
         except Exception:
             hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+        traffic = None
+        try:  # measured DRAM traffic of this exact launch (ncu), only meaningful for the default C2 shape
+            tr = json.load(open(ROOT / "profiles" / "r01e_traffic.json"))
+            if args.workload == "c2" and args.solver == "rk4" and (P, U, T) == (P_DEFAULT, U_DEFAULT, T_DEFAULT):
+                traffic = tr["traffic_bytes"]
+        except Exception:
+            pass
         line = {
             "metric": "hru_timesteps_per_s", "value": value, "unit": "HRU*timesteps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -450,7 +457,10 @@ def run_engine_arm(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_fp64, "unit": "TFLOP/s",
-                         "frac": achieved / peak_fp64 if peak_fp64 else None, "traffic": None,
+                         "frac": achieved / peak_fp64 if peak_fp64 else None, "traffic": traffic,
+                         "traffic_note": "DRAM bytes per launch from ncu (profiles/r01e_traffic.json); algorithmic "
+                                         "bytes are in roofline.hbm; the excess is the unit state of the "
+                                         "time-multiplexed tiles passing through L2/HBM (<3 % of HBM bandwidth)",
                          "kernel": f"hbkRunUnits<{args.solver},{wl['soil']} soil store(s),{'glacier' if wl['glacier'] else 'no glacier'}>",
                          "kernel_ms": main_ms,
                          "flops_per_hru_step": FP64_FLOPS_PER_HRU_STEP, "flops_source": FP64_FLOPS_SOURCE,

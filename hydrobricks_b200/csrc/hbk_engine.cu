@@ -19,6 +19,7 @@
 //    (glacier evolution, land-cover change) get applied by their own kernels.
 //
 // There is no CPU fallback anywhere in this file.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -45,6 +46,7 @@ constexpr int kNH = 4;  // per-unit constants: area fraction of basin, area [m2]
 
 struct KArgs {
     int P, U, tBegin, tEnd, PB, UB, TC, nUTiles, G, nGroups;
+    int clusterMode;  // 1: one thread-block cluster per parameter-set group, one CTA per unit tile, DSMEM reduction
     Flags flags;
     double dt;
     const float* params;  // [HBK_N_PARAMS][ldp]
@@ -118,22 +120,25 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, HBK_MIN_BLOCKS) hbkRunUnits(c
     constexpr int NQ = GLACIER ? 3 : 1;
     const int tid = threadIdx.x;
     const int nThreads = blockDim.x;  // PB * UB
-    const int grp = blockIdx.x % a.nGroups;
-    const int pg = blockIdx.x / a.nGroups;
+    // cluster mode: the cluster's CTAs are the unit tiles of one parameter-set group; every CTA keeps its tile's
+    // state in registers for the whole segment and the outlet is reduced through distributed shared memory.
+    const int grp = a.clusterMode ? 0 : blockIdx.x % a.nGroups;
+    const int pg = a.clusterMode ? blockIdx.x / a.nUTiles : blockIdx.x / a.nGroups;
+    const int crank = a.clusterMode ? blockIdx.x % a.nUTiles : 0;
     const int pl = tid % a.PB;
     const int ul = tid / a.PB;
     const int p = pg * a.PB + pl;
     const bool validP = p < a.P;
-    const int tileBegin = grp * a.G;
-    const int tileEnd = min(tileBegin + a.G, a.nUTiles);
-    const bool multi = a.G > 1;
+    const int tileBegin = a.clusterMode ? crank : grp * a.G;
+    const int tileEnd = a.clusterMode ? crank + 1 : min(tileBegin + a.G, a.nUTiles);
+    const bool multi = !a.clusterMode && a.G > 1;
 
     // shared memory carve-up
     uint64_t* bars = reinterpret_cast<uint64_t*>(smemRaw);  // 2 mbarriers
     const int fRow = (a.forcingMode == 0) ? a.TC * a.UB : (a.TC + 2);  // doubles per variable per stage
     double* fbuf = reinterpret_cast<double*>(smemRaw + 128);             // [2][3][fRow]
     double* qbuf = fbuf + 2 * 3 * fRow;                                  // [NQ][TC][nThreads]
-    double* accb = qbuf + (size_t)NQ * a.TC * nThreads;                  // [NQ][TC][PB]
+    double* accb = qbuf + (size_t)NQ * a.TC * nThreads;                  // [NQ][TC][PB]; cluster mode: [2][NQ][TC][PB]
 
     // per-thread, per-parameter-set constants
     Par par;
@@ -364,6 +369,42 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, HBK_MIN_BLOCKS) hbkRunUnits(c
             __syncthreads();
             // SubBasin::ComputeOutletDischarge (SubBasin.cpp:322-329): add this tile's units, in unit order, to
             // the chunk accumulator; entry (qi, tc, lp) is always owned by the same thread.
+            if (a.clusterMode) {
+                // this CTA's tile sum -> its partial buffer (double buffered by chunk parity) ...
+                double* part = accb + (size_t)(c & 1) * NQ * a.TC * a.PB;
+                for (int idx = tid; idx < NQ * n * a.PB; idx += nThreads) {
+                    const int qi = idx / (n * a.PB);
+                    const int rem = idx - qi * n * a.PB;
+                    const int tc = rem / a.PB;
+                    const int lp = rem - tc * a.PB;
+                    const double* src = qbuf + ((size_t)qi * a.TC + tc) * nThreads + lp;
+                    double s = 0.0;
+                    for (int k = 0; k < a.UB; ++k) s += src[(size_t)k * a.PB];
+                    part[((size_t)qi * a.TC + tc) * a.PB + lp] = s;
+                }
+                // ... then the rows (quantity, step) are dealt round-robin to the cluster's CTAs, which add the
+                // tiles' partials in tile order through DSMEM and write the final series.
+                namespace cg = cooperative_groups;
+                cg::cluster_group cluster = cg::this_cluster();
+                cluster.sync();
+                const int nRows = NQ * n;
+                for (int row = crank; row < nRows; row += a.nUTiles) {
+                    const int qi = row / n, tc = row - qi * n;
+                    for (int lp = tid; lp < a.PB; lp += nThreads) {
+                        const int gp = pg * a.PB + lp;
+                        double s = 0.0;
+                        for (int k = 0; k < a.nUTiles; ++k) {
+                            const double* remote = cluster.map_shared_rank(part, k);
+                            s += remote[((size_t)qi * a.TC + tc) * a.PB + lp];
+                        }
+                        if (gp < a.P && (a.writeOutputs || qi > 0)) {
+                            double* dst = (qi == 0) ? a.outQ : (qi == 1 ? a.outD1 : a.outD2);
+                            __stcs(&dst[(size_t)gp * a.ldt + (t0 + tc)], s);
+                        }
+                    }
+                }
+                continue;  // the next chunk writes the other partial buffer; its cluster.sync orders the reuse
+            }
             const bool last = (tl == nTilesHere - 1);
             for (int idx = tid; idx < NQ * n * a.PB; idx += nThreads) {
                 const int qi = idx / (n * a.PB);
@@ -389,6 +430,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, HBK_MIN_BLOCKS) hbkRunUnits(c
         }
     }
 
+    if (a.clusterMode) cooperative_groups::this_cluster().sync();  // peers may still be reading this CTA's partials
     if (validP && !multi && nTilesHere > 0) {
         const int u = tileBegin * a.UB + ul;
         if (u < a.U) storeState(u);
@@ -643,6 +685,7 @@ struct hbk_engine {
     hbk_structure st{};
     int U = 0, T = 0, P = 0, device = 0;
     int PB = 32, UB = 8, TC = 16, nUTiles = 1, G = 1, nGroups = 1;
+    bool clusterMode = false;
     bool stateLaneP = false;  // state layout: element (p,u) at u*P + p (parameter axis on the lanes) or p*U + u
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -765,6 +808,17 @@ void chooseShape(hbk_engine* e) {
         if (g > 0) e->G = std::min(g, e->nUTiles);
     }
     e->nGroups = (e->nUTiles + e->G - 1) / e->G;
+    // Optional (HBK_CLUSTER=1): one thread-block cluster per parameter-set group when all unit tiles fit in one
+    // cluster (<= 16 CTAs, opt-in size): state stays in registers, the outlet is reduced through distributed shared
+    // memory, DRAM traffic = algorithmic. Measured 11 % SLOWER than time-multiplexing on C2 (cluster.sync of 52 warps
+    // every chunk + 13-CTA co-scheduling, profiles/r01_tuning.md), so it is not the default.
+    const char* wantCluster = std::getenv("HBK_CLUSTER");
+    e->clusterMode = wantCluster && wantCluster[0] == '1' && e->PB == 32 && e->nUTiles >= 2 && e->nUTiles <= 16 &&
+                     !std::getenv("HBK_TILES_PER_BLOCK");
+    if (e->clusterMode) {
+        e->G = 1;
+        e->nGroups = 1;
+    }
     e->stateLaneP = e->PB == 32;
     const int nq = e->st.has_glacier ? 3 : 1;
     // chunk length: shared memory per block small enough for HBK_MIN_BLOCKS blocks per SM
@@ -774,7 +828,7 @@ void chooseShape(hbk_engine* e) {
     int tc = 8;
     for (;;) {
         const size_t fRow = (e->haveRaw[0] ? (size_t)tc * e->UB : (size_t)tc + 2);
-        const size_t bytes = 128 + 2 * 3 * fRow * 8 + (size_t)nq * tc * (e->PB * e->UB + e->PB) * 8;
+        const size_t bytes = 128 + 2 * 3 * fRow * 8 + (size_t)nq * tc * (e->PB * e->UB + 2 * e->PB) * 8;
         if (bytes <= budget || tc == 2) break;
         tc /= 2;
     }
@@ -788,7 +842,7 @@ void chooseShape(hbk_engine* e) {
 size_t smemBytes(const hbk_engine* e, bool tiled) {
     const int nq = e->st.has_glacier ? 3 : 1;
     const size_t fRow = tiled ? (size_t)e->TC * e->UB : (size_t)e->TC + 2;
-    return 128 + 2 * 3 * fRow * 8 + (size_t)nq * e->TC * (e->PB * e->UB + e->PB) * 8;
+    return 128 + 2 * 3 * fRow * 8 + (size_t)nq * e->TC * (e->PB * e->UB + 2 * e->PB) * 8;
 }
 
 using KernelFn = void (*)(const KArgs);
@@ -1201,6 +1255,7 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
     a.nUTiles = e->nUTiles;
     a.G = e->G;
     a.nGroups = e->nGroups;
+    a.clusterMode = e->clusterMode ? 1 : 0;
     a.flags.quickKind = e->st.quick_kind;
     a.flags.slowOrder = e->st.slow_process_order;
     a.flags.splitKind = e->st.splitter_kind;
@@ -1246,10 +1301,27 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
     const size_t smem = smemBytes(e, tiled);
     HBK_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int nPGroups = (e->P + e->PB - 1) / e->PB;
-    const long long grid = (long long)nPGroups * e->nGroups;
+    const long long grid = (long long)nPGroups * (e->clusterMode ? e->nUTiles : e->nGroups);
     if (grid > 2147483647LL) return fail(e, HBK_E_UNSUPPORTED, "grid too large");
     void* args[] = {(void*)&a};
-    HBK_CUDA(cudaLaunchKernel((const void*)fn, dim3((unsigned)grid), dim3(e->PB * e->UB), args, smem, e->stream));
+    if (e->clusterMode) {
+        HBK_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(e->PB * e->UB);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = e->stream;
+        cudaLaunchAttribute attr{};
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = (unsigned)e->nUTiles;
+        attr.val.clusterDim.y = 1;
+        attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        HBK_CUDA(cudaLaunchKernelExC(&cfg, (const void*)fn, args));
+    } else {
+        HBK_CUDA(cudaLaunchKernel((const void*)fn, dim3((unsigned)grid), dim3(e->PB * e->UB), args, smem, e->stream));
+    }
     e->lastLaunches++;
 
     if (writeOutputs && multi) {
