@@ -41,6 +41,9 @@ namespace hbk {
 #ifndef HBK_MIN_BLOCKS
 #define HBK_MIN_BLOCKS 6  // register budget = 65536 / (HBK_MAX_THREADS * HBK_MIN_BLOCKS)
 #endif
+#ifndef HBK_MIN_BLOCKS_GLACIER
+#define HBK_MIN_BLOCKS_GLACIER HBK_MIN_BLOCKS  // the glacier variants carry ~60 more live registers
+#endif
 constexpr int kBlock = HBK_MAX_THREADS;
 constexpr int kNH = 4;  // per-unit constants: area fraction of basin, area [m2], pow(slope,0.5), elevation
 
@@ -115,7 +118,8 @@ __device__ __forceinline__ void tmaLoad1D(void* dst, const void* src, uint32_t b
 // With G = all tiles (ensembles) one block sums every unit of its parameter sets in unit order: no partial
 // buffers, no second pass. With G = 1 (few sets, many units) the state never leaves the registers.
 template <int SOLVER, int NSOIL, bool GLACIER>
-__global__ void __launch_bounds__(HBK_MAX_THREADS, HBK_MIN_BLOCKS) hbkRunUnits(const KArgs a) {
+__global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLACIER : HBK_MIN_BLOCKS)
+    hbkRunUnits(const KArgs a) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     constexpr int NQ = GLACIER ? 3 : 1;
     const int tid = threadIdx.x;
@@ -193,44 +197,59 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, HBK_MIN_BLOCKS) hbkRunUnits(c
             mP = 1 + gP * (elev - a.zrefP) / 100;
         }
     };
-    auto loadState = [&](int u) {
+    // `full` = segment boundary (first load / last store). In between (time-multiplexed tiles) the persistent flux
+    // amounts of a non-null brick are dead — every one is rewritten before it is read within the next step — so only
+    // the storages travel, plus the amounts of null bricks (which keep their stale values, Processor.cpp:258-260).
+    auto loadState = [&](int u, bool full) {
         const long long si = (long long)p * a.sP + (long long)u * a.sU;
+        const bool groundAmts = full || nearlyZero(fG, kPrecision);
+        const bool glacierAmts = full || !glacierVariant || nearlyZero(fGl, kPrecision);
         h.snowG = a.state[HBK_S_GROUND_SNOW * a.lds + si];
         h.wG = a.state[HBK_S_GROUND_WATER * a.lds + si];
         h.slow = a.state[HBK_S_SLOW * a.lds + si];
         h.slow2 = (NSOIL == 2) ? a.state[HBK_S_SLOW2 * a.lds + si] : 0.0;
         h.quick = a.state[HBK_S_QUICK * a.lds + si];
-        h.amtInfil = a.state[HBK_S_AMT_INFILTRATION * a.lds + si];
-        h.amtRest = a.state[HBK_S_AMT_REST * a.lds + si];
-        h.amtMeltG = a.state[HBK_S_AMT_MELT_GROUND * a.lds + si];
+        if (groundAmts) {
+            h.amtInfil = a.state[HBK_S_AMT_INFILTRATION * a.lds + si];
+            h.amtRest = a.state[HBK_S_AMT_REST * a.lds + si];
+            h.amtMeltG = a.state[HBK_S_AMT_MELT_GROUND * a.lds + si];
+        }
         if (GLACIER) {
             h.snowGl = a.state[HBK_S_GLACIER_SNOW * a.lds + si];
             h.wGl = a.state[HBK_S_GLACIER_WATER * a.lds + si];
             h.ice = a.state[HBK_S_ICE * a.lds + si];
-            h.amtMeltGl = a.state[HBK_S_AMT_MELT_GLACIER * a.lds + si];
-            h.amtDep1 = a.state[HBK_S_AMT_DEPOSIT_RAIN_SNOWMELT * a.lds + si];
-            h.amtDep2 = a.state[HBK_S_AMT_DEPOSIT_ICEMELT * a.lds + si];
+            if (glacierAmts) {
+                h.amtMeltGl = a.state[HBK_S_AMT_MELT_GLACIER * a.lds + si];
+                h.amtDep1 = a.state[HBK_S_AMT_DEPOSIT_RAIN_SNOWMELT * a.lds + si];
+                h.amtDep2 = a.state[HBK_S_AMT_DEPOSIT_ICEMELT * a.lds + si];
+            }
         } else {
             h.snowGl = h.wGl = h.ice = h.amtMeltGl = h.amtDep1 = h.amtDep2 = 0.0;
         }
     };
-    auto storeState = [&](int u) {
+    auto storeState = [&](int u, bool full) {
         const long long si = (long long)p * a.sP + (long long)u * a.sU;
+        const bool groundAmts = full || nearlyZero(fG, kPrecision);
+        const bool glacierAmts = full || !glacierVariant || nearlyZero(fGl, kPrecision);
         a.state[HBK_S_GROUND_SNOW * a.lds + si] = h.snowG;
         a.state[HBK_S_GROUND_WATER * a.lds + si] = h.wG;
         a.state[HBK_S_SLOW * a.lds + si] = h.slow;
         if (NSOIL == 2) a.state[HBK_S_SLOW2 * a.lds + si] = h.slow2;
         a.state[HBK_S_QUICK * a.lds + si] = h.quick;
-        a.state[HBK_S_AMT_INFILTRATION * a.lds + si] = h.amtInfil;
-        a.state[HBK_S_AMT_REST * a.lds + si] = h.amtRest;
-        a.state[HBK_S_AMT_MELT_GROUND * a.lds + si] = h.amtMeltG;
+        if (groundAmts) {
+            a.state[HBK_S_AMT_INFILTRATION * a.lds + si] = h.amtInfil;
+            a.state[HBK_S_AMT_REST * a.lds + si] = h.amtRest;
+            a.state[HBK_S_AMT_MELT_GROUND * a.lds + si] = h.amtMeltG;
+        }
         if (GLACIER) {
             a.state[HBK_S_GLACIER_SNOW * a.lds + si] = h.snowGl;
             a.state[HBK_S_GLACIER_WATER * a.lds + si] = h.wGl;
             a.state[HBK_S_ICE * a.lds + si] = h.ice;
-            a.state[HBK_S_AMT_MELT_GLACIER * a.lds + si] = h.amtMeltGl;
-            a.state[HBK_S_AMT_DEPOSIT_RAIN_SNOWMELT * a.lds + si] = h.amtDep1;
-            a.state[HBK_S_AMT_DEPOSIT_ICEMELT * a.lds + si] = h.amtDep2;
+            if (glacierAmts) {
+                a.state[HBK_S_AMT_MELT_GLACIER * a.lds + si] = h.amtMeltGl;
+                a.state[HBK_S_AMT_DEPOSIT_RAIN_SNOWMELT * a.lds + si] = h.amtDep1;
+                a.state[HBK_S_AMT_DEPOSIT_ICEMELT * a.lds + si] = h.amtDep2;
+            }
         }
     };
 
@@ -293,7 +312,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, HBK_MIN_BLOCKS) hbkRunUnits(c
             const double* fs = fbuf + (size_t)(seq & 1) * 3 * fRow;
             if (valid && (multi || !loaded)) {
                 loadUnit(u);
-                loadState(u);
+                loadState(u, c == 0);
             }
             loaded = true;
 
@@ -365,7 +384,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, HBK_MIN_BLOCKS) hbkRunUnits(c
                     qbuf[(size_t)(2 * a.TC + tc) * nThreads + tid] = o.dep2;
                 }
             }
-            if (valid && multi) storeState(u);
+            if (valid && multi) storeState(u, c == nChunks - 1);
             __syncthreads();
             // SubBasin::ComputeOutletDischarge (SubBasin.cpp:322-329): add this tile's units, in unit order, to
             // the chunk accumulator; entry (qi, tc, lp) is always owned by the same thread.
@@ -433,7 +452,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, HBK_MIN_BLOCKS) hbkRunUnits(c
     if (a.clusterMode) cooperative_groups::this_cluster().sync();  // peers may still be reading this CTA's partials
     if (validP && !multi && nTilesHere > 0) {
         const int u = tileBegin * a.UB + ul;
-        if (u < a.U) storeState(u);
+        if (u < a.U) storeState(u, true);
     }
     if (err) atomicOr(a.err, err);
     if (unconverged) atomicAdd(a.unconverged, (unsigned long long)unconverged);
