@@ -666,6 +666,34 @@ __global__ void hbkActDeltaH(const ActArgs a, int n, const int* units, int nRows
     }
 }
 
+// Sum, per parameter set, of the stale instantaneous-flux amounts of glacier bricks that are currently null (zero
+// area): they no longer deposit water, but FluxToBrickInstantaneous::GetRealAmount() still reports their last
+// amount to the sub-basin stores' constraint test (WaterContainer.cpp:98-101, Processor.cpp:258-260). One block
+// per parameter set; only launched when actions can make a glacier vanish.
+__global__ void hbkStaleDeposits(const ActArgs a, double* stale) {
+    const int p = blockIdx.x;
+    __shared__ double s1[128], s2[128];
+    double v1 = 0, v2 = 0;
+    for (int u = threadIdx.x; u < a.U; u += blockDim.x) {
+        if (!(a.hruFlags[u] & 1)) continue;
+        if (!nearlyZero(a.frac[(size_t)a.P * a.U + (size_t)p * a.U + u], kPrecision)) continue;
+        v1 += stateAt(a, HBK_S_AMT_DEPOSIT_RAIN_SNOWMELT, p, u);
+        v2 += stateAt(a, HBK_S_AMT_DEPOSIT_ICEMELT, p, u);
+    }
+    s1[threadIdx.x] = v1;
+    s2[threadIdx.x] = v2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t1 = 0, t2 = 0;
+        for (int i = 0; i < blockDim.x; ++i) {
+            t1 += s1[i];
+            t2 += s2[i];
+        }
+        stale[2 * p] = t1;
+        stale[2 * p + 1] = t2;
+    }
+}
+
 __global__ void hbkBroadcastFractions(double* dst, const double* init, int P, int U) {
     const long long n = (long long)P * U;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -760,6 +788,7 @@ struct hbk_engine {
     double* dDhAreas = nullptr;
     double* dDhVolumes = nullptr;
     int* dDhLastRow = nullptr;
+    double* dStale = nullptr;  // [P][2] stale deposit amounts of null glacier bricks (actions only)
     int dhUnits = 0, dhRows = 0;
     double dhInitialWE = 0;
     std::vector<double> hArea;
@@ -903,6 +932,7 @@ int ensureSetBuffers(hbk_engine* e, int P) {
     freeDev(e->dCorrP);
     freeDev(e->dFracSet);
     freeDev(e->dDhLastRow);
+    freeDev(e->dStale);
     e->recBytes = 0;
     e->initPerSet = false;
     e->P = P;
@@ -996,6 +1026,7 @@ void hbk_engine_destroy(hbk_engine* e) {
     freeDev(e->dDhAreas);
     freeDev(e->dDhVolumes);
     freeDev(e->dDhLastRow);
+    freeDev(e->dStale);
     freeDev(e->dErr);
     freeDev(e->dUnconv);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -1364,20 +1395,37 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
     if (e->st.has_glacier) {
         const int blocks = (e->P + 127) / 128;
         const double dt = e->st.time_step_days;
+        const double* stale = nullptr;
+        if (e->fracPerSet) {  // a glacier may have vanished through an action: its stale flux amounts
+            if (!e->dStale) HBK_CUDA(cudaMalloc(&e->dStale, sizeof(double) * 2 * e->P));
+            ActArgs aa{};
+            aa.P = e->P;
+            aa.U = e->U;
+            aa.frac = e->dFracSet;
+            aa.state = e->dState;  // the amounts of null bricks do not change within a segment
+            aa.lds = (long long)e->P * e->U;
+            aa.sP = e->stateLaneP ? 1 : e->U;
+            aa.sU = e->stateLaneP ? e->P : 1;
+            aa.hruFlags = e->dHruFlags;
+            aa.ldu = e->ldu;
+            hbkStaleDeposits<<<e->P, 128, 0, e->stream>>>(aa, e->dStale);
+            e->lastLaunches++;
+            stale = e->dStale;
+        }
         switch (e->st.solver) {
             case HBK_SOLVER_EULER:
                 hbkBasinStores<0><<<blocks, 128, 0, e->stream>>>(e->dParams, e->ldp, e->P, e->ldt, tBegin, tEnd, dt, e->dD1,
-                                                               e->dD2, nullptr, e->dOutlet, e->dBasinState,
+                                                               e->dD2, stale, e->dOutlet, e->dBasinState,
                                                                writeOutputs ? 1 : 0, e->dErr, e->dUnconv);
                 break;
             case HBK_SOLVER_HEUN:
                 hbkBasinStores<1><<<blocks, 128, 0, e->stream>>>(e->dParams, e->ldp, e->P, e->ldt, tBegin, tEnd, dt, e->dD1,
-                                                               e->dD2, nullptr, e->dOutlet, e->dBasinState,
+                                                               e->dD2, stale, e->dOutlet, e->dBasinState,
                                                                writeOutputs ? 1 : 0, e->dErr, e->dUnconv);
                 break;
             default:
                 hbkBasinStores<2><<<blocks, 128, 0, e->stream>>>(e->dParams, e->ldp, e->P, e->ldt, tBegin, tEnd, dt, e->dD1,
-                                                               e->dD2, nullptr, e->dOutlet, e->dBasinState,
+                                                               e->dD2, stale, e->dOutlet, e->dBasinState,
                                                                writeOutputs ? 1 : 0, e->dErr, e->dUnconv);
                 break;
         }
