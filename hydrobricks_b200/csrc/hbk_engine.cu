@@ -702,6 +702,90 @@ __global__ void hbkBroadcastFractions(double* dst, const double* init, int P, in
     }
 }
 
+// ---- batched objective functions -----------------------------------------------------------------------
+// One block per parameter set; two passes over its outlet row (means, then centred sums), fixed-order tree
+// reductions. obsStats = {n valid, mean_o, sum (o-mean_o)^2}.
+__device__ __forceinline__ double blockSum(double v, double* sh) {
+    const int tid = threadIdx.x;
+    sh[tid] = v;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (tid < s) sh[tid] += sh[tid + s];
+        __syncthreads();
+    }
+    const double r = sh[0];
+    __syncthreads();
+    return r;
+}
+
+__global__ void hbkObsStats(const double* obs, int t0, int T, double* stats) {
+    __shared__ double sh[256];
+    double n = 0, s = 0;
+    for (int t = t0 + threadIdx.x; t < T; t += blockDim.x) {
+        const double o = obs[t];
+        if (o == o) {
+            n += 1;
+            s += o;
+        }
+    }
+    n = blockSum(n, sh);
+    s = blockSum(s, sh);
+    const double mean = s / n;
+    double ss = 0;
+    for (int t = t0 + threadIdx.x; t < T; t += blockDim.x) {
+        const double o = obs[t];
+        if (o == o) ss += (o - mean) * (o - mean);
+    }
+    ss = blockSum(ss, sh);
+    if (threadIdx.x == 0) {
+        stats[0] = n;
+        stats[1] = mean;
+        stats[2] = ss;
+    }
+}
+
+__global__ void hbkScores(const double* __restrict__ outlet, long long ldt, const double* __restrict__ obs, int t0, int T,
+                          const double* __restrict__ stats, int metric, double* __restrict__ out) {
+    __shared__ double sh[256];
+    const int p = blockIdx.x;
+    const double* q = outlet + (size_t)p * ldt;
+    const double n = stats[0], mo = stats[1], sso = stats[2];
+    double a = 0, b = 0;
+    for (int t = t0 + threadIdx.x; t < T; t += blockDim.x) {
+        const double o = obs[t];
+        if (o == o) {
+            const double s = q[t];
+            a += s;
+            b += (s - o) * (s - o);
+        }
+    }
+    const double sumS = blockSum(a, sh);
+    const double sse = blockSum(b, sh);
+    if (metric == HBK_SCORE_NSE) {
+        if (threadIdx.x == 0) out[p] = 1 - sse / sso;
+        return;
+    }
+    const double ms = sumS / n;
+    double c = 0, d = 0;
+    for (int t = t0 + threadIdx.x; t < T; t += blockDim.x) {
+        const double o = obs[t];
+        if (o == o) {
+            const double ds = q[t] - ms;
+            c += ds * ds;
+            d += ds * (o - mo);
+        }
+    }
+    const double sss = blockSum(c, sh);
+    const double sso2 = blockSum(d, sh);
+    if (threadIdx.x == 0) {
+        const double r = sso2 / sqrt(sss * sso);
+        const double cvS = sqrt(sss / (n - 1)) / ms;
+        const double cvO = sqrt(sso / (n - 1)) / mo;
+        const double g = cvS / cvO, be = ms / mo;
+        out[p] = 1 - sqrt((r - 1) * (r - 1) + (g - 1) * (g - 1) + (be - 1) * (be - 1));
+    }
+}
+
 // FP64 roofline denominator: 8 independent DFMA chains per thread (2 flops per DFMA).
 __global__ void hbkFp64Peak(double* out, int iters, double seed) {
     double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6,
@@ -788,6 +872,8 @@ struct hbk_engine {
     double* dDhAreas = nullptr;
     double* dDhVolumes = nullptr;
     int* dDhLastRow = nullptr;
+    double* dScores = nullptr;  // [P]
+    double* dObs = nullptr;     // [T] + 3 stats
     double* dStale = nullptr;  // [P][2] stale deposit amounts of null glacier bricks (actions only)
     int dhUnits = 0, dhRows = 0;
     double dhInitialWE = 0;
@@ -933,6 +1019,7 @@ int ensureSetBuffers(hbk_engine* e, int P) {
     freeDev(e->dFracSet);
     freeDev(e->dDhLastRow);
     freeDev(e->dStale);
+    freeDev(e->dScores);
     e->recBytes = 0;
     e->initPerSet = false;
     e->P = P;
@@ -1027,6 +1114,8 @@ void hbk_engine_destroy(hbk_engine* e) {
     freeDev(e->dDhVolumes);
     freeDev(e->dDhLastRow);
     freeDev(e->dStale);
+    freeDev(e->dScores);
+    freeDev(e->dObs);
     freeDev(e->dErr);
     freeDev(e->dUnconv);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -1621,6 +1710,28 @@ int hbk_last_run_stats(hbk_engine* e, double* ms, int32_t* launches, int64_t* un
 }
 
 void* hbk_stream(hbk_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+int hbk_compute_scores(hbk_engine* e, int32_t metric, const double* observed, int32_t warmup, double* out) {
+    if (!e || !observed || warmup < 0 || warmup >= e->T || (metric != HBK_SCORE_NSE && metric != HBK_SCORE_KGE_2012))
+        return HBK_E_ARG;
+    if (!e->ran) return fail(e, HBK_E_STATE, "no completed run");
+    HBK_CUDA(cudaSetDevice(e->device));
+    if (!e->dObs) HBK_CUDA(cudaMalloc(&e->dObs, sizeof(double) * (e->T + 4)));
+    if (!e->dScores) HBK_CUDA(cudaMalloc(&e->dScores, sizeof(double) * e->P));
+    HBK_CUDA(cudaMemcpyAsync(e->dObs, observed, sizeof(double) * e->T, cudaMemcpyHostToDevice, e->stream));
+    hbkObsStats<<<1, 256, 0, e->stream>>>(e->dObs, warmup, e->T, e->dObs + e->T);
+    hbkScores<<<e->P, 256, 0, e->stream>>>(e->dOutlet, e->ldt, e->dObs, warmup, e->T, e->dObs + e->T, metric, e->dScores);
+    HBK_CUDA(cudaGetLastError());
+    if (out) HBK_CUDA(cudaMemcpyAsync(out, e->dScores, sizeof(double) * e->P, cudaMemcpyDeviceToHost, e->stream));
+    HBK_CUDA(cudaStreamSynchronize(e->stream));
+    return HBK_OK;
+}
+
+int hbk_scores_dev(hbk_engine* e, const double** ptr) {
+    if (!e || !ptr) return HBK_E_ARG;
+    *ptr = e->dScores;
+    return HBK_OK;
+}
 
 int hbk_measure_fp64_peak(int32_t device, double* tflops) {
     if (!tflops) return HBK_E_ARG;

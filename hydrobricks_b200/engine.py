@@ -102,6 +102,8 @@ def load_library():
     L.hbk_stream.argtypes = [vp]
     L.hbk_stream.restype = ctypes.c_void_p
     L.hbk_measure_fp64_peak.argtypes = [i32, dp]
+    L.hbk_compute_scores.argtypes = [vp, i32, dp, i32, dp]
+    L.hbk_scores_dev.argtypes = [vp, ctypes.POINTER(ctypes.c_void_p)]
     _lib = L
     return L
 
@@ -260,6 +262,25 @@ class Engine:
         out = np.empty((self.n_sets, 2), dtype=np.float64)
         self._check(self.L.hbk_get_basin_state(self.h, _dptr(out)))
         return out
+
+    def compute_scores(self, metric, observed, warmup=0, out=None, to_host=True):
+        """Batched NSE ("nse") / KGE-2012 ("kge_2012") of the last run on the device; returns float64[n_sets]
+        (to_host=False leaves them on the device only: scores_device_pointer())."""
+        obs = np.ascontiguousarray(observed, dtype=np.float64)
+        assert obs.shape == (self.n_steps,)
+        kind = {"nse": 0, "kge_2012": 1}[metric] if isinstance(metric, str) else int(metric)
+        if not to_host:
+            self._check(self.L.hbk_compute_scores(self.h, kind, _dptr(obs), int(warmup), None))
+            return None
+        if out is None:
+            out = np.empty(self.n_sets, dtype=np.float64)
+        self._check(self.L.hbk_compute_scores(self.h, kind, _dptr(obs), int(warmup), _dptr(out)))
+        return out
+
+    def scores_device_pointer(self):
+        ptr = ctypes.c_void_p()
+        self._check(self.L.hbk_scores_dev(self.h, ctypes.byref(ptr)))
+        return ptr.value
 
     def outlet_device_pointer(self):
         ptr, ld = ctypes.c_void_p(), ctypes.c_int64()

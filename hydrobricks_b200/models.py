@@ -212,7 +212,13 @@ class Socont:
         return m
 
     def run_batch(self, matrix):
+        self._last_batch = len(matrix)
         return self.model.run_batch(matrix)
+
+    def evaluate_batch(self, metric, observations, warmup=0):
+        """Objective score ("nse" | "kge_2012") of every parameter set of the last run_batch against the observed
+        outlet discharge, computed on the device (python evaluation/metrics.py:40-62, trainer.py:1091-1141)."""
+        return self.engine(getattr(self, "_last_batch", 1)).compute_scores(metric, observations, warmup)
 
     def engine(self, n_sets=0):
         """ctypes view of the underlying hbk_engine (device pointers, stream, statistics) for either backend."""

@@ -171,6 +171,15 @@ int hbk_last_run_stats(hbk_engine* e, double* kernel_ms, int32_t* n_launches, in
 /* Raw CUDA stream handle (cudaStream_t) the engine launches on, for callers timing with events. */
 void* hbk_stream(hbk_engine* e);
 
+/* Batched objective functions on the device (python evaluation/metrics.py:40-62 via HydroErr):
+ * one score per parameter set of the last run against observed[n_steps] (NaN = missing, dropped), skipping the first
+ * `warmup` steps (trainer.py:1091-1141). HBK_SCORE_NSE = 1 - sum((s-o)^2)/sum((o-mean o)^2);
+ * HBK_SCORE_KGE_2012 = 1 - sqrt((r-1)^2 + (CVs/CVo-1)^2 + (mean s/mean o-1)^2), std with ddof=1.
+ * out[n_sets] on the host; hbk_scores_dev gives the device copy (for NCCL gathers). */
+enum { HBK_SCORE_NSE = 0, HBK_SCORE_KGE_2012 = 1 };
+int hbk_compute_scores(hbk_engine* e, int32_t metric, const double* observed, int32_t warmup, double* out);
+int hbk_scores_dev(hbk_engine* e, const double** ptr);
+
 /* Measured FP64 (non-tensor) DFMA throughput of the device in TFLOP/s: the roofline denominator of the
  * compute-bound ensemble configurations (MEASURED_PEAKS.json has no FP64 figure). */
 int hbk_measure_fp64_peak(int32_t device, double* tflops);
