@@ -144,34 +144,51 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
     double* qbuf = fbuf + 2 * 3 * fRow;                                  // [NQ][TC][nThreads]
     double* accb = qbuf + (size_t)NQ * a.TC * nThreads;                  // [NQ][TC][PB]; cluster mode: [2][NQ][TC][PB]
 
-    // per-thread, per-parameter-set constants
+    // per-parameter-set constants: shared memory [field][PB] (or registers, HBK_PAR_SHARED=0)
+    double* sPar = accb + (size_t)(a.clusterMode ? 2 : 1) * NQ * a.TC * a.PB;
     Par par;
     double quickBase = 0, gT = 0, gP = 0, corr = 1;
-    if (validP) {
-        const float* pp = a.params + p;
-        const float t0f = pp[HBK_P_TRANSITION_START * a.ldp], t1f = pp[HBK_P_TRANSITION_END * a.ldp];
-        par.t0 = t0f;
-        par.t1 = t1f;
-        par.invSpan = 1.0 / (double)(t1f - t0f);
-        par.rcf = pp[HBK_P_RAIN_CORRECTION * a.ldp];
-        par.scf = pp[HBK_P_SNOW_CORRECTION * a.ldp];
-        par.ddfG = pp[HBK_P_GROUND_SNOW_DDF * a.ldp];
-        par.tmG = pp[HBK_P_GROUND_SNOW_TMELT * a.ldp];
-        par.ddfGl = pp[HBK_P_GLACIER_SNOW_DDF * a.ldp];
-        par.tmGl = pp[HBK_P_GLACIER_SNOW_TMELT * a.ldp];
-        par.ddfIce = pp[HBK_P_ICE_DDF * a.ldp];
-        par.tmIce = pp[HBK_P_ICE_TMELT * a.ldp];
-        par.A = pp[HBK_P_CAPACITY * a.ldp];
-        par.invA = 1.0 / par.A;
-        par.k1 = pp[HBK_P_K_SLOW_1 * a.ldp];
-        par.perc = pp[HBK_P_PERCOLATION * a.ldp];
-        par.k2 = pp[HBK_P_K_SLOW_2 * a.ldp];
-        quickBase = pp[HBK_P_QUICK * a.ldp];
-        par.quick = quickBase;
-        if (a.forcingMode == 1) {
-            gT = a.gradT ? a.gradT[p] : a.gradTs;
-            gP = a.gradP ? a.gradP[p] : a.gradPs;
-            corr = a.corrP ? a.corrP[p] : a.corrPs;
+    {
+#if HBK_PAR_SHARED
+        double* pv = sPar + pl;
+        const int ps = a.PB;
+        par.b = pv;
+        par.s = ps;
+        const bool fill = validP && ul == 0;
+#else
+        double* pv = par.v;
+        const int ps = 1;
+        const bool fill = validP;
+#endif
+        if (fill) {
+            const float* pp = a.params + p;
+            const float t0f = pp[HBK_P_TRANSITION_START * a.ldp], t1f = pp[HBK_P_TRANSITION_END * a.ldp];
+            pv[0 * ps] = t0f;
+            pv[1 * ps] = t1f;
+            pv[2 * ps] = 1.0 / (double)(t1f - t0f);
+            pv[3 * ps] = pp[HBK_P_RAIN_CORRECTION * a.ldp];
+            pv[4 * ps] = pp[HBK_P_SNOW_CORRECTION * a.ldp];
+            pv[5 * ps] = pp[HBK_P_GROUND_SNOW_DDF * a.ldp];
+            pv[6 * ps] = pp[HBK_P_GROUND_SNOW_TMELT * a.ldp];
+            pv[7 * ps] = pp[HBK_P_GLACIER_SNOW_DDF * a.ldp];
+            pv[8 * ps] = pp[HBK_P_GLACIER_SNOW_TMELT * a.ldp];
+            pv[9 * ps] = pp[HBK_P_ICE_DDF * a.ldp];
+            pv[10 * ps] = pp[HBK_P_ICE_TMELT * a.ldp];
+            const double capacity = pp[HBK_P_CAPACITY * a.ldp];
+            pv[11 * ps] = capacity;
+            pv[12 * ps] = 1.0 / capacity;
+            pv[13 * ps] = pp[HBK_P_K_SLOW_1 * a.ldp];
+            pv[14 * ps] = pp[HBK_P_PERCOLATION * a.ldp];
+            pv[15 * ps] = pp[HBK_P_K_SLOW_2 * a.ldp];
+        }
+        if (validP) {
+            quickBase = a.params[p + (size_t)HBK_P_QUICK * a.ldp];
+            par.quickV = quickBase;
+            if (a.forcingMode == 1) {
+                gT = a.gradT ? a.gradT[p] : a.gradTs;
+                gP = a.gradP ? a.gradP[p] : a.gradPs;
+                corr = a.corrP ? a.corrP[p] : a.corrPs;
+            }
         }
     }
 
@@ -186,7 +203,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
         const double elev = a.hru[3 * a.ldu + u];
         // runoff:socont folded: beta*sqrt(slope)/area * (2/1000)^(5/3) * 86400 * 1000 (ProcessRunoffSocont.cpp:41-56)
         const double socontUnit = 3.174802103936398e-05 * 86400.0 * 1000.0;
-        par.quick = (a.flags.quickKind == 0) ? quickBase * slopeTerm / area * socontUnit : quickBase;
+        par.quickV = (a.flags.quickKind == 0) ? quickBase * slopeTerm / area * socontUnit : quickBase;
         glacierVariant = GLACIER && (a.hruFlags[u] & 1);
         const long long fi = a.fracPerSet ? ((long long)p * a.U + u) : u;
         fG = a.frac[fi];
@@ -976,7 +993,8 @@ void chooseShape(hbk_engine* e) {
 size_t smemBytes(const hbk_engine* e, bool tiled) {
     const int nq = e->st.has_glacier ? 3 : 1;
     const size_t fRow = tiled ? (size_t)e->TC * e->UB : (size_t)e->TC + 2;
-    return 128 + 2 * 3 * fRow * 8 + (size_t)nq * e->TC * (e->PB * e->UB + 2 * e->PB) * 8;
+    return 128 + 2 * 3 * fRow * 8 + (size_t)nq * e->TC * (e->PB * e->UB + 2 * e->PB) * 8 +
+           (size_t)hbk::kParFields * e->PB * 8;
 }
 
 using KernelFn = void (*)(const KArgs);
