@@ -454,7 +454,7 @@ def run_engine_arm(args):
             hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
         traffic = None
         try:  # measured DRAM traffic of this exact launch (ncu), only meaningful for the default C2 shape
-            tr = json.load(open(ROOT / "profiles" / "r01f_traffic.json"))
+            tr = json.load(open(ROOT / "profiles" / "r01h_traffic.json"))
             if args.workload == "c2" and args.solver == "rk4" and (P, U, T) == (P_DEFAULT, U_DEFAULT, T_DEFAULT):
                 traffic = tr["traffic_bytes"]
         except Exception:
@@ -482,7 +482,7 @@ def run_engine_arm(args):
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_fp64, "unit": "TFLOP/s",
                          "frac": achieved / peak_fp64 if peak_fp64 else None, "traffic": traffic,
-                         "traffic_note": "DRAM bytes per launch from ncu (profiles/r01f_traffic.json); algorithmic "
+                         "traffic_note": "DRAM bytes per launch from ncu (profiles/r01h_traffic.json); algorithmic "
                                          "bytes are in roofline.hbm; the excess is the unit state of the "
                                          "time-multiplexed tiles passing through L2/HBM (<3 % of HBM bandwidth)",
                          "kernel": f"hbkRunUnits<{args.solver},{wl['soil']} soil store(s),{'glacier' if wl['glacier'] else 'no glacier'}>",

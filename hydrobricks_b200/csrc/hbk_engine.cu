@@ -994,7 +994,7 @@ size_t smemBytes(const hbk_engine* e, bool tiled) {
     const int nq = e->st.has_glacier ? 3 : 1;
     const size_t fRow = tiled ? (size_t)e->TC * e->UB : (size_t)e->TC + 2;
     return 128 + 2 * 3 * fRow * 8 + (size_t)nq * e->TC * (e->PB * e->UB + 2 * e->PB) * 8 +
-           (size_t)hbk::kParFields * e->PB * 8;
+           (HBK_PAR_SHARED ? (size_t)hbk::kParFields * e->PB * 8 : 0);
 }
 
 using KernelFn = void (*)(const KArgs);
