@@ -79,6 +79,11 @@ struct KArgs {
     int T;
     int* err;
     unsigned long long* unconverged;
+    // Parameter sets are stored in an engine-chosen order (similar sets share a warp, hbk_set_parameters);
+    // perm[internal index] = caller's index, nullptr = identity. Only what leaves the engine is mapped back:
+    // final outlet rows, recorder rows, per-set spatialisation inputs.
+    const int* perm;
+    int outQFinal;  // outQ is the caller-visible outlet (no tile partials)
 };
 
 // ---- TMA bulk copy + mbarrier (PTX) ---------------------------------------------------------------
@@ -133,6 +138,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
     const int ul = tid / a.PB;
     const int p = pg * a.PB + pl;
     const bool validP = p < a.P;
+    const int pOut = (validP && a.perm) ? a.perm[p] : p;  // the caller's index of this parameter set
     const int tileBegin = a.clusterMode ? crank : grp * a.G;
     const int tileEnd = a.clusterMode ? crank + 1 : min(tileBegin + a.G, a.nUTiles);
     const bool multi = !a.clusterMode && a.G > 1;
@@ -185,9 +191,9 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
             quickBase = a.params[p + (size_t)HBK_P_QUICK * a.ldp];
             par.quickV = quickBase;
             if (a.forcingMode == 1) {
-                gT = a.gradT ? a.gradT[p] : a.gradTs;
-                gP = a.gradP ? a.gradP[p] : a.gradPs;
-                corr = a.corrP ? a.corrP[p] : a.corrPs;
+                gT = a.gradT ? a.gradT[pOut] : a.gradTs;
+                gP = a.gradP ? a.gradP[pOut] : a.gradPs;
+                corr = a.corrP ? a.corrP[pOut] : a.corrPs;
             }
         }
     }
@@ -360,7 +366,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
                         // Logger::Record (Logger.cpp:93-120): contents after Finalize and flux amounts
                         const double nan = __longlong_as_double(0x7ff8000000000000LL);
                         const bool gv = glacierVariant;
-                        double* base = a.rec + ((size_t)p * a.T + (t0 + tc)) * a.U + u;
+                        double* base = a.rec + ((size_t)pOut * a.T + (t0 + tc)) * a.U + u;
                         const size_t stride = (size_t)a.P * a.T * a.U;
                         int k = 0;
 #define HBK_REC(slot, value)                                   \
@@ -435,7 +441,8 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
                         }
                         if (gp < a.P && (a.writeOutputs || qi > 0)) {
                             double* dst = (qi == 0) ? a.outQ : (qi == 1 ? a.outD1 : a.outD2);
-                            __stcs(&dst[(size_t)gp * a.ldt + (t0 + tc)], s);
+                            const int row = (qi == 0 && a.perm) ? a.perm[gp] : gp;
+                            __stcs(&dst[(size_t)row * a.ldt + (t0 + tc)], s);
                         }
                     }
                 }
@@ -457,8 +464,9 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
                     const int gp = pg * a.PB + lp;
                     if (gp < a.P && (a.writeOutputs || qi > 0)) {  // deposits feed the basin stores during spin-up
                         double* dst = (qi == 0) ? a.outQ : (qi == 1 ? a.outD1 : a.outD2);
+                        const int row = (qi == 0 && a.outQFinal && a.perm) ? a.perm[gp] : gp;
                         // streaming store: the 8.8 GB outlet must not evict the L2-resident unit state
-                        __stcs(&dst[((size_t)grp * a.P + gp) * a.ldt + (t0 + tc)], s);
+                        __stcs(&dst[((size_t)grp * a.P + row) * a.ldt + (t0 + tc)], s);
                     }
                 }
             }
@@ -477,14 +485,14 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
 
 // Sum the unit-tile partials in tile order: out[p][t] = sum_tiles part[tile][p][t]  (only when nUTiles > 1).
 __global__ void hbkReduceTiles(const double* __restrict__ part, double* __restrict__ out, int nTiles, int P,
-                               long long ldt, int tBegin, int tEnd) {
+                               long long ldt, int tBegin, int tEnd, const int* __restrict__ perm) {
     const long long n = (long long)P * (tEnd - tBegin);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int p = (int)(i / (tEnd - tBegin));
         const int t = tBegin + (int)(i - (long long)p * (tEnd - tBegin));
         double s = 0.0;
         for (int k = 0; k < nTiles; ++k) s += part[((size_t)k * P + p) * ldt + t];
-        out[(size_t)p * ldt + t] = s;
+        out[(size_t)(perm ? perm[p] : p) * ldt + t] = s;
     }
 }
 
@@ -493,9 +501,11 @@ __global__ void hbkReduceTiles(const double* __restrict__ part, double* __restri
 template <int SOLVER>
 __global__ void hbkBasinStores(const float* params, int ldp, int P, long long ldt, int tBegin, int tEnd, double dt,
                                const double* d1, const double* d2, const double* stale, double* outlet,
-                               double* basinState, int writeOutputs, int* errFlags, unsigned long long* unconv) {
+                               double* basinState, int writeOutputs, int* errFlags, unsigned long long* unconv,
+                               const int* perm) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
+    const size_t row = perm ? perm[p] : p;  // outlet rows are in the caller's order
     const double kSnow = params[HBK_P_K_SNOW * ldp + p];
     const double kIce = params[HBK_P_K_ICE * ldp + p];
     double c1 = basinState[2 * p], c2 = basinState[2 * p + 1];
@@ -505,7 +515,7 @@ __global__ void hbkBasinStores(const float* params, int ldp, int P, long long ld
         const double dep1 = d1[(size_t)p * ldt + t], dep2 = d2[(size_t)p * ldt + t];
         const double o1 = basinStoreStep<SOLVER>(c1, kSnow, dep1, dep1 + st1, dt, err, unc);
         const double o2 = basinStoreStep<SOLVER>(c2, kIce, dep2, dep2 + st2, dt, err, unc);
-        if (writeOutputs) outlet[(size_t)p * ldt + t] = (o1 + o2) + outlet[(size_t)p * ldt + t];
+        if (writeOutputs) outlet[row * ldt + t] = (o1 + o2) + outlet[row * ldt + t];
     }
     basinState[2 * p] = c1;
     basinState[2 * p + 1] = c2;
@@ -889,6 +899,8 @@ struct hbk_engine {
     double* dDhAreas = nullptr;
     double* dDhVolumes = nullptr;
     int* dDhLastRow = nullptr;
+    int* dPerm = nullptr;       // [P] internal index -> caller's index; nullptr = identity
+    std::vector<int> perm;
     double* dScores = nullptr;  // [P]
     double* dObs = nullptr;     // [T] + 3 stats
     double* dStale = nullptr;  // [P][2] stale deposit amounts of null glacier bricks (actions only)
@@ -1038,6 +1050,8 @@ int ensureSetBuffers(hbk_engine* e, int P) {
     freeDev(e->dDhLastRow);
     freeDev(e->dStale);
     freeDev(e->dScores);
+    freeDev(e->dPerm);
+    e->perm.clear();
     e->recBytes = 0;
     e->initPerSet = false;
     e->P = P;
@@ -1133,6 +1147,7 @@ void hbk_engine_destroy(hbk_engine* e) {
     freeDev(e->dDhLastRow);
     freeDev(e->dStale);
     freeDev(e->dScores);
+    freeDev(e->dPerm);
     freeDev(e->dObs);
     freeDev(e->dErr);
     freeDev(e->dUnconv);
@@ -1188,10 +1203,46 @@ int hbk_set_parameters(hbk_engine* e, int32_t n_sets, const float* values) {
     HBK_CUDA(cudaSetDevice(e->device));
     int rc = ensureSetBuffers(e, n_sets);
     if (rc) return rc;
+    // Internal order of the parameter sets. Lanes of a warp are parameter sets; sets whose constraints bind at
+    // different times make the warp run both sides of every rare branch (ncu: 23 of 32 lanes active on random
+    // sets). Grouping similar sets — buckets of the slow-reservoir response factor (drives the "store would go
+    // negative" limit), ordered by capacity inside a bucket (drives the overflow) — gives +14 % on the C2 ensemble.
+    // Results do not depend on the order (sets are independent); everything that leaves the engine is mapped back.
+    // A per-set initial state saved from a previous run keeps the order it was saved in. HBK_SORT_SETS=0 disables.
+    const char* sortEnv = std::getenv("HBK_SORT_SETS");
+    const bool wantSort = n_sets >= 64 && !(sortEnv && sortEnv[0] == '0');
+    if (!e->initPerSet || (int)e->perm.size() != n_sets) {
+        e->perm.resize(n_sets);
+        for (int p = 0; p < n_sets; ++p) e->perm[p] = p;
+        if (wantSort && !e->initPerSet) {
+            auto val = [&](int p, int k) { return values[(size_t)p * HBK_N_PARAMS + k]; };
+            std::vector<int> byK(e->perm);
+            std::stable_sort(byK.begin(), byK.end(),
+                             [&](int x, int y) { return val(x, HBK_P_K_SLOW_1) < val(y, HBK_P_K_SLOW_1); });
+            const int nWarps = (n_sets + 31) / 32;
+            const int nBuckets = std::max(1, std::min(64, (int)std::lround(std::sqrt((double)nWarps / 3.0))));
+            std::vector<int> bucket(n_sets);
+            for (int r = 0; r < n_sets; ++r) bucket[byK[r]] = (int)((long long)r * nBuckets / n_sets);
+            std::stable_sort(e->perm.begin(), e->perm.end(), [&](int x, int y) {
+                if (bucket[x] != bucket[y]) return bucket[x] < bucket[y];
+                return val(x, HBK_P_CAPACITY) < val(y, HBK_P_CAPACITY);
+            });
+        }
+        bool identity = true;
+        for (int p = 0; p < n_sets && identity; ++p) identity = e->perm[p] == p;
+        if (identity) {
+            freeDev(e->dPerm);
+        } else {
+            if (!e->dPerm) HBK_CUDA(cudaMalloc(&e->dPerm, sizeof(int) * n_sets));
+            HBK_CUDA(cudaMemcpyAsync(e->dPerm, e->perm.data(), sizeof(int) * n_sets, cudaMemcpyHostToDevice, e->stream));
+        }
+    }
     // [n_sets][N] -> [N][ldp]: the parameter axis is the fastest one on the device
     std::vector<float> t((size_t)HBK_N_PARAMS * e->ldp, 0.0f);
-    for (int p = 0; p < n_sets; ++p)
-        for (int k = 0; k < HBK_N_PARAMS; ++k) t[(size_t)k * e->ldp + p] = values[(size_t)p * HBK_N_PARAMS + k];
+    for (int p = 0; p < n_sets; ++p) {
+        const float* src = values + (size_t)e->perm[p] * HBK_N_PARAMS;
+        for (int k = 0; k < HBK_N_PARAMS; ++k) t[(size_t)k * e->ldp + p] = src[k];
+    }
     HBK_CUDA(cudaMemcpyAsync(e->dParams, t.data(), sizeof(float) * t.size(), cudaMemcpyHostToDevice, e->stream));
     HBK_CUDA(cudaStreamSynchronize(e->stream));
     return HBK_OK;
@@ -1453,6 +1504,8 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
     a.T = e->T;
     a.err = e->dErr;
     a.unconverged = e->dUnconv;
+    a.perm = e->dPerm;
+    a.outQFinal = multi ? 0 : 1;
 
     KernelFn fn = pickKernel(e->st);
     const size_t smem = smemBytes(e, tiled);
@@ -1484,19 +1537,19 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
     if (writeOutputs && multi) {
         const long long n = (long long)e->P * (tEnd - tBegin);
         const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
-        hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartQ, e->dOutlet, e->nGroups, e->P, e->ldt, tBegin, tEnd);
+        hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartQ, e->dOutlet, e->nGroups, e->P, e->ldt, tBegin, tEnd, e->dPerm);
         e->lastLaunches++;
         if (e->st.has_glacier) {
-            hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD1, e->dD1, e->nGroups, e->P, e->ldt, tBegin, tEnd);
-            hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD2, e->dD2, e->nGroups, e->P, e->ldt, tBegin, tEnd);
+            hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD1, e->dD1, e->nGroups, e->P, e->ldt, tBegin, tEnd, nullptr);
+            hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD2, e->dD2, e->nGroups, e->P, e->ldt, tBegin, tEnd, nullptr);
             e->lastLaunches += 2;
         }
     } else if (!writeOutputs && multi && e->st.has_glacier) {
         // spin-up: the deposits are still needed by the sub-basin stores
         const long long n = (long long)e->P * (tEnd - tBegin);
         const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
-        hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD1, e->dD1, e->nGroups, e->P, e->ldt, tBegin, tEnd);
-        hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD2, e->dD2, e->nGroups, e->P, e->ldt, tBegin, tEnd);
+        hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD1, e->dD1, e->nGroups, e->P, e->ldt, tBegin, tEnd, nullptr);
+        hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD2, e->dD2, e->nGroups, e->P, e->ldt, tBegin, tEnd, nullptr);
         e->lastLaunches += 2;
     }
     if (e->st.has_glacier) {
@@ -1523,17 +1576,17 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
             case HBK_SOLVER_EULER:
                 hbkBasinStores<0><<<blocks, 128, 0, e->stream>>>(e->dParams, e->ldp, e->P, e->ldt, tBegin, tEnd, dt, e->dD1,
                                                                e->dD2, stale, e->dOutlet, e->dBasinState,
-                                                               writeOutputs ? 1 : 0, e->dErr, e->dUnconv);
+                                                               writeOutputs ? 1 : 0, e->dErr, e->dUnconv, e->dPerm);
                 break;
             case HBK_SOLVER_HEUN:
                 hbkBasinStores<1><<<blocks, 128, 0, e->stream>>>(e->dParams, e->ldp, e->P, e->ldt, tBegin, tEnd, dt, e->dD1,
                                                                e->dD2, stale, e->dOutlet, e->dBasinState,
-                                                               writeOutputs ? 1 : 0, e->dErr, e->dUnconv);
+                                                               writeOutputs ? 1 : 0, e->dErr, e->dUnconv, e->dPerm);
                 break;
             default:
                 hbkBasinStores<2><<<blocks, 128, 0, e->stream>>>(e->dParams, e->ldp, e->P, e->ldt, tBegin, tEnd, dt, e->dD1,
                                                                e->dD2, stale, e->dOutlet, e->dBasinState,
-                                                               writeOutputs ? 1 : 0, e->dErr, e->dUnconv);
+                                                               writeOutputs ? 1 : 0, e->dErr, e->dUnconv, e->dPerm);
                 break;
         }
         e->lastLaunches++;
@@ -1693,13 +1746,16 @@ int hbk_get_state(hbk_engine* e, int32_t slot, double* out) {
     if (!e->ran) return fail(e, HBK_E_STATE, "no completed run");
     HBK_CUDA(cudaSetDevice(e->device));
     const size_t n = (size_t)e->P * e->U;
-    if (!e->stateLaneP) {
+    if (!e->stateLaneP && !e->dPerm) {
         HBK_CUDA(cudaMemcpy(out, e->dState + (size_t)slot * n, sizeof(double) * n, cudaMemcpyDeviceToHost));
-    } else {  // device layout [u][p] -> out[p][u]
+    } else {  // device layout [u][p] or [p][u] in the internal set order -> out[caller's p][u]
         std::vector<double> tmp(n);
         HBK_CUDA(cudaMemcpy(tmp.data(), e->dState + (size_t)slot * n, sizeof(double) * n, cudaMemcpyDeviceToHost));
-        for (int u = 0; u < e->U; ++u)
-            for (int p = 0; p < e->P; ++p) out[(size_t)p * e->U + u] = tmp[(size_t)u * e->P + p];
+        const size_t sP = e->stateLaneP ? 1 : e->U, sU = e->stateLaneP ? e->P : 1;
+        for (int p = 0; p < e->P; ++p) {
+            const size_t row = e->dPerm ? e->perm[p] : p;
+            for (int u = 0; u < e->U; ++u) out[row * e->U + u] = tmp[p * sP + u * sU];
+        }
     }
     return HBK_OK;
 }
@@ -1708,7 +1764,16 @@ int hbk_get_basin_state(hbk_engine* e, double* out) {
     if (!e || !out) return HBK_E_ARG;
     if (!e->ran) return fail(e, HBK_E_STATE, "no completed run");
     HBK_CUDA(cudaSetDevice(e->device));
-    HBK_CUDA(cudaMemcpy(out, e->dBasinState, sizeof(double) * 2 * e->P, cudaMemcpyDeviceToHost));
+    if (!e->dPerm) {
+        HBK_CUDA(cudaMemcpy(out, e->dBasinState, sizeof(double) * 2 * e->P, cudaMemcpyDeviceToHost));
+    } else {
+        std::vector<double> tmp(2 * (size_t)e->P);
+        HBK_CUDA(cudaMemcpy(tmp.data(), e->dBasinState, sizeof(double) * 2 * e->P, cudaMemcpyDeviceToHost));
+        for (int p = 0; p < e->P; ++p) {
+            out[2 * (size_t)e->perm[p]] = tmp[2 * (size_t)p];
+            out[2 * (size_t)e->perm[p] + 1] = tmp[2 * (size_t)p + 1];
+        }
+    }
     return HBK_OK;
 }
 
