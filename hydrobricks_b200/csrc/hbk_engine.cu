@@ -148,10 +148,10 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
     const int fRow = (a.forcingMode == 0) ? a.TC * a.UB : (a.TC + 2);  // doubles per variable per stage
     double* fbuf = reinterpret_cast<double*>(smemRaw + 128);             // [2][3][fRow]
     double* qbuf = fbuf + 2 * 3 * fRow;                                  // [NQ][TC][nThreads]
-    double* accb = qbuf + (size_t)NQ * a.TC * nThreads;                  // [NQ][TC][PB]; cluster mode: [2][NQ][TC][PB]
+    double* accb = qbuf + (size_t)NQ * a.TC * nThreads;                  // cluster mode only: [2][NQ][TC][PB]
 
     // per-parameter-set constants: shared memory [field][PB] (or registers, HBK_PAR_SHARED=0)
-    double* sPar = accb + (size_t)(a.clusterMode ? 2 : 1) * NQ * a.TC * a.PB;
+    double* sPar = accb + (size_t)(a.clusterMode ? 2 : 0) * NQ * a.TC * a.PB;
     Par par;
     double quickBase = 0, gT = 0, gP = 0, corr = 1;
     {
@@ -401,17 +401,18 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
 #undef HBK_REC
                     }
                 }
-                qbuf[(size_t)tc * nThreads + tid] = o.q;
+                // this thread's slot accumulates its units of the group's tiles in tile order (no race: own slot)
+                double* slot = qbuf + (size_t)tc * nThreads + tid;
+                const bool first = a.clusterMode || tl == 0;
+                slot[0] = first ? o.q : slot[0] + o.q;
                 if (GLACIER) {
-                    qbuf[(size_t)(a.TC + tc) * nThreads + tid] = o.dep1;
-                    qbuf[(size_t)(2 * a.TC + tc) * nThreads + tid] = o.dep2;
+                    slot[(size_t)a.TC * nThreads] = first ? o.dep1 : slot[(size_t)a.TC * nThreads] + o.dep1;
+                    slot[(size_t)2 * a.TC * nThreads] = first ? o.dep2 : slot[(size_t)2 * a.TC * nThreads] + o.dep2;
                 }
             }
             if (valid && multi) storeState(u, c == nChunks - 1);
-            __syncthreads();
-            // SubBasin::ComputeOutletDischarge (SubBasin.cpp:322-329): add this tile's units, in unit order, to
-            // the chunk accumulator; entry (qi, tc, lp) is always owned by the same thread.
             if (a.clusterMode) {
+                __syncthreads();
                 // this CTA's tile sum -> its partial buffer (double buffered by chunk parity) ...
                 double* part = accb + (size_t)(c & 1) * NQ * a.TC * a.PB;
                 for (int idx = tid; idx < NQ * n * a.PB; idx += nThreads) {
@@ -448,19 +449,19 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
                 }
                 continue;  // the next chunk writes the other partial buffer; its cluster.sync orders the reuse
             }
+            // SubBasin::ComputeOutletDischarge (SubBasin.cpp:322-329): after the last tile of the group, the UB
+            // per-thread sums of every (quantity, step, set) are added in thread order and written out.
             const bool last = (tl == nTilesHere - 1);
-            for (int idx = tid; idx < NQ * n * a.PB; idx += nThreads) {
-                const int qi = idx / (n * a.PB);
-                const int rem = idx - qi * n * a.PB;
-                const int tc = rem / a.PB;
-                const int lp = rem - tc * a.PB;
-                const double* src = qbuf + ((size_t)qi * a.TC + tc) * nThreads + lp;
-                double* acc = accb + ((size_t)qi * a.TC + tc) * a.PB + lp;
-                double s = (tl == 0) ? 0.0 : *acc;
-                for (int k = 0; k < a.UB; ++k) s += src[(size_t)k * a.PB];
-                if (!last) {
-                    *acc = s;
-                } else {
+            if (last) {
+                __syncthreads();
+                for (int idx = tid; idx < NQ * n * a.PB; idx += nThreads) {
+                    const int qi = idx / (n * a.PB);
+                    const int rem = idx - qi * n * a.PB;
+                    const int tc = rem / a.PB;
+                    const int lp = rem - tc * a.PB;
+                    const double* src = qbuf + ((size_t)qi * a.TC + tc) * nThreads + lp;
+                    double s = 0.0;
+                    for (int k = 0; k < a.UB; ++k) s += src[(size_t)k * a.PB];
                     const int gp = pg * a.PB + lp;
                     if (gp < a.P && (a.writeOutputs || qi > 0)) {  // deposits feed the basin stores during spin-up
                         double* dst = (qi == 0) ? a.outQ : (qi == 1 ? a.outD1 : a.outD2);
@@ -470,7 +471,8 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
                     }
                 }
             }
-            __syncthreads();
+            // the slots are rewritten by the next chunk; per-unit forcing stages are recycled tile by tile
+            if (last || a.forcingMode == 0) __syncthreads();
         }
     }
 
@@ -986,9 +988,10 @@ void chooseShape(hbk_engine* e) {
     const int nq = e->st.has_glacier ? 3 : 1;
     // chunk length: shared memory per block small enough for HBK_MIN_BLOCKS blocks per SM
     const size_t budget = (size_t)(220 * 1024) / HBK_MIN_BLOCKS - 1024;
-    // (measured: longer chunks cost more than they save, the shared-memory carve-out shrinks the L1 that
-    // serves the register spills; 8 steps per chunk was the optimum on C2, profiles/r01_tuning.md)
-    int tc = 8;
+    // (measured: the shared-memory carve-out shrinks the L1 that serves the register spills; with one block
+    // barrier per chunk, 16 steps per chunk is the optimum on C2: 4 -> 2.07e10, 8 -> 2.14e10, 16 -> 2.18e10,
+    // profiles/r01_tuning.md)
+    int tc = 16;
     for (;;) {
         const size_t fRow = (e->haveRaw[0] ? (size_t)tc * e->UB : (size_t)tc + 2);
         const size_t bytes = 128 + 2 * 3 * fRow * 8 + (size_t)nq * tc * (e->PB * e->UB + 2 * e->PB) * 8;
@@ -1005,7 +1008,7 @@ void chooseShape(hbk_engine* e) {
 size_t smemBytes(const hbk_engine* e, bool tiled) {
     const int nq = e->st.has_glacier ? 3 : 1;
     const size_t fRow = tiled ? (size_t)e->TC * e->UB : (size_t)e->TC + 2;
-    return 128 + 2 * 3 * fRow * 8 + (size_t)nq * e->TC * (e->PB * e->UB + 2 * e->PB) * 8 +
+    return 128 + 2 * 3 * fRow * 8 + (size_t)nq * e->TC * (e->PB * e->UB + (e->clusterMode ? 2 * e->PB : 0)) * 8 +
            (HBK_PAR_SHARED ? (size_t)hbk::kParFields * e->PB * 8 : 0);
 }
 
