@@ -122,7 +122,9 @@ __device__ __forceinline__ void tmaLoad1D(void* dst, const void* src, uint32_t b
 //   outlet contributions to the chunk accumulator; after the last tile write outlet[p][t0..t0+TC).
 // With G = all tiles (ensembles) one block sums every unit of its parameter sets in unit order: no partial
 // buffers, no second pass. With G = 1 (few sets, many units) the state never leaves the registers.
-template <int SOLVER, int NSOIL, bool GLACIER>
+// DAILY: the time step is exactly one day (the reference's usual case); x * 1.0 and x / 1.0 are exact, so the
+// multiplications by dt fold away without changing a bit.
+template <int SOLVER, int NSOIL, bool GLACIER, bool DAILY>
 __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLACIER : HBK_MIN_BLOCKS)
     hbkRunUnits(const KArgs a) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
@@ -276,7 +278,8 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
         }
     };
 
-    const double invDt = 1.0 / a.dt;
+    const double dt = DAILY ? 1.0 : a.dt;
+    const double invDt = DAILY ? 1.0 : 1.0 / a.dt;
     const int nSteps = a.tEnd - a.tBegin;
     const int nChunks = (nSteps + a.TC - 1) / a.TC;
     const int nTilesHere = tileEnd - tileBegin;
@@ -359,8 +362,8 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
                         precip = (precip < 0.0) ? 0.0 : precip;
                         pet = (xe < 0.0) ? 0.0 : xe;
                     }
-                    directPhase<GLACIER>(h, par, precip, temp, a.dt, invDt, fa, fG, fGl, glacierVariant, a.flags, o, err);
-                    solveUnit<SOLVER, NSOIL>(h, par, pet, fa, a.dt, invDt, a.flags, o, err, unconverged);
+                    directPhase<GLACIER>(h, par, precip, temp, dt, invDt, fa, fG, fGl, glacierVariant, a.flags, o, err);
+                    solveUnit<SOLVER, NSOIL>(h, par, pet, fa, dt, invDt, a.flags, o, err, unconverged);
 
                     if (nRec && a.writeOutputs) {
                         // Logger::Record (Logger.cpp:93-120): contents after Finalize and flux amounts
@@ -1015,21 +1018,25 @@ size_t smemBytes(const hbk_engine* e, bool tiled) {
 
 using KernelFn = void (*)(const KArgs);
 
+template <int SOLVER, int NSOIL, bool GLACIER>
+KernelFn pickDaily(bool daily) {
+    return daily ? (KernelFn)hbkRunUnits<SOLVER, NSOIL, GLACIER, true> : (KernelFn)hbkRunUnits<SOLVER, NSOIL, GLACIER, false>;
+}
 template <int SOLVER, int NSOIL>
-KernelFn pickGlacier(bool glacier) {
-    return glacier ? (KernelFn)hbkRunUnits<SOLVER, NSOIL, true> : (KernelFn)hbkRunUnits<SOLVER, NSOIL, false>;
+KernelFn pickGlacier(bool glacier, bool daily) {
+    return glacier ? pickDaily<SOLVER, NSOIL, true>(daily) : pickDaily<SOLVER, NSOIL, false>(daily);
 }
 template <int SOLVER>
-KernelFn pickSoil(int nSoil, bool glacier) {
-    return nSoil == 2 ? pickGlacier<SOLVER, 2>(glacier) : pickGlacier<SOLVER, 1>(glacier);
+KernelFn pickSoil(int nSoil, bool glacier, bool daily) {
+    return nSoil == 2 ? pickGlacier<SOLVER, 2>(glacier, daily) : pickGlacier<SOLVER, 1>(glacier, daily);
 }
 // "Device functions selected from a per-structure process table": the table (hbk_structure) picks the
-// template instantiation.
+// template instantiation, i.e. which process device functions are compiled into the time loop.
 KernelFn pickKernel(const hbk_structure& st) {
     switch (st.solver) {
-        case HBK_SOLVER_EULER: return pickSoil<0>(st.n_soil_stores, st.has_glacier != 0);
-        case HBK_SOLVER_HEUN: return pickSoil<1>(st.n_soil_stores, st.has_glacier != 0);
-        default: return pickSoil<2>(st.n_soil_stores, st.has_glacier != 0);
+        case HBK_SOLVER_EULER: return pickSoil<0>(st.n_soil_stores, st.has_glacier != 0, st.time_step_days == 1.0);
+        case HBK_SOLVER_HEUN: return pickSoil<1>(st.n_soil_stores, st.has_glacier != 0, st.time_step_days == 1.0);
+        default: return pickSoil<2>(st.n_soil_stores, st.has_glacier != 0, st.time_step_days == 1.0);
     }
 }
 
