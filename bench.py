@@ -470,7 +470,8 @@ def run_engine_arm(args):
                        "forcing": "station series + fused elevation-gradient spatialisation",
                        "l2": "256 MiB flush between timed iterations; per-step output 8.8 GB >> L2",
                        "block_shape": "32 parameter sets (lanes) x 4 units per block, all unit tiles time-multiplexed "
-                                      "on the block, 8 steps per chunk"},
+                                      "on the block, 16 steps per chunk; parameter sets ordered inside the engine "
+                                      "so that warps hold similar sets"},
             "wall_ms_per_step": wall_ms / args.steps,
             "e2e": {"value": e2e_value, "unit": "HRU*timesteps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "note": "pinned host params+station series -> device, run, full "
