@@ -30,10 +30,14 @@ sys.path.insert(0, str(ROOT))
 
 U_DEFAULT, T_DEFAULT, P_DEFAULT = 50, 10957, 100000
 START, END = "1981-01-01", "2010-12-31"
-# Executed FP64 work of the dominant kernel per HRU*timestep, from the ncu instruction-mix capture of this same
-# workload (profiles/): flops = DADD + DMUL + 2*DFMA thread instructions / (P*U*T). Updated per round.
-FP64_FLOPS_PER_HRU_STEP = 535.8
-FP64_FLOPS_SOURCE = "profiles/r01a_instmix.csv: (DADD + DMUL + 2*DFMA) thread instructions / HRU*timesteps of the faithful r01a kernel"
+# ALGORITHMIC FP64 work per HRU*timestep: DADD + DMUL + 2*DFMA thread instructions / (P*U*T) executed by the
+# faithful first formulation (r01a, Socont RK4, 1 soil store: the C2 structure), kept fixed while later kernels spend
+# fewer instructions on the same result (r01k executes 267). Heun / Euler were not captured at r01a: scaled by their
+# stage count with the direct phase (17 % of the RK4 step in the per-function profile) held constant.
+FP64_FLOPS_PER_HRU_STEP = {"rk4": 535.8, "heun_explicit": 91.0 + 2 * 111.2, "euler_explicit": 91.0 + 111.2}
+FP64_FLOPS_SOURCE = ("profiles/r01a_instmix.csv: (DADD + DMUL + 2*DFMA) thread instructions / HRU*timesteps of the "
+                     "faithful r01a kernel (Socont RK4, 1 soil store); heun/euler: direct phase 91 + 111.2 per stage "
+                     "(estimate); glacier / 2-store structures use the same figure (under-estimate)")
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -444,7 +448,8 @@ def run_engine_arm(args):
 
     if rank == 0:
         main_ms = kern_ms / args.steps  # device time of one hbk_run (state reset + unit kernel), CUDA events
-        flops = FP64_FLOPS_PER_HRU_STEP * P * U * T
+        flops_unit = FP64_FLOPS_PER_HRU_STEP[args.solver]
+        flops = flops_unit * P * U * T
         achieved = flops / (main_ms * 1e-3) / 1e12
         hbm_bytes = P * T * 8 + 3 * T * 8 + P * hbk_engine.N_PARAMS * 4
         try:
@@ -454,7 +459,7 @@ def run_engine_arm(args):
             hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
         traffic = None
         try:  # measured DRAM traffic of this exact launch (ncu), only meaningful for the default C2 shape
-            tr = json.load(open(ROOT / "profiles" / "r01h_traffic.json"))
+            tr = json.load(open(ROOT / "profiles" / "r01k_traffic.json"))
             if args.workload == "c2" and args.solver == "rk4" and (P, U, T) == (P_DEFAULT, U_DEFAULT, T_DEFAULT):
                 traffic = tr["traffic_bytes"]
         except Exception:
@@ -483,12 +488,12 @@ def run_engine_arm(args):
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_fp64, "unit": "TFLOP/s",
                          "frac": achieved / peak_fp64 if peak_fp64 else None, "traffic": traffic,
-                         "traffic_note": "DRAM bytes per launch from ncu (profiles/r01h_traffic.json); algorithmic "
+                         "traffic_note": "DRAM bytes per launch from ncu (profiles/r01k_traffic.json); algorithmic "
                                          "bytes are in roofline.hbm; the excess is the unit state of the "
                                          "time-multiplexed tiles passing through L2/HBM (<3 % of HBM bandwidth)",
                          "kernel": f"hbkRunUnits<{args.solver},{wl['soil']} soil store(s),{'glacier' if wl['glacier'] else 'no glacier'}>",
                          "kernel_ms": main_ms,
-                         "flops_per_hru_step": FP64_FLOPS_PER_HRU_STEP, "flops_source": FP64_FLOPS_SOURCE,
+                         "flops_per_hru_step": flops_unit, "flops_source": FP64_FLOPS_SOURCE,
                          "peak_source": "DFMA micro-benchmark measured in this run (hbk_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 figure",
                          "note": "not a dense contraction: neither HBM nor tensor binds, the FP64 pipe does "
