@@ -84,6 +84,7 @@ struct KArgs {
     // final outlet rows, recorder rows, per-set spatialisation inputs.
     const int* perm;
     int outQFinal;  // outQ is the caller-visible outlet (no tile partials)
+    const double* swatFactor;  // [T]: 1 + sin(2 pi (day of year - ref) / 365), transform:snow_ice_swat; else nullptr
 };
 
 // ---- TMA bulk copy + mbarrier (PTX) ---------------------------------------------------------------
@@ -188,6 +189,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
             pv[13 * ps] = pp[HBK_P_K_SLOW_1 * a.ldp];
             pv[14 * ps] = pp[HBK_P_PERCOLATION * a.ldp];
             pv[15 * ps] = pp[HBK_P_K_SLOW_2 * a.ldp];
+            pv[16 * ps] = pp[HBK_P_SNOW_ICE * a.ldp];
         }
         if (validP) {
             quickBase = a.params[p + (size_t)HBK_P_QUICK * a.ldp];
@@ -247,9 +249,10 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
                 h.amtMeltGl = a.state[HBK_S_AMT_MELT_GLACIER * a.lds + si];
                 h.amtDep1 = a.state[HBK_S_AMT_DEPOSIT_RAIN_SNOWMELT * a.lds + si];
                 h.amtDep2 = a.state[HBK_S_AMT_DEPOSIT_ICEMELT * a.lds + si];
+                h.amtSnowIce = a.state[HBK_S_AMT_SNOW_ICE * a.lds + si];
             }
         } else {
-            h.snowGl = h.wGl = h.ice = h.amtMeltGl = h.amtDep1 = h.amtDep2 = 0.0;
+            h.snowGl = h.wGl = h.ice = h.amtMeltGl = h.amtDep1 = h.amtDep2 = h.amtSnowIce = 0.0;
         }
     };
     auto storeState = [&](int u, bool full) {
@@ -274,6 +277,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
                 a.state[HBK_S_AMT_MELT_GLACIER * a.lds + si] = h.amtMeltGl;
                 a.state[HBK_S_AMT_DEPOSIT_RAIN_SNOWMELT * a.lds + si] = h.amtDep1;
                 a.state[HBK_S_AMT_DEPOSIT_ICEMELT * a.lds + si] = h.amtDep2;
+                a.state[HBK_S_AMT_SNOW_ICE * a.lds + si] = h.amtSnowIce;
             }
         }
     };
@@ -362,7 +366,8 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
                         precip = (precip < 0.0) ? 0.0 : precip;
                         pet = (xe < 0.0) ? 0.0 : xe;
                     }
-                    directPhase<GLACIER>(h, par, precip, temp, dt, invDt, fa, fG, fGl, glacierVariant, a.flags, o, err);
+                    directPhase<GLACIER>(h, par, precip, temp, dt, invDt, fa, fG, fGl, glacierVariant, a.flags, o, err,
+                                         (GLACIER && a.swatFactor) ? a.swatFactor[t0 + tc] : 0.0);
                     solveUnit<SOLVER, NSOIL>(h, par, pet, fa, dt, invDt, a.flags, o, err, unconverged);
 
                     if (nRec && a.writeOutputs) {
@@ -401,6 +406,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
                         HBK_REC(HBK_R_QUICK_RUNOFF, o.amtQ)
                         HBK_REC(HBK_R_FRACTION_GROUND, fG)
                         HBK_REC(HBK_R_FRACTION_GLACIER, gv ? fGl : nan)
+                        HBK_REC(HBK_R_GLACIER_SNOWPACK_TRANSFO, gv ? h.amtSnowIce : nan)
 #undef HBK_REC
                     }
                 }
@@ -904,6 +910,7 @@ struct hbk_engine {
     double* dDhAreas = nullptr;
     double* dDhVolumes = nullptr;
     int* dDhLastRow = nullptr;
+    double* dSwatFactor = nullptr;  // [T] day-of-year term of transform:snow_ice_swat
     int* dPerm = nullptr;       // [P] internal index -> caller's index; nullptr = identity
     std::vector<int> perm;
     double* dScores = nullptr;  // [P]
@@ -1040,6 +1047,25 @@ KernelFn pickKernel(const hbk_structure& st) {
     }
 }
 
+// TimeMachine::GetCurrentDayOfYear (TimeMachine.cpp:87-98) of the civil date of floor(mjd).
+int dayOfYear(double mjd) {
+    if (mjd <= 0) return 1;
+    const long long z = (long long)std::floor(mjd) - 40587LL + 719468LL;  // days since 0000-03-01
+    const long long era = (z >= 0 ? z : z - 146096) / 146097;
+    const unsigned doe = (unsigned)(z - era * 146097);
+    const unsigned yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+    const unsigned doyMarch = doe - (365 * yoe + yoe / 4 - yoe / 100);
+    const unsigned mp = (5 * doyMarch + 2) / 153;
+    const unsigned day = doyMarch - (153 * mp + 2) / 5 + 1;
+    const unsigned month = mp < 10 ? mp + 3 : mp - 9;
+    const long long year = (long long)yoe + era * 400 + (month <= 2);
+    static const int cumMonthDays[12] = {0, 31, 59, 90, 120, 151, 181, 212, 243, 273, 304, 334};
+    const bool leap = (year % 4 == 0 && (year % 100 != 0 || year % 400 == 0));
+    int doy = cumMonthDays[month - 1] + (int)day;
+    if (leap && month > 2) doy += 1;
+    return doy;
+}
+
 int ensureSetBuffers(hbk_engine* e, int P) {
     if ((size_t)P == e->allocP) return HBK_OK;
     freeDev(e->dParams);
@@ -1118,6 +1144,22 @@ int hbk_engine_create(const hbk_structure* st, int32_t n_units, int32_t n_steps,
               cudaMalloc(&e->dUnconv, sizeof(unsigned long long)) == cudaSuccess;
     if (!ok) return bail(HBK_E_CUDA, "device allocation failed");
     cudaMemset(e->dInitUnit, 0, sizeof(double) * HBK_N_STATES * n_units);
+    if (st->snow_ice_kind < HBK_SNOW_ICE_NONE || st->snow_ice_kind > HBK_SNOW_ICE_SWAT)
+        return bail(HBK_E_ARG, "unknown snow_ice_kind");
+    if (st->has_glacier && st->snow_ice_kind == HBK_SNOW_ICE_SWAT) {
+        // ProcessTransformSnowToIceSwat.cpp:31-39: 1 + sin(2 pi (doy - ref) / 365) per time step, in double like
+        // the reference's expression (2.0f * constants::pi promotes to double), doy as TimeMachine.cpp:87-98
+        std::vector<double> factor(n_steps);
+        const int daysRef = st->north_hemisphere ? 81 : 264;
+        const double pi = 3.1415926535897932384626433832795;
+        for (int t = 0; t < n_steps; ++t) {
+            const int doy = dayOfYear(st->start_mjd + t * st->time_step_days);
+            factor[t] = 1 + std::sin(2.0f * pi * (doy - daysRef) / 365.0f);
+        }
+        if (cudaMalloc(&e->dSwatFactor, sizeof(double) * n_steps) != cudaSuccess ||
+            cudaMemcpy(e->dSwatFactor, factor.data(), sizeof(double) * n_steps, cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail(HBK_E_CUDA, "device allocation failed");
+    }
     *out = e;
     return HBK_OK;
 }
@@ -1129,6 +1171,7 @@ void hbk_engine_destroy(hbk_engine* e) {
     freeDev(e->dParams);
     freeDev(e->dHru);
     freeDev(e->dHruFlags);
+    freeDev(e->dSwatFactor);
     freeDev(e->dFrac);
     freeDev(e->dFracInit);
     for (int v = 0; v < 3; ++v) {
@@ -1479,6 +1522,8 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
     a.flags.slowOrder = e->st.slow_process_order;
     a.flags.splitKind = e->st.splitter_kind;
     a.flags.iceInfinite = e->st.glacier_infinite_storage;
+    a.flags.snowIceKind = e->st.has_glacier ? e->st.snow_ice_kind : 0;
+    a.swatFactor = (a.flags.snowIceKind == HBK_SNOW_ICE_SWAT) ? e->dSwatFactor : nullptr;
     a.flags.noMeltWhenSnow = e->st.glacier_no_melt_when_snow_cover;
     a.dt = e->st.time_step_days;
     a.params = e->dParams;

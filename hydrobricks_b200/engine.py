@@ -19,11 +19,12 @@ LIB_PATH = Path(os.environ.get("HBK_LIB", HERE / "libhbk.so"))  # HBK_LIB: tunin
 SOLVER = {"euler_explicit": 0, "heun_explicit": 1, "rk4": 2, "runge_kutta": 2}
 QUICK_SOCONT, QUICK_LINEAR = 0, 1
 SPLIT_LINEAR, SPLIT_THRESHOLD = 0, 1
+SNOW_ICE_NONE, SNOW_ICE_CONSTANT, SNOW_ICE_SWAT = 0, 1, 2
 VAR = {"precipitation": 0, "p": 0, "temperature": 1, "t": 1, "pet": 2}
 PARAM_SLOTS = [
     "transition_start", "transition_end", "rain_correction", "snow_correction", "ground_snow_ddf",
     "ground_snow_tmelt", "glacier_snow_ddf", "glacier_snow_tmelt", "ice_ddf", "ice_tmelt", "capacity", "k_slow_1",
-    "percolation", "k_slow_2", "quick", "k_snow", "k_ice",
+    "percolation", "k_slow_2", "quick", "k_snow", "k_ice", "snow_ice",
 ]
 N_PARAMS = len(PARAM_SLOTS)
 RECORD_SLOTS = [
@@ -31,12 +32,12 @@ RECORD_SLOTS = [
     "glacier_melt", "ground_snowpack_water", "ground_snowpack_snow", "ground_snowpack_melt",
     "glacier_snowpack_water", "glacier_snowpack_snow", "glacier_snowpack_melt", "slow_water", "slow_et",
     "slow_outflow", "slow_overflow", "slow_percolation", "slow2_water", "slow2_outflow", "quick_water",
-    "quick_runoff", "fraction_ground", "fraction_glacier",
+    "quick_runoff", "fraction_ground", "fraction_glacier", "glacier_snowpack_transfo",
 ]
 STATE_SLOTS = [
     "ground_snow", "glacier_snow", "ground_water", "glacier_water", "ice", "slow", "slow2", "quick",
     "amt_infiltration", "amt_rest", "amt_melt_ground", "amt_melt_glacier", "amt_deposit_rain_snowmelt",
-    "amt_deposit_icemelt",
+    "amt_deposit_icemelt", "amt_snow_ice",
 ]
 
 
@@ -51,6 +52,9 @@ class HbkStructure(ctypes.Structure):
         ("glacier_infinite_storage", ctypes.c_int32),
         ("glacier_no_melt_when_snow_cover", ctypes.c_int32),
         ("time_step_days", ctypes.c_double),
+        ("snow_ice_kind", ctypes.c_int32),
+        ("north_hemisphere", ctypes.c_int32),
+        ("start_mjd", ctypes.c_double),
     ]
 
 

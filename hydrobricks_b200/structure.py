@@ -47,7 +47,7 @@ def _target(proc):
 
 
 class CompiledStructure:
-    def __init__(self, structures, solver: str, time_step_days: float = 1.0):
+    def __init__(self, structures, solver: str, time_step_days: float = 1.0, start_mjd: float = 44605.0):
         if solver not in _e.SOLVER:
             raise UnsupportedStructure(
                 f"solver {solver!r}: only euler_explicit, heun_explicit and rk4/runge_kutta run on the device")
@@ -56,6 +56,7 @@ class CompiledStructure:
         self.labels = {}
         self.params = np.zeros(_e.N_PARAMS, dtype=np.float32)
         self.param_index = {}  # (component, parameter name) -> slot
+        self.start_mjd = float(start_mjd)
         self._compile(structures, time_step_days)
 
     # ------------------------------------------------------------------------------------------------
@@ -87,6 +88,9 @@ class CompiledStructure:
         st = _e.HbkStructure()
         st.solver = _e.SOLVER[self.solver]
         st.time_step_days = float(dt)
+        st.snow_ice_kind = _e.SNOW_ICE_NONE
+        st.north_hemisphere = 1
+        st.start_mjd = self.start_mjd
 
         # --- splitters
         if base["sub_basin_splitters"]:
@@ -142,10 +146,24 @@ class CompiledStructure:
                             f"{g}:{ground['processes'][1]['name']}:output": "ground_runoff"})
 
         # --- snowpacks
+        transfo_kinds = {"transform:snow_ice_constant": _e.SNOW_ICE_CONSTANT,
+                         "transformation:snow_ice_constant": _e.SNOW_ICE_CONSTANT,
+                         "transform:snow_ice_swat": _e.SNOW_ICE_SWAT, "transformation:snow_ice_swat": _e.SNOW_ICE_SWAT}
+
         def snowpack_of(cover):
             sps = [b for b in full["hydro_unit_bricks"] if b["kind"] == "snowpack" and b.get("parent") == cover["name"]]
-            if len(sps) != 1 or _proc_kinds(sps[0]) != ["melt:degree_day"] or _target(sps[0]["processes"][0]) != cover["name"]:
-                raise UnsupportedStructure(f"cover {cover['name']}: expected one snowpack with melt:degree_day")
+            ok = len(sps) == 1 and _target(sps[0]["processes"][0]) == cover["name"]
+            kinds = _proc_kinds(sps[0]) if ok else []
+            if ok and cover["kind"] == "glacier" and len(kinds) == 2 and kinds[1] in transfo_kinds:
+                # SettingsModel::AddSnowIceTransformation (SettingsModel.cpp:547-559): snow -> the glacier's ice
+                out = sps[0]["processes"][1]["outputs"]
+                ok = kinds[0] == "melt:degree_day" and len(out) == 1 and out[0]["target"] == cover["name"] and \
+                    out[0]["flux_type"] == "ice" and not out[0]["instantaneous"] and not out[0]["static"]
+            elif ok:
+                ok = kinds == ["melt:degree_day"]
+            if not ok:
+                raise UnsupportedStructure(f"cover {cover['name']}: expected one snowpack with melt:degree_day"
+                                           " [+ transform:snow_ice_constant|swat on a glacier]")
             return sps[0]
 
         gsp = snowpack_of(ground)
@@ -186,6 +204,18 @@ class CompiledStructure:
                                 f"{glsp['name']}:snow_content": "glacier_snowpack_snow",
                                 f"{glsp['name']}:{glsp['processes'][0]['name']}:output": "glacier_snowpack_melt"})
             snowpacks.append(glsp["name"])
+            if len(glsp["processes"]) == 2:
+                tp = glsp["processes"][1]
+                st.snow_ice_kind = transfo_kinds[tp["kind"]]
+                tv = _params(tp)
+                if st.snow_ice_kind == _e.SNOW_ICE_CONSTANT:
+                    pname = "snow_ice_transformation_rate" if "snow_ice_transformation_rate" in tv else "rate"
+                else:
+                    pname = "snow_ice_transformation_basal_acc_coeff" \
+                        if "snow_ice_transformation_basal_acc_coeff" in tv else "basal_acc_coeff"
+                    st.north_hemisphere = int(not (float(tv.get("north_hemisphere", 1)) == 0))
+                self._set("snow_ice", glsp["name"], pname, tv[pname])
+                self.labels[f"{glsp['name']}:{tp['name']}:output"] = "glacier_snowpack_transfo"
             for name, slot in ((b1, "k_snow"), (b2, "k_ice")):
                 bb = basin_bricks.get(name)
                 if bb is None or bb["kind"] != "storage" or _proc_kinds(bb) != ["outflow:linear"] or \
@@ -340,9 +370,10 @@ def slope_m_per_m(value: float, unit: str) -> np.float32:
     raise ValueError(f"unsupported slope unit {unit!r}")
 
 
-def build_engine(structures, units, solver, n_steps, device=0, time_step_days=1.0):
-    """Compile + create an engine + upload the basin. `units` as in tests/golden (basin order)."""
-    cs = CompiledStructure(structures, solver, time_step_days)
+def build_engine(structures, units, solver, n_steps, device=0, time_step_days=1.0, start_mjd=44605.0):
+    """Compile + create an engine + upload the basin. `units` as in tests/golden (basin order).
+    start_mjd: modified Julian date of time step 0 (default 1981-01-01), read by day-of-year processes."""
+    cs = CompiledStructure(structures, solver, time_step_days, start_mjd)
     eng = _e.Engine(cs.hbk, len(units), n_steps, device)
     area = [u["area"] for u in units]
     elev = [u.get("elevation", 0.0) for u in units]

@@ -36,6 +36,8 @@ enum { HBK_SPLIT_LINEAR = 0, HBK_SPLIT_THRESHOLD = 1 };
 enum { HBK_SLOW_ORDER_ET_OUT_OVF_PERC = 0 /* models/socont.py:171-190 */,
        HBK_SLOW_ORDER_ET_OUT_PERC_OVF = 1 /* core/tests/src/helpers.cpp:74-86 */ };
 enum { HBK_VAR_PRECIPITATION = 0, HBK_VAR_TEMPERATURE = 1, HBK_VAR_PET = 2 };
+/* glacier snowpack process after the melt: none | transform:snow_ice_constant | transform:snow_ice_swat */
+enum { HBK_SNOW_ICE_NONE = 0, HBK_SNOW_ICE_CONSTANT = 1, HBK_SNOW_ICE_SWAT = 2 };
 
 /* The per-structure process table for the Socont family, as the structure compiler
  * (hydrobricks_b200/csrc/hb_host.cpp) derives it from a SettingsModel. */
@@ -49,6 +51,12 @@ typedef struct {
     int32_t glacier_infinite_storage; /* Glacier.cpp:21-33 */
     int32_t glacier_no_melt_when_snow_cover;
     double time_step_days;            /* TimeMachine time step in days */
+    /* continuous snow -> ice transformation on the glacier snowpack (SettingsModel::AddSnowIceTransformation,
+     * SettingsModel.cpp:547-559): HBK_SNOW_ICE_* ; north_hemisphere and the date of the first step feed the
+     * day-of-year term of transform:snow_ice_swat (ProcessTransformSnowToIceSwat.cpp:31-39). */
+    int32_t snow_ice_kind;
+    int32_t north_hemisphere;
+    double start_mjd;                 /* modified Julian date of time step 0 (TimeMachine) */
 } hbk_structure;
 
 /* Parameter slots of one parameter set: float32 like the reference (Parameter.h:121). */
@@ -70,6 +78,7 @@ enum {
     HBK_P_QUICK,      /* surface_runoff:beta or :response_factor */
     HBK_P_K_SNOW,     /* glacier_area_rain_snowmelt_storage:response_factor */
     HBK_P_K_ICE,      /* glacier_area_icemelt_storage:response_factor */
+    HBK_P_SNOW_ICE,   /* glacier_snowpack:snow_ice_transformation_rate or :snow_ice_transformation_basal_acc_coeff */
     HBK_N_PARAMS
 };
 
@@ -83,6 +92,7 @@ enum {
     HBK_R_SLOW2_WATER, HBK_R_SLOW2_OUTFLOW,
     HBK_R_QUICK_WATER, HBK_R_QUICK_RUNOFF,
     HBK_R_FRACTION_GROUND, HBK_R_FRACTION_GLACIER, /* land-cover fraction series (Logger::RecordFractions) */
+    HBK_R_GLACIER_SNOWPACK_TRANSFO,                /* glacier_snowpack:snow_ice_transfo:output */
     HBK_N_RECORDS
 };
 
@@ -91,7 +101,7 @@ enum {
     HBK_S_GROUND_SNOW = 0, HBK_S_GLACIER_SNOW, HBK_S_GROUND_WATER, HBK_S_GLACIER_WATER, HBK_S_ICE,
     HBK_S_SLOW, HBK_S_SLOW2, HBK_S_QUICK,
     HBK_S_AMT_INFILTRATION, HBK_S_AMT_REST, HBK_S_AMT_MELT_GROUND, HBK_S_AMT_MELT_GLACIER,
-    HBK_S_AMT_DEPOSIT_RAIN_SNOWMELT, HBK_S_AMT_DEPOSIT_ICEMELT,
+    HBK_S_AMT_DEPOSIT_RAIN_SNOWMELT, HBK_S_AMT_DEPOSIT_ICEMELT, HBK_S_AMT_SNOW_ICE,
     HBK_N_STATES
 };
 

@@ -98,6 +98,7 @@ struct Event {
 struct hbo_model {
     int nUnits, nSteps, solver, spinupSteps;
     double dt;
+    double startMjd = 44605.0;
     int cursor = 0;
     std::vector<Flux> fluxes;
     std::vector<Container> containers;
@@ -370,6 +371,25 @@ void BrickFinalize(hbo_model& m, Brick& b) {
 
 // ---- processes --------------------------------------------------------------------------------
 
+// TimeMachine::GetCurrentDayOfYear (TimeMachine.cpp:87-98) over UtilsDateTime::FromMJD (civil date of floor(mjd)).
+int DayOfYear(double mjd) {
+    if (mjd <= 0) return 1;
+    long long z = static_cast<long long>(std::floor(mjd)) + 2400001LL - 2440588LL + 719468LL;  // days since 0000-03-01
+    const long long era = (z >= 0 ? z : z - 146096) / 146097;
+    const unsigned doe = static_cast<unsigned>(z - era * 146097);
+    const unsigned yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+    const unsigned doyMarch = doe - (365 * yoe + yoe / 4 - yoe / 100);
+    const unsigned mp = (5 * doyMarch + 2) / 153;
+    const unsigned day = doyMarch - (153 * mp + 2) / 5 + 1;
+    const unsigned month = mp < 10 ? mp + 3 : mp - 9;
+    const long long year = static_cast<long long>(yoe) + era * 400 + (month <= 2);
+    static const int cumMonthDays[12] = {0, 31, 59, 90, 120, 151, 181, 212, 243, 273, 304, 334};
+    const bool leap = (year % 4 == 0 && (year % 100 != 0 || year % 400 == 0));
+    int doy = cumMonthDays[month - 1] + static_cast<int>(day);
+    if (leap && month > 2) doy += 1;
+    return doy;
+}
+
 void StoreRates1(Process& p, double v) { p.rates.assign(1, v); }
 
 void GetRates(hbo_model& m, Process& p) {
@@ -445,6 +465,20 @@ void GetRates(hbo_model& m, Process& p) {
         case HBO_P_PERCOLATION_CONSTANT: {  // ProcessPercolationConstant.cpp:23-25
             const float r = p.params[0];
             StoreRates1(p, r);
+            return;
+        }
+        case HBO_P_TRANSFORM_SNOW_ICE_CONSTANT: {  // ProcessTransformSnowToIceConstant.cpp:27-29
+            const float r = p.params[0];
+            StoreRates1(p, r);
+            return;
+        }
+        case HBO_P_TRANSFORM_SNOW_ICE_SWAT: {  // ProcessTransformSnowToIceSwat.cpp:31-39
+            const int doy = DayOfYear(m.startMjd + m.cursor * m.dt);
+            const bool northHemisphere = !(p.params[1] == 0);
+            const int daysRef = northHemisphere ? 81 : 264;
+            const double pi = 3.1415926535897932384626433832795;  // GlobVars.h:6
+            auto coeff = static_cast<float>(p.params[0] * (1 + std::sin(2.0f * pi * (doy - daysRef) / 365.0f)));
+            StoreRates1(p, coeff * ContentWithChanges(c));
             return;
         }
         default:
@@ -1185,6 +1219,8 @@ int hbo_run(hbo_model* m, double* outlet, double* records) {
     }
     return 0;
 }
+
+void hbo_set_start_mjd(hbo_model* m, double mjd) { m->startMjd = mjd; }
 
 const char* hbo_last_error(hbo_model* m) { return m->error.c_str(); }
 long hbo_unconverged_sweeps(hbo_model* m) { return m->unconverged; }

@@ -31,7 +31,9 @@ enum {
     HBO_P_OUTFLOW_DIRECT = 5,
     HBO_P_OUTFLOW_REST = 6,
     HBO_P_OVERFLOW = 7,
-    HBO_P_PERCOLATION_CONSTANT = 8 /* params: percolation_rate */
+    HBO_P_PERCOLATION_CONSTANT = 8, /* params: percolation_rate */
+    HBO_P_TRANSFORM_SNOW_ICE_CONSTANT = 9, /* params: snow_ice_transformation_rate; on the snowpack's snow container */
+    HBO_P_TRANSFORM_SNOW_ICE_SWAT = 10 /* params: snow_ice_transformation_basal_acc_coeff, north_hemisphere */
 };
 enum {
     HBO_F_TO_BRICK = 0, HBO_F_TO_BRICK_INSTANT = 1, HBO_F_TO_OUTLET = 2, HBO_F_TO_ATMOSPHERE = 3,
@@ -66,6 +68,9 @@ void hbo_add_outlet_flux(hbo_model* m, int flux);
 /* data[T][U], row-major */
 void hbo_set_forcing(hbo_model* m, int var, const double* data);
 int hbo_add_record(hbo_model* m, int kind, int id);
+/* Date of the first time step (modified Julian date), for the processes that read the day of the year
+ * (TimeMachine::GetCurrentDayOfYear, TimeMachine.cpp:87-98). Default 44605 = 1981-01-01. */
+void hbo_set_start_mjd(hbo_model* m, double mjd);
 
 /* Dated actions (ActionsManager::DateUpdate, ActionsManager.cpp:80-104), applied between time steps, before
  * step `step` (>= 1), in the order added for equal steps. Not applied during spin-up (ModelHydro.cpp:141-147). */

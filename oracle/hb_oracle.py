@@ -32,12 +32,18 @@ PROC_KIND = {
     "overflow": 7,
     "outflow:overflow": 7,
     "percolation:constant": 8,
+    "transform:snow_ice_constant": 9,  # aliases of Process.cpp:65-66
+    "transformation:snow_ice_constant": 9,
+    "transform:snow_ice_swat": 10,
+    "transformation:snow_ice_swat": 10,
 }
 PROC_PARAMS = {
     0: ["degree_day_factor", "melting_temperature"],
     3: ["beta"],
     4: ["response_factor"],
     8: ["percolation_rate"],
+    9: ["snow_ice_transformation_rate"],
+    10: ["snow_ice_transformation_basal_acc_coeff", "north_hemisphere"],
 }
 SPLITTER_KIND = {"snow_rain:linear": 0, "snow_rain_transition": 0, "multi_fluxes": 1, "rain": 2, "snow_rain:threshold": 3}
 FORCING = {"precipitation": 0, "p": 0, "temperature": 1, "t": 1, "pet": 2}  # TimeSeries.cpp:134-146
@@ -83,6 +89,7 @@ def lib():
         L.hbo_add_outlet_flux.argtypes = [c_vp, c_int]
         L.hbo_set_forcing.argtypes = [c_vp, c_int, dp]
         L.hbo_add_record.argtypes = [c_vp, c_int, c_int]
+        L.hbo_set_start_mjd.argtypes = [c_vp, c_dbl]
         ipt = ctypes.POINTER(ctypes.c_int)
         L.hbo_add_event.argtypes = [c_vp, c_int, c_int, c_int, c_dbl]
         L.hbo_add_snow_to_ice_unit.argtypes = [c_vp, c_int, c_int]
@@ -166,11 +173,12 @@ class OracleModel:
     """
 
     def __init__(self, structures, units, solver: str, n_steps: int, dt: float = 1.0, spinup_steps: int = 0,
-                 initial_states: dict | None = None):
+                 initial_states: dict | None = None, start_mjd: float = 44605.0):
         self.L = lib()
         self.n_units = len(units)
         self.n_steps = int(n_steps)
         self.h = self.L.hbo_create(self.n_units, self.n_steps, float(dt), SOLVERS[solver], int(spinup_steps))
+        self.L.hbo_set_start_mjd(self.h, float(start_mjd))  # 44605 = 1981-01-01
         self.labels = []  # (label, unit index or -1) per record
         self._rec = {}
         self.initial_states = initial_states or {}
@@ -233,6 +241,10 @@ class OracleModel:
             if ptype == 0:
                 if kind not in (2, 3):
                     raise ValueError("melt process on unsupported brick")
+                container = second
+            elif ptype in (9, 10):  # Process.cpp:325-346: the snowpack's snow container
+                if kind != 3:
+                    raise ValueError("transformation process on unsupported brick")
                 container = second
             else:
                 container = water

@@ -123,9 +123,30 @@ def kat_socont_quick(ref):
     return meta, forcing, q, rec
 
 
+def snow_ice_bundles(hb):
+    """continuous snow -> ice transformation on the glacier snowpack (transform:snow_ice_swat /
+    transform:snow_ice_constant, ProcessTransformSnowToIce{Swat,Constant}.cpp), finite glacier ice."""
+    cases = [("rk4", "swat", 2, {"snow_ice_basal_acc_coeff": 0.004}),
+             ("rk4", "constant", 1, {"snow_ice_rate": 0.8}),
+             ("heun_explicit", "swat", 1, {"snow_ice_basal_acc_coeff": 0.004}),
+             ("euler_explicit", "constant", 2, {"snow_ice_rate": 0.8})]
+    for solver, algo, nb, pr in cases:
+        m, hu, f, _ = ref_cases.gsm_socont(hb, solver=solver, end_date="1982-12-31", n_units=10, soil_storage_nb=nb,
+                                           infinite_storage=False, params=pr,
+                                           snow_ice_transformation="transform:snow_ice_" + algo)
+        structures, units, fdata, q, rec = ref_cases.collect(m, hu, f)
+        meta = {"structures": structures, "units": units, "solver": m.solver, "labels": list(rec),
+                "source": "reference Python layer, 10 synthetic bands with slope/glacier, Rhone-Gletsch meteo "
+                          "1981-1982, snow_ice_transformation=transform:snow_ice_" + algo}
+        save(f"gsm_socont_{solver}_snowice_{algo}_{nb}store", meta, fdata, q, rec)
+
+
 def main():
     hb = refpy.load_reference_python("ref")
     ref = sys.modules["hydrobricks._hydrobricks"]
+    if len(sys.argv) > 1 and sys.argv[1] == "snow_ice":
+        snow_ice_bundles(hb)
+        return
 
     for solver in ["euler_explicit", "heun_explicit", "runge_kutta"]:
         save(f"kat_linear_storage_{solver}", *kat_linear_storage(ref, solver))
@@ -189,6 +210,7 @@ def main():
         extra["spatial_first_" + k] = v[:, 0]
         extra["spatial_last_" + k] = v[:, -1]
     save("c1_sitter_rk4_full", meta, {}, q, {}, extra=extra)
+    snow_ice_bundles(hb)
 
 
 if __name__ == "__main__":
