@@ -37,6 +37,11 @@ _PROCESS_REGISTRY = {
     "overflow": ([], []),
     "outflow:overflow": ([], []),
     "percolation:constant": ([("percolation_rate", 0.1)], []),
+    # ProcessTransformSnowToIce{Constant,Swat}::RegisterProcessSettings; both spellings (Process.cpp:65-66)
+    "transform:snow_ice_constant": ([("snow_ice_transformation_rate", 0.5)], []),
+    "transformation:snow_ice_constant": ([("snow_ice_transformation_rate", 0.5)], []),
+    "transform:snow_ice_swat": ([("snow_ice_transformation_basal_acc_coeff", 0.0014), ("north_hemisphere", 1)], []),
+    "transformation:snow_ice_swat": ([("snow_ice_transformation_basal_acc_coeff", 0.0014), ("north_hemisphere", 1)], []),
 }
 
 _log_level = "message"
@@ -350,8 +355,14 @@ class SettingsModel:
     def add_snowpack_sublimation(self, *a, **k):
         self._unsupported("snowpack sublimation")
 
-    def add_snow_ice_transformation(self, *a, **k):
-        self._unsupported("snow to ice transformation process")
+    def add_snow_ice_transformation(self, transformation_process="transform:snow_ice_swat"):
+        """SettingsModel::AddSnowIceTransformation (SettingsModel.cpp:547-559): on the snowpack of every glacier
+        cover, a process that moves snow into the glacier's ice container."""
+        covers = [(b["name"], b["kind"]) for b in self._sel_structure["hydro_unit_bricks"] if b["is_land_cover"]]
+        for name, kind in covers:
+            self.select_hydro_unit_brick(name + "_snowpack")
+            if kind == "glacier":
+                self.add_brick_process("snow_ice_transfo", transformation_process, name + ":ice")
 
     def add_snow_redistribution(self, *a, **k):
         self._unsupported("snow redistribution")
@@ -521,7 +532,8 @@ class ModelHydro:
             self._settings = model_settings
             self._units = [dict(u) for u in basin_settings.units]
             self._cs, self._engine = _structure.build_engine(model_settings.get_structure(), self._units,
-                                                             model_settings.solver, self._n_steps, device, dt)
+                                                             model_settings.solver, self._n_steps, device, dt,
+                                                             start_mjd=self._mjd0)
             self._engine.set_spinup_steps(int(t["spinup_days"] / dt))
             self._labels = [l for l in model_settings.get_hydro_unit_log_labels()]
             self._device = device

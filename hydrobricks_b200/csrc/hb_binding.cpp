@@ -126,8 +126,8 @@ PYBIND11_MODULE(_hydrobricks, m) {
              [](hb::SettingsModel& s, py::args, py::kwargs) { s.Unsupported("canopy interception"); })
         .def("add_snowpack_refreezing", [](hb::SettingsModel& s, py::args, py::kwargs) { s.Unsupported("snowpack refreezing"); })
         .def("add_snowpack_sublimation", [](hb::SettingsModel& s, py::args, py::kwargs) { s.Unsupported("snowpack sublimation"); })
-        .def("add_snow_ice_transformation",
-             [](hb::SettingsModel& s, py::args, py::kwargs) { s.Unsupported("snow to ice transformation process"); })
+        .def("add_snow_ice_transformation", &hb::SettingsModel::AddSnowIceTransformation,
+             "transformation_process"_a = "transform:snow_ice_swat")
         .def("add_snow_redistribution", [](hb::SettingsModel& s, py::args, py::kwargs) { s.Unsupported("snow redistribution"); })
         .def("set_process_outputs_as_instantaneous", &hb::SettingsModel::SetProcessOutputsAsInstantaneous)
         .def("set_process_outputs_as_static", &hb::SettingsModel::SetProcessOutputsAsStatic)

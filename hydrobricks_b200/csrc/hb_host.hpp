@@ -93,6 +93,12 @@ inline const std::map<string, ProcessDefaults>& processRegistry() {
         {"overflow", {{}, {}}},
         {"outflow:overflow", {{}, {}}},
         {"percolation:constant", {{{"percolation_rate", 0.1f}}, {}}},
+        // ProcessTransformSnowToIce{Constant,Swat}::RegisterProcessSettings; both spellings (Process.cpp:65-66)
+        {"transform:snow_ice_constant", {{{"snow_ice_transformation_rate", 0.5f}}, {}}},
+        {"transformation:snow_ice_constant", {{{"snow_ice_transformation_rate", 0.5f}}, {}}},
+        {"transform:snow_ice_swat", {{{"snow_ice_transformation_basal_acc_coeff", 0.0014f}, {"north_hemisphere", 1.0f}}, {}}},
+        {"transformation:snow_ice_swat",
+         {{{"snow_ice_transformation_basal_acc_coeff", 0.0014f}, {"north_hemisphere", 1.0f}}, {}}},
     };
     return r;
 }
@@ -272,6 +278,16 @@ class SettingsModel {
             brick().isSurfaceComponent = true;
             brick().parent = cover;
             AddBrickProcess("melt", meltProcess, cover);
+        }
+    }
+    // SettingsModel::AddSnowIceTransformation (SettingsModel.cpp:547-559)
+    void AddSnowIceTransformation(const string& transformationProcess = "transform:snow_ice_swat") {
+        vector<std::pair<string, string>> covers;
+        for (auto& b : sel().hydroUnitBricks)
+            if (b.isLandCover) covers.push_back({b.name, b.kind});
+        for (auto& c : covers) {
+            SelectHydroUnitBrickByName(c.first + "_snowpack");
+            if (c.second == "glacier") AddBrickProcess("snow_ice_transfo", transformationProcess, c.first + ":ice");
         }
     }
     [[noreturn]] void Unsupported(const string& what) const {
@@ -512,7 +528,7 @@ inline const std::map<string, int>& recordSlots() {
         {"slow_percolation", HBK_R_SLOW_PERCOLATION}, {"slow2_water", HBK_R_SLOW2_WATER},
         {"slow2_outflow", HBK_R_SLOW2_OUTFLOW}, {"quick_water", HBK_R_QUICK_WATER},
         {"quick_runoff", HBK_R_QUICK_RUNOFF}, {"fraction_ground", HBK_R_FRACTION_GROUND},
-        {"fraction_glacier", HBK_R_FRACTION_GLACIER}};
+        {"fraction_glacier", HBK_R_FRACTION_GLACIER}, {"glacier_snowpack_transfo", HBK_R_GLACIER_SNOWPACK_TRANSFO}};
     return m;
 }
 
@@ -528,6 +544,11 @@ struct Compiled {
     std::map<int, std::set<string>> variantCovers;
     vector<std::pair<string, string>> brickKinds;  // (name, kind) over all variants, for "type:" components
 
+    static int snowIceKindOf(const string& kind) {
+        if (kind == "transform:snow_ice_constant" || kind == "transformation:snow_ice_constant") return HBK_SNOW_ICE_CONSTANT;
+        if (kind == "transform:snow_ice_swat" || kind == "transformation:snow_ice_swat") return HBK_SNOW_ICE_SWAT;
+        return HBK_SNOW_ICE_NONE;
+    }
     static float paramOf(const vector<Param>& v, const string& name, bool* found = nullptr) {
         for (auto& p : v) {
             if (p.name == name) {
@@ -553,7 +574,7 @@ struct Compiled {
     }
     void label(const string& l, const string& slot) { labels[l] = recordSlots().at(slot); }
 
-    Compiled(const SettingsModel& sm, double dtDays) {
+    Compiled(const SettingsModel& sm, double dtDays, double startMjd = 44605.0) {
         const string& solver = sm.solver;
         if (solver == "euler_explicit") {
             st.solver = HBK_SOLVER_EULER;
@@ -565,6 +586,9 @@ struct Compiled {
             throw Unsupported("solver '" + solver + "': only euler_explicit, heun_explicit and rk4/runge_kutta run on the device");
         }
         st.time_step_days = dtDays;
+        st.snow_ice_kind = HBK_SNOW_ICE_NONE;
+        st.north_hemisphere = 1;
+        st.start_mjd = startMjd;
         const auto& structures = sm.Structures();
         if (structures.empty()) throw Unsupported("empty structure");
         if (structures.size() > 2) throw Unsupported("more than two structure variants");
@@ -670,8 +694,18 @@ struct Compiled {
                     sp = &b;
                 }
             }
-            if (!sp || kinds(*sp) != vector<string>{"melt:degree_day"} || target(sp->processes[0]) != cover.name)
-                throw Unsupported("cover " + cover.name + ": expected one snowpack with melt:degree_day");
+            bool ok = sp && !sp->processes.empty() && target(sp->processes[0]) == cover.name;
+            if (ok && cover.kind == "glacier" && sp->processes.size() == 2 && snowIceKindOf(sp->processes[1].kind)) {
+                // SettingsModel::AddSnowIceTransformation: snow -> the glacier's ice container, a regular flux
+                const auto& out = sp->processes[1].outputs;
+                ok = sp->processes[0].kind == "melt:degree_day" && out.size() == 1 && out[0].target == cover.name &&
+                     out[0].fluxType == "ice" && !out[0].instantaneous && !out[0].isStatic;
+            } else if (ok) {
+                ok = kinds(*sp) == vector<string>{"melt:degree_day"};
+            }
+            if (!ok)
+                throw Unsupported("cover " + cover.name + ": expected one snowpack with melt:degree_day"
+                                  " [+ transform:snow_ice_constant|swat on a glacier]");
             return *sp;
         };
         const Brick& gsp = snowpackOf(*ground);
@@ -715,6 +749,24 @@ struct Compiled {
             label(glsp.name + ":snow_content", "glacier_snowpack_snow");
             label(glsp.name + ":" + glsp.processes[0].name + ":output", "glacier_snowpack_melt");
             snowpacks.push_back(glsp.name);
+            if (glsp.processes.size() == 2) {
+                const Process& tp = glsp.processes[1];
+                st.snow_ice_kind = snowIceKindOf(tp.kind);
+                bool has;
+                string pname;
+                if (st.snow_ice_kind == HBK_SNOW_ICE_CONSTANT) {
+                    paramOf(tp.parameters, "snow_ice_transformation_rate", &has);
+                    pname = has ? "snow_ice_transformation_rate" : "rate";
+                } else {
+                    paramOf(tp.parameters, "snow_ice_transformation_basal_acc_coeff", &has);
+                    pname = has ? "snow_ice_transformation_basal_acc_coeff" : "basal_acc_coeff";
+                    bool hasNh;
+                    const float nh = paramOf(tp.parameters, "north_hemisphere", &hasNh);
+                    st.north_hemisphere = (hasNh && nh == 0) ? 0 : 1;
+                }
+                set(HBK_P_SNOW_ICE, glsp.name, pname, paramOf(tp.parameters, pname));
+                label(glsp.name + ":" + tp.name + ":output", "glacier_snowpack_transfo");
+            }
             known.insert(glacier->name);
             known.insert(glsp.name);
             int slot[2] = {HBK_P_K_SNOW, HBK_P_K_ICE};
@@ -998,7 +1050,7 @@ class ModelHydro {
         _dt = (double)ms.timeStep;
         _nSteps = (int)(1 + (parseDateMjd(ms.timerEnd) - _mjd0) / _dt);  // TimeMachine.cpp:61-64
         try {
-            _c.reset(new Compiled(ms, _dt));
+            _c.reset(new Compiled(ms, _dt, _mjd0));
         } catch (const Unsupported& err) {
             throw std::invalid_argument(string("Model initialization failed: ") + err.what());
         }

@@ -36,11 +36,12 @@ ICEMELT_STORAGE = "glacier_area_icemelt_storage"
 class Socont:
     def __init__(self, solver="crank_nicolson", soil_storage_nb=1, surface_runoff="socont_runoff",
                  land_cover_names=None, land_cover_types=None, record_all=False, glacier_infinite_storage=True,
-                 snow_melt_process="melt:degree_day", backend=None):
+                 snow_melt_process="melt:degree_day", snow_ice_transformation=None, backend=None):
         self.backend = resolve_backend(backend)
         self.solver = solver
         self.options = {"soil_storage_nb": soil_storage_nb, "surface_runoff": surface_runoff,
-                        "snow_melt_process": snow_melt_process, "glacier_infinite_storage": glacier_infinite_storage}
+                        "snow_melt_process": snow_melt_process, "glacier_infinite_storage": glacier_infinite_storage,
+                        "snow_ice_transformation": snow_ice_transformation}
         self.land_cover_names = list(land_cover_names or ["open"])
         self.land_cover_types = list(land_cover_types or ["open"])
         self.record_all = record_all
@@ -110,6 +111,8 @@ class Socont:
                 s.add_land_cover_brick(n, "generic_land_cover" if t in ("ground", "generic_land_cover", "open",
                                                                         "forest", "lake") else t)
             s.generate_snowpacks(self.options["snow_melt_process"])
+            if self.options["snow_ice_transformation"]:  # model_settings.py:258-259
+                s.add_snow_ice_transformation(self.options["snow_ice_transformation"])
             for key, brick in structure.items():
                 if brick["kind"] == "land_cover":
                     s.select_hydro_unit_brick(key)
@@ -141,6 +144,12 @@ class Socont:
             a.update({"a_ice": (",".join(self._glacier_names), "degree_day_factor"),
                       "k_snow": (RAIN_SNOWMELT_STORAGE, "response_factor"),
                       "k_ice": (ICEMELT_STORAGE, "response_factor")})
+            snowpacks = ",".join(n + "_snowpack" for n in self._glacier_names)  # parameters.py:2021-2070
+            if self.options["snow_ice_transformation"] in ("transform:snow_ice_constant",
+                                                           "transformation:snow_ice_constant"):
+                a["snow_ice_rate"] = (snowpacks, "snow_ice_transformation_rate")
+            elif self.options["snow_ice_transformation"]:
+                a["snow_ice_basal_acc_coeff"] = (snowpacks, "snow_ice_transformation_basal_acc_coeff")
         self.aliases = a
         self.soil_cover = soil
 

@@ -30,6 +30,13 @@ CASES = {
                                                  glacier_infinite_storage=False),
     "gsm_socont_rk4_noglacier_1store": dict(soil_storage_nb=1, land_cover_names=["ground"],
                                             land_cover_types=["ground"]),
+    "gsm_socont_rk4_snowice_swat_2store": dict(soil_storage_nb=2, land_cover_names=["ground", "glacier"],
+                                               land_cover_types=["ground", "glacier"], glacier_infinite_storage=False,
+                                               snow_ice_transformation="transform:snow_ice_swat"),
+    "gsm_socont_rk4_snowice_constant_1store": dict(soil_storage_nb=1, land_cover_names=["ground", "glacier"],
+                                                   land_cover_types=["ground", "glacier"],
+                                                   glacier_infinite_storage=False,
+                                                   snow_ice_transformation="transform:snow_ice_constant"),
 }
 
 
