@@ -42,6 +42,9 @@ _PROCESS_REGISTRY = {
     "transformation:snow_ice_constant": ([("snow_ice_transformation_rate", 0.5)], []),
     "transform:snow_ice_swat": ([("snow_ice_transformation_basal_acc_coeff", 0.0014), ("north_hemisphere", 1)], []),
     "transformation:snow_ice_swat": ([("snow_ice_transformation_basal_acc_coeff", 0.0014), ("north_hemisphere", 1)], []),
+    # ProcessSublimation{Constant,PET}::RegisterProcessSettings
+    "sublimation:constant": ([("sublimation_rate", 0.1)], []),
+    "sublimation:pet": ([("sublimation_pet_factor", 0.2)], ["pet"]),
 }
 
 _log_level = "message"
@@ -352,8 +355,13 @@ class SettingsModel:
     def add_snowpack_refreezing(self, *a, **k):
         self._unsupported("snowpack refreezing")
 
-    def add_snowpack_sublimation(self, *a, **k):
-        self._unsupported("snowpack sublimation")
+    def add_snowpack_sublimation(self, sublimation_process):
+        """SettingsModel::AddSnowpackSublimation (SettingsModel.cpp:586-598): on every snowpack, from the snow
+        container to the atmosphere (no target)."""
+        covers = [b["name"] for b in self._sel_structure["hydro_unit_bricks"] if b["is_land_cover"]]
+        for name in covers:
+            self.select_hydro_unit_brick(name + "_snowpack")
+            self.add_brick_process("sublimation", sublimation_process)
 
     def add_snow_ice_transformation(self, transformation_process="transform:snow_ice_swat"):
         """SettingsModel::AddSnowIceTransformation (SettingsModel.cpp:547-559): on the snowpack of every glacier

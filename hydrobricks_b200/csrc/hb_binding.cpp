@@ -125,7 +125,7 @@ PYBIND11_MODULE(_hydrobricks, m) {
         .def("generate_canopy_interception",
              [](hb::SettingsModel& s, py::args, py::kwargs) { s.Unsupported("canopy interception"); })
         .def("add_snowpack_refreezing", [](hb::SettingsModel& s, py::args, py::kwargs) { s.Unsupported("snowpack refreezing"); })
-        .def("add_snowpack_sublimation", [](hb::SettingsModel& s, py::args, py::kwargs) { s.Unsupported("snowpack sublimation"); })
+        .def("add_snowpack_sublimation", &hb::SettingsModel::AddSnowpackSublimation, "sublimation_process"_a)
         .def("add_snow_ice_transformation", &hb::SettingsModel::AddSnowIceTransformation,
              "transformation_process"_a = "transform:snow_ice_swat")
         .def("add_snow_redistribution", [](hb::SettingsModel& s, py::args, py::kwargs) { s.Unsupported("snow redistribution"); })

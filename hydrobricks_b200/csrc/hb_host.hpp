@@ -99,6 +99,9 @@ inline const std::map<string, ProcessDefaults>& processRegistry() {
         {"transform:snow_ice_swat", {{{"snow_ice_transformation_basal_acc_coeff", 0.0014f}, {"north_hemisphere", 1.0f}}, {}}},
         {"transformation:snow_ice_swat",
          {{{"snow_ice_transformation_basal_acc_coeff", 0.0014f}, {"north_hemisphere", 1.0f}}, {}}},
+        // ProcessSublimation{Constant,PET}::RegisterProcessSettings
+        {"sublimation:constant", {{{"sublimation_rate", 0.1f}}, {}}},
+        {"sublimation:pet", {{{"sublimation_pet_factor", 0.2f}}, {"pet"}}},
     };
     return r;
 }
@@ -288,6 +291,16 @@ class SettingsModel {
         for (auto& c : covers) {
             SelectHydroUnitBrickByName(c.first + "_snowpack");
             if (c.second == "glacier") AddBrickProcess("snow_ice_transfo", transformationProcess, c.first + ":ice");
+        }
+    }
+    // SettingsModel::AddSnowpackSublimation (SettingsModel.cpp:586-598): no target = a flux to the atmosphere
+    void AddSnowpackSublimation(const string& sublimationProcess) {
+        vector<string> covers;
+        for (auto& b : sel().hydroUnitBricks)
+            if (b.isLandCover) covers.push_back(b.name);
+        for (auto& c : covers) {
+            SelectHydroUnitBrickByName(c + "_snowpack");
+            AddBrickProcess("sublimation", sublimationProcess);
         }
     }
     [[noreturn]] void Unsupported(const string& what) const {
@@ -528,7 +541,9 @@ inline const std::map<string, int>& recordSlots() {
         {"slow_percolation", HBK_R_SLOW_PERCOLATION}, {"slow2_water", HBK_R_SLOW2_WATER},
         {"slow2_outflow", HBK_R_SLOW2_OUTFLOW}, {"quick_water", HBK_R_QUICK_WATER},
         {"quick_runoff", HBK_R_QUICK_RUNOFF}, {"fraction_ground", HBK_R_FRACTION_GROUND},
-        {"fraction_glacier", HBK_R_FRACTION_GLACIER}, {"glacier_snowpack_transfo", HBK_R_GLACIER_SNOWPACK_TRANSFO}};
+        {"fraction_glacier", HBK_R_FRACTION_GLACIER}, {"glacier_snowpack_transfo", HBK_R_GLACIER_SNOWPACK_TRANSFO},
+        {"ground_snowpack_sublimation", HBK_R_GROUND_SNOWPACK_SUBLIMATION},
+        {"glacier_snowpack_sublimation", HBK_R_GLACIER_SNOWPACK_SUBLIMATION}};
     return m;
 }
 
@@ -544,6 +559,11 @@ struct Compiled {
     std::map<int, std::set<string>> variantCovers;
     vector<std::pair<string, string>> brickKinds;  // (name, kind) over all variants, for "type:" components
 
+    static int sublimationKindOf(const string& kind) {
+        if (kind == "sublimation:constant") return HBK_SUBLIMATION_CONSTANT;
+        if (kind == "sublimation:pet") return HBK_SUBLIMATION_PET;
+        return HBK_SUBLIMATION_NONE;
+    }
     static int snowIceKindOf(const string& kind) {
         if (kind == "transform:snow_ice_constant" || kind == "transformation:snow_ice_constant") return HBK_SNOW_ICE_CONSTANT;
         if (kind == "transform:snow_ice_swat" || kind == "transformation:snow_ice_swat") return HBK_SNOW_ICE_SWAT;
@@ -587,6 +607,7 @@ struct Compiled {
         }
         st.time_step_days = dtDays;
         st.snow_ice_kind = HBK_SNOW_ICE_NONE;
+        st.sublimation_kind = HBK_SUBLIMATION_NONE;
         st.north_hemisphere = 1;
         st.start_mjd = startMjd;
         const auto& structures = sm.Structures();
@@ -686,7 +707,14 @@ struct Compiled {
         label(ground->name + ":" + ground->processes[0].name + ":output", "ground_infiltration");
         label(ground->name + ":" + ground->processes[1].name + ":output", "ground_runoff");
 
-        auto snowpackOf = [&](const Brick& cover) -> const Brick& {
+        // One snowpack per cover: melt:degree_day [, snow -> ice transformation on a glacier] [, sublimation], in the
+        // order model_settings.py:255-263 adds them.
+        struct SnowpackInfo {
+            const Brick* brick;
+            const Process* transfo;
+            const Process* sublim;
+        };
+        auto snowpackOf = [&](const Brick& cover) -> SnowpackInfo {
             const Brick* sp = nullptr;
             for (auto& b : full.hydroUnitBricks) {
                 if (b.kind == "snowpack" && b.parent == cover.name) {
@@ -694,21 +722,41 @@ struct Compiled {
                     sp = &b;
                 }
             }
-            bool ok = sp && !sp->processes.empty() && target(sp->processes[0]) == cover.name;
-            if (ok && cover.kind == "glacier" && sp->processes.size() == 2 && snowIceKindOf(sp->processes[1].kind)) {
-                // SettingsModel::AddSnowIceTransformation: snow -> the glacier's ice container, a regular flux
-                const auto& out = sp->processes[1].outputs;
-                ok = sp->processes[0].kind == "melt:degree_day" && out.size() == 1 && out[0].target == cover.name &&
-                     out[0].fluxType == "ice" && !out[0].instantaneous && !out[0].isStatic;
-            } else if (ok) {
-                ok = kinds(*sp) == vector<string>{"melt:degree_day"};
+            SnowpackInfo info{sp, nullptr, nullptr};
+            bool ok = sp && !sp->processes.empty() && sp->processes[0].kind == "melt:degree_day" &&
+                      target(sp->processes[0]) == cover.name;
+            if (ok) {
+                size_t i = 1;
+                if (i < sp->processes.size() && cover.kind == "glacier" && snowIceKindOf(sp->processes[i].kind)) {
+                    // SettingsModel::AddSnowIceTransformation: snow -> the glacier's ice container, a regular flux
+                    info.transfo = &sp->processes[i++];
+                    const auto& out = info.transfo->outputs;
+                    ok = out.size() == 1 && out[0].target == cover.name && out[0].fluxType == "ice" &&
+                         !out[0].instantaneous && !out[0].isStatic;
+                }
+                if (ok && i < sp->processes.size() && sublimationKindOf(sp->processes[i].kind)) {
+                    info.sublim = &sp->processes[i++];
+                    ok = info.sublim->outputs.empty();
+                }
+                ok = ok && i == sp->processes.size();
             }
             if (!ok)
                 throw Unsupported("cover " + cover.name + ": expected one snowpack with melt:degree_day"
-                                  " [+ transform:snow_ice_constant|swat on a glacier]");
-            return *sp;
+                                  " [+ transform:snow_ice_constant|swat on a glacier] [+ sublimation:constant|pet]");
+            return info;
         };
-        const Brick& gsp = snowpackOf(*ground);
+        auto setSublimation = [&](const Brick& sp, const Process& proc, int slot, const char* record) {
+            const int kind = sublimationKindOf(proc.kind);
+            if (st.sublimation_kind != HBK_SUBLIMATION_NONE && st.sublimation_kind != kind)
+                throw Unsupported("different sublimation processes on the snowpacks");
+            st.sublimation_kind = kind;
+            const string pname = kind == HBK_SUBLIMATION_CONSTANT ? "sublimation_rate" : "sublimation_pet_factor";
+            set(slot, sp.name, pname, paramOf(proc.parameters, pname));
+            label(sp.name + ":" + proc.name + ":output", record);
+        };
+        const SnowpackInfo gInfo = snowpackOf(*ground);
+        const Brick& gsp = *gInfo.brick;
+        if (gInfo.sublim) setSublimation(gsp, *gInfo.sublim, HBK_P_GROUND_SUBLIMATION, "ground_snowpack_sublimation");
         set(HBK_P_GROUND_SNOW_DDF, gsp.name, "degree_day_factor", paramOf(gsp.processes[0].parameters, "degree_day_factor"));
         set(HBK_P_GROUND_SNOW_TMELT, gsp.name, "melting_temperature",
             paramOf(gsp.processes[0].parameters, "melting_temperature"));
@@ -735,7 +783,12 @@ struct Compiled {
             set(HBK_P_ICE_DDF, glacier->name, "degree_day_factor", paramOf(glacier->processes[1].parameters, "degree_day_factor"));
             set(HBK_P_ICE_TMELT, glacier->name, "melting_temperature",
                 paramOf(glacier->processes[1].parameters, "melting_temperature"));
-            const Brick& glsp = snowpackOf(*glacier);
+            const SnowpackInfo glInfo = snowpackOf(*glacier);
+            const Brick& glsp = *glInfo.brick;
+            if ((glInfo.sublim == nullptr) != (gInfo.sublim == nullptr))
+                throw Unsupported("sublimation must be on every snowpack or on none");
+            if (glInfo.sublim)
+                setSublimation(glsp, *glInfo.sublim, HBK_P_GLACIER_SUBLIMATION, "glacier_snowpack_sublimation");
             set(HBK_P_GLACIER_SNOW_DDF, glsp.name, "degree_day_factor",
                 paramOf(glsp.processes[0].parameters, "degree_day_factor"));
             set(HBK_P_GLACIER_SNOW_TMELT, glsp.name, "melting_temperature",
@@ -749,8 +802,8 @@ struct Compiled {
             label(glsp.name + ":snow_content", "glacier_snowpack_snow");
             label(glsp.name + ":" + glsp.processes[0].name + ":output", "glacier_snowpack_melt");
             snowpacks.push_back(glsp.name);
-            if (glsp.processes.size() == 2) {
-                const Process& tp = glsp.processes[1];
+            if (glInfo.transfo) {
+                const Process& tp = *glInfo.transfo;
                 st.snow_ice_kind = snowIceKindOf(tp.kind);
                 bool has;
                 string pname;

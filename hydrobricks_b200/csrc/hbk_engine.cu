@@ -366,8 +366,14 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
                         precip = (precip < 0.0) ? 0.0 : precip;
                         pet = (xe < 0.0) ? 0.0 : xe;
                     }
+                    double sublimG = 0.0, sublimGl = 0.0;
+                    if (a.flags.sublimKind != 0) {  // rate = parameter, or PET x parameter (float32 promoted)
+                        const double scale = (a.flags.sublimKind == HBK_SUBLIMATION_PET) ? pet : 1.0;
+                        sublimG = scale * (double)a.params[p + (size_t)HBK_P_GROUND_SUBLIMATION * a.ldp];
+                        if (GLACIER) sublimGl = scale * (double)a.params[p + (size_t)HBK_P_GLACIER_SUBLIMATION * a.ldp];
+                    }
                     directPhase<GLACIER>(h, par, precip, temp, dt, invDt, fa, fG, fGl, glacierVariant, a.flags, o, err,
-                                         (GLACIER && a.swatFactor) ? a.swatFactor[t0 + tc] : 0.0);
+                                         (GLACIER && a.swatFactor) ? a.swatFactor[t0 + tc] : 0.0, sublimG, sublimGl);
                     solveUnit<SOLVER, NSOIL>(h, par, pet, fa, dt, invDt, a.flags, o, err, unconverged);
 
                     if (nRec && a.writeOutputs) {
@@ -407,6 +413,8 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
                         HBK_REC(HBK_R_FRACTION_GROUND, fG)
                         HBK_REC(HBK_R_FRACTION_GLACIER, gv ? fGl : nan)
                         HBK_REC(HBK_R_GLACIER_SNOWPACK_TRANSFO, gv ? h.amtSnowIce : nan)
+                        HBK_REC(HBK_R_GROUND_SNOWPACK_SUBLIMATION, o.amtSubG)
+                        HBK_REC(HBK_R_GLACIER_SNOWPACK_SUBLIMATION, gv ? o.amtSubGl : nan)
 #undef HBK_REC
                     }
                 }
@@ -1146,6 +1154,8 @@ int hbk_engine_create(const hbk_structure* st, int32_t n_units, int32_t n_steps,
     cudaMemset(e->dInitUnit, 0, sizeof(double) * HBK_N_STATES * n_units);
     if (st->snow_ice_kind < HBK_SNOW_ICE_NONE || st->snow_ice_kind > HBK_SNOW_ICE_SWAT)
         return bail(HBK_E_ARG, "unknown snow_ice_kind");
+    if (st->sublimation_kind < HBK_SUBLIMATION_NONE || st->sublimation_kind > HBK_SUBLIMATION_PET)
+        return bail(HBK_E_ARG, "unknown sublimation_kind");
     if (st->has_glacier && st->snow_ice_kind == HBK_SNOW_ICE_SWAT) {
         // ProcessTransformSnowToIceSwat.cpp:31-39: 1 + sin(2 pi (doy - ref) / 365) per time step, in double like
         // the reference's expression (2.0f * constants::pi promotes to double), doy as TimeMachine.cpp:87-98
@@ -1523,6 +1533,7 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
     a.flags.splitKind = e->st.splitter_kind;
     a.flags.iceInfinite = e->st.glacier_infinite_storage;
     a.flags.snowIceKind = e->st.has_glacier ? e->st.snow_ice_kind : 0;
+    a.flags.sublimKind = e->st.sublimation_kind;
     a.swatFactor = (a.flags.snowIceKind == HBK_SNOW_ICE_SWAT) ? e->dSwatFactor : nullptr;
     a.flags.noMeltWhenSnow = e->st.glacier_no_melt_when_snow_cover;
     a.dt = e->st.time_step_days;

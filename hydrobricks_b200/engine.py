@@ -20,11 +20,13 @@ SOLVER = {"euler_explicit": 0, "heun_explicit": 1, "rk4": 2, "runge_kutta": 2}
 QUICK_SOCONT, QUICK_LINEAR = 0, 1
 SPLIT_LINEAR, SPLIT_THRESHOLD = 0, 1
 SNOW_ICE_NONE, SNOW_ICE_CONSTANT, SNOW_ICE_SWAT = 0, 1, 2
+SUBLIMATION_NONE, SUBLIMATION_CONSTANT, SUBLIMATION_PET = 0, 1, 2
 VAR = {"precipitation": 0, "p": 0, "temperature": 1, "t": 1, "pet": 2}
 PARAM_SLOTS = [
     "transition_start", "transition_end", "rain_correction", "snow_correction", "ground_snow_ddf",
     "ground_snow_tmelt", "glacier_snow_ddf", "glacier_snow_tmelt", "ice_ddf", "ice_tmelt", "capacity", "k_slow_1",
     "percolation", "k_slow_2", "quick", "k_snow", "k_ice", "snow_ice",
+    "ground_sublimation", "glacier_sublimation",
 ]
 N_PARAMS = len(PARAM_SLOTS)
 RECORD_SLOTS = [
@@ -33,6 +35,7 @@ RECORD_SLOTS = [
     "glacier_snowpack_water", "glacier_snowpack_snow", "glacier_snowpack_melt", "slow_water", "slow_et",
     "slow_outflow", "slow_overflow", "slow_percolation", "slow2_water", "slow2_outflow", "quick_water",
     "quick_runoff", "fraction_ground", "fraction_glacier", "glacier_snowpack_transfo",
+    "ground_snowpack_sublimation", "glacier_snowpack_sublimation",
 ]
 STATE_SLOTS = [
     "ground_snow", "glacier_snow", "ground_water", "glacier_water", "ice", "slow", "slow2", "quick",
@@ -55,6 +58,8 @@ class HbkStructure(ctypes.Structure):
         ("snow_ice_kind", ctypes.c_int32),
         ("north_hemisphere", ctypes.c_int32),
         ("start_mjd", ctypes.c_double),
+        ("sublimation_kind", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
     ]
 
 

@@ -36,12 +36,14 @@ ICEMELT_STORAGE = "glacier_area_icemelt_storage"
 class Socont:
     def __init__(self, solver="crank_nicolson", soil_storage_nb=1, surface_runoff="socont_runoff",
                  land_cover_names=None, land_cover_types=None, record_all=False, glacier_infinite_storage=True,
-                 snow_melt_process="melt:degree_day", snow_ice_transformation=None, backend=None):
+                 snow_melt_process="melt:degree_day", snow_ice_transformation=None, snow_sublimation_process=None,
+                 backend=None):
         self.backend = resolve_backend(backend)
         self.solver = solver
         self.options = {"soil_storage_nb": soil_storage_nb, "surface_runoff": surface_runoff,
                         "snow_melt_process": snow_melt_process, "glacier_infinite_storage": glacier_infinite_storage,
-                        "snow_ice_transformation": snow_ice_transformation}
+                        "snow_ice_transformation": snow_ice_transformation,
+                        "snow_sublimation_process": snow_sublimation_process}
         self.land_cover_names = list(land_cover_names or ["open"])
         self.land_cover_types = list(land_cover_types or ["open"])
         self.record_all = record_all
@@ -113,6 +115,8 @@ class Socont:
             s.generate_snowpacks(self.options["snow_melt_process"])
             if self.options["snow_ice_transformation"]:  # model_settings.py:258-259
                 s.add_snow_ice_transformation(self.options["snow_ice_transformation"])
+            if self.options["snow_sublimation_process"]:  # model_settings.py:262-263
+                s.add_snowpack_sublimation(self.options["snow_sublimation_process"])
             for key, brick in structure.items():
                 if brick["kind"] == "land_cover":
                     s.select_hydro_unit_brick(key)
@@ -140,6 +144,11 @@ class Socont:
              "melt_t_snow": ("type:snowpack", "melting_temperature"),
              "prec_t_start": ("snow_rain_transition", "transition_start"),
              "prec_t_end": ("snow_rain_transition", "transition_end")}
+        if self.options["snow_sublimation_process"] == "sublimation:constant":  # parameters.py:286-305, 2006-2018
+            a["sublimation_rate"] = ("type:snowpack", "sublimation_rate")
+        elif self.options["snow_sublimation_process"] == "sublimation:pet":
+            a["sublimation_pet_factor"] = ("type:snowpack", "sublimation_pet_factor")
+            a["sublimation_factor"] = ("type:snowpack", "sublimation_pet_factor")
         if self._glacier_names:
             a.update({"a_ice": (",".join(self._glacier_names), "degree_day_factor"),
                       "k_snow": (RAIN_SNOWMELT_STORAGE, "response_factor"),

@@ -89,6 +89,7 @@ class CompiledStructure:
         st.solver = _e.SOLVER[self.solver]
         st.time_step_days = float(dt)
         st.snow_ice_kind = _e.SNOW_ICE_NONE
+        st.sublimation_kind = _e.SUBLIMATION_NONE
         st.north_hemisphere = 1
         st.start_mjd = self.start_mjd
 
@@ -150,23 +151,45 @@ class CompiledStructure:
                          "transformation:snow_ice_constant": _e.SNOW_ICE_CONSTANT,
                          "transform:snow_ice_swat": _e.SNOW_ICE_SWAT, "transformation:snow_ice_swat": _e.SNOW_ICE_SWAT}
 
+        sublim_kinds = {"sublimation:constant": _e.SUBLIMATION_CONSTANT, "sublimation:pet": _e.SUBLIMATION_PET}
+
         def snowpack_of(cover):
+            """One snowpack per cover: melt:degree_day [, snow -> ice transformation on a glacier] [, sublimation], in
+            the order model_settings.py:255-263 adds them. Returns (brick, transformation process, sublimation process)."""
             sps = [b for b in full["hydro_unit_bricks"] if b["kind"] == "snowpack" and b.get("parent") == cover["name"]]
-            ok = len(sps) == 1 and _target(sps[0]["processes"][0]) == cover["name"]
-            kinds = _proc_kinds(sps[0]) if ok else []
-            if ok and cover["kind"] == "glacier" and len(kinds) == 2 and kinds[1] in transfo_kinds:
-                # SettingsModel::AddSnowIceTransformation (SettingsModel.cpp:547-559): snow -> the glacier's ice
-                out = sps[0]["processes"][1]["outputs"]
-                ok = kinds[0] == "melt:degree_day" and len(out) == 1 and out[0]["target"] == cover["name"] and \
-                    out[0]["flux_type"] == "ice" and not out[0]["instantaneous"] and not out[0]["static"]
-            elif ok:
-                ok = kinds == ["melt:degree_day"]
+            ok = len(sps) == 1 and sps[0]["processes"] and sps[0]["processes"][0]["kind"] == "melt:degree_day" and \
+                _target(sps[0]["processes"][0]) == cover["name"]
+            transfo = sublim = None
+            if ok:
+                rest = list(sps[0]["processes"][1:])
+                if rest and rest[0]["kind"] in transfo_kinds and cover["kind"] == "glacier":
+                    # SettingsModel::AddSnowIceTransformation (SettingsModel.cpp:547-559): snow -> the glacier's ice
+                    transfo = rest.pop(0)
+                    out = transfo["outputs"]
+                    ok = len(out) == 1 and out[0]["target"] == cover["name"] and out[0]["flux_type"] == "ice" and \
+                        not out[0]["instantaneous"] and not out[0]["static"]
+                if ok and rest and rest[0]["kind"] in sublim_kinds:
+                    # SettingsModel::AddSnowpackSublimation (SettingsModel.cpp:586-598): no target = to the atmosphere
+                    sublim = rest.pop(0)
+                    ok = not sublim["outputs"]
+                ok = ok and not rest
             if not ok:
                 raise UnsupportedStructure(f"cover {cover['name']}: expected one snowpack with melt:degree_day"
-                                           " [+ transform:snow_ice_constant|swat on a glacier]")
-            return sps[0]
+                                           " [+ transform:snow_ice_constant|swat on a glacier] [+ sublimation:constant|pet]")
+            return sps[0], transfo, sublim
 
-        gsp = snowpack_of(ground)
+        def set_sublimation(sp, proc, slot, record):
+            kind = sublim_kinds[proc["kind"]]
+            if st.sublimation_kind not in (_e.SUBLIMATION_NONE, kind):
+                raise UnsupportedStructure("different sublimation processes on the snowpacks")
+            st.sublimation_kind = kind
+            pname = "sublimation_rate" if kind == _e.SUBLIMATION_CONSTANT else "sublimation_pet_factor"
+            self._set(slot, sp["name"], pname, _params(proc)[pname])
+            self.labels[f"{sp['name']}:{proc['name']}:output"] = record
+
+        gsp, _, gsub = snowpack_of(ground)
+        if gsub is not None:
+            set_sublimation(gsp, gsub, "ground_sublimation", "ground_snowpack_sublimation")
         pp = _params(gsp["processes"][0])
         self._set("ground_snow_ddf", gsp["name"], "degree_day_factor", pp["degree_day_factor"])
         self._set("ground_snow_tmelt", gsp["name"], "melting_temperature", pp["melting_temperature"])
@@ -192,7 +215,11 @@ class CompiledStructure:
             mp = _params(glacier["processes"][1])
             self._set("ice_ddf", glacier["name"], "degree_day_factor", mp["degree_day_factor"])
             self._set("ice_tmelt", glacier["name"], "melting_temperature", mp["melting_temperature"])
-            glsp = snowpack_of(glacier)
+            glsp, gltr, glsub = snowpack_of(glacier)
+            if (glsub is None) != (gsub is None):
+                raise UnsupportedStructure("sublimation must be on every snowpack or on none")
+            if glsub is not None:
+                set_sublimation(glsp, glsub, "glacier_sublimation", "glacier_snowpack_sublimation")
             pp = _params(glsp["processes"][0])
             self._set("glacier_snow_ddf", glsp["name"], "degree_day_factor", pp["degree_day_factor"])
             self._set("glacier_snow_tmelt", glsp["name"], "melting_temperature", pp["melting_temperature"])
@@ -204,8 +231,8 @@ class CompiledStructure:
                                 f"{glsp['name']}:snow_content": "glacier_snowpack_snow",
                                 f"{glsp['name']}:{glsp['processes'][0]['name']}:output": "glacier_snowpack_melt"})
             snowpacks.append(glsp["name"])
-            if len(glsp["processes"]) == 2:
-                tp = glsp["processes"][1]
+            if gltr is not None:
+                tp = gltr
                 st.snow_ice_kind = transfo_kinds[tp["kind"]]
                 tv = _params(tp)
                 if st.snow_ice_kind == _e.SNOW_ICE_CONSTANT:

@@ -38,6 +38,8 @@ enum { HBK_SLOW_ORDER_ET_OUT_OVF_PERC = 0 /* models/socont.py:171-190 */,
 enum { HBK_VAR_PRECIPITATION = 0, HBK_VAR_TEMPERATURE = 1, HBK_VAR_PET = 2 };
 /* glacier snowpack process after the melt: none | transform:snow_ice_constant | transform:snow_ice_swat */
 enum { HBK_SNOW_ICE_NONE = 0, HBK_SNOW_ICE_CONSTANT = 1, HBK_SNOW_ICE_SWAT = 2 };
+/* snowpack -> atmosphere: none | sublimation:constant | sublimation:pet (ProcessSublimation{Constant,PET}.cpp) */
+enum { HBK_SUBLIMATION_NONE = 0, HBK_SUBLIMATION_CONSTANT = 1, HBK_SUBLIMATION_PET = 2 };
 
 /* The per-structure process table for the Socont family, as the structure compiler
  * (hydrobricks_b200/csrc/hb_host.cpp) derives it from a SettingsModel. */
@@ -57,6 +59,10 @@ typedef struct {
     int32_t snow_ice_kind;
     int32_t north_hemisphere;
     double start_mjd;                 /* modified Julian date of time step 0 (TimeMachine) */
+    /* snow sublimation, last process of every snowpack (SettingsModel::AddSnowpackSublimation,
+     * SettingsModel.cpp:586-598): HBK_SUBLIMATION_* */
+    int32_t sublimation_kind;
+    int32_t reserved;
 } hbk_structure;
 
 /* Parameter slots of one parameter set: float32 like the reference (Parameter.h:121). */
@@ -79,6 +85,8 @@ enum {
     HBK_P_K_SNOW,     /* glacier_area_rain_snowmelt_storage:response_factor */
     HBK_P_K_ICE,      /* glacier_area_icemelt_storage:response_factor */
     HBK_P_SNOW_ICE,   /* glacier_snowpack:snow_ice_transformation_rate or :snow_ice_transformation_basal_acc_coeff */
+    HBK_P_GROUND_SUBLIMATION,  /* <cover>_snowpack:sublimation_rate or :sublimation_pet_factor */
+    HBK_P_GLACIER_SUBLIMATION,
     HBK_N_PARAMS
 };
 
@@ -93,6 +101,8 @@ enum {
     HBK_R_QUICK_WATER, HBK_R_QUICK_RUNOFF,
     HBK_R_FRACTION_GROUND, HBK_R_FRACTION_GLACIER, /* land-cover fraction series (Logger::RecordFractions) */
     HBK_R_GLACIER_SNOWPACK_TRANSFO,                /* glacier_snowpack:snow_ice_transfo:output */
+    HBK_R_GROUND_SNOWPACK_SUBLIMATION, HBK_R_GLACIER_SNOWPACK_SUBLIMATION, /* <cover>_snowpack:sublimation:output;
+                                                      0 while the cover is null (the reference keeps the last amount) */
     HBK_N_RECORDS
 };
 

@@ -481,6 +481,22 @@ void GetRates(hbo_model& m, Process& p) {
             StoreRates1(p, coeff * ContentWithChanges(c));
             return;
         }
+        case HBO_P_SUBLIMATION_CONSTANT: {  // ProcessSublimationConstant.cpp:31-36
+            if (!ContentAccessible(m, c)) {
+                StoreRates1(p, 0);
+                return;
+            }
+            StoreRates1(p, static_cast<double>(p.params[0]));
+            return;
+        }
+        case HBO_P_SUBLIMATION_PET: {  // ProcessSublimationPET.cpp:46-51
+            if (!ContentAccessible(m, c)) {
+                StoreRates1(p, 0);
+                return;
+            }
+            StoreRates1(p, m.Forcing(HBO_V_PET, unit) * p.params[0]);
+            return;
+        }
         default:
             throw Fail{"unknown process type"};
     }

@@ -33,7 +33,9 @@ enum {
     HBO_P_OVERFLOW = 7,
     HBO_P_PERCOLATION_CONSTANT = 8, /* params: percolation_rate */
     HBO_P_TRANSFORM_SNOW_ICE_CONSTANT = 9, /* params: snow_ice_transformation_rate; on the snowpack's snow container */
-    HBO_P_TRANSFORM_SNOW_ICE_SWAT = 10 /* params: snow_ice_transformation_basal_acc_coeff, north_hemisphere */
+    HBO_P_TRANSFORM_SNOW_ICE_SWAT = 10, /* params: snow_ice_transformation_basal_acc_coeff, north_hemisphere */
+    HBO_P_SUBLIMATION_CONSTANT = 11,    /* params: sublimation_rate; snow container -> atmosphere */
+    HBO_P_SUBLIMATION_PET = 12          /* params: sublimation_pet_factor; forcing pet */
 };
 enum {
     HBO_F_TO_BRICK = 0, HBO_F_TO_BRICK_INSTANT = 1, HBO_F_TO_OUTLET = 2, HBO_F_TO_ATMOSPHERE = 3,

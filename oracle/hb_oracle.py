@@ -36,6 +36,8 @@ PROC_KIND = {
     "transformation:snow_ice_constant": 9,
     "transform:snow_ice_swat": 10,
     "transformation:snow_ice_swat": 10,
+    "sublimation:constant": 11,
+    "sublimation:pet": 12,
 }
 PROC_PARAMS = {
     0: ["degree_day_factor", "melting_temperature"],
@@ -44,6 +46,8 @@ PROC_PARAMS = {
     8: ["percolation_rate"],
     9: ["snow_ice_transformation_rate"],
     10: ["snow_ice_transformation_basal_acc_coeff", "north_hemisphere"],
+    11: ["sublimation_rate"],
+    12: ["sublimation_pet_factor"],
 }
 SPLITTER_KIND = {"snow_rain:linear": 0, "snow_rain_transition": 0, "multi_fluxes": 1, "rain": 2, "snow_rain:threshold": 3}
 FORCING = {"precipitation": 0, "p": 0, "temperature": 1, "t": 1, "pet": 2}  # TimeSeries.cpp:134-146
@@ -242,9 +246,9 @@ class OracleModel:
                 if kind not in (2, 3):
                     raise ValueError("melt process on unsupported brick")
                 container = second
-            elif ptype in (9, 10):  # Process.cpp:325-346: the snowpack's snow container
+            elif ptype in (9, 10, 11, 12):  # Process.cpp:301-346: the snowpack's snow container
                 if kind != 3:
-                    raise ValueError("transformation process on unsupported brick")
+                    raise ValueError("transformation / sublimation process on unsupported brick")
                 container = second
             else:
                 container = water
@@ -369,7 +373,7 @@ class OracleModel:
                 if proc["type"] == 2:
                     target, _ = self._find_brick(ps["outputs"][0]["target"], unit)
                     L.hbo_set_target_brick(h, proc["id"], target["id"])
-                if proc["type"] == 1:  # ToAtmosphere
+                if proc["type"] in (1, 11, 12):  # ToAtmosphere (ET, sublimation)
                     fl = L.hbo_add_flux(h, F_TO_ATMOSPHERE, 0, 0, 1.0, -1, -1, unit)
                     L.hbo_process_add_output(h, proc["id"], fl)
                     self._flux_of[(bs["name"], ps["name"], unit)] = fl

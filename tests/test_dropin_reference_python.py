@@ -41,6 +41,10 @@ def _structure(backend, **kw):
          glacier_infinite_storage=False, record_all=True, snow_ice_transformation="transform:snow_ice_swat"),
     dict(solver="rk4", soil_storage_nb=2, land_cover_names=["ground", "glacier"], land_cover_types=["ground", "glacier"],
          record_all=False, snow_ice_transformation="transform:snow_ice_constant"),
+    dict(solver="rk4", soil_storage_nb=1, record_all=True, snow_sublimation_process="sublimation:constant"),
+    dict(solver="heun_explicit", soil_storage_nb=2, land_cover_names=["ground", "glacier"],
+         land_cover_types=["ground", "glacier"], record_all=True, snow_ice_transformation="transform:snow_ice_swat",
+         snow_sublimation_process="sublimation:pet"),
 ])
 @pytest.mark.parametrize("backend", ["b200", "b200-native"])
 def test_reference_socont_builds_same_structure_on_both_backends(kw, backend):

@@ -37,6 +37,14 @@ CASES = {
                                                    land_cover_types=["ground", "glacier"],
                                                    glacier_infinite_storage=False,
                                                    snow_ice_transformation="transform:snow_ice_constant"),
+    "gsm_socont_rk4_sublim_constant_noglacier_1store": dict(soil_storage_nb=1, land_cover_names=["ground"],
+                                                            land_cover_types=["ground"],
+                                                            snow_sublimation_process="sublimation:constant"),
+    "gsm_socont_rk4_sublim_pet_glacier_snowice_2store": dict(soil_storage_nb=2, land_cover_names=["ground", "glacier"],
+                                                             land_cover_types=["ground", "glacier"],
+                                                             glacier_infinite_storage=False,
+                                                             snow_ice_transformation="transform:snow_ice_swat",
+                                                             snow_sublimation_process="sublimation:pet"),
 }
 
 

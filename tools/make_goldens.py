@@ -139,6 +139,21 @@ def snow_ice_bundles(hb):
                 "source": "reference Python layer, 10 synthetic bands with slope/glacier, Rhone-Gletsch meteo "
                           "1981-1982, snow_ice_transformation=transform:snow_ice_" + algo}
         save(f"gsm_socont_{solver}_snowice_{algo}_{nb}store", meta, fdata, q, rec)
+    # snow sublimation (sublimation:constant / sublimation:pet, ProcessSublimation{Constant,PET}.cpp) on every snowpack
+    cases = [("rk4", "constant", 1, dict(with_glacier=False), {"sublimation_rate": 0.6}),
+             ("rk4", "pet", 2, dict(infinite_storage=False, snow_ice_transformation="transform:snow_ice_swat"),
+              {"sublimation_pet_factor": 0.5, "snow_ice_basal_acc_coeff": 0.004}),
+             ("heun_explicit", "constant", 1, dict(infinite_storage=False), {"sublimation_rate": 0.6}),
+             ("euler_explicit", "pet", 2, dict(with_glacier=False), {"sublimation_pet_factor": 0.5})]
+    for solver, algo, nb, kw, pr in cases:
+        m, hu, f, _ = ref_cases.gsm_socont(hb, solver=solver, end_date="1982-12-31", n_units=10, soil_storage_nb=nb,
+                                           params=pr, snow_sublimation_process="sublimation:" + algo, **kw)
+        structures, units, fdata, q, rec = ref_cases.collect(m, hu, f)
+        meta = {"structures": structures, "units": units, "solver": m.solver, "labels": list(rec),
+                "source": "reference Python layer, 10 synthetic bands, Rhone-Gletsch meteo 1981-1982, "
+                          "snow_sublimation_process=sublimation:" + algo + " " + json.dumps(kw)}
+        tag = ("glacier" if kw.get("with_glacier", True) else "noglacier") + ("_snowice" if "snow_ice_transformation" in kw else "")
+        save(f"gsm_socont_{solver}_sublim_{algo}_{tag}_{nb}store", meta, fdata, q, rec)
 
 
 def main():

@@ -88,7 +88,7 @@ def synthetic_units_csv(path, n_units=12, seed=3, with_glacier=True, area=1.0e6)
 
 def gsm_socont(hb, solver="rk4", soil_storage_nb=1, surface_runoff="socont_runoff", with_glacier=True,
                end_date="1990-12-31", n_units=12, params=None, infinite_storage=True, record_all=True,
-               spinup_days=0, snow_ice_transformation=None):
+               spinup_days=0, snow_ice_transformation=None, snow_sublimation_process=None):
     import hydrobricks.models as models
 
     tmp = tempfile.mkdtemp()
@@ -102,6 +102,8 @@ def gsm_socont(hb, solver="rk4", soil_storage_nb=1, surface_runoff="socont_runof
         kw["glacier_infinite_storage"] = infinite_storage
     if snow_ice_transformation:
         kw["snow_ice_transformation"] = snow_ice_transformation
+    if snow_sublimation_process:
+        kw["snow_sublimation_process"] = snow_sublimation_process
     socont = models.Socont(**kw)
     parameters = socont.generate_parameters()
     values = {"a_snow": 4.5, "k_quick": 0.3, "A": 120, "k_slow_1": 0.02, "beta": 800}
