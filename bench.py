@@ -345,7 +345,7 @@ def run_engine_arm(args):
     pin_out = torch.empty((P, T), dtype=torch.float64).pin_memory()
     out_ptr = ctypes.cast(pin_out.data_ptr(), ctypes.POINTER(ctypes.c_double))
 
-    def upload():
+    def upload(eng=eng):
         eng.set_parameters(pin_params.numpy())
         eng.set_station_forcing("precipitation", pin_forcing[0].numpy(), SPATIAL["zref"], SPATIAL["grad_p"], 1.0)
         eng.set_station_forcing("temperature", pin_forcing[1].numpy(), SPATIAL["zref"], SPATIAL["grad_t"], 1.0)
@@ -446,6 +446,49 @@ def run_engine_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_scores_value = units_done / t.item()
 
+    # ---- pipelined variant: the outlet of run i travels to the host while run i+1 computes (two engines taking
+    # turns, one fetch thread per engine; every step still uploads its inputs and fetches its full outlet) ----
+    e2e_pipe_value = None
+    if args.pipeline:
+        m2 = models.Socont(solver=args.solver, soil_storage_nb=wl["soil"], surface_runoff="socont_runoff",
+                           land_cover_names=covers, land_cover_types=covers)
+        m2.setup(units, START, end, device=local)
+        engines = [eng, m2.engine(P)]
+        pending = [None, None]
+
+        def fetch(e):
+            e._check(e.L.hbk_get_outlet(e.h, 0, P, out_ptr))
+
+        def pipe_step(i):
+            k = i % 2
+            if pending[k] is not None:
+                pending[k].join()
+            upload(engines[k])
+            engines[k].run()
+            pending[k] = threading.Thread(target=fetch, args=(engines[k],))
+            pending[k].start()
+
+        def drain():
+            for k in range(2):
+                if pending[k] is not None:
+                    pending[k].join()
+                    pending[k] = None
+
+        pipe_step(0)
+        pipe_step(1)
+        drain()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            pipe_step(i)
+        drain()
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_pipe_value = units_done / t.item()
+        del engines, m2
+
     if rank == 0:
         main_ms = kern_ms / args.steps  # device time of one hbk_run (state reset + unit kernel), CUDA events
         flops_unit = FP64_FLOPS_PER_HRU_STEP[args.solver]
@@ -483,7 +526,10 @@ def run_engine_arm(args):
                     "outlet[P x T] -> pinned host, through the C-ABI",
                     "scores_only": {"value": e2e_scores_value, "d2h_bytes_per_step": int(P * 8 ),
                                     "note": "same, but the device computes NSE per set (hbk_compute_scores) and only "
-                                            "the scores come back: the calibration loop's step"}},
+                                            "the scores come back: the calibration loop's step"},
+                    "pipelined": {"value": e2e_pipe_value,
+                                  "note": "same bytes per step as e2e.value, but two engines take turns so that the "
+                                          "outlet of run i is copied to the host while run i+1 computes"}},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_fp64, "unit": "TFLOP/s",
@@ -511,6 +557,7 @@ def run_engine_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--pipeline", action="store_true", help="also time the pipelined end-to-end leg (second engine; measured: +0.6 %, so off by default)")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
