@@ -290,7 +290,7 @@ def run_engine_arm(args):
     import torch.distributed as dist
 
     from hydrobricks_b200 import engine as hbk_engine
-    from hydrobricks_b200 import models
+    from hydrobricks_b200 import models, parallel
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -320,15 +320,19 @@ def run_engine_arm(args):
 
     P, U, T = args.sets, args.units, args.timesteps
     wl = WORKLOADS[args.workload]
-    units = hydro_units(U, area=wl["area"], glacier=wl["glacier"])
+    # C3 on several GPUs: ONE basin of world x U hydro units, every rank holds a block of U units;
+    # per step one all-reduce of the partial outlet and of the two deposit series, then the sub-basin stores
+    unit_sharded = args.workload == "c3" and world > 1
+    units = hydro_units(U, seed=43 + (rank if unit_sharded else 0), area=wl["area"], glacier=wl["glacier"])
     precip, temp, pet = station_series(T)
-    ps = parameter_sets(P, seed=44 + rank)  # every rank its own shard of the ensemble (weak scaling)
+    set_seed = 0 if unit_sharded else rank  # unit shards integrate the SAME parameter sets
+    ps = parameter_sets(P, seed=44 + set_seed)  # every rank its own shard of the ensemble (weak scaling)
     if wl["glacier"]:
-        rng = np.random.Generator(np.random.MT19937(91 + rank))
+        rng = np.random.Generator(np.random.MT19937(91 + set_seed))
         ps.update({"a_ice": ps["a_snow"] + rng.uniform(0.5, 6, P), "k_snow": rng.uniform(0.05, 0.6, P),
                    "k_ice": rng.uniform(0.05, 0.6, P)})
     if wl["soil"] == 2:
-        rng = np.random.Generator(np.random.MT19937(92 + rank))
+        rng = np.random.Generator(np.random.MT19937(92 + set_seed))
         ps.update({"percol": rng.uniform(0, 10, P), "k_slow_2": ps["k_slow_1"] * rng.uniform(0.05, 0.9, P)})
 
     covers = ["ground", "glacier"] if wl["glacier"] else ["ground"]
@@ -338,6 +342,15 @@ def run_engine_arm(args):
     m.setup(units, START, end, device=local)
     matrix = m.parameter_matrix(ps, P)
     eng = m.engine(P)
+    if unit_sharded:
+        eng.set_unit_shard(parallel.basin_area(np.full(world * U, wl["area"])))
+
+    def run_engine(e):
+        e.run()
+        if unit_sharded:
+            parallel.reduce_partials(parallel.shard_partials(e))
+            torch.cuda.current_stream().synchronize()
+            e.finish_sharded_run()
 
     # pinned host staging: the step's inputs and its result
     pin_params = torch.from_numpy(matrix).pin_memory()
@@ -364,7 +377,7 @@ def run_engine_arm(args):
 
     def scores():
         eng.compute_scores("nse", pin_obs.numpy(), score_warmup, to_host=False)
-        if world > 1:  # the only collective of the job: final gather of the per-set scores
+        if world > 1 and not unit_sharded:  # the only collective of the job: final gather of the per-set scores
             s = torch.as_tensor(DeviceArray(eng.scores_device_pointer(), (P,), (8,)), device="cuda")
             dist.all_gather_into_tensor(scores_all, s)
 
@@ -374,12 +387,12 @@ def run_engine_arm(args):
         torch.cuda.synchronize()
 
     def resident_step():
-        eng.run()
+        run_engine(eng)
         scores()
 
     def e2e_step():
         upload()
-        eng.run()
+        run_engine(eng)
         eng._check(eng.L.hbk_get_outlet(eng.h, 0, P, out_ptr))
 
     peak_fp64 = hbk_engine.measure_fp64_peak(local)
@@ -432,7 +445,7 @@ def run_engine_arm(args):
     # ---- the calibration loop's variant: only the per-set objective scores come back ----
     def e2e_scores_step():
         upload()
-        eng.run()
+        run_engine(eng)
         eng.compute_scores("nse", pin_obs.numpy(), score_warmup, out=pin_scores.numpy())
 
     e2e_scores_step()
@@ -513,6 +526,10 @@ def run_engine_arm(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "evals_per_s": world * P * args.steps / (dev_ms * 1e-3),
             "config": {"workload": wl["name"], "sets_per_gpu": P, "hydro_units": U,
+                       "multi_gpu": ("one basin of %d units, a block of %d per GPU; per step one all-reduce of the "
+                                     "partial outlet and the two sub-basin deposit series [T], then the sub-basin "
+                                     "stores" % (world * U, U)) if unit_sharded else
+                                    "parameter axis sharded, no collective on the path, one all_gather of scores",
                        "timesteps": T, "solver": args.solver,
                        "structure": f"socont {wl['soil']} soil store(s), runoff:socont" + (", glacier (GSM)" if wl["glacier"] else ""),
                        "forcing": "station series + fused elevation-gradient spatialisation",

@@ -934,6 +934,10 @@ struct hbk_engine {
     long long lastUnconverged = 0;
     std::vector<double> hFracG, hFracGl;
     std::vector<int> hGlacierVariant;
+    // unit sharding (hbk_set_unit_shard): this engine holds a block of the basin's units; hbk_run stops after the
+    // unit pass and hbk_finish_sharded_run integrates the sub-basin stores on the reduced deposit sums
+    bool shard = false, shardPending = false;
+    double shardBasinArea = 0;
 };
 
 namespace {
@@ -1232,6 +1236,7 @@ int hbk_set_units(hbk_engine* e, const double* area, const double* elevation, co
     const int U = e->U;
     double basinArea = 0;  // SubBasin::AddHydroUnit (SubBasin.cpp:173): running sum in unit order
     for (int u = 0; u < U; ++u) basinArea += area[u];
+    if (e->shard) basinArea = e->shardBasinArea;  // a block of a larger basin (hbk_set_unit_shard)
     std::vector<double> hru((size_t)kNH * e->ldu, 0.0);
     std::vector<int> flags(e->ldu, 0);
     e->hArea.assign(area, area + U);
@@ -1619,7 +1624,7 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
         hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD2, e->dD2, e->nGroups, e->P, e->ldt, tBegin, tEnd, nullptr);
         e->lastLaunches += 2;
     }
-    if (e->st.has_glacier) {
+    if (e->st.has_glacier && !e->shard) {
         const int blocks = (e->P + 127) / 128;
         const double dt = e->st.time_step_days;
         const double* stale = nullptr;
@@ -1671,6 +1676,9 @@ int hbk_run(hbk_engine* e) {
     if (!tiled && !station)
         return fail(e, HBK_E_STATE, "forcing incomplete: precipitation, temperature and pet are all required, "
                                     "either all per unit or all as station series");
+    if (e->shard && (e->spinupSteps > 0 || !e->events.empty()))
+        return fail(e, HBK_E_UNSUPPORTED, "a unit shard runs neither spin-up nor dated actions (the sub-basin stores "
+                                          "and the delta-h reduction span all shards)");
     HBK_CUDA(cudaSetDevice(e->device));
     chooseShape(e);
     e->lastLaunches = 0;
@@ -1778,6 +1786,7 @@ int hbk_run(hbk_engine* e) {
     HBK_CUDA(cudaMemcpy(&unc, e->dUnconv, sizeof(unc), cudaMemcpyDeviceToHost));
     e->lastUnconverged = (long long)unc;
     e->ran = true;
+    e->shardPending = e->shard;
     if (err & kErrRateTooHigh)  // WaterContainer.cpp:83-86 throws; ModelHydro::Run fails
         return fail(e, HBK_E_MODEL, "a change rate exceeded 10000 (WaterContainer::ApplyConstraints)");
     if (err & kErrActionFraction)
@@ -1785,6 +1794,78 @@ int hbk_run(hbk_engine* e) {
                                     "generic land cover cannot absorb the area change");
     if (err & kErrActionInfiniteIce)
         return fail(e, HBK_E_MODEL, "Trying to set the content of an infinite storage (snow-to-ice on infinite glacier ice)");
+    return HBK_OK;
+}
+
+int hbk_set_unit_shard(hbk_engine* e, double basin_area_m2) {
+    if (!e) return HBK_E_ARG;
+    if (!e->unitsSet) return fail(e, HBK_E_STATE, "hbk_set_units has not been called");
+    HBK_CUDA(cudaSetDevice(e->device));
+    e->shard = basin_area_m2 > 0;
+    double basinArea = basin_area_m2;
+    if (!e->shard) {
+        basinArea = 0;
+        for (double a : e->hArea) basinArea += a;
+    }
+    e->shardBasinArea = basinArea;
+    e->shardPending = false;
+    std::vector<double> w(e->U);
+    for (int u = 0; u < e->U; ++u) w[u] = e->hArea[u] / basinArea;  // ModelBuilder.cpp:468, whole-basin area
+    HBK_CUDA(cudaMemcpy(e->dHru, w.data(), sizeof(double) * e->U, cudaMemcpyHostToDevice));
+    return HBK_OK;
+}
+
+int hbk_shard_partials_dev(hbk_engine* e, double** outlet, double** deposits_rain_snowmelt, double** deposits_icemelt,
+                           int64_t* n_rows, int64_t* ld) {
+    if (!e) return HBK_E_ARG;
+    if (!e->shard) return fail(e, HBK_E_STATE, "not a unit shard (hbk_set_unit_shard)");
+    if (!e->ran) return fail(e, HBK_E_STATE, "no completed run");
+    if (outlet) *outlet = e->dOutlet;
+    if (deposits_rain_snowmelt) *deposits_rain_snowmelt = e->st.has_glacier ? e->dD1 : nullptr;
+    if (deposits_icemelt) *deposits_icemelt = e->st.has_glacier ? e->dD2 : nullptr;
+    if (n_rows) *n_rows = e->P;
+    if (ld) *ld = e->ldt;
+    return HBK_OK;
+}
+
+int hbk_finish_sharded_run(hbk_engine* e) {
+    if (!e) return HBK_E_ARG;
+    if (!e->shard) return fail(e, HBK_E_STATE, "not a unit shard (hbk_set_unit_shard)");
+    if (!e->ran || !e->shardPending) return fail(e, HBK_E_STATE, "hbk_run has not been called since the last finish");
+    HBK_CUDA(cudaSetDevice(e->device));
+    e->shardPending = false;
+    if (!e->st.has_glacier) return HBK_OK;  // no sub-basin stores: the reduced unit sums are the outlet
+    const int blocks = (e->P + 127) / 128;
+    const double dt = e->st.time_step_days;
+    HBK_CUDA(cudaEventRecord(e->ev0, e->stream));
+    switch (e->st.solver) {
+        case HBK_SOLVER_EULER:
+            hbkBasinStores<0><<<blocks, 128, 0, e->stream>>>(e->dParams, e->ldp, e->P, e->ldt, 0, e->T, dt, e->dD1, e->dD2,
+                                                           nullptr, e->dOutlet, e->dBasinState, 1, e->dErr, e->dUnconv,
+                                                           e->dPerm);
+            break;
+        case HBK_SOLVER_HEUN:
+            hbkBasinStores<1><<<blocks, 128, 0, e->stream>>>(e->dParams, e->ldp, e->P, e->ldt, 0, e->T, dt, e->dD1, e->dD2,
+                                                           nullptr, e->dOutlet, e->dBasinState, 1, e->dErr, e->dUnconv,
+                                                           e->dPerm);
+            break;
+        default:
+            hbkBasinStores<2><<<blocks, 128, 0, e->stream>>>(e->dParams, e->ldp, e->P, e->ldt, 0, e->T, dt, e->dD1, e->dD2,
+                                                           nullptr, e->dOutlet, e->dBasinState, 1, e->dErr, e->dUnconv,
+                                                           e->dPerm);
+            break;
+    }
+    e->lastLaunches++;
+    HBK_CUDA(cudaGetLastError());
+    HBK_CUDA(cudaEventRecord(e->ev1, e->stream));
+    HBK_CUDA(cudaStreamSynchronize(e->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    e->lastMs += ms;
+    int err = 0;
+    HBK_CUDA(cudaMemcpy(&err, e->dErr, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err & kErrRateTooHigh)
+        return fail(e, HBK_E_MODEL, "a change rate exceeded 10000 (WaterContainer::ApplyConstraints)");
     return HBK_OK;
 }
 

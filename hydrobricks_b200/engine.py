@@ -113,6 +113,10 @@ def load_library():
     L.hbk_measure_fp64_peak.argtypes = [i32, dp]
     L.hbk_compute_scores.argtypes = [vp, i32, dp, i32, dp]
     L.hbk_scores_dev.argtypes = [vp, ctypes.POINTER(ctypes.c_void_p)]
+    L.hbk_set_unit_shard.argtypes = [vp, dbl]
+    L.hbk_shard_partials_dev.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                         ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    L.hbk_finish_sharded_run.argtypes = [vp]
     _lib = L
     return L
 
@@ -290,6 +294,21 @@ class Engine:
         ptr = ctypes.c_void_p()
         self._check(self.L.hbk_scores_dev(self.h, ctypes.byref(ptr)))
         return ptr.value
+
+    # unit sharding (large basins split across GPUs): see include/hbk.h
+    def set_unit_shard(self, basin_area_m2):
+        self._check(self.L.hbk_set_unit_shard(self.h, float(basin_area_m2)))
+
+    def shard_partials_device_pointers(self):
+        """(outlet_ptr, deposits_rain_snowmelt_ptr | None, deposits_icemelt_ptr | None, n_rows, ld) of the last run."""
+        q, d1, d2 = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        n, ld = ctypes.c_int64(), ctypes.c_int64()
+        self._check(self.L.hbk_shard_partials_dev(self.h, ctypes.byref(q), ctypes.byref(d1), ctypes.byref(d2),
+                                                  ctypes.byref(n), ctypes.byref(ld)))
+        return q.value, d1.value, d2.value, n.value, ld.value
+
+    def finish_sharded_run(self):
+        self._check(self.L.hbk_finish_sharded_run(self.h))
 
     def outlet_device_pointer(self):
         ptr, ld = ctypes.c_void_p(), ctypes.c_int64()

@@ -1,6 +1,12 @@
-"""Multi-GPU plumbing (one process per GPU, torch.distributed): parameter sets are independent, so the
-parameter axis is sharded across ranks with NO collective on the hot path; the only exchange is
-the final gather of per-set results (scores [P] or outlet series [P x T]) over NCCL (gloo on CPU in the tests).
+"""Multi-GPU plumbing (one process per GPU, torch.distributed), SURVEY.md §8e.
+
+* Ensembles: parameter sets are independent, so the parameter axis is sharded across ranks with NO collective on the
+  hot path; the only exchange is the final gather of per-set results (scores [P] or outlet series [P x T]).
+* Large distributed basins: blocks of hydro units are sharded across ranks (`ShardedBasin`); every rank integrates its
+  block, then ONE all-reduce(sum) of the area-weighted partial outlet [P x T] and of the two per-step deposit sums into
+  the sub-basin stores, after which the two linear sub-basin stores are integrated on the summed deposits (exactly — no
+  superposition across shards, the 1e-8 thresholds of the reference are not linear).
+NCCL on GPUs, gloo on CPU in the tests.
 """
 from __future__ import annotations
 
@@ -73,3 +79,71 @@ def device_outlet(engine):
 
     ptr, ld = engine.outlet_device_pointer()
     return torch.as_tensor(_DeviceArray(ptr, (engine.n_sets, engine.n_steps), (ld * 8, 8)), device="cuda")
+
+
+def basin_area(areas) -> float:
+    """Area of the whole basin as SubBasin::AddHydroUnit accumulates it (SubBasin.cpp:173): a running float64 sum
+    in unit order — NOT numpy's pairwise sum, the outlet weights area/basinArea must be those of the full model."""
+    a = np.asarray(areas, dtype=np.float64)
+    return float(np.cumsum(a)[-1]) if a.size else 0.0  # cumsum is the plain running sum (np.sum is pairwise)
+
+
+def reduce_partials(partials, group=None):
+    """In-place sum over the ranks of the partial series (torch tensors), one collective per tensor."""
+    import torch.distributed as dist
+
+    for t in partials:
+        if t is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return partials
+
+
+def shard_partials(engine):
+    """Zero-copy torch views [n_sets x ld] of a unit shard's partial outlet and deposit sums in HBM."""
+    import torch
+
+    q, d1, d2, n, ld = engine.shard_partials_device_pointers()
+    view = lambda ptr: None if not ptr else torch.as_tensor(  # noqa: E731
+        _DeviceArray(ptr, (n, ld), (ld * 8, 8)), device="cuda")
+    return [view(q), view(d1), view(d2)]
+
+
+class ShardedBasin:
+    """One large basin split into contiguous blocks of hydro units, one block per rank.
+
+    `make_model(units_block)` builds and sets up a hydrobricks_b200.models.Socont for a block of units on this rank's
+    device (same structure, time axis and forcing on every rank); `units` is the full list in basin order
+    (descending elevation, as HydroUnits sorts them). run() integrates the block and returns nothing; afterwards
+    get_outlet_discharge() gives the outlet of the WHOLE basin on every rank.
+    """
+
+    def __init__(self, make_model, units, group=None):
+        import torch.distributed as dist
+
+        self.group = group
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        units = sorted(units, key=lambda u: -u["elevation"])
+        lo, hi = shard_bounds(len(units), rank, world)
+        self.bounds = (lo, hi)
+        self.total_area = basin_area([u["area"] for u in units])
+        self.model = make_model(units[lo:hi])
+        self._engine = None
+
+    def engine(self, n_sets=1):
+        if self._engine is None:
+            self._engine = self.model.engine(n_sets)
+            self._engine.set_unit_shard(self.total_area)
+        self._engine.n_sets = n_sets
+        return self._engine
+
+    def run(self, n_sets=1):
+        eng = self.engine(n_sets)
+        import torch
+
+        eng.run()  # returns after the engine's stream has drained
+        reduce_partials(shard_partials(eng), self.group)
+        torch.cuda.current_stream().synchronize()  # the collective runs on torch's stream, the engine on its own
+        eng.finish_sharded_run()
+
+    def get_outlet_discharge(self):
+        return self._engine.get_outlet()

@@ -173,6 +173,23 @@ int hbk_add_delta_h_update(hbk_engine* e, int32_t step);
 /* ModelHydro::Reset + Run (ModelHydro.cpp:100-133, 183-193) for all parameter sets. */
 int hbk_run(hbk_engine* e);
 
+/* Unit sharding (large distributed basins): this engine holds a BLOCK of the basin's hydro units,
+ * the other blocks live in other engines (other GPUs). basin_area_m2 = area of the whole basin summed in unit order
+ * as SubBasin::AddHydroUnit does (SubBasin.cpp:173), so that the outlet weights area/basinArea (ModelBuilder.cpp:468)
+ * are those of the full model; <= 0 turns sharding off. Call after hbk_set_units. In shard mode hbk_run stops after
+ * the unit pass: hbk_shard_partials_dev then gives the device buffers [n_rows][ld] float64 holding this block's
+ * area-weighted outlet contribution and its per-step deposits into the two sub-basin stores
+ * (glacier_area_rain_snowmelt_storage, glacier_area_icemelt_storage; NULL without glacier) — the caller sums them
+ * IN PLACE over all shards (one ncclAllReduce each; rows: outlet in the caller's set order, deposits in the engine's
+ * internal set order, identical on all shards given identical parameter sets) and calls hbk_finish_sharded_run,
+ * which integrates the two sub-basin stores on the summed deposits (SubBasin bricks, modules/glacier.py:108-131)
+ * and adds their outflow: hbk_get_outlet then returns the outlet of the whole basin on every shard.
+ * Spin-up and dated actions are refused in shard mode (HBK_E_UNSUPPORTED). */
+int hbk_set_unit_shard(hbk_engine* e, double basin_area_m2);
+int hbk_shard_partials_dev(hbk_engine* e, double** outlet, double** deposits_rain_snowmelt, double** deposits_icemelt,
+                           int64_t* n_rows, int64_t* ld);
+int hbk_finish_sharded_run(hbk_engine* e);
+
 /* ModelHydro::GetOutletDischarge (ModelHydro.cpp:203-205): out[n_sets][n_steps]. */
 int hbk_get_outlet(hbk_engine* e, int32_t first_set, int32_t n_sets, double* out);
 /* ModelHydro::GetHydroUnitValues(label) (ModelHydro.cpp:227-236) for one set: out[n_steps][n_units];

@@ -66,3 +66,38 @@ def test_batched_nse_kge_against_numpy_formulas():
                          (s.mean() / o.mean() - 1) ** 2)
         assert abs(n1[i] - n0) < 1e-12 and abs(k1[i] - k0) < 1e-12
     assert abs(n1[0] - 1.0) < 1e-12  # identical series: NSE = 1 (python/tests/test_models.py:731-738)
+
+
+def _reduce_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # unit-sharded basin: every rank holds the partial outlet and deposit sums of its block of
+    # units; one all-reduce(sum) per series; a series that does not exist (no glacier) is None on every rank
+    U, T = 11, 6
+    lo, hi = parallel.shard_bounds(U, rank, world)
+    contrib = torch.arange(U * T, dtype=torch.float64).reshape(U, T)
+    partial = [contrib[lo:hi].sum(dim=0, keepdim=True), None, 2.0 * contrib[lo:hi].sum(dim=0, keepdim=True)]
+    parallel.reduce_partials(partial)
+    ok = torch.equal(partial[0], contrib.sum(dim=0, keepdim=True)) and partial[1] is None and \
+        torch.equal(partial[2], 2.0 * contrib.sum(dim=0, keepdim=True))
+    out[rank] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_reduce_partials_gloo_world2():
+    world = 2
+    port = 31500 + os.getpid() % 2000
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_reduce_worker, args=(world, port, out), nprocs=world, join=True)
+        assert all(out[r] for r in range(world))
+
+
+def test_basin_area_is_the_running_sum_in_unit_order():
+    rng = np.random.default_rng(3)
+    areas = rng.uniform(1e3, 1e7, 5000)
+    total = 0.0
+    for a in areas:
+        total += float(a)
+    assert parallel.basin_area(areas) == total
