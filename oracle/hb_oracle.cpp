@@ -750,6 +750,175 @@ void SolveRK4(hbo_model& m, double dt) {
     FinalizeTimeStep(m);
 }
 
+// ---- sequential solvers (base/SolverSequential.cpp and its four ComputeBrickRates implementations) ----
+
+// SolverSequential.cpp:22-32
+double TotalRateAt(hbo_model& m, Brick& b, double* contentDelta, double offset) {
+    *contentDelta = offset;
+    double total = 0;
+    for (int ip : b.processes) {
+        const std::vector<double>& processRates = GetChangeRates(m, m.processes[ip]);
+        for (double v : processRates) total += v;
+    }
+    return total;
+}
+
+// SolverSequential.cpp:34-40
+void StoreRatesAtCurrentContent(hbo_model& m, Brick& b, std::vector<double>& rates) {
+    rates.clear();
+    for (int ip : b.processes) {
+        const std::vector<double>& processRates = GetChangeRates(m, m.processes[ip]);
+        rates.insert(rates.end(), processRates.begin(), processRates.end());
+    }
+}
+
+// SolverCrankNicolson.cpp:12-63 (crank) / SolverImplicitEuler.cpp:12-61: end-of-step content by bisection.
+void ComputeBrickRatesBisection(hbo_model& m, Brick& b, double content, double inflow, double h, int iRateStart,
+                                bool crank) {
+    Container& c = m.containers[b.water];
+    double* contentDelta = &c.dyn;
+    std::vector<double> startRates, endRates;
+    double startTotal = 0;
+    if (crank) {
+        startTotal = TotalRateAt(m, b, contentDelta, 0);
+        StoreRatesAtCurrentContent(m, b, startRates);
+    }
+    double hi = content + h * std::max(inflow, 0.0);
+    double maxOutflow = TotalRateAt(m, b, contentDelta, hi - content);
+    double lo = crank ? content + h * (inflow - (startTotal + maxOutflow) / 2) : content + h * (inflow - maxOutflow);
+    lo = std::max(lo, 0.0);  // AllowsNegativeContent() is false for every container of this family
+    double endContent = hi;
+    if (hi > lo) {
+        for (int iter = 0; iter < 100; ++iter) {
+            endContent = (lo + hi) / 2;
+            double endTotal = TotalRateAt(m, b, contentDelta, endContent - content);
+            double g = crank ? endContent - content - h * (inflow - (startTotal + endTotal) / 2)
+                             : endContent - content - h * (inflow - endTotal);
+            if (g > 0) {
+                hi = endContent;
+            } else {
+                lo = endContent;
+            }
+            if (hi - lo < 1e-12) break;
+        }
+        endContent = (lo + hi) / 2;
+    } else {
+        endContent = lo;
+    }
+    TotalRateAt(m, b, contentDelta, endContent - content);
+    StoreRatesAtCurrentContent(m, b, endRates);
+    for (size_t i = 0; i < endRates.size(); ++i) {
+        m.k1[iRateStart + i] = crank ? (startRates[i] + endRates[i]) / 2 : endRates[i];
+    }
+    *contentDelta = 0;
+}
+
+// SolverExponentialEuler.cpp:11-63
+void ComputeBrickRatesExponential(hbo_model& m, Brick& b, double content, double inflow, double h, int iRateStart) {
+    Container& c = m.containers[b.water];
+    double* contentDelta = &c.dyn;
+    std::vector<double> startRates, endRates;
+    double startTotal = TotalRateAt(m, b, contentDelta, 0);
+    StoreRatesAtCurrentContent(m, b, startRates);
+    double scale = std::max(content, content + h * inflow);
+    double eps = std::max(0.001, 0.001 * scale);
+    double slope = (TotalRateAt(m, b, contentDelta, eps) - startTotal) / eps;
+    if (slope <= 1e-10) {
+        for (size_t i = 0; i < startRates.size(); ++i) m.k1[iRateStart + i] = startRates[i];
+        *contentDelta = 0;
+        return;
+    }
+    double netInflow = inflow - startTotal;
+    double endContent = content + netInflow / slope * (1.0 - std::exp(-slope * h));
+    endContent = std::max(endContent, 0.0);
+    double totalRate = std::max(inflow - (endContent - content) / h, 0.0);
+    TotalRateAt(m, b, contentDelta, endContent - content);
+    StoreRatesAtCurrentContent(m, b, endRates);
+    double sumWeights = 0;
+    for (size_t i = 0; i < startRates.size(); ++i) sumWeights += startRates[i] + endRates[i];
+    for (size_t i = 0; i < startRates.size(); ++i) {
+        double weight = sumWeights > 0 ? (startRates[i] + endRates[i]) / sumWeights : 0.0;
+        m.k1[iRateStart + i] = totalRate * weight;
+    }
+    *contentDelta = 0;
+}
+
+// SolverAnalyticLinear.cpp:11-59; HasLinearResponse / GetLinearResponseRate: ProcessOutflowLinear.h:36-46
+void ComputeBrickRatesAnalytic(hbo_model& m, Brick& b, double content, double inflow, double h, int iRateStart) {
+    int iRate = iRateStart;
+    double totalLinearCoefficient = 0;
+    double totalFrozenRate = 0;
+    for (int ip : b.processes) {
+        Process& p = m.processes[ip];
+        if (p.type == HBO_P_OUTFLOW_LINEAR && p.outputs.size() == 1) {
+            totalLinearCoefficient += p.params[0];
+            m.k1[iRate] = 0;
+            iRate++;
+        } else {
+            const std::vector<double>& processRates = GetChangeRates(m, p);
+            for (double v : processRates) {
+                m.k1[iRate] = v;
+                totalFrozenRate += v;
+                iRate++;
+            }
+        }
+    }
+    if (totalLinearCoefficient <= 0) return;
+    double netInflow = inflow - totalFrozenRate;
+    double decay = std::exp(-totalLinearCoefficient * h);
+    double newContent = content * decay + netInflow / totalLinearCoefficient * (1.0 - decay);
+    double linearOutflowRate = (netInflow * h - (newContent - content)) / h;
+    linearOutflowRate = std::max(linearOutflowRate, 0.0);
+    int iRateFill = iRateStart;
+    for (int ip : b.processes) {
+        Process& p = m.processes[ip];
+        if (p.type == HBO_P_OUTFLOW_LINEAR && p.outputs.size() == 1) {
+            m.k1[iRateFill] = linearOutflowRate * p.params[0] / totalLinearCoefficient;
+            iRateFill++;
+        } else {
+            iRateFill += static_cast<int>(p.outputs.size());
+        }
+    }
+}
+
+// SolverSequential.cpp:42-88
+void SolveSequential(hbo_model& m, double dt) {
+    int iRate = 0;
+    for (int ib : m.iterableBricks) {
+        Brick& b = m.bricks[ib];
+        int iRateStart = iRate;
+        for (int ip : b.processes) {
+            Process& p = m.processes[ip];
+            for (size_t j = 0; j < p.outputs.size(); ++j) {
+                m.k1[iRate] = 0;
+                StoreInOutgoingFlux(m, p, &m.k1[iRate], static_cast<int>(j));
+                iRate++;
+            }
+        }
+        if (IsNull(m, b)) continue;
+        Container& c = m.containers[b.water];
+        double content = ContentWithChanges(c);
+        double inflow = SumIncomingFluxes(m, c) / dt;
+        switch (m.solver) {
+            case HBO_SOLVER_CRANK_NICOLSON: ComputeBrickRatesBisection(m, b, content, inflow, dt, iRateStart, true); break;
+            case HBO_SOLVER_IMPLICIT_EULER: ComputeBrickRatesBisection(m, b, content, inflow, dt, iRateStart, false); break;
+            case HBO_SOLVER_EXPONENTIAL_EULER: ComputeBrickRatesExponential(m, b, content, inflow, dt, iRateStart); break;
+            default: ComputeBrickRatesAnalytic(m, b, content, inflow, dt, iRateStart); break;
+        }
+        BrickApplyConstraints(m, b, dt);
+        UpdateContentFromInputs(m, b);
+        int iRateApply = iRateStart;
+        for (int ip : b.processes) {
+            Process& p = m.processes[ip];
+            for (size_t j = 0; j < p.outputs.size(); ++j) {
+                ApplyChange(m, p, static_cast<int>(j), m.k1[iRateApply], dt);
+                iRateApply++;
+            }
+        }
+    }
+    FinalizeTimeStep(m);
+}
+
 // Processor.cpp:278-323
 void ApplyDirectChanges(hbo_model& m, Brick& b, int& ptIndex, double dt) {
     UpdateContentFromInputs(m, b);
@@ -799,7 +968,8 @@ void ProcessTimeStep(hbo_model& m, double dt) {
     switch (m.solver) {
         case HBO_SOLVER_EULER: SolveEuler(m, dt); break;
         case HBO_SOLVER_HEUN: SolveHeun(m, dt); break;
-        default: SolveRK4(m, dt); break;
+        case HBO_SOLVER_RK4: SolveRK4(m, dt); break;
+        default: SolveSequential(m, dt); break;
     }
     m.outletTotal = 0;
     for (int io : m.outletFluxes) m.outletTotal += FluxGetAmount(m, m.fluxes[io]);

@@ -43,7 +43,11 @@ enum {
 };
 enum { HBO_S_SNOW_RAIN_LINEAR = 0, HBO_S_MULTI_FLUXES = 1, HBO_S_RAIN = 2, HBO_S_SNOW_RAIN_THRESHOLD = 3 };
 enum { HBO_V_PRECIPITATION = 0, HBO_V_TEMPERATURE = 1, HBO_V_PET = 2 };
-enum { HBO_SOLVER_EULER = 0, HBO_SOLVER_HEUN = 1, HBO_SOLVER_RK4 = 2 };
+enum { HBO_SOLVER_EULER = 0, HBO_SOLVER_HEUN = 1, HBO_SOLVER_RK4 = 2,
+       /* sequential family (base/SolverSequential.cpp): Solver::Factory names crank_nicolson|trapezoidal,
+        * implicit_euler|euler_implicit, exponential_euler, analytic_linear|analytic (Solver.cpp:42-64) */
+       HBO_SOLVER_CRANK_NICOLSON = 3, HBO_SOLVER_IMPLICIT_EULER = 4, HBO_SOLVER_EXPONENTIAL_EULER = 5,
+       HBO_SOLVER_ANALYTIC_LINEAR = 6 };
 enum { HBO_REC_CONTAINER = 0, HBO_REC_FLUX = 1, HBO_REC_OUTLET = 2, HBO_REC_FRACTION = 3 };
 
 hbo_model* hbo_create(int n_units, int n_steps, double dt_days, int solver, int spinup_steps);

@@ -51,7 +51,9 @@ PROC_PARAMS = {
 }
 SPLITTER_KIND = {"snow_rain:linear": 0, "snow_rain_transition": 0, "multi_fluxes": 1, "rain": 2, "snow_rain:threshold": 3}
 FORCING = {"precipitation": 0, "p": 0, "temperature": 1, "t": 1, "pet": 2}  # TimeSeries.cpp:134-146
-SOLVERS = {"euler_explicit": 0, "heun_explicit": 1, "rk4": 2, "runge_kutta": 2}
+SOLVERS = {"euler_explicit": 0, "heun_explicit": 1, "rk4": 2, "runge_kutta": 2,
+           "crank_nicolson": 3, "trapezoidal": 3, "implicit_euler": 4, "euler_implicit": 4, "exponential_euler": 5,
+           "analytic_linear": 6, "analytic": 6}
 F_TO_BRICK, F_TO_BRICK_INSTANT, F_TO_OUTLET, F_TO_ATMOSPHERE, F_SIMPLE, F_FORCING = range(6)
 WATER, SNOW, ICE = 0, 1, 2
 CONTENT = {"water": WATER, "snow": SNOW, "ice": ICE}

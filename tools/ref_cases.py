@@ -173,7 +173,9 @@ if __name__ == "__main__":
              ("gsm", dict(soil_storage_nb=1, surface_runoff="socont_runoff", with_glacier=False)),
              ("gsm", dict(soil_storage_nb=1, surface_runoff="socont_runoff", with_glacier=True,
                           infinite_storage=False))]
-    for solver in ["rk4", "heun_explicit", "euler_explicit"]:
+    solvers = sys.argv[1:] or ["rk4", "heun_explicit", "euler_explicit", "crank_nicolson", "implicit_euler",
+                               "exponential_euler", "analytic_linear"]
+    for solver in solvers:
         for kind, kw in cases:
             fn = sitter_socont if kind == "sitter" else gsm_socont
             model, hu, forcing, params = fn(hb, solver=solver, end_date="1990-12-31", **kw)
