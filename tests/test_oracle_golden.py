@@ -47,6 +47,33 @@ def test_kat_linear_storage(solver):
     assert abs(30.0 - om.outlet.sum() - content) < 1e-14  # SolverTest.cpp:182
 
 
+@pytest.mark.parametrize("solver", ["analytic_linear", "implicit_euler", "crank_nicolson", "exponential_euler"])
+def test_kat_linear_storage_sequential_solvers(solver):
+    """core/tests/src/SolverTest.cpp:259-430: the sequential solvers on the linear-storage fixture against the
+    closed forms the reference's tests use (tolerances 1e-9 analytic, 1e-8 the others)."""
+    meta, forcing, outlet, _, _ = gu.load(f"kat_linear_storage_{solver}")
+    om = gu.run_oracle(meta, forcing)
+    assert gu.same(om.outlet, outlet)
+    precip = [0.0, 10.0, 10.0, 10.0] + [0.0] * 16
+    k = float(np.float32(0.3))
+    storage, tol = 0.0, (1e-9 if solver == "analytic_linear" else 1e-8)
+    for j, p in enumerate(precip):
+        if solver in ("analytic_linear", "exponential_euler"):
+            new = storage * np.exp(-k) + p / k * (1.0 - np.exp(-k))
+            out = p - (new - storage)
+        elif solver == "implicit_euler":
+            new = (storage + p) / (1.0 + k)
+            out = k * new
+        else:
+            new = (storage * (1.0 - k / 2) + p) / (1.0 + k / 2)
+            out = k * (storage + new) / 2
+        assert abs(om.outlet[j] - out) < tol, (j, om.outlet[j], out)
+        storage = new
+    content = om.records["storage:water_content"][-1, 0]
+    assert abs(content - storage) < tol
+    assert abs(30.0 - om.outlet.sum() - content) < tol
+
+
 def test_kat_socont_quick_discharge():
     """core/tests/src/ModelSocontTest.cpp:575-626."""
     meta, forcing, _, _, _ = gu.load("kat_socont_quick_rk4")

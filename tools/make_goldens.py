@@ -156,11 +156,36 @@ def snow_ice_bundles(hb):
         save(f"gsm_socont_{solver}_sublim_{algo}_{tag}_{nb}store", meta, fdata, q, rec)
 
 
+def sequential_bundles(hb, ref):
+    """the sequential solver family (base/SolverSequential.cpp; crank_nicolson is the default of the
+    reference's Python layer, models/model.py:80)."""
+    for solver in ["crank_nicolson", "implicit_euler", "exponential_euler", "analytic_linear"]:
+        save(f"kat_linear_storage_{solver}", *kat_linear_storage(ref, solver))
+    cases = [("crank_nicolson", "glacier_2store", dict(soil_storage_nb=2)),
+             ("crank_nicolson", "glacier_finite_1store", dict(soil_storage_nb=1, infinite_storage=False)),
+             ("crank_nicolson", "glacier_linear_1store", dict(soil_storage_nb=1, surface_runoff="linear_storage")),
+             ("implicit_euler", "glacier_2store", dict(soil_storage_nb=2)),
+             ("exponential_euler", "glacier_finite_1store", dict(soil_storage_nb=1, infinite_storage=False)),
+             ("exponential_euler", "noglacier_2store", dict(soil_storage_nb=2, with_glacier=False)),
+             ("analytic_linear", "glacier_2store", dict(soil_storage_nb=2)),
+             ("analytic_linear", "glacier_linear_1store", dict(soil_storage_nb=1, surface_runoff="linear_storage"))]
+    for solver, tag, kw in cases:
+        m, hu, f, _ = ref_cases.gsm_socont(hb, solver=solver, end_date="1982-12-31", n_units=10, **kw)
+        structures, units, fdata, q, rec = ref_cases.collect(m, hu, f)
+        meta = {"structures": structures, "units": units, "solver": m.solver, "labels": list(rec),
+                "source": "reference Python layer, 10 synthetic bands with slope/glacier, Rhone-Gletsch meteo "
+                          "1981-1982, sequential solver " + solver}
+        save(f"gsm_socont_{solver}_{tag}", meta, fdata, q, rec)
+
+
 def main():
     hb = refpy.load_reference_python("ref")
     ref = sys.modules["hydrobricks._hydrobricks"]
     if len(sys.argv) > 1 and sys.argv[1] == "snow_ice":
         snow_ice_bundles(hb)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "sequential":
+        sequential_bundles(hb, ref)
         return
 
     for solver in ["euler_explicit", "heun_explicit", "runge_kutta"]:
@@ -226,6 +251,7 @@ def main():
         extra["spatial_last_" + k] = v[:, -1]
     save("c1_sitter_rk4_full", meta, {}, q, {}, extra=extra)
     snow_ice_bundles(hb)
+    sequential_bundles(hb, ref)
 
 
 if __name__ == "__main__":
