@@ -602,8 +602,18 @@ struct Compiled {
             st.solver = HBK_SOLVER_HEUN;
         } else if (solver == "rk4" || solver == "runge_kutta") {
             st.solver = HBK_SOLVER_RK4;
+        } else if (solver == "crank_nicolson" || solver == "trapezoidal") {  // Solver::Factory, Solver.cpp:42-64
+            st.solver = HBK_SOLVER_CRANK_NICOLSON;
+        } else if (solver == "implicit_euler" || solver == "euler_implicit") {
+            st.solver = HBK_SOLVER_IMPLICIT_EULER;
+        } else if (solver == "exponential_euler") {
+            st.solver = HBK_SOLVER_EXPONENTIAL_EULER;
+        } else if (solver == "analytic_linear" || solver == "analytic") {
+            st.solver = HBK_SOLVER_ANALYTIC_LINEAR;
         } else {
-            throw Unsupported("solver '" + solver + "': only euler_explicit, heun_explicit and rk4/runge_kutta run on the device");
+            throw Unsupported("Incorrect solver name: " + solver + ". Valid solver names: rk4, runge_kutta, "
+                              "euler_explicit, heun_explicit, analytic_linear, analytic, implicit_euler, "
+                              "euler_implicit, crank_nicolson, trapezoidal, exponential_euler");
         }
         st.time_step_days = dtDays;
         st.snow_ice_kind = HBK_SNOW_ICE_NONE;

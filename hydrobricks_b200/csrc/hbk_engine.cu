@@ -374,7 +374,11 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
                     }
                     directPhase<GLACIER>(h, par, precip, temp, dt, invDt, fa, fG, fGl, glacierVariant, a.flags, o, err,
                                          (GLACIER && a.swatFactor) ? a.swatFactor[t0 + tc] : 0.0, sublimG, sublimGl);
-                    solveUnit<SOLVER, NSOIL>(h, par, pet, fa, dt, invDt, a.flags, o, err, unconverged);
+                    if constexpr (SOLVER == 3) {
+                        solveUnitSequential<NSOIL>(h, par, pet, fa, dt, invDt, a.flags, o, err);
+                    } else {
+                        solveUnit<SOLVER, NSOIL>(h, par, pet, fa, dt, invDt, a.flags, o, err, unconverged);
+                    }
 
                     if (nRec && a.writeOutputs) {
                         // Logger::Record (Logger.cpp:93-120): contents after Finalize and flux amounts
@@ -521,7 +525,7 @@ template <int SOLVER>
 __global__ void hbkBasinStores(const float* params, int ldp, int P, long long ldt, int tBegin, int tEnd, double dt,
                                const double* d1, const double* d2, const double* stale, double* outlet,
                                double* basinState, int writeOutputs, int* errFlags, unsigned long long* unconv,
-                               const int* perm) {
+                               const int* perm, int seqKind) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
     const size_t row = perm ? perm[p] : p;  // outlet rows are in the caller's order
@@ -532,8 +536,8 @@ __global__ void hbkBasinStores(const float* params, int ldp, int P, long long ld
     int err = 0, unc = 0;
     for (int t = tBegin; t < tEnd; ++t) {
         const double dep1 = d1[(size_t)p * ldt + t], dep2 = d2[(size_t)p * ldt + t];
-        const double o1 = basinStoreStep<SOLVER>(c1, kSnow, dep1, dep1 + st1, dt, err, unc);
-        const double o2 = basinStoreStep<SOLVER>(c2, kIce, dep2, dep2 + st2, dt, err, unc);
+        const double o1 = basinStoreStep<SOLVER>(c1, kSnow, dep1, dep1 + st1, dt, err, unc, seqKind);
+        const double o2 = basinStoreStep<SOLVER>(c2, kIce, dep2, dep2 + st2, dt, err, unc, seqKind);
         if (writeOutputs) outlet[row * ldt + t] = (o1 + o2) + outlet[row * ldt + t];
     }
     basinState[2 * p] = c1;
@@ -1039,7 +1043,13 @@ using KernelFn = void (*)(const KArgs);
 
 template <int SOLVER, int NSOIL, bool GLACIER>
 KernelFn pickDaily(bool daily) {
-    return daily ? (KernelFn)hbkRunUnits<SOLVER, NSOIL, GLACIER, true> : (KernelFn)hbkRunUnits<SOLVER, NSOIL, GLACIER, false>;
+    // the sequential solvers (SOLVER 3) are not the throughput path: one instantiation, dt read at run time
+    if constexpr (SOLVER == 3) {
+        return (KernelFn)hbkRunUnits<SOLVER, NSOIL, GLACIER, false>;
+    } else {
+        return daily ? (KernelFn)hbkRunUnits<SOLVER, NSOIL, GLACIER, true>
+                     : (KernelFn)hbkRunUnits<SOLVER, NSOIL, GLACIER, false>;
+    }
 }
 template <int SOLVER, int NSOIL>
 KernelFn pickGlacier(bool glacier, bool daily) {
@@ -1055,7 +1065,8 @@ KernelFn pickKernel(const hbk_structure& st) {
     switch (st.solver) {
         case HBK_SOLVER_EULER: return pickSoil<0>(st.n_soil_stores, st.has_glacier != 0, st.time_step_days == 1.0);
         case HBK_SOLVER_HEUN: return pickSoil<1>(st.n_soil_stores, st.has_glacier != 0, st.time_step_days == 1.0);
-        default: return pickSoil<2>(st.n_soil_stores, st.has_glacier != 0, st.time_step_days == 1.0);
+        case HBK_SOLVER_RK4: return pickSoil<2>(st.n_soil_stores, st.has_glacier != 0, st.time_step_days == 1.0);
+        default: return pickSoil<3>(st.n_soil_stores, st.has_glacier != 0, false);  // sequential family
     }
 }
 
@@ -1133,7 +1144,7 @@ int hbk_engine_create(const hbk_structure* st, int32_t n_units, int32_t n_steps,
         delete e;
         return code;
     };
-    if (st->solver < 0 || st->solver > 2) return bail(HBK_E_ARG, "unknown solver");
+    if (st->solver < 0 || st->solver > HBK_SOLVER_ANALYTIC_LINEAR) return bail(HBK_E_ARG, "unknown solver");
     if (st->n_soil_stores != 1 && st->n_soil_stores != 2) return bail(HBK_E_UNSUPPORTED, "n_soil_stores must be 1 or 2");
     if (!(st->time_step_days > 0)) return bail(HBK_E_ARG, "time_step_days must be > 0");
     int count = 0;
@@ -1519,6 +1530,24 @@ static int applyEvents(hbk_engine* e, int step) {
     return HBK_OK;
 }
 
+// The two sub-basin stores over [tBegin, tEnd) with the structure's solver (hbkBasinStores).
+static void launchBasinStores(hbk_engine* e, int tBegin, int tEnd, const double* stale, int writeOutputs) {
+    const int blocks = (e->P + 127) / 128;
+    const double dt = e->st.time_step_days;
+    const int seqKind = e->st.solver >= HBK_SOLVER_CRANK_NICOLSON ? e->st.solver - HBK_SOLVER_CRANK_NICOLSON : 0;
+#define HBK_BASIN(S)                                                                                                   \
+    hbkBasinStores<S><<<blocks, 128, 0, e->stream>>>(e->dParams, e->ldp, e->P, e->ldt, tBegin, tEnd, dt, e->dD1, e->dD2, \
+                                                     stale, e->dOutlet, e->dBasinState, writeOutputs, e->dErr,         \
+                                                     e->dUnconv, e->dPerm, seqKind)
+    switch (e->st.solver) {
+        case HBK_SOLVER_EULER: HBK_BASIN(0); break;
+        case HBK_SOLVER_HEUN: HBK_BASIN(1); break;
+        case HBK_SOLVER_RK4: HBK_BASIN(2); break;
+        default: HBK_BASIN(3); break;
+    }
+#undef HBK_BASIN
+}
+
 static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs) {
     const bool tiled = e->haveRaw[0];
     KArgs a{};
@@ -1539,6 +1568,7 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
     a.flags.iceInfinite = e->st.glacier_infinite_storage;
     a.flags.snowIceKind = e->st.has_glacier ? e->st.snow_ice_kind : 0;
     a.flags.sublimKind = e->st.sublimation_kind;
+    a.flags.seqKind = e->st.solver >= HBK_SOLVER_CRANK_NICOLSON ? e->st.solver - HBK_SOLVER_CRANK_NICOLSON : 0;
     a.swatFactor = (a.flags.snowIceKind == HBK_SNOW_ICE_SWAT) ? e->dSwatFactor : nullptr;
     a.flags.noMeltWhenSnow = e->st.glacier_no_melt_when_snow_cover;
     a.dt = e->st.time_step_days;
@@ -1644,23 +1674,7 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
             e->lastLaunches++;
             stale = e->dStale;
         }
-        switch (e->st.solver) {
-            case HBK_SOLVER_EULER:
-                hbkBasinStores<0><<<blocks, 128, 0, e->stream>>>(e->dParams, e->ldp, e->P, e->ldt, tBegin, tEnd, dt, e->dD1,
-                                                               e->dD2, stale, e->dOutlet, e->dBasinState,
-                                                               writeOutputs ? 1 : 0, e->dErr, e->dUnconv, e->dPerm);
-                break;
-            case HBK_SOLVER_HEUN:
-                hbkBasinStores<1><<<blocks, 128, 0, e->stream>>>(e->dParams, e->ldp, e->P, e->ldt, tBegin, tEnd, dt, e->dD1,
-                                                               e->dD2, stale, e->dOutlet, e->dBasinState,
-                                                               writeOutputs ? 1 : 0, e->dErr, e->dUnconv, e->dPerm);
-                break;
-            default:
-                hbkBasinStores<2><<<blocks, 128, 0, e->stream>>>(e->dParams, e->ldp, e->P, e->ldt, tBegin, tEnd, dt, e->dD1,
-                                                               e->dD2, stale, e->dOutlet, e->dBasinState,
-                                                               writeOutputs ? 1 : 0, e->dErr, e->dUnconv, e->dPerm);
-                break;
-        }
+        launchBasinStores(e, tBegin, tEnd, stale, writeOutputs ? 1 : 0);
         e->lastLaunches++;
     }
     HBK_CUDA(cudaGetLastError());
@@ -1838,23 +1852,7 @@ int hbk_finish_sharded_run(hbk_engine* e) {
     const int blocks = (e->P + 127) / 128;
     const double dt = e->st.time_step_days;
     HBK_CUDA(cudaEventRecord(e->ev0, e->stream));
-    switch (e->st.solver) {
-        case HBK_SOLVER_EULER:
-            hbkBasinStores<0><<<blocks, 128, 0, e->stream>>>(e->dParams, e->ldp, e->P, e->ldt, 0, e->T, dt, e->dD1, e->dD2,
-                                                           nullptr, e->dOutlet, e->dBasinState, 1, e->dErr, e->dUnconv,
-                                                           e->dPerm);
-            break;
-        case HBK_SOLVER_HEUN:
-            hbkBasinStores<1><<<blocks, 128, 0, e->stream>>>(e->dParams, e->ldp, e->P, e->ldt, 0, e->T, dt, e->dD1, e->dD2,
-                                                           nullptr, e->dOutlet, e->dBasinState, 1, e->dErr, e->dUnconv,
-                                                           e->dPerm);
-            break;
-        default:
-            hbkBasinStores<2><<<blocks, 128, 0, e->stream>>>(e->dParams, e->ldp, e->P, e->ldt, 0, e->T, dt, e->dD1, e->dD2,
-                                                           nullptr, e->dOutlet, e->dBasinState, 1, e->dErr, e->dUnconv,
-                                                           e->dPerm);
-            break;
-    }
+    launchBasinStores(e, 0, e->T, nullptr, 1);
     e->lastLaunches++;
     HBK_CUDA(cudaGetLastError());
     HBK_CUDA(cudaEventRecord(e->ev1, e->stream));

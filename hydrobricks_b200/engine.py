@@ -16,7 +16,10 @@ import os  # noqa: E402
 LIB_PATH = Path(os.environ.get("HBK_LIB", HERE / "libhbk.so"))  # HBK_LIB: tuning builds of the same sources
 
 # enums of include/hbk.h
-SOLVER = {"euler_explicit": 0, "heun_explicit": 1, "rk4": 2, "runge_kutta": 2}
+SOLVER = {"euler_explicit": 0, "heun_explicit": 1, "rk4": 2, "runge_kutta": 2,
+          # sequential family (base/SolverSequential.cpp); crank_nicolson is the reference Python layer's default
+          "crank_nicolson": 3, "trapezoidal": 3, "implicit_euler": 4, "euler_implicit": 4, "exponential_euler": 5,
+          "analytic_linear": 6, "analytic": 6}
 QUICK_SOCONT, QUICK_LINEAR = 0, 1
 SPLIT_LINEAR, SPLIT_THRESHOLD = 0, 1
 SNOW_ICE_NONE, SNOW_ICE_CONSTANT, SNOW_ICE_SWAT = 0, 1, 2

@@ -50,7 +50,7 @@ class CompiledStructure:
     def __init__(self, structures, solver: str, time_step_days: float = 1.0, start_mjd: float = 44605.0):
         if solver not in _e.SOLVER:
             raise UnsupportedStructure(
-                f"solver {solver!r}: only euler_explicit, heun_explicit and rk4/runge_kutta run on the device")
+                f"Incorrect solver name: {solver!r}. Valid solver names: " + ", ".join(_e.SOLVER))
         self.solver = solver
         self.structures = structures
         self.labels = {}

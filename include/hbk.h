@@ -26,8 +26,12 @@ typedef struct hbk_engine hbk_engine;
 
 enum { HBK_OK = 0, HBK_E_ARG = -1, HBK_E_CUDA = -2, HBK_E_STATE = -3, HBK_E_MODEL = -4, HBK_E_UNSUPPORTED = -5 };
 
-/* Solver::Factory names (core/src/base/Solver.cpp:42-64): euler_explicit, heun_explicit, rk4|runge_kutta */
-enum { HBK_SOLVER_EULER = 0, HBK_SOLVER_HEUN = 1, HBK_SOLVER_RK4 = 2 };
+/* Solver::Factory names (core/src/base/Solver.cpp:42-64): euler_explicit, heun_explicit, rk4|runge_kutta, and the
+ * sequential family of base/SolverSequential.cpp (one brick after the other): crank_nicolson|
+ * trapezoidal (the default of the reference's Python layer, models/model.py:80), implicit_euler|euler_implicit,
+ * exponential_euler, analytic_linear|analytic */
+enum { HBK_SOLVER_EULER = 0, HBK_SOLVER_HEUN = 1, HBK_SOLVER_RK4 = 2, HBK_SOLVER_CRANK_NICOLSON = 3,
+       HBK_SOLVER_IMPLICIT_EULER = 4, HBK_SOLVER_EXPONENTIAL_EULER = 5, HBK_SOLVER_ANALYTIC_LINEAR = 6 };
 /* surface_runoff brick process: runoff:socont (ProcessRunoffSocont.cpp:41-56) | outflow:linear */
 enum { HBK_QUICK_SOCONT = 0, HBK_QUICK_LINEAR = 1 };
 /* snow_rain_transition splitter: snow_rain:linear | snow_rain:threshold */

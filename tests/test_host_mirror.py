@@ -103,7 +103,11 @@ def test_unsupported_structures_are_refused():
         structure.CompiledStructure(meta["structures"], "rk4")
     meta, _, _, _, _ = gu.load("socont_sitter_rk4_1store")
     with pytest.raises(structure.UnsupportedStructure):
-        structure.CompiledStructure(meta["structures"], "crank_nicolson")
+        structure.CompiledStructure(meta["structures"], "adams_bashforth")
+    # the sequential family (base/SolverSequential.cpp) compiles to its own solver ids
+    for name, sid in (("crank_nicolson", 3), ("trapezoidal", 3), ("implicit_euler", 4), ("exponential_euler", 5),
+                      ("analytic", 6)):
+        assert structure.CompiledStructure(meta["structures"], name).hbk.solver == sid
 
 
 def test_structure_variant_assignment():
