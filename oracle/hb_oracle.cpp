@@ -1142,6 +1142,37 @@ void ApplyDeltaH(hbo_model& m) {
     }
 }
 
+// ActionGlacierEvolutionAreaScaling::Apply (ActionGlacierEvolutionAreaScaling.cpp:75-123): every unit of the lookup
+// table follows its own column (retreat of ITS ice volume -> row -> new area; the ice w.e. is rescaled to the new
+// area). Tables and Init are those of the delta-h action (…AreaScaling.cpp:9-68 = …DeltaH.cpp:9-70).
+void ApplyAreaScaling(hbo_model& m) {
+    const int n = static_cast<int>(m.dhBricks.size());
+    int nRows = m.dhRows;
+    double rowPcIncrement = 1.0 / (nRows - 1);
+    for (int i = 0; i < n; ++i) {
+        Brick& b = m.bricks[m.dhBricks[i]];
+        if (NearlyZero(b.areaFraction, PRECISION)) continue;
+        Container& ice = m.containers[b.second];
+        double area = b.areaFraction * m.dhUnitAreas[i];
+        double brickIceWE = ice.content;
+        double iceVolume = area * brickIceWE;
+        if (NearlyZero(iceVolume, PRECISION)) {
+            ChangeLandCoverAreaFraction(m, m.dhBricks[i], 0);
+            continue;
+        }
+        double initialWE = m.dhVolumes[i] * 900.0;  // _tableVolume.row(0) * constants::iceDensity
+        double glacierRetreatPc = (initialWE - iceVolume) / initialWE;
+        glacierRetreatPc = std::max(0.0, glacierRetreatPc);
+        int row = static_cast<int>(glacierRetreatPc / rowPcIncrement);
+        double newArea = m.dhAreas[static_cast<size_t>(row) * n + i];
+        double newFraction = newArea / m.dhUnitAreas[i];
+        newFraction = CheckFraction(newFraction);
+        ChangeLandCoverAreaFraction(m, m.dhBricks[i], newFraction);
+        double iceWE = iceVolume / newArea;  // +inf when the table's area is 0 (as the reference)
+        ice.content = iceWE;
+    }
+}
+
 // ActionGlacierSnowToIceTransformation::Apply (ActionGlacierSnowToIceTransformation.cpp:41-74)
 void ApplySnowToIce(hbo_model& m) {
     for (auto& pr : m.snowToIce) {
@@ -1164,6 +1195,7 @@ void ApplyEvents(hbo_model& m, int step) {
             case HBO_ACT_LAND_COVER_CHANGE: ChangeLandCoverAreaFraction(m, e.brick, e.value); break;
             case HBO_ACT_SNOW_TO_ICE: ApplySnowToIce(m); break;
             case HBO_ACT_DELTA_H: ApplyDeltaH(m); break;
+            case HBO_ACT_AREA_SCALING: ApplyAreaScaling(m); break;
         }
     }
 }

@@ -80,7 +80,7 @@ void hbo_set_start_mjd(hbo_model* m, double mjd);
 
 /* Dated actions (ActionsManager::DateUpdate, ActionsManager.cpp:80-104), applied between time steps, before
  * step `step` (>= 1), in the order added for equal steps. Not applied during spin-up (ModelHydro.cpp:141-147). */
-enum { HBO_ACT_LAND_COVER_CHANGE = 0, HBO_ACT_SNOW_TO_ICE = 1, HBO_ACT_DELTA_H = 2 };
+enum { HBO_ACT_LAND_COVER_CHANGE = 0, HBO_ACT_SNOW_TO_ICE = 1, HBO_ACT_DELTA_H = 2, HBO_ACT_AREA_SCALING = 3 };
 /* land-cover change: `brick` = the changed land-cover brick, value = new area fraction (already checked/snapped).
  * snow-to-ice: brick = -1 (all glacier units registered with hbo_add_snow_to_ice_unit). delta-h: brick = -1. */
 void hbo_add_event(hbo_model* m, int step, int kind, int brick, double value);

@@ -446,7 +446,7 @@ class OracleModel:
         for s in steps:
             self.L.hbo_add_event(self.h, int(s), 1, -1, 0.0)
 
-    def set_delta_h(self, cover, unit_indices, areas, volumes, steps):
+    def set_delta_h(self, cover, unit_indices, areas, volumes, steps, area_scaling=False):
         areas = np.ascontiguousarray(areas, dtype=np.float64)
         volumes = np.ascontiguousarray(volumes, dtype=np.float64)
         n = len(unit_indices)
@@ -455,8 +455,8 @@ class OracleModel:
         dp = ctypes.POINTER(ctypes.c_double)
         self.L.hbo_set_delta_h(self.h, n, bricks, ua.ctypes.data_as(dp), areas.shape[0], areas.ctypes.data_as(dp),
                                volumes.ctypes.data_as(dp))
-        for s in steps:
-            self.L.hbo_add_event(self.h, int(s), 2, -1, 0.0)
+        for s in steps:  # ActionGlacierEvolutionAreaScaling shares the tables and Init of the delta-h action
+            self.L.hbo_add_event(self.h, int(s), 3 if area_scaling else 2, -1, 0.0)
 
     # -- recording (Logger.cpp:93-120; label scheme SettingsModel.cpp:808-841) --------------------
     def record(self, label: str):

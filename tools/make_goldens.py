@@ -178,11 +178,36 @@ def sequential_bundles(hb, ref):
         save(f"gsm_socont_{solver}_{tag}", meta, fdata, q, rec)
 
 
+def action_bundles(ref, only_new=False):
+    """Dated actions (SURVEY §8 a21, config C4 in small): delta-h glacier evolution, land-cover changes, snow->ice;
+    the area-scaling glacier evolution (ActionGlacierEvolutionAreaScaling) and actions under a sequential solver."""
+    import ref_actions_case as rc
+
+    cases = [("rk4", (True, True, True), False), ("rk4", (True, False, False), False), ("rk4", (False, True, False), False),
+             ("heun_explicit", (True, True, True), False), ("euler_explicit", (True, True, True), False)]
+    new = [("rk4", (True, False, False), True), ("heun_explicit", (True, True, True), True),
+           ("crank_nicolson", (True, True, True), False)]
+    for solver, flags, area_scaling in (new if only_new else cases + new):
+        meta, forcing, q, rec, frac, areas, volumes = rc.run_reference(ref, solver, *flags, area_scaling=area_scaling)
+        tag = "".join(n for n, f in zip(("as" if area_scaling else "dh", "lc", "s2i"), flags) if f)
+        extra = {"spatial_dh_areas": areas, "spatial_dh_volumes": volumes}
+        for k, v in frac.items():
+            extra["spatial_fraction_" + k] = v
+        keep = ["glacier:ice_content", "glacier:water_content", "ground:water_content",
+                "glacier_snowpack:snow_content", "ground_snowpack:snow_content", "slow_reservoir:water_content",
+                "surface_runoff:water_content", "glacier:melt:output", "glacier:outflow_rain_snowmelt:output"]
+        meta["labels"] = keep
+        save(f"actions_{solver}_{tag}", meta, forcing, q, {k: rec[k] for k in keep}, extra=extra)
+
+
 def main():
     hb = refpy.load_reference_python("ref")
     ref = sys.modules["hydrobricks._hydrobricks"]
     if len(sys.argv) > 1 and sys.argv[1] == "snow_ice":
         snow_ice_bundles(hb)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "actions_new":
+        action_bundles(ref, only_new=True)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "sequential":
         sequential_bundles(hb, ref)
@@ -216,21 +241,7 @@ def main():
             bundle(f"gsm_socont_{solver}_{tag}", m, hu, f,
                    "reference Python layer, 10 synthetic bands with slope/glacier, Rhone-Gletsch meteo 1981-1982")
 
-    # Dated actions (SURVEY §8 a21, config C4 in small): delta-h glacier evolution, land-cover changes, snow->ice
-    import ref_actions_case as rc
-
-    for solver, flags in [("rk4", (True, True, True)), ("rk4", (True, False, False)), ("rk4", (False, True, False)),
-                          ("heun_explicit", (True, True, True)), ("euler_explicit", (True, True, True))]:
-        meta, forcing, q, rec, frac, areas, volumes = rc.run_reference(ref, solver, *flags)
-        tag = "".join(n for n, f in zip(("dh", "lc", "s2i"), flags) if f)
-        extra = {"spatial_dh_areas": areas, "spatial_dh_volumes": volumes}
-        for k, v in frac.items():
-            extra["spatial_fraction_" + k] = v
-        keep = ["glacier:ice_content", "glacier:water_content", "ground:water_content",
-                "glacier_snowpack:snow_content", "ground_snowpack:snow_content", "slow_reservoir:water_content",
-                "surface_runoff:water_content", "glacier:melt:output", "glacier:outflow_rain_snowmelt:output"]
-        meta["labels"] = keep
-        save(f"actions_{solver}_{tag}", meta, forcing, q, {k: rec[k] for k in keep}, extra=extra)
+    action_bundles(ref)
 
     # C1: full bundled catchment, 1981-2020, outlet + station series only (fused spatialisation input).
     m, hu, f, params = ref_cases.sitter_socont(hb, solver="rk4", soil_storage_nb=1, end_date="2020-12-31")

@@ -76,7 +76,7 @@ CHANGES = [  # (days after start, unit position in basin order, new glacier area
     (400, 1, 0.90), (800, 2, 0.75), (800.0, 0, 1.05), (1300, 3, 0.0), (1700, 1, 0.60)]
 
 
-def run_reference(ref, solver, with_delta_h=True, with_changes=True, with_snow_to_ice=True):
+def run_reference(ref, solver, with_delta_h=True, with_changes=True, with_snow_to_ice=True, area_scaling=False):
     units, forcing, T, gl, areas, volumes = synthetic_case()
     m = build_settings(ref, solver)
     end = str(np.datetime64("1981-01-01") + np.timedelta64(T - 1, "D"))
@@ -88,7 +88,8 @@ def run_reference(ref, solver, with_delta_h=True, with_changes=True, with_snow_t
         assert model.add_action(a)
         keep.append(a)
     if with_delta_h:
-        a = ref.ActionGlacierEvolutionDeltaH()
+        # area_scaling: ActionGlacierEvolutionAreaScaling, same tables, every unit follows its own column
+        a = ref.ActionGlacierEvolutionAreaScaling() if area_scaling else ref.ActionGlacierEvolutionDeltaH()
         a.add_lookup_tables(10, "glacier", np.array([m.units[i]["id"] for i in gl], dtype=np.int32), areas, volumes)
         assert model.add_action(a)
         keep.append(a)
@@ -109,7 +110,8 @@ def run_reference(ref, solver, with_delta_h=True, with_changes=True, with_snow_t
     rec = {label: model.get_hydro_unit_values(label) for label in model.get_recorded_hydro_unit_labels()}
     frac = {label: model.get_hydro_unit_fractions(label) for label in model.get_recorded_hydro_unit_fraction_labels()}
     meta = {"structures": m.settings.get_structure(), "units": m.units, "solver": solver, "labels": list(rec),
-            "actions": {"delta_h": {"month": 10, "cover": "glacier", "unit_positions": gl} if with_delta_h else None,
+            "actions": {"delta_h": {"month": 10, "cover": "glacier", "unit_positions": gl,
+                                    "area_scaling": bool(area_scaling)} if with_delta_h else None,
                         "changes": [[d, gl[p], s * areas[0][p] / m.units[gl[p]]["area"]] for d, p, s in CHANGES]
                         if with_changes else [],
                         "snow_to_ice": [9, 30] if with_snow_to_ice else None, "start_mjd": START_MJD},
@@ -151,10 +153,11 @@ def run_oracle(meta, forcing, areas, volumes, labels):
             om.add_snow_to_ice("glacier", [k])
         elif kind == "dh":
             if first_dh:
-                om.set_delta_h("glacier", act["delta_h"]["unit_positions"], areas, volumes, [k])
+                om.set_delta_h("glacier", act["delta_h"]["unit_positions"], areas, volumes, [k],
+                               area_scaling=act["delta_h"].get("area_scaling", False))
                 first_dh = False
             else:
-                om.L.hbo_add_event(om.h, int(k), 2, -1, 0.0)
+                om.L.hbo_add_event(om.h, int(k), 3 if act["delta_h"].get("area_scaling") else 2, -1, 0.0)
         else:
             om.add_land_cover_change(k, payload[0], "glacier", payload[1])
     for label in labels:
@@ -168,8 +171,9 @@ if __name__ == "__main__":
 
     ref = refpy.load_extension("ref")
     ref.init()
-    for solver in ["rk4", "heun_explicit", "euler_explicit"]:
-        for flags in [(True, True, True), (True, False, False), (False, True, False), (False, False, True)]:
+    for solver in ["rk4", "heun_explicit", "euler_explicit", "crank_nicolson"]:
+        for flags in [(True, True, True), (True, False, False), (False, True, False), (False, False, True),
+                      (True, False, False, True), (True, True, True, True)]:
             meta, forcing, q, rec, frac, areas, volumes = run_reference(ref, solver, *flags)
             om = run_oracle(meta, forcing, areas, volumes, list(rec))
             bad = int(np.sum(om.outlet != q))
