@@ -574,15 +574,20 @@ class ModelHydro:
         glacier = self._cs.glacier_name
         events = []  # (step, order, callable)
         sporadic = []
+        have_tables = False
         for order, action in enumerate(self._actions):
             if isinstance(action, ActionGlacierSnowToIceTransformation):
                 if action.land_cover != glacier:
                     raise ValueError(f"snow-to-ice: land cover '{action.land_cover}' is not the glacier cover")
                 for k in _schedule.recursive_steps(self._mjd0, self._n_steps, action.month, action.day, dt):
                     events.append((k, order, lambda k=k: eng.add_snow_to_ice(k)))
-            elif isinstance(action, ActionGlacierEvolutionAreaScaling):
-                raise ValueError("ActionGlacierEvolutionAreaScaling is not available in the B200 engine")
             elif isinstance(action, ActionGlacierEvolutionDeltaH):
+                # ActionGlacierEvolutionAreaScaling shares the lookup-table interface and Init of the delta-h action
+                # (ActionGlacierEvolutionAreaScaling.cpp:9-68); only its Apply rule differs
+                area_scaling = isinstance(action, ActionGlacierEvolutionAreaScaling)
+                if have_tables:
+                    raise ValueError("only one glacier-evolution action per model")
+                have_tables = True
                 if action.land_cover != glacier:
                     raise ValueError(f"delta-h: land cover '{action.land_cover}' is not the glacier cover")
                 try:
@@ -591,7 +596,8 @@ class ModelHydro:
                     raise ValueError(f"The hydro unit {err} was not found") from err
                 eng.set_delta_h_tables(units, action.areas, action.volumes)
                 for k in _schedule.recursive_steps(self._mjd0, self._n_steps, action.month, 1, dt):
-                    events.append((k, order, lambda k=k: eng.add_delta_h_update(k)))
+                    events.append((k, order, (lambda k=k: eng.add_area_scaling_update(k)) if area_scaling
+                                   else (lambda k=k: eng.add_delta_h_update(k))))
             elif isinstance(action, ActionLandCoverChange):
                 for date, unit_id, cover, area in action.changes:
                     sporadic.append((date, order, unit_id, cover, area))

@@ -1350,14 +1350,18 @@ class ModelHydro {
             double area;
         };
         vector<Sp> sporadic;
+        bool haveTables = false;
         for (int order = 0; order < (int)_actions.size(); ++order) {
             Action* a = _actions[order];
             if (auto* s2i = dynamic_cast<ActionGlacierSnowToIceTransformation*>(a)) {
                 if (s2i->cover != _c->glacierName) throw std::invalid_argument("snow-to-ice: land cover is not the glacier cover");
                 for (int k : recursiveSteps(_mjd0, _nSteps, s2i->month, s2i->day, _dt)) events.push_back({k, order, 1, -1, 0});
-            } else if (dynamic_cast<ActionGlacierEvolutionAreaScaling*>(a)) {
-                throw std::invalid_argument("ActionGlacierEvolutionAreaScaling is not available in the B200 engine");
             } else if (auto* dh = dynamic_cast<ActionGlacierEvolutionDeltaH*>(a)) {
+                // ActionGlacierEvolutionAreaScaling shares the lookup-table interface and Init of the delta-h action
+                // (…AreaScaling.cpp:9-68); only its Apply rule differs (event kind 3)
+                const bool areaScaling = dynamic_cast<ActionGlacierEvolutionAreaScaling*>(a) != nullptr;
+                if (haveTables) throw std::invalid_argument("only one glacier-evolution action per model");
+                haveTables = true;
                 if (dh->cover != _c->glacierName) throw std::invalid_argument("delta-h: land cover is not the glacier cover");
                 vector<int32_t> units;
                 for (int id : dh->unitIds) {
@@ -1366,7 +1370,8 @@ class ModelHydro {
                     units.push_back(it->second);
                 }
                 check(hbk_set_delta_h_tables(_e, (int)units.size(), units.data(), dh->rows, dh->areas.data(), dh->volumes.data()));
-                for (int k : recursiveSteps(_mjd0, _nSteps, dh->month, 1, _dt)) events.push_back({k, order, 2, -1, 0});
+                for (int k : recursiveSteps(_mjd0, _nSteps, dh->month, 1, _dt))
+                    events.push_back({k, order, areaScaling ? 3 : 2, -1, 0});
             } else if (auto* lc = dynamic_cast<ActionLandCoverChange*>(a)) {
                 for (auto& c : lc->changes) sporadic.push_back({c.date, order, c.unitId, c.cover, c.area});
             } else {
@@ -1393,6 +1398,8 @@ class ModelHydro {
                 check(hbk_add_land_cover_change(_e, ev.step, ev.unit, ev.value));
             } else if (ev.kind == 1) {
                 check(hbk_add_snow_to_ice(_e, ev.step));
+            } else if (ev.kind == 3) {
+                check(hbk_add_area_scaling_update(_e, ev.step));
             } else {
                 check(hbk_add_delta_h_update(_e, ev.step));
             }

@@ -716,6 +716,41 @@ __global__ void hbkActDeltaH(const ActArgs a, int n, const int* units, int nRows
     }
 }
 
+// ActionGlacierEvolutionAreaScaling::Apply (ActionGlacierEvolutionAreaScaling.cpp:75-123): one thread per
+// (parameter set, unit of the lookup table); the units are independent.
+__global__ void hbkActAreaScaling(const ActArgs a, int n, const int* units, int nRows, const double* areas,
+                                  const double* volumes) {
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= (long long)a.P * n) return;
+    const int p = (int)(idx / n), i = (int)(idx % n);
+    const int u = units[i];
+    const double f = a.frac[(size_t)a.P * a.U + (size_t)p * a.U + u];
+    if (nearlyZero(f, kPrecision)) return;
+    const double unitArea = a.hru[1 * a.ldu + u];
+    const double area = f * unitArea;
+    double& ice = stateAt(a, HBK_S_ICE, p, u);
+    const double iceVolume = area * ice;
+    if (nearlyZero(iceVolume, kPrecision)) {
+        changeGlacierFraction(a, p, u, 0.0);
+        return;
+    }
+    const double initialWE = volumes[i] * 900.0;  // _tableVolume.row(0) * constants::iceDensity
+    double retreat = (initialWE - iceVolume) / initialWE;
+    retreat = (0.0 < retreat) ? retreat : 0.0;
+    const double rowInc = 1.0 / (nRows - 1);
+    int row = (int)(retreat / rowInc);
+    row = min(row, nRows - 1);
+    const double newArea = areas[(size_t)row * n + i];
+    double fraction = newArea / unitArea;
+    if (nearlyZero(fraction, kPrecision)) {  // Action::CheckLandCoverAreaFraction (Action.cpp:71-91)
+        fraction = 0.0;
+    } else if (fabs(1 - fraction) <= kPrecision) {
+        fraction = 1.0;
+    }
+    changeGlacierFraction(a, p, u, fraction);
+    ice = iceVolume / newArea;  // +inf when the table's area is 0, as in the reference
+}
+
 // Sum, per parameter set, of the stale instantaneous-flux amounts of glacier bricks that are currently null (zero
 // area): they no longer deposit water, but FluxToBrickInstantaneous::GetRealAmount() still reports their last
 // amount to the sub-basin stores' constraint test (WaterContainer.cpp:98-101, Processor.cpp:258-260). One block
@@ -913,7 +948,7 @@ struct hbk_engine {
     bool unitsSet = false, ran = false;
     // dated actions
     struct Event {
-        int step, kind, unit;  // kind 0 land-cover change, 1 snow->ice, 2 delta-h
+        int step, kind, unit;  // kind 0 land-cover change, 1 snow->ice, 2 delta-h, 3 area scaling
         double value;
     };
     std::vector<Event> events;
@@ -1446,6 +1481,13 @@ int hbk_add_delta_h_update(hbk_engine* e, int32_t step) {
     return HBK_OK;
 }
 
+int hbk_add_area_scaling_update(hbk_engine* e, int32_t step) {
+    if (!e || step < 1) return HBK_E_ARG;
+    if (e->dhUnits == 0) return fail(e, HBK_E_STATE, "hbk_set_delta_h_tables has not been called");
+    e->events.push_back({step, 3, -1, 0.0});
+    return HBK_OK;
+}
+
 int hbk_set_delta_h_tables(hbk_engine* e, int32_t n, const int32_t* units, int32_t nRows, const double* areas,
                            const double* volumes) {
     if (!e || n <= 0 || !units || nRows < 2 || !areas || !volumes) return HBK_E_ARG;
@@ -1520,6 +1562,10 @@ static int applyEvents(hbk_engine* e, int step) {
             hbkActLandCoverChange<<<pBlocks, 128, 0, e->stream>>>(a, ev.unit, ev.value);
         } else if (ev.kind == 1) {
             hbkActSnowToIce<<<148 * 2, 256, 0, e->stream>>>(a);
+        } else if (ev.kind == 3) {
+            const long long n = (long long)e->P * e->dhUnits;
+            hbkActAreaScaling<<<(unsigned)((n + 127) / 128), 128, 0, e->stream>>>(a, e->dhUnits, e->dDhUnits, e->dhRows,
+                                                                                  e->dDhAreas, e->dDhVolumes);
         } else {
             hbkActDeltaH<<<pBlocks, 128, 0, e->stream>>>(a, e->dhUnits, e->dDhUnits, e->dhRows, e->dDhAreas, e->dDhVolumes,
                                                          e->dhInitialWE, e->dDhLastRow);

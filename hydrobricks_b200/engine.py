@@ -104,6 +104,7 @@ def load_library():
     L.hbk_add_snow_to_ice.argtypes = [vp, i32]
     L.hbk_set_delta_h_tables.argtypes = [vp, i32, ip, i32, dp, dp]
     L.hbk_add_delta_h_update.argtypes = [vp, i32]
+    L.hbk_add_area_scaling_update.argtypes = [vp, i32]
     L.hbk_run.argtypes = [vp]
     L.hbk_get_outlet.argtypes = [vp, i32, i32, dp]
     L.hbk_get_recorded.argtypes = [vp, i32, i32, dp]
@@ -253,6 +254,9 @@ class Engine:
 
     def add_delta_h_update(self, step):
         self._check(self.L.hbk_add_delta_h_update(self.h, int(step)))
+
+    def add_area_scaling_update(self, step):
+        self._check(self.L.hbk_add_area_scaling_update(self.h, int(step)))
 
     def run(self):
         self._check(self.L.hbk_run(self.h))

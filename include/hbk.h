@@ -173,6 +173,10 @@ int hbk_add_snow_to_ice(hbk_engine* e, int32_t step);
 int hbk_set_delta_h_tables(hbk_engine* e, int32_t n_units, const int32_t* units, int32_t n_rows, const double* areas,
                            const double* volumes);
 int hbk_add_delta_h_update(hbk_engine* e, int32_t step);
+/*  - area scaling: ActionGlacierEvolutionAreaScaling::Apply (…AreaScaling.cpp:75-123) on the SAME lookup tables and
+ *    Init as delta-h (hbk_set_delta_h_tables): every unit of the table follows its own column — retreat of its own
+ *    ice volume -> row -> new glacier area, ice w.e. rescaled to the new area. */
+int hbk_add_area_scaling_update(hbk_engine* e, int32_t step);
 
 /* ModelHydro::Reset + Run (ModelHydro.cpp:100-133, 183-193) for all parameter sets. */
 int hbk_run(hbk_engine* e);
