@@ -77,6 +77,10 @@ WORKLOADS = {
     # configs[2]: 1M HRUs (100 m grid) x 40 years, snow + glacier + soil + groundwater bricks, one parameter set
     "c3": dict(sets=1, units=1000000, timesteps=14610, glacier=True, soil=2, area=1.0e4,
                name="C3 synthetic distributed basin, 1M HRUs x 40 y, GSM-Socont"),
+    # configs[3]: glacierised Socont with delta-h glacier evolution and land-cover-change actions over 50 years: the
+    # run is cut into kernel launches at the action dates (49 October updates + 50 dated land-cover edits)
+    "c4": dict(sets=20000, units=50, timesteps=18262, glacier=True, soil=2, area=1.0e6, finite_ice=True, actions=True,
+               name="C4 glacierised Socont, delta-h evolution + land-cover changes, 50 y"),
     # configs[4]: solver sweep, 10k sets x 1k HRUs x 10 years
     "c5": dict(sets=10000, units=1000, timesteps=3653, glacier=False, soil=1, area=1.0e6,
                name="C5 solver sweep, 10k sets x 1k HRUs x 10 y"),
@@ -99,6 +103,59 @@ def parameter_sets(P, seed=44):
 SPATIAL = {"zref": 1250.0, "grad_t": -0.6, "grad_p": 0.05}
 
 
+def mjd_axis(T):
+    return np.arange(T, dtype=np.float64) + 44605.0  # 1981-01-01
+
+
+def c4_tables(units, rows=11):
+    """Synthetic delta-h lookup tables over the glacier units of `units` (basin order): 11 rows,
+    the lower units vanish first, 40..160 m of ice. Returns (unit positions, areas[rows x n] m2, volumes m3)."""
+    gl = [i for i, u in enumerate(units) if dict(u["land_covers"]).get("glacier", 0.0) > 0]
+    a0 = np.array([units[i]["area"] * dict(units[i]["land_covers"])["glacier"] for i in gl])
+    z = np.array([units[i]["elevation"] for i in gl])
+    rank = (z - z.min()) / max(z.max() - z.min(), 1.0)
+    thick0 = 40.0 + 120.0 * rank
+    areas = np.zeros((rows, len(gl)))
+    volumes = np.zeros((rows, len(gl)))
+    for r in range(rows):
+        x = r / (rows - 1)
+        keep = np.clip((1 + 0.6 * rank) * (1 - x) - 0.45 * (1 - rank) * x, 0, 1)
+        if r == rows - 1:
+            keep[:] = 0
+        areas[r] = a0 * keep
+        volumes[r] = areas[r] * thick0 * (1 - 0.7 * x)
+    areas[0] = a0
+    volumes[0] = a0 * thick0
+    return gl, areas, volumes
+
+
+def c4_changes(units, gl, areas, T):
+    """One dated land-cover edit per year (15 January): the glacier of one unit is set to a share of its initial area."""
+    out = []
+    for year in range(1, T // 365 + 1):
+        day = 365 * year + 14
+        if day >= T:
+            break
+        j = year % len(gl)
+        out.append((mjd_axis(1)[0] + day, units[gl[j]]["id"], float(areas[0][j] * max(0.2, 1.0 - 0.012 * year))))
+    return out
+
+
+def add_c4_actions(m, T):
+    """Registers the C4 actions on a set-up model through the reference's action classes; returns them (the model
+    holds non-owning pointers, ModelHydro::AddAction)."""
+    hb = m.backend
+    gl, areas, volumes = c4_tables(m.units)
+    dh = hb.ActionGlacierEvolutionDeltaH()
+    dh.add_lookup_tables(10, "glacier", np.array([m.units[i]["id"] for i in gl], dtype=np.int32), areas, volumes)
+    assert m.model.add_action(dh)
+    lc = hb.ActionLandCoverChange()
+    for date, unit_id, area in c4_changes(m.units, gl, areas, T):
+        lc.add_change(date, unit_id, "glacier", area)
+    assert m.model.add_action(lc)
+    return [dh, lc]
+
+
 def spatialise(units, precip, temp, pet):
     """forcing.py:1061-1113 in numpy: the pre-spatialised [T x U] arrays the reference core is given."""
     z = np.array([u["elevation"] for u in units])
@@ -109,8 +166,6 @@ def spatialise(units, precip, temp, pet):
     return p2, t2, e2
 
 
-def mjd_axis(T):
-    return np.arange(T, dtype=np.float64) + 44605.0  # 1981-01-01
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -337,10 +392,12 @@ def run_engine_arm(args):
 
     covers = ["ground", "glacier"] if wl["glacier"] else ["ground"]
     m = models.Socont(solver=args.solver, soil_storage_nb=wl["soil"], surface_runoff="socont_runoff",
-                      land_cover_names=covers, land_cover_types=covers)
+                      land_cover_names=covers, land_cover_types=covers,
+                      glacier_infinite_storage=not wl.get("finite_ice", False))
     end = END if T == T_DEFAULT else str(np.datetime64(START) + np.timedelta64(T - 1, "D"))
     m.setup(units, START, end, device=local)
     matrix = m.parameter_matrix(ps, P)
+    actions = add_c4_actions(m, T) if wl.get("actions") else []
     eng = m.engine(P)
     if unit_sharded:
         eng.set_unit_shard(parallel.basin_area(np.full(world * U, wl["area"])))
@@ -365,6 +422,14 @@ def run_engine_arm(args):
         eng.set_station_forcing("pet", pin_forcing[2].numpy())
 
     upload()
+    if actions:
+        # one run through the host's ModelHydro maps the action dates to time steps and registers them with the engine
+        # as kernel boundaries (ActionsManager::DateUpdate); the timed eng.run() calls below reuse that schedule
+        m.model.set_parameter_sets(matrix)
+        m.model.set_station_forcing("precipitation", precip, SPATIAL["zref"], SPATIAL["grad_p"], 1.0)
+        m.model.set_station_forcing("temperature", temp, SPATIAL["zref"], SPATIAL["grad_t"], 1.0)
+        m.model.set_station_forcing("pet", pet)
+        m.model.run()
     stream = torch.cuda.ExternalStream(eng.stream())
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
     scores_all = torch.empty(world * P, dtype=torch.float64, device="cuda") if world > 1 else None

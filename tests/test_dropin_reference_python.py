@@ -31,6 +31,7 @@ def _structure(backend, **kw):
 
 
 @pytest.mark.parametrize("kw", [
+    dict(soil_storage_nb=1, record_all=True),  # the reference layer's default solver: crank_nicolson (model.py:80)
     dict(solver="rk4", soil_storage_nb=1, surface_runoff="socont_runoff", record_all=True),
     dict(solver="heun_explicit", soil_storage_nb=2, surface_runoff="linear_storage", record_all=False),
     dict(solver="rk4", soil_storage_nb=2, land_cover_names=["ground", "glacier"], land_cover_types=["ground", "glacier"],
