@@ -229,6 +229,13 @@ class Socont:
                 m[:, slot] = np.asarray(values, dtype=np.float32)
         return m
 
+    def run_sets(self, matrix):
+        """Integrate the parameter sets [n_sets x HBK_N_PARAMS] in one launch and leave the outlet on the device
+        (evaluate_batch scores it there; get_outlet_discharge_batch fetches it)."""
+        self._last_batch = len(matrix)
+        self.model.set_parameter_sets(matrix)
+        self.model.run()
+
     def run_batch(self, matrix):
         self._last_batch = len(matrix)
         return self.model.run_batch(matrix)

@@ -1,0 +1,88 @@
+"""Host logic of the calibration bridge (hydrobricks_b200/trainer.py) on CPU: the batched restatement of
+SpotpySetup.parameters() / simulation() / objectivefunction() (reference trainer.py:934-1141)."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from hydrobricks_b200 import trainer
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_sample_respects_ranges_and_constraints():
+    space = trainer.ParameterSpace.for_socont(["a_snow", "a_ice", "k_slow_1", "k_slow_2", "k_quick", "A"])
+    v = space.sample(5000, np.random.default_rng(1))
+    assert set(v) == set(space.names) and all(len(x) == 5000 for x in v.values())
+    assert (v["a_snow"] < v["a_ice"]).all()  # models/socont.py:280-285
+    assert (v["k_slow_2"] < v["k_slow_1"]).all() and (v["k_slow_1"] < v["k_quick"]).all()
+    for name, (lo, hi) in space.ranges.items():
+        assert (v[name] >= lo).all() and (v[name] <= hi).all()
+    assert space.satisfied(v).all()
+    # constraints on parameters that are not part of the space are ignored (parameters.py:1089-1091)
+    only = trainer.ParameterSpace.for_socont(["a_snow", "A"])
+    assert only.satisfied(only.sample(100, np.random.default_rng(2))).all()
+
+
+def test_sampler_gives_up_like_the_reference():
+    space = trainer.ParameterSpace({"x": (0.0, 1.0), "y": (2.0, 3.0)}, [("x", ">", "y")])
+    with pytest.raises(RuntimeError, match="constraints could not be satisfied"):
+        space.sample(10, np.random.default_rng(0), max_attempts=20)
+    with pytest.raises(ValueError):
+        trainer.ParameterSpace({"x": (1.0, 0.0)})
+    with pytest.raises(ValueError):
+        trainer.ParameterSpace({"x": (0.0, 1.0)}, [("x", "~", "x")])
+
+
+class _FakeModel:
+    """Stands in for models.Socont: the 'outlet' of a set is its parameter x repeated, the score 1 - (x - 0.3)^2."""
+
+    def __init__(self):
+        self.runs = []
+
+    def parameter_matrix(self, sets, n):
+        assert all(len(np.atleast_1d(v)) == n for v in sets.values())
+        return np.column_stack([np.asarray(sets["x"], dtype=np.float32), np.asarray(sets["y"], dtype=np.float32)])
+
+    def run_sets(self, matrix):
+        self.runs.append(len(matrix))
+        self._m = matrix
+
+    def evaluate_batch(self, metric, obs, warmup):
+        return 1.0 - (self._m[:, 0].astype(np.float64) - 0.3) ** 2
+
+
+def test_monte_carlo_batches_scores_and_best():
+    space = trainer.ParameterSpace({"x": (0.0, 1.0), "y": (0.0, 1.0)}, [("x", "<", "y")])
+    model = _FakeModel()
+    mc = trainer.BatchedMonteCarlo(model, space, np.zeros(10), warmup=2, objective="nse")
+    best, score = mc.run(1000, batch=300, seed=3)
+    assert model.runs == [300, 300, 300, 100]  # one launch per batch
+    assert len(mc.scores) == 1000 and all(len(v) == 1000 for v in mc.parameters.values())
+    assert abs(best["x"] - 0.3) < 0.02 and score == mc.scores.max() and best["x"] < best["y"]
+    # rejected sets are not run and get the worst score (trainer.py:1007-1020, 1101-1108)
+    s = mc.evaluate({"x": np.array([0.2, 0.9, 0.1, 1.5]), "y": np.array([0.5, 0.1, 0.4, 2.0])})
+    assert model.runs[-1] == 2 and np.isneginf(s[[1, 3]]).all() and np.isfinite(s[[0, 2]]).all()
+    with pytest.raises(ValueError):
+        trainer.BatchedMonteCarlo(model, space, np.zeros(10), objective="rmse")
+
+
+@pytest.mark.skipif(not Path("/root/reference/python/src/hydrobricks").exists(), reason="reference sources not available")
+def test_space_from_the_reference_parameter_set():
+    """The reference's own ParameterSet (ranges, aliases, constraints of hb.models.Socont) feeds the batched sampler."""
+    sys.path.insert(0, str(ROOT / "tools"))
+    import refpy
+
+    refpy.load_reference_python("b200")
+    import hydrobricks.models as models
+
+    socont = models.Socont(soil_storage_nb=2, solver="rk4")
+    ps = socont.generate_parameters()
+    space = trainer.ParameterSpace.from_parameter_set(ps, ["a_snow", "A", "k_slow_1", "k_slow_2", "percol", "beta"])
+    assert space.ranges["A"] == (0.0, 3000.0) and space.ranges["beta"] == (100.0, 30000.0)
+    assert space.ranges["a_snow"] == (2.0, 20.0) and space.ranges["percol"] == (0.0, 10.0)
+    v = space.sample(2000, np.random.default_rng(5))
+    assert (v["k_slow_2"] < v["k_slow_1"]).all()
+    for name in space.names:
+        assert trainer.SOCONT_RANGES[name] == space.ranges[name]
