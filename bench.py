@@ -569,9 +569,10 @@ def run_engine_arm(args):
 
     if rank == 0:
         main_ms = kern_ms / args.steps  # device time of one hbk_run (state reset + unit kernel), CUDA events
-        flops_unit = FP64_FLOPS_PER_HRU_STEP[args.solver]
-        flops = flops_unit * P * U * T
-        achieved = flops / (main_ms * 1e-3) / 1e12
+        # the sequential solvers (bisection / exponential / analytic schemes) have no algorithmic flop figure: their
+        # work depends on the number of halvings; the roofline fraction is reported for the explicit solvers only
+        flops_unit = FP64_FLOPS_PER_HRU_STEP.get(args.solver)
+        achieved = flops_unit * P * U * T / (main_ms * 1e-3) / 1e12 if flops_unit else None
         hbm_bytes = P * T * 8 + 3 * T * 8 + P * hbk_engine.N_PARAMS * 4
         try:
             hbm_peak = json.load(open(ROOT / "MEASURED_PEAKS.json"))["hbm_gbs"]
@@ -615,7 +616,7 @@ def run_engine_arm(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_fp64, "unit": "TFLOP/s",
-                         "frac": achieved / peak_fp64 if peak_fp64 else None, "traffic": traffic,
+                         "frac": achieved / peak_fp64 if (peak_fp64 and achieved) else None, "traffic": traffic,
                          "traffic_note": "DRAM bytes per launch from ncu (profiles/r01k_traffic.json); algorithmic "
                                          "bytes are in roofline.hbm; the excess is the unit state of the "
                                          "time-multiplexed tiles passing through L2/HBM (<3 % of HBM bandwidth)",
@@ -644,7 +645,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--solver", default="rk4", choices=["rk4", "heun_explicit", "euler_explicit"])
+    ap.add_argument("--solver", default="rk4", choices=["rk4", "heun_explicit", "euler_explicit", "crank_nicolson",
+                                                        "implicit_euler", "exponential_euler", "analytic_linear"])
     ap.add_argument("--sets", type=int, default=None, help="parameter sets per GPU")
     ap.add_argument("--units", type=int, default=None)
     ap.add_argument("--timesteps", type=int, default=None)
