@@ -5,9 +5,9 @@
 // arithmetic keeps the reference's operation order and its float32-parameter promotions, so that on
 // the same compiler flags it reproduces the compiled reference (oracle/_ref) bit for bit.
 //
-// Parity status: PINNED (tests/test_oracle_kat.py: SolverTest / ModelSocontTest known-answer vectors;
-// tests/test_oracle_vs_ref.py: bit-exact against oracle/_ref where that library is present;
-// tests/golden/*.npz: vectors generated from the reference by tools/make_goldens.py).
+// Parity status: PINNED (tests/test_oracle_golden.py: SolverTest / ModelSocontTest known-answer vectors and
+// tests/golden/*.npz, vectors generated from the reference by tools/make_goldens.py, bit-exact;
+// tests/test_oracle_vs_ref.py: bit-exact against oracle/_ref where that library and /root/reference are present).
 #include "hb_oracle.h"
 
 #include <algorithm>

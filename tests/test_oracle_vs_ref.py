@@ -1,0 +1,59 @@
+"""Live pinning of the oracle restatement against the compiled, UNMODIFIED reference core (oracle/_ref), in the build
+container only (needs /root/reference for the reference's Python layer and its bundled meteo files): the same cases
+tools/ref_cases.py and tools/ref_actions_case.py sweep in full, here a subset that runs in seconds. Bit-exact: outlet
+discharge and every recorded series."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "tools"))
+
+pytestmark = pytest.mark.skipif(not Path("/root/reference/python/src/hydrobricks").exists() or
+                                not list((ROOT / "oracle" / "_ref").glob("_hydrobricks*.so")),
+                                reason="reference sources / compiled reference not available")
+
+
+@pytest.mark.parametrize("solver, kw", [
+    ("rk4", dict(soil_storage_nb=2, with_glacier=True)),
+    ("crank_nicolson", dict(soil_storage_nb=2, with_glacier=True, infinite_storage=False)),
+    ("implicit_euler", dict(soil_storage_nb=1, with_glacier=False)),
+    ("exponential_euler", dict(soil_storage_nb=1, with_glacier=True, surface_runoff="linear_storage")),
+    ("analytic_linear", dict(soil_storage_nb=2, with_glacier=True, snow_sublimation_process="sublimation:pet")),
+])
+def test_oracle_bit_exact_against_compiled_reference(solver, kw):
+    import ref_cases
+    import refpy
+    from oracle import hb_oracle
+
+    hb = refpy.load_reference_python("ref")
+    model, hu, forcing, _ = ref_cases.gsm_socont(hb, solver=solver, end_date="1982-06-30", n_units=8, **kw)
+    structures, units, fdata, q_ref, rec_ref = ref_cases.collect(model, hu, forcing)
+    om = hb_oracle.OracleModel(structures, units, solver, len(q_ref))
+    for k, v in fdata.items():
+        om.set_forcing(k, v)
+    for label in rec_ref:
+        om.record(label)
+    q = om.run()
+    assert np.array_equal(q, q_ref)
+    for label, ref in rec_ref.items():
+        assert np.array_equal(om.records[label], ref, equal_nan=True), label
+
+
+@pytest.mark.parametrize("solver, flags, area_scaling", [
+    ("rk4", (True, True, True), True),
+    ("crank_nicolson", (True, True, False), False),
+])
+def test_oracle_actions_bit_exact_against_compiled_reference(solver, flags, area_scaling):
+    import ref_actions_case as rc
+    import refpy
+
+    ref = refpy.load_extension("ref")
+    ref.init()
+    meta, forcing, q, rec, _, areas, volumes = rc.run_reference(ref, solver, *flags, area_scaling=area_scaling)
+    om = rc.run_oracle(meta, forcing, areas, volumes, list(rec))
+    assert np.array_equal(om.outlet, q)
+    for label in rec:
+        assert np.array_equal(om.records[label], rec[label], equal_nan=True), label
