@@ -1,0 +1,122 @@
+"""The arithmetic of the CUDA kernels on the CPU: hydrobricks_b200/csrc/hbk_device.cuh — the same source the kernels
+are built from — compiled by g++ with -DHBK_HOST_EMULATION (tests/host_emul) and run over every golden case of the
+reference (tests/golden, one parameter set, all solvers incl. the sequential family, glacier / snow-ice / sublimation
+options), at the GPU parity bar: 1e-10 relative + 1e-12 mm on the outlet discharge and on recorded storages.
+
+What this covers is the per-(set, unit) step functions (directPhase, solveUnit, solveUnitSequential, basinStoreStep,
+the constraint sweep, the rate laws); the kernel plumbing around them is only exercised by the `-m gpu` tests. It makes
+a change to the device arithmetic checkable without a GPU box."""
+import ctypes
+import math
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import golden_utils as gu
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent
+EMUL = HERE / "host_emul"
+RTOL, ATOL = 1e-10, 1e-12
+CASES = [b for b in gu.bundles() if not b.startswith(("c1_", "kat_linear", "actions_"))]
+
+
+@pytest.fixture(scope="module")
+def emul():
+    lib = EMUL / "libhbkemul.so"
+    srcs = [EMUL / "hbk_host_emul.cpp", EMUL / "hbk_host_shims.h", ROOT / "hydrobricks_b200" / "csrc" / "hbk_device.cuh",
+            ROOT / "include" / "hbk.h"]
+    if not lib.exists() or lib.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-DHBK_HOST_EMULATION",
+                               f"-I{EMUL}", "-o", str(lib), str(EMUL / "hbk_host_emul.cpp")])
+    L = ctypes.CDLL(str(lib))
+    dp, fp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)
+    L.hbk_emul_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, dp, fp, ip, dp, dp, fp, dp, dp, dp, dp, dp, dp,
+                               dp, dp, ctypes.POINTER(ctypes.c_longlong)]
+    return L
+
+
+def _day_of_year(mjd):
+    d = np.datetime64("1858-11-17") + np.timedelta64(int(math.floor(mjd)), "D")
+    return int((d - d.astype("datetime64[Y]")).astype(int)) + 1
+
+
+def _close(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    assert np.array_equal(np.isnan(a), np.isnan(b)), "NaN pattern differs"
+    ok = np.isnan(b) | (np.abs(a - b) <= RTOL * np.abs(b) + ATOL)
+    if not ok.all():
+        i = int(np.argmax(~ok))
+        raise AssertionError(f"{(~ok).sum()} values differ; first at {np.unravel_index(i, a.shape)}: "
+                             f"{a.flat[i]!r} vs {b.flat[i]!r}")
+
+
+def run_emul(L, meta, forcing, solver=None, dt=1.0):
+    from hydrobricks_b200 import engine as _e
+    from hydrobricks_b200 import structure
+
+    cs = structure.CompiledStructure(meta["structures"], solver or meta["solver"], dt)
+    units = meta["units"]
+    U, T = len(units), len(next(iter(forcing.values())))
+    area = np.array([u["area"] for u in units], dtype=np.float64)
+    slope = None
+    if cs.hbk.quick_kind == _e.QUICK_SOCONT:
+        slope = np.array([structure.slope_m_per_m(*u["slope"]) for u in units], dtype=np.float32)
+    covers = [u["land_covers"] for u in units]
+    gv = np.array(cs.assign_structure_variants(covers), dtype=np.int32)
+    fg = np.array([dict(c).get(cs.ground_name, 1.0) for c in covers], dtype=np.float64)
+    fgl = np.array([dict(c).get(cs.glacier_name, 0.0) if cs.glacier_name else 0.0 for c in covers], dtype=np.float64)
+    params = np.ascontiguousarray(cs.parameter_vector(), dtype=np.float32)
+    f = {("precipitation" if k in ("p", "precipitation") else "temperature" if k in ("t", "temperature") else "pet"):
+         np.ascontiguousarray(v, dtype=np.float64) for k, v in forcing.items()}
+    swat = None
+    if cs.hbk.has_glacier and cs.hbk.snow_ice_kind == _e.SNOW_ICE_SWAT:
+        # hbk_engine_create: 1 + sin(2 pi (doy - ref) / 365), ProcessTransformSnowToIceSwat.cpp:31-39
+        ref_day = 81 if cs.hbk.north_hemisphere else 264
+        pi = 3.1415926535897932384626433832795
+        swat = np.array([1 + math.sin(2.0 * pi * (_day_of_year(cs.hbk.start_mjd + t * dt) - ref_day) / 365.0)
+                         for t in range(T)], dtype=np.float64)
+    dp, fp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)
+    ptr = lambda a, t: None if a is None else a.ctypes.data_as(t)  # noqa: E731
+    outlet = np.empty(T)
+    rec = {k: np.empty((T, U)) for k in ("slow", "snow", "ice")}
+    unconv = ctypes.c_longlong(0)
+    err = L.hbk_emul_run(ctypes.addressof(cs.hbk), U, T, ptr(area, dp), ptr(slope, fp), ptr(gv, ip), ptr(fg, dp),
+                         ptr(fgl, dp), ptr(params, fp), ptr(f["precipitation"], dp), ptr(f["temperature"], dp),
+                         ptr(f["pet"], dp), ptr(swat, dp), ptr(outlet, dp), ptr(rec["slow"], dp), ptr(rec["snow"], dp),
+                         ptr(rec["ice"], dp), ctypes.byref(unconv))
+    assert err & 1 == 0, "a change rate exceeded 10000"
+    return cs, outlet, rec, unconv.value
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_device_arithmetic_on_host_matches_reference(name, emul):
+    meta, forcing, outlet, records, _ = gu.load(name)
+    cs, q, rec, _ = run_emul(emul, meta, forcing)
+    _close(q, outlet)
+    _close(rec["slow"], records["slow_reservoir:water_content"])
+    snow_label = f"{cs.ground_name}_snowpack:snow_content"
+    if snow_label in records:
+        _close(rec["snow"], records[snow_label])
+    if cs.glacier_name and f"{cs.glacier_name}:ice_content" in records and not cs.hbk.glacier_infinite_storage:
+        _close(rec["ice"], records[f"{cs.glacier_name}:ice_content"])
+
+
+@pytest.mark.parametrize("solver", ["rk4", "heun_explicit", "euler_explicit", "crank_nicolson", "implicit_euler",
+                                    "exponential_euler", "analytic_linear"])
+def test_device_arithmetic_on_host_two_day_step(solver, emul):
+    """A time step other than one day, every solver, against the oracle restatement built with the same dt."""
+    from oracle import hb_oracle
+
+    meta, forcing, _, _, _ = gu.load("gsm_socont_rk4_glacier_2store")
+    n = 500
+    forcing = {k: np.ascontiguousarray(v[:n]) for k, v in forcing.items()}
+    _, q, rec, _ = run_emul(emul, meta, forcing, solver=solver, dt=2.0)
+    om = hb_oracle.OracleModel(meta["structures"], meta["units"], solver, n, dt=2.0)
+    for k, v in forcing.items():
+        om.set_forcing(k, v)
+    om.record("slow_reservoir:water_content")
+    _close(q, om.run())
+    _close(rec["slow"], om.records["slow_reservoir:water_content"])
