@@ -82,12 +82,77 @@ class LogNull:
     pass
 
 
+class ParameterModifierType:
+    """base/ParameterModifier.h: what the modifier's values are indexed by."""
+    Yearly, Monthly, Dates = "Yearly", "Monthly", "Dates"
+
+
+class ParameterModifier:
+    """base/ParameterModifier.cpp: a parameter value looked up by the year, the month or the exact date of a modified
+    Julian date (NaN when the date has no entry). A standalone object, as in the reference's binding
+    (Binding.cpp:284-303): nothing attaches it to a running model, time-varying parameters inside a run are out of
+    scope."""
+
+    def __init__(self, type=ParameterModifierType.Yearly):  # noqa: A002 (the binding's argument name)
+        self._type, self._dates, self._values = type, [], []
+
+    def set_type(self, type):  # noqa: A002
+        self._type = type
+
+    def get_type(self):
+        return self._type
+
+    def _require(self, wanted, method):
+        if self._type != wanted:
+            raise RuntimeError(f"ParameterModifier::{method} - Modifier type is not {wanted}.")
+
+    def set_yearly_values(self, year_start, year_end, values):
+        self._require(ParameterModifierType.Yearly, "SetYearlyValues")
+        self._values = [float(np.float32(v)) for v in values]
+        self._dates = [float(y) for y in range(int(year_start), int(year_end) + 1)]
+        return len(self._values) == len(self._dates)
+
+    def set_monthly_values(self, values):
+        self._require(ParameterModifierType.Monthly, "SetMonthlyValues")
+        self._values = [float(np.float32(v)) for v in values]
+        self._dates = []
+        return len(self._values) == 12
+
+    def set_dates_and_values(self, dates, values):
+        self._require(ParameterModifierType.Dates, "SetDatesAndValues")
+        self._dates = [float(d) for d in dates]
+        self._values = [float(np.float32(v)) for v in values]
+        return len(self._values) == len(self._dates)
+
+    def update_value(self, date):
+        day = np.datetime64("1858-11-17") + np.timedelta64(int(np.floor(date)), "D")
+        year = int(str(day)[:4])
+        month = int(str(day)[5:7])
+        if self._type == ParameterModifierType.Monthly:
+            return self._values[month - 1] if len(self._values) == 12 else float("nan")
+        key = float(year) if self._type == ParameterModifierType.Yearly else float(date)
+        for d, v in zip(self._dates, self._values):
+            if d == key:
+                return v
+        return float("nan")
+
+    def updates_on_year_change(self):
+        return self._type == ParameterModifierType.Yearly
+
+    def updates_on_month_change(self):
+        return self._type == ParameterModifierType.Monthly
+
+    def updates_on_date_change(self):
+        return self._type == ParameterModifierType.Dates
+
+
 class Parameter:
-    """base/Parameter.h: name + float32 value."""
+    """base/Parameter.h, Parameter.cpp: name + float32 value + optional modifier."""
 
     def __init__(self, name, value):
         self.name = name
         self.value = float(np.float32(value))
+        self._modifier = None
 
     def get_name(self):
         return self.name
@@ -100,6 +165,21 @@ class Parameter:
 
     def set_value(self, value):
         self.value = float(np.float32(value))
+
+    def set_modifier(self, modifier):
+        self._modifier = modifier
+
+    def has_modifier(self):
+        return self._modifier is not None
+
+    def update_from_modifier(self, date):
+        if self._modifier is None:
+            return False
+        value = self._modifier.update_value(date)
+        if value != value:  # NaN: no entry for this date
+            return False
+        self.value = value
+        return True
 
     def __repr__(self):
         return f"<_hydrobricks.Parameter named '{self.name}'>"
@@ -853,13 +933,6 @@ class ActionGlacierEvolutionDeltaH(Action):
 class ActionGlacierEvolutionAreaScaling(ActionGlacierEvolutionDeltaH):
     """Same table interface as the delta-h action (ActionGlacierEvolutionAreaScaling.h:23-24); its Apply rule is
     outside the engine's scope and ModelHydro.run() refuses it."""
-
-
-class ParameterModifier:
-    """Time-varying parameters (base/ParameterModifier.h) are outside the engine's scope."""
-
-    def __init__(self, *a, **k):
-        raise RuntimeError("ParameterModifier (time-varying parameters) is not available in the B200 engine.")
 
 
 class ActionGlacierSnowToIceTransformation(Action):

@@ -150,6 +150,51 @@ PYBIND11_MODULE(_hydrobricks, m) {
         .def("get_lateral_connection_count", &hb::SettingsBasin::GetLateralConnectionCount)
         .def("clear", &hb::SettingsBasin::Clear);
 
+    py::class_<hb::Parameter>(m, "Parameter")
+        .def(py::init<const std::string&, float>())
+        .def_readwrite("name", &hb::Parameter::name)
+        .def_readwrite("value", &hb::Parameter::value)
+        .def("get_name", [](hb::Parameter& p) { return p.name; })
+        .def("set_name", [](hb::Parameter& p, const std::string& n) { p.name = n; })
+        .def("get_value", [](hb::Parameter& p) { return p.value; })
+        .def("set_value", [](hb::Parameter& p, float v) { p.value = v; })
+        .def("set_modifier", &hb::Parameter::SetModifier, "modifier"_a)
+        .def("has_modifier", [](hb::Parameter& p) { return p.hasModifier; })
+        .def("update_from_modifier", &hb::Parameter::UpdateFromModifier, "date"_a)
+        .def("__repr__", [](const hb::Parameter& p) { return "<_hydrobricks.Parameter named '" + p.name + "'>"; });
+
+    py::enum_<hb::ParameterModifierType>(m, "ParameterModifierType")
+        .value("Yearly", hb::ParameterModifierType::Yearly)
+        .value("Monthly", hb::ParameterModifierType::Monthly)
+        .value("Dates", hb::ParameterModifierType::Dates);
+
+    py::class_<hb::ParameterModifier>(m, "ParameterModifier")
+        .def(py::init<>())
+        .def(py::init<hb::ParameterModifierType>(), "type"_a)
+        .def("set_type", [](hb::ParameterModifier& p, hb::ParameterModifierType t) { p.type = t; }, "type"_a)
+        .def("get_type", [](hb::ParameterModifier& p) { return p.type; })
+        .def("set_yearly_values", &hb::ParameterModifier::SetYearlyValues, "year_start"_a, "year_end"_a, "values"_a)
+        .def("set_monthly_values", &hb::ParameterModifier::SetMonthlyValues, "values"_a)
+        .def("set_dates_and_values", &hb::ParameterModifier::SetDatesAndValues, "dates"_a, "values"_a)
+        .def("update_value", &hb::ParameterModifier::UpdateValue, "date"_a)
+        .def("updates_on_year_change", &hb::ParameterModifier::UpdatesOnYearChange)
+        .def("updates_on_month_change", &hb::ParameterModifier::UpdatesOnMonthChange)
+        .def("updates_on_date_change", &hb::ParameterModifier::UpdatesOnDateChange);
+
+    py::class_<hb::TimeSeries>(m, "TimeSeries")
+        .def_static("create",
+                    [](const std::string& name, const f64arr& time, const i32arr& ids, const f64arr& data) {
+                        if (data.ndim() != 2 || data.shape(0) != time.size() || data.shape(1) != ids.size())
+                            throw py::value_error("TimeSeries.create: data must be [len(time) x len(ids)]");
+                        hb::TimeSeries ts;
+                        ts.name = name;
+                        ts.time.assign(time.data(), time.data() + time.size());
+                        ts.ids.assign(ids.data(), ids.data() + ids.size());
+                        ts.data.assign(data.data(), data.data() + data.size());
+                        return ts;
+                    },
+                    "data_name"_a, "time"_a, "ids"_a, "data"_a);
+
     py::class_<hb::Action>(m, "Action").def(py::init<>());
     py::class_<hb::ActionLandCoverChange, hb::Action>(m, "ActionLandCoverChange")
         .def(py::init<>())
@@ -200,6 +245,7 @@ PYBIND11_MODULE(_hydrobricks, m) {
                  return mh.CreateTimeSeries(name, time.data(), (int)time.size(), ids.data(), (int)ids.size(), data.data());
              },
              "data_name"_a, "time"_a, "ids"_a, "data"_a)
+        .def("add_time_series", &hb::ModelHydro::AddTimeSeries, "time_series"_a)
         .def("clear_time_series", &hb::ModelHydro::ClearTimeSeries)
         .def("attach_time_series_to_hydro_units", &hb::ModelHydro::AttachTimeSeriesToHydroUnits)
         .def("forcing_loaded", &hb::ModelHydro::ForcingLoaded)

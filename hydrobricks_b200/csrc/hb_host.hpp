@@ -1047,6 +1047,95 @@ inline double checkFraction(double f) {  // Action::CheckLandCoverAreaFraction (
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Standalone value classes of the binding surface (Binding.cpp:270-306). The reference exposes them but its Python
+// layer never attaches a modifier to a running model (nothing adds parameters to ModelHydro's ParametersUpdater), so
+// here too they are plain objects: time-varying parameters inside a run stay out of scope.
+enum class ParameterModifierType { Yearly, Monthly, Dates };
+
+// base/ParameterModifier.cpp: value looked up by the year (Yearly), the month (Monthly) or the exact date (Dates)
+// of a modified Julian date; NaN when the date has no entry.
+struct ParameterModifier {
+    ParameterModifierType type = ParameterModifierType::Yearly;
+    vector<double> dates;
+    vector<float> values;
+    ParameterModifier() = default;
+    explicit ParameterModifier(ParameterModifierType t) : type(t) {}
+    bool SetYearlyValues(int yearStart, int yearEnd, const vector<float>& v) {
+        if (type != ParameterModifierType::Yearly) throw std::runtime_error("ParameterModifier::SetYearlyValues - Modifier type is not Yearly.");
+        values = v;
+        dates.clear();
+        for (int y = yearStart; y <= yearEnd; ++y) dates.push_back((double)y);
+        return values.size() == dates.size();
+    }
+    bool SetMonthlyValues(const vector<float>& v) {
+        if (type != ParameterModifierType::Monthly) throw std::runtime_error("ParameterModifier::SetMonthlyValues - Modifier type is not Monthly.");
+        values = v;
+        dates.clear();
+        return values.size() == 12;
+    }
+    bool SetDatesAndValues(const vector<double>& d, const vector<float>& v) {
+        if (type != ParameterModifierType::Dates) throw std::runtime_error("ParameterModifier::SetDatesAndValues - Modifier type is not Dates.");
+        dates = d;
+        values = v;
+        return values.size() == dates.size();
+    }
+    // Utils.cpp FindT with tolerance 0: index of the entry equal to `value`, -1 otherwise
+    int find(double value) const {
+        for (size_t i = 0; i < dates.size() && i < values.size(); ++i)
+            if (dates[i] == value) return (int)i;
+        return -1;
+    }
+    float UpdateValue(double mjd) const {
+        const float nan = std::numeric_limits<float>::quiet_NaN();
+        int y;
+        unsigned m, d;
+        civilFromDays((long)std::floor(mjd) + kMjdEpochUnixDays, y, m, d);
+        switch (type) {
+            case ParameterModifierType::Yearly: {
+                const int i = find((double)y);
+                return i < 0 ? nan : values[i];
+            }
+            case ParameterModifierType::Monthly: return values.size() == 12 ? values[m - 1] : nan;
+            default: {
+                const int i = find(mjd);
+                return i < 0 ? nan : values[i];
+            }
+        }
+    }
+    bool UpdatesOnYearChange() const { return type == ParameterModifierType::Yearly; }
+    bool UpdatesOnMonthChange() const { return type == ParameterModifierType::Monthly; }
+    bool UpdatesOnDateChange() const { return type == ParameterModifierType::Dates; }
+};
+
+// base/Parameter.h / Parameter.cpp: name + float32 value + optional modifier.
+struct Parameter {
+    string name;
+    float value;
+    ParameterModifier modifier;
+    bool hasModifier = false;
+    Parameter(const string& n, float v) : name(n), value(v) {}
+    void SetModifier(const ParameterModifier& m) {
+        modifier = m;
+        hasModifier = true;
+    }
+    bool UpdateFromModifier(double mjd) {
+        if (!hasModifier) return false;
+        const float v = modifier.UpdateValue(mjd);
+        if (std::isnan(v)) return false;
+        value = v;
+        return true;
+    }
+};
+
+// base/TimeSeries.cpp (TimeSeries::Create): a named [time x ids] block handed to ModelHydro::AddTimeSeries.
+struct TimeSeries {
+    string name;
+    vector<double> time;
+    vector<int> ids;
+    vector<double> data;  // [time][ids]
+};
+
+// ---------------------------------------------------------------------------------------------------------
 struct Action {
     virtual ~Action() = default;
 };
@@ -1170,6 +1259,9 @@ class ModelHydro {
         s.data.assign(data, data + (size_t)nTime * nIds);
         _series[var] = std::move(s);
         return true;
+    }
+    bool AddTimeSeries(const TimeSeries& ts) {  // ModelHydro::AddTimeSeries (ModelHydro.cpp:296-304)
+        return CreateTimeSeries(ts.name, ts.time.data(), (int)ts.time.size(), ts.ids.data(), (int)ts.ids.size(), ts.data.data());
     }
     void ClearTimeSeries() {
         _series.clear();

@@ -287,7 +287,30 @@ PYBIND11_MODULE(_hydrobricks, m) {
         .def("get_name", &Parameter::GetName)
         .def("set_name", &Parameter::SetName)
         .def("get_value", &Parameter::GetValue)
-        .def("set_value", &Parameter::SetValue);
+        .def("set_value", &Parameter::SetValue)
+        .def("set_modifier", &Parameter::SetModifier, "modifier"_a)
+        .def("has_modifier", &Parameter::HasModifier)
+        .def("update_from_modifier", &Parameter::UpdateFromModifier, "date"_a)
+        .def("__repr__", [](const Parameter& a) { return "<_hydrobricks.Parameter named '" + a.GetName() + "'>"; });
+
+    py::enum_<ParameterModifierType>(m, "ParameterModifierType")
+        .value("Yearly", ParameterModifierType::Yearly)
+        .value("Monthly", ParameterModifierType::Monthly)
+        .value("Dates", ParameterModifierType::Dates);
+
+    py::class_<ParameterModifier>(m, "ParameterModifier")
+        .def(py::init<>())
+        .def(py::init<ParameterModifierType>(), "type"_a)
+        .def("set_type", &ParameterModifier::SetType, "type"_a)
+        .def("get_type", &ParameterModifier::GetType)
+        .def("set_yearly_values", py::overload_cast<int, int, const vecFloat&>(&ParameterModifier::SetYearlyValues),
+             "year_start"_a, "year_end"_a, "values"_a)
+        .def("set_monthly_values", py::overload_cast<const vecFloat&>(&ParameterModifier::SetMonthlyValues), "values"_a)
+        .def("set_dates_and_values", &ParameterModifier::SetDatesAndValues, "dates"_a, "values"_a)
+        .def("update_value", &ParameterModifier::UpdateValue, "date"_a)
+        .def("updates_on_year_change", &ParameterModifier::UpdatesOnYearChange)
+        .def("updates_on_month_change", &ParameterModifier::UpdatesOnMonthChange)
+        .def("updates_on_date_change", &ParameterModifier::UpdatesOnDateChange);
 
     py::class_<TimeSeries>(m, "TimeSeries")
         .def_static(

@@ -1,0 +1,103 @@
+"""Parameter / ParameterModifier / TimeSeries of the binding surface (core/bindings/Binding.cpp:270-306) on both hosts
+(the compiled module hydrobricks_b200.native._hydrobricks and the Python mirror), and — where the compiled reference
+exists — against the reference's own classes on the same calls."""
+import math
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+MJD = lambda s: float((np.datetime64(s) - np.datetime64("1858-11-17")).astype(int))  # noqa: E731
+
+
+def _modules():
+    from hydrobricks_b200 import _hydrobricks as mirror
+    from hydrobricks_b200.native import _hydrobricks as native
+
+    mods = {"python": mirror, "native": native}
+    if list((ROOT / "oracle" / "_ref").glob("_hydrobricks*.so")):
+        sys.path.insert(0, str(ROOT / "tools"))
+        import refpy
+
+        mods["reference"] = refpy.load_extension("ref")
+    return mods
+
+
+MODS = _modules()
+
+
+def _scenario(hb):
+    """One fixed sequence of calls; returns everything observable."""
+    out = []
+    p = hb.Parameter("degree_day_factor", 3.1)
+    out += [p.get_name(), p.get_value(), p.name, p.value, repr(p), p.has_modifier(), p.update_from_modifier(MJD("2001-05-05"))]
+    p.set_name("ddf")
+    p.set_value(4.7)
+    out += [p.get_name(), p.get_value()]
+    T = hb.ParameterModifierType
+    yearly = hb.ParameterModifier(T.Yearly)
+    out += [yearly.set_yearly_values(2000, 2003, [1.0, 2.0, 3.5, 4.25]), yearly.updates_on_year_change(),
+            yearly.updates_on_month_change(), yearly.updates_on_date_change()]
+    out += [yearly.update_value(MJD(d)) for d in ("2000-01-01", "2001-12-31", "2003-06-15", "1999-12-31", "2004-01-01")]
+    out.append(yearly.set_yearly_values(2000, 2003, [1.0, 2.0]))  # wrong length -> False
+    monthly = hb.ParameterModifier(T.Monthly)
+    out += [monthly.set_monthly_values([float(i) + 0.1 for i in range(12)]), monthly.updates_on_month_change()]
+    out += [monthly.update_value(MJD(d)) for d in ("1985-01-31", "1985-02-01", "2020-12-25")]
+    out.append(monthly.set_monthly_values([1.0, 2.0]))
+    dates = hb.ParameterModifier(T.Dates)
+    out += [dates.set_dates_and_values([MJD("1990-03-01"), MJD("1995-07-15")], [7.0, 9.5]), dates.updates_on_date_change()]
+    out += [dates.update_value(MJD(d)) for d in ("1990-03-01", "1995-07-15", "1992-01-01", "1980-01-01")]
+    p.set_modifier(yearly)
+    yearly.set_yearly_values(2000, 2003, [1.0, 2.0, 3.5, 4.25])
+    p.set_modifier(yearly)
+    out += [p.has_modifier(), p.update_from_modifier(MJD("2002-02-02")), p.get_value(),
+            p.update_from_modifier(MJD("2010-02-02")), p.get_value()]
+    g = hb.ParameterModifier()
+    g.set_type(T.Monthly)
+    out.append(g.get_type() == T.Monthly)
+    return out
+
+
+def _same(a, b):
+    if isinstance(a, float) and isinstance(b, float):
+        return (math.isnan(a) and math.isnan(b)) or a == b
+    return a == b
+
+
+@pytest.mark.parametrize("name", [n for n in MODS if n != "reference"])
+def test_value_classes_behave_like_the_reference(name):
+    got = _scenario(MODS[name])
+    # known answers (base/Parameter.cpp, ParameterModifier.cpp); float32 storage
+    f32 = lambda x: float(np.float32(x))  # noqa: E731
+    assert got[:7] == ["degree_day_factor", f32(3.1), "degree_day_factor", f32(3.1),
+                       "<_hydrobricks.Parameter named 'degree_day_factor'>", False, False]
+    assert got[7:9] == ["ddf", f32(4.7)]
+    assert got[9:13] == [True, True, False, False]
+    assert got[13:16] == [1.0, 2.0, 4.25] and math.isnan(got[16]) and math.isnan(got[17])
+    if "reference" in MODS:
+        ref = _scenario(MODS["reference"])
+        assert len(ref) == len(got)
+        for i, (a, b) in enumerate(zip(got, ref)):
+            assert _same(a, b), (i, a, b)
+
+
+@pytest.mark.parametrize("name", [n for n in MODS if n != "reference"])
+def test_modifier_type_is_enforced(name):
+    hb = MODS[name]
+    m = hb.ParameterModifier(hb.ParameterModifierType.Monthly)
+    with pytest.raises(RuntimeError):
+        m.set_yearly_values(2000, 2001, [1.0, 2.0])
+    with pytest.raises(RuntimeError):
+        m.set_dates_and_values([50000.0], [1.0])
+
+
+@pytest.mark.parametrize("name", [n for n in MODS if n != "reference"])
+def test_time_series_create(name):
+    hb = MODS[name]
+    time = np.arange(5, dtype=np.float64) + 44605.0
+    ids = np.array([3, 1, 2], dtype=np.int32)
+    ts = hb.TimeSeries.create("precipitation", time, ids, np.arange(15, dtype=np.float64).reshape(5, 3))
+    assert ts is not None
+    assert hasattr(hb.ModelHydro, "add_time_series")
