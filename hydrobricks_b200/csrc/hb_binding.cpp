@@ -150,6 +150,17 @@ PYBIND11_MODULE(_hydrobricks, m) {
         .def("get_lateral_connection_count", &hb::SettingsBasin::GetLateralConnectionCount)
         .def("clear", &hb::SettingsBasin::Clear);
 
+    // SubBasin (Binding.cpp:260-268): the reference builds the spatial structure here; this engine builds it inside
+    // ModelHydro.init_with_basin, so the class only validates the basin settings the way SubBasin::Initialize does.
+    struct SubBasinShell {};
+    py::class_<SubBasinShell>(m, "SubBasin")
+        .def(py::init<>())
+        .def("init",
+             [](SubBasinShell&, hb::SettingsBasin& bs) {
+                 if (bs.units.empty()) throw py::value_error("Basin initialization failed: no hydro unit");
+             },
+             "spatial_structure"_a);
+
     py::class_<hb::Parameter>(m, "Parameter")
         .def(py::init<const std::string&, float>())
         .def_readwrite("name", &hb::Parameter::name)
@@ -381,6 +392,17 @@ PYBIND11_MODULE(_hydrobricks, m) {
             mh.GetState(HBK_S_GROUND_SNOW, buf.data());
             for (int u = 0; u < U; ++u) sum += buf[u] * g[u] * (areas[u] / total);
             mh.GetState(HBK_S_GLACIER_SNOW, buf.data());
+            for (int u = 0; u < U; ++u) sum += buf[u] * gl[u] * (areas[u] / total);
+            return sum;
+        })
+        .def("get_total_glacier_storage_changes", [](hb::ModelHydro& mh) {
+            const int U = mh.UnitCount(), P = mh.SetCount();
+            std::vector<double> g, gl, buf((size_t)P * U);
+            mh.fractions(g, gl);
+            auto areas = mh.GetHydroUnitAreas();
+            double total = 0, sum = 0;
+            for (double a : areas) total += a;
+            mh.GetState(HBK_S_ICE, buf.data());
             for (int u = 0; u < U; ++u) sum += buf[u] * gl[u] * (areas[u] / total);
             return sum;
         })

@@ -101,3 +101,34 @@ def test_time_series_create(name):
     ts = hb.TimeSeries.create("precipitation", time, ids, np.arange(15, dtype=np.float64).reshape(5, 3))
     assert ts is not None
     assert hasattr(hb.ModelHydro, "add_time_series")
+
+
+@pytest.mark.skipif("reference" not in MODS, reason="compiled reference not available")
+@pytest.mark.parametrize("name", [n for n in MODS if n != "reference"])
+def test_binding_surface_has_every_reference_class_and_method(name):
+    """Every public class and method the reference's module exports exists on this module (Binding.cpp:164-413)."""
+    ref, mod = MODS["reference"], MODS[name]
+    missing = []
+    for item in dir(ref):
+        if item.startswith("_"):
+            continue
+        if not hasattr(mod, item):
+            missing.append(item)
+            continue
+        if isinstance(getattr(ref, item), type):
+            # attributes the mirror sets per instance are not class members
+            skip = {"name", "value"} if name == "python" else set()
+            for member in dir(getattr(ref, item)):
+                if not member.startswith("_") and member not in skip and not hasattr(getattr(mod, item), member):
+                    missing.append(f"{item}.{member}")
+    assert not missing, missing
+
+
+@pytest.mark.parametrize("name", [n for n in MODS if n != "reference"])
+def test_sub_basin_init_validates_the_basin(name):
+    hb = MODS[name]
+    with pytest.raises(ValueError):
+        hb.SubBasin().init(hb.SettingsBasin())
+    basin = hb.SettingsBasin()
+    basin.add_hydro_unit(1, 100.0, 500.0)
+    hb.SubBasin().init(basin)
