@@ -19,9 +19,12 @@ def _modules():
     mods = {"python": mirror, "native": native}
     if list((ROOT / "oracle" / "_ref").glob("_hydrobricks*.so")):
         sys.path.insert(0, str(ROOT / "tools"))
-        import refpy
+        try:  # optional cross-check; never let a missing / unloadable reference build break test collection
+            import refpy
 
-        mods["reference"] = refpy.load_extension("ref")
+            mods["reference"] = refpy.load_extension("ref")
+        except Exception:
+            pass
     return mods
 
 
