@@ -23,19 +23,30 @@ RTOL, ATOL = 1e-10, 1e-12
 CASES = [b for b in gu.bundles() if not b.startswith(("c1_", "kat_linear", "actions_"))]
 
 
-@pytest.fixture(scope="module")
-def emul():
-    lib = EMUL / "libhbkemul.so"
+def build_emul(name="libhbkemul.so", defines=()):
+    """Compile hbk_device.cuh + the harness for the host (rebuilt when a source is newer) and bind it."""
+    lib = EMUL / name
     srcs = [EMUL / "hbk_host_emul.cpp", EMUL / "hbk_host_shims.h", ROOT / "hydrobricks_b200" / "csrc" / "hbk_device.cuh",
             ROOT / "include" / "hbk.h"]
     if not lib.exists() or lib.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-DHBK_HOST_EMULATION",
-                               f"-I{EMUL}", "-o", str(lib), str(EMUL / "hbk_host_emul.cpp")])
+                               *defines, f"-I{EMUL}", "-o", str(lib), str(EMUL / "hbk_host_emul.cpp")])
     L = ctypes.CDLL(str(lib))
     dp, fp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)
     L.hbk_emul_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, dp, fp, ip, dp, dp, fp, dp, dp, dp, dp, dp, dp,
                                dp, dp, ctypes.POINTER(ctypes.c_longlong)]
     return L
+
+
+@pytest.fixture(scope="module")
+def emul():
+    return build_emul()
+
+
+@pytest.fixture(scope="module")
+def emul_faithful():
+    """The same arithmetic built with -DHBK_FAITHFUL=1 (divisions as the reference writes them, verification sweep kept)."""
+    return build_emul("libhbkemul_faithful.so", ("-DHBK_FAITHFUL=1",))
 
 
 def _day_of_year(mjd):
@@ -102,6 +113,14 @@ def test_device_arithmetic_on_host_matches_reference(name, emul):
         _close(rec["snow"], records[snow_label])
     if cs.glacier_name and f"{cs.glacier_name}:ice_content" in records and not cs.hbk.glacier_infinite_storage:
         _close(rec["ice"], records[f"{cs.glacier_name}:ice_content"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_faithful_build_matches_reference(name, emul_faithful):
+    meta, forcing, outlet, records, _ = gu.load(name)
+    _, q, rec, _ = run_emul(emul_faithful, meta, forcing)
+    _close(q, outlet)
+    _close(rec["slow"], records["slow_reservoir:water_content"])
 
 
 @pytest.mark.parametrize("solver", ["rk4", "heun_explicit", "euler_explicit", "crank_nicolson", "implicit_euler",
