@@ -650,7 +650,9 @@ def main():
     ap.add_argument("--sets", type=int, default=None, help="parameter sets per GPU")
     ap.add_argument("--units", type=int, default=None)
     ap.add_argument("--timesteps", type=int, default=None)
-    ap.add_argument("--ref-sets-per-core", type=int, default=2)
+    ap.add_argument("--ref-sets-per-core", type=int, default=8,
+                    help="reference arm / cpu_baseline: parameter sets per host core and step (8 = ~7 s of wall time per "
+                         "step on a 16-core box, ~100 core-seconds)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     for key in ("sets", "units", "timesteps"):
