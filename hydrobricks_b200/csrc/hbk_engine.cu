@@ -1701,8 +1701,6 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
         e->lastLaunches += 2;
     }
     if (e->st.has_glacier && !e->shard) {
-        const int blocks = (e->P + 127) / 128;
-        const double dt = e->st.time_step_days;
         const double* stale = nullptr;
         if (e->fracPerSet) {  // a glacier may have vanished through an action: its stale flux amounts
             if (!e->dStale) HBK_CUDA(cudaMalloc(&e->dStale, sizeof(double) * 2 * e->P));
@@ -1895,8 +1893,6 @@ int hbk_finish_sharded_run(hbk_engine* e) {
     HBK_CUDA(cudaSetDevice(e->device));
     e->shardPending = false;
     if (!e->st.has_glacier) return HBK_OK;  // no sub-basin stores: the reduced unit sums are the outlet
-    const int blocks = (e->P + 127) / 128;
-    const double dt = e->st.time_step_days;
     HBK_CUDA(cudaEventRecord(e->ev0, e->stream));
     launchBasinStores(e, 0, e->T, nullptr, 1);
     e->lastLaunches++;
