@@ -412,5 +412,44 @@ PYBIND11_MODULE(_hydrobricks, m) {
         .def("engine_handle", [](hb::ModelHydro& mh) { return (std::uintptr_t)mh.engine(); },
              "Raw hbk_engine* (for hydrobricks_b200.engine.Engine.from_handle: device pointers, stream, statistics).");
 
+    // The structure compiler alone (no engine, no device): what hb::Compiled derives from a SettingsModel. Lets the CPU
+    // test suite compare it with the Python compiler (hydrobricks_b200/structure.py) on every reference structure.
+    m.def(
+        "compile_structure",
+        [](hb::SettingsModel& sm, double dt_days, double start_mjd) {
+            std::unique_ptr<hb::Compiled> c;
+            try {
+                c.reset(new hb::Compiled(sm, dt_days, start_mjd));
+            } catch (const hb::Unsupported& err) {
+                throw py::value_error(std::string("Model initialization failed: ") + err.what());
+            }
+            py::dict st;
+            st["solver"] = c->st.solver;
+            st["n_soil_stores"] = c->st.n_soil_stores;
+            st["quick_kind"] = c->st.quick_kind;
+            st["slow_process_order"] = c->st.slow_process_order;
+            st["splitter_kind"] = c->st.splitter_kind;
+            st["has_glacier"] = c->st.has_glacier;
+            st["glacier_infinite_storage"] = c->st.glacier_infinite_storage;
+            st["glacier_no_melt_when_snow_cover"] = c->st.glacier_no_melt_when_snow_cover;
+            st["time_step_days"] = c->st.time_step_days;
+            st["snow_ice_kind"] = c->st.snow_ice_kind;
+            st["north_hemisphere"] = c->st.north_hemisphere;
+            st["start_mjd"] = c->st.start_mjd;
+            st["sublimation_kind"] = c->st.sublimation_kind;
+            py::dict out;
+            out["structure"] = st;
+            out["params"] = f32arr(HBK_N_PARAMS, c->params);
+            py::dict labels, index;
+            for (auto& kv : c->labels) labels[py::str(kv.first)] = kv.second;
+            for (auto& kv : c->paramIndex) index[py::make_tuple(kv.first.first, kv.first.second)] = kv.second;
+            out["labels"] = labels;
+            out["param_index"] = index;
+            out["ground_name"] = c->groundName;
+            out["glacier_name"] = c->glacierName;
+            return out;
+        },
+        "model_settings"_a, "time_step_days"_a = 1.0, "start_mjd"_a = 44605.0);
+
     py::class_<LogNull>(m, "LogNull").def(py::init<>());
 }

@@ -41,3 +41,58 @@ def run_oracle(meta, forcing, labels=None):
 def same(a, b):
     """Bit-exact including NaN placement."""
     return np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)
+
+
+def settings_from_structures(hb, meta, n_steps, solver=None):
+    """Rebuild a SettingsModel on the host module `hb` (mirror or compiled) from the structure description a golden
+    bundle carries, through the reference's select-then-add API, and give it the bundle's parameter values."""
+    s = hb.SettingsModel()
+    s.log_all(True)
+    s.set_solver(solver or meta["solver"])
+    start = np.datetime64("1981-01-01")
+    s.set_timer("1981-01-01", str(start + np.timedelta64(n_steps - 1, "D")), 1, "day")
+    for i, st in enumerate(meta["structures"]):
+        if i > 0:
+            s.add_structure()
+        tr = next(x for x in st["hydro_unit_splitters"] if x["name"] == "snow_rain_transition")
+        s.generate_precipitation_splitters(True, tr["kind"])
+        for b in st["hydro_unit_bricks"]:
+            if b["is_land_cover"]:
+                s.add_land_cover_brick(b["name"], b["kind"])
+        s.generate_snowpacks("melt:degree_day")
+        extras = {}  # AddSnowIceTransformation / AddSnowpackSublimation, in the order of model_settings.py:258-263
+        for b in st["hydro_unit_bricks"]:
+            if b["is_surface_component"]:
+                for proc in b["processes"][1:]:
+                    extras[proc["name"]] = proc["kind"]
+        if "snow_ice_transfo" in extras:
+            s.add_snow_ice_transformation(extras["snow_ice_transfo"])
+        if "sublimation" in extras:
+            s.add_snowpack_sublimation(extras["sublimation"])
+        for b in st["hydro_unit_bricks"] + st["sub_basin_bricks"]:
+            if b["is_surface_component"]:
+                continue
+            if b["is_land_cover"]:
+                s.select_hydro_unit_brick(b["name"])
+            elif b["attach"] == "sub_basin":
+                s.add_sub_basin_brick(b["name"], b["kind"])
+            else:
+                s.add_hydro_unit_brick(b["name"], b["kind"])
+            for p in b["parameters"]:
+                s.add_brick_parameter(p["name"], p["value"])
+            for proc in b["processes"]:
+                s.add_brick_process(proc["name"], proc["kind"], proc["outputs"][0]["target"] if proc["outputs"] else "")
+                if proc["outputs"] and proc["outputs"][0]["static"]:
+                    s.set_process_outputs_as_static()
+                if proc["outputs"] and proc["outputs"][0]["instantaneous"]:
+                    s.set_process_outputs_as_instantaneous()
+        s.add_logging_to("outlet")
+    for st in meta["structures"]:
+        for el in st["hydro_unit_bricks"] + st["sub_basin_bricks"] + st["hydro_unit_splitters"]:
+            for p in el.get("parameters", []):
+                if p["name"] not in ("infinite_storage", "no_melt_when_snow_cover"):
+                    assert s.set_parameter_value(el["name"], p["name"], p["value"])
+            for proc in el.get("processes", []):
+                for p in proc["parameters"]:
+                    assert s.set_parameter_value(el["name"], p["name"], p["value"])
+    return s

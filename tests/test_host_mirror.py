@@ -116,3 +116,30 @@ def test_structure_variant_assignment():
     gv = cs.assign_structure_variants([u["land_covers"] for u in meta["units"]])
     expect = [1 if dict(u["land_covers"]).get("glacier", 0) > 1e-8 else 0 for u in meta["units"]]
     assert gv == expect and 0 < sum(gv) < len(gv)
+
+
+COMPILER_CASES = [b for b in gu.bundles() if not b.startswith(("c1_", "kat_"))]
+
+
+@pytest.mark.parametrize("name", COMPILER_CASES)
+def test_cpp_and_python_structure_compilers_agree(name):
+    """hb::Compiled (csrc/hb_host.hpp) and structure.CompiledStructure derive the same process table, the same float32
+    parameter vector in the same slots, the same label -> recorder-slot map and the same parameter index from every
+    reference structure (the C++ side through the pure-host `compile_structure` entry: no device involved)."""
+    from hydrobricks_b200 import engine
+    from hydrobricks_b200.native import _hydrobricks as native
+
+    meta, _, outlet, _, _ = gu.load(name)
+    s = gu.settings_from_structures(native, meta, len(outlet))
+    strip = lambda sts: [{k: v for k, v in st.items() if k != "log_items"} for st in sts]  # noqa: E731
+    assert strip(s.get_structure()) == strip(meta["structures"])  # the rebuilt settings ARE the reference's structure
+    cpp = native.compile_structure(s, 1.0, 44605.0)
+    py = structure.CompiledStructure(meta["structures"], meta["solver"], 1.0, 44605.0)
+    for field in ("solver", "n_soil_stores", "quick_kind", "slow_process_order", "splitter_kind", "has_glacier",
+                  "glacier_infinite_storage", "glacier_no_melt_when_snow_cover", "time_step_days", "snow_ice_kind",
+                  "north_hemisphere", "start_mjd", "sublimation_kind"):
+        assert cpp["structure"][field] == getattr(py.hbk, field), field
+    assert np.array_equal(np.asarray(cpp["params"], dtype=np.float32), py.parameter_vector())
+    assert {k: v for k, v in cpp["labels"].items()} == {k: engine.RECORD_SLOTS.index(v) for k, v in py.labels.items()}
+    assert {tuple(k): v for k, v in cpp["param_index"].items()} == {tuple(k): v for k, v in py.param_index.items()}
+    assert cpp["ground_name"] == py.ground_name and (cpp["glacier_name"] or None) == py.glacier_name
