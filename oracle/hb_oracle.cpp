@@ -115,8 +115,8 @@ struct hbo_model {
     std::vector<double> dhUnitAreas, dhAreas, dhVolumes;
     int dhRows = 0, dhLastRow = 0;
     double dhInitialWE = 0;
-    const double* forcing[3] = {nullptr, nullptr, nullptr};
-    std::vector<double> forcingStore[3];
+    const double* forcing[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<double> forcingStore[4];
     double outletTotal = 0;
     // Processor state (base/Processor.h)
     std::vector<int> iterableBricks;
@@ -405,6 +405,18 @@ void GetRates(hbo_model& m, Process& p) {
             const float ddf = p.params[0], tm = p.params[1];
             double t = m.Forcing(HBO_V_TEMPERATURE, unit);
             if (t >= tm) melt = (t - tm) * ddf;
+            StoreRates1(p, melt);
+            return;
+        }
+        case HBO_P_MELT_TEMPERATURE_INDEX: {  // ProcessMeltTemperatureIndex.cpp:62-74
+            if (!ContentAccessible(m, c)) {
+                StoreRates1(p, 0);
+                return;
+            }
+            double melt = 0;
+            const float mf = p.params[0], tm = p.params[1], rc = p.params[2];
+            double t = m.Forcing(HBO_V_TEMPERATURE, unit);
+            if (t >= tm) melt = (t - tm) * (mf + rc * m.Forcing(HBO_V_SOLAR_RADIATION, unit));
             StoreRates1(p, melt);
             return;
         }
@@ -1402,7 +1414,7 @@ int hbo_run(hbo_model* m, double* outlet, double* records) {
             }
         }
         m->dhLastRow = 0;
-        for (int v = 0; v < 3; ++v) {
+        for (int v = 0; v < 4; ++v) {
             if (!m->forcing[v]) {
                 m->forcingStore[v].assign(static_cast<size_t>(m->nSteps) * m->nUnits, 0.0);
                 m->forcing[v] = m->forcingStore[v].data();

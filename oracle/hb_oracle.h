@@ -35,14 +35,19 @@ enum {
     HBO_P_TRANSFORM_SNOW_ICE_CONSTANT = 9, /* params: snow_ice_transformation_rate; on the snowpack's snow container */
     HBO_P_TRANSFORM_SNOW_ICE_SWAT = 10, /* params: snow_ice_transformation_basal_acc_coeff, north_hemisphere */
     HBO_P_SUBLIMATION_CONSTANT = 11,    /* params: sublimation_rate; snow container -> atmosphere */
-    HBO_P_SUBLIMATION_PET = 12          /* params: sublimation_pet_factor; forcing pet */
+    HBO_P_SUBLIMATION_PET = 12,         /* params: sublimation_pet_factor; forcing pet */
+    /* melt:temperature_index (ProcessMeltTemperatureIndex.cpp): params melt_factor, melting_temperature,
+     * radiation_coefficient; forcing temperature + solar_radiation. melt:degree_day_aspect
+     * (ProcessMeltDegreeDayAspect.cpp) needs no type of its own: the builder hands HBO_P_MELT_DEGREE_DAY the
+     * degree-day factor of the unit's aspect class, exactly what SetParameters binds (…Aspect.cpp:38-58). */
+    HBO_P_MELT_TEMPERATURE_INDEX = 13
 };
 enum {
     HBO_F_TO_BRICK = 0, HBO_F_TO_BRICK_INSTANT = 1, HBO_F_TO_OUTLET = 2, HBO_F_TO_ATMOSPHERE = 3,
     HBO_F_SIMPLE = 4, HBO_F_FORCING = 5
 };
 enum { HBO_S_SNOW_RAIN_LINEAR = 0, HBO_S_MULTI_FLUXES = 1, HBO_S_RAIN = 2, HBO_S_SNOW_RAIN_THRESHOLD = 3 };
-enum { HBO_V_PRECIPITATION = 0, HBO_V_TEMPERATURE = 1, HBO_V_PET = 2 };
+enum { HBO_V_PRECIPITATION = 0, HBO_V_TEMPERATURE = 1, HBO_V_PET = 2, HBO_V_SOLAR_RADIATION = 3 };
 enum { HBO_SOLVER_EULER = 0, HBO_SOLVER_HEUN = 1, HBO_SOLVER_RK4 = 2,
        /* sequential family (base/SolverSequential.cpp): Solver::Factory names crank_nicolson|trapezoidal,
         * implicit_euler|euler_implicit, exponential_euler, analytic_linear|analytic (Solver.cpp:42-64) */

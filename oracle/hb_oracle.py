@@ -38,6 +38,8 @@ PROC_KIND = {
     "transformation:snow_ice_swat": 10,
     "sublimation:constant": 11,
     "sublimation:pet": 12,
+    "melt:degree_day_aspect": 0,  # the degree-day factor of the unit's aspect class (ProcessMeltDegreeDayAspect.cpp:38-58)
+    "melt:temperature_index": 13,
 }
 PROC_PARAMS = {
     0: ["degree_day_factor", "melting_temperature"],
@@ -48,9 +50,14 @@ PROC_PARAMS = {
     10: ["snow_ice_transformation_basal_acc_coeff", "north_hemisphere"],
     11: ["sublimation_rate"],
     12: ["sublimation_pet_factor"],
+    13: ["melt_factor", "melting_temperature", "radiation_coefficient"],
 }
+ASPECT_DDF = {"north": "degree_day_factor_n", "N": "degree_day_factor_n", "south": "degree_day_factor_s",
+              "S": "degree_day_factor_s", "east": "degree_day_factor_ew", "west": "degree_day_factor_ew",
+              "E": "degree_day_factor_ew", "W": "degree_day_factor_ew"}
 SPLITTER_KIND = {"snow_rain:linear": 0, "snow_rain_transition": 0, "multi_fluxes": 1, "rain": 2, "snow_rain:threshold": 3}
-FORCING = {"precipitation": 0, "p": 0, "temperature": 1, "t": 1, "pet": 2}  # TimeSeries.cpp:134-146
+FORCING = {"precipitation": 0, "p": 0, "temperature": 1, "t": 1, "pet": 2,
+           "solar_radiation": 3, "r_solar": 3, "r": 3}  # TimeSeries.cpp:134-146
 SOLVERS = {"euler_explicit": 0, "heun_explicit": 1, "rk4": 2, "runge_kutta": 2,
            "crank_nicolson": 3, "trapezoidal": 3, "implicit_euler": 4, "euler_implicit": 4, "exponential_euler": 5,
            "analytic_linear": 6, "analytic": 6}
@@ -244,7 +251,7 @@ class OracleModel:
             L.hbo_container_add_input(h, water, fl)
         for ps in bs["processes"]:
             ptype = PROC_KIND[ps["kind"]]
-            if ptype == 0:
+            if ptype in (0, 13):
                 if kind not in (2, 3):
                     raise ValueError("melt process on unsupported brick")
                 container = second
@@ -255,7 +262,16 @@ class OracleModel:
             else:
                 container = water
             pp = _params(ps)
-            vals = [pp[n] for n in PROC_PARAMS.get(ptype, [])]
+            if ps["kind"] == "melt:degree_day_aspect":
+                aspect = (unit_info or {}).get("aspect_class")
+                if aspect not in ASPECT_DDF:
+                    raise ValueError(f"Invalid aspect: {aspect}")
+                name = ASPECT_DDF[aspect]
+                if name.endswith("_ew") and name not in pp:
+                    name = "degree_day_factor_we"
+                vals = [pp[name], pp["melting_temperature"]]
+            else:
+                vals = [pp[n] for n in PROC_PARAMS.get(ptype, [])]
             area = unit_info["area"] if unit_info else 0.0
             slope = np.float32(0)
             if ptype == 3:

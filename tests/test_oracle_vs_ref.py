@@ -57,3 +57,20 @@ def test_oracle_actions_bit_exact_against_compiled_reference(solver, flags, area
     assert np.array_equal(om.outlet, q)
     for label in rec:
         assert np.array_equal(om.records[label], rec[label], equal_nan=True), label
+
+
+@pytest.mark.parametrize("kind, solver, kw", [
+    ("melt:degree_day_aspect", "heun_explicit", dict(glacier=True, nsoil=1)),
+    ("melt:temperature_index", "implicit_euler", dict(glacier=True, nsoil=2)),
+])
+def test_oracle_melt_variants_bit_exact_against_compiled_reference(kind, solver, kw):
+    import ref_melt_cases as rm
+    import refpy
+
+    ref = refpy.load_extension("ref")
+    ref.init()
+    meta, forcing, q, rec = rm.run_reference(ref, kind, solver, n_steps=500, **kw)
+    om = rm.run_oracle(meta, forcing, list(rec))
+    assert np.array_equal(om.outlet, q)
+    for label in rec:
+        assert np.array_equal(om.records[label], rec[label], equal_nan=True), label

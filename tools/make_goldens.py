@@ -41,6 +41,8 @@ def run_ref_module(ref, settings, units, forcing, labels_from_model=True):
         basin.add_hydro_unit(u["id"], u["area"], u.get("elevation", -9999))
         if u.get("slope"):
             basin.add_hydro_unit_property_double("slope", u["slope"][0], u["slope"][1])
+        if u.get("aspect_class"):
+            basin.add_hydro_unit_property_str("aspect_class", u["aspect_class"])
         for name, frac in u["land_covers"]:
             basin.add_land_cover(name, "", frac)
     model = ref.ModelHydro()
@@ -200,11 +202,28 @@ def action_bundles(ref, only_new=False):
         save(f"actions_{solver}_{tag}", meta, forcing, q, {k: rec[k] for k in keep}, extra=extra)
 
 
+def melt_variant_bundles(ref):
+    """snow_melt_process variants the CUDA engine does not implement yet (melt:degree_day_aspect,
+    melt:temperature_index): vectors for the oracle now and for the engine next, kept apart under tests/golden/next/ so
+    that the engine's parity tests do not pick them up."""
+    import ref_melt_cases as rm
+
+    (OUT / "next").mkdir(parents=True, exist_ok=True)
+    for kind, tag in (("melt:degree_day_aspect", "aspect"), ("melt:temperature_index", "tindex")):
+        for solver, kw, name in (("rk4", dict(glacier=True, nsoil=2), "glacier_2store"),
+                                 ("crank_nicolson", dict(glacier=False, nsoil=1), "noglacier_1store")):
+            meta, forcing, q, rec = rm.run_reference(ref, kind, solver, **kw)
+            save(f"next/melt_{tag}_{solver}_{name}", meta, forcing, q, rec)
+
+
 def main():
     hb = refpy.load_reference_python("ref")
     ref = sys.modules["hydrobricks._hydrobricks"]
     if len(sys.argv) > 1 and sys.argv[1] == "snow_ice":
         snow_ice_bundles(hb)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "melt":
+        melt_variant_bundles(ref)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "actions_new":
         action_bundles(ref, only_new=True)
@@ -263,6 +282,7 @@ def main():
     save("c1_sitter_rk4_full", meta, {}, q, {}, extra=extra)
     snow_ice_bundles(hb)
     sequential_bundles(hb, ref)
+    melt_variant_bundles(ref)
 
 
 if __name__ == "__main__":
