@@ -37,13 +37,15 @@ class Socont:
     def __init__(self, solver="crank_nicolson", soil_storage_nb=1, surface_runoff="socont_runoff",
                  land_cover_names=None, land_cover_types=None, record_all=False, glacier_infinite_storage=True,
                  snow_melt_process="melt:degree_day", snow_ice_transformation=None, snow_sublimation_process=None,
-                 backend=None):
+                 snow_redistribution=None, snow_redistribution_skip_glaciers=True, backend=None):
         self.backend = resolve_backend(backend)
         self.solver = solver
         self.options = {"soil_storage_nb": soil_storage_nb, "surface_runoff": surface_runoff,
                         "snow_melt_process": snow_melt_process, "glacier_infinite_storage": glacier_infinite_storage,
                         "snow_ice_transformation": snow_ice_transformation,
-                        "snow_sublimation_process": snow_sublimation_process}
+                        "snow_sublimation_process": snow_sublimation_process,
+                        "snow_redistribution": snow_redistribution,
+                        "snow_redistribution_skip_glaciers": snow_redistribution_skip_glaciers}
         self.land_cover_names = list(land_cover_names or ["open"])
         self.land_cover_types = list(land_cover_types or ["open"])
         self.record_all = record_all
@@ -115,6 +117,9 @@ class Socont:
             s.generate_snowpacks(self.options["snow_melt_process"])
             if self.options["snow_ice_transformation"]:  # model_settings.py:258-259
                 s.add_snow_ice_transformation(self.options["snow_ice_transformation"])
+            if self.options["snow_redistribution"]:  # model_settings.py:260-261; refused by the B200 host modules
+                s.add_snow_redistribution(self.options["snow_redistribution"],
+                                          self.options["snow_redistribution_skip_glaciers"])
             if self.options["snow_sublimation_process"]:  # model_settings.py:262-263
                 s.add_snowpack_sublimation(self.options["snow_sublimation_process"])
             for key, brick in structure.items():

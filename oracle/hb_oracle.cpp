@@ -58,7 +58,11 @@ struct Container {  // containers/WaterContainer.h:342-353
 
 struct Process {
     int brick, type, container;
-    float params[4] = {0, 0, 0, 0};
+    float params[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // lateral processes (ProcessLateral.cpp): per output the receiving snowpack brick and the connection's weight
+    std::vector<int> lateralTargets;
+    std::vector<double> weights;
+    float slopeDeg = 0;
     int targetBrick = -1;
     double unitArea = 0;
     float slope = 0;
@@ -106,6 +110,7 @@ struct hbo_model {
     std::vector<Brick> bricks;
     std::vector<Splitter> splitters;
     std::vector<std::vector<int>> unitBricks, unitSplitters;
+    std::vector<double> unitAreas;  // HydroUnit::GetArea, for the lateral processes
     std::vector<int> basinBricks;
     std::vector<int> outletFluxes;
     std::vector<Record> records;
@@ -418,6 +423,51 @@ void GetRates(hbo_model& m, Process& p) {
             double t = m.Forcing(HBO_V_TEMPERATURE, unit);
             if (t >= tm) melt = (t - tm) * (mf + rc * m.Forcing(HBO_V_SOLAR_RADIATION, unit));
             StoreRates1(p, melt);
+            return;
+        }
+        case HBO_P_LATERAL_SNOW_SLIDE: {  // ProcessLateralSnowSlide.cpp:48-118
+            if (p.outputs.empty()) {
+                p.rates.clear();
+                return;
+            }
+            const float coeff = p.params[0], expo = p.params[1], minSlope = p.params[2], maxSlope = p.params[3],
+                        minSnowHoldingDepth = p.params[4], maxSnowDepth = p.params[5];
+            const float sweToDepthFactor = 1000.0 / 250.0;  // constants::waterDensity / constants::snowDensity
+            double swe = ContentWithChanges(c);
+            double snowDepth = swe * sweToDepthFactor;
+            float slope = std::max(p.slopeDeg, minSlope);
+            double snowHoldingThresholdMeters = coeff * pow(slope, expo);
+            double snowHoldingThreshold = snowHoldingThresholdMeters * 1000.0;
+            if (p.slopeDeg > maxSlope) snowHoldingThreshold = minSnowHoldingDepth;
+            snowHoldingThreshold = std::max<double>(snowHoldingThreshold, minSnowHoldingDepth);
+            if (maxSnowDepth > 0.0f) snowHoldingThreshold = std::min<double>(snowHoldingThreshold, maxSnowDepth);
+            double excessSwe = 0.0;
+            if (snowDepth > snowHoldingThreshold) {
+                double excessSnowDepth = snowDepth - snowHoldingThreshold;
+                excessSwe = excessSnowDepth / sweToDepthFactor;
+            }
+            p.rates.assign(p.outputs.size(), 0.0);
+            if (excessSwe <= 0.0) return;
+            if (excessSwe > 1000.0) excessSwe = 1000.0;
+            const Brick& origin = m.bricks[p.brick];
+            const double originFraction = m.bricks[origin.parent].areaFraction;  // SurfaceComponent::GetParentAreaFraction
+            for (size_t i = 0; i < p.outputs.size(); ++i) {
+                const Brick& target = m.bricks[p.lateralTargets[i]];
+                double targetFraction = m.bricks[target.parent].areaFraction;
+                if (NearlyZero(targetFraction, PRECISION)) {
+                    p.rates[i] = 0.0;
+                    continue;
+                }
+                p.rates[i] = excessSwe * p.weights[i] * targetFraction;
+                // AvoidUnrealisticAccumulation (ProcessLateralSnowSlide.cpp:120-134): Snowpack::GetContent(Snow)
+                double targetSwe = m.containers[target.second].content;
+                if (maxSnowDepth > 0.0f && targetSwe > 1.5 * maxSnowDepth / sweToDepthFactor) p.rates[i] = 0;
+                // ProcessLateral::ComputeFractionAreas (ProcessLateral.cpp:67-76) -> Flux::SetFractionUnitArea
+                double fractionAreas = (m.unitAreas[origin.unit] * originFraction) / (m.unitAreas[target.unit] * targetFraction);
+                Flux& f = m.fluxes[p.outputs[i]];
+                f.fractionUnitArea = fractionAreas;
+                f.fractionTotal = f.fractionUnitArea * f.fractionLandCover;
+            }
             return;
         }
         case HBO_P_ET_SOCONT: {  // ProcessETSocont.cpp:35-38 (exponent is a float member = 0.5)
@@ -1282,6 +1332,17 @@ void hbo_set_cover_links(hbo_model* m, int cover_brick, int generic_cover_brick,
 }
 void hbo_set_parent(hbo_model* m, int brick, int parent_brick) { m->bricks[brick].parent = parent_brick; }
 void hbo_set_target_brick(hbo_model* m, int process, int target_brick) { m->processes[process].targetBrick = target_brick; }
+// ProcessLateralSnowSlide::SetHydroUnitProperties (slope in degrees, float) + ProcessLateral::AttachFluxOutWithWeight:
+// call once per output, in output order, after hbo_process_add_output.
+void hbo_set_lateral_slope(hbo_model* m, int process, float slope_deg) { m->processes[process].slopeDeg = slope_deg; }
+void hbo_add_lateral_output(hbo_model* m, int process, int target_snowpack_brick, double weight) {
+    m->processes[process].lateralTargets.push_back(target_snowpack_brick);
+    m->processes[process].weights.push_back(weight);
+}
+void hbo_set_unit_area(hbo_model* m, int unit, double area) {
+    if (static_cast<int>(m->unitAreas.size()) <= unit) m->unitAreas.resize(unit + 1, 0.0);
+    m->unitAreas[unit] = area;
+}
 
 int hbo_add_container(hbo_model* m, int brick, int content_kind, float capacity, int infinite_storage,
                       int no_melt_when_snow_cover, double initial_state) {
@@ -1313,7 +1374,7 @@ int hbo_add_process(hbo_model* m, int brick, int type, int container, const floa
     p.brick = brick;
     p.type = type;
     p.container = container;
-    for (int i = 0; i < n_params && i < 4; ++i) p.params[i] = params[i];
+    for (int i = 0; i < n_params && i < 8; ++i) p.params[i] = params[i];
     p.targetBrick = target_brick;
     p.unitArea = unit_area;
     p.slope = slope;
@@ -1371,6 +1432,10 @@ int hbo_add_record(hbo_model* m, int kind, int id) {
 void hbo_finalize_graph(hbo_model* m) {
     for (Brick& b : m->bricks) {
         if (b.kind == HBO_BRICK_STORAGE) continue;
+        // SurfaceComponent::SetAreaFraction is only reached for surface components listed in the basin settings
+        // (SubBasin.cpp:84-94); the basins built here list land covers only, so a snowpack's weighted out-fluxes (the
+        // lateral ones) keep the default land-cover fraction of 1.
+        if (b.kind == HBO_BRICK_SNOWPACK) continue;
         double value = b.areaFraction;
         for (int ip : b.processes) {
             for (int io : m->processes[ip].outputs) {

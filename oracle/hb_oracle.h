@@ -40,7 +40,10 @@ enum {
      * radiation_coefficient; forcing temperature + solar_radiation. melt:degree_day_aspect
      * (ProcessMeltDegreeDayAspect.cpp) needs no type of its own: the builder hands HBO_P_MELT_DEGREE_DAY the
      * degree-day factor of the unit's aspect class, exactly what SetParameters binds (…Aspect.cpp:38-58). */
-    HBO_P_MELT_TEMPERATURE_INDEX = 13
+    HBO_P_MELT_TEMPERATURE_INDEX = 13,
+    /* transport:snow_slide (ProcessLateralSnowSlide.cpp): params coeff, exp, min_slope, max_slope,
+     * min_snow_holding_depth, max_snow_depth; one instantaneous snow flux per (lateral connection, receiving snowpack) */
+    HBO_P_LATERAL_SNOW_SLIDE = 14
 };
 enum {
     HBO_F_TO_BRICK = 0, HBO_F_TO_BRICK_INSTANT = 1, HBO_F_TO_OUTLET = 2, HBO_F_TO_ATMOSPHERE = 3,
@@ -78,6 +81,9 @@ void hbo_splitter_add_input(hbo_model* m, int splitter, int flux);
 void hbo_add_outlet_flux(hbo_model* m, int flux);
 /* data[T][U], row-major */
 void hbo_set_forcing(hbo_model* m, int var, const double* data);
+void hbo_set_lateral_slope(hbo_model* m, int process, float slope_deg);
+void hbo_add_lateral_output(hbo_model* m, int process, int target_snowpack_brick, double weight);
+void hbo_set_unit_area(hbo_model* m, int unit, double area);
 int hbo_add_record(hbo_model* m, int kind, int id);
 /* Date of the first time step (modified Julian date), for the processes that read the day of the year
  * (TimeMachine::GetCurrentDayOfYear, TimeMachine.cpp:87-98). Default 44605 = 1981-01-01. */

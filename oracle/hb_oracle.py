@@ -40,6 +40,7 @@ PROC_KIND = {
     "sublimation:pet": 12,
     "melt:degree_day_aspect": 0,  # the degree-day factor of the unit's aspect class (ProcessMeltDegreeDayAspect.cpp:38-58)
     "melt:temperature_index": 13,
+    "transport:snow_slide": 14,
 }
 PROC_PARAMS = {
     0: ["degree_day_factor", "melting_temperature"],
@@ -51,6 +52,7 @@ PROC_PARAMS = {
     11: ["sublimation_rate"],
     12: ["sublimation_pet_factor"],
     13: ["melt_factor", "melting_temperature", "radiation_coefficient"],
+    14: ["coeff", "exp", "min_slope", "max_slope", "min_snow_holding_depth", "max_snow_depth"],
 }
 ASPECT_DDF = {"north": "degree_day_factor_n", "N": "degree_day_factor_n", "south": "degree_day_factor_s",
               "S": "degree_day_factor_s", "east": "degree_day_factor_ew", "west": "degree_day_factor_ew",
@@ -101,6 +103,9 @@ def lib():
         L.hbo_splitter_add_input.argtypes = [c_vp, c_int, c_int]
         L.hbo_add_outlet_flux.argtypes = [c_vp, c_int]
         L.hbo_set_forcing.argtypes = [c_vp, c_int, dp]
+        L.hbo_set_lateral_slope.argtypes = [c_vp, c_int, ctypes.c_float]
+        L.hbo_add_lateral_output.argtypes = [c_vp, c_int, c_int, ctypes.c_double]
+        L.hbo_set_unit_area.argtypes = [c_vp, c_int, ctypes.c_double]
         L.hbo_add_record.argtypes = [c_vp, c_int, c_int]
         L.hbo_set_start_mjd.argtypes = [c_vp, c_dbl]
         ipt = ctypes.POINTER(ctypes.c_int)
@@ -255,7 +260,7 @@ class OracleModel:
                 if kind not in (2, 3):
                     raise ValueError("melt process on unsupported brick")
                 container = second
-            elif ptype in (9, 10, 11, 12):  # Process.cpp:301-346: the snowpack's snow container
+            elif ptype in (9, 10, 11, 12, 14):  # Process.cpp:301-346: the snowpack's snow container
                 if kind != 3:
                     raise ValueError("transformation / sublimation process on unsupported brick")
                 container = second
@@ -347,6 +352,8 @@ class OracleModel:
                     L.hbo_set_area_fraction(h, self._bricks[(name, iu)]["id"], float(fraction))
                     self._bricks[(name, iu)]["fraction"] = float(fraction)
 
+        for iu, u in enumerate(units):
+            L.hbo_set_unit_area(h, iu, float(u["area"]))
         # second loop (ModelBuilder.cpp:198-204)
         for iu, u in enumerate(units):
             st = st_by_id[st_ids[iu]]
@@ -398,6 +405,25 @@ class OracleModel:
                     continue
                 for out in ps["outputs"]:
                     content = CONTENT[out["flux_type"]]
+                    if out["target"] == "lateral":
+                        # ModelBuilder.cpp:476-508: one flux per (lateral connection of the unit, snowpack of the
+                        # receiving unit), weighted with the connection's fraction
+                        if content != SNOW:
+                            raise ValueError("Lateral flux type not yet supported")
+                        value, slope_unit = u["slope"]
+                        if slope_unit not in ("deg", "degree", "degrees", "°"):
+                            raise ValueError("snow slide: slope in degrees expected")
+                        L.hbo_set_lateral_slope(h, proc["id"], float(np.float32(value)))
+                        for receiver, fraction in u.get("lateral", []):
+                            for (bname, bunit), tb in self._bricks.items():
+                                if bunit != receiver or tb["kind"] != 3:
+                                    continue
+                                kind = F_TO_BRICK_INSTANT if out["instantaneous"] else F_TO_BRICK
+                                fl = L.hbo_add_flux(h, kind, int(out["static"]), 1, 1.0, tb["second"], -1, unit)
+                                self._attach_in(tb, fl, SNOW)
+                                L.hbo_process_add_output(h, proc["id"], fl)
+                                L.hbo_add_lateral_output(h, proc["id"], tb["id"], float(fraction))
+                        continue
                     if out["target"] == "outlet":
                         if unit >= 0:
                             fl = L.hbo_add_flux(h, F_TO_OUTLET, 1, int(can_have_fraction(brick)),

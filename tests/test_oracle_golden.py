@@ -124,9 +124,10 @@ NEXT_CASES = sorted("next/" + p.stem for p in (gu.GOLDEN / "next").glob("*.npz")
 
 
 @pytest.mark.parametrize("name", NEXT_CASES)
-def test_oracle_matches_reference_on_the_melt_variants(name):
+def test_oracle_matches_reference_on_options_the_engine_lacks(name):
     """snow_melt_process = melt:degree_day_aspect / melt:temperature_index (ProcessMeltDegreeDayAspect.cpp,
-    ProcessMeltTemperatureIndex.cpp): the oracle is pinned bit for bit; the CUDA engine does not implement them yet and
+    ProcessMeltTemperatureIndex.cpp) and snow_redistribution = transport:snow_slide (ProcessLateralSnowSlide.cpp, lateral
+    connections between units): the oracle is pinned bit for bit; the CUDA engine does not implement them yet and
     refuses such structures (tests/golden/next is outside the engine's parity lists)."""
     from hydrobricks_b200 import structure
 

@@ -74,3 +74,19 @@ def test_oracle_melt_variants_bit_exact_against_compiled_reference(kind, solver,
     assert np.array_equal(om.outlet, q)
     for label in rec:
         assert np.array_equal(om.records[label], rec[label], equal_nan=True), label
+
+
+def test_oracle_snow_slide_bit_exact_against_compiled_reference():
+    import ref_melt_cases as rm
+    import ref_snow_slide_case as rs
+    import refpy
+
+    ref = refpy.load_extension("ref")
+    ref.init()
+    meta, forcing, q, rec = rs.run_reference(ref, "heun_explicit", glacier=True, nsoil=2, n_steps=500, skip_glaciers=False)
+    om = rm.run_oracle(meta, forcing, list(rec))
+    assert np.array_equal(om.outlet, q)
+    for label in rec:
+        assert np.array_equal(om.records[label], rec[label], equal_nan=True), label
+    snow = rec["ground_snowpack:snow_content"]
+    assert snow[-1, -1] > 4 * snow[-1, 0]  # the snow did slide to the lowest unit

@@ -45,6 +45,9 @@ def run_ref_module(ref, settings, units, forcing, labels_from_model=True):
             basin.add_hydro_unit_property_str("aspect_class", u["aspect_class"])
         for name, frac in u["land_covers"]:
             basin.add_land_cover(name, "", frac)
+    for u in units:  # lateral connections (hydro_units.py set_connectivity): (receiver position, fraction)
+        for receiver, fraction in u.get("lateral", []):
+            basin.add_lateral_connection(u["id"], units[receiver]["id"], fraction, "snow_slide")
     model = ref.ModelHydro()
     model.init_with_basin(settings, basin)
     n = len(next(iter(forcing.values())))
@@ -216,6 +219,17 @@ def melt_variant_bundles(ref):
             save(f"next/melt_{tag}_{solver}_{name}", meta, forcing, q, rec)
 
 
+def snow_slide_bundles(ref):
+    """transport:snow_slide (refused by the engine: it couples the units inside a step); oracle vectors only."""
+    import ref_snow_slide_case as rs
+
+    (OUT / "next").mkdir(parents=True, exist_ok=True)
+    for solver, kw, name in (("rk4", dict(glacier=True, nsoil=1), "glacier_1store"),
+                             ("crank_nicolson", dict(glacier=False, nsoil=2), "noglacier_2store")):
+        meta, forcing, q, rec = rs.run_reference(ref, solver, **kw)
+        save(f"next/snow_slide_{solver}_{name}", meta, forcing, q, rec)
+
+
 def main():
     hb = refpy.load_reference_python("ref")
     ref = sys.modules["hydrobricks._hydrobricks"]
@@ -224,6 +238,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "melt":
         melt_variant_bundles(ref)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "snow_slide":
+        snow_slide_bundles(ref)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "actions_new":
         action_bundles(ref, only_new=True)
@@ -283,6 +300,7 @@ def main():
     snow_ice_bundles(hb)
     sequential_bundles(hb, ref)
     melt_variant_bundles(ref)
+    snow_slide_bundles(ref)
 
 
 if __name__ == "__main__":
