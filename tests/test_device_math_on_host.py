@@ -195,3 +195,16 @@ def test_melt_variants_need_only_glue_around_the_step_functions(name, emul):
     _close(rec["snow"], records[f"{cs.ground_name}_snowpack:snow_content"])
     if cs.glacier_name:
         _close(rec["ice"], records[f"{cs.glacier_name}:ice_content"])
+
+
+def test_staged_instruction_diet_options_are_bit_identical(emul):
+    """-DHBK_OPT=6 (the two staged, unmeasured instruction-diet options of hbk_device.cuh) must not change a single bit
+    of any result: same outlet and storages as the default build on every golden."""
+    opt = build_emul("libhbkemul_opt.so", ("-DHBK_OPT=6",))
+    for name in CASES:
+        meta, forcing, _, _, _ = gu.load(name)
+        _, qa, ra, _ = run_emul(emul, meta, forcing)
+        _, qb, rb, _ = run_emul(opt, meta, forcing)
+        assert np.array_equal(qa, qb), name
+        for k in ra:
+            assert np.array_equal(ra[k], rb[k], equal_nan=True), (name, k)
