@@ -198,9 +198,9 @@ def test_melt_variants_need_only_glue_around_the_step_functions(name, emul):
 
 
 def test_staged_instruction_diet_options_are_bit_identical(emul):
-    """-DHBK_OPT=6 (the two staged, unmeasured instruction-diet options of hbk_device.cuh) must not change a single bit
+    """-DHBK_OPT=7 (the three staged, unmeasured instruction-diet options of hbk_device.cuh) must not change a single bit
     of any result: same outlet and storages as the default build on every golden."""
-    opt = build_emul("libhbkemul_opt.so", ("-DHBK_OPT=6",))
+    opt = build_emul("libhbkemul_opt.so", ("-DHBK_OPT=7",))
     for name in CASES:
         meta, forcing, _, _, _ = gu.load(name)
         _, qa, ra, _ = run_emul(emul, meta, forcing)
