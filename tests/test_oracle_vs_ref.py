@@ -90,3 +90,26 @@ def test_oracle_snow_slide_bit_exact_against_compiled_reference():
         assert np.array_equal(om.records[label], rec[label], equal_nan=True), label
     snow = rec["ground_snowpack:snow_content"]
     assert snow[-1, -1] > 4 * snow[-1, 0]  # the snow did slide to the lowest unit
+
+
+@pytest.mark.parametrize("solver", ["rk4", "crank_nicolson"])
+def test_oracle_spinup_bit_exact_against_compiled_reference(solver):
+    """ModelHydro::RunSpinup (ModelHydro.cpp:135-181): the first steps replayed unlogged, clock rewound, states kept."""
+    import ref_cases
+    import refpy
+    from oracle import hb_oracle
+
+    hb = refpy.load_reference_python("ref")
+    model, hu, forcing, _ = ref_cases.gsm_socont(hb, solver=solver, end_date="1982-03-31", n_units=8, soil_storage_nb=2,
+                                                 with_glacier=True, infinite_storage=False, spinup_days=200)
+    structures, units, fdata, q_ref, rec_ref = ref_cases.collect(model, hu, forcing)
+    om = hb_oracle.OracleModel(structures, units, solver, len(q_ref), spinup_steps=200)
+    for k, v in fdata.items():
+        om.set_forcing(k, v)
+    for label in rec_ref:
+        om.record(label)
+    q = om.run()
+    assert q_ref[0] > 0  # the run does not start from empty storages
+    assert np.array_equal(q, q_ref)
+    for label, ref in rec_ref.items():
+        assert np.array_equal(om.records[label], ref, equal_nan=True), label
