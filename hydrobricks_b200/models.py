@@ -37,7 +37,8 @@ class Socont:
     def __init__(self, solver="crank_nicolson", soil_storage_nb=1, surface_runoff="socont_runoff",
                  land_cover_names=None, land_cover_types=None, record_all=False, glacier_infinite_storage=True,
                  snow_melt_process="melt:degree_day", snow_ice_transformation=None, snow_sublimation_process=None,
-                 snow_redistribution=None, snow_redistribution_skip_glaciers=True, backend=None):
+                 snow_redistribution=None, snow_redistribution_skip_glaciers=True, snow_rain_process=None,
+                 backend=None):
         self.backend = resolve_backend(backend)
         self.solver = solver
         self.options = {"soil_storage_nb": soil_storage_nb, "surface_runoff": surface_runoff,
@@ -45,6 +46,7 @@ class Socont:
                         "snow_ice_transformation": snow_ice_transformation,
                         "snow_sublimation_process": snow_sublimation_process,
                         "snow_redistribution": snow_redistribution,
+                        "snow_rain_process": snow_rain_process,  # model_settings.py:194-200; None -> snow_rain:linear
                         "snow_redistribution_skip_glaciers": snow_redistribution_skip_glaciers}
         self.land_cover_names = list(land_cover_names or ["open"])
         self.land_cover_types = list(land_cover_types or ["open"])
@@ -110,7 +112,7 @@ class Socont:
         for i, (names, types, structure) in enumerate(self._variants()):
             if i > 0:
                 s.add_structure()
-            s.generate_precipitation_splitters(True, "snow_rain:linear")
+            s.generate_precipitation_splitters(True, self.options["snow_rain_process"] or "snow_rain:linear")
             for t, n in zip(types, names):
                 s.add_land_cover_brick(n, "generic_land_cover" if t in ("ground", "generic_land_cover", "open",
                                                                         "forest", "lake") else t)

@@ -118,7 +118,8 @@ def test_structure_variant_assignment():
     assert gv == expect and 0 < sum(gv) < len(gv)
 
 
-COMPILER_CASES = [b for b in gu.bundles() if not b.startswith(("c1_", "kat_"))]
+COMPILER_CASES = [b for b in gu.bundles() if not b.startswith(("c1_", "kat_"))] + \
+    sorted("next/" + p.stem for p in (gu.GOLDEN / "next").glob("splitter_threshold_*.npz"))
 
 
 @pytest.mark.parametrize("name", COMPILER_CASES)

@@ -136,5 +136,8 @@ def test_oracle_matches_reference_on_options_the_engine_lacks(name):
     assert gu.same(om.outlet, outlet)
     for label, ref in records.items():
         assert gu.same(om.records[label], ref), label
-    with pytest.raises(structure.UnsupportedStructure):
-        structure.CompiledStructure(meta["structures"], meta["solver"])
+    if name.startswith(("next/melt_", "next/snow_slide_")):
+        with pytest.raises(structure.UnsupportedStructure):
+            structure.CompiledStructure(meta["structures"], meta["solver"])
+    else:  # next/splitter_threshold_*: in the engine, waiting for its first GPU run
+        assert structure.CompiledStructure(meta["structures"], meta["solver"]).hbk.splitter_kind == 1

@@ -230,6 +230,18 @@ def snow_slide_bundles(ref):
         save(f"next/snow_slide_{solver}_{name}", meta, forcing, q, rec)
 
 
+def threshold_splitter_bundles(ref):
+    """snow_rain:threshold instead of the linear transition: supported by the engine since the first kernels but never
+    pinned by a vector before; kept under tests/golden/next/ until its GPU test has run on a B200."""
+    import ref_threshold_case as rt
+
+    (OUT / "next").mkdir(parents=True, exist_ok=True)
+    for solver, kw, name in (("rk4", dict(glacier=True, nsoil=1), "glacier_1store"),
+                             ("heun_explicit", dict(glacier=False, nsoil=2), "noglacier_2store")):
+        meta, forcing, q, rec = rt.run_reference(ref, solver, **kw)
+        save(f"next/splitter_threshold_{solver}_{name}", meta, forcing, q, rec)
+
+
 def main():
     hb = refpy.load_reference_python("ref")
     ref = sys.modules["hydrobricks._hydrobricks"]
@@ -238,6 +250,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "melt":
         melt_variant_bundles(ref)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "threshold":
+        threshold_splitter_bundles(ref)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "snow_slide":
         snow_slide_bundles(ref)
@@ -301,6 +316,7 @@ def main():
     sequential_bundles(hb, ref)
     melt_variant_bundles(ref)
     snow_slide_bundles(ref)
+    threshold_splitter_bundles(ref)
 
 
 if __name__ == "__main__":
