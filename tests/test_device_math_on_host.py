@@ -210,13 +210,18 @@ def test_staged_instruction_diet_options_are_bit_identical(emul):
             assert np.array_equal(ra[k], rb[k], equal_nan=True), (name, k)
 
 
-@pytest.mark.parametrize("name", sorted("next/" + p.stem for p in (gu.GOLDEN / "next").glob("splitter_threshold_*.npz")))
-def test_threshold_splitter_on_host_matches_reference(name, emul):
-    """snow_rain:threshold (SplitterSnowRainThreshold.cpp:45-54, hbk_structure.splitter_kind = 1): the device step
-    functions against vectors of the reference."""
+PENDING_GPU = sorted("next/" + p.stem for pat in ("splitter_threshold_*.npz", "slow_order_*.npz")
+                     for p in (gu.GOLDEN / "next").glob(pat))
+
+
+@pytest.mark.parametrize("name", PENDING_GPU)
+def test_threshold_splitter_and_helper_process_order_on_host(name, emul):
+    """snow_rain:threshold (SplitterSnowRainThreshold.cpp:45-54, hbk_structure.splitter_kind = 1) and the slow-reservoir
+    process order of core/tests/src/helpers.cpp (slow_process_order = 1): the device step functions against vectors of
+    the reference."""
     meta, forcing, outlet, records, _ = gu.load(name)
     cs, q, rec, _ = run_emul(emul, meta, forcing)
-    assert cs.hbk.splitter_kind == 1
+    assert (cs.hbk.splitter_kind == 1) if "threshold" in name else (cs.hbk.slow_process_order == 1)
     _close(q, outlet)
     _close(rec["slow"], records["slow_reservoir:water_content"])
     _close(rec["snow"], records[f"{cs.ground_name}_snowpack:snow_content"])

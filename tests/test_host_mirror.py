@@ -119,7 +119,8 @@ def test_structure_variant_assignment():
 
 
 COMPILER_CASES = [b for b in gu.bundles() if not b.startswith(("c1_", "kat_"))] + \
-    sorted("next/" + p.stem for p in (gu.GOLDEN / "next").glob("splitter_threshold_*.npz"))
+    sorted("next/" + p.stem for pat in ("splitter_threshold_*.npz", "slow_order_*.npz")
+           for p in (gu.GOLDEN / "next").glob(pat))
 
 
 @pytest.mark.parametrize("name", COMPILER_CASES)

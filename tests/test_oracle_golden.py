@@ -139,5 +139,6 @@ def test_oracle_matches_reference_on_options_the_engine_lacks(name):
     if name.startswith(("next/melt_", "next/snow_slide_")):
         with pytest.raises(structure.UnsupportedStructure):
             structure.CompiledStructure(meta["structures"], meta["solver"])
-    else:  # next/splitter_threshold_*: in the engine, waiting for its first GPU run
-        assert structure.CompiledStructure(meta["structures"], meta["solver"]).hbk.splitter_kind == 1
+    else:  # next/splitter_threshold_*, next/slow_order_*: in the engine, waiting for their first GPU run
+        cs = structure.CompiledStructure(meta["structures"], meta["solver"])
+        assert (cs.hbk.splitter_kind == 1) if "threshold" in name else (cs.hbk.slow_process_order == 1)

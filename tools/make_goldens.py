@@ -242,6 +242,16 @@ def threshold_splitter_bundles(ref):
         save(f"next/splitter_threshold_{solver}_{name}", meta, forcing, q, rec)
 
 
+def slow_order_bundles(ref):
+    """hbk_structure.slow_process_order = 1 (the process order of core/tests/src/helpers.cpp), two soil stores."""
+    import ref_slow_order_case as ro
+
+    (OUT / "next").mkdir(parents=True, exist_ok=True)
+    for solver in ("rk4", "crank_nicolson"):
+        meta, forcing, q, rec = ro.run_reference(ref, solver)
+        save(f"next/slow_order_{solver}_noglacier_2store", meta, forcing, q, rec)
+
+
 def main():
     hb = refpy.load_reference_python("ref")
     ref = sys.modules["hydrobricks._hydrobricks"]
@@ -250,6 +260,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "melt":
         melt_variant_bundles(ref)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "slow_order":
+        slow_order_bundles(ref)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "threshold":
         threshold_splitter_bundles(ref)
@@ -317,6 +330,7 @@ def main():
     melt_variant_bundles(ref)
     snow_slide_bundles(ref)
     threshold_splitter_bundles(ref)
+    slow_order_bundles(ref)
 
 
 if __name__ == "__main__":
