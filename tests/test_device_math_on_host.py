@@ -225,3 +225,20 @@ def test_threshold_splitter_and_helper_process_order_on_host(name, emul):
     _close(q, outlet)
     _close(rec["slow"], records["slow_reservoir:water_content"])
     _close(rec["snow"], records[f"{cs.ground_name}_snowpack:snow_content"])
+
+
+def test_c1_full_period_on_host(emul):
+    """BASELINE config C1 (ch_sitter_appenzell, 35 elevation bands, 1981-2020 = 14 610 daily steps, RK4): the device
+    arithmetic over the whole 40 years against the reference's outlet, forcing rebuilt from the station series with the
+    reference's formulas (forcing.py:1061-1113) as in tests/test_oracle_golden.py."""
+    meta, _, outlet, _, extra = gu.load("c1_sitter_rk4_full")
+    elev = np.array([u["elevation"] for u in meta["units"]])
+    sp = meta["spatialisation"]
+    t = extra["station_t"][:, None] + sp["temperature"]["gradient"] * (elev - sp["temperature"]["ref_elevation"]) / 100
+    p = extra["station_p"][:, None] * sp["precipitation"]["correction_factor"]
+    p = p * (1 + sp["precipitation"]["gradient"] * (elev - sp["precipitation"]["ref_elevation"]) / 100)
+    p[p < 0] = 0
+    pet = np.repeat(extra["station_pet"][:, None], len(elev), axis=1)
+    _, q, _, unconverged = run_emul(emul, meta, {"p": p, "t": t, "pet": pet})
+    assert len(q) == 14610 and unconverged == 0
+    _close(q, outlet)
