@@ -113,3 +113,44 @@ def test_oracle_spinup_bit_exact_against_compiled_reference(solver):
     assert np.array_equal(q, q_ref)
     for label, ref in rec_ref.items():
         assert np.array_equal(om.records[label], ref, equal_nan=True), label
+
+
+@pytest.mark.parametrize("solver", ["rk4", "crank_nicolson"])
+def test_oracle_two_day_step_bit_exact_against_compiled_reference(solver):
+    """A time step of two days (TimeMachine step 2 'day'): the oracle's dt handling against the reference, including the
+    reference's own artefacts at that step length (land-cover water driven negative by a direct outflow of content/day
+    over two days, logged and reset to 0, WaterContainer.cpp:212-215)."""
+    import ref_threshold_case as rt
+    import refpy
+    from oracle import hb_oracle
+
+    ref = refpy.load_extension("ref")
+    ref.init()
+    n = 200
+    m, units, forcing = rt.build(ref, solver, glacier=True, nsoil=2, n_steps=n)
+    s = m.settings
+    s.set_timer("1981-01-01", str(np.datetime64("1981-01-01") + np.timedelta64(2 * (n - 1), "D")), 2, "day")
+    basin = ref.SettingsBasin()
+    for u in units:
+        basin.add_hydro_unit(u["id"], u["area"], u["elevation"])
+        basin.add_hydro_unit_property_double("slope", u["slope"][0], u["slope"][1])
+        for name, frac in u["land_covers"]:
+            basin.add_land_cover(name, "", frac)
+    model = ref.ModelHydro()
+    model.init_with_basin(s, basin)
+    time = 44605.0 + 2.0 * np.arange(n)
+    ids = np.array([u["id"] for u in units], dtype=np.int32)
+    for k, v in forcing.items():
+        assert model.create_time_series(k, time, ids, np.ascontiguousarray(v))
+    assert model.attach_time_series_to_hydro_units()
+    model.run()
+    q_ref = np.asarray(model.get_outlet_discharge())
+    rec = {label: model.get_hydro_unit_values(label) for label in model.get_recorded_hydro_unit_labels()}
+    om = hb_oracle.OracleModel(s.get_structure(), units, solver, n, dt=2.0)
+    for k, v in forcing.items():
+        om.set_forcing(k, v)
+    for label in rec:
+        om.record(label)
+    assert np.array_equal(om.run(), q_ref)
+    for label, r in rec.items():
+        assert np.array_equal(om.records[label], r, equal_nan=True), label
