@@ -117,6 +117,18 @@ __device__ __forceinline__ void tmaLoad1D(void* dst, const void* src, uint32_t b
                  : "memory");
 }
 
+// Snowpack sublimation rates of one step (sublimation:constant: the parameter; sublimation:pet: PET x the parameter,
+// float32 promoted; ProcessSublimation{Constant,PET}.cpp). Out of line and read from global memory at use, so that the
+// kernels of structures without the option carry neither the registers nor predicated instructions for it.
+template <bool GLACIER>
+__device__ __noinline__ double2 sublimationRates(const float* params, int ldp, int kind, int p, double pet) {
+    const double scale = (kind == HBK_SUBLIMATION_PET) ? pet : 1.0;
+    double2 r;
+    r.x = scale * (double)params[p + (size_t)HBK_P_GROUND_SUBLIMATION * ldp];
+    r.y = GLACIER ? scale * (double)params[p + (size_t)HBK_P_GLACIER_SUBLIMATION * ldp] : 0.0;
+    return r;
+}
+
 // ---- main kernel ------------------------------------------------------------------------------------
 // Block = PB parameter sets x UB units (threads), time-multiplexed over a GROUP of G consecutive unit tiles:
 //   for each chunk of TC steps: for each tile of the group: [load state] TC steps [store state], add the tile's
@@ -125,42 +137,48 @@ __device__ __forceinline__ void tmaLoad1D(void* dst, const void* src, uint32_t b
 // buffers, no second pass. With G = 1 (few sets, many units) the state never leaves the registers.
 // DAILY: the time step is exactly one day (the reference's usual case); x * 1.0 and x / 1.0 are exact, so the
 // multiplications by dt fold away without changing a bit.
-template <int SOLVER, int NSOIL, bool GLACIER, bool DAILY>
+template <int SOLVER, int NSOIL, bool GLACIER, bool DAILY, bool ENS>
 __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLACIER : HBK_MIN_BLOCKS)
     hbkRunUnits(const KArgs a) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     constexpr int NQ = GLACIER ? 3 : 1;
+    // ENS: the block shape of calibration ensembles fixed at compile time — 32 parameter sets (lanes) x 4 units, 16 steps per
+    // chunk, station forcing with fused spatialisation, no cluster — so that the address arithmetic of the time loop
+    // folds into immediates (at 80 registers ptxas otherwise re-derives it from the kernel arguments at every step)
+    const int PB = ENS ? 32 : a.PB, UB = ENS ? 4 : a.UB, TC = ENS ? 16 : a.TC;
+    const int forcingMode = ENS ? 1 : a.forcingMode;
+    const bool clusterMode = ENS ? false : (a.clusterMode != 0);
     const int tid = threadIdx.x;
-    const int nThreads = blockDim.x;  // PB * UB
+    const int nThreads = ENS ? 128 : blockDim.x;  // PB * UB
     // cluster mode: the cluster's CTAs are the unit tiles of one parameter-set group; every CTA keeps its tile's
     // state in registers for the whole segment and the outlet is reduced through distributed shared memory.
-    const int grp = a.clusterMode ? 0 : blockIdx.x % a.nGroups;
-    const int pg = a.clusterMode ? blockIdx.x / a.nUTiles : blockIdx.x / a.nGroups;
-    const int crank = a.clusterMode ? blockIdx.x % a.nUTiles : 0;
-    const int pl = tid % a.PB;
-    const int ul = tid / a.PB;
-    const int p = pg * a.PB + pl;
+    const int grp = clusterMode ? 0 : blockIdx.x % a.nGroups;
+    const int pg = clusterMode ? blockIdx.x / a.nUTiles : blockIdx.x / a.nGroups;
+    const int crank = clusterMode ? blockIdx.x % a.nUTiles : 0;
+    const int pl = tid % PB;
+    const int ul = tid / PB;
+    const int p = pg * PB + pl;
     const bool validP = p < a.P;
     const int pOut = (validP && a.perm) ? a.perm[p] : p;  // the caller's index of this parameter set
-    const int tileBegin = a.clusterMode ? crank : grp * a.G;
-    const int tileEnd = a.clusterMode ? crank + 1 : min(tileBegin + a.G, a.nUTiles);
-    const bool multi = !a.clusterMode && a.G > 1;
+    const int tileBegin = clusterMode ? crank : grp * a.G;
+    const int tileEnd = clusterMode ? crank + 1 : min(tileBegin + a.G, a.nUTiles);
+    const bool multi = !clusterMode && a.G > 1;
 
     // shared memory carve-up
     uint64_t* bars = reinterpret_cast<uint64_t*>(smemRaw);  // 2 mbarriers
-    const int fRow = (a.forcingMode == 0) ? a.TC * a.UB : (a.TC + 2);  // doubles per variable per stage
+    const int fRow = (forcingMode == 0) ? TC * UB : (TC + 2);  // doubles per variable per stage
     double* fbuf = reinterpret_cast<double*>(smemRaw + 128);             // [2][3][fRow]
     double* qbuf = fbuf + 2 * 3 * fRow;                                  // [NQ][TC][nThreads]
-    double* accb = qbuf + (size_t)NQ * a.TC * nThreads;                  // cluster mode only: [2][NQ][TC][PB]
+    double* accb = qbuf + (size_t)NQ * TC * nThreads;                  // cluster mode only: [2][NQ][TC][PB]
 
     // per-parameter-set constants: shared memory [field][PB] (or registers, HBK_PAR_SHARED=0)
-    double* sPar = accb + (size_t)(a.clusterMode ? 2 : 0) * NQ * a.TC * a.PB;
+    double* sPar = accb + (size_t)(clusterMode ? 2 : 0) * NQ * TC * PB;
     Par par;
     double quickBase = 0, gT = 0, gP = 0, corr = 1;
     {
 #if HBK_PAR_SHARED
         double* pv = sPar + pl;
-        const int ps = a.PB;
+        const int ps = PB;
         par.b = pv;
         par.s = ps;
         const bool fill = validP && ul == 0;
@@ -194,7 +212,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
         if (validP) {
             quickBase = a.params[p + (size_t)HBK_P_QUICK * a.ldp];
             par.quickV = quickBase;
-            if (a.forcingMode == 1) {
+            if (forcingMode == 1) {
                 gT = a.gradT ? a.gradT[pOut] : a.gradTs;
                 gP = a.gradP ? a.gradP[pOut] : a.gradPs;
                 corr = a.corrP ? a.corrP[pOut] : a.corrPs;
@@ -204,10 +222,11 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
 
     // per-(set, unit) values, (re)loaded per tile when the block time-multiplexes several tiles
     Hru h;
-    double fa = 0, fG = 1, fGl = 0, cT = 0, mP = 1;
+    double fa = 0, faW = 0, fG = 1, fGl = 0, cT = 0, mP = 1;  // faW: weight of the outlet fluxes (Flux.cpp:20-26)
     bool glacierVariant = false;
     auto loadUnit = [&](int u) {
         fa = a.hru[0 * a.ldu + u];
+        faW = (fa < 1.0) ? fa : 1.0;
         const double area = a.hru[1 * a.ldu + u];
         const double slopeTerm = a.hru[2 * a.ldu + u];
         const double elev = a.hru[3 * a.ldu + u];
@@ -218,7 +237,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
         const long long fi = a.fracPerSet ? ((long long)p * a.U + u) : u;
         fG = a.frac[fi];
         fGl = a.frac[a.fracLd + fi];
-        if (a.forcingMode == 1) {
+        if (forcingMode == 1) {
             // forcing.py:1073-1075 / 1104-1106: g*(z - zref) -> /100 -> (1 + ...) -> x * ...
             cT = gT * (elev - a.zrefT) / 100;
             mP = 1 + gP * (elev - a.zrefP) / 100;
@@ -285,28 +304,28 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
     const double dt = DAILY ? 1.0 : a.dt;
     const double invDt = DAILY ? 1.0 : 1.0 / a.dt;
     const int nSteps = a.tEnd - a.tBegin;
-    const int nChunks = (nSteps + a.TC - 1) / a.TC;
+    const int nChunks = (nSteps + TC - 1) / TC;
     const int nTilesHere = tileEnd - tileBegin;
     // forcing pipeline: one load per chunk (station series) or per (chunk, tile) (per-unit series)
-    const int nLoads = (a.forcingMode == 0) ? nChunks * nTilesHere : nChunks;
+    const int nLoads = (forcingMode == 0) ? nChunks * nTilesHere : nChunks;
 
     auto issueLoad = [&](int seq) {
         const int stage = seq & 1;
         double* dst = fbuf + (size_t)stage * 3 * fRow;
-        if (a.forcingMode == 0) {
+        if (forcingMode == 0) {
             const int c = seq / nTilesHere, tile = tileBegin + seq % nTilesHere;
-            const int t0 = a.tBegin + c * a.TC;
-            const int n = min(a.TC, a.tEnd - t0);
-            const uint32_t bytes = (uint32_t)(n * a.UB * sizeof(double));
+            const int t0 = a.tBegin + c * TC;
+            const int n = min(TC, a.tEnd - t0);
+            const uint32_t bytes = (uint32_t)(n * UB * sizeof(double));
             mbarExpectTx(&bars[stage], 3 * bytes);
             for (int v = 0; v < 3; ++v) {
-                const double* src = a.forcing[v] + ((size_t)tile * a.tld + t0) * a.UB;
+                const double* src = a.forcing[v] + ((size_t)tile * a.tld + t0) * UB;
                 tmaLoad1D(dst + (size_t)v * fRow, src, bytes, &bars[stage]);
             }
         } else {
-            const int t0 = a.tBegin + seq * a.TC;
+            const int t0 = a.tBegin + seq * TC;
             const int t0a = t0 & ~1;  // 16-byte aligned source
-            const uint32_t bytes = (uint32_t)((a.TC + 2) * sizeof(double));
+            const uint32_t bytes = (uint32_t)((TC + 2) * sizeof(double));
             mbarExpectTx(&bars[stage], 3 * bytes);
             for (int v = 0; v < 3; ++v) tmaLoad1D(dst + (size_t)v * fRow, a.forcing[v] + t0a, bytes, &bars[stage]);
         }
@@ -326,16 +345,16 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
     bool loaded = false;
 
     for (int c = 0; c < nChunks; ++c) {
-        const int t0 = a.tBegin + c * a.TC;
-        const int n = min(a.TC, a.tEnd - t0);
-        const int off = (a.forcingMode == 1) ? (t0 & 1) : 0;
+        const int t0 = a.tBegin + c * TC;
+        const int n = min(TC, a.tEnd - t0);
+        const int off = (forcingMode == 1) ? (t0 & 1) : 0;
         for (int tl = 0; tl < nTilesHere; ++tl) {
             const int tile = tileBegin + tl;
-            const int u = tile * a.UB + ul;
+            const int u = tile * UB + ul;
             const bool valid = validP && (u < a.U);
             // ---- forcing for this (chunk, tile) ----
-            const int seq = (a.forcingMode == 0) ? c * nTilesHere + tl : c;
-            if (a.forcingMode == 0 || tl == 0) {
+            const int seq = (forcingMode == 0) ? c * nTilesHere + tl : c;
+            if (forcingMode == 0 || tl == 0) {
                 if (tid == 0 && seq + 1 < nLoads) issueLoad(seq + 1);
                 mbarWait(&bars[seq & 1], (seq >> 1) & 1);
             }
@@ -346,38 +365,37 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
             }
             loaded = true;
 
+            // this thread's forcing column in the staged chunk (per-unit series: its unit's column; station series: the
+            // shared series, spatialised below) and its outlet slots
+            const double* fcol = fs + ((forcingMode == 0) ? ul : off);
+            const int fStep = (forcingMode == 0) ? UB : 1;
+            double* slotCol = qbuf + tid;
             for (int tc = 0; tc < n; ++tc) {
                 StepOut o;
                 o.q = 0.0;
                 o.dep1 = 0.0;
                 o.dep2 = 0.0;
                 if (valid) {
-                    double precip, temp, pet;
-                    if (a.forcingMode == 0) {
-                        precip = fs[0 * fRow + tc * a.UB + ul];
-                        temp = fs[1 * fRow + tc * a.UB + ul];
-                        pet = fs[2 * fRow + tc * a.UB + ul];
-                    } else {
-                        const double xp = fs[0 * fRow + tc + off];
-                        const double xt = fs[1 * fRow + tc + off];
-                        const double xe = fs[2 * fRow + tc + off];
-                        temp = xt + cT;
-                        precip = (xp * corr) * mP;
+                    const double* fp = fcol + tc * fStep;
+                    double precip = fp[0], temp = fp[fRow], pet = fp[2 * fRow];
+                    if (forcingMode != 0) {  // fused spatialisation (forcing.py:1061-1113)
+                        temp = temp + cT;
+                        precip = (precip * corr) * mP;
                         precip = (precip < 0.0) ? 0.0 : precip;
-                        pet = (xe < 0.0) ? 0.0 : xe;
+                        pet = (pet < 0.0) ? 0.0 : pet;
                     }
                     double sublimG = 0.0, sublimGl = 0.0;
-                    if (a.flags.sublimKind != 0) {  // rate = parameter, or PET x parameter (float32 promoted)
-                        const double scale = (a.flags.sublimKind == HBK_SUBLIMATION_PET) ? pet : 1.0;
-                        sublimG = scale * (double)a.params[p + (size_t)HBK_P_GROUND_SUBLIMATION * a.ldp];
-                        if (GLACIER) sublimGl = scale * (double)a.params[p + (size_t)HBK_P_GLACIER_SUBLIMATION * a.ldp];
+                    if (a.flags.sublimKind != 0) {
+                        const double2 su = sublimationRates<GLACIER>(a.params, a.ldp, a.flags.sublimKind, p, pet);
+                        sublimG = su.x;
+                        sublimGl = su.y;
                     }
                     directPhase<GLACIER>(h, par, precip, temp, dt, invDt, fa, fG, fGl, glacierVariant, a.flags, o, err,
                                          (GLACIER && a.swatFactor) ? a.swatFactor[t0 + tc] : 0.0, sublimG, sublimGl);
                     if constexpr (SOLVER == 3) {
-                        solveUnitSequential<NSOIL>(h, par, pet, fa, dt, invDt, a.flags, o, err);
+                        solveUnitSequential<NSOIL>(h, par, pet, faW, dt, invDt, a.flags, o, err);
                     } else {
-                        solveUnit<SOLVER, NSOIL>(h, par, pet, fa, dt, invDt, a.flags, o, err, unconverged);
+                        solveUnit<SOLVER, NSOIL>(h, par, pet, faW, dt, invDt, a.flags, o, err, unconverged);
                     }
 
                     if (nRec && a.writeOutputs) {
@@ -423,28 +441,35 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
                     }
                 }
                 // this thread's slot accumulates its units of the group's tiles in tile order (no race: own slot)
-                double* slot = qbuf + (size_t)tc * nThreads + tid;
-                const bool first = a.clusterMode || tl == 0;
-                slot[0] = first ? o.q : slot[0] + o.q;
+                double* slot = slotCol + (size_t)tc * nThreads;
+                const bool first = clusterMode || tl == 0;
+                if (!first) o.q += slot[0];  // slot + x == x + slot
+                slot[0] = o.q;
                 if (GLACIER) {
-                    slot[(size_t)a.TC * nThreads] = first ? o.dep1 : slot[(size_t)a.TC * nThreads] + o.dep1;
-                    slot[(size_t)2 * a.TC * nThreads] = first ? o.dep2 : slot[(size_t)2 * a.TC * nThreads] + o.dep2;
+                    double* s1 = slot + (size_t)TC * nThreads;
+                    double* s2 = s1 + (size_t)TC * nThreads;
+                    if (!first) {
+                        o.dep1 += s1[0];
+                        o.dep2 += s2[0];
+                    }
+                    s1[0] = o.dep1;
+                    s2[0] = o.dep2;
                 }
             }
             if (valid && multi) storeState(u, c == nChunks - 1);
-            if (a.clusterMode) {
+            if (clusterMode) {
                 __syncthreads();
                 // this CTA's tile sum -> its partial buffer (double buffered by chunk parity) ...
-                double* part = accb + (size_t)(c & 1) * NQ * a.TC * a.PB;
-                for (int idx = tid; idx < NQ * n * a.PB; idx += nThreads) {
-                    const int qi = idx / (n * a.PB);
-                    const int rem = idx - qi * n * a.PB;
-                    const int tc = rem / a.PB;
-                    const int lp = rem - tc * a.PB;
-                    const double* src = qbuf + ((size_t)qi * a.TC + tc) * nThreads + lp;
+                double* part = accb + (size_t)(c & 1) * NQ * TC * PB;
+                for (int idx = tid; idx < NQ * n * PB; idx += nThreads) {
+                    const int qi = idx / (n * PB);
+                    const int rem = idx - qi * n * PB;
+                    const int tc = rem / PB;
+                    const int lp = rem - tc * PB;
+                    const double* src = qbuf + ((size_t)qi * TC + tc) * nThreads + lp;
                     double s = 0.0;
-                    for (int k = 0; k < a.UB; ++k) s += src[(size_t)k * a.PB];
-                    part[((size_t)qi * a.TC + tc) * a.PB + lp] = s;
+                    for (int k = 0; k < UB; ++k) s += src[(size_t)k * PB];
+                    part[((size_t)qi * TC + tc) * PB + lp] = s;
                 }
                 // ... then the rows (quantity, step) are dealt round-robin to the cluster's CTAs, which add the
                 // tiles' partials in tile order through DSMEM and write the final series.
@@ -454,12 +479,12 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
                 const int nRows = NQ * n;
                 for (int row = crank; row < nRows; row += a.nUTiles) {
                     const int qi = row / n, tc = row - qi * n;
-                    for (int lp = tid; lp < a.PB; lp += nThreads) {
-                        const int gp = pg * a.PB + lp;
+                    for (int lp = tid; lp < PB; lp += nThreads) {
+                        const int gp = pg * PB + lp;
                         double s = 0.0;
                         for (int k = 0; k < a.nUTiles; ++k) {
                             const double* remote = cluster.map_shared_rank(part, k);
-                            s += remote[((size_t)qi * a.TC + tc) * a.PB + lp];
+                            s += remote[((size_t)qi * TC + tc) * PB + lp];
                         }
                         if (gp < a.P && (a.writeOutputs || qi > 0)) {
                             double* dst = (qi == 0) ? a.outQ : (qi == 1 ? a.outD1 : a.outD2);
@@ -475,15 +500,15 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
             const bool last = (tl == nTilesHere - 1);
             if (last) {
                 __syncthreads();
-                for (int idx = tid; idx < NQ * n * a.PB; idx += nThreads) {
-                    const int qi = idx / (n * a.PB);
-                    const int rem = idx - qi * n * a.PB;
-                    const int tc = rem / a.PB;
-                    const int lp = rem - tc * a.PB;
-                    const double* src = qbuf + ((size_t)qi * a.TC + tc) * nThreads + lp;
+                for (int idx = tid; idx < NQ * n * PB; idx += nThreads) {
+                    const int qi = idx / (n * PB);
+                    const int rem = idx - qi * n * PB;
+                    const int tc = rem / PB;
+                    const int lp = rem - tc * PB;
+                    const double* src = qbuf + ((size_t)qi * TC + tc) * nThreads + lp;
                     double s = 0.0;
-                    for (int k = 0; k < a.UB; ++k) s += src[(size_t)k * a.PB];
-                    const int gp = pg * a.PB + lp;
+                    for (int k = 0; k < UB; ++k) s += src[(size_t)k * PB];
+                    const int gp = pg * PB + lp;
                     if (gp < a.P && (a.writeOutputs || qi > 0)) {  // deposits feed the basin stores during spin-up
                         double* dst = (qi == 0) ? a.outQ : (qi == 1 ? a.outD1 : a.outD2);
                         const int row = (qi == 0 && a.outQFinal && a.perm) ? a.perm[gp] : gp;
@@ -493,13 +518,13 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
                 }
             }
             // the slots are rewritten by the next chunk; per-unit forcing stages are recycled tile by tile
-            if (last || a.forcingMode == 0) __syncthreads();
+            if (last || forcingMode == 0) __syncthreads();
         }
     }
 
-    if (a.clusterMode) cooperative_groups::this_cluster().sync();  // peers may still be reading this CTA's partials
+    if (clusterMode) cooperative_groups::this_cluster().sync();  // peers may still be reading this CTA's partials
     if (validP && !multi && nTilesHere > 0) {
-        const int u = tileBegin * a.UB + ul;
+        const int u = tileBegin * UB + ul;
         if (u < a.U) storeState(u, true);
     }
     if (err) atomicOr(a.err, err);
@@ -923,6 +948,8 @@ struct hbk_engine {
     double* dGradT = nullptr;
     double* dGradP = nullptr;
     double* dCorrP = nullptr;
+    int perSetDroppedVars = 0;   // bit var: that variable's per-set arrays were freed
+    bool perSetDropped = false;  // per-set gradients / corrections were configured, then freed by a change of n_sets
     double gradTs = 0, gradPs = 0, corrPs = 1, zrefT = 0, zrefP = 0;
     long long tld = 0;
     double* dState = nullptr;      // [HBK_N_STATES][P*U]
@@ -1077,31 +1104,36 @@ size_t smemBytes(const hbk_engine* e, bool tiled) {
 using KernelFn = void (*)(const KArgs);
 
 template <int SOLVER, int NSOIL, bool GLACIER>
-KernelFn pickDaily(bool daily) {
+KernelFn pickDaily(bool daily, bool ens) {
     // the sequential solvers (SOLVER 3) are not the throughput path: one instantiation, dt read at run time
     if constexpr (SOLVER == 3) {
-        return (KernelFn)hbkRunUnits<SOLVER, NSOIL, GLACIER, false>;
+        return (KernelFn)hbkRunUnits<SOLVER, NSOIL, GLACIER, false, false>;
     } else {
-        return daily ? (KernelFn)hbkRunUnits<SOLVER, NSOIL, GLACIER, true>
-                     : (KernelFn)hbkRunUnits<SOLVER, NSOIL, GLACIER, false>;
+        // the compile-time ensemble shape exists for daily steps only (the case ensembles are run in)
+        if (daily && ens) return (KernelFn)hbkRunUnits<SOLVER, NSOIL, GLACIER, true, true>;
+        return daily ? (KernelFn)hbkRunUnits<SOLVER, NSOIL, GLACIER, true, false>
+                     : (KernelFn)hbkRunUnits<SOLVER, NSOIL, GLACIER, false, false>;
     }
 }
 template <int SOLVER, int NSOIL>
-KernelFn pickGlacier(bool glacier, bool daily) {
-    return glacier ? pickDaily<SOLVER, NSOIL, true>(daily) : pickDaily<SOLVER, NSOIL, false>(daily);
+KernelFn pickGlacier(bool glacier, bool daily, bool ens) {
+    return glacier ? pickDaily<SOLVER, NSOIL, true>(daily, ens) : pickDaily<SOLVER, NSOIL, false>(daily, ens);
 }
 template <int SOLVER>
-KernelFn pickSoil(int nSoil, bool glacier, bool daily) {
-    return nSoil == 2 ? pickGlacier<SOLVER, 2>(glacier, daily) : pickGlacier<SOLVER, 1>(glacier, daily);
+KernelFn pickSoil(int nSoil, bool glacier, bool daily, bool ens) {
+    return nSoil == 2 ? pickGlacier<SOLVER, 2>(glacier, daily, ens) : pickGlacier<SOLVER, 1>(glacier, daily, ens);
 }
 // "Device functions selected from a per-structure process table": the table (hbk_structure) picks the
-// template instantiation, i.e. which process device functions are compiled into the time loop.
-KernelFn pickKernel(const hbk_structure& st) {
+// template instantiation, i.e. which process device functions are compiled into the time loop. ens: the launch has the
+// ensemble block shape (32 sets x 4 units, 16-step chunks, station forcing, no cluster) that one instantiation per
+// structure fixes at compile time.
+KernelFn pickKernel(const hbk_structure& st, bool ens) {
+    const bool daily = st.time_step_days == 1.0, glacier = st.has_glacier != 0;
     switch (st.solver) {
-        case HBK_SOLVER_EULER: return pickSoil<0>(st.n_soil_stores, st.has_glacier != 0, st.time_step_days == 1.0);
-        case HBK_SOLVER_HEUN: return pickSoil<1>(st.n_soil_stores, st.has_glacier != 0, st.time_step_days == 1.0);
-        case HBK_SOLVER_RK4: return pickSoil<2>(st.n_soil_stores, st.has_glacier != 0, st.time_step_days == 1.0);
-        default: return pickSoil<3>(st.n_soil_stores, st.has_glacier != 0, false);  // sequential family
+        case HBK_SOLVER_EULER: return pickSoil<0>(st.n_soil_stores, glacier, daily, ens);
+        case HBK_SOLVER_HEUN: return pickSoil<1>(st.n_soil_stores, glacier, daily, ens);
+        case HBK_SOLVER_RK4: return pickSoil<2>(st.n_soil_stores, glacier, daily, ens);
+        default: return pickSoil<3>(st.n_soil_stores, glacier, false, false);  // sequential family
     }
 }
 
@@ -1138,6 +1170,9 @@ int ensureSetBuffers(hbk_engine* e, int P) {
     freeDev(e->dPartD1);
     freeDev(e->dPartD2);
     freeDev(e->dRec);
+    if (e->dGradT) e->perSetDroppedVars |= 1 << HBK_VAR_TEMPERATURE;
+    if (e->dGradP || e->dCorrP) e->perSetDroppedVars |= 1 << HBK_VAR_PRECIPITATION;
+    if (e->perSetDroppedVars) e->perSetDropped = true;  // hbk_run refuses until they are set again
     freeDev(e->dGradT);
     freeDev(e->dGradP);
     freeDev(e->dCorrP);
@@ -1192,7 +1227,7 @@ int hbk_engine_create(const hbk_structure* st, int32_t n_units, int32_t n_steps,
     cudaEventCreate(&e->ev0);
     cudaEventCreate(&e->ev1);
     e->ldu = (n_units + 31) / 32 * 32;
-    e->tld = (n_steps + 15) / 16 * 16 + 32;
+    e->tld = (n_steps + 15) / 16 * 16 + 96;  // >= last chunk start + 64 + 2 (HBK_CHUNK_STEPS <= 64)
     bool ok = cudaMalloc(&e->dHru, sizeof(double) * kNH * e->ldu) == cudaSuccess &&
               cudaMalloc(&e->dHruFlags, sizeof(int) * e->ldu) == cudaSuccess &&
               cudaMalloc(&e->dFrac, sizeof(double) * 2 * n_units) == cudaSuccess &&
@@ -1201,7 +1236,9 @@ int hbk_engine_create(const hbk_structure* st, int32_t n_units, int32_t n_steps,
               cudaMalloc(&e->dErr, sizeof(int)) == cudaSuccess &&
               cudaMalloc(&e->dUnconv, sizeof(unsigned long long)) == cudaSuccess;
     if (!ok) return bail(HBK_E_CUDA, "device allocation failed");
-    cudaMemset(e->dInitUnit, 0, sizeof(double) * HBK_N_STATES * n_units);
+    if (cudaMemsetAsync(e->dInitUnit, 0, sizeof(double) * HBK_N_STATES * n_units, e->stream) != cudaSuccess ||
+        cudaStreamSynchronize(e->stream) != cudaSuccess)
+        return bail(HBK_E_CUDA, "device memset failed");
     if (st->snow_ice_kind < HBK_SNOW_ICE_NONE || st->snow_ice_kind > HBK_SNOW_ICE_SWAT)
         return bail(HBK_E_ARG, "unknown snow_ice_kind");
     if (st->sublimation_kind < HBK_SUBLIMATION_NONE || st->sublimation_kind > HBK_SUBLIMATION_PET)
@@ -1299,6 +1336,10 @@ int hbk_set_units(hbk_engine* e, const double* area, const double* elevation, co
         e->hGlacierVariant[u] = flags[u];
         if (frac_ground) e->hFracG[u] = frac_ground[u];
         if (frac_glacier) e->hFracGl[u] = frac_glacier[u];
+        // a structure without a glacier cover has the ground as its only land cover: the kernels fold its fraction (= 1)
+        if (!e->st.has_glacier && e->hFracG[u] != 1.0)
+            return fail(e, HBK_E_MODEL, "the ground is the only land cover of this structure: its area fraction must be 1 "
+                                        "(the land-cover fractions of a hydro unit sum to 1)");
     }
     std::vector<double> frac(2 * (size_t)U);
     for (int u = 0; u < U; ++u) {
@@ -1410,6 +1451,12 @@ int hbk_set_station_forcing(hbk_engine* e, int32_t var, const double* series, do
     }
     if (rc) return rc;
     HBK_CUDA(cudaStreamSynchronize(e->stream));
+    if (var != HBK_VAR_PET) {
+        // the station call of a variable replaces its per-set arrays: once both spatialised variables have been set
+        // again after a change of n_sets nothing stale or missing is left
+        e->perSetDroppedVars &= ~(1 << var);
+        if (e->perSetDroppedVars == 0) e->perSetDropped = false;
+    }
     e->haveStation[var] = true;
     e->haveRaw[var] = false;
     return HBK_OK;
@@ -1419,10 +1466,17 @@ int hbk_set_initial_state(hbk_engine* e, int32_t slot, const double* values) {
     if (!e || slot < 0 || slot >= HBK_N_STATES) return HBK_E_ARG;
     HBK_CUDA(cudaSetDevice(e->device));
     if (values) {
-        HBK_CUDA(cudaMemcpy(e->dInitUnit + (size_t)slot * e->U, values, sizeof(double) * e->U, cudaMemcpyHostToDevice));
+        HBK_CUDA(cudaMemcpyAsync(e->dInitUnit + (size_t)slot * e->U, values, sizeof(double) * e->U, cudaMemcpyHostToDevice,
+                                 e->stream));
     } else {
-        HBK_CUDA(cudaMemset(e->dInitUnit + (size_t)slot * e->U, 0, sizeof(double) * e->U));
+        HBK_CUDA(cudaMemsetAsync(e->dInitUnit + (size_t)slot * e->U, 0, sizeof(double) * e->U, e->stream));
     }
+    if (e->initPerSet && e->dBasinInit) {
+        // leaving the per-set initial state of hbk_save_as_initial_state: the sub-basin stores start empty again
+        // (their saved contents belong to the saved unit states, not to the per-unit initial contents used from now on)
+        HBK_CUDA(cudaMemsetAsync(e->dBasinInit, 0, sizeof(double) * 2 * e->P, e->stream));
+    }
+    HBK_CUDA(cudaStreamSynchronize(e->stream));
     e->initPerSet = false;
     return HBK_OK;
 }
@@ -1432,8 +1486,11 @@ int hbk_save_as_initial_state(hbk_engine* e) {
     HBK_CUDA(cudaSetDevice(e->device));
     const size_t n = sizeof(double) * HBK_N_STATES * (size_t)e->P * e->U;
     if (!e->dInitFull) HBK_CUDA(cudaMalloc(&e->dInitFull, n));
-    HBK_CUDA(cudaMemcpy(e->dInitFull, e->dState, n, cudaMemcpyDeviceToDevice));
-    HBK_CUDA(cudaMemcpy(e->dBasinInit, e->dBasinState, sizeof(double) * 2 * e->P, cudaMemcpyDeviceToDevice));
+    // on the engine's stream (created non-blocking: the legacy default stream is NOT ordered against it), then drained,
+    // so that the next hbk_run's restore copy can never overlap this save
+    HBK_CUDA(cudaMemcpyAsync(e->dInitFull, e->dState, n, cudaMemcpyDeviceToDevice, e->stream));
+    HBK_CUDA(cudaMemcpyAsync(e->dBasinInit, e->dBasinState, sizeof(double) * 2 * e->P, cudaMemcpyDeviceToDevice, e->stream));
+    HBK_CUDA(cudaStreamSynchronize(e->stream));
     e->initPerSet = true;
     return HBK_OK;
 }
@@ -1655,7 +1712,8 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
     a.perm = e->dPerm;
     a.outQFinal = multi ? 0 : 1;
 
-    KernelFn fn = pickKernel(e->st);
+    const bool ens = e->PB == 32 && e->UB == 4 && e->TC == 16 && !tiled && !e->clusterMode && !std::getenv("HBK_NO_ENS_SHAPE");
+    KernelFn fn = pickKernel(e->st, ens);
     const size_t smem = smemBytes(e, tiled);
     HBK_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int nPGroups = (e->P + e->PB - 1) / e->PB;
@@ -1734,6 +1792,9 @@ int hbk_run(hbk_engine* e) {
     if (!tiled && !station)
         return fail(e, HBK_E_STATE, "forcing incomplete: precipitation, temperature and pet are all required, "
                                     "either all per unit or all as station series");
+    if (station && e->perSetDropped)
+        return fail(e, HBK_E_STATE, "per-set gradients / correction factors must be set again (hbk_set_station_forcing) "
+                                    "after the number of parameter sets changed");
     if (e->shard && (e->spinupSteps > 0 || !e->events.empty()))
         return fail(e, HBK_E_UNSUPPORTED, "a unit shard runs neither spin-up nor dated actions (the sub-basin stores "
                                           "and the delta-h reduction span all shards)");

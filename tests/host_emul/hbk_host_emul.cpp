@@ -63,6 +63,7 @@ int runSet(const hbk_structure& st, int U, int T, const double* area, const floa
     for (int u = 0; u < U; ++u) {
         Hru& h = state[u];
         const double fa = area[u] / basinArea;
+        const double faW = (fa < 1.0) ? fa : 1.0;  // weight of the outlet fluxes (Flux.cpp:20-26)
         const double slopeTerm = slope ? std::pow((double)slope[u], 0.5) : 0.0;
         const double socontUnit = 3.174802103936398e-05 * 86400.0 * 1000.0;
         par.quickV = (f.quickKind == 0) ? quickBase * slopeTerm / area[u] * socontUnit : quickBase;
@@ -99,9 +100,9 @@ int runSet(const hbk_structure& st, int U, int T, const double* area, const floa
             directPhase<GLACIER>(h, par, p, tt, dt, invDt, fa, fG, fGl, gv, f, o, err, (GLACIER && swat) ? swat[t] : 0.0,
                                  sublimG, sublimGl);
             if (SOLVER == 3) {
-                solveUnitSequential<NSOIL>(h, par, e, fa, dt, invDt, f, o, err);
+                solveUnitSequential<NSOIL>(h, par, e, faW, dt, invDt, f, o, err);
             } else {
-                solveUnit<(SOLVER == 3 ? 0 : SOLVER), NSOIL>(h, par, e, fa, dt, invDt, f, o, err, unconverged);
+                solveUnit<(SOLVER == 3 ? 0 : SOLVER), NSOIL>(h, par, e, faW, dt, invDt, f, o, err, unconverged);
             }
             outlet[t] += o.q;  // units in unit order (the kernel sums per tile, then the tiles in order)
             d1[t] += o.dep1;

@@ -20,7 +20,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT / "tools"))
 
 import fuzz_cases  # noqa: E402
-from test_device_math_on_host import emul, emul_faithful, run_emul  # noqa: E402,F401
+from test_device_math_on_host import emul, emul_faithful, emul_fast, run_emul  # noqa: E402,F401
 
 RTOL, ATOL = 1e-10, 1e-12
 N = 48
@@ -30,14 +30,23 @@ def _excess(a, b):
     return float(np.max(np.abs(a - b) / (RTOL * np.abs(b) + ATOL)))
 
 
-@pytest.mark.parametrize("solver", ["rk4", "heun_explicit", "euler_explicit", "crank_nicolson", "implicit_euler",
-                                    "exponential_euler", "analytic_linear"])
+SOLVERS = ["rk4", "heun_explicit", "euler_explicit", "crank_nicolson", "implicit_euler", "exponential_euler",
+           "analytic_linear"]
+
+
+def _worst(L, seed, solver):
+    meta, forcing, om, vals = fuzz_cases.run_oracle(seed, solver)
+    _, q, rec, unc = run_emul(L, meta, forcing)
+    return max(_excess(q, om.outlet), _excess(rec["slow"], om.records["slow_reservoir:water_content"])), om, vals, q, rec, unc
+
+
+@pytest.mark.parametrize("solver", SOLVERS)
 def test_device_arithmetic_fuzz(solver, emul):  # noqa: F811
+    """The shipped arithmetic: inside the bar on every case whose reference sweep converges; where it does not, RK4 still
+    holds it on every case of this sample (the quotients round like the reference's divisions), Heun / Euler on most."""
     converged = beyond = 0
     for seed in range(N):
-        meta, forcing, om, vals = fuzz_cases.run_oracle(seed, solver)
-        _, q, rec, _ = run_emul(emul, meta, forcing)
-        worst = max(_excess(q, om.outlet), _excess(rec["slow"], om.records["slow_reservoir:water_content"]))
+        worst, om, vals, _, _, _ = _worst(emul, seed, solver)
         if om.unconverged == 0:
             converged += 1
             assert worst <= 1.0, f"seed {seed} ({vals}): {worst:.3g} x the tolerance with a converged sweep"
@@ -45,21 +54,36 @@ def test_device_arithmetic_fuzz(solver, emul):  # noqa: F811
             beyond += 1
             assert float(vals["A"]) < 50.0, f"seed {seed}: non-converged sweep at A = {vals['A']}"
     assert converged >= N * 0.6
-    if solver in ("rk4", "heun_explicit", "euler_explicit"):
-        assert beyond > 0  # the sample does contain the ill-conditioned regime
+    if solver == "rk4":
+        assert beyond == 0
+    elif solver in ("heun_explicit", "euler_explicit"):
+        assert beyond <= 3  # the reference's own -ffp-contract=fast build differs on 5 of 120 such cases
     else:
         assert converged == N  # the sequential solvers apply the constraint once: nothing to converge
 
 
-def test_faithful_build_holds_the_bar_in_the_non_converging_regime(emul_faithful):  # noqa: F811
-    """-DHBK_FAITHFUL=1 (divisions as the reference writes them, verification sweep kept): RK4 stays within 1e-10 of
-    the reference on every case, converged or not — the shipped reciprocal forms lose about half of the non-converged
-    ones (test above). Evidence for the option documented in hbk_device.cuh / DESIGN.md §4."""
+@pytest.mark.parametrize("solver", ["rk4", "heun_explicit", "euler_explicit"])
+def test_default_build_is_bit_identical_to_the_faithful_build_on_the_fuzz_cases(solver, emul, emul_faithful):  # noqa: F811
+    """divExact (reciprocal + two fused multiply-adds) against the divisions written as divisions, over the randomised
+    parameter space incl. the non-converging small-capacity regime, where one different bit in a quotient would show."""
     non_converged = 0
     for seed in range(N):
-        meta, forcing, om, vals = fuzz_cases.run_oracle(seed, "rk4")
-        _, q, rec, _ = run_emul(emul_faithful, meta, forcing)
-        worst = max(_excess(q, om.outlet), _excess(rec["slow"], om.records["slow_reservoir:water_content"]))
+        _, om, vals, qa, ra, ua = _worst(emul, seed, solver)
+        meta, forcing, _, _ = fuzz_cases.run_oracle(seed, solver)
+        _, qb, rb, ub = run_emul(emul_faithful, meta, forcing)
         non_converged += om.unconverged > 0
-        assert worst <= 1.0, f"seed {seed} ({vals}): {worst:.3g} x the tolerance (unconverged sweeps: {om.unconverged})"
+        assert np.array_equal(qa, qb) and np.array_equal(ra["slow"], rb["slow"]) and ua == ub, f"seed {seed} ({vals})"
     assert non_converged > 0
+
+
+def test_fast_arithmetic_variant_loses_the_non_converging_regime(emul_fast):  # noqa: F811
+    """-DHBK_FAST_ARITH=1 (round-1 kernels: bare reciprocals, verification sweep skipped) is fine wherever the
+    reference's sweep converges and NOT where it does not — the reason it is no longer the default."""
+    beyond = 0
+    for seed in range(N):
+        worst, om, vals, _, _, _ = _worst(emul_fast, seed, "rk4")
+        if om.unconverged == 0:
+            assert worst <= 1.0, f"seed {seed} ({vals})"
+        else:
+            beyond += worst > 1.0
+    assert beyond > 0

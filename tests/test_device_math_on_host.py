@@ -45,8 +45,16 @@ def emul():
 
 @pytest.fixture(scope="module")
 def emul_faithful():
-    """The same arithmetic built with -DHBK_FAITHFUL=1 (divisions as the reference writes them, verification sweep kept)."""
+    """The same arithmetic built with -DHBK_FAITHFUL=1: every division of the reference written as a division (the
+    shipped default computes the same correctly rounded quotients from reciprocals, hbk_device.cuh divExact)."""
     return build_emul("libhbkemul_faithful.so", ("-DHBK_FAITHFUL=1",))
+
+
+@pytest.fixture(scope="module")
+def emul_fast():
+    """-DHBK_FAST_ARITH=1: the round-1 kernels' arithmetic (bare reciprocal multiplications, verification sweep skipped),
+    kept as a measurement variant only."""
+    return build_emul("libhbkemul_fast.so", ("-DHBK_FAST_ARITH=1",))
 
 
 def _day_of_year(mjd):
@@ -197,15 +205,29 @@ def test_melt_variants_need_only_glue_around_the_step_functions(name, emul):
         _close(rec["ice"], records[f"{cs.glacier_name}:ice_content"])
 
 
-def test_staged_instruction_diet_options_are_bit_identical(emul):
-    """-DHBK_OPT=7 (the three staged, unmeasured instruction-diet options of hbk_device.cuh) must not change a single bit
-    of any result: same outlet and storages as the default build on every golden."""
-    opt = build_emul("libhbkemul_opt.so", ("-DHBK_OPT=7",))
+def test_instruction_diet_options_are_bit_identical(emul):
+    """-DHBK_OPT (the instruction-diet options of hbk_device.cuh, default 7 = all on) must not change a single bit of
+    any result: the build with all of them off gives the same outlet and storages on every golden."""
+    plain = build_emul("libhbkemul_opt0.so", ("-DHBK_OPT=0",))
     for name in CASES:
         meta, forcing, _, _, _ = gu.load(name)
         _, qa, ra, _ = run_emul(emul, meta, forcing)
-        _, qb, rb, _ = run_emul(opt, meta, forcing)
+        _, qb, rb, _ = run_emul(plain, meta, forcing)
         assert np.array_equal(qa, qb), name
+        for k in ra:
+            assert np.array_equal(ra[k], rb[k], equal_nan=True), (name, k)
+
+
+def test_default_arithmetic_is_bit_identical_to_the_faithful_build(emul, emul_faithful):
+    """The shipped arithmetic rounds every quotient like the reference's division (reciprocal + two fused multiply-adds,
+    divExact) and keeps the verification sweep: not one bit may differ from the build that writes the divisions as
+    divisions, on any golden."""
+    for name in CASES:
+        meta, forcing, _, _, _ = gu.load(name)
+        _, qa, ra, ua = run_emul(emul, meta, forcing)
+        _, qb, rb, ub = run_emul(emul_faithful, meta, forcing)
+        assert np.array_equal(qa, qb), name
+        assert ua == ub
         for k in ra:
             assert np.array_equal(ra[k], rb[k], equal_nan=True), (name, k)
 
