@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
             pv[10 * ps] = pp[HBK_P_ICE_TMELT * a.ldp];
             const double capacity = pp[HBK_P_CAPACITY * a.ldp];
             pv[11 * ps] = capacity;
-            pv[12 * ps] = 1.0 / capacity;
+            pv[12 * ps] = (capacity == 0.0) ? kInvZeroCapacity : 1.0 / capacity;
             pv[13 * ps] = pp[HBK_P_K_SLOW_1 * a.ldp];
             pv[14 * ps] = pp[HBK_P_PERCOLATION * a.ldp];
             pv[15 * ps] = pp[HBK_P_K_SLOW_2 * a.ldp];
@@ -915,6 +915,23 @@ __global__ void hbkFp64Peak(double* out, int iters, double seed) {
     if (s == 123.456) out[0] = s;  // keep the chains alive
 }
 
+// sqrtUnit against sqrt() on n values spread over (2^-40, 1] (and 1 itself): counts the values whose bits differ.
+__global__ void hbkSqrtCheck(long long n, unsigned long long* mismatches) {
+    unsigned long long bad = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        unsigned long long z = (unsigned long long)i * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;  // splitmix64
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        const double m = 1.0 + (double)(z >> 12) * (1.0 / 4503599627370496.0);  // [1, 2)
+        const int ex = (int)(z & 0xfff) % 41;                                       // 2^-1 .. 2^-41
+        double x = ldexp(m, -1 - ex);
+        if (i == 0) x = 1.0;
+        if (__double_as_longlong(sqrtUnit(x)) != __double_as_longlong(sqrt(x))) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 }  // namespace hbk
 
 // =====================================================================================================
@@ -1357,6 +1374,8 @@ int hbk_set_units(hbk_engine* e, const double* area, const double* elevation, co
 int hbk_set_parameters(hbk_engine* e, int32_t n_sets, const float* values) {
     if (!e || n_sets <= 0 || !values) return HBK_E_ARG;
     HBK_CUDA(cudaSetDevice(e->device));
+    for (size_t i = 0; i < (size_t)n_sets * HBK_N_PARAMS; ++i)
+        if (!std::isfinite(values[i])) return fail(e, HBK_E_ARG, "parameter values must be finite");
     int rc = ensureSetBuffers(e, n_sets);
     if (rc) return rc;
     // Internal order of the parameter sets. Lanes of a warp are parameter sets; sets whose constraints bind at
@@ -2062,6 +2081,20 @@ int hbk_compute_scores(hbk_engine* e, int32_t metric, const double* observed, in
 int hbk_scores_dev(hbk_engine* e, const double** ptr) {
     if (!e || !ptr) return HBK_E_ARG;
     *ptr = e->dScores;
+    return HBK_OK;
+}
+
+int hbk_selftest_sqrt(int32_t device, int64_t n, int64_t* mismatches) {
+    if (!mismatches || n <= 0) return HBK_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return HBK_E_CUDA;
+    unsigned long long* d = nullptr;
+    if (cudaMalloc(&d, sizeof(*d)) != cudaSuccess || cudaMemset(d, 0, sizeof(*d)) != cudaSuccess) return HBK_E_CUDA;
+    hbkSqrtCheck<<<148 * 8, 256>>>((long long)n, d);
+    unsigned long long h = 0;
+    const bool ok = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess;
+    cudaFree(d);
+    if (!ok) return HBK_E_CUDA;
+    *mismatches = (int64_t)h;
     return HBK_OK;
 }
 

@@ -115,6 +115,7 @@ def load_library():
     L.hbk_stream.argtypes = [vp]
     L.hbk_stream.restype = ctypes.c_void_p
     L.hbk_measure_fp64_peak.argtypes = [i32, dp]
+    L.hbk_selftest_sqrt.argtypes = [i32, i64, ctypes.POINTER(i64)]
     L.hbk_compute_scores.argtypes = [vp, i32, dp, i32, dp]
     L.hbk_scores_dev.argtypes = [vp, ctypes.POINTER(ctypes.c_void_p)]
     L.hbk_set_unit_shard.argtypes = [vp, dbl]
@@ -123,6 +124,15 @@ def load_library():
     L.hbk_finish_sharded_run.argtypes = [vp]
     _lib = L
     return L
+
+
+def selftest_sqrt(n=1 << 26, device=0):
+    """Number of values on which the kernels' square root of a filling ratio differs from sqrt() (must be 0)."""
+    out = ctypes.c_int64()
+    rc = load_library().hbk_selftest_sqrt(int(device), int(n), ctypes.byref(out))
+    if rc != 0:
+        raise HbkError(rc, "hbk_selftest_sqrt failed")
+    return out.value
 
 
 def measure_fp64_peak(device=0):

@@ -229,6 +229,11 @@ int hbk_scores_dev(hbk_engine* e, const double** ptr);
  * compute-bound ensemble configurations (MEASURED_PEAKS.json has no FP64 figure). */
 int hbk_measure_fp64_peak(int32_t device, double* tflops);
 
+/* Device self-test of the kernels' square root of a filling ratio (csrc/hbk_device.cuh sqrtUnit: CUDA's sqrt sequence
+ * without its special-case path) against sqrt() on n pseudo-random values of (2^-41, 1]: number of values whose bits
+ * differ (must be 0). Diagnostic entry point, not part of the ModelHydro surface. */
+int hbk_selftest_sqrt(int32_t device, int64_t n, int64_t* mismatches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,7 +46,7 @@ int runSet(const hbk_structure& st, int U, int T, const double* area, const floa
     par.v[10] = pp[HBK_P_ICE_TMELT];
     const double capacity = pp[HBK_P_CAPACITY];
     par.v[11] = capacity;
-    par.v[12] = 1.0 / capacity;
+    par.v[12] = (capacity == 0.0) ? kInvZeroCapacity : 1.0 / capacity;
     par.v[13] = pp[HBK_P_K_SLOW_1];
     par.v[14] = pp[HBK_P_PERCOLATION];
     par.v[15] = pp[HBK_P_K_SLOW_2];
