@@ -30,15 +30,30 @@ sys.path.insert(0, str(ROOT))
 
 U_DEFAULT, T_DEFAULT, P_DEFAULT = 50, 10957, 100000
 START, END = "1981-01-01", "2010-12-31"
-# ALGORITHMIC FP64 work per HRU*timestep: DADD + DMUL + 2*DFMA thread instructions / (P*U*T) executed by the
-# faithful first formulation (r01a, Socont RK4, 1 soil store: the C2 structure), kept fixed while later kernels spend
-# fewer instructions on the same result (r01k executes 267). Heun / Euler were not captured at r01a: scaled by their
-# stage count with the direct phase (17 % of the RK4 step in the per-function profile) held constant.
-FP64_FLOPS_PER_HRU_STEP = {"rk4": 535.8, "heun_explicit": 91.0 + 2 * 111.2, "euler_explicit": 91.0 + 111.2}
-FP64_FLOPS_SOURCE = ("profiles/r01a_instmix.csv: (DADD + DMUL + 2*DFMA) thread instructions / HRU*timesteps of the "
-                     "faithful r01a kernel (Socont RK4, 1 soil store); heun/euler: direct phase 91 + 111.2 per stage "
-                     "(estimate); glacier / 2-store structures use the same figure (under-estimate)")
+# ALGORITHMIC FP64 work per HRU*timestep: counted in an instrumented build of the CPU restatement (tools/count_flops.py,
+# oracle/flop_count.h) — additions + multiplications + divisions + pow/sqrt calls (one operation each, as
+# the reference's source writes them) per solver and structure; comparisons are listed in the file, not counted.
+def algorithmic_flops(solver, glacier, soil):
+    try:
+        table = json.load(open(ROOT / "profiles" / "flops_per_hru_step.json"))["per_hru_step"]
+        name = "gsm_socont_2store_glacier" if (glacier or soil == 2) else "socont_1store"
+        return table[solver][name]["flops"], table[solver][name]
+    except Exception:
+        return None, None
 
+
+FP64_FLOPS_SOURCE = ("profiles/flops_per_hru_step.json: FP64 add + mul + div + pow/sqrt operations per HRU*timestep of "
+                     "the reference's algorithm, counted in the instrumented CPU restatement (tools/count_flops.py); the "
+                     "reference forbids FMA contraction, so its adds and multiplies cannot pair into the DFMAs the peak "
+                     "is measured with")
+
+
+def kernel_profile():
+    """Counters of the current hot kernel from its committed ncu capture (tools/ncu_profile_json.py)."""
+    try:
+        return json.load(open(ROOT / "profiles" / "kernel_profile.json"))
+    except Exception:
+        return None
 
 # ---------------------------------------------------------------------------------------------------------
 # synthetic workload (SURVEY.md §8d)
@@ -172,6 +187,10 @@ def spatialise(units, precip, temp, pet):
 # reference arm: the reference's CPU implementation on all host cores
 # ---------------------------------------------------------------------------------------------------------
 _W = {}
+# parameter sets per host core for the cpu_baseline sample (>= 64 per core for the ensembles; C5 has 20 x
+# the units per set, C3 is one parameter set per core on a 1 000-unit basin)
+REF_SETS_PER_CORE = {"c2": 64, "c4": 32, "c5": 4, "c3": 1}
+REF_UNITS = {"c3": 1000}  # the reference is timed on U = 1 000 (and once on 10 000) for the basin config
 
 
 def _load_ref_backend():
@@ -186,34 +205,49 @@ def _load_ref_backend():
     return mod
 
 
-def _ref_worker_init(U, T):
+def workload_parameter_sets(wl, P, seed=44, extra_seed=0):
+    ps = parameter_sets(P, seed=seed)
+    if wl["glacier"]:
+        rng = np.random.Generator(np.random.MT19937(91 + extra_seed))
+        ps.update({"a_ice": ps["a_snow"] + rng.uniform(0.5, 6, P), "k_snow": rng.uniform(0.05, 0.6, P),
+                   "k_ice": rng.uniform(0.05, 0.6, P)})
+    if wl["soil"] == 2:
+        rng = np.random.Generator(np.random.MT19937(92 + extra_seed))
+        ps.update({"percol": rng.uniform(0, 10, P), "k_slow_2": ps["k_slow_1"] * rng.uniform(0.05, 0.9, P)})
+    return ps
+
+
+def _ref_worker_init(workload, solver, U, T, log_path):
     from hydrobricks_b200 import models
 
+    # the reference logs "did not stabilize after 10 sweeps" on stderr: keep it in a file per worker and count it
+    fd = os.open(f"{log_path}.{os.getpid()}", os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o600)
+    os.dup2(fd, 2)
+    wl = WORKLOADS[workload]
     ref = _load_ref_backend()
-    units = hydro_units(U)
+    units = hydro_units(U, area=wl["area"], glacier=wl["glacier"])
     precip, temp, pet = station_series(T)
+    covers = ["ground", "glacier"] if wl["glacier"] else ["ground"]
+    kw = dict(solver=solver, soil_storage_nb=wl["soil"], surface_runoff="socont_runoff", land_cover_names=covers,
+              land_cover_types=covers, glacier_infinite_storage=not wl.get("finite_ice", False))
+    end = END if T == T_DEFAULT else str(np.datetime64(START) + np.timedelta64(T - 1, "D"))
     if ref is not None:
         ref.init()
-        try:
-            ref.set_message_log_level()
-        except Exception:
-            pass
-        m = models.Socont(solver="rk4", soil_storage_nb=1, surface_runoff="socont_runoff",
-                          land_cover_names=["ground"], land_cover_types=["ground"], backend=ref)
-        m.setup(units, START, "2010-12-31" if T == T_DEFAULT else str(np.datetime64(START) + np.timedelta64(T - 1, "D")))
+        m = models.Socont(backend=ref, **kw)
+        m.setup(units, START, end)
         p2, t2, e2 = spatialise(m.units, precip, temp, pet)
         m.set_forcing(mjd_axis(T), p2, t2, e2)
+        _W["actions"] = add_c4_actions(m, T) if wl.get("actions") else []
         _W["kind"], _W["model"] = "reference", m
     else:  # oracle port (the restatement) when the compiled reference did not travel
         from hydrobricks_b200 import _hydrobricks as mirror
         from oracle import hb_oracle
 
-        m = models.Socont(solver="rk4", soil_storage_nb=1, surface_runoff="socont_runoff",
-                          land_cover_names=["ground"], land_cover_types=["ground"], backend=mirror)
+        m = models.Socont(backend=mirror, **kw)
         m.units = sorted(units, key=lambda u: -u["elevation"])
         _W["kind"], _W["model"], _W["oracle"] = "port", m, hb_oracle
         _W["forcing"] = spatialise(m.units, precip, temp, pet)
-    _W["T"], _W["U"] = T, U
+    _W["T"], _W["U"], _W["solver"] = T, U, solver
 
 
 def _ref_worker_run(sets):
@@ -232,7 +266,7 @@ def _ref_worker_run(sets):
             for alias, v in values.items():
                 comp, name = m.aliases[alias]
                 m.settings.set_parameter_value(comp, name, v)
-            om = _W["oracle"].OracleModel(m.settings.get_structure(), m.units, "rk4", T)
+            om = _W["oracle"].OracleModel(m.settings.get_structure(), m.units, _W["solver"], T)
             for k, v in zip(("precipitation", "temperature", "pet"), _W["forcing"]):
                 om.set_forcing(k, v)
             t0 = time.perf_counter()
@@ -241,23 +275,33 @@ def _ref_worker_run(sets):
     return t_run, float(np.sum(q))
 
 
-def run_reference_arm(args, sets_per_core=None, quiet=False):
+def run_reference_arm(args, quiet=False):
+    import glob
+    import math
     import multiprocessing as mp
+    import tempfile
 
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
-    U, T = args.units, args.timesteps
-    n_per_core = sets_per_core or args.ref_sets_per_core
-    ps = parameter_sets(cores * n_per_core * (args.steps + args.warmup) + 1)
+    wl = WORKLOADS[args.workload]
+    T = args.timesteps
+    U = REF_UNITS.get(args.workload, args.units)
+    # >= the workload's sets per core over the timed steps (64 for C2), spread over the steps so that the arm ends
+    # within minutes whatever --steps the driver asks for
+    target = REF_SETS_PER_CORE.get(args.workload, 64)
+    n_per_core = args.ref_sets_per_core or max(1, math.ceil(target / max(args.steps, 1)))
+    n_steps = args.steps + args.warmup
+    ps = workload_parameter_sets(wl, cores * n_per_core * n_steps + 1)
     chunks = []
     k = 0
-    for _ in range(args.steps + args.warmup):
+    for _ in range(n_steps):
         step = []
         for _c in range(cores):
             step.append([{a: float(ps[a][k + j]) for a in ps} for j in range(n_per_core)])
             k += n_per_core
         chunks.append(step)
+    log_path = os.path.join(tempfile.mkdtemp(prefix="hbref_"), "stderr")
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_ref_worker_init, initargs=(U, T)) as pool:
+    with ctx.Pool(cores, initializer=_ref_worker_init, initargs=(args.workload, args.solver, U, T, log_path)) as pool:
         pool.map(_ref_worker_run, [[] for _ in range(cores)])  # make sure every worker is initialised
         times = []
         kind = "reference" if _load_ref_backend() is not None else "port"
@@ -267,6 +311,12 @@ def run_reference_arm(args, sets_per_core=None, quiet=False):
             dt = time.perf_counter() - t0
             if i >= args.warmup:
                 times.append((dt, max(r[0] for r in res)))
+    warnings = 0
+    for f in glob.glob(log_path + ".*"):
+        try:
+            warnings += open(f, errors="replace").read().count("did not stabilize")
+        except OSError:
+            pass
     wall = sum(t[0] for t in times)
     n_sets = cores * n_per_core * len(times)
     value = n_sets * U * T / wall
@@ -275,12 +325,17 @@ def run_reference_arm(args, sets_per_core=None, quiet=False):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "evals_per_s": n_sets / wall,
-        "config": {"workload": "C2 Socont-RK4 calibration ensemble (bounded CPU sample)", "sets_per_step": cores * n_per_core,
-                   "hydro_units": U, "timesteps": T, "solver": "rk4", "structure": "socont 1 soil store, runoff:socont",
+        "config": {"workload": wl["name"] + " (bounded CPU sample)", "sets_per_step": cores * n_per_core,
+                   "hydro_units": U, "timesteps": T, "solver": args.solver,
+                   "structure": f"socont {wl['soil']} soil store(s), runoff:socont" + (", glacier (GSM)" if wl["glacier"] else ""),
                    "forcing": "pre-spatialised per-unit series (station + elevation gradients)"},
         "cpu_baseline": {"value": value, "unit": "HRU*timesteps/s", "cores": cores, "kind": kind,
-                         "sample": f"{cores * n_per_core} parameter sets per step ({n_per_core} per core) x {U} units x "
-                                   f"{T} steps, one model instance per core, wall time incl. parameter update"},
+                         "sample": f"{n_sets} parameter sets over {len(times)} timed step(s) ({n_per_core} per core and "
+                                   f"step, {n_per_core * len(times)} per core in total) x {U} units x {T} steps, one model "
+                                   f"instance per core, wall time incl. parameter update",
+                         "did_not_stabilize_warnings": warnings,
+                         "note": "the reference's own 'did not stabilize after 10 sweeps' log lines over the whole sample "
+                                 "(incl. warm-up steps)"},
         "e2e": {"value": value, "unit": "HRU*timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -356,12 +411,16 @@ def run_engine_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (engine arm) needs a CUDA device; there is no CPU fallback")
 
-    # cpu_baseline: rank 0, N=1 only, in a child process BEFORE this process touches CUDA
+    # cpu_baseline: rank 0, N=1 only, in a child process BEFORE this process touches CUDA: the reference's own CPU
+    # implementation on all host cores, 64 parameter sets per core of the same workload
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline and args.workload == "c2":
-        out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                              "--units", str(args.units), "--timesteps", str(args.timesteps),
-                              "--ref-sets-per-core", str(args.ref_sets_per_core)], capture_output=True, text=True)
+    if world == 1 and not args.no_cpu_baseline:
+        cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+               "--workload", args.workload, "--solver", args.solver, "--timesteps", str(args.timesteps),
+               "--ref-sets-per-core", str(args.ref_sets_per_core or REF_SETS_PER_CORE.get(args.workload, 64))]
+        if args.workload in ("c2", "c4", "c5"):
+            cmd += ["--units", str(args.units)]
+        out = subprocess.run(cmd, capture_output=True, text=True)
         for ln in out.stdout.splitlines():
             if ln.startswith("{"):
                 cpu_baseline = json.loads(ln)["cpu_baseline"]
@@ -373,22 +432,49 @@ def run_engine_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    P, U, T = args.sets, args.units, args.timesteps
+    U, T = args.units, args.timesteps
     wl = WORKLOADS[args.workload]
-    # C3 on several GPUs: ONE basin of world x U hydro units, every rank holds a block of U units;
-    # per step one all-reduce of the partial outlet and of the two deposit series, then the sub-basin stores
+    # C3 on several GPUs: ONE basin, every rank holds a block of its hydro units; per step one
+    # all-reduce of the partial outlet and of the two deposit series, then the sub-basin stores.
+    #   weak: a basin of world x U units (U per rank)      strong: the basin of U units split over the ranks
     unit_sharded = args.workload == "c3" and world > 1
-    units = hydro_units(U, seed=43 + (rank if unit_sharded else 0), area=wl["area"], glacier=wl["glacier"])
+    strong = args.scaling == "strong"
+    if unit_sharded:
+        P = args.sets
+        U_total = U if strong else world * U
+        u0, u1 = parallel.shard_bounds(U_total, rank, world)
+        units = hydro_units(U_total, area=wl["area"], glacier=wl["glacier"])[u0:u1]
+        U = u1 - u0
+        set_seed = 0  # unit shards integrate the SAME parameter sets
+        ps = parameter_sets(P, seed=44)
+        p0 = 0
+    else:
+        # ensembles: the parameter axis is sharded, no communication on the path.
+        #   weak: every rank integrates args.sets sets of its own     strong: args.sets sets in total, split over the ranks
+        units = hydro_units(U, area=wl["area"], glacier=wl["glacier"])
+        U_total = U
+        if strong:
+            p0, p1 = parallel.shard_bounds(args.sets, rank, world)
+            P = p1 - p0
+            set_seed = 0
+            ps = {k: v[p0:p1] for k, v in parameter_sets(args.sets, seed=44).items()}
+        else:
+            P, p0, set_seed = args.sets, 0, rank
+            ps = parameter_sets(P, seed=44 + set_seed)
+    P_total = args.sets if (strong or unit_sharded) else world * args.sets
     precip, temp, pet = station_series(T)
-    set_seed = 0 if unit_sharded else rank  # unit shards integrate the SAME parameter sets
-    ps = parameter_sets(P, seed=44 + set_seed)  # every rank its own shard of the ensemble (weak scaling)
+    n_draw = args.sets if strong and not unit_sharded else P
     if wl["glacier"]:
         rng = np.random.Generator(np.random.MT19937(91 + set_seed))
-        ps.update({"a_ice": ps["a_snow"] + rng.uniform(0.5, 6, P), "k_snow": rng.uniform(0.05, 0.6, P),
-                   "k_ice": rng.uniform(0.05, 0.6, P)})
+        extra = {"a_ice": rng.uniform(0.5, 6, n_draw), "k_snow": rng.uniform(0.05, 0.6, n_draw),
+                 "k_ice": rng.uniform(0.05, 0.6, n_draw)}
+        sl = slice(p0, p0 + P) if (strong and not unit_sharded) else slice(None)
+        ps.update({"a_ice": ps["a_snow"] + extra["a_ice"][sl], "k_snow": extra["k_snow"][sl], "k_ice": extra["k_ice"][sl]})
     if wl["soil"] == 2:
         rng = np.random.Generator(np.random.MT19937(92 + set_seed))
-        ps.update({"percol": rng.uniform(0, 10, P), "k_slow_2": ps["k_slow_1"] * rng.uniform(0.05, 0.9, P)})
+        percol, ratio = rng.uniform(0, 10, n_draw), rng.uniform(0.05, 0.9, n_draw)
+        sl = slice(p0, p0 + P) if (strong and not unit_sharded) else slice(None)
+        ps.update({"percol": percol[sl], "k_slow_2": ps["k_slow_1"] * ratio[sl]})
 
     covers = ["ground", "glacier"] if wl["glacier"] else ["ground"]
     m = models.Socont(solver=args.solver, soil_storage_nb=wl["soil"], surface_runoff="socont_runoff",
@@ -400,7 +486,7 @@ def run_engine_arm(args):
     actions = add_c4_actions(m, T) if wl.get("actions") else []
     eng = m.engine(P)
     if unit_sharded:
-        eng.set_unit_shard(parallel.basin_area(np.full(world * U, wl["area"])))
+        eng.set_unit_shard(parallel.basin_area(np.full(U_total, wl["area"])))
 
     def run_engine(e):
         e.run()
@@ -437,7 +523,12 @@ def run_engine_arm(args):
         m.model.run()
     stream = torch.cuda.ExternalStream(eng.stream())
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
-    scores_all = torch.empty(world * P, dtype=torch.float64, device="cuda") if world > 1 else None
+    gather_scores = world > 1 and not unit_sharded
+    if gather_scores:  # ranks may hold different numbers of sets (strong scaling): gather padded to the largest share
+        p_max = max(parallel.shard_bounds(args.sets, r, world)[1] - parallel.shard_bounds(args.sets, r, world)[0]
+                    for r in range(world)) if strong else P
+        scores_pad = torch.zeros(p_max, dtype=torch.float64, device="cuda")
+        scores_all = torch.empty(world * p_max, dtype=torch.float64, device="cuda")
 
     # synthetic observed discharge for the objective function (NSE of every parameter set, computed on the device)
     rng = np.random.default_rng(5)
@@ -447,9 +538,10 @@ def run_engine_arm(args):
 
     def scores():
         eng.compute_scores("nse", pin_obs.numpy(), score_warmup, to_host=False)
-        if world > 1 and not unit_sharded:  # the only collective of the job: final gather of the per-set scores
-            s = torch.as_tensor(DeviceArray(eng.scores_device_pointer(), (P,), (8,)), device="cuda")
-            dist.all_gather_into_tensor(scores_all, s)
+        if gather_scores:  # the only collective of the job: final gather of the per-set scores
+            sc = torch.as_tensor(DeviceArray(eng.scores_device_pointer(), (P,), (8,)), device="cuda")
+            scores_pad[:P].copy_(sc)
+            dist.all_gather_into_tensor(scores_all, scores_pad)
 
     def barrier():
         if world > 1:
@@ -459,11 +551,6 @@ def run_engine_arm(args):
     def resident_step():
         run_engine(eng)
         scores()
-
-    def e2e_step():
-        upload()
-        run_engine(eng)
-        eng._check(eng.L.hbk_get_outlet(eng.h, 0, P, out_ptr))
 
     peak_fp64 = hbk_engine.measure_fp64_peak(local)
 
@@ -488,21 +575,34 @@ def run_engine_arm(args):
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
+    unconverged_sweeps = eng.last_run_stats()["unconverged_sweeps"]
+    unconverged_sets = int((eng.unconverged_per_set() > 0).sum())
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([dev_ms, wall * 1e3, sum(kernel_ms)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, wall_ms, kern_ms = t.tolist()
-    units_done = world * P * U * T * args.steps
+    units_done = P_total * U_total * T * args.steps
     value = units_done / (dev_ms * 1e-3)
 
-    # ---- end to end: pinned host inputs -> device -> run -> full outlet back to pinned host ----
+    # ---- end to end: pinned host inputs -> device -> run -> full outlet back to pinned host, through the C-ABI. The
+    # outlet of step i is fetched asynchronously (hbk_get_outlet_async, one strided copy on the engine's copy stream)
+    # while step i+1 uploads its inputs and integrates into the engine's second outlet buffer; every step's outlet has
+    # landed in host memory when the timed region ends (hbk_wait_outlet). ----
+    def e2e_step():
+        upload()
+        run_engine(eng)
+        eng._check(eng.L.hbk_wait_outlet(eng.h))  # the host buffer is free again (copy of the previous step done)
+        eng._check(eng.L.hbk_get_outlet_async(eng.h, 0, P, out_ptr))
+
     for _ in range(min(args.warmup, 1)):
         e2e_step()
+    eng.wait_outlet()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         e2e_step()
+    eng.wait_outlet()
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -511,6 +611,23 @@ def run_engine_arm(args):
     e2e_value = units_done / t.item()
     h2d = pin_params.numel() * 4 + sum(x.numel() * 8 for x in pin_forcing)
     d2h = P * T * 8
+
+    # ---- the same with the blocking fetch (hbk_get_outlet): copy after compute, nothing overlaps ----
+    def e2e_blocking_step():
+        upload()
+        run_engine(eng)
+        eng._check(eng.L.hbk_get_outlet(eng.h, 0, P, out_ptr))
+
+    e2e_blocking_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_blocking_step()
+    barrier()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_blocking_value = units_done / t.item()
 
     # ---- the calibration loop's variant: only the per-set objective scores come back ----
     def e2e_scores_step():
@@ -529,54 +646,9 @@ def run_engine_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_scores_value = units_done / t.item()
 
-    # ---- pipelined variant: the outlet of run i travels to the host while run i+1 computes (two engines taking
-    # turns, one fetch thread per engine; every step still uploads its inputs and fetches its full outlet) ----
-    e2e_pipe_value = None
-    if args.pipeline:
-        m2 = models.Socont(solver=args.solver, soil_storage_nb=wl["soil"], surface_runoff="socont_runoff",
-                           land_cover_names=covers, land_cover_types=covers)
-        m2.setup(units, START, end, device=local)
-        engines = [eng, m2.engine(P)]
-        pending = [None, None]
-
-        def fetch(e):
-            e._check(e.L.hbk_get_outlet(e.h, 0, P, out_ptr))
-
-        def pipe_step(i):
-            k = i % 2
-            if pending[k] is not None:
-                pending[k].join()
-            upload(engines[k])
-            engines[k].run()
-            pending[k] = threading.Thread(target=fetch, args=(engines[k],))
-            pending[k].start()
-
-        def drain():
-            for k in range(2):
-                if pending[k] is not None:
-                    pending[k].join()
-                    pending[k] = None
-
-        pipe_step(0)
-        pipe_step(1)
-        drain()
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            pipe_step(i)
-        drain()
-        barrier()
-        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_pipe_value = units_done / t.item()
-        del engines, m2
-
     if rank == 0:
         main_ms = kern_ms / args.steps  # device time of one hbk_run (state reset + unit kernel), CUDA events
-        # the sequential solvers (bisection / exponential / analytic schemes) have no algorithmic flop figure: their
-        # work depends on the number of halvings; the roofline fraction is reported for the explicit solvers only
-        flops_unit = FP64_FLOPS_PER_HRU_STEP.get(args.solver)
+        flops_unit, flops_detail = algorithmic_flops(args.solver, wl["glacier"], wl["soil"])
         achieved = flops_unit * P * U * T / (main_ms * 1e-3) / 1e12 if flops_unit else None
         hbm_bytes = P * T * 8 + 3 * T * 8 + P * hbk_engine.N_PARAMS * 4
         try:
@@ -584,22 +656,19 @@ def run_engine_arm(args):
             hbm_src = "MEASURED_PEAKS.json"
         except Exception:
             hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
-        traffic = None
-        try:  # measured DRAM traffic of this exact launch (ncu), only meaningful for the default C2 shape
-            tr = json.load(open(ROOT / "profiles" / "r01k_traffic.json"))
-            if args.workload == "c2" and args.solver == "rk4" and (P, U, T) == (P_DEFAULT, U_DEFAULT, T_DEFAULT):
-                traffic = tr["traffic_bytes"]
-        except Exception:
-            pass
+        prof = kernel_profile() or {}
+        default_shape = args.workload == "c2" and args.solver == "rk4" and (args.sets, U, T) == (P_DEFAULT, U_DEFAULT, T_DEFAULT)
+        traffic = prof.get("dram_bytes_full_c2_launch") if (default_shape and not strong) else None
         line = {
             "metric": "hru_timesteps_per_s", "value": value, "unit": "HRU*timesteps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "evals_per_s": world * P * args.steps / (dev_ms * 1e-3),
-            "config": {"workload": wl["name"], "sets_per_gpu": P, "hydro_units": U,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "evals_per_s": P_total * args.steps / (dev_ms * 1e-3),
+            "config": {"workload": wl["name"], "sets_per_gpu": P, "sets_total": P_total, "hydro_units": U_total,
+                       "hydro_units_per_gpu": U,
                        "multi_gpu": ("one basin of %d units, a block of %d per GPU; per step one all-reduce of the "
                                      "partial outlet and the two sub-basin deposit series [T], then the sub-basin "
-                                     "stores" % (world * U, U)) if unit_sharded else
+                                     "stores" % (U_total, U)) if unit_sharded else
                                     "parameter axis sharded, no collective on the path, one all_gather of scores",
                        "timesteps": T, "solver": args.solver,
                        "structure": f"socont {wl['soil']} soil store(s), runoff:socont" + (", glacier (GSM)" if wl["glacier"] else ""),
@@ -607,31 +676,52 @@ def run_engine_arm(args):
                        "l2": "256 MiB flush between timed iterations; per-step output 8.8 GB >> L2",
                        "block_shape": "32 parameter sets (lanes) x 4 units per block, all unit tiles time-multiplexed "
                                       "on the block, 16 steps per chunk; parameter sets ordered inside the engine "
-                                      "so that warps hold similar sets"},
+                                      "so that warps hold similar sets",
+                       "arithmetic": "every quotient of the reference correctly rounded, verification sweep kept "
+                                     "(bit-identical to the division-for-division build, DESIGN.md §4)"},
             "wall_ms_per_step": wall_ms / args.steps,
             "e2e": {"value": e2e_value, "unit": "HRU*timesteps/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "note": "pinned host params+station series -> device, run, full "
-                    "outlet[P x T] -> pinned host, through the C-ABI", "host_outlet_buffer_pinned": host_out_pinned,
-                    "scores_only": {"value": e2e_scores_value, "d2h_bytes_per_step": int(P * 8 ),
+                    "d2h_bytes_per_step": int(d2h),
+                    "note": "per step: pinned host params + station series -> device, run, full outlet[P x T] -> pinned "
+                            "host through the C-ABI; the fetch is hbk_get_outlet_async, so the copy of step i overlaps "
+                            "the run of step i+1; all outlets have landed when the clock stops",
+                    "host_outlet_buffer_pinned": host_out_pinned,
+                    "blocking_fetch": {"value": e2e_blocking_value,
+                                       "note": "same bytes, hbk_get_outlet after every run (copy not overlapped)"},
+                    "scores_only": {"value": e2e_scores_value, "d2h_bytes_per_step": int(P * 8),
                                     "note": "same, but the device computes NSE per set (hbk_compute_scores) and only "
-                                            "the scores come back: the calibration loop's step"},
-                    "pipelined": {"value": e2e_pipe_value,
-                                  "note": "same bytes per step as e2e.value, but two engines take turns so that the "
-                                          "outlet of run i is copied to the host while run i+1 computes"}},
+                                            "the scores come back: the calibration loop's step; NSE follows the published "
+                                            "formula, parity against HydroErr is unpinned (absent from the image)"}},
             "gpu_launches": launches,
             "clocks": clocks,
+            "parity": {"unconverged_sweeps_last_run": int(unconverged_sweeps), "sets_with_unconverged_sweeps": unconverged_sets,
+                       "sets_per_gpu": P,
+                       "note": "constraint passes in which the reference logs 'did not stabilize after 10 sweeps' "
+                               "(Processor.cpp:191-209, soil capacities below ~60 mm): there the reference's own result "
+                               "hangs on the last bit (its -ffp-contract=fast build disagrees with itself on 130 of 207 "
+                               "such sets, tests/golden/ensemble_fuzz_reference_fma.json); everywhere else 1e-10"},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_fp64, "unit": "TFLOP/s",
                          "frac": achieved / peak_fp64 if (peak_fp64 and achieved) else None, "traffic": traffic,
-                         "traffic_note": "DRAM bytes per launch from ncu (profiles/r01k_traffic.json); algorithmic "
-                                         "bytes are in roofline.hbm; the excess is the unit state of the "
-                                         "time-multiplexed tiles passing through L2/HBM (<3 % of HBM bandwidth)",
+                         "traffic_note": "DRAM bytes of the full-size C2 launch from ncu (profiles/kernel_profile.json, "
+                                         "kernel version %s); algorithmic bytes are in roofline.hbm; the excess is the "
+                                         "unit state of the time-multiplexed tiles passing through L2/HBM (<3 %% of HBM "
+                                         "bandwidth)" % prof.get("version"),
                          "kernel": f"hbkRunUnits<{args.solver},{wl['soil']} soil store(s),{'glacier' if wl['glacier'] else 'no glacier'}>",
                          "kernel_ms": main_ms,
-                         "flops_per_hru_step": flops_unit, "flops_source": FP64_FLOPS_SOURCE,
-                         "peak_source": "DFMA micro-benchmark measured in this run (hbk_measure_fp64_peak); "
-                                        "MEASURED_PEAKS.json has no FP64 figure",
-                         "note": "not a dense contraction: neither HBM nor tensor binds, the FP64 pipe does "
-                                 "(SURVEY.md §8d); the HBM fraction is listed for completeness",
+                         "flops_per_hru_step": flops_unit, "flops_detail": flops_detail, "flops_source": FP64_FLOPS_SOURCE,
+                         "frac_of_non_fma_peak": 2 * achieved / peak_fp64 if (peak_fp64 and achieved) else None,
+                         "flops_executed_per_hru_step": prof.get("flops_executed_per_hru_step") if default_shape else None,
+                         "fp64_pipe_pct": prof.get("fp64_pipe_pct") if default_shape else None,
+                         "issue_slots_pct": prof.get("issue_active_pct") if default_shape else None,
+                         "profile_version": prof.get("version"),
+                         "peak_source": "DFMA micro-benchmark measured in this run (hbk_measure_fp64_peak, builder-"
+                                        "measured: MEASURED_PEAKS.json has no FP64 figure); 2 flop per DFMA",
+                         "note": "not a dense contraction: neither HBM nor tensor binds, the FP64 pipe / instruction "
+                                 "issue does (SURVEY.md §8d). frac counts the reference's algorithmic operations (one "
+                                 "per add / mul / div / pow) against the DFMA peak (two per instruction): an algorithm "
+                                 "whose adds and multiplies may not be contracted tops out at 0.5 "
+                                 "(frac_of_non_fma_peak); fp64_pipe_pct / issue_slots_pct are the ncu counters of the "
+                                 "committed profile of this kernel version",
                          "hbm": {"achieved": hbm_bytes / (main_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": hbm_bytes / (main_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
                                  "algorithmic_bytes_per_launch": int(hbm_bytes)}},
@@ -645,7 +735,8 @@ def run_engine_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--pipeline", action="store_true", help="also time the pipelined end-to-end leg (second engine; measured: +0.6 %, so off by default)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --sets parameter sets (c3: --units hydro units) PER GPU; strong: in total, split over the GPUs")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -655,9 +746,9 @@ def main():
     ap.add_argument("--sets", type=int, default=None, help="parameter sets per GPU")
     ap.add_argument("--units", type=int, default=None)
     ap.add_argument("--timesteps", type=int, default=None)
-    ap.add_argument("--ref-sets-per-core", type=int, default=8,
-                    help="reference arm / cpu_baseline: parameter sets per host core and step (8 = ~7 s of wall time per "
-                         "step on a 16-core box, ~100 core-seconds)")
+    ap.add_argument("--ref-sets-per-core", type=int, default=None,
+                    help="reference arm / cpu_baseline: parameter sets per host core and step; default: >= 64 per core "
+                         "over the timed steps (SURVEY.md §8d), i.e. ceil(64 / steps) per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     for key in ("sets", "units", "timesteps"):

@@ -79,6 +79,7 @@ struct KArgs {
     int T;
     int* err;
     unsigned long long* unconverged;
+    int* unconvergedPerSet;  // [P], internal set order: sweeps of that set's units that did not stabilise
     // Parameter sets are stored in an engine-chosen order (similar sets share a warp, hbk_set_parameters);
     // perm[internal index] = caller's index, nullptr = identity. Only what leaves the engine is mapped back:
     // final outlet rows, recorder rows, per-set spatialisation inputs.
@@ -528,7 +529,10 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
         if (u < a.U) storeState(u, true);
     }
     if (err) atomicOr(a.err, err);
-    if (unconverged) atomicAdd(a.unconverged, (unsigned long long)unconverged);
+    if (unconverged) {
+        atomicAdd(a.unconverged, (unsigned long long)unconverged);
+        if (validP) atomicAdd(&a.unconvergedPerSet[p], unconverged);
+    }
 }
 
 // Sum the unit-tile partials in tile order: out[p][t] = sum_tiles part[tile][p][t]  (only when nUTiles > 1).
@@ -975,7 +979,14 @@ struct hbk_engine {
     double* dInitFull = nullptr;   // [HBK_N_STATES][P*U] after save_as_initial_state
     double* dBasinState = nullptr; // [P][2]
     double* dBasinInit = nullptr;
-    double* dOutlet = nullptr;     // [P][ldt]
+    double* dOutlet = nullptr;     // [P][ldt]: the buffer the current / last run writes (one of dOutletBuf)
+    // hbk_get_outlet_async: the outlet of run i travels to the host on its own stream while run i+1 computes into the
+    // other buffer
+    double* dOutletBuf[2] = {nullptr, nullptr};
+    int outletCur = 0;
+    bool copyPending[2] = {false, false};
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t copyDone[2] = {nullptr, nullptr};
     double* dPartQ = nullptr;      // [nGroups][P][ldt] (nGroups > 1)
     int partGroups = 0;
     double* dD1 = nullptr;         // [P][ldt]
@@ -988,6 +999,7 @@ struct hbk_engine {
     size_t recBytes = 0;
     int* dErr = nullptr;
     unsigned long long* dUnconv = nullptr;
+    int* dUnconvSet = nullptr;  // [P]
     int spinupSteps = 0;
     bool unitsSet = false, ran = false;
     // dated actions
@@ -1180,7 +1192,12 @@ int ensureSetBuffers(hbk_engine* e, int P) {
     freeDev(e->dInitFull);
     freeDev(e->dBasinState);
     freeDev(e->dBasinInit);
-    freeDev(e->dOutlet);
+    if (e->copyStream) cudaStreamSynchronize(e->copyStream);
+    freeDev(e->dOutletBuf[0]);
+    freeDev(e->dOutletBuf[1]);
+    e->dOutlet = nullptr;
+    e->outletCur = 0;
+    e->copyPending[0] = e->copyPending[1] = false;
     freeDev(e->dPartQ);
     freeDev(e->dD1);
     freeDev(e->dD2);
@@ -1198,6 +1215,7 @@ int ensureSetBuffers(hbk_engine* e, int P) {
     freeDev(e->dStale);
     freeDev(e->dScores);
     freeDev(e->dPerm);
+    freeDev(e->dUnconvSet);
     e->perm.clear();
     e->recBytes = 0;
     e->initPerSet = false;
@@ -1209,7 +1227,9 @@ int ensureSetBuffers(hbk_engine* e, int P) {
     HBK_CUDA(cudaMalloc(&e->dBasinState, sizeof(double) * 2 * P));
     HBK_CUDA(cudaMalloc(&e->dBasinInit, sizeof(double) * 2 * P));
     HBK_CUDA(cudaMemsetAsync(e->dBasinInit, 0, sizeof(double) * 2 * P, e->stream));
-    HBK_CUDA(cudaMalloc(&e->dOutlet, sizeof(double) * (size_t)P * e->ldt));
+    HBK_CUDA(cudaMalloc(&e->dOutletBuf[0], sizeof(double) * (size_t)P * e->ldt));
+    e->dOutlet = e->dOutletBuf[0];
+    HBK_CUDA(cudaMalloc(&e->dUnconvSet, sizeof(int) * P));
     e->allocP = P;
     return HBK_OK;
 }
@@ -1301,7 +1321,12 @@ void hbk_engine_destroy(hbk_engine* e) {
     freeDev(e->dInitFull);
     freeDev(e->dBasinState);
     freeDev(e->dBasinInit);
-    freeDev(e->dOutlet);
+    if (e->copyStream) cudaStreamSynchronize(e->copyStream);
+    freeDev(e->dOutletBuf[0]);
+    freeDev(e->dOutletBuf[1]);
+    if (e->copyDone[0]) cudaEventDestroy(e->copyDone[0]);
+    if (e->copyDone[1]) cudaEventDestroy(e->copyDone[1]);
+    if (e->copyStream) cudaStreamDestroy(e->copyStream);
     freeDev(e->dPartQ);
     freeDev(e->dD1);
     freeDev(e->dD2);
@@ -1319,6 +1344,7 @@ void hbk_engine_destroy(hbk_engine* e) {
     freeDev(e->dObs);
     freeDev(e->dErr);
     freeDev(e->dUnconv);
+    freeDev(e->dUnconvSet);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -1728,6 +1754,7 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
     a.T = e->T;
     a.err = e->dErr;
     a.unconverged = e->dUnconv;
+    a.unconvergedPerSet = e->dUnconvSet;
     a.perm = e->dPerm;
     a.outQFinal = multi ? 0 : 1;
 
@@ -1820,6 +1847,18 @@ int hbk_run(hbk_engine* e) {
     HBK_CUDA(cudaSetDevice(e->device));
     chooseShape(e);
     e->lastLaunches = 0;
+    if (e->copyPending[e->outletCur]) {
+        // an asynchronous fetch (hbk_get_outlet_async) is still reading the outlet of the last run: this run writes the
+        // other buffer; should that one still be in flight too, the unit kernel waits for its copy on the device
+        e->outletCur ^= 1;
+        if (!e->dOutletBuf[e->outletCur])
+            HBK_CUDA(cudaMalloc(&e->dOutletBuf[e->outletCur], sizeof(double) * (size_t)e->P * e->ldt));
+        if (e->copyPending[e->outletCur]) {
+            HBK_CUDA(cudaStreamWaitEvent(e->stream, e->copyDone[e->outletCur], 0));
+            e->copyPending[e->outletCur] = false;
+        }
+        e->dOutlet = e->dOutletBuf[e->outletCur];
+    }
 
     // (re)allocate shape-dependent buffers
     const bool multi = e->nGroups > 1;
@@ -1886,6 +1925,7 @@ int hbk_run(hbk_engine* e) {
     }
     HBK_CUDA(cudaMemsetAsync(e->dErr, 0, sizeof(int), e->stream));
     HBK_CUDA(cudaMemsetAsync(e->dUnconv, 0, sizeof(unsigned long long), e->stream));
+    HBK_CUDA(cudaMemsetAsync(e->dUnconvSet, 0, sizeof(int) * e->P, e->stream));
 
     int rc;
     if (e->spinupSteps > 0) {  // ModelHydro::RunSpinup (ModelHydro.cpp:135-181)
@@ -1998,6 +2038,32 @@ int hbk_get_outlet(hbk_engine* e, int32_t first, int32_t n, double* out) {
     return HBK_OK;
 }
 
+int hbk_get_outlet_async(hbk_engine* e, int32_t first, int32_t n, double* out) {
+    if (!e || !out || first < 0 || n <= 0 || first + n > e->P) return HBK_E_ARG;
+    if (!e->ran) return fail(e, HBK_E_STATE, "no completed run");
+    HBK_CUDA(cudaSetDevice(e->device));
+    if (!e->copyStream) {
+        HBK_CUDA(cudaStreamCreateWithFlags(&e->copyStream, cudaStreamNonBlocking));
+        HBK_CUDA(cudaEventCreateWithFlags(&e->copyDone[0], cudaEventDisableTiming));
+        HBK_CUDA(cudaEventCreateWithFlags(&e->copyDone[1], cudaEventDisableTiming));
+    }
+    // hbk_run has drained the compute stream, so the outlet is complete; one strided copy on the copy stream
+    HBK_CUDA(cudaMemcpy2DAsync(out, sizeof(double) * e->T, e->dOutlet + (size_t)first * e->ldt, sizeof(double) * e->ldt,
+                               sizeof(double) * e->T, n, cudaMemcpyDeviceToHost, e->copyStream));
+    HBK_CUDA(cudaEventRecord(e->copyDone[e->outletCur], e->copyStream));
+    e->copyPending[e->outletCur] = true;
+    return HBK_OK;
+}
+
+int hbk_wait_outlet(hbk_engine* e) {
+    if (!e) return HBK_E_ARG;
+    if (!e->copyStream) return HBK_OK;
+    HBK_CUDA(cudaSetDevice(e->device));
+    HBK_CUDA(cudaStreamSynchronize(e->copyStream));
+    e->copyPending[0] = e->copyPending[1] = false;
+    return HBK_OK;
+}
+
 int hbk_get_recorded(hbk_engine* e, int32_t slot, int32_t set, double* out) {
     if (!e || !out || slot < 0 || slot >= HBK_N_RECORDS || set < 0 || set >= e->P) return HBK_E_ARG;
     if (!e->ran) return fail(e, HBK_E_STATE, "no completed run");
@@ -2057,6 +2123,16 @@ int hbk_last_run_stats(hbk_engine* e, double* ms, int32_t* launches, int64_t* un
     if (ms) *ms = e->lastMs;
     if (launches) *launches = e->lastLaunches;
     if (unconverged) *unconverged = e->lastUnconverged;
+    return HBK_OK;
+}
+
+int hbk_get_unconverged(hbk_engine* e, int32_t* out) {
+    if (!e || !out) return HBK_E_ARG;
+    if (!e->ran) return fail(e, HBK_E_STATE, "no completed run");
+    HBK_CUDA(cudaSetDevice(e->device));
+    std::vector<int> tmp(e->P);
+    HBK_CUDA(cudaMemcpy(tmp.data(), e->dUnconvSet, sizeof(int) * e->P, cudaMemcpyDeviceToHost));
+    for (int p = 0; p < e->P; ++p) out[e->dPerm ? e->perm[p] : p] = tmp[p];
     return HBK_OK;
 }
 

@@ -107,11 +107,14 @@ def load_library():
     L.hbk_add_area_scaling_update.argtypes = [vp, i32]
     L.hbk_run.argtypes = [vp]
     L.hbk_get_outlet.argtypes = [vp, i32, i32, dp]
+    L.hbk_get_outlet_async.argtypes = [vp, i32, i32, dp]
+    L.hbk_wait_outlet.argtypes = [vp]
     L.hbk_get_recorded.argtypes = [vp, i32, i32, dp]
     L.hbk_get_state.argtypes = [vp, i32, dp]
     L.hbk_get_basin_state.argtypes = [vp, dp]
     L.hbk_outlet_dev.argtypes = [vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(i64)]
     L.hbk_last_run_stats.argtypes = [vp, dp, ip, ctypes.POINTER(i64)]
+    L.hbk_get_unconverged.argtypes = [vp, ip]
     L.hbk_stream.argtypes = [vp]
     L.hbk_stream.restype = ctypes.c_void_p
     L.hbk_measure_fp64_peak.argtypes = [i32, dp]
@@ -277,6 +280,16 @@ class Engine:
         self._check(self.L.hbk_get_outlet(self.h, int(first), int(n), _dptr(out)))
         return out
 
+    def get_outlet_async(self, out, first=0, n=None):
+        """Queue the copy of the outlet rows into `out` (C-contiguous float64 [n][n_steps], ideally page-locked) on the
+        engine's copy stream; `wait_outlet()` returns when it has landed. The next run() may start right away."""
+        n = self.n_sets - first if n is None else n
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == (n, self.n_steps)
+        self._check(self.L.hbk_get_outlet_async(self.h, int(first), int(n), _dptr(out)))
+
+    def wait_outlet(self):
+        self._check(self.L.hbk_wait_outlet(self.h))
+
     def get_recorded(self, slot, set_index=0):
         out = np.empty((self.n_steps, self.n_units), dtype=np.float64)
         self._check(self.L.hbk_get_recorded(self.h, RECORD_SLOTS.index(slot) if isinstance(slot, str) else slot,
@@ -336,6 +349,12 @@ class Engine:
         ms, n, unc = ctypes.c_double(), ctypes.c_int32(), ctypes.c_int64()
         self._check(self.L.hbk_last_run_stats(self.h, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(unc)))
         return {"kernel_ms": ms.value, "launches": n.value, "unconverged_sweeps": unc.value}
+
+    def unconverged_per_set(self):
+        """Constraint passes per parameter set that did not stabilise within 10 sweeps (hbk_get_unconverged)."""
+        out = np.zeros(self.n_sets, dtype=np.int32)
+        self._check(self.L.hbk_get_unconverged(self.h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        return out
 
     def stream(self):
         return self.L.hbk_stream(self.h)

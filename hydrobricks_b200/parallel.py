@@ -63,7 +63,8 @@ class ShardedEnsemble:
         local = np.ascontiguousarray(shard_rows(matrix, rank, world), dtype=np.float32)
         self.model.model.set_parameter_sets(local)
         self.model.model.run()
-        scores = score_fn(device_outlet(self.model.model._engine))
+        # Socont.engine() gives the ctypes view of the hbk_engine for either host backend (native C++ module or mirror)
+        scores = score_fn(device_outlet(self.model.engine(len(local))))
         return gather_rows(scores, len(matrix), self.group)
 
 

@@ -200,6 +200,11 @@ int hbk_finish_sharded_run(hbk_engine* e);
 
 /* ModelHydro::GetOutletDischarge (ModelHydro.cpp:203-205): out[n_sets][n_steps]. */
 int hbk_get_outlet(hbk_engine* e, int32_t first_set, int32_t n_sets, double* out);
+/* The same without blocking the caller: the copy is queued on a stream of its own (one cudaMemcpy2DAsync; `out` should be
+ * page-locked) and hbk_wait_outlet returns once it has landed. A following hbk_run computes into a second outlet buffer,
+ * so the outlet of run i travels to the host while run i+1 integrates (calibration loops that keep every series). */
+int hbk_get_outlet_async(hbk_engine* e, int32_t first_set, int32_t n_sets, double* out);
+int hbk_wait_outlet(hbk_engine* e);
 /* ModelHydro::GetHydroUnitValues(label) (ModelHydro.cpp:227-236) for one set: out[n_steps][n_units];
  * NaN where the unit's structure variant has no such brick. */
 int hbk_get_recorded(hbk_engine* e, int32_t record_slot, int32_t set, double* out);
@@ -213,6 +218,10 @@ int hbk_get_basin_state(hbk_engine* e, double* out);
 int hbk_outlet_dev(hbk_engine* e, const double** ptr, int64_t* ld);
 /* Device time of the last hbk_run (CUDA events on the engine's stream), and kernel launch count. */
 int hbk_last_run_stats(hbk_engine* e, double* kernel_ms, int32_t* n_launches, int64_t* unconverged_sweeps);
+/* Per parameter set: number of constraint passes of its hydro units in the last run that ended with the reference's
+ * "The storage constraints did not stabilize after 10 sweeps" (Processor.cpp:191-209) — the ill-conditioned small-capacity
+ * regime in which the reference's own result hangs on the last bit. out[n_sets], caller's set order. */
+int hbk_get_unconverged(hbk_engine* e, int32_t* out);
 /* Raw CUDA stream handle (cudaStream_t) the engine launches on, for callers timing with events. */
 void* hbk_stream(hbk_engine* e);
 

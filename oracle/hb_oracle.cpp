@@ -10,6 +10,15 @@
 // tests/test_oracle_vs_ref.py: bit-exact against oracle/_ref where that library and /root/reference are present).
 #include "hb_oracle.h"
 
+#ifdef HBO_COUNT_FLOPS  // instrumented build (oracle/flop_count.h): every FP64 operation counts itself
+hbo_counters g_hbo_counters = {0, 0, 0, 0, 0, 0, 0};
+extern "C" void hbo_flop_counts(unsigned long long* out7, int reset) {
+    const hbo_counters c = g_hbo_counters;
+    out7[0] = c.add; out7[1] = c.mul; out7[2] = c.div; out7[3] = c.cmp; out7[4] = c.abs; out7[5] = c.pow; out7[6] = c.exp;
+    if (reset) g_hbo_counters = {0, 0, 0, 0, 0, 0, 0};
+}
+#endif
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -1101,7 +1110,7 @@ void TransferLandCoverContent(hbo_model& m, Brick& changed, double oldFraction, 
             if (s.role == role) return true;
         return false;
     };
-    auto depth = [&](const std::vector<Slot>& v, int role) {
+    auto depth = [&](const std::vector<Slot>& v, int role) -> double {
         for (const Slot& s : v)
             if (s.role == role) return m.containers[s.container].content;
         return 0.0;

@@ -71,6 +71,10 @@ PRECISION = 1e-8
 
 def build(force: bool = False) -> Path:
     """Compile libhboracle.so (g++ only; seconds)."""
+    import os
+
+    if os.environ.get("HBO_LIB"):  # tools/count_flops.py: the instrumented build (make -C oracle count)
+        return Path(os.environ["HBO_LIB"])
     so = HERE / "libhboracle.so"
     src = HERE / "hb_oracle.cpp"
     if force or not so.exists() or so.stat().st_mtime < max(src.stat().st_mtime, (HERE / "hb_oracle.h").stat().st_mtime):
