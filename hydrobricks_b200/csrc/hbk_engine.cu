@@ -80,6 +80,12 @@ struct KArgs {
     int* err;
     unsigned long long* unconverged;
     int* unconvergedPerSet;  // [P], internal set order: sweeps of that set's units that did not stabilise
+    // work queue (persistent blocks): items = (time slice, virtual block), slice-major; nullptr = one block per virtual
+    // block over the whole segment. progress[vb] = slices of that virtual block that are complete.
+    int* workCounter;
+    int* progress;
+    int nVBlocks, nItems, sliceChunks;
+    unsigned long long* blockTimes;  // tuning aid (HBK_BLOCK_TIMES): [grid][3] start ns, end ns, SM id; else nullptr
     // Parameter sets are stored in an engine-chosen order (similar sets share a warp, hbk_set_parameters);
     // perm[internal index] = caller's index, nullptr = identity. Only what leaves the engine is mapped back:
     // final outlet rows, recorder rows, per-set spatialisation inputs.
@@ -153,17 +159,12 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
     const int nThreads = ENS ? 128 : blockDim.x;  // PB * UB
     // cluster mode: the cluster's CTAs are the unit tiles of one parameter-set group; every CTA keeps its tile's
     // state in registers for the whole segment and the outlet is reduced through distributed shared memory.
-    const int grp = clusterMode ? 0 : blockIdx.x % a.nGroups;
-    const int pg = clusterMode ? blockIdx.x / a.nUTiles : blockIdx.x / a.nGroups;
-    const int crank = clusterMode ? blockIdx.x % a.nUTiles : 0;
     const int pl = tid % PB;
     const int ul = tid / PB;
-    const int p = pg * PB + pl;
-    const bool validP = p < a.P;
-    const int pOut = (validP && a.perm) ? a.perm[p] : p;  // the caller's index of this parameter set
-    const int tileBegin = clusterMode ? crank : grp * a.G;
-    const int tileEnd = clusterMode ? crank + 1 : min(tileBegin + a.G, a.nUTiles);
-    const bool multi = !clusterMode && a.G > 1;
+    // identity of the (virtual) block being integrated: set by setBlock() — once for a plain launch, once per work item
+    // when the blocks are persistent and pull (time slice, virtual block) items from the queue
+    int grp = 0, pg = 0, crank = 0, p = 0, pOut = 0, tileBegin = 0, tileEnd = 0;
+    bool validP = false, multi = false;
 
     // shared memory carve-up
     uint64_t* bars = reinterpret_cast<uint64_t*>(smemRaw);  // 2 mbarriers
@@ -176,7 +177,18 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
     double* sPar = accb + (size_t)(clusterMode ? 2 : 0) * NQ * TC * PB;
     Par par;
     double quickBase = 0, gT = 0, gP = 0, corr = 1;
-    {
+    auto setBlock = [&](int vb) {
+        // cluster mode: the cluster's CTAs are the unit tiles of one parameter-set group; every CTA keeps its tile's
+        // state in registers for the whole segment and the outlet is reduced through distributed shared memory.
+        grp = clusterMode ? 0 : vb % a.nGroups;
+        pg = clusterMode ? vb / a.nUTiles : vb / a.nGroups;
+        crank = clusterMode ? vb % a.nUTiles : 0;
+        p = pg * PB + pl;
+        validP = p < a.P;
+        pOut = (validP && a.perm) ? a.perm[p] : p;  // the caller's index of this parameter set
+        tileBegin = clusterMode ? crank : grp * a.G;
+        tileEnd = clusterMode ? crank + 1 : min(tileBegin + a.G, a.nUTiles);
+        multi = !clusterMode && a.G > 1;
 #if HBK_PAR_SHARED
         double* pv = sPar + pl;
         const int ps = PB;
@@ -219,7 +231,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
                 corr = a.corrP ? a.corrP[pOut] : a.corrPs;
             }
         }
-    }
+    };
 
     // per-(set, unit) values, (re)loaded per tile when the block time-multiplexes several tiles
     Hru h;
@@ -251,25 +263,25 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
         const long long si = (long long)p * a.sP + (long long)u * a.sU;
         const bool groundAmts = full || nearlyZero(fG, kPrecision);
         const bool glacierAmts = full || !glacierVariant || nearlyZero(fGl, kPrecision);
-        h.snowG = a.state[HBK_S_GROUND_SNOW * a.lds + si];
-        h.wG = a.state[HBK_S_GROUND_WATER * a.lds + si];
-        h.slow = a.state[HBK_S_SLOW * a.lds + si];
-        h.slow2 = (NSOIL == 2) ? a.state[HBK_S_SLOW2 * a.lds + si] : 0.0;
-        h.quick = a.state[HBK_S_QUICK * a.lds + si];
+        h.snowG = __ldcg(&a.state[HBK_S_GROUND_SNOW * a.lds + si]);
+        h.wG = __ldcg(&a.state[HBK_S_GROUND_WATER * a.lds + si]);
+        h.slow = __ldcg(&a.state[HBK_S_SLOW * a.lds + si]);
+        h.slow2 = (NSOIL == 2) ? __ldcg(&a.state[HBK_S_SLOW2 * a.lds + si]) : 0.0;
+        h.quick = __ldcg(&a.state[HBK_S_QUICK * a.lds + si]);
         if (groundAmts) {
-            h.amtInfil = a.state[HBK_S_AMT_INFILTRATION * a.lds + si];
-            h.amtRest = a.state[HBK_S_AMT_REST * a.lds + si];
-            h.amtMeltG = a.state[HBK_S_AMT_MELT_GROUND * a.lds + si];
+            h.amtInfil = __ldcg(&a.state[HBK_S_AMT_INFILTRATION * a.lds + si]);
+            h.amtRest = __ldcg(&a.state[HBK_S_AMT_REST * a.lds + si]);
+            h.amtMeltG = __ldcg(&a.state[HBK_S_AMT_MELT_GROUND * a.lds + si]);
         }
         if (GLACIER) {
-            h.snowGl = a.state[HBK_S_GLACIER_SNOW * a.lds + si];
-            h.wGl = a.state[HBK_S_GLACIER_WATER * a.lds + si];
-            h.ice = a.state[HBK_S_ICE * a.lds + si];
+            h.snowGl = __ldcg(&a.state[HBK_S_GLACIER_SNOW * a.lds + si]);
+            h.wGl = __ldcg(&a.state[HBK_S_GLACIER_WATER * a.lds + si]);
+            h.ice = __ldcg(&a.state[HBK_S_ICE * a.lds + si]);
             if (glacierAmts) {
-                h.amtMeltGl = a.state[HBK_S_AMT_MELT_GLACIER * a.lds + si];
-                h.amtDep1 = a.state[HBK_S_AMT_DEPOSIT_RAIN_SNOWMELT * a.lds + si];
-                h.amtDep2 = a.state[HBK_S_AMT_DEPOSIT_ICEMELT * a.lds + si];
-                h.amtSnowIce = a.state[HBK_S_AMT_SNOW_ICE * a.lds + si];
+                h.amtMeltGl = __ldcg(&a.state[HBK_S_AMT_MELT_GLACIER * a.lds + si]);
+                h.amtDep1 = __ldcg(&a.state[HBK_S_AMT_DEPOSIT_RAIN_SNOWMELT * a.lds + si]);
+                h.amtDep2 = __ldcg(&a.state[HBK_S_AMT_DEPOSIT_ICEMELT * a.lds + si]);
+                h.amtSnowIce = __ldcg(&a.state[HBK_S_AMT_SNOW_ICE * a.lds + si]);
             }
         } else {
             h.snowGl = h.wGl = h.ice = h.amtMeltGl = h.amtDep1 = h.amtDep2 = h.amtSnowIce = 0.0;
@@ -306,15 +318,16 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
     const double invDt = DAILY ? 1.0 : 1.0 / a.dt;
     const int nSteps = a.tEnd - a.tBegin;
     const int nChunks = (nSteps + TC - 1) / TC;
-    const int nTilesHere = tileEnd - tileBegin;
-    // forcing pipeline: one load per chunk (station series) or per (chunk, tile) (per-unit series)
-    const int nLoads = (forcingMode == 0) ? nChunks * nTilesHere : nChunks;
+    // the chunks [cBegin, cEnd) of the current work item (the whole segment without the queue) and its forcing loads:
+    // one per chunk (station series) or per (chunk, tile) (per-unit series), numbered seq = 0.. within the item;
+    // loadBase = loads issued by earlier items of this block (the two mbarriers alternate over the running number)
+    int cBegin = 0, cEnd = nChunks, nTilesHere = 0, nLoads = 0, loadBase = 0;
 
     auto issueLoad = [&](int seq) {
-        const int stage = seq & 1;
+        const int stage = (loadBase + seq) & 1;
         double* dst = fbuf + (size_t)stage * 3 * fRow;
         if (forcingMode == 0) {
-            const int c = seq / nTilesHere, tile = tileBegin + seq % nTilesHere;
+            const int c = cBegin + seq / nTilesHere, tile = tileBegin + seq % nTilesHere;
             const int t0 = a.tBegin + c * TC;
             const int n = min(TC, a.tEnd - t0);
             const uint32_t bytes = (uint32_t)(n * UB * sizeof(double));
@@ -324,7 +337,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
                 tmaLoad1D(dst + (size_t)v * fRow, src, bytes, &bars[stage]);
             }
         } else {
-            const int t0 = a.tBegin + seq * TC;
+            const int t0 = a.tBegin + (cBegin + seq) * TC;
             const int t0a = t0 & ~1;  // 16-byte aligned source
             const uint32_t bytes = (uint32_t)((TC + 2) * sizeof(double));
             mbarExpectTx(&bars[stage], 3 * bytes);
@@ -332,20 +345,68 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
         }
     };
 
+    if (a.blockTimes && tid == 0) {
+        unsigned long long t;
+        unsigned sm;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        a.blockTimes[3 * (size_t)blockIdx.x] = t;
+        a.blockTimes[3 * (size_t)blockIdx.x + 2] = sm;
+    }
     if (tid == 0) {
         mbarInit(&bars[0], 1);
         mbarInit(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+
+    const int nRec = __popcll(a.recordMask);
+    const bool queued = a.workCounter != nullptr;
+    __shared__ int sItem;
+    for (;;) {  // work items (exactly one without the queue)
+    int slice = 0, vbCur = 0;
+    if (queued) {
+        // Persistent blocks, items in slice-major order: every virtual block advances slice by slice, whichever block
+        // is free takes the next item. A set-group that is slower than the others no longer holds a multiprocessor
+        // slot to the end of the launch while the rest of the device drains (profiles/r02_tuning.md: 13 % of the
+        // block-time of the C2 launch was such a tail).
+        if (tid == 0) sItem = atomicAdd(a.workCounter, 1);
+        __syncthreads();
+        const int item = sItem;
+        __syncthreads();
+        if (item >= a.nItems) break;
+        slice = item / a.nVBlocks;
+        const int vb = item - slice * a.nVBlocks;
+        vbCur = vb;
+        setBlock(vb);
+        cBegin = slice * a.sliceChunks;
+        cEnd = min(cBegin + a.sliceChunks, nChunks);
+        if (slice > 0) {
+            // the previous slice of this virtual block has a smaller item number, so a running block holds it (or has
+            // finished it): wait for its state to be published
+            if (tid == 0) {
+                int done;
+                long long spins = 0;
+                do {
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(a.progress + vb) : "memory");
+                    if (done < slice) __nanosleep(256);
+                } while (done < slice && ++spins < (1LL << 27));  // ~30 s: a logic error must not hang the device
+                if (done < slice) atomicOr(a.err, kErrQueueStall);
+            }
+            __syncthreads();
+        }
+    } else {
+        setBlock(blockIdx.x);
+    }
+    nTilesHere = tileEnd - tileBegin;
+    nLoads = (forcingMode == 0) ? (cEnd - cBegin) * nTilesHere : (cEnd - cBegin);
     if (tid == 0 && nLoads > 0) issueLoad(0);
 
     int err = 0;
     int unconverged = 0;
-    const int nRec = __popcll(a.recordMask);
     bool loaded = false;
 
-    for (int c = 0; c < nChunks; ++c) {
+    for (int c = cBegin; c < cEnd; ++c) {
         const int t0 = a.tBegin + c * TC;
         const int n = min(TC, a.tEnd - t0);
         const int off = (forcingMode == 1) ? (t0 & 1) : 0;
@@ -354,15 +415,16 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
             const int u = tile * UB + ul;
             const bool valid = validP && (u < a.U);
             // ---- forcing for this (chunk, tile) ----
-            const int seq = (forcingMode == 0) ? c * nTilesHere + tl : c;
+            const int seq = (forcingMode == 0) ? (c - cBegin) * nTilesHere + tl : (c - cBegin);
+            const int gseq = loadBase + seq;
             if (forcingMode == 0 || tl == 0) {
                 if (tid == 0 && seq + 1 < nLoads) issueLoad(seq + 1);
-                mbarWait(&bars[seq & 1], (seq >> 1) & 1);
+                mbarWait(&bars[gseq & 1], (gseq >> 1) & 1);
             }
-            const double* fs = fbuf + (size_t)(seq & 1) * 3 * fRow;
+            const double* fs = fbuf + (size_t)(gseq & 1) * 3 * fRow;
             if (valid && (multi || !loaded)) {
                 loadUnit(u);
-                loadState(u, c == 0);
+                loadState(u, c == cBegin);
             }
             loaded = true;
 
@@ -457,7 +519,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
                     s2[0] = o.dep2;
                 }
             }
-            if (valid && multi) storeState(u, c == nChunks - 1);
+            if (valid && multi) storeState(u, c == cEnd - 1);
             if (clusterMode) {
                 __syncthreads();
                 // this CTA's tile sum -> its partial buffer (double buffered by chunk parity) ...
@@ -532,6 +594,21 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
     if (unconverged) {
         atomicAdd(a.unconverged, (unsigned long long)unconverged);
         if (validP) atomicAdd(&a.unconvergedPerSet[p], unconverged);
+    }
+    if (!queued) break;
+    loadBase += nLoads;
+    // publish the slice: every thread's state stores, then the counter
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const int done = slice + 1;
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.progress + vbCur), "r"(done) : "memory");
+    }
+    }  // work items
+    if (a.blockTimes && tid == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.blockTimes[3 * (size_t)blockIdx.x + 1] = t;
     }
 }
 
@@ -1000,6 +1077,8 @@ struct hbk_engine {
     int* dErr = nullptr;
     unsigned long long* dUnconv = nullptr;
     int* dUnconvSet = nullptr;  // [P]
+    int* dQueue = nullptr;      // work queue of the unit kernel: [0] item counter, [1 + vb] slices done per virtual block
+    size_t queueInts = 0;
     int spinupSteps = 0;
     bool unitsSet = false, ran = false;
     // dated actions
@@ -1345,6 +1424,7 @@ void hbk_engine_destroy(hbk_engine* e) {
     freeDev(e->dErr);
     freeDev(e->dUnconv);
     freeDev(e->dUnconvSet);
+    freeDev(e->dQueue);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -1765,6 +1845,52 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
     const int nPGroups = (e->P + e->PB - 1) / e->PB;
     const long long grid = (long long)nPGroups * (e->clusterMode ? e->nUTiles : e->nGroups);
     if (grid > 2147483647LL) return fail(e, HBK_E_UNSUPPORTED, "grid too large");
+    // tuning aid: HBK_BLOCK_TIMES=<file> dumps start / end time and SM of every block of the (last) unit launch
+    unsigned long long* dTimes = nullptr;
+    const char* timesPath = std::getenv("HBK_BLOCK_TIMES");
+    if (timesPath && cudaMalloc(&dTimes, sizeof(unsigned long long) * 3 * (size_t)grid) == cudaSuccess &&
+        cudaMemset(dTimes, 0, sizeof(unsigned long long) * 3 * (size_t)grid) == cudaSuccess)
+        a.blockTimes = dTimes;
+    // Work queue: when there are more blocks than the device holds at once, launch one persistent block per slot and let
+    // the blocks pull (time slice, virtual block) items — otherwise the launch ends with a long tail in which the slower
+    // parameter-set groups finish alone (measured on C2: the last quarter of the launch ran at falling residency).
+    unsigned launchGrid = (unsigned)grid;
+    a.workCounter = nullptr;
+    a.progress = nullptr;
+    {
+        int perSM = 0;
+        HBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, (const void*)fn, e->PB * e->UB, smem));
+        int nSM = 148;
+        cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, e->device);
+        long long slots = (long long)perSM * nSM;
+        if (const char* forced = std::getenv("HBK_QUEUE_SLOTS")) {  // testing knob: pretend the device holds this many blocks
+            const long long v = std::atoll(forced);
+            if (v > 0) slots = std::min(slots, v);
+        }
+        const int nChunks = (tEnd - tBegin + e->TC - 1) / e->TC;
+        const char* q = std::getenv("HBK_QUEUE");
+        const bool want = !(q && q[0] == '0') && !e->clusterMode && slots > 0 && grid > slots && nChunks >= 8;
+        if (want) {
+            const int targetSlices = 16;
+            a.sliceChunks = std::max(4, (nChunks + targetSlices - 1) / targetSlices);
+            const int nSlices = (nChunks + a.sliceChunks - 1) / a.sliceChunks;
+            a.nVBlocks = (int)grid;
+            const long long nItems = grid * nSlices;
+            if (nItems < 2000000000LL) {
+                a.nItems = (int)nItems;
+                const size_t need = 1 + (size_t)grid;
+                if (need > e->queueInts) {
+                    freeDev(e->dQueue);
+                    HBK_CUDA(cudaMalloc(&e->dQueue, sizeof(int) * need));
+                    e->queueInts = need;
+                }
+                HBK_CUDA(cudaMemsetAsync(e->dQueue, 0, sizeof(int) * need, e->stream));
+                a.workCounter = e->dQueue;
+                a.progress = e->dQueue + 1;
+                launchGrid = (unsigned)slots;
+            }
+        }
+    }
     void* args[] = {(void*)&a};
     if (e->clusterMode) {
         HBK_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -1782,9 +1908,20 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
         cfg.numAttrs = 1;
         HBK_CUDA(cudaLaunchKernelExC(&cfg, (const void*)fn, args));
     } else {
-        HBK_CUDA(cudaLaunchKernel((const void*)fn, dim3((unsigned)grid), dim3(e->PB * e->UB), args, smem, e->stream));
+        HBK_CUDA(cudaLaunchKernel((const void*)fn, dim3(launchGrid), dim3(e->PB * e->UB), args, smem, e->stream));
     }
     e->lastLaunches++;
+    if (dTimes) {
+        std::vector<unsigned long long> h(3 * (size_t)grid);
+        if (cudaStreamSynchronize(e->stream) == cudaSuccess &&
+            cudaMemcpy(h.data(), dTimes, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            if (FILE* f = std::fopen(timesPath, "wb")) {
+                std::fwrite(h.data(), sizeof(unsigned long long), h.size(), f);
+                std::fclose(f);
+            }
+        }
+        cudaFree(dTimes);
+    }
 
     if (writeOutputs && multi) {
         const long long n = (long long)e->P * (tEnd - tBegin);
@@ -1967,6 +2104,7 @@ int hbk_run(hbk_engine* e) {
     e->shardPending = e->shard;
     if (err & kErrRateTooHigh)  // WaterContainer.cpp:83-86 throws; ModelHydro::Run fails
         return fail(e, HBK_E_MODEL, "a change rate exceeded 10000 (WaterContainer::ApplyConstraints)");
+    if (err & kErrQueueStall) return fail(e, HBK_E_CUDA, "internal error: the unit kernel's work queue stalled");
     if (err & kErrActionFraction)
         return fail(e, HBK_E_MODEL, "Application of an action failed: land-cover fraction outside [0 .. 1] or the "
                                     "generic land cover cannot absorb the area change");
