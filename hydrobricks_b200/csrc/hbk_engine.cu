@@ -35,6 +35,9 @@
 
 namespace hbk {
 
+#ifndef HBK_ENS_TC
+#define HBK_ENS_TC 16  // steps per chunk of the compile-time ensemble shape
+#endif
 #ifndef HBK_MAX_THREADS
 #define HBK_MAX_THREADS 128  // largest block the host may launch (PB * UB); 128 x 6 blocks = 24 warps/SM measured best
 #endif
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
     // ENS: the block shape of calibration ensembles fixed at compile time — 32 parameter sets (lanes) x 4 units, 16 steps per
     // chunk, station forcing with fused spatialisation, no cluster — so that the address arithmetic of the time loop
     // folds into immediates (at 80 registers ptxas otherwise re-derives it from the kernel arguments at every step)
-    const int PB = ENS ? 32 : a.PB, UB = ENS ? 4 : a.UB, TC = ENS ? 16 : a.TC;
+    const int PB = ENS ? 32 : a.PB, UB = ENS ? 4 : a.UB, TC = ENS ? HBK_ENS_TC : a.TC;
     const int forcingMode = ENS ? 1 : a.forcingMode;
     const bool clusterMode = ENS ? false : (a.clusterMode != 0);
     const int tid = threadIdx.x;
@@ -1188,7 +1191,7 @@ void chooseShape(hbk_engine* e) {
     // (measured: the shared-memory carve-out shrinks the L1 that serves the register spills; with one block
     // barrier per chunk, 16 steps per chunk is the optimum on C2: 4 -> 2.07e10, 8 -> 2.14e10, 16 -> 2.18e10,
     // profiles/r01_tuning.md)
-    int tc = 16;
+    int tc = HBK_ENS_TC;
     for (;;) {
         const size_t fRow = (e->haveRaw[0] ? (size_t)tc * e->UB : (size_t)tc + 2);
         const size_t bytes = 128 + 2 * 3 * fRow * 8 + (size_t)nq * tc * (e->PB * e->UB + 2 * e->PB) * 8;
@@ -1838,7 +1841,7 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
     a.perm = e->dPerm;
     a.outQFinal = multi ? 0 : 1;
 
-    const bool ens = e->PB == 32 && e->UB == 4 && e->TC == 16 && !tiled && !e->clusterMode && !std::getenv("HBK_NO_ENS_SHAPE");
+    const bool ens = e->PB == 32 && e->UB == 4 && e->TC == HBK_ENS_TC && !tiled && !e->clusterMode && !std::getenv("HBK_NO_ENS_SHAPE");
     KernelFn fn = pickKernel(e->st, ens);
     const size_t smem = smemBytes(e, tiled);
     HBK_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
