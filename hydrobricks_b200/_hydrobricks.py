@@ -28,6 +28,11 @@ _FORCING_NAMES = {"precipitation", "pet", "temperature", "temperature_min", "tem
 # default parameters and forcing of every process type the engine runs.
 _PROCESS_REGISTRY = {
     "melt:degree_day": ([("degree_day_factor", 3.0), ("melting_temperature", 0.0)], ["temperature"]),
+    # ProcessMeltDegreeDayAspect.cpp:13-19, ProcessMeltTemperatureIndex.cpp:14-20
+    "melt:degree_day_aspect": ([("degree_day_factor_n", 3.0), ("degree_day_factor_s", 3.0), ("degree_day_factor_ew", 3.0),
+                                ("melting_temperature", 0.0)], ["temperature"]),
+    "melt:temperature_index": ([("melt_factor", 3.0), ("melting_temperature", 0.0),
+                                ("radiation_coefficient", 0.0007)], ["temperature", "solar_radiation"]),
     "et:socont": ([], ["pet"]),
     "infiltration:socont": ([], []),
     "runoff:socont": ([("beta", 500.0)], []),
@@ -394,8 +399,13 @@ class SettingsModel:
 
     def generate_precipitation_splitters(self, with_snow=True, splitter_type="snow_rain:linear"):
         """SettingsModel::GeneratePrecipitationSplitters (SettingsModel.cpp:491-530)."""
-        if not with_snow:
-            raise RuntimeError("The B200 engine needs the snow routine (with_snow=True) of the Socont family.")
+        if not with_snow:  # SplitterRain (SplitterRain.cpp:37-39): all precipitation is rain, no snowpacks
+            self._add_hydro_unit_splitter("rain", "rain")
+            self._sel_splitter["forcing"] += ["precipitation"]
+            self._add_splitter_output("rain_splitter")
+            self._sel_splitter["parameters"].append(_param("rain_correction_factor", 1.0))
+            self._add_hydro_unit_splitter("rain_splitter", "multi_fluxes")
+            return
         if splitter_type not in ("snow_rain:linear", "snow_rain:threshold"):
             raise RuntimeError(f"Splitter type '{splitter_type}' is not available in the B200 engine.")
         self._add_hydro_unit_splitter("snow_rain_transition", splitter_type)
@@ -748,7 +758,7 @@ class ModelHydro:
             self._engine.set_parameters(self._pending_sets)
         self._engine.set_station_forcing(variable.lower(), series, ref_elevation, gradient, correction)
         self._station = getattr(self, "_station", set()) | {_engine.VAR[variable.lower()]}
-        self._forcing_loaded = len(self._station) == 3
+        self._forcing_loaded = len(self._station) >= (4 if self._cs.hbk.melt_kind == _engine.MELT_TEMPERATURE_INDEX else 3)
 
     # -- parameters ----------------------------------------------------------------------------------
     def update_parameters(self, model_settings):

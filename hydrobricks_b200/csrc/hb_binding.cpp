@@ -72,6 +72,7 @@ int varIndex(std::string name) {
     if (name == "precipitation" || name == "p") return HBK_VAR_PRECIPITATION;
     if (name == "temperature" || name == "t") return HBK_VAR_TEMPERATURE;
     if (name == "pet") return HBK_VAR_PET;
+    if (name == "solar_radiation" || name == "r_solar" || name == "r") return HBK_VAR_SOLAR_RADIATION;
     throw py::value_error("Unknown forcing variable '" + name + "'");
 }
 

@@ -84,6 +84,14 @@ struct ProcessDefaults {
 inline const std::map<string, ProcessDefaults>& processRegistry() {
     static const std::map<string, ProcessDefaults> r = {
         {"melt:degree_day", {{{"degree_day_factor", 3.0f}, {"melting_temperature", 0.0f}}, {"temperature"}}},
+        // ProcessMeltDegreeDayAspect.cpp:13-19, ProcessMeltTemperatureIndex.cpp:14-20
+        {"melt:degree_day_aspect",
+         {{{"degree_day_factor_n", 3.0f}, {"degree_day_factor_s", 3.0f}, {"degree_day_factor_ew", 3.0f},
+           {"melting_temperature", 0.0f}},
+          {"temperature"}}},
+        {"melt:temperature_index",
+         {{{"melt_factor", 3.0f}, {"melting_temperature", 0.0f}, {"radiation_coefficient", 0.0007f}},
+          {"temperature", "solar_radiation"}}},
         {"et:socont", {{}, {"pet"}}},
         {"infiltration:socont", {{}, {}}},
         {"runoff:socont", {{{"beta", 500.0f}}, {}}},
@@ -251,7 +259,14 @@ class SettingsModel {
 
     // ---- generators (SettingsModel.cpp:491-545)
     void GeneratePrecipitationSplitters(bool withSnow = true, const string& type = "snow_rain:linear") {
-        if (!withSnow) throw std::runtime_error("The B200 engine needs the snow routine (with_snow=True).");
+        if (!withSnow) {  // SplitterRain (SplitterRain.cpp:37-39): all precipitation is rain, no snowpacks
+            addSplitter("rain", "rain");
+            splitter().forcing = {"precipitation"};
+            addSplitterOutput("rain_splitter", "water");
+            splitter().parameters.push_back({"rain_correction_factor", 1.0f});
+            addSplitter("rain_splitter", "multi_fluxes");
+            return;
+        }
         if (type != "snow_rain:linear" && type != "snow_rain:threshold")
             throw std::runtime_error("Splitter type '" + type + "' is not available in the B200 engine.");
         addSplitter("snow_rain_transition", type);
@@ -489,6 +504,7 @@ struct UnitSettings {
     double slopeValue = 0;
     string slopeUnit;
     vector<std::pair<string, double>> landCovers;
+    string aspectClass;  // property "aspect_class" (melt:degree_day_aspect)
 };
 
 class SettingsBasin {
@@ -501,7 +517,9 @@ class SettingsBasin {
         units.push_back(u);
     }
     void AddLandCover(const string& name, const string&, double fraction) { last().landCovers.push_back({name, fraction}); }
-    void AddHydroUnitPropertyString(const string&, const string&) {}
+    void AddHydroUnitPropertyString(const string& name, const string& value) {
+        if (name == "aspect_class") last().aspectClass = value;
+    }
     void AddHydroUnitPropertyDouble(const string& name, double value, const string& unit) {
         if (name == "slope") {
             last().hasSlope = true;
@@ -564,6 +582,43 @@ struct Compiled {
         if (kind == "sublimation:pet") return HBK_SUBLIMATION_PET;
         return HBK_SUBLIMATION_NONE;
     }
+    static int meltKindOf(const string& kind) {
+        if (kind == "melt:degree_day") return HBK_MELT_DEGREE_DAY;
+        if (kind == "melt:degree_day_aspect") return HBK_MELT_DEGREE_DAY_ASPECT;
+        if (kind == "melt:temperature_index") return HBK_MELT_TEMPERATURE_INDEX;
+        return -1;
+    }
+    // HydroUnit property "aspect_class" -> HBK_ASPECT_* (ProcessMeltDegreeDayAspect.cpp:38-58)
+    static int aspectOf(const string& a) {
+        if (a == "north" || a == "N") return HBK_ASPECT_NORTH;
+        if (a == "south" || a == "S") return HBK_ASPECT_SOUTH;
+        if (a == "east" || a == "west" || a == "E" || a == "W") return HBK_ASPECT_EAST_WEST;
+        throw std::invalid_argument("Invalid aspect: " + a);
+    }
+    bool noSnow = false;
+    // The melt process of a snowpack or of the glacier ice: its kind (one per structure) and its parameters.
+    void setMelt(const string& component, const Process& proc, int slotA, int slotTm, int slotB, int slotC) {
+        const int kind = meltKindOf(proc.kind);
+        if (kind < 0) throw Unsupported(component + ": melt process " + proc.kind);
+        if (st.melt_kind != -1 && st.melt_kind != kind)
+            throw Unsupported("different melt processes on the snowpacks / the glacier ice");
+        st.melt_kind = kind;
+        set(slotTm, component, "melting_temperature", paramOf(proc.parameters, "melting_temperature"));
+        if (kind == HBK_MELT_DEGREE_DAY) {
+            set(slotA, component, "degree_day_factor", paramOf(proc.parameters, "degree_day_factor"));
+        } else if (kind == HBK_MELT_DEGREE_DAY_ASPECT) {
+            set(slotA, component, "degree_day_factor_n", paramOf(proc.parameters, "degree_day_factor_n"));
+            set(slotB, component, "degree_day_factor_s", paramOf(proc.parameters, "degree_day_factor_s"));
+            bool hasEw, hasWe;
+            const float ew = paramOf(proc.parameters, "degree_day_factor_ew", &hasEw);
+            const float we = paramOf(proc.parameters, "degree_day_factor_we", &hasWe);
+            if (!hasEw && !hasWe) throw Unsupported("Missing parameter 'degree_day_factor_ew' or 'degree_day_factor_we'");
+            set(slotC, component, hasEw ? "degree_day_factor_ew" : "degree_day_factor_we", hasEw ? ew : we);
+        } else {
+            set(slotA, component, "melt_factor", paramOf(proc.parameters, "melt_factor"));
+            set(slotB, component, "radiation_coefficient", paramOf(proc.parameters, "radiation_coefficient"));
+        }
+    }
     static int snowIceKindOf(const string& kind) {
         if (kind == "transform:snow_ice_constant" || kind == "transformation:snow_ice_constant") return HBK_SNOW_ICE_CONSTANT;
         if (kind == "transform:snow_ice_swat" || kind == "transformation:snow_ice_swat") return HBK_SNOW_ICE_SWAT;
@@ -620,6 +675,7 @@ struct Compiled {
         st.sublimation_kind = HBK_SUBLIMATION_NONE;
         st.north_hemisphere = 1;
         st.start_mjd = startMjd;
+        st.melt_kind = -1;
         const auto& structures = sm.Structures();
         if (structures.empty()) throw Unsupported("empty structure");
         if (structures.size() > 2) throw Unsupported("more than two structure variants");
@@ -654,33 +710,57 @@ struct Compiled {
         // splitters
         if (!base->subBasinSplitters.empty()) throw Unsupported("sub-basin splitters");
         const Splitter* tr = nullptr;
+        const Splitter* rainOnly = nullptr;
         int nMulti = 0;
         for (auto& s : full.hydroUnitSplitters) {
             if (s.kind == "snow_rain:linear" || s.kind == "snow_rain:threshold") tr = &s;
+            if (s.kind == "rain") rainOnly = &s;
             if (s.kind == "multi_fluxes") nMulti++;
         }
-        if (!tr || nMulti != 2 || full.hydroUnitSplitters.size() != 3)
-            throw Unsupported("expected snow_rain_transition + rain/snow multi_fluxes splitters");
-        if (tr->kind == "snow_rain:linear") {
-            st.splitter_kind = HBK_SPLIT_LINEAR;
-            set(HBK_P_TRANSITION_START, tr->name, "transition_start", paramOf(tr->parameters, "transition_start"));
-            set(HBK_P_TRANSITION_END, tr->name, "transition_end", paramOf(tr->parameters, "transition_end"));
-        } else {
-            st.splitter_kind = HBK_SPLIT_THRESHOLD;
-            set(HBK_P_TRANSITION_START, tr->name, "threshold", paramOf(tr->parameters, "threshold"));
-        }
-        bool f;
-        float rcf = paramOf(tr->parameters, "rain_correction_factor", &f);
-        set(HBK_P_RAIN_CORRECTION, tr->name, "rain_correction_factor", f ? rcf : 1.0f);
-        float scf = paramOf(tr->parameters, "snow_correction_factor", &f);
-        set(HBK_P_SNOW_CORRECTION, tr->name, "snow_correction_factor", f ? scf : 1.0f);
         vector<string> rainTargets, snowTargets;
-        for (auto& o : tr->outputs) {
+        bool f;
+        noSnow = rainOnly && !tr;
+        if (noSnow) {
+            // SettingsModel::GeneratePrecipitationSplitters(withSnow = false) (SettingsModel.cpp:518-529): SplitterRain
+            // (SplitterRain.cpp:37-39) sends precipitation x rain_correction_factor to the land covers; no snowpacks. On
+            // the device this is the threshold splitter with a threshold no temperature reaches (-FLT_MAX): rain =
+            // precipitation x rcf, snow = 0, and the snowpack code only ever moves zeros.
+            if (nMulti != 1 || full.hydroUnitSplitters.size() != 2)
+                throw Unsupported("expected the rain splitter + the rain multi_fluxes splitter");
+            tr = rainOnly;
+            st.splitter_kind = HBK_SPLIT_THRESHOLD;
+            params[HBK_P_TRANSITION_START] = -3.402823466e+38f;
+            params[HBK_P_SNOW_CORRECTION] = 1.0f;
+            float rcf = paramOf(tr->parameters, "rain_correction_factor", &f);
+            set(HBK_P_RAIN_CORRECTION, tr->name, "rain_correction_factor", f ? rcf : 1.0f);
             const Splitter* tgt = nullptr;
-            for (auto& s : full.hydroUnitSplitters)
-                if (s.name == o.target && s.kind == "multi_fluxes") tgt = &s;
-            if (!tgt) throw Unsupported("snow_rain_transition must feed multi_fluxes splitters");
-            for (auto& oo : tgt->outputs) (o.fluxType == "snow" ? snowTargets : rainTargets).push_back(oo.target);
+            if (tr->outputs.size() == 1)
+                for (auto& s : full.hydroUnitSplitters)
+                    if (s.name == tr->outputs[0].target && s.kind == "multi_fluxes") tgt = &s;
+            if (!tgt) throw Unsupported("the rain splitter must feed a multi_fluxes splitter");
+            for (auto& oo : tgt->outputs) rainTargets.push_back(oo.target);
+        } else {
+            if (!tr || nMulti != 2 || full.hydroUnitSplitters.size() != 3)
+                throw Unsupported("expected snow_rain_transition + rain/snow multi_fluxes splitters");
+            if (tr->kind == "snow_rain:linear") {
+                st.splitter_kind = HBK_SPLIT_LINEAR;
+                set(HBK_P_TRANSITION_START, tr->name, "transition_start", paramOf(tr->parameters, "transition_start"));
+                set(HBK_P_TRANSITION_END, tr->name, "transition_end", paramOf(tr->parameters, "transition_end"));
+            } else {
+                st.splitter_kind = HBK_SPLIT_THRESHOLD;
+                set(HBK_P_TRANSITION_START, tr->name, "threshold", paramOf(tr->parameters, "threshold"));
+            }
+            float rcf = paramOf(tr->parameters, "rain_correction_factor", &f);
+            set(HBK_P_RAIN_CORRECTION, tr->name, "rain_correction_factor", f ? rcf : 1.0f);
+            float scf = paramOf(tr->parameters, "snow_correction_factor", &f);
+            set(HBK_P_SNOW_CORRECTION, tr->name, "snow_correction_factor", f ? scf : 1.0f);
+            for (auto& o : tr->outputs) {
+                const Splitter* tgt = nullptr;
+                for (auto& s : full.hydroUnitSplitters)
+                    if (s.name == o.target && s.kind == "multi_fluxes") tgt = &s;
+                if (!tgt) throw Unsupported("snow_rain_transition must feed multi_fluxes splitters");
+                for (auto& oo : tgt->outputs) (o.fluxType == "snow" ? snowTargets : rainTargets).push_back(oo.target);
+            }
         }
 
         // land covers
@@ -733,7 +813,7 @@ struct Compiled {
                 }
             }
             SnowpackInfo info{sp, nullptr, nullptr};
-            bool ok = sp && !sp->processes.empty() && sp->processes[0].kind == "melt:degree_day" &&
+            bool ok = sp && !sp->processes.empty() && meltKindOf(sp->processes[0].kind) >= 0 &&
                       target(sp->processes[0]) == cover.name;
             if (ok) {
                 size_t i = 1;
@@ -752,7 +832,7 @@ struct Compiled {
             }
             if (!ok)
                 throw Unsupported("cover " + cover.name + ": expected one snowpack with melt:degree_day"
-                                  " [+ transform:snow_ice_constant|swat on a glacier] [+ sublimation:constant|pet]");
+                                  "|degree_day_aspect|temperature_index [+ transform:snow_ice_constant|swat on a glacier] [+ sublimation:constant|pet]");
             return info;
         };
         auto setSublimation = [&](const Brick& sp, const Process& proc, int slot, const char* record) {
@@ -764,23 +844,31 @@ struct Compiled {
             set(slot, sp.name, pname, paramOf(proc.parameters, pname));
             label(sp.name + ":" + proc.name + ":output", record);
         };
-        const SnowpackInfo gInfo = snowpackOf(*ground);
-        const Brick& gsp = *gInfo.brick;
-        if (gInfo.sublim) setSublimation(gsp, *gInfo.sublim, HBK_P_GROUND_SUBLIMATION, "ground_snowpack_sublimation");
-        set(HBK_P_GROUND_SNOW_DDF, gsp.name, "degree_day_factor", paramOf(gsp.processes[0].parameters, "degree_day_factor"));
-        set(HBK_P_GROUND_SNOW_TMELT, gsp.name, "melting_temperature",
-            paramOf(gsp.processes[0].parameters, "melting_temperature"));
-        label(gsp.name + ":water_content", "ground_snowpack_water");
-        label(gsp.name + ":snow_content", "ground_snowpack_snow");
-        label(gsp.name + ":" + gsp.processes[0].name + ":output", "ground_snowpack_melt");
-        vector<string> snowpacks = {gsp.name};
-        std::set<string> known = {ground->name, gsp.name, slowName, quickName};
+        vector<string> snowpacks;
+        std::set<string> known = {ground->name, slowName, quickName};
+        SnowpackInfo gInfo{nullptr, nullptr, nullptr};
+        if (!noSnow) {
+            gInfo = snowpackOf(*ground);
+            const Brick& gsp = *gInfo.brick;
+            if (gInfo.sublim) setSublimation(gsp, *gInfo.sublim, HBK_P_GROUND_SUBLIMATION, "ground_snowpack_sublimation");
+            setMelt(gsp.name, gsp.processes[0], HBK_P_GROUND_SNOW_DDF, HBK_P_GROUND_SNOW_TMELT, HBK_P_GROUND_SNOW_MELT_B,
+                    HBK_P_GROUND_SNOW_MELT_C);
+            label(gsp.name + ":water_content", "ground_snowpack_water");
+            label(gsp.name + ":snow_content", "ground_snowpack_snow");
+            label(gsp.name + ":" + gsp.processes[0].name + ":output", "ground_snowpack_melt");
+            snowpacks.push_back(gsp.name);
+            known.insert(gsp.name);
+        }
 
         string b1, b2;
         if (glacier) {
             st.has_glacier = 1;
-            if (kinds(*glacier) != vector<string>{"outflow:direct", "melt:degree_day"})
-                throw Unsupported("glacier cover: expected outflow:direct + melt:degree_day");
+            {
+                const vector<string> gk = kinds(*glacier);
+                if (gk.size() != 2 || gk[0] != "outflow:direct" || meltKindOf(gk[1]) < 0)
+                    throw Unsupported("glacier cover: expected outflow:direct + melt:degree_day|degree_day_aspect|"
+                                      "temperature_index");
+            }
             for (auto& p : glacier->processes)
                 if (p.outputs.empty() || !p.outputs[0].instantaneous) throw Unsupported("glacier outputs must be instantaneous");
             b1 = target(glacier->processes[0]);
@@ -790,48 +878,49 @@ struct Compiled {
             float noMelt = paramOf(glacier->parameters, "no_melt_when_snow_cover", &hasNoMelt);
             st.glacier_infinite_storage = hasInf && std::fabs(inf) > 1.1920929e-07f ? 1 : 0;  // Glacier.cpp:23-28
             st.glacier_no_melt_when_snow_cover = hasNoMelt && noMelt > 0 ? 1 : 0;
-            set(HBK_P_ICE_DDF, glacier->name, "degree_day_factor", paramOf(glacier->processes[1].parameters, "degree_day_factor"));
-            set(HBK_P_ICE_TMELT, glacier->name, "melting_temperature",
-                paramOf(glacier->processes[1].parameters, "melting_temperature"));
-            const SnowpackInfo glInfo = snowpackOf(*glacier);
-            const Brick& glsp = *glInfo.brick;
-            if ((glInfo.sublim == nullptr) != (gInfo.sublim == nullptr))
-                throw Unsupported("sublimation must be on every snowpack or on none");
-            if (glInfo.sublim)
-                setSublimation(glsp, *glInfo.sublim, HBK_P_GLACIER_SUBLIMATION, "glacier_snowpack_sublimation");
-            set(HBK_P_GLACIER_SNOW_DDF, glsp.name, "degree_day_factor",
-                paramOf(glsp.processes[0].parameters, "degree_day_factor"));
-            set(HBK_P_GLACIER_SNOW_TMELT, glsp.name, "melting_temperature",
-                paramOf(glsp.processes[0].parameters, "melting_temperature"));
+            setMelt(glacier->name, glacier->processes[1], HBK_P_ICE_DDF, HBK_P_ICE_TMELT, HBK_P_ICE_MELT_B, HBK_P_ICE_MELT_C);
             const string& n = glacier->name;
             label(n + ":water_content", "glacier_water");
             label(n + ":ice_content", "glacier_ice");
             label(n + ":" + glacier->processes[0].name + ":output", "glacier_outflow");
             label(n + ":" + glacier->processes[1].name + ":output", "glacier_melt");
-            label(glsp.name + ":water_content", "glacier_snowpack_water");
-            label(glsp.name + ":snow_content", "glacier_snowpack_snow");
-            label(glsp.name + ":" + glsp.processes[0].name + ":output", "glacier_snowpack_melt");
-            snowpacks.push_back(glsp.name);
-            if (glInfo.transfo) {
-                const Process& tp = *glInfo.transfo;
-                st.snow_ice_kind = snowIceKindOf(tp.kind);
-                bool has;
-                string pname;
-                if (st.snow_ice_kind == HBK_SNOW_ICE_CONSTANT) {
-                    paramOf(tp.parameters, "snow_ice_transformation_rate", &has);
-                    pname = has ? "snow_ice_transformation_rate" : "rate";
-                } else {
-                    paramOf(tp.parameters, "snow_ice_transformation_basal_acc_coeff", &has);
-                    pname = has ? "snow_ice_transformation_basal_acc_coeff" : "basal_acc_coeff";
-                    bool hasNh;
-                    const float nh = paramOf(tp.parameters, "north_hemisphere", &hasNh);
-                    st.north_hemisphere = (hasNh && nh == 0) ? 0 : 1;
+            if (noSnow) {
+                if (st.glacier_no_melt_when_snow_cover)  // IceContainer.cpp:10-32 needs the related snowpack
+                    throw Unsupported("No snowpack provided for the glacier melt limitation.");
+            } else {
+                const SnowpackInfo glInfo = snowpackOf(*glacier);
+                const Brick& glsp = *glInfo.brick;
+                if ((glInfo.sublim == nullptr) != (gInfo.sublim == nullptr))
+                    throw Unsupported("sublimation must be on every snowpack or on none");
+                if (glInfo.sublim)
+                    setSublimation(glsp, *glInfo.sublim, HBK_P_GLACIER_SUBLIMATION, "glacier_snowpack_sublimation");
+                setMelt(glsp.name, glsp.processes[0], HBK_P_GLACIER_SNOW_DDF, HBK_P_GLACIER_SNOW_TMELT,
+                        HBK_P_GLACIER_SNOW_MELT_B, HBK_P_GLACIER_SNOW_MELT_C);
+                label(glsp.name + ":water_content", "glacier_snowpack_water");
+                label(glsp.name + ":snow_content", "glacier_snowpack_snow");
+                label(glsp.name + ":" + glsp.processes[0].name + ":output", "glacier_snowpack_melt");
+                snowpacks.push_back(glsp.name);
+                known.insert(glsp.name);
+                if (glInfo.transfo) {
+                    const Process& tp = *glInfo.transfo;
+                    st.snow_ice_kind = snowIceKindOf(tp.kind);
+                    bool has;
+                    string pname;
+                    if (st.snow_ice_kind == HBK_SNOW_ICE_CONSTANT) {
+                        paramOf(tp.parameters, "snow_ice_transformation_rate", &has);
+                        pname = has ? "snow_ice_transformation_rate" : "rate";
+                    } else {
+                        paramOf(tp.parameters, "snow_ice_transformation_basal_acc_coeff", &has);
+                        pname = has ? "snow_ice_transformation_basal_acc_coeff" : "basal_acc_coeff";
+                        bool hasNh;
+                        const float nh = paramOf(tp.parameters, "north_hemisphere", &hasNh);
+                        st.north_hemisphere = (hasNh && nh == 0) ? 0 : 1;
+                    }
+                    set(HBK_P_SNOW_ICE, glsp.name, pname, paramOf(tp.parameters, pname));
+                    label(glsp.name + ":" + tp.name + ":output", "glacier_snowpack_transfo");
                 }
-                set(HBK_P_SNOW_ICE, glsp.name, pname, paramOf(tp.parameters, pname));
-                label(glsp.name + ":" + tp.name + ":output", "glacier_snowpack_transfo");
             }
             known.insert(glacier->name);
-            known.insert(glsp.name);
             int slot[2] = {HBK_P_K_SNOW, HBK_P_K_ICE};
             const string* names[2] = {&b1, &b2};
             for (int i = 0; i < 2; ++i) {
@@ -929,6 +1018,7 @@ struct Compiled {
             if (!known.count(b.name)) throw Unsupported("brick outside the Socont family: " + b.name);
             if (!b.forcing.empty()) throw Unsupported("brick-level forcing");
         }
+        if (st.melt_kind < 0) st.melt_kind = HBK_MELT_DEGREE_DAY;
     }
 
     // ModelBuilder::AssignHydroUnitStructures (ModelBuilder.cpp:36-97) -> glacier-variant flag of one unit
@@ -1232,6 +1322,11 @@ class ModelHydro {
         }
         check(hbk_set_units(_e, area.data(), elev.data(), _c->st.quick_kind == HBK_QUICK_SOCONT ? slope.data() : nullptr,
                             gv.data(), fg.data(), fgl.data()));
+        if (_c->st.melt_kind == HBK_MELT_DEGREE_DAY_ASPECT) {
+            vector<int32_t> aspect(U);
+            for (int u = 0; u < U; ++u) aspect[u] = Compiled::aspectOf(_units[u].aspectClass);
+            check(hbk_set_unit_aspect(_e, aspect.data()));
+        }
         check(hbk_set_spinup_steps(_e, (int)(ms.spinupDays / _dt)));
         _labels = ms.GetHydroUnitLogLabels();
         _sets.assign(_c->params, _c->params + HBK_N_PARAMS);
@@ -1250,6 +1345,8 @@ class ModelHydro {
             var = HBK_VAR_TEMPERATURE;
         } else if (key == "pet") {
             var = HBK_VAR_PET;
+        } else if (key == "solar_radiation" || key == "r_solar" || key == "r") {  // TimeSeries.cpp:134-146
+            var = HBK_VAR_SOLAR_RADIATION;
         } else {
             throw std::invalid_argument("Unknown forcing variable '" + name + "'");
         }
@@ -1299,7 +1396,7 @@ class ModelHydro {
         if (gradSet || corrSet) check(hbk_set_parameters(_e, _nSets, _sets.data()));
         check(hbk_set_station_forcing(_e, var, series, zref, gradient, gradSet, corr, corrSet));
         _stationVars.insert(var);
-        _forcingLoaded = _stationVars.size() == 3;
+        _forcingLoaded = _stationVars.size() >= (_c->st.melt_kind == HBK_MELT_TEMPERATURE_INDEX ? 4u : 3u);
     }
 
     // ---- parameters

@@ -64,7 +64,8 @@ struct KArgs {
     long long fracLd;
     int fracPerSet;
     int forcingMode;            // 0: tiled per-unit series, 1: station series + fused spatialisation
-    const double* forcing[3];   // mode 0: [nUTiles][tld][UB]; mode 1: [tld]
+    const double* forcing[HBK_N_VARS];  // mode 0: [nUTiles][tld][UB]; mode 1: [tld]
+    int nVars;                  // 3, or 4 with the solar radiation of melt:temperature_index
     long long tld;
     const double* gradT;  // per set or nullptr
     const double* gradP;
@@ -139,6 +140,36 @@ __device__ __noinline__ double2 sublimationRates(const float* params, int ldp, i
     return r;
 }
 
+// The three melt factors of one (set, unit) under melt:degree_day_aspect (aspect: HBK_ASPECT_*) resp. of one step under
+// melt:temperature_index. Out of line and read from global memory at use like the sublimation rates: structures with the
+// plain melt:degree_day carry neither registers nor instructions for them in the time loop.
+struct AspectFactors {
+    double ground, glacierSnow, ice;
+};
+template <bool GLACIER>
+__device__ __noinline__ AspectFactors aspectFactors(const float* params, int ldp, int p, int aspect) {
+    const int g = aspect == 0 ? HBK_P_GROUND_SNOW_DDF : (aspect == 1 ? HBK_P_GROUND_SNOW_MELT_B : HBK_P_GROUND_SNOW_MELT_C);
+    const int s = aspect == 0 ? HBK_P_GLACIER_SNOW_DDF : (aspect == 1 ? HBK_P_GLACIER_SNOW_MELT_B : HBK_P_GLACIER_SNOW_MELT_C);
+    const int i = aspect == 0 ? HBK_P_ICE_DDF : (aspect == 1 ? HBK_P_ICE_MELT_B : HBK_P_ICE_MELT_C);
+    AspectFactors f;
+    f.ground = (double)params[p + (size_t)g * ldp];
+    f.glacierSnow = GLACIER ? (double)params[p + (size_t)s * ldp] : 0.0;
+    f.ice = GLACIER ? (double)params[p + (size_t)i * ldp] : 0.0;
+    return f;
+}
+template <bool GLACIER>
+__device__ __noinline__ AspectFactors radiationFactors(const float* params, int ldp, int p, double radiation) {
+    AspectFactors f;  // float32 parameters promoted, the product and the sum in double like the reference's expression
+    f.ground = (double)params[p + (size_t)HBK_P_GROUND_SNOW_DDF * ldp] +
+               (double)params[p + (size_t)HBK_P_GROUND_SNOW_MELT_B * ldp] * radiation;
+    f.glacierSnow = GLACIER ? (double)params[p + (size_t)HBK_P_GLACIER_SNOW_DDF * ldp] +
+                                  (double)params[p + (size_t)HBK_P_GLACIER_SNOW_MELT_B * ldp] * radiation
+                            : 0.0;
+    f.ice = GLACIER ? (double)params[p + (size_t)HBK_P_ICE_DDF * ldp] + (double)params[p + (size_t)HBK_P_ICE_MELT_B * ldp] * radiation
+                    : 0.0;
+    return f;
+}
+
 // ---- main kernel ------------------------------------------------------------------------------------
 // Block = PB parameter sets x UB units (threads), time-multiplexed over a GROUP of G consecutive unit tiles:
 //   for each chunk of TC steps: for each tile of the group: [load state] TC steps [store state], add the tile's
@@ -157,6 +188,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
     // folds into immediates (at 80 registers ptxas otherwise re-derives it from the kernel arguments at every step)
     const int PB = ENS ? 32 : a.PB, UB = ENS ? 4 : a.UB, TC = ENS ? HBK_ENS_TC : a.TC;
     const int forcingMode = ENS ? 1 : a.forcingMode;
+    const int NV = ENS ? 3 : a.nVars;  // staged forcing variables (the ensemble shape never carries the radiation)
     const bool clusterMode = ENS ? false : (a.clusterMode != 0);
     const int tid = threadIdx.x;
     const int nThreads = ENS ? 128 : blockDim.x;  // PB * UB
@@ -172,8 +204,8 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
     // shared memory carve-up
     uint64_t* bars = reinterpret_cast<uint64_t*>(smemRaw);  // 2 mbarriers
     const int fRow = (forcingMode == 0) ? TC * UB : (TC + 2);  // doubles per variable per stage
-    double* fbuf = reinterpret_cast<double*>(smemRaw + 128);             // [2][3][fRow]
-    double* qbuf = fbuf + 2 * 3 * fRow;                                  // [NQ][TC][nThreads]
+    double* fbuf = reinterpret_cast<double*>(smemRaw + 128);             // [2][NV][fRow]
+    double* qbuf = fbuf + 2 * NV * fRow;                                 // [NQ][TC][nThreads]
     double* accb = qbuf + (size_t)NQ * TC * nThreads;                  // cluster mode only: [2][NQ][TC][PB]
 
     // per-parameter-set constants: shared memory [field][PB] (or registers, HBK_PAR_SHARED=0)
@@ -249,7 +281,18 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
         // runoff:socont folded: beta*sqrt(slope)/area * (2/1000)^(5/3) * 86400 * 1000 (ProcessRunoffSocont.cpp:41-56)
         const double socontUnit = 3.174802103936398e-05 * 86400.0 * 1000.0;
         par.quickV = (a.flags.quickKind == 0) ? quickBase * slopeTerm / area * socontUnit : quickBase;
-        glacierVariant = GLACIER && (a.hruFlags[u] & 1);
+        const int unitFlags = a.hruFlags[u];
+        glacierVariant = GLACIER && (unitFlags & 1);
+#if !HBK_PAR_SHARED
+        if (a.flags.meltKind == HBK_MELT_DEGREE_DAY_ASPECT) {
+            // ProcessMeltDegreeDayAspect::SetParameters (ProcessMeltDegreeDayAspect.cpp:38-58): the melt processes of this
+            // unit use the degree-day factor of its aspect class — a per-(set, unit) value, picked when the unit is loaded
+            const AspectFactors f3 = aspectFactors<GLACIER>(a.params, a.ldp, p, (unitFlags >> 1) & 3);
+            par.v[5] = f3.ground;
+            par.v[7] = f3.glacierSnow;
+            par.v[9] = f3.ice;
+        }
+#endif
         const long long fi = a.fracPerSet ? ((long long)p * a.U + u) : u;
         fG = a.frac[fi];
         fGl = a.frac[a.fracLd + fi];
@@ -328,14 +371,14 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
 
     auto issueLoad = [&](int seq) {
         const int stage = (loadBase + seq) & 1;
-        double* dst = fbuf + (size_t)stage * 3 * fRow;
+        double* dst = fbuf + (size_t)stage * NV * fRow;
         if (forcingMode == 0) {
             const int c = cBegin + seq / nTilesHere, tile = tileBegin + seq % nTilesHere;
             const int t0 = a.tBegin + c * TC;
             const int n = min(TC, a.tEnd - t0);
             const uint32_t bytes = (uint32_t)(n * UB * sizeof(double));
-            mbarExpectTx(&bars[stage], 3 * bytes);
-            for (int v = 0; v < 3; ++v) {
+            mbarExpectTx(&bars[stage], NV * bytes);
+            for (int v = 0; v < NV; ++v) {
                 const double* src = a.forcing[v] + ((size_t)tile * a.tld + t0) * UB;
                 tmaLoad1D(dst + (size_t)v * fRow, src, bytes, &bars[stage]);
             }
@@ -343,8 +386,8 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
             const int t0 = a.tBegin + (cBegin + seq) * TC;
             const int t0a = t0 & ~1;  // 16-byte aligned source
             const uint32_t bytes = (uint32_t)((TC + 2) * sizeof(double));
-            mbarExpectTx(&bars[stage], 3 * bytes);
-            for (int v = 0; v < 3; ++v) tmaLoad1D(dst + (size_t)v * fRow, a.forcing[v] + t0a, bytes, &bars[stage]);
+            mbarExpectTx(&bars[stage], NV * bytes);
+            for (int v = 0; v < NV; ++v) tmaLoad1D(dst + (size_t)v * fRow, a.forcing[v] + t0a, bytes, &bars[stage]);
         }
     };
 
@@ -424,7 +467,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
                 if (tid == 0 && seq + 1 < nLoads) issueLoad(seq + 1);
                 mbarWait(&bars[gseq & 1], (gseq >> 1) & 1);
             }
-            const double* fs = fbuf + (size_t)(gseq & 1) * 3 * fRow;
+            const double* fs = fbuf + (size_t)(gseq & 1) * NV * fRow;
             if (valid && (multi || !loaded)) {
                 loadUnit(u);
                 loadState(u, c == cBegin);
@@ -450,6 +493,16 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
                         precip = (precip < 0.0) ? 0.0 : precip;
                         pet = (pet < 0.0) ? 0.0 : pet;
                     }
+#if !HBK_PAR_SHARED
+                    if (!ENS && a.flags.meltKind == HBK_MELT_TEMPERATURE_INDEX) {
+                        // ProcessMeltTemperatureIndex.cpp:68-71: (T - Tm) * (melt_factor + radiation_coefficient * R); the
+                        // factor in brackets takes the place of the degree-day factor for this step
+                        const AspectFactors f3 = radiationFactors<GLACIER>(a.params, a.ldp, p, fp[3 * fRow]);
+                        par.v[5] = f3.ground;
+                        par.v[7] = f3.glacierSnow;
+                        par.v[9] = f3.ice;
+                    }
+#endif
                     double sublimG = 0.0, sublimGl = 0.0;
                     if (a.flags.sublimKind != 0) {
                         const double2 su = sublimationRates<GLACIER>(a.params, a.ldp, a.flags.sublimKind, p, pet);
@@ -1041,10 +1094,12 @@ struct hbk_engine {
     double* dFrac = nullptr;      // [2][U] (per unit) or [2][P*U]
     double* dFracInit = nullptr;  // initial fractions [2][U]
     int fracPerSet = 0;
-    double* dForcingRaw[3] = {nullptr, nullptr, nullptr};    // [T][U]
-    double* dForcingTiled[3] = {nullptr, nullptr, nullptr};  // [nUTiles][tld][UB]
-    double* dStation[3] = {nullptr, nullptr, nullptr};       // [tld]
-    bool haveRaw[3] = {false, false, false}, haveStation[3] = {false, false, false};
+    double* dForcingRaw[HBK_N_VARS] = {};    // [T][U]
+    double* dForcingTiled[HBK_N_VARS] = {};  // [nUTiles][tld][UB]
+    double* dStation[HBK_N_VARS] = {};       // [tld]
+    bool haveRaw[HBK_N_VARS] = {}, haveStation[HBK_N_VARS] = {};
+    int nVars() const { return st.melt_kind == HBK_MELT_TEMPERATURE_INDEX ? 4 : 3; }
+    std::vector<int> hAspect;  // HBK_ASPECT_* per unit (hbk_set_unit_aspect); empty = not given
     int tiledUB = 0;
     double* dGradT = nullptr;
     double* dGradP = nullptr;
@@ -1194,7 +1249,7 @@ void chooseShape(hbk_engine* e) {
     int tc = HBK_ENS_TC;
     for (;;) {
         const size_t fRow = (e->haveRaw[0] ? (size_t)tc * e->UB : (size_t)tc + 2);
-        const size_t bytes = 128 + 2 * 3 * fRow * 8 + (size_t)nq * tc * (e->PB * e->UB + 2 * e->PB) * 8;
+        const size_t bytes = 128 + 2 * e->nVars() * fRow * 8 + (size_t)nq * tc * (e->PB * e->UB + 2 * e->PB) * 8;
         if (bytes <= budget || tc == 2) break;
         tc /= 2;
     }
@@ -1208,7 +1263,7 @@ void chooseShape(hbk_engine* e) {
 size_t smemBytes(const hbk_engine* e, bool tiled) {
     const int nq = e->st.has_glacier ? 3 : 1;
     const size_t fRow = tiled ? (size_t)e->TC * e->UB : (size_t)e->TC + 2;
-    return 128 + 2 * 3 * fRow * 8 + (size_t)nq * e->TC * (e->PB * e->UB + (e->clusterMode ? 2 * e->PB : 0)) * 8 +
+    return 128 + 2 * e->nVars() * fRow * 8 + (size_t)nq * e->TC * (e->PB * e->UB + (e->clusterMode ? 2 * e->PB : 0)) * 8 +
            (HBK_PAR_SHARED ? (size_t)hbk::kParFields * e->PB * 8 : 0);
 }
 
@@ -1362,6 +1417,10 @@ int hbk_engine_create(const hbk_structure* st, int32_t n_units, int32_t n_steps,
         return bail(HBK_E_ARG, "unknown snow_ice_kind");
     if (st->sublimation_kind < HBK_SUBLIMATION_NONE || st->sublimation_kind > HBK_SUBLIMATION_PET)
         return bail(HBK_E_ARG, "unknown sublimation_kind");
+    if (st->melt_kind < HBK_MELT_DEGREE_DAY || st->melt_kind > HBK_MELT_TEMPERATURE_INDEX)
+        return bail(HBK_E_ARG, "unknown melt_kind");
+    if (HBK_PAR_SHARED && st->melt_kind != HBK_MELT_DEGREE_DAY)
+        return bail(HBK_E_UNSUPPORTED, "this build (HBK_PAR_SHARED) only has melt:degree_day");
     if (st->has_glacier && st->snow_ice_kind == HBK_SNOW_ICE_SWAT) {
         // ProcessTransformSnowToIceSwat.cpp:31-39: 1 + sin(2 pi (doy - ref) / 365) per time step, in double like
         // the reference's expression (2.0f * constants::pi promotes to double), doy as TimeMachine.cpp:87-98
@@ -1390,7 +1449,7 @@ void hbk_engine_destroy(hbk_engine* e) {
     freeDev(e->dSwatFactor);
     freeDev(e->dFrac);
     freeDev(e->dFracInit);
-    for (int v = 0; v < 3; ++v) {
+    for (int v = 0; v < HBK_N_VARS; ++v) {
         freeDev(e->dForcingRaw[v]);
         freeDev(e->dForcingTiled[v]);
         freeDev(e->dStation[v]);
@@ -1458,8 +1517,9 @@ int hbk_set_units(hbk_engine* e, const double* area, const double* elevation, co
         // pow(_slope, 0.5) of ProcessRunoffSocont.cpp:51 with _slope float32, evaluated with the host libm
         hru[2 * e->ldu + u] = slope ? std::pow((double)slope[u], 0.5) : 0.0;
         hru[3 * e->ldu + u] = elevation ? elevation[u] : 0.0;
-        flags[u] = (glacier_variant && glacier_variant[u]) ? 1 : 0;
-        e->hGlacierVariant[u] = flags[u];
+        e->hGlacierVariant[u] = (glacier_variant && glacier_variant[u]) ? 1 : 0;
+        // bit 0: the unit carries the glacier bricks; bits 1-2: HBK_ASPECT_* (hbk_set_unit_aspect)
+        flags[u] = e->hGlacierVariant[u] | ((e->hAspect.empty() ? 0 : e->hAspect[u]) << 1);
         if (frac_ground) e->hFracG[u] = frac_ground[u];
         if (frac_glacier) e->hFracGl[u] = frac_glacier[u];
         // a structure without a glacier cover has the ground as its only land cover: the kernels fold its fraction (= 1)
@@ -1477,6 +1537,21 @@ int hbk_set_units(hbk_engine* e, const double* area, const double* elevation, co
     HBK_CUDA(cudaMemcpy(e->dFracInit, frac.data(), sizeof(double) * frac.size(), cudaMemcpyHostToDevice));
     HBK_CUDA(cudaMemcpy(e->dFrac, frac.data(), sizeof(double) * frac.size(), cudaMemcpyHostToDevice));
     e->unitsSet = true;
+    return HBK_OK;
+}
+
+int hbk_set_unit_aspect(hbk_engine* e, const int32_t* aspect_class) {
+    if (!e || !aspect_class) return HBK_E_ARG;
+    HBK_CUDA(cudaSetDevice(e->device));
+    for (int u = 0; u < e->U; ++u)
+        if (aspect_class[u] < HBK_ASPECT_NORTH || aspect_class[u] > HBK_ASPECT_EAST_WEST)
+            return fail(e, HBK_E_ARG, "Invalid aspect: the aspect class of a hydro unit is north, south or east/west "
+                                      "(ProcessMeltDegreeDayAspect.cpp:38-58)");
+    e->hAspect.assign(aspect_class, aspect_class + e->U);
+    std::vector<int> flags(e->ldu, 0);
+    for (int u = 0; u < e->U; ++u)
+        flags[u] = (e->hGlacierVariant.empty() ? 0 : e->hGlacierVariant[u]) | (e->hAspect[u] << 1);
+    HBK_CUDA(cudaMemcpy(e->dHruFlags, flags.data(), sizeof(int) * flags.size(), cudaMemcpyHostToDevice));
     return HBK_OK;
 }
 
@@ -1533,7 +1608,7 @@ int hbk_set_parameters(hbk_engine* e, int32_t n_sets, const float* values) {
 }
 
 int hbk_set_forcing(hbk_engine* e, int32_t var, const double* data) {
-    if (!e || var < 0 || var > 2 || !data) return HBK_E_ARG;
+    if (!e || var < 0 || var >= HBK_N_VARS || !data) return HBK_E_ARG;
     HBK_CUDA(cudaSetDevice(e->device));
     const size_t n = (size_t)e->T * e->U;
     if (!e->dForcingRaw[var]) HBK_CUDA(cudaMalloc(&e->dForcingRaw[var], sizeof(double) * n));
@@ -1547,7 +1622,7 @@ int hbk_set_forcing(hbk_engine* e, int32_t var, const double* data) {
 
 int hbk_set_station_forcing(hbk_engine* e, int32_t var, const double* series, double ref_elevation, double gradient,
                             const double* gradient_per_set, double correction, const double* correction_per_set) {
-    if (!e || var < 0 || var > 2 || !series) return HBK_E_ARG;
+    if (!e || var < 0 || var >= HBK_N_VARS || !series) return HBK_E_ARG;
     HBK_CUDA(cudaSetDevice(e->device));
     if ((gradient_per_set || correction_per_set) && e->P == 0)
         return fail(e, HBK_E_STATE, "set the parameters before per-set spatialisation gradients");
@@ -1579,7 +1654,7 @@ int hbk_set_station_forcing(hbk_engine* e, int32_t var, const double* series, do
     }
     if (rc) return rc;
     HBK_CUDA(cudaStreamSynchronize(e->stream));
-    if (var != HBK_VAR_PET) {
+    if (var == HBK_VAR_TEMPERATURE || var == HBK_VAR_PRECIPITATION) {
         // the station call of a variable replaces its per-set arrays: once both spatialised variables have been set
         // again after a change of n_sets nothing stale or missing is left
         e->perSetDroppedVars &= ~(1 << var);
@@ -1800,6 +1875,8 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
     a.flags.snowIceKind = e->st.has_glacier ? e->st.snow_ice_kind : 0;
     a.flags.sublimKind = e->st.sublimation_kind;
     a.flags.seqKind = e->st.solver >= HBK_SOLVER_CRANK_NICOLSON ? e->st.solver - HBK_SOLVER_CRANK_NICOLSON : 0;
+    a.flags.meltKind = e->st.melt_kind;
+    a.nVars = e->nVars();
     a.swatFactor = (a.flags.snowIceKind == HBK_SNOW_ICE_SWAT) ? e->dSwatFactor : nullptr;
     a.flags.noMeltWhenSnow = e->st.glacier_no_melt_when_snow_cover;
     a.dt = e->st.time_step_days;
@@ -1812,7 +1889,7 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
     a.fracPerSet = e->fracPerSet;
     a.fracLd = e->fracPerSet ? (long long)e->P * e->U : e->U;
     a.forcingMode = tiled ? 0 : 1;
-    for (int v = 0; v < 3; ++v) a.forcing[v] = tiled ? e->dForcingTiled[v] : e->dStation[v];
+    for (int v = 0; v < a.nVars; ++v) a.forcing[v] = tiled ? e->dForcingTiled[v] : e->dStation[v];
     a.tld = e->tld;
     a.gradT = e->dGradT;
     a.gradP = e->dGradP;
@@ -1841,7 +1918,8 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
     a.perm = e->dPerm;
     a.outQFinal = multi ? 0 : 1;
 
-    const bool ens = e->PB == 32 && e->UB == 4 && e->TC == HBK_ENS_TC && !tiled && !e->clusterMode && !std::getenv("HBK_NO_ENS_SHAPE");
+    const bool ens = e->PB == 32 && e->UB == 4 && e->TC == HBK_ENS_TC && !tiled && !e->clusterMode && a.nVars == 3 &&
+                     !std::getenv("HBK_NO_ENS_SHAPE");
     KernelFn fn = pickKernel(e->st, ens);
     const size_t smem = smemBytes(e, tiled);
     HBK_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1973,11 +2051,19 @@ int hbk_run(hbk_engine* e) {
     if (!e) return HBK_E_ARG;
     if (!e->unitsSet) return fail(e, HBK_E_STATE, "hbk_set_units has not been called");
     if (e->P <= 0) return fail(e, HBK_E_STATE, "hbk_set_parameters has not been called");
-    const bool tiled = e->haveRaw[0] && e->haveRaw[1] && e->haveRaw[2];
-    const bool station = e->haveStation[0] && e->haveStation[1] && e->haveStation[2];
+    bool tiled = true, station = true;
+    for (int v = 0; v < e->nVars(); ++v) {
+        tiled = tiled && e->haveRaw[v];
+        station = station && e->haveStation[v];
+    }
     if (!tiled && !station)
-        return fail(e, HBK_E_STATE, "forcing incomplete: precipitation, temperature and pet are all required, "
-                                    "either all per unit or all as station series");
+        return fail(e, HBK_E_STATE, e->nVars() == 4
+                        ? "forcing incomplete: precipitation, temperature, pet and solar_radiation (melt:temperature_index) "
+                          "are all required, either all per unit or all as station series"
+                        : "forcing incomplete: precipitation, temperature and pet are all required, "
+                          "either all per unit or all as station series");
+    if (e->st.melt_kind == HBK_MELT_DEGREE_DAY_ASPECT && e->hAspect.empty())
+        return fail(e, HBK_E_STATE, "melt:degree_day_aspect needs the aspect class of every hydro unit (hbk_set_unit_aspect)");
     if (station && e->perSetDropped)
         return fail(e, HBK_E_STATE, "per-set gradients / correction factors must be set again (hbk_set_station_forcing) "
                                     "after the number of parameter sets changed");
@@ -2024,7 +2110,7 @@ int hbk_run(hbk_engine* e) {
         e->recBytes = recBytes;
     }
     if (tiled && e->tiledUB != e->UB) {
-        for (int v = 0; v < 3; ++v) {
+        for (int v = 0; v < e->nVars(); ++v) {
             freeDev(e->dForcingTiled[v]);
             const size_t n = (size_t)e->nUTiles * e->tld * e->UB;
             HBK_CUDA(cudaMalloc(&e->dForcingTiled[v], sizeof(double) * n));

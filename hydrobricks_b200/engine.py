@@ -24,12 +24,18 @@ QUICK_SOCONT, QUICK_LINEAR = 0, 1
 SPLIT_LINEAR, SPLIT_THRESHOLD = 0, 1
 SNOW_ICE_NONE, SNOW_ICE_CONSTANT, SNOW_ICE_SWAT = 0, 1, 2
 SUBLIMATION_NONE, SUBLIMATION_CONSTANT, SUBLIMATION_PET = 0, 1, 2
-VAR = {"precipitation": 0, "p": 0, "temperature": 1, "t": 1, "pet": 2}
+MELT_DEGREE_DAY, MELT_DEGREE_DAY_ASPECT, MELT_TEMPERATURE_INDEX = 0, 1, 2
+MELT_KIND = {"melt:degree_day": 0, "melt:degree_day_aspect": 1, "melt:temperature_index": 2}
+# HydroUnit property "aspect_class" (ProcessMeltDegreeDayAspect.cpp:38-58) -> HBK_ASPECT_*
+ASPECT = {"north": 0, "N": 0, "south": 1, "S": 1, "east": 2, "west": 2, "E": 2, "W": 2}
+VAR = {"precipitation": 0, "p": 0, "temperature": 1, "t": 1, "pet": 2,
+       "solar_radiation": 3, "r_solar": 3, "r": 3}  # TimeSeries.cpp:134-146
 PARAM_SLOTS = [
     "transition_start", "transition_end", "rain_correction", "snow_correction", "ground_snow_ddf",
     "ground_snow_tmelt", "glacier_snow_ddf", "glacier_snow_tmelt", "ice_ddf", "ice_tmelt", "capacity", "k_slow_1",
     "percolation", "k_slow_2", "quick", "k_snow", "k_ice", "snow_ice",
     "ground_sublimation", "glacier_sublimation",
+    "ground_snow_melt_b", "ground_snow_melt_c", "glacier_snow_melt_b", "glacier_snow_melt_c", "ice_melt_b", "ice_melt_c",
 ]
 N_PARAMS = len(PARAM_SLOTS)
 RECORD_SLOTS = [
@@ -62,7 +68,7 @@ class HbkStructure(ctypes.Structure):
         ("north_hemisphere", ctypes.c_int32),
         ("start_mjd", ctypes.c_double),
         ("sublimation_kind", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("melt_kind", ctypes.c_int32),
     ]
 
 
@@ -92,6 +98,7 @@ def load_library():
     L.hbk_last_error.argtypes = [vp]
     L.hbk_last_error.restype = ctypes.c_char_p
     L.hbk_set_units.argtypes = [vp, dp, dp, fp, ip, dp, dp]
+    L.hbk_set_unit_aspect.argtypes = [vp, ip]
     L.hbk_set_parameters.argtypes = [vp, i32, fp]
     L.hbk_set_forcing.argtypes = [vp, i32, dp]
     L.hbk_set_station_forcing.argtypes = [vp, i32, dp, dbl, dbl, dp, dbl, dp]
@@ -200,6 +207,16 @@ class Engine:
             self.h, _dptr(area), _dptr(elevation),
             slope.ctypes.data_as(ctypes.POINTER(ctypes.c_float)) if slope is not None else None,
             gv.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)) if gv is not None else None, _dptr(fg), _dptr(fgl)))
+
+    def set_unit_aspect(self, aspect_classes):
+        """Aspect class per unit: HBK_ASPECT_* integers or the reference's strings (north|N|south|S|east|west|E|W)."""
+        try:
+            a = [ASPECT[x] if isinstance(x, str) else int(x) for x in aspect_classes]
+        except KeyError as err:
+            raise ValueError(f"Invalid aspect: {err.args[0]}") from None
+        a = np.ascontiguousarray(a, dtype=np.int32)
+        assert a.shape == (self.n_units,)
+        self._check(self.L.hbk_set_unit_aspect(self.h, a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
 
     def set_parameters(self, values):
         v = np.ascontiguousarray(values, dtype=np.float32)

@@ -7,8 +7,9 @@ core/tests/src/helpers.cpp:9-107) by the ROLE of each brick, not by its name:
 
   snow_rain_transition splitter (snow_rain:linear | snow_rain:threshold) -> rain / snow multi_fluxes splitters
   one generic land cover     {infiltration:socont -> S, outflow:rest -> Q}            (direct brick)
-  optional glacier land cover {outflow:direct -> B1 (instantaneous), melt:degree_day -> B2 (instantaneous)}
-  one snowpack per cover      {melt:degree_day -> cover}
+  optional glacier land cover {outflow:direct -> B1 (instantaneous), melt:<kind> -> B2 (instantaneous)}
+  one snowpack per cover      {melt:<kind> -> cover}      <kind> = degree_day | degree_day_aspect | temperature_index,
+                                                          the same on every snowpack and on the ice (socont.py:141)
   S  storage, capacity        {et:socont, outflow:linear -> outlet, overflow -> outlet, [percolation:constant -> S2]}
   S2 storage                  {outflow:linear -> outlet}
   Q  storage                  {runoff:socont -> outlet | outflow:linear -> outlet}
@@ -98,30 +99,51 @@ class CompiledStructure:
             raise UnsupportedStructure("sub-basin splitters")
         tr = [s for s in splitters.values() if s["kind"] in ("snow_rain:linear", "snow_rain:threshold")]
         multi = [s for s in splitters.values() if s["kind"] == "multi_fluxes"]
-        if len(tr) != 1 or len(multi) != 2 or len(splitters) != 3:
-            raise UnsupportedStructure("expected snow_rain_transition + rain/snow multi_fluxes splitters")
-        tr = tr[0]
-        sp = _params(tr)
-        if tr["kind"] == "snow_rain:linear":
-            st.splitter_kind = _e.SPLIT_LINEAR
-            self._set("transition_start", tr["name"], "transition_start", sp["transition_start"])
-            self._set("transition_end", tr["name"], "transition_end", sp["transition_end"])
-        else:
+        rain_only = [s for s in splitters.values() if s["kind"] == "rain"]
+        self.no_snow = len(rain_only) == 1 and not tr
+        if self.no_snow:
+            # SettingsModel::GeneratePrecipitationSplitters(withSnow = false) (SettingsModel.cpp:518-529): SplitterRain
+            # (SplitterRain.cpp:37-39) sends precipitation x rain_correction_factor to the land covers; no snowpacks.
+            # On the device this is the threshold splitter with a threshold no temperature reaches (-FLT_MAX): rain =
+            # precipitation x rcf, snow = 0, and the snowpack code only ever moves zeros.
+            if len(multi) != 1 or len(splitters) != 2:
+                raise UnsupportedStructure("expected the rain splitter + the rain multi_fluxes splitter")
+            tr = rain_only[0]
             st.splitter_kind = _e.SPLIT_THRESHOLD
-            self._set("transition_start", tr["name"], "threshold", sp["threshold"])
-        self._set("rain_correction", tr["name"], "rain_correction_factor", sp.get("rain_correction_factor", 1.0))
-        self._set("snow_correction", tr["name"], "snow_correction_factor", sp.get("snow_correction_factor", 1.0))
-        self.splitter_name = tr["name"]
-        rain_targets = snow_targets = None
-        for out in tr["outputs"]:
-            tgt = splitters.get(out["target"])
+            self.params[_e.PARAM_SLOTS.index("transition_start")] = -np.finfo(np.float32).max
+            self.params[_e.PARAM_SLOTS.index("snow_correction")] = 1.0
+            self._set("rain_correction", tr["name"], "rain_correction_factor",
+                      _params(tr).get("rain_correction_factor", 1.0))
+            self.splitter_name = tr["name"]
+            tgt = splitters.get(tr["outputs"][0]["target"]) if len(tr["outputs"]) == 1 else None
             if tgt is None or tgt["kind"] != "multi_fluxes":
-                raise UnsupportedStructure("snow_rain_transition must feed multi_fluxes splitters")
-            names = [o["target"] for o in tgt["outputs"]]
-            if out["flux_type"] == "snow":
-                snow_targets = names
+                raise UnsupportedStructure("the rain splitter must feed a multi_fluxes splitter")
+            rain_targets, snow_targets = [o["target"] for o in tgt["outputs"]], []
+        else:
+            if len(tr) != 1 or len(multi) != 2 or len(splitters) != 3:
+                raise UnsupportedStructure("expected snow_rain_transition + rain/snow multi_fluxes splitters")
+            tr = tr[0]
+            sp = _params(tr)
+            if tr["kind"] == "snow_rain:linear":
+                st.splitter_kind = _e.SPLIT_LINEAR
+                self._set("transition_start", tr["name"], "transition_start", sp["transition_start"])
+                self._set("transition_end", tr["name"], "transition_end", sp["transition_end"])
             else:
-                rain_targets = names
+                st.splitter_kind = _e.SPLIT_THRESHOLD
+                self._set("transition_start", tr["name"], "threshold", sp["threshold"])
+            self._set("rain_correction", tr["name"], "rain_correction_factor", sp.get("rain_correction_factor", 1.0))
+            self._set("snow_correction", tr["name"], "snow_correction_factor", sp.get("snow_correction_factor", 1.0))
+            self.splitter_name = tr["name"]
+            rain_targets = snow_targets = None
+            for out in tr["outputs"]:
+                tgt = splitters.get(out["target"])
+                if tgt is None or tgt["kind"] != "multi_fluxes":
+                    raise UnsupportedStructure("snow_rain_transition must feed multi_fluxes splitters")
+                names = [o["target"] for o in tgt["outputs"]]
+                if out["flux_type"] == "snow":
+                    snow_targets = names
+                else:
+                    rain_targets = names
 
         # --- land covers
         covers = [b for b in full["hydro_unit_bricks"] if b["is_land_cover"]]
@@ -152,12 +174,38 @@ class CompiledStructure:
                          "transform:snow_ice_swat": _e.SNOW_ICE_SWAT, "transformation:snow_ice_swat": _e.SNOW_ICE_SWAT}
 
         sublim_kinds = {"sublimation:constant": _e.SUBLIMATION_CONSTANT, "sublimation:pet": _e.SUBLIMATION_PET}
+        st.melt_kind = -1
+
+        def set_melt(component, proc, slot_a, slot_tm, slot_b, slot_c):
+            """The melt process of a snowpack or of the glacier ice: its kind (one per structure) and its parameters —
+            degree_day_factor | degree_day_factor_n, _s, _ew (or _we, ProcessMeltDegreeDayAspect.cpp:48-55) |
+            melt_factor, radiation_coefficient."""
+            kind = _e.MELT_KIND.get(proc["kind"])
+            if kind is None:
+                raise UnsupportedStructure(f"{component}: melt process {proc['kind']}")
+            if st.melt_kind not in (-1, kind):
+                raise UnsupportedStructure("different melt processes on the snowpacks / the glacier ice")
+            st.melt_kind = kind
+            pp = _params(proc)
+            self._set(slot_tm, component, "melting_temperature", pp["melting_temperature"])
+            if kind == _e.MELT_DEGREE_DAY:
+                self._set(slot_a, component, "degree_day_factor", pp["degree_day_factor"])
+            elif kind == _e.MELT_DEGREE_DAY_ASPECT:
+                self._set(slot_a, component, "degree_day_factor_n", pp["degree_day_factor_n"])
+                self._set(slot_b, component, "degree_day_factor_s", pp["degree_day_factor_s"])
+                ew = "degree_day_factor_ew" if "degree_day_factor_ew" in pp else "degree_day_factor_we"
+                if ew not in pp:
+                    raise UnsupportedStructure("Missing parameter 'degree_day_factor_ew' or 'degree_day_factor_we'")
+                self._set(slot_c, component, ew, pp[ew])
+            else:
+                self._set(slot_a, component, "melt_factor", pp["melt_factor"])
+                self._set(slot_b, component, "radiation_coefficient", pp["radiation_coefficient"])
 
         def snowpack_of(cover):
             """One snowpack per cover: melt:degree_day [, snow -> ice transformation on a glacier] [, sublimation], in
             the order model_settings.py:255-263 adds them. Returns (brick, transformation process, sublimation process)."""
             sps = [b for b in full["hydro_unit_bricks"] if b["kind"] == "snowpack" and b.get("parent") == cover["name"]]
-            ok = len(sps) == 1 and sps[0]["processes"] and sps[0]["processes"][0]["kind"] == "melt:degree_day" and \
+            ok = len(sps) == 1 and sps[0]["processes"] and sps[0]["processes"][0]["kind"] in _e.MELT_KIND and \
                 _target(sps[0]["processes"][0]) == cover["name"]
             transfo = sublim = None
             if ok:
@@ -175,7 +223,7 @@ class CompiledStructure:
                 ok = ok and not rest
             if not ok:
                 raise UnsupportedStructure(f"cover {cover['name']}: expected one snowpack with melt:degree_day"
-                                           " [+ transform:snow_ice_constant|swat on a glacier] [+ sublimation:constant|pet]")
+                                           "|degree_day_aspect|temperature_index [+ transform:snow_ice_constant|swat on a glacier] [+ sublimation:constant|pet]")
             return sps[0], transfo, sublim
 
         def set_sublimation(sp, proc, slot, record):
@@ -187,24 +235,28 @@ class CompiledStructure:
             self._set(slot, sp["name"], pname, _params(proc)[pname])
             self.labels[f"{sp['name']}:{proc['name']}:output"] = record
 
-        gsp, _, gsub = snowpack_of(ground)
-        if gsub is not None:
-            set_sublimation(gsp, gsub, "ground_sublimation", "ground_snowpack_sublimation")
-        pp = _params(gsp["processes"][0])
-        self._set("ground_snow_ddf", gsp["name"], "degree_day_factor", pp["degree_day_factor"])
-        self._set("ground_snow_tmelt", gsp["name"], "melting_temperature", pp["melting_temperature"])
-        self.labels.update({f"{gsp['name']}:water_content": "ground_snowpack_water",
-                            f"{gsp['name']}:snow_content": "ground_snowpack_snow",
-                            f"{gsp['name']}:{gsp['processes'][0]['name']}:output": "ground_snowpack_melt"})
-        snowpacks = [gsp["name"]]
+        gsp = gsub = None
+        snowpacks = []
+        if not self.no_snow:
+            gsp, _, gsub = snowpack_of(ground)
+            if gsub is not None:
+                set_sublimation(gsp, gsub, "ground_sublimation", "ground_snowpack_sublimation")
+            set_melt(gsp["name"], gsp["processes"][0], "ground_snow_ddf", "ground_snow_tmelt", "ground_snow_melt_b",
+                     "ground_snow_melt_c")
+            self.labels.update({f"{gsp['name']}:water_content": "ground_snowpack_water",
+                                f"{gsp['name']}:snow_content": "ground_snowpack_snow",
+                                f"{gsp['name']}:{gsp['processes'][0]['name']}:output": "ground_snowpack_melt"})
+            snowpacks = [gsp["name"]]
 
         # --- glacier
         st.has_glacier = 0
         b1 = b2 = None
         if glacier is not None:
             st.has_glacier = 1
-            if _proc_kinds(glacier) != ["outflow:direct", "melt:degree_day"]:
-                raise UnsupportedStructure("glacier cover: expected outflow:direct + melt:degree_day")
+            gk = _proc_kinds(glacier)
+            if len(gk) != 2 or gk[0] != "outflow:direct" or gk[1] not in _e.MELT_KIND:
+                raise UnsupportedStructure("glacier cover: expected outflow:direct + melt:degree_day|degree_day_aspect|"
+                                           "temperature_index")
             for proc in glacier["processes"]:
                 if not proc["outputs"][0]["instantaneous"]:
                     raise UnsupportedStructure("glacier outputs must be instantaneous")
@@ -212,37 +264,38 @@ class CompiledStructure:
             gp = _params(glacier)
             st.glacier_infinite_storage = int("infinite_storage" in gp and abs(float(gp["infinite_storage"])) > np.finfo(np.float32).eps)
             st.glacier_no_melt_when_snow_cover = int("no_melt_when_snow_cover" in gp and float(gp["no_melt_when_snow_cover"]) > 0)
-            mp = _params(glacier["processes"][1])
-            self._set("ice_ddf", glacier["name"], "degree_day_factor", mp["degree_day_factor"])
-            self._set("ice_tmelt", glacier["name"], "melting_temperature", mp["melting_temperature"])
-            glsp, gltr, glsub = snowpack_of(glacier)
-            if (glsub is None) != (gsub is None):
-                raise UnsupportedStructure("sublimation must be on every snowpack or on none")
-            if glsub is not None:
-                set_sublimation(glsp, glsub, "glacier_sublimation", "glacier_snowpack_sublimation")
-            pp = _params(glsp["processes"][0])
-            self._set("glacier_snow_ddf", glsp["name"], "degree_day_factor", pp["degree_day_factor"])
-            self._set("glacier_snow_tmelt", glsp["name"], "melting_temperature", pp["melting_temperature"])
+            set_melt(glacier["name"], glacier["processes"][1], "ice_ddf", "ice_tmelt", "ice_melt_b", "ice_melt_c")
             n = glacier["name"]
             self.labels.update({f"{n}:water_content": "glacier_water", f"{n}:ice_content": "glacier_ice",
                                 f"{n}:{glacier['processes'][0]['name']}:output": "glacier_outflow",
-                                f"{n}:{glacier['processes'][1]['name']}:output": "glacier_melt",
-                                f"{glsp['name']}:water_content": "glacier_snowpack_water",
-                                f"{glsp['name']}:snow_content": "glacier_snowpack_snow",
-                                f"{glsp['name']}:{glsp['processes'][0]['name']}:output": "glacier_snowpack_melt"})
-            snowpacks.append(glsp["name"])
-            if gltr is not None:
-                tp = gltr
-                st.snow_ice_kind = transfo_kinds[tp["kind"]]
-                tv = _params(tp)
-                if st.snow_ice_kind == _e.SNOW_ICE_CONSTANT:
-                    pname = "snow_ice_transformation_rate" if "snow_ice_transformation_rate" in tv else "rate"
-                else:
-                    pname = "snow_ice_transformation_basal_acc_coeff" \
-                        if "snow_ice_transformation_basal_acc_coeff" in tv else "basal_acc_coeff"
-                    st.north_hemisphere = int(not (float(tv.get("north_hemisphere", 1)) == 0))
-                self._set("snow_ice", glsp["name"], pname, tv[pname])
-                self.labels[f"{glsp['name']}:{tp['name']}:output"] = "glacier_snowpack_transfo"
+                                f"{n}:{glacier['processes'][1]['name']}:output": "glacier_melt"})
+            if self.no_snow:
+                if st.glacier_no_melt_when_snow_cover:  # IceContainer.cpp:10-32 needs the related snowpack
+                    raise UnsupportedStructure("No snowpack provided for the glacier melt limitation.")
+            else:
+                glsp, gltr, glsub = snowpack_of(glacier)
+                if (glsub is None) != (gsub is None):
+                    raise UnsupportedStructure("sublimation must be on every snowpack or on none")
+                if glsub is not None:
+                    set_sublimation(glsp, glsub, "glacier_sublimation", "glacier_snowpack_sublimation")
+                set_melt(glsp["name"], glsp["processes"][0], "glacier_snow_ddf", "glacier_snow_tmelt",
+                         "glacier_snow_melt_b", "glacier_snow_melt_c")
+                self.labels.update({f"{glsp['name']}:water_content": "glacier_snowpack_water",
+                                    f"{glsp['name']}:snow_content": "glacier_snowpack_snow",
+                                    f"{glsp['name']}:{glsp['processes'][0]['name']}:output": "glacier_snowpack_melt"})
+                snowpacks.append(glsp["name"])
+                if gltr is not None:
+                    tp = gltr
+                    st.snow_ice_kind = transfo_kinds[tp["kind"]]
+                    tv = _params(tp)
+                    if st.snow_ice_kind == _e.SNOW_ICE_CONSTANT:
+                        pname = "snow_ice_transformation_rate" if "snow_ice_transformation_rate" in tv else "rate"
+                    else:
+                        pname = "snow_ice_transformation_basal_acc_coeff" \
+                            if "snow_ice_transformation_basal_acc_coeff" in tv else "basal_acc_coeff"
+                        st.north_hemisphere = int(not (float(tv.get("north_hemisphere", 1)) == 0))
+                    self._set("snow_ice", glsp["name"], pname, tv[pname])
+                    self.labels[f"{glsp['name']}:{tp['name']}:output"] = "glacier_snowpack_transfo"
             for name, slot in ((b1, "k_snow"), (b2, "k_ice")):
                 bb = basin_bricks.get(name)
                 if bb is None or bb["kind"] != "storage" or _proc_kinds(bb) != ["outflow:linear"] or \
@@ -320,9 +373,9 @@ class CompiledStructure:
         self.labels[f"{quick_name}:water_content"] = "quick_water"
         self.labels[f"{quick_name}:{qp['name']}:output"] = "quick_runoff"
 
-        known = {self.ground_name, gsp["name"], slow_name, quick_name}
+        known = {self.ground_name, slow_name, quick_name} | set(snowpacks)
         if glacier is not None:
-            known |= {glacier["name"], snowpacks[1]}
+            known.add(glacier["name"])
         if slow2_name:
             known.add(slow2_name)
         extra = set(bricks) - known
@@ -332,6 +385,8 @@ class CompiledStructure:
             if b.get("forcing"):
                 raise UnsupportedStructure("brick-level forcing")
         self.names = {"slow": slow_name, "slow2": slow2_name, "quick": quick_name}
+        if st.melt_kind < 0:
+            st.melt_kind = _e.MELT_DEGREE_DAY
         self.hbk = st
 
     # ------------------------------------------------------------------------------------------------
@@ -412,4 +467,6 @@ def build_engine(structures, units, solver, n_steps, device=0, time_step_days=1.
     fg = [dict(c).get(cs.ground_name, 1.0) for c in covers]
     fgl = [dict(c).get(cs.glacier_name, 0.0) if cs.glacier_name else 0.0 for c in covers]
     eng.set_units(area, elev, slope, gv, fg, fgl)
+    if cs.hbk.melt_kind == _e.MELT_DEGREE_DAY_ASPECT:
+        eng.set_unit_aspect([u.get("aspect_class") or u.get("properties", {}).get("aspect_class") for u in units])
     return cs, eng

@@ -39,14 +39,23 @@ enum { HBK_SPLIT_LINEAR = 0, HBK_SPLIT_THRESHOLD = 1 };
 /* order of the slow_reservoir processes = rate-vector layout (Processor.cpp:146-172) */
 enum { HBK_SLOW_ORDER_ET_OUT_OVF_PERC = 0 /* models/socont.py:171-190 */,
        HBK_SLOW_ORDER_ET_OUT_PERC_OVF = 1 /* core/tests/src/helpers.cpp:74-86 */ };
-enum { HBK_VAR_PRECIPITATION = 0, HBK_VAR_TEMPERATURE = 1, HBK_VAR_PET = 2 };
+/* forcing variables (TimeSeries.cpp:134-146); solar radiation only feeds melt:temperature_index */
+enum { HBK_VAR_PRECIPITATION = 0, HBK_VAR_TEMPERATURE = 1, HBK_VAR_PET = 2, HBK_VAR_SOLAR_RADIATION = 3, HBK_N_VARS = 4 };
 /* glacier snowpack process after the melt: none | transform:snow_ice_constant | transform:snow_ice_swat */
 enum { HBK_SNOW_ICE_NONE = 0, HBK_SNOW_ICE_CONSTANT = 1, HBK_SNOW_ICE_SWAT = 2 };
 /* snowpack -> atmosphere: none | sublimation:constant | sublimation:pet (ProcessSublimation{Constant,PET}.cpp) */
 enum { HBK_SUBLIMATION_NONE = 0, HBK_SUBLIMATION_CONSTANT = 1, HBK_SUBLIMATION_PET = 2 };
+/* melt process of every snowpack and of the glacier ice (the reference's Socont option snow_melt_process,
+ * models/socont.py:68,141 -> modules/glacier.py:87-131): melt:degree_day (ProcessMeltDegreeDay.cpp:49-60) |
+ * melt:degree_day_aspect (ProcessMeltDegreeDayAspect.cpp:38-80: the degree-day factor of the unit's aspect class) |
+ * melt:temperature_index (ProcessMeltTemperatureIndex.cpp:62-74: factor = melt_factor + radiation_coefficient x solar
+ * radiation, a fourth forcing series) */
+enum { HBK_MELT_DEGREE_DAY = 0, HBK_MELT_DEGREE_DAY_ASPECT = 1, HBK_MELT_TEMPERATURE_INDEX = 2 };
+/* aspect class of a hydro unit (HydroUnit::GetPropertyString("aspect_class")): north|N, south|S, east|west|E|W */
+enum { HBK_ASPECT_NORTH = 0, HBK_ASPECT_SOUTH = 1, HBK_ASPECT_EAST_WEST = 2 };
 
 /* The per-structure process table for the Socont family, as the structure compiler
- * (hydrobricks_b200/csrc/hb_host.cpp) derives it from a SettingsModel. */
+ * (hydrobricks_b200/csrc/hb_host.hpp, hb::Compiled) derives it from a SettingsModel. */
 typedef struct {
     int32_t solver;
     int32_t n_soil_stores;            /* 1 | 2 (slow_reservoir [+ percolation -> slow_reservoir_2]) */
@@ -66,7 +75,7 @@ typedef struct {
     /* snow sublimation, last process of every snowpack (SettingsModel::AddSnowpackSublimation,
      * SettingsModel.cpp:586-598): HBK_SUBLIMATION_* */
     int32_t sublimation_kind;
-    int32_t reserved;
+    int32_t melt_kind;                /* HBK_MELT_*, the same process on every snowpack and on the glacier ice */
 } hbk_structure;
 
 /* Parameter slots of one parameter set: float32 like the reference (Parameter.h:121). */
@@ -75,7 +84,7 @@ enum {
     HBK_P_TRANSITION_END,
     HBK_P_RAIN_CORRECTION,
     HBK_P_SNOW_CORRECTION,
-    HBK_P_GROUND_SNOW_DDF, /* <cover>_snowpack:degree_day_factor */
+    HBK_P_GROUND_SNOW_DDF, /* <cover>_snowpack:degree_day_factor | :degree_day_factor_n | :melt_factor (HBK_MELT_*) */
     HBK_P_GROUND_SNOW_TMELT,
     HBK_P_GLACIER_SNOW_DDF,
     HBK_P_GLACIER_SNOW_TMELT,
@@ -91,6 +100,11 @@ enum {
     HBK_P_SNOW_ICE,   /* glacier_snowpack:snow_ice_transformation_rate or :snow_ice_transformation_basal_acc_coeff */
     HBK_P_GROUND_SUBLIMATION,  /* <cover>_snowpack:sublimation_rate or :sublimation_pet_factor */
     HBK_P_GLACIER_SUBLIMATION,
+    /* second and third parameter of the three melt processes: degree_day_factor_s and degree_day_factor_ew|_we
+     * (melt:degree_day_aspect) or radiation_coefficient and nothing (melt:temperature_index); unused by melt:degree_day */
+    HBK_P_GROUND_SNOW_MELT_B, HBK_P_GROUND_SNOW_MELT_C,
+    HBK_P_GLACIER_SNOW_MELT_B, HBK_P_GLACIER_SNOW_MELT_C,
+    HBK_P_ICE_MELT_B, HBK_P_ICE_MELT_C,
     HBK_N_PARAMS
 };
 
@@ -132,17 +146,23 @@ const char* hbk_last_error(const hbk_engine* e);
 int hbk_set_units(hbk_engine* e, const double* area_m2, const double* elevation_m, const float* slope_m_per_m,
                   const int32_t* glacier_variant, const double* fraction_ground, const double* fraction_glacier);
 
+/* Aspect class of every unit, HBK_ASPECT_* (HydroUnit property "aspect_class", read by
+ * ProcessMeltDegreeDayAspect::SetHydroUnitProperties, ProcessMeltDegreeDayAspect.cpp:35-37); required before hbk_run
+ * when melt_kind is HBK_MELT_DEGREE_DAY_ASPECT. */
+int hbk_set_unit_aspect(hbk_engine* e, const int32_t* aspect_class);
+
 /* SettingsModel::SetParameterValue + ModelHydro::UpdateParameters (ModelHydro.cpp:76-84), batched:
  * values[n_sets][HBK_N_PARAMS] float32. */
 int hbk_set_parameters(hbk_engine* e, int32_t n_sets, const float* values);
 
 /* ModelHydro::CreateTimeSeries + AttachTimeSeriesToHydroUnits (ModelHydro.cpp:306-346):
- * data[n_steps][n_units] float64, columns in basin order, shared by all parameter sets. */
+ * data[n_steps][n_units] float64, columns in basin order, shared by all parameter sets. variable = HBK_VAR_*;
+ * solar radiation is required iff melt_kind is HBK_MELT_TEMPERATURE_INDEX. */
 int hbk_set_forcing(hbk_engine* e, int32_t variable, const double* data);
 
 /* Fused forcing spatialisation (python forcing.py:1061-1113): station series[n_steps]; per unit
  *   temperature: x + g*(z - z_ref)/100;  precipitation: max(0, (x*corr) * (1 + g*(z - z_ref)/100));
- *   pet: x.   gradient / correction may be per parameter set ([n_sets], NULL -> scalar). */
+ *   pet, solar radiation: x.   gradient / correction may be per parameter set ([n_sets], NULL -> scalar). */
 int hbk_set_station_forcing(hbk_engine* e, int32_t variable, const double* series, double ref_elevation,
                             double gradient, const double* gradient_per_set, double correction,
                             const double* correction_per_set);

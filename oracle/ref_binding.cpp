@@ -96,6 +96,9 @@ py::list ForcingList(const vector<VariableType>& forcing) {
             case VariableType::Precipitation: l.append("precipitation"); break;
             case VariableType::Temperature: l.append("temperature"); break;
             case VariableType::PET: l.append("pet"); break;
+            case VariableType::TemperatureMin: l.append("temperature_min"); break;
+            case VariableType::TemperatureMax: l.append("temperature_max"); break;
+            case VariableType::Radiation: l.append("solar_radiation"); break;  // names of Binding.cpp:30-52
             default: l.append(static_cast<int>(f)); break;
         }
     }

@@ -54,12 +54,17 @@ def settings_from_structures(hb, meta, n_steps, solver=None):
     for i, st in enumerate(meta["structures"]):
         if i > 0:
             s.add_structure()
-        tr = next(x for x in st["hydro_unit_splitters"] if x["name"] == "snow_rain_transition")
-        s.generate_precipitation_splitters(True, tr["kind"])
+        tr = next((x for x in st["hydro_unit_splitters"] if x["name"] == "snow_rain_transition"), None)
+        if tr is None:  # SettingsModel::GeneratePrecipitationSplitters(withSnow = false): the rain splitter only
+            s.generate_precipitation_splitters(False)
+        else:
+            s.generate_precipitation_splitters(True, tr["kind"])
         for b in st["hydro_unit_bricks"]:
             if b["is_land_cover"]:
                 s.add_land_cover_brick(b["name"], b["kind"])
-        s.generate_snowpacks("melt:degree_day")
+        if tr is not None:
+            s.generate_snowpacks(next(b["processes"][0]["kind"] for b in st["hydro_unit_bricks"]
+                                      if b["is_surface_component"]))
         extras = {}  # AddSnowIceTransformation / AddSnowpackSublimation, in the order of model_settings.py:258-263
         for b in st["hydro_unit_bricks"]:
             if b["is_surface_component"]:

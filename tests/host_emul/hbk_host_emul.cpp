@@ -18,7 +18,7 @@ template <int SOLVER, int NSOIL, bool GLACIER>
 int runSet(const hbk_structure& st, int U, int T, const double* area, const float* slope, const int32_t* glacierVariant,
            const double* fracG, const double* fracGl, const float* pp, const double* precip, const double* temp,
            const double* pet, const double* swat, double* outlet, double* recSlow, double* recSnowG, double* recIce,
-           long long* unconvergedOut, const double* ddfUnit, const double* radiation, const double* radCoef) {
+           long long* unconvergedOut, const int32_t* aspect, const double* radiation) {
     Flags f{};
     f.quickKind = st.quick_kind;
     f.slowOrder = st.slow_process_order;
@@ -69,27 +69,26 @@ int runSet(const hbk_structure& st, int U, int T, const double* area, const floa
         par.quickV = (f.quickKind == 0) ? quickBase * slopeTerm / area[u] * socontUnit : quickBase;
         const bool gv = GLACIER && glacierVariant && glacierVariant[u];
         const double fG = fracG ? fracG[u] : 1.0, fGl = fracGl ? fracGl[u] : 0.0;
-        // Melt-process variants as GLUE around unchanged step functions (prototype of the engine's next step):
-        //  melt:degree_day_aspect  -> the degree-day factor is per (set, unit): ddfUnit[3][U] (ground snowpack, glacier
-        //                             snowpack, glacier ice) replaces the three per-set factors when the unit is loaded;
+        // Melt-process variants: the glue of hbkRunUnits (hbk_engine.cu loadUnit / time loop) around the unchanged step
+        // functions.
+        //  melt:degree_day_aspect  -> the degree-day factors of the unit's aspect class (slots DDF | MELT_B | MELT_C)
+        //                             replace the three per-set factors when the unit is loaded;
         //  melt:temperature_index  -> per step, factor = melt_factor + radiation_coefficient * solar radiation
-        //                             (ProcessMeltTemperatureIndex.cpp:68-71): ddfUnit holds the melt factors,
-        //                             radCoef[3] the coefficients, radiation[T][U] the fourth forcing series.
-        double ddf0[3] = {par.v[5], par.v[7], par.v[9]};
-        if (ddfUnit) {
-            for (int k = 0; k < 3; ++k) ddf0[k] = ddfUnit[(size_t)k * U + u];
+        //                             (ProcessMeltTemperatureIndex.cpp:68-71), radiation[T][U] the fourth forcing series.
+        if (st.melt_kind == HBK_MELT_DEGREE_DAY_ASPECT) {
+            const int a = aspect[u];
+            par.v[5] = pp[a == 0 ? HBK_P_GROUND_SNOW_DDF : (a == 1 ? HBK_P_GROUND_SNOW_MELT_B : HBK_P_GROUND_SNOW_MELT_C)];
+            par.v[7] = pp[a == 0 ? HBK_P_GLACIER_SNOW_DDF : (a == 1 ? HBK_P_GLACIER_SNOW_MELT_B : HBK_P_GLACIER_SNOW_MELT_C)];
+            par.v[9] = pp[a == 0 ? HBK_P_ICE_DDF : (a == 1 ? HBK_P_ICE_MELT_B : HBK_P_ICE_MELT_C)];
         }
-        par.v[5] = ddf0[0];
-        par.v[7] = ddf0[1];
-        par.v[9] = ddf0[2];
         for (int t = 0; t < T; ++t) {
             StepOut o{};
             const double p = precip[(size_t)t * U + u], tt = temp[(size_t)t * U + u], e = pet[(size_t)t * U + u];
-            if (radiation) {
+            if (st.melt_kind == HBK_MELT_TEMPERATURE_INDEX) {
                 const double rad = radiation[(size_t)t * U + u];
-                par.v[5] = ddf0[0] + radCoef[0] * rad;
-                par.v[7] = ddf0[1] + radCoef[1] * rad;
-                par.v[9] = ddf0[2] + radCoef[2] * rad;
+                par.v[5] = (double)pp[HBK_P_GROUND_SNOW_DDF] + (double)pp[HBK_P_GROUND_SNOW_MELT_B] * rad;
+                par.v[7] = (double)pp[HBK_P_GLACIER_SNOW_DDF] + (double)pp[HBK_P_GLACIER_SNOW_MELT_B] * rad;
+                par.v[9] = (double)pp[HBK_P_ICE_DDF] + (double)pp[HBK_P_ICE_MELT_B] * rad;
             }
             double sublimG = 0.0, sublimGl = 0.0;
             if (f.sublimKind != 0) {
@@ -129,17 +128,16 @@ int runSet(const hbk_structure& st, int U, int T, const double* area, const floa
 
 #define HBK_EMUL_ARGS                                                                                               \
     *st, n_units, n_steps, area, slope, glacier_variant, frac_ground, frac_glacier, params, precip, temp, pet, swat, \
-        outlet, rec_slow, rec_snow_ground, rec_ice, unconverged, g_ddfUnit, g_radiation, g_radCoef
+        outlet, rec_slow, rec_snow_ground, rec_ice, unconverged, g_aspect, g_radiation
 
-// optional melt-variant glue of the next call (hbk_emul_set_melt_glue); reset after every run
-static const double* g_ddfUnit = nullptr;
+// melt-variant inputs of the next call (hbk_emul_set_melt_inputs): HBK_ASPECT_* per unit (melt:degree_day_aspect) and
+// the solar radiation [n_steps][n_units] (melt:temperature_index); reset after every run
+static const int32_t* g_aspect = nullptr;
 static const double* g_radiation = nullptr;
-static const double* g_radCoef = nullptr;
 
-extern "C" void hbk_emul_set_melt_glue(const double* ddf_unit, const double* radiation, const double* rad_coef) {
-    g_ddfUnit = ddf_unit;
+extern "C" void hbk_emul_set_melt_inputs(const int32_t* aspect, const double* radiation) {
+    g_aspect = aspect;
     g_radiation = radiation;
-    g_radCoef = rad_coef;
 }
 
 template <int SOLVER, int NSOIL>
@@ -172,6 +170,6 @@ extern "C" int hbk_emul_run(const hbk_structure* st, int n_units, int n_steps, c
         case HBK_SOLVER_RK4: rc = HBK_EMUL_SOIL(2); break;
         default: rc = HBK_EMUL_SOIL(3); break;
     }
-    hbk_emul_set_melt_glue(nullptr, nullptr, nullptr);
+    hbk_emul_set_melt_inputs(nullptr, nullptr);
     return rc;
 }

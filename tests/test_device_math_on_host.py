@@ -20,7 +20,7 @@ HERE = Path(__file__).resolve().parent
 ROOT = HERE.parent
 EMUL = HERE / "host_emul"
 RTOL, ATOL = 1e-10, 1e-12
-CASES = [b for b in gu.bundles() if not b.startswith(("c1_", "kat_linear", "actions_"))]
+CASES = [b for b in gu.bundles() if not b.startswith(("c1_", "kat_linear", "actions_", "melt_"))]
 
 
 def build_emul(name="libhbkemul.so", defines=()):
@@ -149,55 +149,30 @@ def test_device_arithmetic_on_host_two_day_step(solver, emul):
     _close(rec["slow"], om.records["slow_reservoir:water_content"])
 
 
-NEXT_CASES = sorted("next/" + p.stem for p in (gu.GOLDEN / "next").glob("melt_*.npz"))
+MELT_CASES = sorted(p.stem for p in gu.GOLDEN.glob("melt_*.npz"))
 
 
-@pytest.mark.parametrize("name", NEXT_CASES)
-def test_melt_variants_need_only_glue_around_the_step_functions(name, emul):
-    """melt:degree_day_aspect and melt:temperature_index (not in the engine yet) on the UNCHANGED device step functions:
-    the degree-day factor handed to them becomes per (set, unit) — the factor of the unit's aspect class — or per step
-    — melt_factor + radiation_coefficient x solar radiation. With that glue (prototyped in tests/host_emul) the
-    arithmetic reproduces the reference's goldens at the parity bar, so the engine's next step is kernel glue, a fourth
-    forcing stream and six parameter slots, not new arithmetic."""
-    import copy
+@pytest.mark.parametrize("name", MELT_CASES)
+def test_melt_variants_on_host(name, emul):
+    """melt:degree_day_aspect and melt:temperature_index: the structure compiler's parameter slots (degree_day_factor_n /
+    _s / _ew resp. melt_factor / radiation_coefficient) + the kernel glue restated in tests/host_emul — the factor of the
+    unit's aspect class picked when the unit is loaded, resp. melt_factor + radiation_coefficient x solar radiation per
+    step — around the unchanged device step functions, against the reference's goldens."""
+    from hydrobricks_b200 import engine as _e
 
     meta, forcing, outlet, records, _ = gu.load(name)
-    units = meta["units"]
-    U = len(units)
-    aspect_param = {"north": "degree_day_factor_n", "N": "degree_day_factor_n", "south": "degree_day_factor_s",
-                    "S": "degree_day_factor_s", "east": "degree_day_factor_ew", "west": "degree_day_factor_ew",
-                    "E": "degree_day_factor_ew", "W": "degree_day_factor_ew"}
-    # the equivalent degree-day structure (what the structure compiler will derive) + the glue arrays
-    plain = copy.deepcopy(meta)
-    ddf_unit = np.zeros((3, U))
-    rad_coef = np.zeros(3)
-    rows = {"ground_snowpack": 0, "glacier_snowpack": 1, "glacier": 2}
-    tindex = False
-    for st in plain["structures"]:
-        for b in st["hydro_unit_bricks"]:
-            for proc in b["processes"]:
-                if proc["kind"] not in ("melt:degree_day_aspect", "melt:temperature_index"):
-                    continue
-                pp = {p["name"]: float(np.float32(p["value"])) for p in proc["parameters"]}
-                row = rows[b["name"]]
-                if proc["kind"] == "melt:degree_day_aspect":
-                    ddf_unit[row] = [pp[aspect_param[u["aspect_class"]]] for u in units]
-                else:
-                    tindex = True
-                    ddf_unit[row] = pp["melt_factor"]
-                    rad_coef[row] = pp["radiation_coefficient"]
-                proc["kind"] = "melt:degree_day"
-                proc["parameters"] = [{"name": "degree_day_factor", "value": 3.0},
-                                      {"name": "melting_temperature", "value": pp["melting_temperature"]}]
-                proc["forcing"] = ["temperature"]
-    radiation = np.ascontiguousarray(forcing.pop("solar_radiation")) if tindex else None
-    dp = ctypes.POINTER(ctypes.c_double)
-    emul.hbk_emul_set_melt_glue.argtypes = [dp, dp, dp]
-    emul.hbk_emul_set_melt_glue.restype = None
-    ddf_unit = np.ascontiguousarray(ddf_unit)
-    emul.hbk_emul_set_melt_glue(ddf_unit.ctypes.data_as(dp), radiation.ctypes.data_as(dp) if tindex else None,
-                                rad_coef.ctypes.data_as(dp) if tindex else None)
-    cs, q, rec, _ = run_emul(emul, plain, forcing)
+    forcing = dict(forcing)
+    radiation = forcing.pop("solar_radiation", None)
+    aspect = np.array([_e.ASPECT[u["aspect_class"]] for u in meta["units"]], dtype=np.int32)
+    if radiation is not None:
+        radiation = np.ascontiguousarray(radiation, dtype=np.float64)
+    emul.hbk_emul_set_melt_inputs.argtypes = [ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double)]
+    emul.hbk_emul_set_melt_inputs.restype = None
+    emul.hbk_emul_set_melt_inputs(aspect.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                  radiation.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+                                  if radiation is not None else None)
+    cs, q, rec, _ = run_emul(emul, meta, forcing)
+    assert cs.hbk.melt_kind == (_e.MELT_TEMPERATURE_INDEX if radiation is not None else _e.MELT_DEGREE_DAY_ASPECT)
     _close(q, outlet)
     _close(rec["slow"], records["slow_reservoir:water_content"])
     _close(rec["snow"], records[f"{cs.ground_name}_snowpack:snow_content"])
@@ -232,8 +207,7 @@ def test_default_arithmetic_is_bit_identical_to_the_faithful_build(emul, emul_fa
             assert np.array_equal(ra[k], rb[k], equal_nan=True), (name, k)
 
 
-PENDING_GPU = sorted("next/" + p.stem for pat in ("splitter_threshold_*.npz", "slow_order_*.npz")
-                     for p in (gu.GOLDEN / "next").glob(pat))
+PENDING_GPU = sorted(p.stem for pat in ("splitter_threshold_*.npz", "slow_order_*.npz") for p in gu.GOLDEN.glob(pat))
 
 
 @pytest.mark.parametrize("name", PENDING_GPU)

@@ -118,9 +118,7 @@ def test_structure_variant_assignment():
     assert gv == expect and 0 < sum(gv) < len(gv)
 
 
-COMPILER_CASES = [b for b in gu.bundles() if not b.startswith(("c1_", "kat_"))] + \
-    sorted("next/" + p.stem for pat in ("splitter_threshold_*.npz", "slow_order_*.npz")
-           for p in (gu.GOLDEN / "next").glob(pat))
+COMPILER_CASES = [b for b in gu.bundles() if not b.startswith(("c1_", "kat_"))]
 
 
 @pytest.mark.parametrize("name", COMPILER_CASES)

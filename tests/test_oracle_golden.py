@@ -125,10 +125,9 @@ NEXT_CASES = sorted("next/" + p.stem for p in (gu.GOLDEN / "next").glob("*.npz")
 
 @pytest.mark.parametrize("name", NEXT_CASES)
 def test_oracle_matches_reference_on_options_the_engine_lacks(name):
-    """snow_melt_process = melt:degree_day_aspect / melt:temperature_index (ProcessMeltDegreeDayAspect.cpp,
-    ProcessMeltTemperatureIndex.cpp) and snow_redistribution = transport:snow_slide (ProcessLateralSnowSlide.cpp, lateral
-    connections between units): the oracle is pinned bit for bit; the CUDA engine does not implement them yet and
-    refuses such structures (tests/golden/next is outside the engine's parity lists)."""
+    """snow_redistribution = transport:snow_slide (ProcessLateralSnowSlide.cpp, lateral connections between units): the
+    oracle is pinned bit for bit; the CUDA engine does not implement it yet and refuses such structures
+    (tests/golden/next is outside the engine's parity lists)."""
     from hydrobricks_b200 import structure
 
     meta, forcing, outlet, records, _ = gu.load(name)
@@ -136,9 +135,5 @@ def test_oracle_matches_reference_on_options_the_engine_lacks(name):
     assert gu.same(om.outlet, outlet)
     for label, ref in records.items():
         assert gu.same(om.records[label], ref), label
-    if name.startswith(("next/melt_", "next/snow_slide_")):
-        with pytest.raises(structure.UnsupportedStructure):
-            structure.CompiledStructure(meta["structures"], meta["solver"])
-    else:  # next/splitter_threshold_*, next/slow_order_*: in the engine, waiting for their first GPU run
-        cs = structure.CompiledStructure(meta["structures"], meta["solver"])
-        assert (cs.hbk.splitter_kind == 1) if "threshold" in name else (cs.hbk.slow_process_order == 1)
+    with pytest.raises(structure.UnsupportedStructure):
+        structure.CompiledStructure(meta["structures"], meta["solver"])

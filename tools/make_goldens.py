@@ -206,17 +206,14 @@ def action_bundles(ref, only_new=False):
 
 
 def melt_variant_bundles(ref):
-    """snow_melt_process variants the CUDA engine does not implement yet (melt:degree_day_aspect,
-    melt:temperature_index): vectors for the oracle now and for the engine next, kept apart under tests/golden/next/ so
-    that the engine's parity tests do not pick them up."""
+    """snow_melt_process variants melt:degree_day_aspect and melt:temperature_index (in the engine since round 2)."""
     import ref_melt_cases as rm
 
-    (OUT / "next").mkdir(parents=True, exist_ok=True)
     for kind, tag in (("melt:degree_day_aspect", "aspect"), ("melt:temperature_index", "tindex")):
         for solver, kw, name in (("rk4", dict(glacier=True, nsoil=2), "glacier_2store"),
                                  ("crank_nicolson", dict(glacier=False, nsoil=1), "noglacier_1store")):
             meta, forcing, q, rec = rm.run_reference(ref, kind, solver, **kw)
-            save(f"next/melt_{tag}_{solver}_{name}", meta, forcing, q, rec)
+            save(f"melt_{tag}_{solver}_{name}", meta, forcing, q, rec)
 
 
 def snow_slide_bundles(ref):
@@ -231,25 +228,31 @@ def snow_slide_bundles(ref):
 
 
 def threshold_splitter_bundles(ref):
-    """snow_rain:threshold instead of the linear transition: supported by the engine since the first kernels but never
-    pinned by a vector before; kept under tests/golden/next/ until its GPU test has run on a B200."""
+    """snow_rain:threshold instead of the linear transition."""
     import ref_threshold_case as rt
 
-    (OUT / "next").mkdir(parents=True, exist_ok=True)
     for solver, kw, name in (("rk4", dict(glacier=True, nsoil=1), "glacier_1store"),
                              ("heun_explicit", dict(glacier=False, nsoil=2), "noglacier_2store")):
         meta, forcing, q, rec = rt.run_reference(ref, solver, **kw)
-        save(f"next/splitter_threshold_{solver}_{name}", meta, forcing, q, rec)
+        save(f"splitter_threshold_{solver}_{name}", meta, forcing, q, rec)
+
+
+def rain_only_bundles(ref):
+    """The rain splitter of GeneratePrecipitationSplitters(withSnow = false): no snow routine at all."""
+    import ref_rain_case as rr
+
+    for solver, kw, name in (("rk4", dict(nsoil=2), "2store"), ("crank_nicolson", dict(nsoil=1), "1store")):
+        meta, forcing, q, rec = rr.run_reference(ref, solver, **kw)
+        save(f"splitter_rain_{solver}_nosnow_{name}", meta, forcing, q, rec)
 
 
 def slow_order_bundles(ref):
     """hbk_structure.slow_process_order = 1 (the process order of core/tests/src/helpers.cpp), two soil stores."""
     import ref_slow_order_case as ro
 
-    (OUT / "next").mkdir(parents=True, exist_ok=True)
     for solver in ("rk4", "crank_nicolson"):
         meta, forcing, q, rec = ro.run_reference(ref, solver)
-        save(f"next/slow_order_{solver}_noglacier_2store", meta, forcing, q, rec)
+        save(f"slow_order_{solver}_noglacier_2store", meta, forcing, q, rec)
 
 
 def main():
@@ -266,6 +269,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "threshold":
         threshold_splitter_bundles(ref)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "rain_only":
+        rain_only_bundles(ref)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "snow_slide":
         snow_slide_bundles(ref)
@@ -330,6 +336,7 @@ def main():
     melt_variant_bundles(ref)
     snow_slide_bundles(ref)
     threshold_splitter_bundles(ref)
+    rain_only_bundles(ref)
     slow_order_bundles(ref)
 
 
