@@ -147,18 +147,37 @@ class Socont:
         a = {"A": ("slow_reservoir", "capacity"), "k_slow": ("slow_reservoir", "response_factor"),
              "k_slow_1": ("slow_reservoir", "response_factor"), "k_slow_2": ("slow_reservoir_2", "response_factor"),
              "percol": ("slow_reservoir", "percolation_rate"), "k_quick": ("surface_runoff", "response_factor"),
-             "beta": ("surface_runoff", "beta"), "a_snow": ("type:snowpack", "degree_day_factor"),
-             "melt_t_snow": ("type:snowpack", "melting_temperature"),
+             "beta": ("surface_runoff", "beta"), "melt_t_snow": ("type:snowpack", "melting_temperature"),
              "prec_t_start": ("snow_rain_transition", "transition_start"),
              "prec_t_end": ("snow_rain_transition", "transition_end")}
+        glaciers = ",".join(self._glacier_names)
+        smp = self.options["snow_melt_process"]  # parameters.py:1755-1820 (glacier ice), 1940-1975 (snowpacks)
+        if smp == "melt:degree_day":
+            a["a_snow"] = ("type:snowpack", "degree_day_factor")
+            if glaciers:
+                a["a_ice"] = (glaciers, "degree_day_factor")
+        elif smp == "melt:degree_day_aspect":
+            for suffix in ("n", "s", "ew"):
+                a[f"a_snow_{suffix}"] = ("type:snowpack", f"degree_day_factor_{suffix}")
+                if glaciers:
+                    a[f"a_ice_{suffix}"] = (glaciers, f"degree_day_factor_{suffix}")
+        elif smp == "melt:temperature_index":
+            shared = "type:snowpack,type:glacier" if glaciers else "type:snowpack"  # one melt factor for snow and ice
+            a["melt_factor"] = a["mf"] = (shared, "melt_factor")
+            a["r_snow"] = ("type:snowpack", "radiation_coefficient")
+            if glaciers:
+                a["r_ice"] = (glaciers, "radiation_coefficient")
+        else:
+            raise ValueError(f"The snow melt process option {smp} is not recognised.")
+        if glaciers:
+            a["melt_t_ice"] = (glaciers, "melting_temperature")
         if self.options["snow_sublimation_process"] == "sublimation:constant":  # parameters.py:286-305, 2006-2018
             a["sublimation_rate"] = ("type:snowpack", "sublimation_rate")
         elif self.options["snow_sublimation_process"] == "sublimation:pet":
             a["sublimation_pet_factor"] = ("type:snowpack", "sublimation_pet_factor")
             a["sublimation_factor"] = ("type:snowpack", "sublimation_pet_factor")
         if self._glacier_names:
-            a.update({"a_ice": (",".join(self._glacier_names), "degree_day_factor"),
-                      "k_snow": (RAIN_SNOWMELT_STORAGE, "response_factor"),
+            a.update({"k_snow": (RAIN_SNOWMELT_STORAGE, "response_factor"),
                       "k_ice": (ICEMELT_STORAGE, "response_factor")})
             snowpacks = ",".join(n + "_snowpack" for n in self._glacier_names)  # parameters.py:2021-2070
             if self.options["snow_ice_transformation"] in ("transform:snow_ice_constant",
@@ -182,6 +201,8 @@ class Socont:
             basin.add_hydro_unit(u["id"], u["area"], u["elevation"])
             if u.get("slope"):
                 basin.add_hydro_unit_property_double("slope", u["slope"][0], u["slope"][1])
+            if u.get("aspect_class"):  # hydro_units.py: the property melt:degree_day_aspect reads
+                basin.add_hydro_unit_property_str("aspect_class", u["aspect_class"])
             for name, frac in u["land_covers"]:
                 basin.add_land_cover(name, "", frac)
         self.model = self.backend.ModelHydro()
@@ -201,11 +222,15 @@ class Socont:
                 raise ValueError(f"Failed setting parameter {alias}")
         self.model.update_parameters(self.settings)
 
-    def set_forcing(self, time_mjd, precipitation, temperature, pet):
-        """Pre-spatialised forcing [T x U] in the basin order of self.units (model.py:354-384)."""
+    def set_forcing(self, time_mjd, precipitation, temperature, pet, solar_radiation=None):
+        """Pre-spatialised forcing [T x U] in the basin order of self.units (model.py:354-384); solar_radiation only
+        with snow_melt_process="melt:temperature_index"."""
         ids = np.array([u["id"] for u in self.units], dtype=np.int32)
         self.model.clear_time_series()
-        for name, data in (("precipitation", precipitation), ("temperature", temperature), ("pet", pet)):
+        series = [("precipitation", precipitation), ("temperature", temperature), ("pet", pet)]
+        if solar_radiation is not None:
+            series.append(("solar_radiation", solar_radiation))
+        for name, data in series:
             if not self.model.create_time_series(name, np.asarray(time_mjd, dtype=np.float64), ids, data):
                 raise ValueError("Failed adding time series.")
         if not self.model.attach_time_series_to_hydro_units():
