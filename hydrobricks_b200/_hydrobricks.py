@@ -614,6 +614,7 @@ class ModelHydro:
         self._mjd0 = 0.0
         self._device = 0
         self._pending_sets = None
+        self._shard = False
 
     # -- setup ---------------------------------------------------------------------------------------
     def init_with_basin(self, model_settings, basin_settings, device=0):
@@ -640,6 +641,16 @@ class ModelHydro:
 
     def is_valid(self):
         return self._engine is not None
+
+    # -- unit shards (one block of a large basin per GPU) -----------------------------------
+    def set_unit_shard(self, basin_area_m2, reduce=None):
+        """This model holds a block of the units of a larger basin of the given total area (hbk_set_unit_shard).
+        reduce(device_pointer, n): in-place sum over all shards (parallel.make_reduce_callback); with it run() covers
+        spin-up and dated actions and returns the outlet of the whole basin. Actions are registered with the tables and
+        changes of the WHOLE basin on every shard; the entries of units outside this block are skipped."""
+        self._engine.set_unit_shard(float(basin_area_m2))
+        self._engine.set_shard_reduce(reduce)
+        self._shard = basin_area_m2 > 0
 
     # -- actions (dated state edits, applied between kernel segments) -----------------------------------
     def add_action(self, action):
@@ -680,11 +691,20 @@ class ModelHydro:
                 have_tables = True
                 if action.land_cover != glacier:
                     raise ValueError(f"delta-h: land cover '{action.land_cover}' is not the glacier cover")
-                try:
-                    units = [pos[int(i)] for i in action.hu_ids]
-                except KeyError as err:
-                    raise ValueError(f"The hydro unit {err} was not found") from err
-                eng.set_delta_h_tables(units, action.areas, action.volumes)
+                if self._shard:
+                    # this block's columns of the lookup tables; the row sums of the whole table, summed in table order
+                    # like ActionGlacierEvolutionDeltaH.cpp:123-126, come with them
+                    cols = [j for j, i in enumerate(action.hu_ids) if int(i) in pos]
+                    units = [pos[int(action.hu_ids[j])] for j in cols]
+                    vol = np.asarray(action.volumes, dtype=np.float64)
+                    eng.set_delta_h_tables(units, np.asarray(action.areas, dtype=np.float64)[:, cols], vol[:, cols])
+                    eng.set_delta_h_shard_totals(np.cumsum(vol, axis=1)[:, -1])
+                else:
+                    try:
+                        units = [pos[int(i)] for i in action.hu_ids]
+                    except KeyError as err:
+                        raise ValueError(f"The hydro unit {err} was not found") from err
+                    eng.set_delta_h_tables(units, action.areas, action.volumes)
                 for k in _schedule.recursive_steps(self._mjd0, self._n_steps, action.month, 1, dt):
                     events.append((k, order, (lambda k=k: eng.add_area_scaling_update(k)) if area_scaling
                                    else (lambda k=k: eng.add_delta_h_update(k))))
@@ -695,6 +715,10 @@ class ModelHydro:
                 raise ValueError(f"Action {type(action).__name__} is not available in the B200 engine")
         for n, (date, order, unit_id, cover, area) in enumerate(sorted(sporadic, key=lambda c: c[0])):
             if unit_id not in pos:
+                if self._shard:  # a unit of another block: only the kernel boundary (all shards run the same segments)
+                    k = _schedule.sporadic_step(self._mjd0, date, dt)
+                    events.append((k, 10000 + n, lambda k=k: eng.add_land_cover_change(k, -1, 0.0)))
+                    continue
                 raise ValueError(f"The hydro unit {unit_id} was not found")
             u = pos[unit_id]
             if cover != glacier:

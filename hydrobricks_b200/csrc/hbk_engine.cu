@@ -833,10 +833,8 @@ __global__ void hbkActSnowToIce(const ActArgs a) {
 }
 
 // ActionGlacierEvolutionDeltaH::Apply (ActionGlacierEvolutionDeltaH.cpp:79-142): one thread per parameter set.
-__global__ void hbkActDeltaH(const ActArgs a, int n, const int* units, int nRows, const double* areas,
-                             const double* volumes, double initialWE, int* lastRow) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= a.P) return;
+// Step 1 (:90-104): water equivalent of the glacier over the units of the lookup table.
+__device__ double deltaHGlacierWE(const ActArgs& a, int p, int n, const int* units) {
     double glacierWE = 0.0;
     for (int i = 0; i < n; ++i) {
         const int u = units[i];
@@ -845,6 +843,12 @@ __global__ void hbkActDeltaH(const ActArgs a, int n, const int* units, int nRows
         const double area = f * a.hru[1 * a.ldu + u];
         glacierWE += area * stateAt(a, HBK_S_ICE, p, u);
     }
+    return glacierWE;
+}
+// Step 2 (:106-142): retreat -> table row -> new extents, ice redistributed by the row's volume shares. rowSums: the
+// volume sum of every row over the WHOLE table when this engine only holds some of its columns (unit shard), else nullptr.
+__device__ void deltaHApply(const ActArgs& a, int p, int n, const int* units, int nRows, const double* areas,
+                            const double* volumes, const double* rowSums, double initialWE, int* lastRow, double glacierWE) {
     double retreat = (initialWE - glacierWE) / initialWE;
     retreat = (0.0 < retreat) ? retreat : 0.0;
     const double rowInc = 1.0 / (nRows - 1);
@@ -864,7 +868,11 @@ __global__ void hbkActDeltaH(const ActArgs a, int n, const int* units, int nRows
         lastRow[p] = row;
     }
     double rowVolumeSum = 0;
-    for (int i = 0; i < n; ++i) rowVolumeSum += volumes[(size_t)row * n + i];
+    if (rowSums) {
+        rowVolumeSum = rowSums[row];
+    } else {
+        for (int i = 0; i < n; ++i) rowVolumeSum += volumes[(size_t)row * n + i];
+    }
     for (int i = 0; i < n; ++i) {
         const int u = units[i];
         const double areaGlacier = areas[(size_t)row * n + i];
@@ -876,6 +884,24 @@ __global__ void hbkActDeltaH(const ActArgs a, int n, const int* units, int nRows
             ice = glacierWE * volumeRatio / areaGlacier;
         }
     }
+}
+__global__ void hbkActDeltaH(const ActArgs a, int n, const int* units, int nRows, const double* areas,
+                             const double* volumes, double initialWE, int* lastRow) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.P) return;
+    deltaHApply(a, p, n, units, nRows, areas, volumes, nullptr, initialWE, lastRow, deltaHGlacierWE(a, p, n, units));
+}
+// Unit shards: this block's part of the water equivalent; the sum over the shards comes back through the caller's
+// reduction (hbk_set_shard_reduce) before the second kernel applies the row of the whole table.
+__global__ void hbkActDeltaHSum(const ActArgs a, int n, const int* units, double* we) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < a.P) we[p] = deltaHGlacierWE(a, p, n, units);
+}
+__global__ void hbkActDeltaHApply(const ActArgs a, int n, const int* units, int nRows, const double* areas,
+                                  const double* volumes, const double* rowSums, double initialWE, int* lastRow,
+                                  const double* we) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < a.P) deltaHApply(a, p, n, units, nRows, areas, volumes, rowSums, initialWE, lastRow, we[p]);
 }
 
 // ActionGlacierEvolutionAreaScaling::Apply (ActionGlacierEvolutionAreaScaling.cpp:75-123): one thread per
@@ -1157,6 +1183,7 @@ struct hbk_engine {
     double* dObs = nullptr;     // [T] + 3 stats
     double* dStale = nullptr;  // [P][2] stale deposit amounts of null glacier bricks (actions only)
     int dhUnits = 0, dhRows = 0;
+    bool dhTablesSet = false;  // since the last hbk_clear_actions (dhUnits may be 0 on a unit shard)
     double dhInitialWE = 0;
     std::vector<double> hArea;
     size_t allocP = 0;
@@ -1170,6 +1197,20 @@ struct hbk_engine {
     // unit pass and hbk_finish_sharded_run integrates the sub-basin stores on the reduced deposit sums
     bool shard = false, shardPending = false;
     double shardBasinArea = 0;
+    // sums over all shards inside hbk_run (hbk_set_shard_reduce): spin-up, delta-h dates, end of run
+    hbk_shard_reduce_fn shardReduce = nullptr;
+    void* shardUser = nullptr;
+    double* dShardStage = nullptr;  // contiguous staging of the column blocks handed to the callback
+    size_t shardStageN = 0;
+    double* dStaleSeg = nullptr;    // [segment][P][2]: stale deposit amounts of null glacier bricks per segment
+    size_t staleSegN = 0;
+    double* dShardWE = nullptr;     // [P] glacier water equivalent of this block at a delta-h date
+    double* dDhRowSums = nullptr;   // [dhRows] volume sums of the whole table's rows (hbk_set_delta_h_shard_totals)
+    bool dhShardTotals = false;
+    struct Segment {
+        int tBegin, tEnd;
+    };
+    std::vector<Segment> shardSegments;  // segments of the current run (shard mode with a callback)
 };
 
 namespace {
@@ -1350,6 +1391,9 @@ int ensureSetBuffers(hbk_engine* e, int P) {
     freeDev(e->dFracSet);
     freeDev(e->dDhLastRow);
     freeDev(e->dStale);
+    freeDev(e->dStaleSeg);
+    e->staleSegN = 0;
+    freeDev(e->dShardWE);
     freeDev(e->dScores);
     freeDev(e->dPerm);
     freeDev(e->dUnconvSet);
@@ -1487,6 +1531,10 @@ void hbk_engine_destroy(hbk_engine* e) {
     freeDev(e->dUnconv);
     freeDev(e->dUnconvSet);
     freeDev(e->dQueue);
+    freeDev(e->dShardStage);
+    freeDev(e->dStaleSeg);
+    freeDev(e->dShardWE);
+    freeDev(e->dDhRowSums);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -1714,13 +1762,16 @@ int hbk_clear_actions(hbk_engine* e) {
     if (!e) return HBK_E_ARG;
     e->events.clear();
     e->dhUnits = 0;
+    e->dhTablesSet = false;
     return HBK_OK;
 }
 
 int hbk_add_land_cover_change(hbk_engine* e, int32_t step, int32_t unit, double fraction) {
-    if (!e || unit < 0 || unit >= e->U || step < 1) return HBK_E_ARG;
+    // unit = -1 on a unit shard: the edit concerns a unit of another block; this block only cuts its run at the same step
+    // (all shards must run the same segments: their per-segment sums are reduced together)
+    if (!e || unit < -1 || (unit == -1 && !e->shard) || unit >= e->U || step < 1) return HBK_E_ARG;
     if (!e->st.has_glacier) return fail(e, HBK_E_MODEL, "land-cover change needs a structure with a glacier cover");
-    if (!e->unitsSet || !e->hGlacierVariant[unit])
+    if (!e->unitsSet || (unit >= 0 && !e->hGlacierVariant[unit]))
         return fail(e, HBK_E_MODEL, "land-cover change on a hydro unit whose structure variant has no glacier cover");
     if (fraction < 0 || fraction > 1) return fail(e, HBK_E_MODEL, "The fraction is not in the range [0 .. 1]");
     e->events.push_back({step, 0, unit, fraction});
@@ -1736,21 +1787,22 @@ int hbk_add_snow_to_ice(hbk_engine* e, int32_t step) {
 
 int hbk_add_delta_h_update(hbk_engine* e, int32_t step) {
     if (!e || step < 1) return HBK_E_ARG;
-    if (e->dhUnits == 0) return fail(e, HBK_E_STATE, "hbk_set_delta_h_tables has not been called");
+    if (!e->dhTablesSet) return fail(e, HBK_E_STATE, "hbk_set_delta_h_tables has not been called");
     e->events.push_back({step, 2, -1, 0.0});
     return HBK_OK;
 }
 
 int hbk_add_area_scaling_update(hbk_engine* e, int32_t step) {
     if (!e || step < 1) return HBK_E_ARG;
-    if (e->dhUnits == 0) return fail(e, HBK_E_STATE, "hbk_set_delta_h_tables has not been called");
+    if (!e->dhTablesSet) return fail(e, HBK_E_STATE, "hbk_set_delta_h_tables has not been called");
     e->events.push_back({step, 3, -1, 0.0});
     return HBK_OK;
 }
 
 int hbk_set_delta_h_tables(hbk_engine* e, int32_t n, const int32_t* units, int32_t nRows, const double* areas,
                            const double* volumes) {
-    if (!e || n <= 0 || !units || nRows < 2 || !areas || !volumes) return HBK_E_ARG;
+    // n = 0: a unit shard that holds none of the table's units (it still takes part in the reductions of every update)
+    if (!e || n < 0 || (n == 0 && !e->shard) || nRows < 2 || (n > 0 && (!units || !areas || !volumes))) return HBK_E_ARG;
     if (!e->unitsSet) return fail(e, HBK_E_STATE, "hbk_set_units must precede hbk_set_delta_h_tables");
     if (!e->st.has_glacier || e->st.glacier_infinite_storage)
         return fail(e, HBK_E_MODEL, "glacier evolution needs a glacier cover with a finite ice storage");
@@ -1787,17 +1839,81 @@ int hbk_set_delta_h_tables(hbk_engine* e, int32_t n, const int32_t* units, int32
     freeDev(e->dDhUnits);
     freeDev(e->dDhAreas);
     freeDev(e->dDhVolumes);
-    HBK_CUDA(cudaMalloc(&e->dDhUnits, sizeof(int) * n));
-    HBK_CUDA(cudaMalloc(&e->dDhAreas, sizeof(double) * (size_t)n * nRows));
-    HBK_CUDA(cudaMalloc(&e->dDhVolumes, sizeof(double) * (size_t)n * nRows));
-    HBK_CUDA(cudaMemcpy(e->dDhUnits, units, sizeof(int) * n, cudaMemcpyHostToDevice));
-    HBK_CUDA(cudaMemcpy(e->dDhAreas, areas, sizeof(double) * (size_t)n * nRows, cudaMemcpyHostToDevice));
-    HBK_CUDA(cudaMemcpy(e->dDhVolumes, volumes, sizeof(double) * (size_t)n * nRows, cudaMemcpyHostToDevice));
+    HBK_CUDA(cudaMalloc(&e->dDhUnits, sizeof(int) * std::max(n, 1)));
+    HBK_CUDA(cudaMalloc(&e->dDhAreas, sizeof(double) * std::max<size_t>((size_t)n * nRows, 1)));
+    HBK_CUDA(cudaMalloc(&e->dDhVolumes, sizeof(double) * std::max<size_t>((size_t)n * nRows, 1)));
+    if (n > 0) {
+        HBK_CUDA(cudaMemcpy(e->dDhUnits, units, sizeof(int) * n, cudaMemcpyHostToDevice));
+        HBK_CUDA(cudaMemcpy(e->dDhAreas, areas, sizeof(double) * (size_t)n * nRows, cudaMemcpyHostToDevice));
+        HBK_CUDA(cudaMemcpy(e->dDhVolumes, volumes, sizeof(double) * (size_t)n * nRows, cudaMemcpyHostToDevice));
+    }
     e->dhUnits = n;
     e->dhRows = nRows;
+    e->dhTablesSet = true;
     double initialVolume = 0;
     for (int i = 0; i < n; ++i) initialVolume += volumes[i];
     e->dhInitialWE = initialVolume * 900.0;
+    e->dhShardTotals = false;
+    return HBK_OK;
+}
+
+int hbk_set_delta_h_shard_totals(hbk_engine* e, int32_t n_rows, const double* row_volume_sums) {
+    if (!e || !row_volume_sums) return HBK_E_ARG;
+    if (e->dhRows == 0) return fail(e, HBK_E_STATE, "hbk_set_delta_h_tables has not been called");
+    if (n_rows != e->dhRows) return fail(e, HBK_E_ARG, "delta-h: n_rows differs from the lookup tables");
+    HBK_CUDA(cudaSetDevice(e->device));
+    freeDev(e->dDhRowSums);
+    HBK_CUDA(cudaMalloc(&e->dDhRowSums, sizeof(double) * n_rows));
+    HBK_CUDA(cudaMemcpy(e->dDhRowSums, row_volume_sums, sizeof(double) * n_rows, cudaMemcpyHostToDevice));
+    e->dhInitialWE = row_volume_sums[0] * 900.0;  // ActionGlacierEvolutionDeltaH.cpp:66-69 over the whole table
+    e->dhShardTotals = true;
+    return HBK_OK;
+}
+
+// Sum over all shards, through the caller's callback, of column blocks [t0, t1) of row-major [P][ldt] buffers and of
+// contiguous vectors: gathered into one contiguous staging buffer (one collective), then scattered back.
+struct ShardBlock {
+    double* buf;
+    long long ld;  // row stride in doubles; 0 = contiguous vector of n doubles
+    int t0, t1;
+    size_t n;
+};
+static int shardReduceBlocks(hbk_engine* e, const std::vector<ShardBlock>& blocks) {
+    size_t total = 0;
+    for (const auto& b : blocks) total += b.ld ? (size_t)e->P * (b.t1 - b.t0) : b.n;
+    if (total == 0) return HBK_OK;
+    if (total > e->shardStageN) {
+        freeDev(e->dShardStage);
+        HBK_CUDA(cudaMalloc(&e->dShardStage, sizeof(double) * total));
+        e->shardStageN = total;
+    }
+    size_t off = 0;
+    for (const auto& b : blocks) {
+        if (b.ld) {
+            const size_t w = (size_t)(b.t1 - b.t0);
+            HBK_CUDA(cudaMemcpy2DAsync(e->dShardStage + off, w * 8, b.buf + b.t0, (size_t)b.ld * 8, w * 8, e->P,
+                                       cudaMemcpyDeviceToDevice, e->stream));
+            off += (size_t)e->P * w;
+        } else {
+            HBK_CUDA(cudaMemcpyAsync(e->dShardStage + off, b.buf, b.n * 8, cudaMemcpyDeviceToDevice, e->stream));
+            off += b.n;
+        }
+    }
+    HBK_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->shardReduce(e->shardUser, e->dShardStage, (int64_t)total) != 0)
+        return fail(e, HBK_E_STATE, "the shard reduction callback (hbk_set_shard_reduce) reported a failure");
+    off = 0;
+    for (const auto& b : blocks) {
+        if (b.ld) {
+            const size_t w = (size_t)(b.t1 - b.t0);
+            HBK_CUDA(cudaMemcpy2DAsync(b.buf + b.t0, (size_t)b.ld * 8, e->dShardStage + off, w * 8, w * 8, e->P,
+                                       cudaMemcpyDeviceToDevice, e->stream));
+            off += (size_t)e->P * w;
+        } else {
+            HBK_CUDA(cudaMemcpyAsync(b.buf, e->dShardStage + off, b.n * 8, cudaMemcpyDeviceToDevice, e->stream));
+            off += b.n;
+        }
+    }
     return HBK_OK;
 }
 
@@ -1819,13 +1935,25 @@ static int applyEvents(hbk_engine* e, int step) {
     for (const auto& ev : e->events) {
         if (ev.step != step) continue;
         if (ev.kind == 0) {
+            if (ev.unit < 0) continue;  // an edit in another block of the basin (unit shard): boundary only
             hbkActLandCoverChange<<<pBlocks, 128, 0, e->stream>>>(a, ev.unit, ev.value);
         } else if (ev.kind == 1) {
             hbkActSnowToIce<<<148 * 2, 256, 0, e->stream>>>(a);
         } else if (ev.kind == 3) {
+            if (e->dhUnits == 0) continue;  // a unit shard without any unit of the table: nothing to scale here
             const long long n = (long long)e->P * e->dhUnits;
             hbkActAreaScaling<<<(unsigned)((n + 127) / 128), 128, 0, e->stream>>>(a, e->dhUnits, e->dDhUnits, e->dhRows,
                                                                                   e->dDhAreas, e->dDhVolumes);
+        } else if (e->shard) {
+            // the glacier of the whole basin: this block's water equivalent, summed over the shards by the caller
+            if (!e->dShardWE) HBK_CUDA(cudaMalloc(&e->dShardWE, sizeof(double) * e->P));
+            hbkActDeltaHSum<<<pBlocks, 128, 0, e->stream>>>(a, e->dhUnits, e->dDhUnits, e->dShardWE);
+            int rc = shardReduceBlocks(e, {{e->dShardWE, 0, 0, 0, (size_t)e->P}});
+            if (rc) return rc;
+            hbkActDeltaHApply<<<pBlocks, 128, 0, e->stream>>>(a, e->dhUnits, e->dDhUnits, e->dhRows, e->dDhAreas,
+                                                              e->dDhVolumes, e->dDhRowSums, e->dhInitialWE, e->dDhLastRow,
+                                                              e->dShardWE);
+            e->lastLaunches++;
         } else {
             hbkActDeltaH<<<pBlocks, 128, 0, e->stream>>>(a, e->dhUnits, e->dDhUnits, e->dhRows, e->dDhAreas, e->dDhVolumes,
                                                          e->dhInitialWE, e->dDhLastRow);
@@ -2022,6 +2150,39 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
         hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD2, e->dD2, e->nGroups, e->P, e->ldt, tBegin, tEnd, nullptr);
         e->lastLaunches += 2;
     }
+    if (e->st.has_glacier && e->shard && e->shardReduce && writeOutputs) {
+        // the sub-basin stores wait for the sums over the shards (end of hbk_run); what has to be kept per segment is the
+        // stale deposit amounts of this block's vanished glaciers
+        const size_t seg = e->shardSegments.size();
+        e->shardSegments.push_back({tBegin, tEnd});
+        if (e->fracPerSet) {
+            const size_t need = (seg + 1) * 2 * (size_t)e->P;
+            if (need > e->staleSegN) {
+                const size_t cap = std::max(need, 2 * e->staleSegN + 64 * (size_t)e->P);
+                double* grown = nullptr;
+                HBK_CUDA(cudaMalloc(&grown, sizeof(double) * cap));
+                if (e->dStaleSeg)
+                    HBK_CUDA(cudaMemcpyAsync(grown, e->dStaleSeg, sizeof(double) * e->staleSegN, cudaMemcpyDeviceToDevice,
+                                             e->stream));
+                HBK_CUDA(cudaStreamSynchronize(e->stream));
+                freeDev(e->dStaleSeg);
+                e->dStaleSeg = grown;
+                e->staleSegN = cap;
+            }
+            ActArgs aa{};
+            aa.P = e->P;
+            aa.U = e->U;
+            aa.frac = e->dFracSet;
+            aa.state = e->dState;
+            aa.lds = (long long)e->P * e->U;
+            aa.sP = e->stateLaneP ? 1 : e->U;
+            aa.sU = e->stateLaneP ? e->P : 1;
+            aa.hruFlags = e->dHruFlags;
+            aa.ldu = e->ldu;
+            hbkStaleDeposits<<<e->P, 128, 0, e->stream>>>(aa, e->dStaleSeg + seg * 2 * (size_t)e->P);
+            e->lastLaunches++;
+        }
+    }
     if (e->st.has_glacier && !e->shard) {
         const double* stale = nullptr;
         if (e->fracPerSet) {  // a glacier may have vanished through an action: its stale flux amounts
@@ -2067,9 +2228,18 @@ int hbk_run(hbk_engine* e) {
     if (station && e->perSetDropped)
         return fail(e, HBK_E_STATE, "per-set gradients / correction factors must be set again (hbk_set_station_forcing) "
                                     "after the number of parameter sets changed");
-    if (e->shard && (e->spinupSteps > 0 || !e->events.empty()))
-        return fail(e, HBK_E_UNSUPPORTED, "a unit shard runs neither spin-up nor dated actions (the sub-basin stores "
-                                          "and the delta-h reduction span all shards)");
+    const bool shardCb = e->shard && e->shardReduce != nullptr;
+    if (e->shard && !shardCb && (e->spinupSteps > 0 || !e->events.empty()))
+        return fail(e, HBK_E_UNSUPPORTED, "a unit shard runs spin-up and dated actions only with a reduction callback "
+                                          "(hbk_set_shard_reduce): the sub-basin stores and the delta-h water equivalent "
+                                          "span all shards");
+    if (shardCb && e->dhTablesSet && !e->dhShardTotals) {
+        for (const auto& ev : e->events)
+            if (ev.kind == 2)
+                return fail(e, HBK_E_STATE, "delta-h on a unit shard needs the row sums of the whole lookup table "
+                                            "(hbk_set_delta_h_shard_totals)");
+    }
+    e->shardSegments.clear();
     HBK_CUDA(cudaSetDevice(e->device));
     chooseShape(e);
     e->lastLaunches = 0;
@@ -2157,6 +2327,13 @@ int hbk_run(hbk_engine* e) {
     if (e->spinupSteps > 0) {  // ModelHydro::RunSpinup (ModelHydro.cpp:135-181)
         rc = launchSegment(e, 0, e->spinupSteps, false);
         if (rc) return rc;
+        if (shardCb && e->st.has_glacier) {
+            // the sub-basin stores are spun up on the deposits of the whole basin
+            rc = shardReduceBlocks(e, {{e->dD1, e->ldt, 0, e->spinupSteps, 0}, {e->dD2, e->ldt, 0, e->spinupSteps, 0}});
+            if (rc) return rc;
+            launchBasinStores(e, 0, e->spinupSteps, nullptr, 0);
+            e->lastLaunches++;
+        }
     }
     if (e->events.empty()) {
         rc = launchSegment(e, 0, e->T, true);
@@ -2179,6 +2356,26 @@ int hbk_run(hbk_engine* e) {
         rc = launchSegment(e, t, e->T, true);
         if (rc) return rc;
     }
+    if (shardCb) {
+        // end of the unit pass: partial outlet, deposits and stale amounts summed over the shards in one collective, then
+        // the sub-basin stores segment by segment on the sums (exact: no superposition across shards)
+        std::vector<ShardBlock> blocks = {{e->dOutlet, e->ldt, 0, e->T, 0}};
+        if (e->st.has_glacier) {
+            blocks.push_back({e->dD1, e->ldt, 0, e->T, 0});
+            blocks.push_back({e->dD2, e->ldt, 0, e->T, 0});
+            if (e->fracPerSet) blocks.push_back({e->dStaleSeg, 0, 0, 0, e->shardSegments.size() * 2 * (size_t)e->P});
+        }
+        rc = shardReduceBlocks(e, blocks);
+        if (rc) return rc;
+        if (e->st.has_glacier) {
+            for (size_t seg = 0; seg < e->shardSegments.size(); ++seg) {
+                launchBasinStores(e, e->shardSegments[seg].tBegin, e->shardSegments[seg].tEnd,
+                                  e->fracPerSet ? e->dStaleSeg + seg * 2 * (size_t)e->P : nullptr, 1);
+                e->lastLaunches++;
+            }
+        }
+        HBK_CUDA(cudaGetLastError());
+    }
     HBK_CUDA(cudaEventRecord(e->ev1, e->stream));
     HBK_CUDA(cudaStreamSynchronize(e->stream));
     float ms = 0;
@@ -2190,7 +2387,7 @@ int hbk_run(hbk_engine* e) {
     HBK_CUDA(cudaMemcpy(&unc, e->dUnconv, sizeof(unc), cudaMemcpyDeviceToHost));
     e->lastUnconverged = (long long)unc;
     e->ran = true;
-    e->shardPending = e->shard;
+    e->shardPending = e->shard && !shardCb;
     if (err & kErrRateTooHigh)  // WaterContainer.cpp:83-86 throws; ModelHydro::Run fails
         return fail(e, HBK_E_MODEL, "a change rate exceeded 10000 (WaterContainer::ApplyConstraints)");
     if (err & kErrQueueStall) return fail(e, HBK_E_CUDA, "internal error: the unit kernel's work queue stalled");
@@ -2217,6 +2414,13 @@ int hbk_set_unit_shard(hbk_engine* e, double basin_area_m2) {
     std::vector<double> w(e->U);
     for (int u = 0; u < e->U; ++u) w[u] = e->hArea[u] / basinArea;  // ModelBuilder.cpp:468, whole-basin area
     HBK_CUDA(cudaMemcpy(e->dHru, w.data(), sizeof(double) * e->U, cudaMemcpyHostToDevice));
+    return HBK_OK;
+}
+
+int hbk_set_shard_reduce(hbk_engine* e, hbk_shard_reduce_fn reduce, void* user) {
+    if (!e) return HBK_E_ARG;
+    e->shardReduce = reduce;
+    e->shardUser = user;
     return HBK_OK;
 }
 

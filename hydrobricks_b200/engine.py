@@ -72,6 +72,10 @@ class HbkStructure(ctypes.Structure):
     ]
 
 
+# hbk_shard_reduce_fn: int (*)(void* user, double* device_buffer, int64_t n)
+SHARD_REDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64)
+
+
 class HbkError(RuntimeError):
     def __init__(self, code, message):
         super().__init__(f"hbk error {code}: {message}")
@@ -132,6 +136,8 @@ def load_library():
     L.hbk_shard_partials_dev.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
                                          ctypes.POINTER(i64), ctypes.POINTER(i64)]
     L.hbk_finish_sharded_run.argtypes = [vp]
+    L.hbk_set_shard_reduce.argtypes = [vp, SHARD_REDUCE_FN, vp]
+    L.hbk_set_delta_h_shard_totals.argtypes = [vp, i32, dp]
     _lib = L
     return L
 
@@ -356,6 +362,32 @@ class Engine:
 
     def finish_sharded_run(self):
         self._check(self.L.hbk_finish_sharded_run(self.h))
+
+    def set_shard_reduce(self, reduce):
+        """reduce(device_pointer: int, n: int) must sum the n float64 at that device address over all shards in place
+        (hbk_set_shard_reduce); with it a unit shard runs spin-up and dated actions and finishes inside run(). None
+        removes it."""
+        if reduce is None:
+            self._reduce_cb = None
+            self._check(self.L.hbk_set_shard_reduce(self.h, SHARD_REDUCE_FN(0), None))
+            return
+
+        def trampoline(_user, ptr, n):
+            try:
+                reduce(int(ptr), int(n))
+                return 0
+            except Exception:  # an exception must not unwind through the C frames
+                import traceback
+
+                traceback.print_exc()
+                return 1
+
+        self._reduce_cb = SHARD_REDUCE_FN(trampoline)  # kept alive as long as the engine may call it
+        self._check(self.L.hbk_set_shard_reduce(self.h, self._reduce_cb, None))
+
+    def set_delta_h_shard_totals(self, row_volume_sums):
+        v = np.ascontiguousarray(row_volume_sums, dtype=np.float64)
+        self._check(self.L.hbk_set_delta_h_shard_totals(self.h, len(v), _dptr(v)))
 
     def outlet_device_pointer(self):
         ptr, ld = ctypes.c_void_p(), ctypes.c_int64()

@@ -99,6 +99,20 @@ def reduce_partials(partials, group=None):
     return partials
 
 
+def make_reduce_callback(group=None):
+    """The in-place sum over the ranks that a unit shard asks for inside its run (hbk_set_shard_reduce,
+    Engine.set_shard_reduce): one all-reduce(sum) of n float64 at a device address, complete when it returns."""
+    import torch
+    import torch.distributed as dist
+
+    def reduce(ptr, n):
+        t = torch.as_tensor(_DeviceArray(ptr, (n,), None), device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        torch.cuda.current_stream().synchronize()
+
+    return reduce
+
+
 def shard_partials(engine):
     """Zero-copy torch views [n_sets x ld] of a unit shard's partial outlet and deposit sums in HBM."""
     import torch
@@ -116,9 +130,14 @@ class ShardedBasin:
     device (same structure, time axis and forcing on every rank); `units` is the full list in basin order
     (descending elevation, as HydroUnits sorts them). run() integrates the block and returns nothing; afterwards
     get_outlet_discharge() gives the outlet of the WHOLE basin on every rank.
+
+    in_run_reduce=True hands the engine a reduction callback (hbk_set_shard_reduce): the sums over the ranks then happen
+    inside the run — which is what spin-up (ModelHydro::RunSpinup) and dated actions (the delta-h water equivalent of the
+    whole glacier at every update) need — and run() goes through the model's own run(), so that actions registered on
+    the model (tables / changes of the WHOLE basin, the same on every rank) are scheduled. Needs the Python host.
     """
 
-    def __init__(self, make_model, units, group=None):
+    def __init__(self, make_model, units, group=None, in_run_reduce=False):
         import torch.distributed as dist
 
         self.group = group
@@ -129,6 +148,9 @@ class ShardedBasin:
         self.total_area = basin_area([u["area"] for u in units])
         self.model = make_model(units[lo:hi])
         self._engine = None
+        self.in_run_reduce = in_run_reduce
+        if in_run_reduce:
+            self.model.model.set_unit_shard(self.total_area, make_reduce_callback(group))
 
     def engine(self, n_sets=1):
         if self._engine is None:
@@ -138,6 +160,10 @@ class ShardedBasin:
         return self._engine
 
     def run(self, n_sets=1):
+        if self.in_run_reduce:
+            self._engine = self.model.engine(n_sets)
+            self.model.model.run()
+            return
         eng = self.engine(n_sets)
         import torch
 

@@ -188,6 +188,7 @@ int hbk_set_record_mask(hbk_engine* e, uint64_t mask);
  *    areas/volumes[n_rows][n_units] (row-major) of hbk_set_delta_h_tables, which also performs Init
  *    (…DeltaH.cpp:21-70): checks the initial glacier areas and sets the initial ice content. */
 int hbk_clear_actions(hbk_engine* e);
+/* unit = -1 (unit shards only): the edit concerns a unit of another block; this block just cuts its run at `step`. */
 int hbk_add_land_cover_change(hbk_engine* e, int32_t step, int32_t unit, double glacier_fraction);
 int hbk_add_snow_to_ice(hbk_engine* e, int32_t step);
 int hbk_set_delta_h_tables(hbk_engine* e, int32_t n_units, const int32_t* units, int32_t n_rows, const double* areas,
@@ -212,11 +213,27 @@ int hbk_run(hbk_engine* e);
  * internal set order, identical on all shards given identical parameter sets) and calls hbk_finish_sharded_run,
  * which integrates the two sub-basin stores on the summed deposits (SubBasin bricks, modules/glacier.py:108-131)
  * and adds their outflow: hbk_get_outlet then returns the outlet of the whole basin on every shard.
- * Spin-up and dated actions are refused in shard mode (HBK_E_UNSUPPORTED). */
+ * Without a reduction callback (below) spin-up and dated actions are refused in shard mode (HBK_E_UNSUPPORTED). */
 int hbk_set_unit_shard(hbk_engine* e, double basin_area_m2);
 int hbk_shard_partials_dev(hbk_engine* e, double** outlet, double** deposits_rain_snowmelt, double** deposits_icemelt,
                            int64_t* n_rows, int64_t* ld);
 int hbk_finish_sharded_run(hbk_engine* e);
+/* Unit shards with spin-up (ModelHydro::RunSpinup, ModelHydro.cpp:135-181) and dated actions: the engine then needs sums
+ * over all shards INSIDE hbk_run — the spin-up deposits before the sub-basin stores are spun up, the glacier water
+ * equivalent of every parameter set at each delta-h date (ActionGlacierEvolutionDeltaH.cpp:90-104 sums it over all
+ * glacier units of the basin), the partial outlet / deposits / stale amounts at the end — and asks the caller for them:
+ * reduce(user, buf, n) must replace the n float64 at the DEVICE address buf by their sum over all shards (one
+ * ncclAllReduce / MPI_Allreduce on the caller's communicator; every shard calls it the same number of times with the same
+ * n, in the same order) and return 0 once the result is in place. The engine's stream is idle during the call. With a
+ * callback set, hbk_run completes the run itself (hbk_finish_sharded_run is not called) and hbk_get_outlet returns the
+ * outlet of the whole basin on every shard. NULL removes the callback. */
+typedef int (*hbk_shard_reduce_fn)(void* user, double* device_buffer, int64_t n);
+int hbk_set_shard_reduce(hbk_engine* e, hbk_shard_reduce_fn reduce, void* user);
+/* Delta-h lookup tables of a unit shard: hbk_set_delta_h_tables is given the shard's own columns; the quantities
+ * ActionGlacierEvolutionDeltaH::Apply takes over the WHOLE table — the volume sum of every row (summed in table order,
+ * ...DeltaH.cpp:123-126; row 0 x ice density is the initial water equivalent, :66-69) — come from the caller:
+ * row_volume_sums[n_rows]. Call after hbk_set_delta_h_tables. */
+int hbk_set_delta_h_shard_totals(hbk_engine* e, int32_t n_rows, const double* row_volume_sums);
 
 /* ModelHydro::GetOutletDischarge (ModelHydro.cpp:203-205): out[n_sets][n_steps]. */
 int hbk_get_outlet(hbk_engine* e, int32_t first_set, int32_t n_sets, double* out);
