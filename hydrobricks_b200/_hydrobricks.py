@@ -47,6 +47,9 @@ _PROCESS_REGISTRY = {
     "transformation:snow_ice_constant": ([("snow_ice_transformation_rate", 0.5)], []),
     "transform:snow_ice_swat": ([("snow_ice_transformation_basal_acc_coeff", 0.0014), ("north_hemisphere", 1)], []),
     "transformation:snow_ice_swat": ([("snow_ice_transformation_basal_acc_coeff", 0.0014), ("north_hemisphere", 1)], []),
+    # ProcessLateralSnowSlide::RegisterProcessSettings (ProcessLateralSnowSlide.cpp:24-31)
+    "transport:snow_slide": ([("coeff", 3178.4), ("exp", -1.998), ("min_slope", 10.0), ("max_slope", 75.0),
+                              ("min_snow_holding_depth", 50.0), ("max_snow_depth", 20000.0)], []),
     # ProcessSublimation{Constant,PET}::RegisterProcessSettings
     "sublimation:constant": ([("sublimation_rate", 0.1)], []),
     "sublimation:pet": ([("sublimation_pet_factor", 0.2)], ["pet"]),
@@ -462,8 +465,19 @@ class SettingsModel:
             if kind == "glacier":
                 self.add_brick_process("snow_ice_transfo", transformation_process, name + ":ice")
 
-    def add_snow_redistribution(self, *a, **k):
-        self._unsupported("snow redistribution")
+    def add_snow_redistribution(self, redistribution_process="transport:snow_slide", skip_glaciers=True):
+        """SettingsModel::AddSnowRedistribution (SettingsModel.cpp:560-572): on the snowpack of every land cover (the
+        glacier covers only without skip_glaciers), a lateral process whose instantaneous snow fluxes go to the
+        snowpacks of the connected units."""
+        if redistribution_process != "transport:snow_slide":
+            raise RuntimeError(f"Process type '{redistribution_process}' is not available in the B200 engine.")
+        covers = [(b["name"], b["kind"]) for b in self._sel_structure["hydro_unit_bricks"] if b["is_land_cover"]]
+        for name, kind in covers:
+            if skip_glaciers and kind == "glacier":
+                continue
+            self.select_hydro_unit_brick(name + "_snowpack")
+            self.add_brick_process("snow_redistribution", redistribution_process, "lateral:snow")
+            self.set_process_outputs_as_instantaneous()
 
     # -- parameters ----------------------------------------------------------------------------------
     def set_parameter_value(self, component, name, value):
@@ -539,10 +553,11 @@ class SettingsBasin:
 
     def __init__(self):
         self.units = []
+        self.connections = []
 
     def add_hydro_unit(self, id, area, elevation=-9999):  # noqa: A002
         self.units.append({"id": int(id), "area": float(area), "elevation": float(elevation), "slope": None,
-                           "properties": {}, "land_covers": []})
+                           "properties": {}, "land_covers": [], "lateral": []})
 
     def add_land_cover(self, name, kind, fraction):
         self.units[-1]["land_covers"].append((name, float(fraction)))
@@ -555,14 +570,17 @@ class SettingsBasin:
         if name == "slope":
             self.units[-1]["slope"] = (float(value), unit)
 
-    def add_lateral_connection(self, *a, **k):
-        raise RuntimeError("Lateral connections are not available in the B200 engine (SURVEY.md §8f).")
+    def add_lateral_connection(self, giver_hydro_unit_id, receiver_hydro_unit_id, fraction, type=""):  # noqa: A002
+        """SettingsBasin::AddLateralConnection: kept by unit id; resolved to basin positions when the model is built
+        (ModelBuilder.cpp:476-508)."""
+        self.connections.append((int(giver_hydro_unit_id), int(receiver_hydro_unit_id), float(fraction), type))
 
     def get_lateral_connection_count(self):
-        return 0
+        return len(self.connections)
 
     def clear(self):
         self.units = []
+        self.connections = []
 
 
 class SubBasin:
@@ -630,6 +648,13 @@ class ModelHydro:
             self._n_steps = int(1 + (_parse_date_mjd(t["end"]) - self._mjd0) / dt)
             self._settings = model_settings
             self._units = [dict(u) for u in basin_settings.units]
+            pos = {u["id"]: i for i, u in enumerate(self._units)}
+            for u in self._units:
+                u["lateral"] = []
+            for giver, receiver, fraction, _kind in getattr(basin_settings, "connections", []):
+                if giver not in pos or receiver not in pos:
+                    raise KeyError(f"lateral connection: hydro unit {giver if giver not in pos else receiver} not found")
+                self._units[pos[giver]]["lateral"].append((pos[receiver], fraction))
             self._cs, self._engine = _structure.build_engine(model_settings.get_structure(), self._units,
                                                              model_settings.solver, self._n_steps, device, dt,
                                                              start_mjd=self._mjd0)

@@ -170,6 +170,73 @@ __device__ __noinline__ AspectFactors radiationFactors(const float* params, int 
     return f;
 }
 
+// Per-parameter-set values of one set (pp = its column of the float32 parameter table), promoted to double where the
+// reference's expressions promote them; pv[field * ps].
+__device__ __forceinline__ void fillPar(double* pv, int ps, const float* pp, int ldp) {
+    const float t0f = pp[HBK_P_TRANSITION_START * ldp], t1f = pp[HBK_P_TRANSITION_END * ldp];
+    pv[0 * ps] = t0f;
+    pv[1 * ps] = t1f;
+    pv[2 * ps] = 1.0 / (double)(t1f - t0f);
+    pv[3 * ps] = pp[HBK_P_RAIN_CORRECTION * ldp];
+    pv[4 * ps] = pp[HBK_P_SNOW_CORRECTION * ldp];
+    pv[5 * ps] = pp[HBK_P_GROUND_SNOW_DDF * ldp];
+    pv[6 * ps] = pp[HBK_P_GROUND_SNOW_TMELT * ldp];
+    pv[7 * ps] = pp[HBK_P_GLACIER_SNOW_DDF * ldp];
+    pv[8 * ps] = pp[HBK_P_GLACIER_SNOW_TMELT * ldp];
+    pv[9 * ps] = pp[HBK_P_ICE_DDF * ldp];
+    pv[10 * ps] = pp[HBK_P_ICE_TMELT * ldp];
+    const double capacity = pp[HBK_P_CAPACITY * ldp];
+    pv[11 * ps] = capacity;
+    pv[12 * ps] = (capacity == 0.0) ? kInvZeroCapacity : 1.0 / capacity;
+    pv[13 * ps] = pp[HBK_P_K_SLOW_1 * ldp];
+    pv[14 * ps] = pp[HBK_P_PERCOLATION * ldp];
+    pv[15 * ps] = pp[HBK_P_K_SLOW_2 * ldp];
+    pv[16 * ps] = pp[HBK_P_SNOW_ICE * ldp];
+}
+
+// Logger::Record (Logger.cpp:93-120) of one (set, unit, step): contents after Finalize and flux amounts, into the slots
+// of the record mask [slot][P][T][U]; NaN where the unit's structure variant has no such brick.
+__device__ __forceinline__ void recordStep(const KArgs& a, int pOut, int t, int u, const Hru& h, const StepOut& o, double fG,
+                                           double fGl, bool gv) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    double* base = a.rec + ((size_t)pOut * a.T + t) * a.U + u;
+    const size_t stride = (size_t)a.P * a.T * a.U;
+    int k = 0;
+#define HBK_REC(slot, value)                                   \
+    if (a.recordMask & (1ull << (slot))) {                     \
+        base[(size_t)k * stride] = (value);                    \
+        ++k;                                                   \
+    }
+    HBK_REC(HBK_R_GROUND_WATER, h.wG)
+    HBK_REC(HBK_R_GROUND_INFILTRATION, h.amtInfil)
+    HBK_REC(HBK_R_GROUND_RUNOFF, h.amtRest)
+    HBK_REC(HBK_R_GLACIER_WATER, gv ? h.wGl : nan)
+    HBK_REC(HBK_R_GLACIER_ICE, gv ? h.ice : nan)
+    HBK_REC(HBK_R_GLACIER_OUTFLOW, gv ? h.amtDep1 : nan)
+    HBK_REC(HBK_R_GLACIER_MELT, gv ? h.amtDep2 : nan)
+    HBK_REC(HBK_R_GROUND_SNOWPACK_WATER, 0.0)
+    HBK_REC(HBK_R_GROUND_SNOWPACK_SNOW, h.snowG)
+    HBK_REC(HBK_R_GROUND_SNOWPACK_MELT, h.amtMeltG)
+    HBK_REC(HBK_R_GLACIER_SNOWPACK_WATER, gv ? 0.0 : nan)
+    HBK_REC(HBK_R_GLACIER_SNOWPACK_SNOW, gv ? h.snowGl : nan)
+    HBK_REC(HBK_R_GLACIER_SNOWPACK_MELT, gv ? h.amtMeltGl : nan)
+    HBK_REC(HBK_R_SLOW_WATER, h.slow)
+    HBK_REC(HBK_R_SLOW_ET, o.amtEt)
+    HBK_REC(HBK_R_SLOW_OUTFLOW, o.amtOut)
+    HBK_REC(HBK_R_SLOW_OVERFLOW, o.amtOvf)
+    HBK_REC(HBK_R_SLOW_PERCOLATION, o.amtPerc)
+    HBK_REC(HBK_R_SLOW2_WATER, h.slow2)
+    HBK_REC(HBK_R_SLOW2_OUTFLOW, o.amtOut2)
+    HBK_REC(HBK_R_QUICK_WATER, h.quick)
+    HBK_REC(HBK_R_QUICK_RUNOFF, o.amtQ)
+    HBK_REC(HBK_R_FRACTION_GROUND, fG)
+    HBK_REC(HBK_R_FRACTION_GLACIER, gv ? fGl : nan)
+    HBK_REC(HBK_R_GLACIER_SNOWPACK_TRANSFO, gv ? h.amtSnowIce : nan)
+    HBK_REC(HBK_R_GROUND_SNOWPACK_SUBLIMATION, o.amtSubG)
+    HBK_REC(HBK_R_GLACIER_SNOWPACK_SUBLIMATION, gv ? o.amtSubGl : nan)
+#undef HBK_REC
+}
+
 // ---- main kernel ------------------------------------------------------------------------------------
 // Block = PB parameter sets x UB units (threads), time-multiplexed over a GROUP of G consecutive unit tiles:
 //   for each chunk of TC steps: for each tile of the group: [load state] TC steps [store state], add the tile's
@@ -235,28 +302,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
         const int ps = 1;
         const bool fill = validP;
 #endif
-        if (fill) {
-            const float* pp = a.params + p;
-            const float t0f = pp[HBK_P_TRANSITION_START * a.ldp], t1f = pp[HBK_P_TRANSITION_END * a.ldp];
-            pv[0 * ps] = t0f;
-            pv[1 * ps] = t1f;
-            pv[2 * ps] = 1.0 / (double)(t1f - t0f);
-            pv[3 * ps] = pp[HBK_P_RAIN_CORRECTION * a.ldp];
-            pv[4 * ps] = pp[HBK_P_SNOW_CORRECTION * a.ldp];
-            pv[5 * ps] = pp[HBK_P_GROUND_SNOW_DDF * a.ldp];
-            pv[6 * ps] = pp[HBK_P_GROUND_SNOW_TMELT * a.ldp];
-            pv[7 * ps] = pp[HBK_P_GLACIER_SNOW_DDF * a.ldp];
-            pv[8 * ps] = pp[HBK_P_GLACIER_SNOW_TMELT * a.ldp];
-            pv[9 * ps] = pp[HBK_P_ICE_DDF * a.ldp];
-            pv[10 * ps] = pp[HBK_P_ICE_TMELT * a.ldp];
-            const double capacity = pp[HBK_P_CAPACITY * a.ldp];
-            pv[11 * ps] = capacity;
-            pv[12 * ps] = (capacity == 0.0) ? kInvZeroCapacity : 1.0 / capacity;
-            pv[13 * ps] = pp[HBK_P_K_SLOW_1 * a.ldp];
-            pv[14 * ps] = pp[HBK_P_PERCOLATION * a.ldp];
-            pv[15 * ps] = pp[HBK_P_K_SLOW_2 * a.ldp];
-            pv[16 * ps] = pp[HBK_P_SNOW_ICE * a.ldp];
-        }
+        if (fill) fillPar(pv, ps, a.params + p, a.ldp);
         if (validP) {
             quickBase = a.params[p + (size_t)HBK_P_QUICK * a.ldp];
             par.quickV = quickBase;
@@ -517,47 +563,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
                         solveUnit<SOLVER, NSOIL>(h, par, pet, faW, dt, invDt, a.flags, o, err, unconverged);
                     }
 
-                    if (nRec && a.writeOutputs) {
-                        // Logger::Record (Logger.cpp:93-120): contents after Finalize and flux amounts
-                        const double nan = __longlong_as_double(0x7ff8000000000000LL);
-                        const bool gv = glacierVariant;
-                        double* base = a.rec + ((size_t)pOut * a.T + (t0 + tc)) * a.U + u;
-                        const size_t stride = (size_t)a.P * a.T * a.U;
-                        int k = 0;
-#define HBK_REC(slot, value)                                   \
-    if (a.recordMask & (1ull << (slot))) {                     \
-        base[(size_t)k * stride] = (value);                    \
-        ++k;                                                   \
-    }
-                        HBK_REC(HBK_R_GROUND_WATER, h.wG)
-                        HBK_REC(HBK_R_GROUND_INFILTRATION, h.amtInfil)
-                        HBK_REC(HBK_R_GROUND_RUNOFF, h.amtRest)
-                        HBK_REC(HBK_R_GLACIER_WATER, gv ? h.wGl : nan)
-                        HBK_REC(HBK_R_GLACIER_ICE, gv ? h.ice : nan)
-                        HBK_REC(HBK_R_GLACIER_OUTFLOW, gv ? h.amtDep1 : nan)
-                        HBK_REC(HBK_R_GLACIER_MELT, gv ? h.amtDep2 : nan)
-                        HBK_REC(HBK_R_GROUND_SNOWPACK_WATER, 0.0)
-                        HBK_REC(HBK_R_GROUND_SNOWPACK_SNOW, h.snowG)
-                        HBK_REC(HBK_R_GROUND_SNOWPACK_MELT, h.amtMeltG)
-                        HBK_REC(HBK_R_GLACIER_SNOWPACK_WATER, gv ? 0.0 : nan)
-                        HBK_REC(HBK_R_GLACIER_SNOWPACK_SNOW, gv ? h.snowGl : nan)
-                        HBK_REC(HBK_R_GLACIER_SNOWPACK_MELT, gv ? h.amtMeltGl : nan)
-                        HBK_REC(HBK_R_SLOW_WATER, h.slow)
-                        HBK_REC(HBK_R_SLOW_ET, o.amtEt)
-                        HBK_REC(HBK_R_SLOW_OUTFLOW, o.amtOut)
-                        HBK_REC(HBK_R_SLOW_OVERFLOW, o.amtOvf)
-                        HBK_REC(HBK_R_SLOW_PERCOLATION, o.amtPerc)
-                        HBK_REC(HBK_R_SLOW2_WATER, h.slow2)
-                        HBK_REC(HBK_R_SLOW2_OUTFLOW, o.amtOut2)
-                        HBK_REC(HBK_R_QUICK_WATER, h.quick)
-                        HBK_REC(HBK_R_QUICK_RUNOFF, o.amtQ)
-                        HBK_REC(HBK_R_FRACTION_GROUND, fG)
-                        HBK_REC(HBK_R_FRACTION_GLACIER, gv ? fGl : nan)
-                        HBK_REC(HBK_R_GLACIER_SNOWPACK_TRANSFO, gv ? h.amtSnowIce : nan)
-                        HBK_REC(HBK_R_GROUND_SNOWPACK_SUBLIMATION, o.amtSubG)
-                        HBK_REC(HBK_R_GLACIER_SNOWPACK_SUBLIMATION, gv ? o.amtSubGl : nan)
-#undef HBK_REC
-                    }
+                    if (nRec && a.writeOutputs) recordStep(a, pOut, t0 + tc, u, h, o, fG, fGl, glacierVariant);
                 }
                 // this thread's slot accumulates its units of the group's tiles in tile order (no race: own slot)
                 double* slot = slotCol + (size_t)tc * nThreads;
@@ -665,6 +671,242 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         a.blockTimes[3 * (size_t)blockIdx.x + 1] = t;
+    }
+}
+
+// ---- lateral kernel (transport:snow_slide) -----------------------------------------------------------
+// The snow slide couples the units of a parameter set INSIDE a time step: a snowpack that exceeds its holding depth hands
+// snow, instantaneously, to the snowpacks of the units it is connected to, and the reference processes the units in basin
+// order (Processor.cpp:237-276), so a receiver that comes later sees the snow in the same step. One thread therefore owns
+// one parameter set and walks its units in basin order, step by step; the unit state lives in the state arrays (element
+// (p, u) at u * P + p: the loads and stores of a warp's 32 sets are contiguous), the per-step arithmetic is the same
+// device code as everywhere else (directPhase with the slide hooked into the snowpack step, solveUnit). Parallelism is the
+// parameter axis only — the option is for glacier-evolution studies with one or a few hundred sets, not the ensemble path.
+struct LatArgs {
+    const int* off;        // [U + 1]: the connections of giver u are [off[u], off[u + 1]), in the order they were added
+    const int* recv;       // [nConn] receiving unit (> giver)
+    const double* weight;  // [nConn] share of the giver's sliding snow
+    const double* thr;     // [U][ldp] snow holding threshold [mm of snow depth] of (unit, set), evaluated on the host
+    double* pend;          // [2][U][P] snow received this step, not yet taken in (ground / glacier snowpack)
+    int skipGlaciers;      // the glacier snowpacks receive but do not give (SettingsModel.cpp:565-567)
+    const double* raw[HBK_N_VARS];  // forcing mode 0: the API layout [T][U]
+};
+
+template <int SOLVER, int NSOIL, bool GLACIER>
+__global__ void __launch_bounds__(128) hbkRunLateral(const KArgs a, const LatArgs L) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.P) return;
+    const int pOut = a.perm ? a.perm[p] : p;
+    Par par;
+    fillPar(par.v, 1, a.params + p, a.ldp);
+    const double quickBase = a.params[p + (size_t)HBK_P_QUICK * a.ldp];
+    double gT = 0, gP = 0, corr = 1;
+    if (a.forcingMode == 1) {
+        gT = a.gradT ? a.gradT[pOut] : a.gradTs;
+        gP = a.gradP ? a.gradP[pOut] : a.gradPs;
+        corr = a.corrP ? a.corrP[pOut] : a.corrPs;
+    }
+    const double dt = a.dt, invDt = 1.0 / a.dt;
+    const int nRec = __popcll(a.recordMask);
+    const float maxSnowDepth = a.params[p + (size_t)HBK_P_SLIDE_MAX_SNOW_DEPTH * a.ldp];
+    // AvoidUnrealisticAccumulation (ProcessLateralSnowSlide.cpp:120-134): 1.5 * max_snow_depth / (water / snow density)
+    const double accumulationLimit = 1.5 * maxSnowDepth / 4.0f;
+    const size_t PU = (size_t)a.P * a.U;
+    int err = 0, unconverged = 0;
+    for (int t = a.tBegin; t < a.tEnd; ++t) {
+        double q = 0.0, d1 = 0.0, d2 = 0.0;
+        for (int u = 0; u < a.U; ++u) {
+            // ---- unit constants (as hbkRunUnits loadUnit)
+            const double fa = a.hru[0 * a.ldu + u];
+            const double faW = (fa < 1.0) ? fa : 1.0;
+            const double area = a.hru[1 * a.ldu + u];
+            const double socontUnit = 3.174802103936398e-05 * 86400.0 * 1000.0;
+            par.quickV = (a.flags.quickKind == 0) ? quickBase * a.hru[2 * a.ldu + u] / area * socontUnit : quickBase;
+            const int unitFlags = a.hruFlags[u];
+            const bool gv = GLACIER && (unitFlags & 1);
+            if (a.flags.meltKind == HBK_MELT_DEGREE_DAY_ASPECT) {
+                const AspectFactors f3 = aspectFactors<GLACIER>(a.params, a.ldp, p, (unitFlags >> 1) & 3);
+                par.v[5] = f3.ground;
+                par.v[7] = f3.glacierSnow;
+                par.v[9] = f3.ice;
+            }
+            const long long fi = a.fracPerSet ? ((long long)p * a.U + u) : u;
+            const double fG = a.frac[fi], fGl = a.frac[a.fracLd + fi];
+            // ---- forcing
+            double precip, temp, pet, rad = 0.0;
+            if (a.forcingMode == 0) {
+                const size_t k = (size_t)t * a.U + u;
+                precip = L.raw[0][k];
+                temp = L.raw[1][k];
+                pet = L.raw[2][k];
+                if (a.nVars == 4) rad = L.raw[3][k];
+            } else {  // station series + fused spatialisation (forcing.py:1061-1113)
+                const double elev = a.hru[3 * a.ldu + u];
+                temp = a.forcing[1][t] + gT * (elev - a.zrefT) / 100;
+                precip = (a.forcing[0][t] * corr) * (1 + gP * (elev - a.zrefP) / 100);
+                precip = (precip < 0.0) ? 0.0 : precip;
+                pet = a.forcing[2][t];
+                pet = (pet < 0.0) ? 0.0 : pet;
+                if (a.nVars == 4) rad = a.forcing[3][t];
+            }
+            if (a.flags.meltKind == HBK_MELT_TEMPERATURE_INDEX) {
+                const AspectFactors f3 = radiationFactors<GLACIER>(a.params, a.ldp, p, rad);
+                par.v[5] = f3.ground;
+                par.v[7] = f3.glacierSnow;
+                par.v[9] = f3.ice;
+            }
+            double sublimG = 0.0, sublimGl = 0.0;
+            if (a.flags.sublimKind != 0) {
+                const double2 su = sublimationRates<GLACIER>(a.params, a.ldp, a.flags.sublimKind, p, pet);
+                sublimG = su.x;
+                sublimGl = su.y;
+            }
+            // ---- state
+            const size_t si = (size_t)p * a.sP + (size_t)u * a.sU;
+            Hru h;
+            h.snowG = a.state[HBK_S_GROUND_SNOW * a.lds + si];
+            h.wG = a.state[HBK_S_GROUND_WATER * a.lds + si];
+            h.slow = a.state[HBK_S_SLOW * a.lds + si];
+            h.slow2 = (NSOIL == 2) ? a.state[HBK_S_SLOW2 * a.lds + si] : 0.0;
+            h.quick = a.state[HBK_S_QUICK * a.lds + si];
+            h.amtInfil = a.state[HBK_S_AMT_INFILTRATION * a.lds + si];
+            h.amtRest = a.state[HBK_S_AMT_REST * a.lds + si];
+            h.amtMeltG = a.state[HBK_S_AMT_MELT_GROUND * a.lds + si];
+            if (GLACIER) {
+                h.snowGl = a.state[HBK_S_GLACIER_SNOW * a.lds + si];
+                h.wGl = a.state[HBK_S_GLACIER_WATER * a.lds + si];
+                h.ice = a.state[HBK_S_ICE * a.lds + si];
+                h.amtMeltGl = a.state[HBK_S_AMT_MELT_GLACIER * a.lds + si];
+                h.amtDep1 = a.state[HBK_S_AMT_DEPOSIT_RAIN_SNOWMELT * a.lds + si];
+                h.amtDep2 = a.state[HBK_S_AMT_DEPOSIT_ICEMELT * a.lds + si];
+                h.amtSnowIce = a.state[HBK_S_AMT_SNOW_ICE * a.lds + si];
+            } else {
+                h.snowGl = h.wGl = h.ice = h.amtMeltGl = h.amtDep1 = h.amtDep2 = h.amtSnowIce = 0.0;
+            }
+            // snow that earlier units of this step slid onto this unit's snowpacks
+            double* pendG = L.pend + (size_t)u * a.P + p;
+            double* pendGl = L.pend + PU + (size_t)u * a.P + p;
+            const double receivedG = *pendG, receivedGl = GLACIER ? *pendGl : 0.0;
+            *pendG = 0.0;
+            if (GLACIER) *pendGl = 0.0;
+
+            // ProcessLateralSnowSlide::GetRates + WaterContainer::ApplyConstraints + Process::ApplyChange for the slide
+            // process of one of this unit's snowpacks (fOrigin: area fraction of its land cover)
+            auto slideOf = [&](double fOrigin) {
+                return [&, fOrigin](double content, double stat, double inputsStatic, double& dyn, bool& tooHigh) {
+                    const int c0 = L.off[u], c1 = L.off[u + 1];
+                    if (c0 == c1) return;  // no connection: StoreRates({})
+                    const double swe = content + stat;  // GetContentWithChanges
+                    if (swe <= kPrecision) return;      // Process::GetChangeRates (Process.cpp:480-487): all rates 0
+                    const double snowDepth = swe * 4.0f;  // constants::waterDensity / constants::snowDensity, a float
+                    const double threshold = L.thr[(size_t)u * a.ldp + p];
+                    double excess = 0.0;
+                    if (snowDepth > threshold) excess = (snowDepth - threshold) / 4.0f;
+                    if (excess <= 0.0) return;
+                    if (excess > 1000.0) excess = 1000.0;
+                    // one output per (connection, snowpack of the receiving unit): ground, then glacier where the
+                    // receiver carries the glacier bricks (ModelBuilder.cpp:476-508); rate < 0 stands for "no such output"
+                    auto rateOf = [&](int k, int cover, double& fTarget) -> double {
+                        const int r = L.recv[k];
+                        if (cover == 1 && !(a.hruFlags[r] & 1)) return -1.0;
+                        const long long fr = a.fracPerSet ? ((long long)p * a.U + r) : r;
+                        fTarget = a.frac[cover * a.fracLd + fr];
+                        if (nearlyZero(fTarget, kPrecision)) return 0.0;
+                        double rate = excess * L.weight[k] * fTarget;
+                        if (maxSnowDepth > 0.0f) {  // AvoidUnrealisticAccumulation: the receiver's snow content
+                            const double targetSwe = a.state[(cover ? HBK_S_GLACIER_SNOW : HBK_S_GROUND_SNOW) * a.lds +
+                                                             (size_t)p * a.sP + (size_t)r * a.sU];
+                            if (targetSwe > accumulationLimit) rate = 0.0;
+                        }
+                        return rate;
+                    };
+                    const int nCovers = GLACIER ? 2 : 1;
+                    double outputs = 0.0;
+                    for (int k = c0; k < c1; ++k) {
+                        for (int cover = 0; cover < nCovers; ++cover) {
+                            double fTarget;
+                            const double rate = rateOf(k, cover, fTarget);
+                            if (rate < 0.0) continue;
+                            tooHigh = tooHigh || rate > 10000.0;
+                            outputs += rate;
+                        }
+                    }
+                    // WaterContainer::ApplyConstraints (WaterContainer.cpp:117-142) on the snow container
+                    const double change = -outputs;
+                    const double balance = content + inputsStatic + change * dt;
+                    const bool limited = change < 0.0 && balance < 0.0;
+                    const double diff = balance / dt;
+                    for (int k = c0; k < c1; ++k) {
+                        for (int cover = 0; cover < nCovers; ++cover) {
+                            double fTarget = 0.0;
+                            double rate = rateOf(k, cover, fTarget);
+                            if (rate < 0.0) continue;
+                            if (limited && !nearlyZero(rate, kEpsD)) {
+                                rate = (fabs(diff - change) <= kPrecision) ? 0.0 : rate + diff * fabs(rate / outputs);
+                            }
+                            rate = (rate < 0.0) ? 0.0 : rate;  // Process::ApplyChange (Process.cpp:495-508)
+                            if (rate > kPrecision) {
+                                const double amount = rate * dt;
+                                dyn -= amount;
+                                // ProcessLateral::ComputeFractionAreas (ProcessLateral.cpp:67-76) -> the flux's weight;
+                                // FluxToBrickInstantaneous::UpdateFlux books it into the receiver's static change
+                                const int r = L.recv[k];
+                                const double fractionAreas = (area * fOrigin) / (a.hru[1 * a.ldu + r] * fTarget);
+                                const double booked = (fractionAreas != 1.0) ? amount * fractionAreas : amount;
+                                L.pend[(size_t)cover * PU + (size_t)r * a.P + p] += booked;
+                            }
+                        }
+                    }
+                };
+            };
+            auto slideG = slideOf(GLACIER ? fG : 1.0);
+            auto slideGlAll = slideOf(fGl);
+            auto slideGl = [&](double content, double stat, double inputsStatic, double& dyn, bool& tooHigh) {
+                if (!L.skipGlaciers) slideGlAll(content, stat, inputsStatic, dyn, tooHigh);
+            };
+            StepOut o;
+            directPhase<GLACIER, true, decltype(slideG), decltype(slideGl)>(
+                h, par, precip, temp, dt, invDt, fa, fG, fGl, gv, a.flags, o, err,
+                (GLACIER && a.swatFactor) ? a.swatFactor[t] : 0.0, sublimG, sublimGl, receivedG, receivedGl, slideG, slideGl);
+            if constexpr (SOLVER == 3) {
+                solveUnitSequential<NSOIL>(h, par, pet, faW, dt, invDt, a.flags, o, err);
+            } else {
+                solveUnit<SOLVER, NSOIL>(h, par, pet, faW, dt, invDt, a.flags, o, err, unconverged);
+            }
+            if (nRec && a.writeOutputs) recordStep(a, pOut, t, u, h, o, fG, fGl, gv);
+            // ---- state back
+            a.state[HBK_S_GROUND_SNOW * a.lds + si] = h.snowG;
+            a.state[HBK_S_GROUND_WATER * a.lds + si] = h.wG;
+            a.state[HBK_S_SLOW * a.lds + si] = h.slow;
+            if (NSOIL == 2) a.state[HBK_S_SLOW2 * a.lds + si] = h.slow2;
+            a.state[HBK_S_QUICK * a.lds + si] = h.quick;
+            a.state[HBK_S_AMT_INFILTRATION * a.lds + si] = h.amtInfil;
+            a.state[HBK_S_AMT_REST * a.lds + si] = h.amtRest;
+            a.state[HBK_S_AMT_MELT_GROUND * a.lds + si] = h.amtMeltG;
+            if (GLACIER) {
+                a.state[HBK_S_GLACIER_SNOW * a.lds + si] = h.snowGl;
+                a.state[HBK_S_GLACIER_WATER * a.lds + si] = h.wGl;
+                a.state[HBK_S_ICE * a.lds + si] = h.ice;
+                a.state[HBK_S_AMT_MELT_GLACIER * a.lds + si] = h.amtMeltGl;
+                a.state[HBK_S_AMT_DEPOSIT_RAIN_SNOWMELT * a.lds + si] = h.amtDep1;
+                a.state[HBK_S_AMT_DEPOSIT_ICEMELT * a.lds + si] = h.amtDep2;
+                a.state[HBK_S_AMT_SNOW_ICE * a.lds + si] = h.amtSnowIce;
+            }
+            // SubBasin::ComputeOutletDischarge (SubBasin.cpp:322-329): units in basin order
+            q += o.q;
+            d1 += o.dep1;
+            d2 += o.dep2;
+        }
+        if (a.writeOutputs) a.outQ[(size_t)pOut * a.ldt + t] = q;
+        if (GLACIER) {
+            a.outD1[(size_t)p * a.ldt + t] = d1;
+            a.outD2[(size_t)p * a.ldt + t] = d2;
+        }
+    }
+    if (err) atomicOr(a.err, err);
+    if (unconverged) {
+        atomicAdd(a.unconverged, (unsigned long long)unconverged);
+        atomicAdd(&a.unconvergedPerSet[p], unconverged);
     }
 }
 
@@ -1126,6 +1368,17 @@ struct hbk_engine {
     bool haveRaw[HBK_N_VARS] = {}, haveStation[HBK_N_VARS] = {};
     int nVars() const { return st.melt_kind == HBK_MELT_TEMPERATURE_INDEX ? 4 : 3; }
     std::vector<int> hAspect;  // HBK_ASPECT_* per unit (hbk_set_unit_aspect); empty = not given
+    // transport:snow_slide (hbk_set_lateral_connections)
+    std::vector<int> hLatOff, hLatRecv;
+    std::vector<double> hLatWeight;
+    std::vector<float> hSlopeDeg;
+    std::vector<float> hParamsT;  // [HBK_N_PARAMS][ldp], the device layout (internal set order)
+    int* dLatOff = nullptr;
+    int* dLatRecv = nullptr;
+    double* dLatWeight = nullptr;
+    double* dLatThr = nullptr;   // [U][ldp]
+    double* dLatPend = nullptr;  // [2][U][P]
+    bool latThrDirty = true;
     int tiledUB = 0;
     double* dGradT = nullptr;
     double* dGradP = nullptr;
@@ -1281,6 +1534,13 @@ void chooseShape(hbk_engine* e) {
         e->nGroups = 1;
     }
     e->stateLaneP = e->PB == 32;
+    if (e->st.snow_slide_kind != HBK_SNOW_SLIDE_NONE) {
+        // hbkRunLateral: one thread per parameter set, the sets of a warp side by side in the state arrays; no unit tiles
+        e->stateLaneP = true;
+        e->G = e->nUTiles;
+        e->nGroups = 1;
+        e->clusterMode = false;
+    }
     const int nq = e->st.has_glacier ? 3 : 1;
     // chunk length: shared memory per block small enough for HBK_MIN_BLOCKS blocks per SM
     const size_t budget = (size_t)(220 * 1024) / minBlocks - 1024;
@@ -1344,6 +1604,23 @@ KernelFn pickKernel(const hbk_structure& st, bool ens) {
     }
 }
 
+template <int SOLVER, int NSOIL>
+void lateralGlacier(bool glacier, int blocks, cudaStream_t stream, const KArgs& a, const LatArgs& L) {
+    if (glacier) {
+        hbkRunLateral<SOLVER, NSOIL, true><<<blocks, 128, 0, stream>>>(a, L);
+    } else {
+        hbkRunLateral<SOLVER, NSOIL, false><<<blocks, 128, 0, stream>>>(a, L);
+    }
+}
+template <int SOLVER>
+void lateralSoil(int nSoil, bool glacier, int blocks, cudaStream_t stream, const KArgs& a, const LatArgs& L) {
+    if (nSoil == 2) {
+        lateralGlacier<SOLVER, 2>(glacier, blocks, stream, a, L);
+    } else {
+        lateralGlacier<SOLVER, 1>(glacier, blocks, stream, a, L);
+    }
+}
+
 // TimeMachine::GetCurrentDayOfYear (TimeMachine.cpp:87-98) of the civil date of floor(mjd).
 int dayOfYear(double mjd) {
     if (mjd <= 0) return 1;
@@ -1391,6 +1668,9 @@ int ensureSetBuffers(hbk_engine* e, int P) {
     freeDev(e->dFracSet);
     freeDev(e->dDhLastRow);
     freeDev(e->dStale);
+    freeDev(e->dLatThr);
+    freeDev(e->dLatPend);
+    e->latThrDirty = true;
     freeDev(e->dStaleSeg);
     e->staleSegN = 0;
     freeDev(e->dShardWE);
@@ -1463,6 +1743,10 @@ int hbk_engine_create(const hbk_structure* st, int32_t n_units, int32_t n_steps,
         return bail(HBK_E_ARG, "unknown sublimation_kind");
     if (st->melt_kind < HBK_MELT_DEGREE_DAY || st->melt_kind > HBK_MELT_TEMPERATURE_INDEX)
         return bail(HBK_E_ARG, "unknown melt_kind");
+    if (st->snow_slide_kind < HBK_SNOW_SLIDE_NONE || st->snow_slide_kind > HBK_SNOW_SLIDE_ALL)
+        return bail(HBK_E_ARG, "unknown snow_slide_kind");
+    if (HBK_PAR_SHARED && st->snow_slide_kind != HBK_SNOW_SLIDE_NONE)
+        return bail(HBK_E_UNSUPPORTED, "this build (HBK_PAR_SHARED) has no transport:snow_slide");
     if (HBK_PAR_SHARED && st->melt_kind != HBK_MELT_DEGREE_DAY)
         return bail(HBK_E_UNSUPPORTED, "this build (HBK_PAR_SHARED) only has melt:degree_day");
     if (st->has_glacier && st->snow_ice_kind == HBK_SNOW_ICE_SWAT) {
@@ -1531,6 +1815,11 @@ void hbk_engine_destroy(hbk_engine* e) {
     freeDev(e->dUnconv);
     freeDev(e->dUnconvSet);
     freeDev(e->dQueue);
+    freeDev(e->dLatOff);
+    freeDev(e->dLatRecv);
+    freeDev(e->dLatWeight);
+    freeDev(e->dLatThr);
+    freeDev(e->dLatPend);
     freeDev(e->dShardStage);
     freeDev(e->dStaleSeg);
     freeDev(e->dShardWE);
@@ -1652,6 +1941,81 @@ int hbk_set_parameters(hbk_engine* e, int32_t n_sets, const float* values) {
     }
     HBK_CUDA(cudaMemcpyAsync(e->dParams, t.data(), sizeof(float) * t.size(), cudaMemcpyHostToDevice, e->stream));
     HBK_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->st.snow_slide_kind != HBK_SNOW_SLIDE_NONE) {
+        e->hParamsT.swap(t);
+        e->latThrDirty = true;
+    }
+    return HBK_OK;
+}
+
+int hbk_set_lateral_connections(hbk_engine* e, int32_t n, const int32_t* giver, const int32_t* receiver,
+                                const double* fraction, const float* slope_degrees) {
+    if (!e || n < 0 || (n > 0 && (!giver || !receiver || !fraction)) || !slope_degrees) return HBK_E_ARG;
+    if (e->st.snow_slide_kind == HBK_SNOW_SLIDE_NONE)
+        return fail(e, HBK_E_STATE, "lateral connections are only used by structures with transport:snow_slide");
+    HBK_CUDA(cudaSetDevice(e->device));
+    const int U = e->U;
+    std::vector<std::vector<std::pair<int, double>>> per(U);
+    for (int i = 0; i < n; ++i) {
+        if (giver[i] < 0 || giver[i] >= U || receiver[i] < 0 || receiver[i] >= U)
+            return fail(e, HBK_E_ARG, "lateral connection: hydro unit index out of range");
+        if (receiver[i] <= giver[i])
+            return fail(e, HBK_E_UNSUPPORTED, "lateral connection: the receiving unit must come after the giving unit in "
+                                              "basin order (snow slides downhill in a basin sorted by elevation)");
+        per[giver[i]].push_back({receiver[i], fraction[i]});
+    }
+    e->hLatOff.assign(U + 1, 0);
+    e->hLatRecv.clear();
+    e->hLatWeight.clear();
+    for (int u = 0; u < U; ++u) {
+        for (auto& c : per[u]) {
+            e->hLatRecv.push_back(c.first);
+            e->hLatWeight.push_back(c.second);
+        }
+        e->hLatOff[u + 1] = (int)e->hLatRecv.size();
+    }
+    e->hSlopeDeg.assign(slope_degrees, slope_degrees + U);
+    freeDev(e->dLatOff);
+    freeDev(e->dLatRecv);
+    freeDev(e->dLatWeight);
+    const size_t nc = std::max<size_t>(e->hLatRecv.size(), 1);
+    HBK_CUDA(cudaMalloc(&e->dLatOff, sizeof(int) * (U + 1)));
+    HBK_CUDA(cudaMalloc(&e->dLatRecv, sizeof(int) * nc));
+    HBK_CUDA(cudaMalloc(&e->dLatWeight, sizeof(double) * nc));
+    HBK_CUDA(cudaMemcpy(e->dLatOff, e->hLatOff.data(), sizeof(int) * (U + 1), cudaMemcpyHostToDevice));
+    if (!e->hLatRecv.empty()) {
+        HBK_CUDA(cudaMemcpy(e->dLatRecv, e->hLatRecv.data(), sizeof(int) * e->hLatRecv.size(), cudaMemcpyHostToDevice));
+        HBK_CUDA(cudaMemcpy(e->dLatWeight, e->hLatWeight.data(), sizeof(double) * e->hLatWeight.size(),
+                            cudaMemcpyHostToDevice));
+    }
+    e->latThrDirty = true;
+    return HBK_OK;
+}
+
+// Snow holding threshold [mm of snow depth] of every (unit, parameter set), ProcessLateralSnowSlide.cpp:62-78, with the
+// host libm: `*_coeff * pow(slope, *_exp)` resolves to the C pow(double, double) on the promoted floats.
+static int uploadSlideThresholds(hbk_engine* e) {
+    const int U = e->U, ldp = e->ldp;
+    std::vector<double> thr((size_t)U * ldp, 0.0);
+    auto par = [&](int slot, int p) { return e->hParamsT[(size_t)slot * ldp + p]; };
+    for (int u = 0; u < U; ++u) {
+        const float slopeDeg = e->hSlopeDeg[u];
+        for (int p = 0; p < e->P; ++p) {
+            const float coeff = par(HBK_P_SLIDE_COEFF, p), expo = par(HBK_P_SLIDE_EXP, p);
+            const float minSlope = par(HBK_P_SLIDE_MIN_SLOPE, p), maxSlope = par(HBK_P_SLIDE_MAX_SLOPE, p);
+            const float minHolding = par(HBK_P_SLIDE_MIN_HOLDING_DEPTH, p), maxDepth = par(HBK_P_SLIDE_MAX_SNOW_DEPTH, p);
+            const float slope = std::max(slopeDeg, minSlope);
+            const double meters = coeff * ::pow((double)slope, (double)expo);
+            double threshold = meters * 1000.0;
+            if (slopeDeg > maxSlope) threshold = minHolding;
+            threshold = std::max<double>(threshold, minHolding);
+            if (maxDepth > 0.0f) threshold = std::min<double>(threshold, maxDepth);
+            thr[(size_t)u * ldp + p] = threshold;
+        }
+    }
+    if (!e->dLatThr) HBK_CUDA(cudaMalloc(&e->dLatThr, sizeof(double) * thr.size()));
+    HBK_CUDA(cudaMemcpy(e->dLatThr, thr.data(), sizeof(double) * thr.size(), cudaMemcpyHostToDevice));
+    e->latThrDirty = false;
     return HBK_OK;
 }
 
@@ -1982,70 +2346,8 @@ static void launchBasinStores(hbk_engine* e, int tBegin, int tEnd, const double*
 #undef HBK_BASIN
 }
 
-static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs) {
-    const bool tiled = e->haveRaw[0];
-    KArgs a{};
-    a.P = e->P;
-    a.U = e->U;
-    a.tBegin = tBegin;
-    a.tEnd = tEnd;
-    a.PB = e->PB;
-    a.UB = e->UB;
-    a.TC = e->TC;
-    a.nUTiles = e->nUTiles;
-    a.G = e->G;
-    a.nGroups = e->nGroups;
-    a.clusterMode = e->clusterMode ? 1 : 0;
-    a.flags.quickKind = e->st.quick_kind;
-    a.flags.slowOrder = e->st.slow_process_order;
-    a.flags.splitKind = e->st.splitter_kind;
-    a.flags.iceInfinite = e->st.glacier_infinite_storage;
-    a.flags.snowIceKind = e->st.has_glacier ? e->st.snow_ice_kind : 0;
-    a.flags.sublimKind = e->st.sublimation_kind;
-    a.flags.seqKind = e->st.solver >= HBK_SOLVER_CRANK_NICOLSON ? e->st.solver - HBK_SOLVER_CRANK_NICOLSON : 0;
-    a.flags.meltKind = e->st.melt_kind;
-    a.nVars = e->nVars();
-    a.swatFactor = (a.flags.snowIceKind == HBK_SNOW_ICE_SWAT) ? e->dSwatFactor : nullptr;
-    a.flags.noMeltWhenSnow = e->st.glacier_no_melt_when_snow_cover;
-    a.dt = e->st.time_step_days;
-    a.params = e->dParams;
-    a.ldp = e->ldp;
-    a.hru = e->dHru;
-    a.hruFlags = e->dHruFlags;
-    a.ldu = e->ldu;
-    a.frac = e->fracPerSet ? e->dFracSet : e->dFrac;
-    a.fracPerSet = e->fracPerSet;
-    a.fracLd = e->fracPerSet ? (long long)e->P * e->U : e->U;
-    a.forcingMode = tiled ? 0 : 1;
-    for (int v = 0; v < a.nVars; ++v) a.forcing[v] = tiled ? e->dForcingTiled[v] : e->dStation[v];
-    a.tld = e->tld;
-    a.gradT = e->dGradT;
-    a.gradP = e->dGradP;
-    a.corrP = e->dCorrP;
-    a.gradTs = e->gradTs;
-    a.gradPs = e->gradPs;
-    a.corrPs = e->corrPs;
-    a.zrefT = e->zrefT;
-    a.zrefP = e->zrefP;
-    a.state = e->dState;
-    a.lds = (long long)e->P * e->U;
-    a.sP = e->stateLaneP ? 1 : e->U;
-    a.sU = e->stateLaneP ? e->P : 1;
-    const bool multi = e->nGroups > 1;
-    a.outQ = multi ? e->dPartQ : e->dOutlet;
-    a.outD1 = multi ? e->dPartD1 : e->dD1;
-    a.outD2 = multi ? e->dPartD2 : e->dD2;
-    a.ldt = e->ldt;
-    a.writeOutputs = writeOutputs ? 1 : 0;
-    a.recordMask = e->recordMask;
-    a.rec = e->dRec;
-    a.T = e->T;
-    a.err = e->dErr;
-    a.unconverged = e->dUnconv;
-    a.unconvergedPerSet = e->dUnconvSet;
-    a.perm = e->dPerm;
-    a.outQFinal = multi ? 0 : 1;
-
+// The tiled unit kernel (hbkRunUnits) over one segment.
+static int launchUnitKernel(hbk_engine* e, KArgs& a, bool tiled, int tBegin, int tEnd) {
     const bool ens = e->PB == 32 && e->UB == 4 && e->TC == HBK_ENS_TC && !tiled && !e->clusterMode && a.nVars == 3 &&
                      !std::getenv("HBK_NO_ENS_SHAPE");
     KernelFn fn = pickKernel(e->st, ens);
@@ -2130,6 +2432,103 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
             }
         }
         cudaFree(dTimes);
+    }
+    return HBK_OK;
+}
+
+// transport:snow_slide: the sequential-over-units kernel (hbkRunLateral), one thread per parameter set.
+static int launchLateralKernel(hbk_engine* e, KArgs& a) {
+    LatArgs L{};
+    L.off = e->dLatOff;
+    L.recv = e->dLatRecv;
+    L.weight = e->dLatWeight;
+    L.thr = e->dLatThr;
+    L.pend = e->dLatPend;
+    L.skipGlaciers = e->st.snow_slide_kind == HBK_SNOW_SLIDE_SKIP_GLACIERS ? 1 : 0;
+    for (int v = 0; v < a.nVars; ++v) L.raw[v] = e->dForcingRaw[v];
+    const int blocks = (e->P + 127) / 128;
+    const bool glacier = e->st.has_glacier != 0;
+    switch (e->st.solver) {
+        case HBK_SOLVER_EULER: lateralSoil<0>(e->st.n_soil_stores, glacier, blocks, e->stream, a, L); break;
+        case HBK_SOLVER_HEUN: lateralSoil<1>(e->st.n_soil_stores, glacier, blocks, e->stream, a, L); break;
+        case HBK_SOLVER_RK4: lateralSoil<2>(e->st.n_soil_stores, glacier, blocks, e->stream, a, L); break;
+        default: lateralSoil<3>(e->st.n_soil_stores, glacier, blocks, e->stream, a, L); break;
+    }
+    e->lastLaunches++;
+    HBK_CUDA(cudaGetLastError());
+    return HBK_OK;
+}
+
+static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs) {
+    const bool tiled = e->haveRaw[0];
+    KArgs a{};
+    a.P = e->P;
+    a.U = e->U;
+    a.tBegin = tBegin;
+    a.tEnd = tEnd;
+    a.PB = e->PB;
+    a.UB = e->UB;
+    a.TC = e->TC;
+    a.nUTiles = e->nUTiles;
+    a.G = e->G;
+    a.nGroups = e->nGroups;
+    a.clusterMode = e->clusterMode ? 1 : 0;
+    a.flags.quickKind = e->st.quick_kind;
+    a.flags.slowOrder = e->st.slow_process_order;
+    a.flags.splitKind = e->st.splitter_kind;
+    a.flags.iceInfinite = e->st.glacier_infinite_storage;
+    a.flags.snowIceKind = e->st.has_glacier ? e->st.snow_ice_kind : 0;
+    a.flags.sublimKind = e->st.sublimation_kind;
+    a.flags.seqKind = e->st.solver >= HBK_SOLVER_CRANK_NICOLSON ? e->st.solver - HBK_SOLVER_CRANK_NICOLSON : 0;
+    a.flags.meltKind = e->st.melt_kind;
+    a.nVars = e->nVars();
+    a.swatFactor = (a.flags.snowIceKind == HBK_SNOW_ICE_SWAT) ? e->dSwatFactor : nullptr;
+    a.flags.noMeltWhenSnow = e->st.glacier_no_melt_when_snow_cover;
+    a.dt = e->st.time_step_days;
+    a.params = e->dParams;
+    a.ldp = e->ldp;
+    a.hru = e->dHru;
+    a.hruFlags = e->dHruFlags;
+    a.ldu = e->ldu;
+    a.frac = e->fracPerSet ? e->dFracSet : e->dFrac;
+    a.fracPerSet = e->fracPerSet;
+    a.fracLd = e->fracPerSet ? (long long)e->P * e->U : e->U;
+    a.forcingMode = tiled ? 0 : 1;
+    for (int v = 0; v < a.nVars; ++v) a.forcing[v] = tiled ? e->dForcingTiled[v] : e->dStation[v];
+    a.tld = e->tld;
+    a.gradT = e->dGradT;
+    a.gradP = e->dGradP;
+    a.corrP = e->dCorrP;
+    a.gradTs = e->gradTs;
+    a.gradPs = e->gradPs;
+    a.corrPs = e->corrPs;
+    a.zrefT = e->zrefT;
+    a.zrefP = e->zrefP;
+    a.state = e->dState;
+    a.lds = (long long)e->P * e->U;
+    a.sP = e->stateLaneP ? 1 : e->U;
+    a.sU = e->stateLaneP ? e->P : 1;
+    const bool multi = e->nGroups > 1;
+    a.outQ = multi ? e->dPartQ : e->dOutlet;
+    a.outD1 = multi ? e->dPartD1 : e->dD1;
+    a.outD2 = multi ? e->dPartD2 : e->dD2;
+    a.ldt = e->ldt;
+    a.writeOutputs = writeOutputs ? 1 : 0;
+    a.recordMask = e->recordMask;
+    a.rec = e->dRec;
+    a.T = e->T;
+    a.err = e->dErr;
+    a.unconverged = e->dUnconv;
+    a.unconvergedPerSet = e->dUnconvSet;
+    a.perm = e->dPerm;
+    a.outQFinal = multi ? 0 : 1;
+
+    if (e->st.snow_slide_kind != HBK_SNOW_SLIDE_NONE) {
+        int rc = launchLateralKernel(e, a);
+        if (rc) return rc;
+    } else {
+        int rc = launchUnitKernel(e, a, tiled, tBegin, tEnd);
+        if (rc) return rc;
     }
 
     if (writeOutputs && multi) {
@@ -2240,6 +2639,12 @@ int hbk_run(hbk_engine* e) {
                                             "(hbk_set_delta_h_shard_totals)");
     }
     e->shardSegments.clear();
+    const bool lateral = e->st.snow_slide_kind != HBK_SNOW_SLIDE_NONE;
+    if (lateral) {
+        if (!e->dLatOff)
+            return fail(e, HBK_E_STATE, "transport:snow_slide needs the lateral connections (hbk_set_lateral_connections)");
+        if (e->shard) return fail(e, HBK_E_UNSUPPORTED, "transport:snow_slide couples the units: no unit shards");
+    }
     HBK_CUDA(cudaSetDevice(e->device));
     chooseShape(e);
     e->lastLaunches = 0;
@@ -2279,7 +2684,15 @@ int hbk_run(hbk_engine* e) {
         if (recBytes) HBK_CUDA(cudaMalloc(&e->dRec, recBytes));
         e->recBytes = recBytes;
     }
-    if (tiled && e->tiledUB != e->UB) {
+    if (lateral) {
+        if (e->latThrDirty || !e->dLatThr) {
+            int rcT = uploadSlideThresholds(e);
+            if (rcT) return rcT;
+        }
+        if (!e->dLatPend) HBK_CUDA(cudaMalloc(&e->dLatPend, sizeof(double) * 2 * (size_t)e->P * e->U));
+        HBK_CUDA(cudaMemsetAsync(e->dLatPend, 0, sizeof(double) * 2 * (size_t)e->P * e->U, e->stream));
+    }
+    if (tiled && !lateral && e->tiledUB != e->UB) {
         for (int v = 0; v < e->nVars(); ++v) {
             freeDev(e->dForcingTiled[v]);
             const size_t n = (size_t)e->nUTiles * e->tld * e->UB;

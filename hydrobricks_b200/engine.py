@@ -24,6 +24,7 @@ QUICK_SOCONT, QUICK_LINEAR = 0, 1
 SPLIT_LINEAR, SPLIT_THRESHOLD = 0, 1
 SNOW_ICE_NONE, SNOW_ICE_CONSTANT, SNOW_ICE_SWAT = 0, 1, 2
 SUBLIMATION_NONE, SUBLIMATION_CONSTANT, SUBLIMATION_PET = 0, 1, 2
+SNOW_SLIDE_NONE, SNOW_SLIDE_SKIP_GLACIERS, SNOW_SLIDE_ALL = 0, 1, 2
 MELT_DEGREE_DAY, MELT_DEGREE_DAY_ASPECT, MELT_TEMPERATURE_INDEX = 0, 1, 2
 MELT_KIND = {"melt:degree_day": 0, "melt:degree_day_aspect": 1, "melt:temperature_index": 2}
 # HydroUnit property "aspect_class" (ProcessMeltDegreeDayAspect.cpp:38-58) -> HBK_ASPECT_*
@@ -36,6 +37,7 @@ PARAM_SLOTS = [
     "percolation", "k_slow_2", "quick", "k_snow", "k_ice", "snow_ice",
     "ground_sublimation", "glacier_sublimation",
     "ground_snow_melt_b", "ground_snow_melt_c", "glacier_snow_melt_b", "glacier_snow_melt_c", "ice_melt_b", "ice_melt_c",
+    "slide_coeff", "slide_exp", "slide_min_slope", "slide_max_slope", "slide_min_holding_depth", "slide_max_snow_depth",
 ]
 N_PARAMS = len(PARAM_SLOTS)
 RECORD_SLOTS = [
@@ -69,6 +71,8 @@ class HbkStructure(ctypes.Structure):
         ("start_mjd", ctypes.c_double),
         ("sublimation_kind", ctypes.c_int32),
         ("melt_kind", ctypes.c_int32),
+        ("snow_slide_kind", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
     ]
 
 
@@ -103,6 +107,7 @@ def load_library():
     L.hbk_last_error.restype = ctypes.c_char_p
     L.hbk_set_units.argtypes = [vp, dp, dp, fp, ip, dp, dp]
     L.hbk_set_unit_aspect.argtypes = [vp, ip]
+    L.hbk_set_lateral_connections.argtypes = [vp, i32, ip, ip, dp, fp]
     L.hbk_set_parameters.argtypes = [vp, i32, fp]
     L.hbk_set_forcing.argtypes = [vp, i32, dp]
     L.hbk_set_station_forcing.argtypes = [vp, i32, dp, dbl, dbl, dp, dbl, dp]
@@ -223,6 +228,18 @@ class Engine:
         a = np.ascontiguousarray(a, dtype=np.int32)
         assert a.shape == (self.n_units,)
         self._check(self.L.hbk_set_unit_aspect(self.h, a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+
+    def set_lateral_connections(self, givers, receivers, fractions, slope_degrees):
+        """SettingsBasin::AddLateralConnection, in the order added: unit positions (basin order) and the share of the
+        giver's sliding snow; slope_degrees[n_units] float32 (transport:snow_slide)."""
+        i32p = ctypes.POINTER(ctypes.c_int32)
+        g = np.ascontiguousarray(givers, dtype=np.int32)
+        r = np.ascontiguousarray(receivers, dtype=np.int32)
+        f = np.ascontiguousarray(fractions, dtype=np.float64)
+        s = np.ascontiguousarray(slope_degrees, dtype=np.float32)
+        assert g.shape == r.shape == f.shape and s.shape == (self.n_units,)
+        self._check(self.L.hbk_set_lateral_connections(self.h, len(g), g.ctypes.data_as(i32p), r.ctypes.data_as(i32p),
+                                                       _dptr(f), s.ctypes.data_as(ctypes.POINTER(ctypes.c_float))))
 
     def set_parameters(self, values):
         v = np.ascontiguousarray(values, dtype=np.float32)

@@ -119,7 +119,7 @@ class Socont:
             s.generate_snowpacks(self.options["snow_melt_process"])
             if self.options["snow_ice_transformation"]:  # model_settings.py:258-259
                 s.add_snow_ice_transformation(self.options["snow_ice_transformation"])
-            if self.options["snow_redistribution"]:  # model_settings.py:260-261; refused by the B200 host modules
+            if self.options["snow_redistribution"]:  # model_settings.py:260-261
                 s.add_snow_redistribution(self.options["snow_redistribution"],
                                           self.options["snow_redistribution_skip_glaciers"])
             if self.options["snow_sublimation_process"]:  # model_settings.py:262-263
@@ -205,6 +205,9 @@ class Socont:
                 basin.add_hydro_unit_property_str("aspect_class", u["aspect_class"])
             for name, frac in u["land_covers"]:
                 basin.add_land_cover(name, "", frac)
+        for u in self.units:  # hydro_units.py set_connectivity: (receiver position in basin order, fraction)
+            for receiver, fraction in u.get("lateral", []):
+                basin.add_lateral_connection(u["id"], self.units[receiver]["id"], fraction, "snow_slide")
         self.model = self.backend.ModelHydro()
         try:
             self.model.init_with_basin(self.settings, basin, device)

@@ -10,6 +10,7 @@ core/tests/src/helpers.cpp:9-107) by the ROLE of each brick, not by its name:
   optional glacier land cover {outflow:direct -> B1 (instantaneous), melt:<kind> -> B2 (instantaneous)}
   one snowpack per cover      {melt:<kind> -> cover}      <kind> = degree_day | degree_day_aspect | temperature_index,
                                                           the same on every snowpack and on the ice (socont.py:141)
+                              [+ transform:snow_ice_* on a glacier] [+ transport:snow_slide -> lateral] [+ sublimation:*]
   S  storage, capacity        {et:socont, outflow:linear -> outlet, overflow -> outlet, [percolation:constant -> S2]}
   S2 storage                  {outflow:linear -> outlet}
   Q  storage                  {runoff:socont -> outlet | outflow:linear -> outlet}
@@ -175,6 +176,8 @@ class CompiledStructure:
 
         sublim_kinds = {"sublimation:constant": _e.SUBLIMATION_CONSTANT, "sublimation:pet": _e.SUBLIMATION_PET}
         st.melt_kind = -1
+        st.snow_slide_kind = _e.SNOW_SLIDE_NONE
+        slide_on = {}  # snowpack name -> its transport:snow_slide process
 
         def set_melt(component, proc, slot_a, slot_tm, slot_b, slot_c):
             """The melt process of a snowpack or of the glacier ice: its kind (one per structure) and its parameters —
@@ -216,6 +219,14 @@ class CompiledStructure:
                     out = transfo["outputs"]
                     ok = len(out) == 1 and out[0]["target"] == cover["name"] and out[0]["flux_type"] == "ice" and \
                         not out[0]["instantaneous"] and not out[0]["static"]
+                if ok and rest and rest[0]["kind"] == "transport:snow_slide":
+                    # SettingsModel::AddSnowRedistribution (SettingsModel.cpp:560-572): instantaneous snow fluxes to
+                    # the snowpacks of the laterally connected units
+                    slide = rest.pop(0)
+                    out = slide["outputs"]
+                    ok = len(out) == 1 and out[0]["target"] == "lateral" and out[0]["flux_type"] == "snow" and \
+                        out[0]["instantaneous"]
+                    slide_on[sps[0]["name"]] = slide
                 if ok and rest and rest[0]["kind"] in sublim_kinds:
                     # SettingsModel::AddSnowpackSublimation (SettingsModel.cpp:586-598): no target = to the atmosphere
                     sublim = rest.pop(0)
@@ -304,6 +315,25 @@ class CompiledStructure:
                 self._set(slot, name, "response_factor", _params(bb["processes"][0])["response_factor"])
         if sorted(snow_targets or []) != sorted(snowpacks):
             raise UnsupportedStructure("snow must go to the snowpack of every land cover")
+        if slide_on:
+            # the snowpacks of the generic cover always slide, those of the glacier unless skipGlaciers; one set of
+            # parameters for every sliding snowpack (ProcessLateralSnowSlide.cpp:24-31)
+            if gsp is None or gsp["name"] not in slide_on:
+                raise UnsupportedStructure("transport:snow_slide must be on the snowpack of the generic land cover")
+            st.snow_slide_kind = _e.SNOW_SLIDE_ALL if len(slide_on) == len(snowpacks) and len(snowpacks) > 1 \
+                else _e.SNOW_SLIDE_SKIP_GLACIERS
+            names = {"coeff": "slide_coeff", "exp": "slide_exp", "min_slope": "slide_min_slope",
+                     "max_slope": "slide_max_slope", "min_snow_holding_depth": "slide_min_holding_depth",
+                     "max_snow_depth": "slide_max_snow_depth"}
+            first = None
+            for sp_name, proc in slide_on.items():
+                pv = _params(proc)
+                if first is None:
+                    first = pv
+                elif any(pv[k] != first[k] for k in names):
+                    raise UnsupportedStructure("transport:snow_slide: different parameters on the snowpacks")
+                for pname, slot in names.items():
+                    self._set(slot, sp_name, pname, pv[pname])
         self.basin_store_names = (b1, b2)
         # sub-basin bricks that no glacier feeds stay empty forever (helpers.cpp:55-59): ignore them, but
         # only if they are plain linear stores to the outlet.
@@ -452,6 +482,14 @@ def slope_m_per_m(value: float, unit: str) -> np.float32:
     raise ValueError(f"unsupported slope unit {unit!r}")
 
 
+def slope_degrees(value: float, unit: str) -> np.float32:
+    """HydroUnit::GetPropertyDouble("slope", "degrees") + the float cast of ProcessLateralSnowSlide.cpp:33-35."""
+    if unit in ("degrees", "degree", "deg", "°"):
+        return np.float32(value)
+    # HydroUnitProperty::GetValue (HydroUnitProperty.cpp:19-49) converts degrees to other units, never back
+    raise ValueError(f"The unit 'degrees' is not supported for the property 'slope' given in {unit!r}.")
+
+
 def build_engine(structures, units, solver, n_steps, device=0, time_step_days=1.0, start_mjd=44605.0):
     """Compile + create an engine + upload the basin. `units` as in tests/golden (basin order).
     start_mjd: modified Julian date of time step 0 (default 1981-01-01), read by day-of-year processes."""
@@ -469,4 +507,13 @@ def build_engine(structures, units, solver, n_steps, device=0, time_step_days=1.
     eng.set_units(area, elev, slope, gv, fg, fgl)
     if cs.hbk.melt_kind == _e.MELT_DEGREE_DAY_ASPECT:
         eng.set_unit_aspect([u.get("aspect_class") or u.get("properties", {}).get("aspect_class") for u in units])
+    if cs.hbk.snow_slide_kind != _e.SNOW_SLIDE_NONE:
+        # hydro_units.py set_connectivity -> SettingsBasin::AddLateralConnection: (receiver position, fraction) per unit
+        givers, receivers, fractions = [], [], []
+        for i, u in enumerate(units):
+            for receiver, fraction in u.get("lateral", []):
+                givers.append(i)
+                receivers.append(int(receiver))
+                fractions.append(float(fraction))
+        eng.set_lateral_connections(givers, receivers, fractions, [slope_degrees(*u["slope"]) for u in units])
     return cs, eng

@@ -53,6 +53,11 @@ enum { HBK_SUBLIMATION_NONE = 0, HBK_SUBLIMATION_CONSTANT = 1, HBK_SUBLIMATION_P
 enum { HBK_MELT_DEGREE_DAY = 0, HBK_MELT_DEGREE_DAY_ASPECT = 1, HBK_MELT_TEMPERATURE_INDEX = 2 };
 /* aspect class of a hydro unit (HydroUnit::GetPropertyString("aspect_class")): north|N, south|S, east|west|E|W */
 enum { HBK_ASPECT_NORTH = 0, HBK_ASPECT_SOUTH = 1, HBK_ASPECT_EAST_WEST = 2 };
+/* snow redistribution (SettingsModel::AddSnowRedistribution, SettingsModel.cpp:560-572): none | transport:snow_slide on
+ * the snowpacks of the non-glacier covers (skipGlaciers, the default of the reference's Socont) | on every snowpack.
+ * ProcessLateralSnowSlide.cpp:46-134: snow above a slope-dependent holding depth slides, within the step, onto the
+ * snowpacks of the units the giving unit is laterally connected to (hbk_set_lateral_connections). */
+enum { HBK_SNOW_SLIDE_NONE = 0, HBK_SNOW_SLIDE_SKIP_GLACIERS = 1, HBK_SNOW_SLIDE_ALL = 2 };
 
 /* The per-structure process table for the Socont family, as the structure compiler
  * (hydrobricks_b200/csrc/hb_host.hpp, hb::Compiled) derives it from a SettingsModel. */
@@ -76,6 +81,8 @@ typedef struct {
      * SettingsModel.cpp:586-598): HBK_SUBLIMATION_* */
     int32_t sublimation_kind;
     int32_t melt_kind;                /* HBK_MELT_*, the same process on every snowpack and on the glacier ice */
+    int32_t snow_slide_kind;          /* HBK_SNOW_SLIDE_* */
+    int32_t reserved;
 } hbk_structure;
 
 /* Parameter slots of one parameter set: float32 like the reference (Parameter.h:121). */
@@ -105,6 +112,9 @@ enum {
     HBK_P_GROUND_SNOW_MELT_B, HBK_P_GROUND_SNOW_MELT_C,
     HBK_P_GLACIER_SNOW_MELT_B, HBK_P_GLACIER_SNOW_MELT_C,
     HBK_P_ICE_MELT_B, HBK_P_ICE_MELT_C,
+    /* transport:snow_slide (ProcessLateralSnowSlide.cpp:24-31), the same values on every snowpack that slides */
+    HBK_P_SLIDE_COEFF, HBK_P_SLIDE_EXP, HBK_P_SLIDE_MIN_SLOPE, HBK_P_SLIDE_MAX_SLOPE, HBK_P_SLIDE_MIN_HOLDING_DEPTH,
+    HBK_P_SLIDE_MAX_SNOW_DEPTH,
     HBK_N_PARAMS
 };
 
@@ -150,6 +160,16 @@ int hbk_set_units(hbk_engine* e, const double* area_m2, const double* elevation_
  * ProcessMeltDegreeDayAspect::SetHydroUnitProperties, ProcessMeltDegreeDayAspect.cpp:35-37); required before hbk_run
  * when melt_kind is HBK_MELT_DEGREE_DAY_ASPECT. */
 int hbk_set_unit_aspect(hbk_engine* e, const int32_t* aspect_class);
+
+/* SettingsBasin::AddLateralConnection (hydro_units.py set_connectivity; ModelBuilder.cpp:476-508): n connections
+ * giver -> receiver (unit indices in basin order) with the share of the giver's sliding snow that the receiver gets, in
+ * the order they were added (= the order of the process's outputs); slope_degrees[n_units]: the units' "slope" property in
+ * degrees as ProcessLateralSnowSlide::SetHydroUnitProperties reads it (float). Required when snow_slide_kind is set. The
+ * units of a parameter set are then integrated one after the other inside a time step, in basin order, as the reference
+ * does (a giver processed before its receiver feeds it in the same step); every receiver must come AFTER its giver in
+ * basin order (downhill in a basin sorted by elevation, HBK_E_UNSUPPORTED otherwise). */
+int hbk_set_lateral_connections(hbk_engine* e, int32_t n, const int32_t* giver, const int32_t* receiver,
+                                const double* fraction, const float* slope_degrees);
 
 /* SettingsModel::SetParameterValue + ModelHydro::UpdateParameters (ModelHydro.cpp:76-84), batched:
  * values[n_sets][HBK_N_PARAMS] float32. */

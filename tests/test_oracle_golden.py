@@ -118,22 +118,3 @@ def test_oracle_actions_match_reference_bit_exact(name):
     assert gu.same(om.outlet, outlet)
     for label, ref in records.items():
         assert gu.same(om.records[label], ref), label
-
-
-NEXT_CASES = sorted("next/" + p.stem for p in (gu.GOLDEN / "next").glob("*.npz"))
-
-
-@pytest.mark.parametrize("name", NEXT_CASES)
-def test_oracle_matches_reference_on_options_the_engine_lacks(name):
-    """snow_redistribution = transport:snow_slide (ProcessLateralSnowSlide.cpp, lateral connections between units): the
-    oracle is pinned bit for bit; the CUDA engine does not implement it yet and refuses such structures
-    (tests/golden/next is outside the engine's parity lists)."""
-    from hydrobricks_b200 import structure
-
-    meta, forcing, outlet, records, _ = gu.load(name)
-    om = gu.run_oracle(meta, forcing)
-    assert gu.same(om.outlet, outlet)
-    for label, ref in records.items():
-        assert gu.same(om.records[label], ref), label
-    with pytest.raises(structure.UnsupportedStructure):
-        structure.CompiledStructure(meta["structures"], meta["solver"])

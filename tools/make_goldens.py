@@ -217,14 +217,14 @@ def melt_variant_bundles(ref):
 
 
 def snow_slide_bundles(ref):
-    """transport:snow_slide (refused by the engine: it couples the units inside a step); oracle vectors only."""
+    """transport:snow_slide: lateral snow fluxes between the units inside a step (the engine's sequential-over-units
+    kernel)."""
     import ref_snow_slide_case as rs
 
-    (OUT / "next").mkdir(parents=True, exist_ok=True)
     for solver, kw, name in (("rk4", dict(glacier=True, nsoil=1), "glacier_1store"),
                              ("crank_nicolson", dict(glacier=False, nsoil=2), "noglacier_2store")):
         meta, forcing, q, rec = rs.run_reference(ref, solver, **kw)
-        save(f"next/snow_slide_{solver}_{name}", meta, forcing, q, rec)
+        save(f"snow_slide_{solver}_{name}", meta, forcing, q, rec)
 
 
 def threshold_splitter_bundles(ref):
