@@ -107,6 +107,11 @@ inline const std::map<string, ProcessDefaults>& processRegistry() {
         {"transform:snow_ice_swat", {{{"snow_ice_transformation_basal_acc_coeff", 0.0014f}, {"north_hemisphere", 1.0f}}, {}}},
         {"transformation:snow_ice_swat",
          {{{"snow_ice_transformation_basal_acc_coeff", 0.0014f}, {"north_hemisphere", 1.0f}}, {}}},
+        // ProcessLateralSnowSlide::RegisterProcessSettings (ProcessLateralSnowSlide.cpp:24-31)
+        {"transport:snow_slide",
+         {{{"coeff", 3178.4f}, {"exp", -1.998f}, {"min_slope", 10.0f}, {"max_slope", 75.0f},
+           {"min_snow_holding_depth", 50.0f}, {"max_snow_depth", 20000.0f}},
+          {}}},
         // ProcessSublimation{Constant,PET}::RegisterProcessSettings
         {"sublimation:constant", {{{"sublimation_rate", 0.1f}}, {}}},
         {"sublimation:pet", {{{"sublimation_pet_factor", 0.2f}}, {"pet"}}},
@@ -306,6 +311,21 @@ class SettingsModel {
         for (auto& c : covers) {
             SelectHydroUnitBrickByName(c.first + "_snowpack");
             if (c.second == "glacier") AddBrickProcess("snow_ice_transfo", transformationProcess, c.first + ":ice");
+        }
+    }
+    // SettingsModel::AddSnowRedistribution (SettingsModel.cpp:560-572): a lateral process on the snowpack of every land
+    // cover (the glacier covers only without skipGlaciers), instantaneous snow fluxes to the connected units' snowpacks
+    void AddSnowRedistribution(const string& redistributionProcess = "transport:snow_slide", bool skipGlaciers = true) {
+        if (redistributionProcess != "transport:snow_slide")
+            throw std::runtime_error("Process type '" + redistributionProcess + "' is not available in the B200 engine.");
+        vector<std::pair<string, string>> covers;
+        for (auto& b : sel().hydroUnitBricks)
+            if (b.isLandCover) covers.push_back({b.name, b.kind});
+        for (auto& c : covers) {
+            if (skipGlaciers && c.second == "glacier") continue;
+            SelectHydroUnitBrickByName(c.first + "_snowpack");
+            AddBrickProcess("snow_redistribution", redistributionProcess, "lateral:snow");
+            SetProcessOutputsAsInstantaneous();
         }
     }
     // SettingsModel::AddSnowpackSublimation (SettingsModel.cpp:586-598): no target = a flux to the atmosphere
@@ -527,12 +547,21 @@ class SettingsBasin {
             last().slopeUnit = unit;
         }
     }
-    void AddLateralConnection(int, int, double, const string& = "") {
-        throw std::runtime_error("Lateral connections are not available in the B200 engine (SURVEY.md §8f).");
+    // SettingsBasin::AddLateralConnection: kept by unit id, resolved to basin positions when the model is built
+    struct Connection {
+        int giver, receiver;
+        double fraction;
+    };
+    void AddLateralConnection(int giver, int receiver, double fraction, const string& = "") {
+        connections.push_back({giver, receiver, fraction});
     }
-    int GetLateralConnectionCount() const { return 0; }
-    void Clear() { units.clear(); }
+    int GetLateralConnectionCount() const { return (int)connections.size(); }
+    void Clear() {
+        units.clear();
+        connections.clear();
+    }
     vector<UnitSettings> units;
+    vector<Connection> connections;
 
   private:
     UnitSettings& last() {
@@ -803,6 +832,7 @@ struct Compiled {
             const Brick* brick;
             const Process* transfo;
             const Process* sublim;
+            const Process* slide = nullptr;
         };
         auto snowpackOf = [&](const Brick& cover) -> SnowpackInfo {
             const Brick* sp = nullptr;
@@ -823,6 +853,12 @@ struct Compiled {
                     const auto& out = info.transfo->outputs;
                     ok = out.size() == 1 && out[0].target == cover.name && out[0].fluxType == "ice" &&
                          !out[0].instantaneous && !out[0].isStatic;
+                }
+                if (ok && i < sp->processes.size() && sp->processes[i].kind == "transport:snow_slide") {
+                    // SettingsModel::AddSnowRedistribution: instantaneous snow fluxes to the connected units' snowpacks
+                    info.slide = &sp->processes[i++];
+                    const auto& out = info.slide->outputs;
+                    ok = out.size() == 1 && out[0].target == "lateral" && out[0].fluxType == "snow" && out[0].instantaneous;
                 }
                 if (ok && i < sp->processes.size() && sublimationKindOf(sp->processes[i].kind)) {
                     info.sublim = &sp->processes[i++];
@@ -847,6 +883,7 @@ struct Compiled {
         vector<string> snowpacks;
         std::set<string> known = {ground->name, slowName, quickName};
         SnowpackInfo gInfo{nullptr, nullptr, nullptr};
+        vector<std::pair<string, const Process*>> slideOn;  // snowpack name, its transport:snow_slide process
         if (!noSnow) {
             gInfo = snowpackOf(*ground);
             const Brick& gsp = *gInfo.brick;
@@ -858,6 +895,7 @@ struct Compiled {
             label(gsp.name + ":" + gsp.processes[0].name + ":output", "ground_snowpack_melt");
             snowpacks.push_back(gsp.name);
             known.insert(gsp.name);
+            if (gInfo.slide) slideOn.push_back({gsp.name, gInfo.slide});
         }
 
         string b1, b2;
@@ -901,6 +939,7 @@ struct Compiled {
                 label(glsp.name + ":" + glsp.processes[0].name + ":output", "glacier_snowpack_melt");
                 snowpacks.push_back(glsp.name);
                 known.insert(glsp.name);
+                if (glInfo.slide) slideOn.push_back({glsp.name, glInfo.slide});
                 if (glInfo.transfo) {
                     const Process& tp = *glInfo.transfo;
                     st.snow_ice_kind = snowIceKindOf(tp.kind);
@@ -936,6 +975,26 @@ struct Compiled {
             std::sort(a.begin(), a.end());
             std::sort(b.begin(), b.end());
             if (a != b) throw Unsupported("snow must go to the snowpack of every land cover");
+        }
+        st.snow_slide_kind = HBK_SNOW_SLIDE_NONE;
+        if (!slideOn.empty()) {
+            // the snowpacks of the generic cover always slide, those of the glacier unless skipGlaciers; one set of
+            // parameters for every sliding snowpack (ProcessLateralSnowSlide.cpp:24-31)
+            if (!gInfo.slide) throw Unsupported("transport:snow_slide must be on the snowpack of the generic land cover");
+            st.snow_slide_kind = (slideOn.size() == snowpacks.size() && snowpacks.size() > 1) ? HBK_SNOW_SLIDE_ALL
+                                                                                             : HBK_SNOW_SLIDE_SKIP_GLACIERS;
+            static const std::pair<const char*, int> names[6] = {
+                {"coeff", HBK_P_SLIDE_COEFF}, {"exp", HBK_P_SLIDE_EXP}, {"min_slope", HBK_P_SLIDE_MIN_SLOPE},
+                {"max_slope", HBK_P_SLIDE_MAX_SLOPE}, {"min_snow_holding_depth", HBK_P_SLIDE_MIN_HOLDING_DEPTH},
+                {"max_snow_depth", HBK_P_SLIDE_MAX_SNOW_DEPTH}};
+            for (auto& sp : slideOn) {
+                for (auto& nm : names) {
+                    const float v = paramOf(sp.second->parameters, nm.first);
+                    if (sp.second != slideOn[0].second && v != paramOf(slideOn[0].second->parameters, nm.first))
+                        throw Unsupported("transport:snow_slide: different parameters on the snowpacks");
+                    set(nm.second, sp.first, nm.first, v);
+                }
+            }
         }
         for (auto& bb : base->subBasinBricks) {
             if (bb.name == b1 || bb.name == b2) continue;
@@ -1322,6 +1381,32 @@ class ModelHydro {
         }
         check(hbk_set_units(_e, area.data(), elev.data(), _c->st.quick_kind == HBK_QUICK_SOCONT ? slope.data() : nullptr,
                             gv.data(), fg.data(), fgl.data()));
+        if (_c->st.snow_slide_kind != HBK_SNOW_SLIDE_NONE) {
+            // ModelBuilder.cpp:476-508: connections by unit id -> basin positions, in the order they were added
+            std::map<int, int> pos;
+            for (int u = 0; u < U; ++u) pos[_units[u].id] = u;
+            vector<int32_t> giver, receiver;
+            vector<double> fraction;
+            for (auto& c : bs.connections) {
+                auto g = pos.find(c.giver), r = pos.find(c.receiver);
+                if (g == pos.end() || r == pos.end())
+                    throw std::invalid_argument("Model initialization failed: lateral connection to an unknown hydro unit");
+                giver.push_back(g->second);
+                receiver.push_back(r->second);
+                fraction.push_back(c.fraction);
+            }
+            vector<float> slopeDeg(U, 0.0f);
+            for (int u = 0; u < U; ++u) {
+                if (!_units[u].hasSlope) throw std::invalid_argument("No property with the name 'slope' was found.");
+                const string& su = _units[u].slopeUnit;
+                // HydroUnitProperty::GetValue (HydroUnitProperty.cpp:19-49) converts degrees to other units, never back
+                if (su != "degrees" && su != "degree" && su != "deg" && su != "°")
+                    throw std::invalid_argument("The unit 'degrees' is not supported for the property 'slope'.");
+                slopeDeg[u] = (float)_units[u].slopeValue;
+            }
+            check(hbk_set_lateral_connections(_e, (int)giver.size(), giver.data(), receiver.data(), fraction.data(),
+                                              slopeDeg.data()));
+        }
         if (_c->st.melt_kind == HBK_MELT_DEGREE_DAY_ASPECT) {
             vector<int32_t> aspect(U);
             for (int u = 0; u < U; ++u) aspect[u] = Compiled::aspectOf(_units[u].aspectClass);

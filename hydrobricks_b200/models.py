@@ -220,7 +220,7 @@ class Socont:
         for alias, value in values.items():
             component, name = self.aliases.get(alias, (None, None))
             if component is None:
-                component, name = alias.split(":", 1)
+                component, name = alias.rsplit(":", 1)  # "type:snowpack:coeff" -> ("type:snowpack", "coeff")
             if not self.settings.set_parameter_value(component, name, value):
                 raise ValueError(f"Failed setting parameter {alias}")
         self.model.update_parameters(self.settings)
@@ -256,7 +256,7 @@ class Socont:
         for alias, values in sets.items():
             component, name = self.aliases.get(alias, (None, None))
             if component is None:
-                component, name = alias.split(":", 1)
+                component, name = alias.rsplit(":", 1)  # "type:snowpack:coeff" -> ("type:snowpack", "coeff")
             slots = self.model.parameter_slot(component, name)
             if not slots:
                 raise ValueError(f"parameter {alias} is not part of this structure")

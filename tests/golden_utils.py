@@ -72,6 +72,11 @@ def settings_from_structures(hb, meta, n_steps, solver=None):
                     extras[proc["name"]] = proc["kind"]
         if "snow_ice_transfo" in extras:
             s.add_snow_ice_transformation(extras["snow_ice_transfo"])
+        if "snow_redistribution" in extras:  # on the glacier snowpacks too unless skipGlaciers (SettingsModel.cpp:565-567)
+            glacier_snowpacks = [b for b in st["hydro_unit_bricks"] if b["is_surface_component"] and any(
+                c["name"] == b["parent"] and c["kind"] == "glacier" for c in st["hydro_unit_bricks"])]
+            skip = not any(p["name"] == "snow_redistribution" for b in glacier_snowpacks for p in b["processes"])
+            s.add_snow_redistribution(extras["snow_redistribution"], skip)
         if "sublimation" in extras:
             s.add_snowpack_sublimation(extras["sublimation"])
         for b in st["hydro_unit_bricks"] + st["sub_basin_bricks"]:
