@@ -943,7 +943,18 @@ class ModelHydro:
         return self._storage_total([("ice", gl)])
 
     def dump_outputs(self, path):
-        raise RuntimeError("dump_outputs (netCDF) is outside the hot path and not available in the B200 engine.")
+        """ModelHydro::DumpOutputs -> ResultWriter::WriteNetCDF (ResultWriter.cpp:8-87): the same variables under the
+        same names in <path>/results.npz (netCDF is absent from this image); read it back with results.Results."""
+        from . import results
+
+        return results.write_results(self, path, self._cs.assign_structure_variants_ids(
+            [u["land_covers"] for u in self._units]))
+
+    def start_mjd(self):
+        return self._mjd0
+
+    def time_step_days(self):
+        return self._cs.hbk.time_step_days
 
 
 class ActionLandCoverChange(Action):

@@ -408,9 +408,18 @@ PYBIND11_MODULE(_hydrobricks, m) {
             for (int u = 0; u < U; ++u) sum += buf[u] * gl[u] * (areas[u] / total);
             return sum;
         })
-        .def("dump_outputs", [](hb::ModelHydro&, const std::string&) -> bool {
-            throw std::runtime_error("dump_outputs (netCDF) is outside the hot path and not available in the B200 engine.");
+        // ModelHydro::DumpOutputs -> ResultWriter::WriteNetCDF (ResultWriter.cpp:8-87): the same variables under the same
+        // names in <path>/results.npz (netCDF is absent from this image), written by hydrobricks_b200/results.py from this
+        // object's getters
+        .def("dump_outputs", [](py::object self, const std::string& path) -> bool {
+            return py::module_::import("hydrobricks_b200.results").attr("write_results")(self, path).cast<bool>();
         }, "path"_a)
+        .def("get_hydro_unit_structure_ids", [](hb::ModelHydro& mh) {
+            auto v = mh.GetHydroUnitStructureIds();
+            return i32arr(v.size(), v.data());
+        })
+        .def("start_mjd", &hb::ModelHydro::StartMjd)
+        .def("time_step_days", &hb::ModelHydro::TimeStepDays)
         .def("engine_handle", [](hb::ModelHydro& mh) { return (std::uintptr_t)mh.engine(); },
              "Raw hbk_engine* (for hydrobricks_b200.engine.Engine.from_handle: device pointers, stream, statistics).");
 

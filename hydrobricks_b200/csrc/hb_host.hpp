@@ -1082,7 +1082,11 @@ struct Compiled {
 
     // ModelBuilder::AssignHydroUnitStructures (ModelBuilder.cpp:36-97) -> glacier-variant flag of one unit
     int glacierVariantOf(const vector<std::pair<string, double>>& covers) const {
-        if (variantCovers.size() <= 1) return variantCovers.begin()->first == glacierStructureId ? 1 : 0;
+        return structureIdOf(covers) == glacierStructureId ? 1 : 0;
+    }
+    // ... -> the id of the structure variant of one unit (results: hydro_units_structure_ids)
+    int structureIdOf(const vector<std::pair<string, double>>& covers) const {
+        if (variantCovers.size() <= 1) return variantCovers.begin()->first;
         std::set<string> present;
         for (auto& c : covers)
             if (std::fabs(c.second) > 1e-8) present.insert(c.first);
@@ -1109,7 +1113,7 @@ struct Compiled {
             }
             if (sid < 0) sid = largestId;
         }
-        return sid == glacierStructureId ? 1 : 0;
+        return sid;
     }
 
     // SettingsModel::SetParameterValue target resolution incl. lists and "type:" components -> slots
@@ -1564,6 +1568,13 @@ class ModelHydro {
         for (auto& u : _units) ids.push_back(u.id);
         return ids;
     }
+    vector<int> GetHydroUnitStructureIds() const {
+        vector<int> ids;
+        for (auto& u : _units) ids.push_back(_c->structureIdOf(u.landCovers));
+        return ids;
+    }
+    double StartMjd() const { return _mjd0; }
+    double TimeStepDays() const { return _dt; }
     vector<double> GetHydroUnitAreas() const {
         vector<double> a;
         for (auto& u : _units) a.push_back(u.area);

@@ -422,6 +422,10 @@ class CompiledStructure:
     # ------------------------------------------------------------------------------------------------
     def assign_structure_variants(self, unit_land_covers):
         """ModelBuilder::AssignHydroUnitStructures (ModelBuilder.cpp:36-97) -> glacier_variant flag per unit."""
+        return [1 if sid == self.glacier_structure_id else 0 for sid in self.assign_structure_variants_ids(unit_land_covers)]
+
+    def assign_structure_variants_ids(self, unit_land_covers):
+        """... -> the id of the structure variant of every unit (results: hydro_units_structure_ids)."""
         out = []
         ids = sorted(self.variant_covers)
         for covers in unit_land_covers:
@@ -437,7 +441,7 @@ class CompiledStructure:
                     else:
                         size = max(len(c) for c in self.variant_covers.values())
                         sid = min(i for i in ids if len(self.variant_covers[i]) == size)
-            out.append(1 if sid == self.glacier_structure_id else 0)
+            out.append(sid)
         return out
 
     def parameter_vector(self, overrides=None):

@@ -8,6 +8,7 @@
 // golden vectors at the 1e-10 bar without a GPU; what it does NOT cover is the kernel plumbing (tiles, TMA staging,
 // state streaming, reductions), which only the `-m gpu` tests exercise. Never linked into the product.
 #include "../../include/hbk.h"
+static long long hbkSeqEvaluations = 0;  // counted by seqBrickRates (rate-law evaluations inside the bisection)
 #include "../../hydrobricks_b200/csrc/hbk_device.cuh"
 
 using namespace hbk;
@@ -134,6 +135,12 @@ int runSet(const hbk_structure& st, int U, int T, const double* area, const floa
 // the solar radiation [n_steps][n_units] (melt:temperature_index); reset after every run
 static const int32_t* g_aspect = nullptr;
 static const double* g_radiation = nullptr;
+
+extern "C" long long hbk_emul_seq_evaluations(int reset) {
+    const long long n = hbkSeqEvaluations;
+    if (reset) hbkSeqEvaluations = 0;
+    return n;
+}
 
 extern "C" void hbk_emul_set_melt_inputs(const int32_t* aspect, const double* radiation) {
     g_aspect = aspect;

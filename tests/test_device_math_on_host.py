@@ -238,3 +238,32 @@ def test_c1_full_period_on_host(emul):
     _, q, _, unconverged = run_emul(emul, meta, {"p": p, "t": t, "pet": pet})
     assert len(q) == 14610 and unconverged == 0
     _close(q, outlet)
+
+
+@pytest.fixture(scope="module")
+def emul_plain_bisection():
+    return build_emul("libhbkemul_plainbisect.so", ["-DHBK_SEQ_FAST_BISECTION=0"])
+
+
+SEQ_CASES = [b for b in CASES if any(s in b for s in ("crank_nicolson", "implicit_euler"))]
+
+
+@pytest.mark.parametrize("name", SEQ_CASES)
+def test_fast_bisection_replays_the_reference_halving(name, emul, emul_plain_bisection):
+    """crank_nicolson / implicit_euler (SolverCrankNicolson.cpp:12-63, SolverImplicitEuler.cpp:12-61): the shipped
+    bisection decides midpoints outside a certified root bracket without evaluating the rate laws; against the plain loop
+    (every midpoint evaluated, -DHBK_SEQ_FAST_BISECTION=0) the results must agree to the last bits (a decision can only
+    flip within round-off of the root: < 1e-12 mm) at a fraction of the evaluations."""
+    meta, forcing, outlet, records, _ = gu.load(name)
+    for L in (emul, emul_plain_bisection):
+        L.hbk_emul_seq_evaluations.restype = ctypes.c_longlong
+        L.hbk_emul_seq_evaluations.argtypes = [ctypes.c_int]
+        L.hbk_emul_seq_evaluations(1)
+    _, q_fast, rec_fast, _ = run_emul(emul, meta, forcing)
+    _, q_plain, rec_plain, _ = run_emul(emul_plain_bisection, meta, forcing)
+    n_fast, n_plain = emul.hbk_emul_seq_evaluations(1), emul_plain_bisection.hbk_emul_seq_evaluations(1)
+    assert np.max(np.abs(q_fast - q_plain)) <= 1e-11 * max(1.0, float(np.max(np.abs(q_plain))))
+    assert np.nanmax(np.abs(rec_fast["slow"] - rec_plain["slow"])) <= 1e-11
+    assert (q_fast == q_plain).mean() > 0.99  # bit-identical but for the rare midpoint within round-off of the root
+    assert n_plain > 2.5 * n_fast, (n_plain, n_fast)
+    _close(q_fast, outlet)
