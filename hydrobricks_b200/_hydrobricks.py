@@ -887,14 +887,16 @@ class ModelHydro:
     def get_hydro_unit_values(self, label):
         if label not in self._cs.labels:
             raise RuntimeError(f"Label '{label}' is not recorded.")
-        return self._engine.get_recorded(self._cs.labels[label], 0)
+        return self._cs.recorded(self._engine, label)
 
     def get_hydro_unit_fractions(self, label):
         """Logger fraction series (Logger.cpp:111-119): recorded per step, so action-driven changes show."""
-        slot = {self._cs.ground_name: "fraction_ground", self._cs.glacier_name: "fraction_glacier"}.get(label)
-        if slot is None:
+        slot = {self._cs.ground_name: "fraction_ground", self._cs.glacier_name: "fraction_glacier",
+                self._cs.glacier2_name: "fraction_glacier"}.get(label)
+        if slot is None or label is None:
             raise RuntimeError(f"Fraction label '{label}' is not recorded.")
-        return self._engine.get_recorded(slot, 0)
+        # the second glacier cover's fraction is the glacier fraction of the twin units
+        return self._cs.layout.gather(self._engine.get_recorded(slot, 0), label == self._cs.glacier2_name)
 
     def get_hydro_unit_ids(self):
         return [u["id"] for u in self._units]
@@ -903,20 +905,25 @@ class ModelHydro:
         return np.array([u["area"] for u in self._units], dtype=np.float64)
 
     def _fractions(self):
-        g = np.array([dict(u["land_covers"]).get(self._cs.ground_name, 1.0) for u in self._units])
-        gl = np.array([dict(u["land_covers"]).get(self._cs.glacier_name, 0.0) if self._cs.glacier_name else 0.0
-                       for u in self._units])
-        return g, gl
+        """Initial land-cover fractions per ENGINE unit (a twin: no ground, the second glacier cover's fraction)."""
+        layout = self._cs.layout
+        g = [dict(u["land_covers"]).get(self._cs.ground_name, 1.0) for u in self._units]
+        gl = [dict(u["land_covers"]).get(self._cs.glacier_name, 0.0) if self._cs.glacier_name else 0.0
+              for u in self._units]
+        for u in layout.twin_of[layout.n_basin:]:
+            g.append(0.0)
+            gl.append(dict(self._units[u]["land_covers"]).get(self._cs.glacier2_name, 0.0))
+        return np.array(g), np.array(gl)
 
     def get_total_et(self):
         """Logger::GetTotalET (Logger.cpp:168-216): area-weighted sum of the ET flux records."""
         areas = self.get_hydro_unit_areas()
-        et = self._engine.get_recorded("slow_et", 0)
+        et = self._cs.layout.gather(self._engine.get_recorded("slow_et", 0), False)
         return float((np.nan_to_num(et) * (areas / areas.sum())[None, :]).sum())
 
     def _storage_total(self, slots_with_fraction):
         areas = self.get_hydro_unit_areas()
-        w = areas / areas.sum()
+        w = self._cs.layout.expand(areas / areas.sum())  # a twin carries a cover of its unit: the unit's weight
         total = 0.0
         for slot, frac in slots_with_fraction:
             end = self._engine.get_state(slot)[0]

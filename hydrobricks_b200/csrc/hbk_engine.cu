@@ -132,11 +132,12 @@ __device__ __forceinline__ void tmaLoad1D(void* dst, const void* src, uint32_t b
 // float32 promoted; ProcessSublimation{Constant,PET}.cpp). Out of line and read from global memory at use, so that the
 // kernels of structures without the option carry neither the registers nor predicated instructions for it.
 template <bool GLACIER>
-__device__ __noinline__ double2 sublimationRates(const float* params, int ldp, int kind, int p, double pet) {
+__device__ __noinline__ double2 sublimationRates(const float* params, int ldp, int kind, int p, double pet, bool twin = false) {
     const double scale = (kind == HBK_SUBLIMATION_PET) ? pet : 1.0;
     double2 r;
     r.x = scale * (double)params[p + (size_t)HBK_P_GROUND_SUBLIMATION * ldp];
-    r.y = GLACIER ? scale * (double)params[p + (size_t)HBK_P_GLACIER_SUBLIMATION * ldp] : 0.0;
+    r.y = GLACIER ? scale * (double)params[p + (size_t)(twin ? HBK_P_GLACIER2_SUBLIMATION : HBK_P_GLACIER_SUBLIMATION) * ldp]
+                  : 0.0;
     return r;
 }
 
@@ -147,10 +148,14 @@ struct AspectFactors {
     double ground, glacierSnow, ice;
 };
 template <bool GLACIER>
-__device__ __noinline__ AspectFactors aspectFactors(const float* params, int ldp, int p, int aspect) {
+__device__ __noinline__ AspectFactors aspectFactors(const float* params, int ldp, int p, int aspect, bool twin = false) {
     const int g = aspect == 0 ? HBK_P_GROUND_SNOW_DDF : (aspect == 1 ? HBK_P_GROUND_SNOW_MELT_B : HBK_P_GROUND_SNOW_MELT_C);
-    const int s = aspect == 0 ? HBK_P_GLACIER_SNOW_DDF : (aspect == 1 ? HBK_P_GLACIER_SNOW_MELT_B : HBK_P_GLACIER_SNOW_MELT_C);
-    const int i = aspect == 0 ? HBK_P_ICE_DDF : (aspect == 1 ? HBK_P_ICE_MELT_B : HBK_P_ICE_MELT_C);
+    int s = aspect == 0 ? HBK_P_GLACIER_SNOW_DDF : (aspect == 1 ? HBK_P_GLACIER_SNOW_MELT_B : HBK_P_GLACIER_SNOW_MELT_C);
+    int i = aspect == 0 ? HBK_P_ICE_DDF : (aspect == 1 ? HBK_P_ICE_MELT_B : HBK_P_ICE_MELT_C);
+    if (twin) {  // the second glacier cover's own factors
+        s = aspect == 0 ? HBK_P_GLACIER2_SNOW_DDF : (aspect == 1 ? HBK_P_GLACIER2_SNOW_MELT_B : HBK_P_GLACIER2_SNOW_MELT_C);
+        i = aspect == 0 ? HBK_P_ICE2_DDF : (aspect == 1 ? HBK_P_ICE2_MELT_B : HBK_P_ICE2_MELT_C);
+    }
     AspectFactors f;
     f.ground = (double)params[p + (size_t)g * ldp];
     f.glacierSnow = GLACIER ? (double)params[p + (size_t)s * ldp] : 0.0;
@@ -158,16 +163,31 @@ __device__ __noinline__ AspectFactors aspectFactors(const float* params, int ldp
     return f;
 }
 template <bool GLACIER>
-__device__ __noinline__ AspectFactors radiationFactors(const float* params, int ldp, int p, double radiation) {
+__device__ __noinline__ AspectFactors radiationFactors(const float* params, int ldp, int p, double radiation,
+                                                       bool twin = false) {
     AspectFactors f;  // float32 parameters promoted, the product and the sum in double like the reference's expression
     f.ground = (double)params[p + (size_t)HBK_P_GROUND_SNOW_DDF * ldp] +
                (double)params[p + (size_t)HBK_P_GROUND_SNOW_MELT_B * ldp] * radiation;
-    f.glacierSnow = GLACIER ? (double)params[p + (size_t)HBK_P_GLACIER_SNOW_DDF * ldp] +
-                                  (double)params[p + (size_t)HBK_P_GLACIER_SNOW_MELT_B * ldp] * radiation
-                            : 0.0;
-    f.ice = GLACIER ? (double)params[p + (size_t)HBK_P_ICE_DDF * ldp] + (double)params[p + (size_t)HBK_P_ICE_MELT_B * ldp] * radiation
-                    : 0.0;
+    const int sA = twin ? HBK_P_GLACIER2_SNOW_DDF : HBK_P_GLACIER_SNOW_DDF, sB = twin ? HBK_P_GLACIER2_SNOW_MELT_B : HBK_P_GLACIER_SNOW_MELT_B;
+    const int iA = twin ? HBK_P_ICE2_DDF : HBK_P_ICE_DDF, iB = twin ? HBK_P_ICE2_MELT_B : HBK_P_ICE_MELT_B;
+    f.glacierSnow = GLACIER ? (double)params[p + (size_t)sA * ldp] + (double)params[p + (size_t)sB * ldp] * radiation : 0.0;
+    f.ice = GLACIER ? (double)params[p + (size_t)iA * ldp] + (double)params[p + (size_t)iB * ldp] * radiation : 0.0;
     return f;
+}
+
+// The glacier parameters of the unit being loaded when the structure has twin units (hbk_set_unit_twins): an ordinary
+// unit takes the first cover's slots, a twin the second cover's. Out of line, read from global memory at use.
+struct GlacierPars {
+    double snowDdf, snowTm, iceDdf, iceTm, snowIce;
+};
+__device__ __noinline__ GlacierPars glacierPars(const float* params, int ldp, int p, bool twin) {
+    GlacierPars g;
+    g.snowDdf = (double)params[p + (size_t)(twin ? HBK_P_GLACIER2_SNOW_DDF : HBK_P_GLACIER_SNOW_DDF) * ldp];
+    g.snowTm = (double)params[p + (size_t)(twin ? HBK_P_GLACIER2_SNOW_TMELT : HBK_P_GLACIER_SNOW_TMELT) * ldp];
+    g.iceDdf = (double)params[p + (size_t)(twin ? HBK_P_ICE2_DDF : HBK_P_ICE_DDF) * ldp];
+    g.iceTm = (double)params[p + (size_t)(twin ? HBK_P_ICE2_TMELT : HBK_P_ICE_TMELT) * ldp];
+    g.snowIce = (double)params[p + (size_t)(twin ? HBK_P_SNOW_ICE2 : HBK_P_SNOW_ICE) * ldp];
+    return g;
 }
 
 // Per-parameter-set values of one set (pp = its column of the float32 parameter table), promoted to double where the
@@ -317,7 +337,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
     // per-(set, unit) values, (re)loaded per tile when the block time-multiplexes several tiles
     Hru h;
     double fa = 0, faW = 0, fG = 1, fGl = 0, cT = 0, mP = 1;  // faW: weight of the outlet fluxes (Flux.cpp:20-26)
-    bool glacierVariant = false;
+    bool glacierVariant = false, twin = false;
     auto loadUnit = [&](int u) {
         fa = a.hru[0 * a.ldu + u];
         faW = (fa < 1.0) ? fa : 1.0;
@@ -329,11 +349,20 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
         par.quickV = (a.flags.quickKind == 0) ? quickBase * slopeTerm / area * socontUnit : quickBase;
         const int unitFlags = a.hruFlags[u];
         glacierVariant = GLACIER && (unitFlags & 1);
+        twin = GLACIER && (unitFlags & 8);
 #if !HBK_PAR_SHARED
+        if (GLACIER && a.flags.hasTwins) {
+            const GlacierPars g = glacierPars(a.params, a.ldp, p, twin);
+            par.v[7] = g.snowDdf;
+            par.v[8] = g.snowTm;
+            par.v[9] = g.iceDdf;
+            par.v[10] = g.iceTm;
+            par.v[16] = g.snowIce;
+        }
         if (a.flags.meltKind == HBK_MELT_DEGREE_DAY_ASPECT) {
             // ProcessMeltDegreeDayAspect::SetParameters (ProcessMeltDegreeDayAspect.cpp:38-58): the melt processes of this
             // unit use the degree-day factor of its aspect class — a per-(set, unit) value, picked when the unit is loaded
-            const AspectFactors f3 = aspectFactors<GLACIER>(a.params, a.ldp, p, (unitFlags >> 1) & 3);
+            const AspectFactors f3 = aspectFactors<GLACIER>(a.params, a.ldp, p, (unitFlags >> 1) & 3, twin);
             par.v[5] = f3.ground;
             par.v[7] = f3.glacierSnow;
             par.v[9] = f3.ice;
@@ -543,7 +572,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
                     if (!ENS && a.flags.meltKind == HBK_MELT_TEMPERATURE_INDEX) {
                         // ProcessMeltTemperatureIndex.cpp:68-71: (T - Tm) * (melt_factor + radiation_coefficient * R); the
                         // factor in brackets takes the place of the degree-day factor for this step
-                        const AspectFactors f3 = radiationFactors<GLACIER>(a.params, a.ldp, p, fp[3 * fRow]);
+                        const AspectFactors f3 = radiationFactors<GLACIER>(a.params, a.ldp, p, fp[3 * fRow], twin);
                         par.v[5] = f3.ground;
                         par.v[7] = f3.glacierSnow;
                         par.v[9] = f3.ice;
@@ -551,7 +580,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
 #endif
                     double sublimG = 0.0, sublimGl = 0.0;
                     if (a.flags.sublimKind != 0) {
-                        const double2 su = sublimationRates<GLACIER>(a.params, a.ldp, a.flags.sublimKind, p, pet);
+                        const double2 su = sublimationRates<GLACIER>(a.params, a.ldp, a.flags.sublimKind, p, pet, twin);
                         sublimG = su.x;
                         sublimGl = su.y;
                     }
@@ -1368,6 +1397,13 @@ struct hbk_engine {
     bool haveRaw[HBK_N_VARS] = {}, haveStation[HBK_N_VARS] = {};
     int nVars() const { return st.melt_kind == HBK_MELT_TEMPERATURE_INDEX ? 4 : 3; }
     std::vector<int> hAspect;  // HBK_ASPECT_* per unit (hbk_set_unit_aspect); empty = not given
+    std::vector<int> hTwinOf;  // unit a twin (second glacier cover) belongs to, -1 = ordinary unit; empty = no twins
+    bool hasTwins = false;
+    // bit 0: the unit carries the glacier bricks; bits 1-2: HBK_ASPECT_*; bit 3: twin (second glacier cover)
+    int unitFlags(int u) const {
+        return (hGlacierVariant.empty() ? 0 : hGlacierVariant[u]) | ((hAspect.empty() ? 0 : hAspect[u]) << 1) |
+               ((!hTwinOf.empty() && hTwinOf[u] >= 0) ? 8 : 0);
+    }
     // transport:snow_slide (hbk_set_lateral_connections)
     std::vector<int> hLatOff, hLatRecv;
     std::vector<double> hLatWeight;
@@ -1840,7 +1876,8 @@ int hbk_set_units(hbk_engine* e, const double* area, const double* elevation, co
     HBK_CUDA(cudaSetDevice(e->device));
     const int U = e->U;
     double basinArea = 0;  // SubBasin::AddHydroUnit (SubBasin.cpp:173): running sum in unit order
-    for (int u = 0; u < U; ++u) basinArea += area[u];
+    for (int u = 0; u < U; ++u)
+        if (e->hTwinOf.empty() || e->hTwinOf[u] < 0) basinArea += area[u];  // twins carry a cover of a unit already counted
     if (e->shard) basinArea = e->shardBasinArea;  // a block of a larger basin (hbk_set_unit_shard)
     std::vector<double> hru((size_t)kNH * e->ldu, 0.0);
     std::vector<int> flags(e->ldu, 0);
@@ -1855,8 +1892,7 @@ int hbk_set_units(hbk_engine* e, const double* area, const double* elevation, co
         hru[2 * e->ldu + u] = slope ? std::pow((double)slope[u], 0.5) : 0.0;
         hru[3 * e->ldu + u] = elevation ? elevation[u] : 0.0;
         e->hGlacierVariant[u] = (glacier_variant && glacier_variant[u]) ? 1 : 0;
-        // bit 0: the unit carries the glacier bricks; bits 1-2: HBK_ASPECT_* (hbk_set_unit_aspect)
-        flags[u] = e->hGlacierVariant[u] | ((e->hAspect.empty() ? 0 : e->hAspect[u]) << 1);
+        flags[u] = e->unitFlags(u);
         if (frac_ground) e->hFracG[u] = frac_ground[u];
         if (frac_glacier) e->hFracGl[u] = frac_glacier[u];
         // a structure without a glacier cover has the ground as its only land cover: the kernels fold its fraction (= 1)
@@ -1886,9 +1922,24 @@ int hbk_set_unit_aspect(hbk_engine* e, const int32_t* aspect_class) {
                                       "(ProcessMeltDegreeDayAspect.cpp:38-58)");
     e->hAspect.assign(aspect_class, aspect_class + e->U);
     std::vector<int> flags(e->ldu, 0);
-    for (int u = 0; u < e->U; ++u)
-        flags[u] = (e->hGlacierVariant.empty() ? 0 : e->hGlacierVariant[u]) | (e->hAspect[u] << 1);
+    for (int u = 0; u < e->U; ++u) flags[u] = e->unitFlags(u);
     HBK_CUDA(cudaMemcpy(e->dHruFlags, flags.data(), sizeof(int) * flags.size(), cudaMemcpyHostToDevice));
+    return HBK_OK;
+}
+
+int hbk_set_unit_twins(hbk_engine* e, const int32_t* twin_of) {
+    if (!e || !twin_of) return HBK_E_ARG;
+    if (!e->st.has_glacier) return fail(e, HBK_E_MODEL, "twin units carry a second glacier cover: the structure has none");
+    if (HBK_PAR_SHARED) return fail(e, HBK_E_UNSUPPORTED, "this build (HBK_PAR_SHARED) has no twin units");
+    bool any = false;
+    for (int u = 0; u < e->U; ++u) {
+        if (twin_of[u] < -1 || twin_of[u] >= e->U || twin_of[u] == u || (twin_of[u] >= 0 && twin_of[twin_of[u]] >= 0))
+            return fail(e, HBK_E_ARG, "twin_of: index of an ordinary unit, or -1");
+        any = any || twin_of[u] >= 0;
+    }
+    e->hTwinOf.assign(twin_of, twin_of + e->U);
+    e->hasTwins = any;
+    e->unitsSet = false;  // hbk_set_units computes the basin area and the unit flags from it
     return HBK_OK;
 }
 
@@ -2481,6 +2532,7 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
     a.flags.sublimKind = e->st.sublimation_kind;
     a.flags.seqKind = e->st.solver >= HBK_SOLVER_CRANK_NICOLSON ? e->st.solver - HBK_SOLVER_CRANK_NICOLSON : 0;
     a.flags.meltKind = e->st.melt_kind;
+    a.flags.hasTwins = e->hasTwins ? 1 : 0;
     a.nVars = e->nVars();
     a.swatFactor = (a.flags.snowIceKind == HBK_SNOW_ICE_SWAT) ? e->dSwatFactor : nullptr;
     a.flags.noMeltWhenSnow = e->st.glacier_no_melt_when_snow_cover;
@@ -2639,6 +2691,9 @@ int hbk_run(hbk_engine* e) {
                                             "(hbk_set_delta_h_shard_totals)");
     }
     e->shardSegments.clear();
+    if (e->hasTwins && (!e->events.empty() || e->st.snow_slide_kind != HBK_SNOW_SLIDE_NONE || e->shard))
+        return fail(e, HBK_E_UNSUPPORTED, "units with a second glacier cover (hbk_set_unit_twins) run neither dated actions "
+                                          "nor lateral connections nor unit shards");
     const bool lateral = e->st.snow_slide_kind != HBK_SNOW_SLIDE_NONE;
     if (lateral) {
         if (!e->dLatOff)

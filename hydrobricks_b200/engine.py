@@ -38,6 +38,8 @@ PARAM_SLOTS = [
     "ground_sublimation", "glacier_sublimation",
     "ground_snow_melt_b", "ground_snow_melt_c", "glacier_snow_melt_b", "glacier_snow_melt_c", "ice_melt_b", "ice_melt_c",
     "slide_coeff", "slide_exp", "slide_min_slope", "slide_max_slope", "slide_min_holding_depth", "slide_max_snow_depth",
+    "glacier2_snow_ddf", "glacier2_snow_tmelt", "ice2_ddf", "ice2_tmelt", "snow_ice2", "glacier2_sublimation",
+    "glacier2_snow_melt_b", "glacier2_snow_melt_c", "ice2_melt_b", "ice2_melt_c",
 ]
 N_PARAMS = len(PARAM_SLOTS)
 RECORD_SLOTS = [
@@ -107,6 +109,7 @@ def load_library():
     L.hbk_last_error.restype = ctypes.c_char_p
     L.hbk_set_units.argtypes = [vp, dp, dp, fp, ip, dp, dp]
     L.hbk_set_unit_aspect.argtypes = [vp, ip]
+    L.hbk_set_unit_twins.argtypes = [vp, ip]
     L.hbk_set_lateral_connections.argtypes = [vp, i32, ip, ip, dp, fp]
     L.hbk_set_parameters.argtypes = [vp, i32, fp]
     L.hbk_set_forcing.argtypes = [vp, i32, dp]
@@ -219,6 +222,13 @@ class Engine:
             slope.ctypes.data_as(ctypes.POINTER(ctypes.c_float)) if slope is not None else None,
             gv.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)) if gv is not None else None, _dptr(fg), _dptr(fgl)))
 
+    def set_unit_twins(self, twin_of):
+        """twin_of[n_units]: index of the unit whose second glacier cover this entry carries, -1 for an ordinary unit
+        (hbk_set_unit_twins); before set_units."""
+        t = np.ascontiguousarray(twin_of, dtype=np.int32)
+        assert t.shape == (self.n_units,)
+        self._check(self.L.hbk_set_unit_twins(self.h, t.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+
     def set_unit_aspect(self, aspect_classes):
         """Aspect class per unit: HBK_ASPECT_* integers or the reference's strings (north|N|south|S|east|west|E|W)."""
         try:
@@ -249,8 +259,15 @@ class Engine:
         self.n_sets = v.shape[0]
         self._check(self.L.hbk_set_parameters(self.h, self.n_sets, v.ctypes.data_as(ctypes.POINTER(ctypes.c_float))))
 
+    def _per_engine_unit(self, a):
+        """[... x basin units] -> [... x engine units] when the engine carries twin units (structure.UnitLayout)."""
+        layout = getattr(self, "layout", None)
+        if layout is not None and layout.has_twins and a.shape[-1] == layout.n_basin:
+            return np.ascontiguousarray(layout.expand(a))
+        return a
+
     def set_forcing(self, variable, data):
-        a = np.ascontiguousarray(data, dtype=np.float64)
+        a = self._per_engine_unit(np.ascontiguousarray(data, dtype=np.float64))
         assert a.shape == (self.n_steps, self.n_units), a.shape
         self._check(self.L.hbk_set_forcing(self.h, VAR[variable] if isinstance(variable, str) else variable, _dptr(a)))
 
@@ -271,7 +288,7 @@ class Engine:
                                                    float(correction), _dptr(c_set)))
 
     def set_initial_state(self, slot, values=None):
-        v = None if values is None else np.ascontiguousarray(values, dtype=np.float64)
+        v = None if values is None else self._per_engine_unit(np.ascontiguousarray(values, dtype=np.float64))
         self._check(self.L.hbk_set_initial_state(self.h, STATE_SLOTS.index(slot) if isinstance(slot, str) else slot,
                                                  _dptr(v)))
 

@@ -171,6 +171,13 @@ class Socont:
             raise ValueError(f"The snow melt process option {smp} is not recognised.")
         if glaciers:
             a["melt_t_ice"] = (glaciers, "melting_temperature")
+        if len(self._glacier_names) > 1:  # parameters.py:1766-1835: one alias per glacier cover, by name and by index
+            per_cover = {"melt:degree_day": [("a_ice", "degree_day_factor")],
+                         "melt:degree_day_aspect": [(f"a_ice_{x}", f"degree_day_factor_{x}") for x in ("n", "s", "ew")],
+                         "melt:temperature_index": [("r_ice", "radiation_coefficient")]}[smp]
+            for i, name in enumerate(self._glacier_names):
+                for alias, pname in per_cover + [("melt_t_ice", "melting_temperature")]:
+                    a[f"{alias}_{name.replace('-', '_')}"] = a[f"{alias}_{i}"] = (name, pname)
         if self.options["snow_sublimation_process"] == "sublimation:constant":  # parameters.py:286-305, 2006-2018
             a["sublimation_rate"] = ("type:snowpack", "sublimation_rate")
         elif self.options["snow_sublimation_process"] == "sublimation:pet":

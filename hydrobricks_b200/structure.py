@@ -150,12 +150,17 @@ class CompiledStructure:
         covers = [b for b in full["hydro_unit_bricks"] if b["is_land_cover"]]
         ground = [b for b in covers if b["kind"] == "generic_land_cover"]
         glacier = [b for b in covers if b["kind"] == "glacier"]
-        if len(ground) != 1 or len(glacier) > 1 or len(ground) + len(glacier) != len(covers):
-            raise UnsupportedStructure("expected one generic land cover and at most one glacier cover")
+        if len(ground) != 1 or len(glacier) > 2 or len(ground) + len(glacier) != len(covers):
+            raise UnsupportedStructure("expected one generic land cover and at most two glacier covers")
         ground = ground[0]
+        # a second glacier cover (glacier_ice + glacier_debris, models/socont.py:131-140) is carried by twin units
+        # (hbk_set_unit_twins): the same bricks once more with the HBK_P_GLACIER2_* / HBK_P_ICE2_* parameter slots
+        glacier2 = glacier[1] if len(glacier) > 1 else None
         glacier = glacier[0] if glacier else None
         self.ground_name = ground["name"]
         self.glacier_name = glacier["name"] if glacier else None
+        self.glacier2_name = glacier2["name"] if glacier2 else None
+        self.twin_labels = set()  # log labels of the second glacier cover: recorded in the twin units' columns
         if sorted(rain_targets or []) != sorted(c["name"] for c in covers):
             raise UnsupportedStructure("rain must go to every land cover")
         if _proc_kinds(ground) != ["infiltration:socont", "outflow:rest"]:
@@ -262,42 +267,70 @@ class CompiledStructure:
         # --- glacier
         st.has_glacier = 0
         b1 = b2 = None
-        if glacier is not None:
+        for second, glacier_cover in enumerate((glacier, glacier2)):
+            if glacier_cover is None:
+                continue
+            sfx = "2" if second else ""
+            slots = {"ice_ddf": f"ice{sfx}_ddf", "ice_tmelt": f"ice{sfx}_tmelt", "ice_melt_b": f"ice{sfx}_melt_b",
+                     "ice_melt_c": f"ice{sfx}_melt_c", "glacier_snow_ddf": f"glacier{sfx}_snow_ddf",
+                     "glacier_snow_tmelt": f"glacier{sfx}_snow_tmelt", "glacier_snow_melt_b": f"glacier{sfx}_snow_melt_b",
+                     "glacier_snow_melt_c": f"glacier{sfx}_snow_melt_c", "glacier_sublimation": f"glacier{sfx}_sublimation",
+                     "snow_ice": f"snow_ice{sfx}"}
+
+            def label(name, slot):
+                self.labels[name] = slot
+                if second:
+                    self.twin_labels.add(name)
+
             st.has_glacier = 1
-            gk = _proc_kinds(glacier)
+            gk = _proc_kinds(glacier_cover)
             if len(gk) != 2 or gk[0] != "outflow:direct" or gk[1] not in _e.MELT_KIND:
                 raise UnsupportedStructure("glacier cover: expected outflow:direct + melt:degree_day|degree_day_aspect|"
                                            "temperature_index")
-            for proc in glacier["processes"]:
+            for proc in glacier_cover["processes"]:
                 if not proc["outputs"][0]["instantaneous"]:
                     raise UnsupportedStructure("glacier outputs must be instantaneous")
-            b1, b2 = _target(glacier["processes"][0]), _target(glacier["processes"][1])
-            gp = _params(glacier)
-            st.glacier_infinite_storage = int("infinite_storage" in gp and abs(float(gp["infinite_storage"])) > np.finfo(np.float32).eps)
-            st.glacier_no_melt_when_snow_cover = int("no_melt_when_snow_cover" in gp and float(gp["no_melt_when_snow_cover"]) > 0)
-            set_melt(glacier["name"], glacier["processes"][1], "ice_ddf", "ice_tmelt", "ice_melt_b", "ice_melt_c")
-            n = glacier["name"]
-            self.labels.update({f"{n}:water_content": "glacier_water", f"{n}:ice_content": "glacier_ice",
-                                f"{n}:{glacier['processes'][0]['name']}:output": "glacier_outflow",
-                                f"{n}:{glacier['processes'][1]['name']}:output": "glacier_melt"})
+            targets = (_target(glacier_cover["processes"][0]), _target(glacier_cover["processes"][1]))
+            gp = _params(glacier_cover)
+            infinite = int("infinite_storage" in gp and abs(float(gp["infinite_storage"])) > np.finfo(np.float32).eps)
+            no_melt = int("no_melt_when_snow_cover" in gp and float(gp["no_melt_when_snow_cover"]) > 0)
+            if second:
+                if targets != (b1, b2) or infinite != st.glacier_infinite_storage or \
+                        no_melt != st.glacier_no_melt_when_snow_cover:
+                    raise UnsupportedStructure("the glacier covers must share their options and their sub-basin stores")
+            else:
+                b1, b2 = targets
+                st.glacier_infinite_storage, st.glacier_no_melt_when_snow_cover = infinite, no_melt
+            set_melt(glacier_cover["name"], glacier_cover["processes"][1], slots["ice_ddf"], slots["ice_tmelt"],
+                     slots["ice_melt_b"], slots["ice_melt_c"])
+            n = glacier_cover["name"]
+            label(f"{n}:water_content", "glacier_water")
+            label(f"{n}:ice_content", "glacier_ice")
+            label(f"{n}:{glacier_cover['processes'][0]['name']}:output", "glacier_outflow")
+            label(f"{n}:{glacier_cover['processes'][1]['name']}:output", "glacier_melt")
             if self.no_snow:
                 if st.glacier_no_melt_when_snow_cover:  # IceContainer.cpp:10-32 needs the related snowpack
                     raise UnsupportedStructure("No snowpack provided for the glacier melt limitation.")
             else:
-                glsp, gltr, glsub = snowpack_of(glacier)
+                glsp, gltr, glsub = snowpack_of(glacier_cover)
                 if (glsub is None) != (gsub is None):
                     raise UnsupportedStructure("sublimation must be on every snowpack or on none")
                 if glsub is not None:
-                    set_sublimation(glsp, glsub, "glacier_sublimation", "glacier_snowpack_sublimation")
-                set_melt(glsp["name"], glsp["processes"][0], "glacier_snow_ddf", "glacier_snow_tmelt",
-                         "glacier_snow_melt_b", "glacier_snow_melt_c")
-                self.labels.update({f"{glsp['name']}:water_content": "glacier_snowpack_water",
-                                    f"{glsp['name']}:snow_content": "glacier_snowpack_snow",
-                                    f"{glsp['name']}:{glsp['processes'][0]['name']}:output": "glacier_snowpack_melt"})
+                    set_sublimation(glsp, glsub, slots["glacier_sublimation"], "glacier_snowpack_sublimation")
+                    if second:
+                        self.twin_labels.add(f"{glsp['name']}:{glsub['name']}:output")
+                set_melt(glsp["name"], glsp["processes"][0], slots["glacier_snow_ddf"], slots["glacier_snow_tmelt"],
+                         slots["glacier_snow_melt_b"], slots["glacier_snow_melt_c"])
+                label(f"{glsp['name']}:water_content", "glacier_snowpack_water")
+                label(f"{glsp['name']}:snow_content", "glacier_snowpack_snow")
+                label(f"{glsp['name']}:{glsp['processes'][0]['name']}:output", "glacier_snowpack_melt")
                 snowpacks.append(glsp["name"])
+                kind = transfo_kinds[gltr["kind"]] if gltr is not None else _e.SNOW_ICE_NONE
+                if second and kind != st.snow_ice_kind:
+                    raise UnsupportedStructure("the snow -> ice transformation must be the same on every glacier snowpack")
                 if gltr is not None:
                     tp = gltr
-                    st.snow_ice_kind = transfo_kinds[tp["kind"]]
+                    st.snow_ice_kind = kind
                     tv = _params(tp)
                     if st.snow_ice_kind == _e.SNOW_ICE_CONSTANT:
                         pname = "snow_ice_transformation_rate" if "snow_ice_transformation_rate" in tv else "rate"
@@ -305,8 +338,9 @@ class CompiledStructure:
                         pname = "snow_ice_transformation_basal_acc_coeff" \
                             if "snow_ice_transformation_basal_acc_coeff" in tv else "basal_acc_coeff"
                         st.north_hemisphere = int(not (float(tv.get("north_hemisphere", 1)) == 0))
-                    self._set("snow_ice", glsp["name"], pname, tv[pname])
-                    self.labels[f"{glsp['name']}:{tp['name']}:output"] = "glacier_snowpack_transfo"
+                    self._set(slots["snow_ice"], glsp["name"], pname, tv[pname])
+                    label(f"{glsp['name']}:{tp['name']}:output", "glacier_snowpack_transfo")
+        if glacier is not None:
             for name, slot in ((b1, "k_snow"), (b2, "k_ice")):
                 bb = basin_bricks.get(name)
                 if bb is None or bb["kind"] != "storage" or _proc_kinds(bb) != ["outflow:linear"] or \
@@ -404,8 +438,9 @@ class CompiledStructure:
         self.labels[f"{quick_name}:{qp['name']}:output"] = "quick_runoff"
 
         known = {self.ground_name, slow_name, quick_name} | set(snowpacks)
-        if glacier is not None:
-            known.add(glacier["name"])
+        for g in (glacier, glacier2):
+            if g is not None:
+                known.add(g["name"])
         if slow2_name:
             known.add(slow2_name)
         extra = set(bricks) - known
@@ -475,6 +510,13 @@ class CompiledStructure:
     def record_slots(self, labels):
         return [self.labels[label] for label in labels]
 
+    def recorded(self, eng, label, set_index=0):
+        """ModelHydro::GetHydroUnitValues(label) [T x basin units] from the engine's recorder (the second glacier
+        cover's labels live in the twin units' columns)."""
+        values = eng.get_recorded(self.labels[label], set_index)
+        layout = getattr(self, "layout", None)
+        return values if layout is None else layout.gather(values, label in self.twin_labels)
+
 
 def slope_m_per_m(value: float, unit: str) -> np.float32:
     """HydroUnitProperty::GetValue(..., "m/m") + the float32 cast of HydroUnit::GetPropertyFloat
@@ -494,23 +536,72 @@ def slope_degrees(value: float, unit: str) -> np.float32:
     raise ValueError(f"The unit 'degrees' is not supported for the property 'slope' given in {unit!r}.")
 
 
+class UnitLayout:
+    """Engine units of a basin: the basin's units in order, then one TWIN per unit that carries the glacier bricks when
+    the structure has a second glacier cover (hbk_set_unit_twins). twin_of[engine unit] = basin unit or -1; twin_col[basin
+    unit] = engine column of its twin or -1."""
+
+    def __init__(self, n_basin, twins_for):
+        self.n_basin = n_basin
+        self.twin_of = [-1] * n_basin + list(twins_for)
+        self.n_engine = len(self.twin_of)
+        self.twin_col = [-1] * n_basin
+        for k, u in enumerate(twins_for):
+            self.twin_col[u] = n_basin + k
+
+    @property
+    def has_twins(self):
+        return self.n_engine > self.n_basin
+
+    def expand(self, per_unit, axis=-1):
+        """A per-basin-unit array -> per-engine-unit (a twin takes its unit's value: same forcing, area, elevation...)."""
+        a = np.asarray(per_unit)
+        if not self.has_twins:
+            return a
+        return np.concatenate([a, np.take(a, self.twin_of[self.n_basin:], axis=axis)], axis=axis)
+
+    def gather(self, engine_values, twin):
+        """Engine columns [... x n_engine] -> basin columns [... x n_basin] of a recorded series: the units' own columns,
+        or for a label of the second glacier cover the twins' columns (NaN where a unit has no twin)."""
+        a = np.asarray(engine_values)
+        if not self.has_twins:
+            return a
+        own = a[..., :self.n_basin]
+        if not twin:
+            return own
+        out = np.full_like(own, np.nan)
+        idx = [u for u, c in enumerate(self.twin_col) if c >= 0]
+        out[..., idx] = a[..., [self.twin_col[u] for u in idx]]
+        return out
+
+
 def build_engine(structures, units, solver, n_steps, device=0, time_step_days=1.0, start_mjd=44605.0):
     """Compile + create an engine + upload the basin. `units` as in tests/golden (basin order).
     start_mjd: modified Julian date of time step 0 (default 1981-01-01), read by day-of-year processes."""
     cs = CompiledStructure(structures, solver, time_step_days, start_mjd)
-    eng = _e.Engine(cs.hbk, len(units), n_steps, device)
-    area = [u["area"] for u in units]
-    elev = [u.get("elevation", 0.0) for u in units]
-    slope = None
-    if cs.hbk.quick_kind == _e.QUICK_SOCONT:
-        slope = [slope_m_per_m(*u["slope"]) for u in units]
     covers = [u["land_covers"] for u in units]
     gv = cs.assign_structure_variants(covers)
+    layout = UnitLayout(len(units), [u for u, g in enumerate(gv) if g] if cs.glacier2_name else [])
+    cs.layout = layout
+    eng = _e.Engine(cs.hbk, layout.n_engine, n_steps, device)
+    eng.layout = layout
+    area = layout.expand([u["area"] for u in units])
+    elev = layout.expand([u.get("elevation", 0.0) for u in units])
+    slope = None
+    if cs.hbk.quick_kind == _e.QUICK_SOCONT:
+        slope = layout.expand([slope_m_per_m(*u["slope"]) for u in units])
     fg = [dict(c).get(cs.ground_name, 1.0) for c in covers]
     fgl = [dict(c).get(cs.glacier_name, 0.0) if cs.glacier_name else 0.0 for c in covers]
+    if layout.has_twins:
+        # a twin: no ground (a null brick), the second cover's fraction as its glacier fraction
+        fg = fg + [0.0] * (layout.n_engine - layout.n_basin)
+        fgl = fgl + [dict(covers[u]).get(cs.glacier2_name, 0.0) for u in layout.twin_of[layout.n_basin:]]
+        gv = gv + [1] * (layout.n_engine - layout.n_basin)
+        eng.set_unit_twins(layout.twin_of)
     eng.set_units(area, elev, slope, gv, fg, fgl)
     if cs.hbk.melt_kind == _e.MELT_DEGREE_DAY_ASPECT:
-        eng.set_unit_aspect([u.get("aspect_class") or u.get("properties", {}).get("aspect_class") for u in units])
+        eng.set_unit_aspect(layout.expand(
+            [_e.ASPECT.get(u.get("aspect_class") or u.get("properties", {}).get("aspect_class"), -1) for u in units]))
     if cs.hbk.snow_slide_kind != _e.SNOW_SLIDE_NONE:
         # hydro_units.py set_connectivity -> SettingsBasin::AddLateralConnection: (receiver position, fraction) per unit
         givers, receivers, fractions = [], [], []

@@ -115,6 +115,10 @@ enum {
     /* transport:snow_slide (ProcessLateralSnowSlide.cpp:24-31), the same values on every snowpack that slides */
     HBK_P_SLIDE_COEFF, HBK_P_SLIDE_EXP, HBK_P_SLIDE_MIN_SLOPE, HBK_P_SLIDE_MAX_SLOPE, HBK_P_SLIDE_MIN_HOLDING_DEPTH,
     HBK_P_SLIDE_MAX_SNOW_DEPTH,
+    /* second glacier cover of a unit (hbk_set_unit_twins; glacier_ice + glacier_debris of the reference's Socont,
+     * parameters.py:1766-1835): its snowpack's and its ice's melt parameters, snow -> ice transformation, sublimation */
+    HBK_P_GLACIER2_SNOW_DDF, HBK_P_GLACIER2_SNOW_TMELT, HBK_P_ICE2_DDF, HBK_P_ICE2_TMELT, HBK_P_SNOW_ICE2,
+    HBK_P_GLACIER2_SUBLIMATION, HBK_P_GLACIER2_SNOW_MELT_B, HBK_P_GLACIER2_SNOW_MELT_C, HBK_P_ICE2_MELT_B, HBK_P_ICE2_MELT_C,
     HBK_N_PARAMS
 };
 
@@ -160,6 +164,16 @@ int hbk_set_units(hbk_engine* e, const double* area_m2, const double* elevation_
  * ProcessMeltDegreeDayAspect::SetHydroUnitProperties, ProcessMeltDegreeDayAspect.cpp:35-37); required before hbk_run
  * when melt_kind is HBK_MELT_DEGREE_DAY_ASPECT. */
 int hbk_set_unit_aspect(hbk_engine* e, const int32_t* aspect_class);
+
+/* Several glacier covers per hydro unit (models/socont.py:131-140: every land cover of type glacier gets its own brick,
+ * snowpack, melt parameters and area fraction; all of them deposit into the same two sub-basin stores). The columns of a
+ * unit's land covers are independent of one another, so the engine carries the SECOND glacier cover of a unit as a twin
+ * unit: an extra entry of hbk_set_units with the same area, elevation, slope and forcing, ground fraction 0 (a null brick:
+ * its soil and surface stores stay empty) and the second cover's fraction as its glacier fraction, whose glacier
+ * parameters come from the HBK_P_GLACIER2_* / HBK_P_ICE2_* slots. twin_of[n_units]: index of the unit a twin belongs to,
+ * -1 for an ordinary unit. Twins do not count towards the basin area (outlet weights area / basinArea,
+ * ModelBuilder.cpp:468). Call before hbk_set_units. Dated actions and lateral connections are refused with twins. */
+int hbk_set_unit_twins(hbk_engine* e, const int32_t* twin_of);
 
 /* SettingsBasin::AddLateralConnection (hydro_units.py set_connectivity; ModelBuilder.cpp:476-508): n connections
  * giver -> receiver (unit indices in basin order) with the share of the giver's sliding snow that the receiver gets, in

@@ -246,6 +246,17 @@ def rain_only_bundles(ref):
         save(f"splitter_rain_{solver}_nosnow_{name}", meta, forcing, q, rec)
 
 
+def two_glaciers_bundles(ref):
+    """glacier_ice + glacier_debris in one unit (the engine's twin units, hbk_set_unit_twins)."""
+    import ref_two_glaciers_case as rt
+
+    for solver, kw, name in (("rk4", dict(nsoil=1), "finite_1store"), ("rk4", dict(nsoil=2, infinite=True), "infinite_2store"),
+                             ("crank_nicolson", dict(nsoil=1, transfo="transform:snow_ice_constant"), "snowice_1store"),
+                             ("heun_explicit", dict(nsoil=1, melt="melt:degree_day_aspect"), "aspect_1store")):
+        meta, forcing, q, rec = rt.run_reference(ref, solver, **kw)
+        save(f"two_glaciers_{solver}_{name}", meta, forcing, q, rec)
+
+
 def slow_order_bundles(ref):
     """hbk_structure.slow_process_order = 1 (the process order of core/tests/src/helpers.cpp), two soil stores."""
     import ref_slow_order_case as ro
@@ -269,6 +280,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "threshold":
         threshold_splitter_bundles(ref)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "two_glaciers":
+        two_glaciers_bundles(ref)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "rain_only":
         rain_only_bundles(ref)
@@ -337,6 +351,7 @@ def main():
     snow_slide_bundles(ref)
     threshold_splitter_bundles(ref)
     rain_only_bundles(ref)
+    two_glaciers_bundles(ref)
     slow_order_bundles(ref)
 
 
