@@ -345,37 +345,40 @@ PYBIND11_MODULE(_hydrobricks, m) {
             auto a = mh.GetHydroUnitAreas();
             return f64arr(a.size(), a.data());
         })
+        .def("engine_unit_count", &hb::ModelHydro::EngineUnitCount)
+        .def("twin_of", [](hb::ModelHydro& mh) {
+            auto v = mh.TwinOf();
+            return i32arr(v.size(), v.data());
+        }, "Engine unit -> basin unit whose second glacier cover it carries, -1 for the units themselves (empty: no twins).")
         .def("get_state", [](hb::ModelHydro& mh, int slot) {
-            f64arr out({(py::ssize_t)mh.SetCount(), (py::ssize_t)mh.UnitCount()});
+            f64arr out({(py::ssize_t)mh.SetCount(), (py::ssize_t)mh.EngineUnitCount()});
             mh.GetState(slot, out.mutable_data());
             return out;
         }, "state_slot"_a)
         // water-balance totals (Logger.cpp:168-339): area-weighted ET sum, end-of-run storage contents
         .def("get_total_et", [](hb::ModelHydro& mh) {
-            const int T = mh.StepCount(), U = mh.UnitCount();
+            const int T = mh.StepCount(), U = mh.EngineUnitCount();
             std::vector<double> et((size_t)T * U);
             mh.GetRecorded(HBK_R_SLOW_ET, 0, et.data());
-            auto areas = mh.GetHydroUnitAreas();
-            double total = 0, sum = 0;
-            for (double a : areas) total += a;
+            const auto w = mh.EngineUnitWeights();
+            double sum = 0;
             for (int t = 0; t < T; ++t)
                 for (int u = 0; u < U; ++u) {
                     double v = et[(size_t)t * U + u];
-                    if (v == v) sum += v * (areas[u] / total);
+                    if (v == v) sum += v * w[u];
                 }
             return sum;
         })
         .def("get_total_water_storage_changes", [](hb::ModelHydro& mh) {
-            const int U = mh.UnitCount(), P = mh.SetCount();
+            const int U = mh.EngineUnitCount(), P = mh.SetCount();
             std::vector<double> g, gl, buf((size_t)P * U);
             mh.fractions(g, gl);
-            auto areas = mh.GetHydroUnitAreas();
-            double total = 0, sum = 0;
-            for (double a : areas) total += a;
+            const auto w = mh.EngineUnitWeights();
+            double sum = 0;
             const int slots[5] = {HBK_S_GROUND_WATER, HBK_S_GLACIER_WATER, HBK_S_SLOW, HBK_S_SLOW2, HBK_S_QUICK};
             for (int k = 0; k < 5; ++k) {
                 mh.GetState(slots[k], buf.data());
-                for (int u = 0; u < U; ++u) sum += buf[u] * (k == 0 ? g[u] : (k == 1 ? gl[u] : 1.0)) * (areas[u] / total);
+                for (int u = 0; u < U; ++u) sum += buf[u] * (k == 0 ? g[u] : (k == 1 ? gl[u] : 1.0)) * w[u];
             }
             if (mh.compiled().st.has_glacier) {
                 std::vector<double> b((size_t)P * 2);
@@ -385,27 +388,25 @@ PYBIND11_MODULE(_hydrobricks, m) {
             return sum;
         })
         .def("get_total_snow_storage_changes", [](hb::ModelHydro& mh) {
-            const int U = mh.UnitCount(), P = mh.SetCount();
+            const int U = mh.EngineUnitCount(), P = mh.SetCount();
             std::vector<double> g, gl, buf((size_t)P * U);
             mh.fractions(g, gl);
-            auto areas = mh.GetHydroUnitAreas();
-            double total = 0, sum = 0;
-            for (double a : areas) total += a;
+            const auto w = mh.EngineUnitWeights();
+            double sum = 0;
             mh.GetState(HBK_S_GROUND_SNOW, buf.data());
-            for (int u = 0; u < U; ++u) sum += buf[u] * g[u] * (areas[u] / total);
+            for (int u = 0; u < U; ++u) sum += buf[u] * g[u] * w[u];
             mh.GetState(HBK_S_GLACIER_SNOW, buf.data());
-            for (int u = 0; u < U; ++u) sum += buf[u] * gl[u] * (areas[u] / total);
+            for (int u = 0; u < U; ++u) sum += buf[u] * gl[u] * w[u];
             return sum;
         })
         .def("get_total_glacier_storage_changes", [](hb::ModelHydro& mh) {
-            const int U = mh.UnitCount(), P = mh.SetCount();
+            const int U = mh.EngineUnitCount(), P = mh.SetCount();
             std::vector<double> g, gl, buf((size_t)P * U);
             mh.fractions(g, gl);
-            auto areas = mh.GetHydroUnitAreas();
-            double total = 0, sum = 0;
-            for (double a : areas) total += a;
+            const auto w = mh.EngineUnitWeights();
+            double sum = 0;
             mh.GetState(HBK_S_ICE, buf.data());
-            for (int u = 0; u < U; ++u) sum += buf[u] * gl[u] * (areas[u] / total);
+            for (int u = 0; u < U; ++u) sum += buf[u] * gl[u] * w[u];
             return sum;
         })
         // ModelHydro::DumpOutputs -> ResultWriter::WriteNetCDF (ResultWriter.cpp:8-87): the same variables under the same
@@ -448,6 +449,8 @@ PYBIND11_MODULE(_hydrobricks, m) {
             st["north_hemisphere"] = c->st.north_hemisphere;
             st["start_mjd"] = c->st.start_mjd;
             st["sublimation_kind"] = c->st.sublimation_kind;
+            st["melt_kind"] = c->st.melt_kind;
+            st["snow_slide_kind"] = c->st.snow_slide_kind;
             py::dict out;
             out["structure"] = st;
             out["params"] = f32arr(HBK_N_PARAMS, c->params);
@@ -458,6 +461,10 @@ PYBIND11_MODULE(_hydrobricks, m) {
             out["param_index"] = index;
             out["ground_name"] = c->groundName;
             out["glacier_name"] = c->glacierName;
+            out["glacier2_name"] = c->glacier2Name;
+            py::list twins;
+            for (auto& l : c->twinLabels) twins.append(l);
+            out["twin_labels"] = twins;
             return out;
         },
         "model_settings"_a, "time_step_days"_a = 1.0, "start_mjd"_a = 44605.0);

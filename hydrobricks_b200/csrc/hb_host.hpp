@@ -601,7 +601,8 @@ struct Compiled {
     float params[HBK_N_PARAMS] = {};
     std::map<std::pair<string, string>, int> paramIndex;
     std::map<string, int> labels;  // log label -> HBK_R_* slot
-    string groundName, glacierName;
+    string groundName, glacierName, glacier2Name;
+    std::set<string> twinLabels;  // log labels of the second glacier cover: recorded in the twin units' columns
     int glacierStructureId = -1;
     std::map<int, std::set<string>> variantCovers;
     vector<std::pair<string, string>> brickKinds;  // (name, kind) over all variants, for "type:" components
@@ -795,6 +796,9 @@ struct Compiled {
         // land covers
         const Brick* ground = nullptr;
         const Brick* glacier = nullptr;
+        // a second glacier cover (glacier_ice + glacier_debris, models/socont.py:131-140) is carried by twin units
+        // (hbk_set_unit_twins): the same bricks once more with the HBK_P_GLACIER2_* / HBK_P_ICE2_* parameter slots
+        const Brick* glacier2 = nullptr;
         int nCovers = 0;
         for (auto& b : full.hydroUnitBricks) {
             if (!b.isLandCover) continue;
@@ -803,17 +807,19 @@ struct Compiled {
                 if (ground) throw Unsupported("more than one generic land cover");
                 ground = &b;
             } else if (b.kind == "glacier") {
-                if (glacier) throw Unsupported("more than one glacier cover");
-                glacier = &b;
+                if (glacier2) throw Unsupported("more than two glacier covers");
+                (glacier ? glacier2 : glacier) = &b;
             }
         }
-        if (!ground || nCovers != 1 + (glacier ? 1 : 0))
-            throw Unsupported("expected one generic land cover and at most one glacier cover");
+        if (!ground || nCovers != 1 + (glacier ? 1 : 0) + (glacier2 ? 1 : 0))
+            throw Unsupported("expected one generic land cover and at most two glacier covers");
         groundName = ground->name;
         glacierName = glacier ? glacier->name : "";
+        glacier2Name = glacier2 ? glacier2->name : "";
         {
             vector<string> want = {ground->name};
             if (glacier) want.push_back(glacier->name);
+            if (glacier2) want.push_back(glacier2->name);
             std::sort(want.begin(), want.end());
             std::sort(rainTargets.begin(), rainTargets.end());
             if (want != rainTargets) throw Unsupported("rain must go to every land cover");
@@ -899,66 +905,94 @@ struct Compiled {
         }
 
         string b1, b2;
-        if (glacier) {
+        const Brick* glacierCovers[2] = {glacier, glacier2};
+        for (int second = 0; second < 2; ++second) {
+            const Brick* cover = glacierCovers[second];
+            if (!cover) continue;
+            auto lab = [&](const string& l, const string& slot) {
+                label(l, slot);
+                if (second) twinLabels.insert(l);
+            };
             st.has_glacier = 1;
             {
-                const vector<string> gk = kinds(*glacier);
+                const vector<string> gk = kinds(*cover);
                 if (gk.size() != 2 || gk[0] != "outflow:direct" || meltKindOf(gk[1]) < 0)
                     throw Unsupported("glacier cover: expected outflow:direct + melt:degree_day|degree_day_aspect|"
                                       "temperature_index");
             }
-            for (auto& p : glacier->processes)
+            for (auto& p : cover->processes)
                 if (p.outputs.empty() || !p.outputs[0].instantaneous) throw Unsupported("glacier outputs must be instantaneous");
-            b1 = target(glacier->processes[0]);
-            b2 = target(glacier->processes[1]);
             bool hasInf, hasNoMelt;
-            float inf = paramOf(glacier->parameters, "infinite_storage", &hasInf);
-            float noMelt = paramOf(glacier->parameters, "no_melt_when_snow_cover", &hasNoMelt);
-            st.glacier_infinite_storage = hasInf && std::fabs(inf) > 1.1920929e-07f ? 1 : 0;  // Glacier.cpp:23-28
-            st.glacier_no_melt_when_snow_cover = hasNoMelt && noMelt > 0 ? 1 : 0;
-            setMelt(glacier->name, glacier->processes[1], HBK_P_ICE_DDF, HBK_P_ICE_TMELT, HBK_P_ICE_MELT_B, HBK_P_ICE_MELT_C);
-            const string& n = glacier->name;
-            label(n + ":water_content", "glacier_water");
-            label(n + ":ice_content", "glacier_ice");
-            label(n + ":" + glacier->processes[0].name + ":output", "glacier_outflow");
-            label(n + ":" + glacier->processes[1].name + ":output", "glacier_melt");
+            float inf = paramOf(cover->parameters, "infinite_storage", &hasInf);
+            float noMelt = paramOf(cover->parameters, "no_melt_when_snow_cover", &hasNoMelt);
+            const int infinite = hasInf && std::fabs(inf) > 1.1920929e-07f ? 1 : 0;  // Glacier.cpp:23-28
+            const int noMeltFlag = hasNoMelt && noMelt > 0 ? 1 : 0;
+            if (second) {
+                if (target(cover->processes[0]) != b1 || target(cover->processes[1]) != b2 ||
+                    infinite != st.glacier_infinite_storage || noMeltFlag != st.glacier_no_melt_when_snow_cover)
+                    throw Unsupported("the glacier covers must share their options and their sub-basin stores");
+            } else {
+                b1 = target(cover->processes[0]);
+                b2 = target(cover->processes[1]);
+                st.glacier_infinite_storage = infinite;
+                st.glacier_no_melt_when_snow_cover = noMeltFlag;
+            }
+            setMelt(cover->name, cover->processes[1], second ? HBK_P_ICE2_DDF : HBK_P_ICE_DDF,
+                    second ? HBK_P_ICE2_TMELT : HBK_P_ICE_TMELT, second ? HBK_P_ICE2_MELT_B : HBK_P_ICE_MELT_B,
+                    second ? HBK_P_ICE2_MELT_C : HBK_P_ICE_MELT_C);
+            const string& n = cover->name;
+            lab(n + ":water_content", "glacier_water");
+            lab(n + ":ice_content", "glacier_ice");
+            lab(n + ":" + cover->processes[0].name + ":output", "glacier_outflow");
+            lab(n + ":" + cover->processes[1].name + ":output", "glacier_melt");
+            known.insert(cover->name);
             if (noSnow) {
                 if (st.glacier_no_melt_when_snow_cover)  // IceContainer.cpp:10-32 needs the related snowpack
                     throw Unsupported("No snowpack provided for the glacier melt limitation.");
-            } else {
-                const SnowpackInfo glInfo = snowpackOf(*glacier);
-                const Brick& glsp = *glInfo.brick;
-                if ((glInfo.sublim == nullptr) != (gInfo.sublim == nullptr))
-                    throw Unsupported("sublimation must be on every snowpack or on none");
-                if (glInfo.sublim)
-                    setSublimation(glsp, *glInfo.sublim, HBK_P_GLACIER_SUBLIMATION, "glacier_snowpack_sublimation");
-                setMelt(glsp.name, glsp.processes[0], HBK_P_GLACIER_SNOW_DDF, HBK_P_GLACIER_SNOW_TMELT,
-                        HBK_P_GLACIER_SNOW_MELT_B, HBK_P_GLACIER_SNOW_MELT_C);
-                label(glsp.name + ":water_content", "glacier_snowpack_water");
-                label(glsp.name + ":snow_content", "glacier_snowpack_snow");
-                label(glsp.name + ":" + glsp.processes[0].name + ":output", "glacier_snowpack_melt");
-                snowpacks.push_back(glsp.name);
-                known.insert(glsp.name);
-                if (glInfo.slide) slideOn.push_back({glsp.name, glInfo.slide});
-                if (glInfo.transfo) {
-                    const Process& tp = *glInfo.transfo;
-                    st.snow_ice_kind = snowIceKindOf(tp.kind);
-                    bool has;
-                    string pname;
-                    if (st.snow_ice_kind == HBK_SNOW_ICE_CONSTANT) {
-                        paramOf(tp.parameters, "snow_ice_transformation_rate", &has);
-                        pname = has ? "snow_ice_transformation_rate" : "rate";
-                    } else {
-                        paramOf(tp.parameters, "snow_ice_transformation_basal_acc_coeff", &has);
-                        pname = has ? "snow_ice_transformation_basal_acc_coeff" : "basal_acc_coeff";
-                        bool hasNh;
-                        const float nh = paramOf(tp.parameters, "north_hemisphere", &hasNh);
-                        st.north_hemisphere = (hasNh && nh == 0) ? 0 : 1;
-                    }
-                    set(HBK_P_SNOW_ICE, glsp.name, pname, paramOf(tp.parameters, pname));
-                    label(glsp.name + ":" + tp.name + ":output", "glacier_snowpack_transfo");
-                }
+                continue;
             }
+            const SnowpackInfo glInfo = snowpackOf(*cover);
+            const Brick& glsp = *glInfo.brick;
+            if ((glInfo.sublim == nullptr) != (gInfo.sublim == nullptr))
+                throw Unsupported("sublimation must be on every snowpack or on none");
+            if (glInfo.sublim) {
+                setSublimation(glsp, *glInfo.sublim, second ? HBK_P_GLACIER2_SUBLIMATION : HBK_P_GLACIER_SUBLIMATION,
+                               "glacier_snowpack_sublimation");
+                if (second) twinLabels.insert(glsp.name + ":" + glInfo.sublim->name + ":output");
+            }
+            setMelt(glsp.name, glsp.processes[0], second ? HBK_P_GLACIER2_SNOW_DDF : HBK_P_GLACIER_SNOW_DDF,
+                    second ? HBK_P_GLACIER2_SNOW_TMELT : HBK_P_GLACIER_SNOW_TMELT,
+                    second ? HBK_P_GLACIER2_SNOW_MELT_B : HBK_P_GLACIER_SNOW_MELT_B,
+                    second ? HBK_P_GLACIER2_SNOW_MELT_C : HBK_P_GLACIER_SNOW_MELT_C);
+            lab(glsp.name + ":water_content", "glacier_snowpack_water");
+            lab(glsp.name + ":snow_content", "glacier_snowpack_snow");
+            lab(glsp.name + ":" + glsp.processes[0].name + ":output", "glacier_snowpack_melt");
+            snowpacks.push_back(glsp.name);
+            known.insert(glsp.name);
+            if (glInfo.slide) slideOn.push_back({glsp.name, glInfo.slide});
+            const int kind = glInfo.transfo ? snowIceKindOf(glInfo.transfo->kind) : HBK_SNOW_ICE_NONE;
+            if (second && kind != st.snow_ice_kind)
+                throw Unsupported("the snow -> ice transformation must be the same on every glacier snowpack");
+            if (glInfo.transfo) {
+                const Process& tp = *glInfo.transfo;
+                st.snow_ice_kind = kind;
+                bool has;
+                string pname;
+                if (st.snow_ice_kind == HBK_SNOW_ICE_CONSTANT) {
+                    paramOf(tp.parameters, "snow_ice_transformation_rate", &has);
+                    pname = has ? "snow_ice_transformation_rate" : "rate";
+                } else {
+                    paramOf(tp.parameters, "snow_ice_transformation_basal_acc_coeff", &has);
+                    pname = has ? "snow_ice_transformation_basal_acc_coeff" : "basal_acc_coeff";
+                    bool hasNh;
+                    const float nh = paramOf(tp.parameters, "north_hemisphere", &hasNh);
+                    st.north_hemisphere = (hasNh && nh == 0) ? 0 : 1;
+                }
+                set(second ? HBK_P_SNOW_ICE2 : HBK_P_SNOW_ICE, glsp.name, pname, paramOf(tp.parameters, pname));
+                lab(glsp.name + ":" + tp.name + ":output", "glacier_snowpack_transfo");
+            }
+        }
+        if (glacier) {
             known.insert(glacier->name);
             int slot[2] = {HBK_P_K_SNOW, HBK_P_K_ICE};
             const string* names[2] = {&b1, &b2};
@@ -1364,31 +1398,50 @@ class ModelHydro {
         if (_units.empty()) throw std::invalid_argument("Basin initialization failed: no hydro unit");
         hbk_engine_destroy(_e);
         _e = nullptr;
-        if (hbk_engine_create(&_c->st, (int)_units.size(), _nSteps, device, &_e) != HBK_OK)
+        // Engine units: the basin's units in order, then one TWIN per unit that carries the glacier bricks when the
+        // structure has a second glacier cover (hbk_set_unit_twins): same area, elevation, slope and forcing, no ground,
+        // the second cover's fraction as its glacier fraction.
+        const int nBasin = (int)_units.size();
+        _twinOf.assign(nBasin, -1);
+        _twinCol.assign(nBasin, -1);
+        if (!_c->glacier2Name.empty()) {
+            for (int u = 0; u < nBasin; ++u) {
+                if (_c->glacierVariantOf(_units[u].landCovers)) {
+                    _twinCol[u] = (int)_twinOf.size();
+                    _twinOf.push_back(u);
+                }
+            }
+        }
+        const int U = (int)_twinOf.size();
+        if (hbk_engine_create(&_c->st, U, _nSteps, device, &_e) != HBK_OK)
             throw std::invalid_argument("hbk_engine_create failed: no usable CUDA device (the B200 engine has no CPU fallback)");
-        const int U = (int)_units.size();
         vector<double> area(U), elev(U), fg(U, 1.0), fgl(U, 0.0);
         vector<float> slope(U, 0.0f);
         vector<int32_t> gv(U, 0);
-        for (int u = 0; u < U; ++u) {
-            area[u] = _units[u].area;
-            elev[u] = _units[u].elevation;
+        for (int e = 0; e < U; ++e) {
+            const bool twin = e >= nBasin;
+            const int u = twin ? _twinOf[e] : e;
+            area[e] = _units[u].area;
+            elev[e] = _units[u].elevation;
             if (_c->st.quick_kind == HBK_QUICK_SOCONT) {
                 if (!_units[u].hasSlope) throw std::invalid_argument("No property with the name 'slope' was found.");
-                slope[u] = slopeMPerM(_units[u].slopeValue, _units[u].slopeUnit);
+                slope[e] = slopeMPerM(_units[u].slopeValue, _units[u].slopeUnit);
             }
-            gv[u] = _c->glacierVariantOf(_units[u].landCovers);
+            gv[e] = twin ? 1 : _c->glacierVariantOf(_units[u].landCovers);
+            if (twin) fg[e] = 0.0;
             for (auto& lc : _units[u].landCovers) {
-                if (lc.first == _c->groundName) fg[u] = lc.second;
-                if (!_c->glacierName.empty() && lc.first == _c->glacierName) fgl[u] = lc.second;
+                if (!twin && lc.first == _c->groundName) fg[e] = lc.second;
+                if (!twin && !_c->glacierName.empty() && lc.first == _c->glacierName) fgl[e] = lc.second;
+                if (twin && lc.first == _c->glacier2Name) fgl[e] = lc.second;
             }
         }
+        if (U > nBasin) check(hbk_set_unit_twins(_e, _twinOf.data()));
         check(hbk_set_units(_e, area.data(), elev.data(), _c->st.quick_kind == HBK_QUICK_SOCONT ? slope.data() : nullptr,
                             gv.data(), fg.data(), fgl.data()));
         if (_c->st.snow_slide_kind != HBK_SNOW_SLIDE_NONE) {
             // ModelBuilder.cpp:476-508: connections by unit id -> basin positions, in the order they were added
             std::map<int, int> pos;
-            for (int u = 0; u < U; ++u) pos[_units[u].id] = u;
+            for (int u = 0; u < nBasin; ++u) pos[_units[u].id] = u;
             vector<int32_t> giver, receiver;
             vector<double> fraction;
             for (auto& c : bs.connections) {
@@ -1400,20 +1453,21 @@ class ModelHydro {
                 fraction.push_back(c.fraction);
             }
             vector<float> slopeDeg(U, 0.0f);
-            for (int u = 0; u < U; ++u) {
+            for (int e = 0; e < U; ++e) {
+                const int u = unitOf(e);
                 if (!_units[u].hasSlope) throw std::invalid_argument("No property with the name 'slope' was found.");
                 const string& su = _units[u].slopeUnit;
                 // HydroUnitProperty::GetValue (HydroUnitProperty.cpp:19-49) converts degrees to other units, never back
                 if (su != "degrees" && su != "degree" && su != "deg" && su != "°")
                     throw std::invalid_argument("The unit 'degrees' is not supported for the property 'slope'.");
-                slopeDeg[u] = (float)_units[u].slopeValue;
+                slopeDeg[e] = (float)_units[u].slopeValue;
             }
             check(hbk_set_lateral_connections(_e, (int)giver.size(), giver.data(), receiver.data(), fraction.data(),
                                               slopeDeg.data()));
         }
         if (_c->st.melt_kind == HBK_MELT_DEGREE_DAY_ASPECT) {
             vector<int32_t> aspect(U);
-            for (int u = 0; u < U; ++u) aspect[u] = Compiled::aspectOf(_units[u].aspectClass);
+            for (int e = 0; e < U; ++e) aspect[e] = Compiled::aspectOf(_units[unitOf(e)].aspectClass);
             check(hbk_set_unit_aspect(_e, aspect.data()));
         }
         check(hbk_set_spinup_steps(_e, (int)(ms.spinupDays / _dt)));
@@ -1455,14 +1509,14 @@ class ModelHydro {
         _stationVars.clear();
     }
     bool AttachTimeSeriesToHydroUnits() {
-        const int U = (int)_units.size();
+        const int U = EngineUnitCount();  // a twin reads its unit's column
         for (auto& kv : _series) {
             const Series& s = kv.second;
             std::map<int, int> pos;
             for (int i = 0; i < (int)s.ids.size(); ++i) pos[s.ids[i]] = i;
             vector<int> cols(U);
             for (int u = 0; u < U; ++u) {
-                auto it = pos.find(_units[u].id);
+                auto it = pos.find(_units[unitOf(u)].id);
                 if (it == pos.end()) return false;
                 cols[u] = it->second;
             }
@@ -1540,6 +1594,28 @@ class ModelHydro {
     // ---- results
     int StepCount() const { return _nSteps; }
     int UnitCount() const { return (int)_units.size(); }
+    // engine units = the basin's units + the twins that carry a second glacier cover (hbk_set_unit_twins)
+    int EngineUnitCount() const { return _twinOf.empty() ? (int)_units.size() : (int)_twinOf.size(); }
+    int unitOf(int engineUnit) const {
+        return (engineUnit < (int)_units.size() || _twinOf.empty()) ? engineUnit : _twinOf[engineUnit];
+    }
+    vector<int> TwinOf() const { return _twinOf; }
+    // a recorded series [T x engine units] -> [T x basin units]: the units' own columns, or the twins' columns for a label
+    // of the second glacier cover (NaN where a unit has no twin)
+    void gatherRecorded(int slot, int set, bool twinLabel, double* out) {
+        const int U = UnitCount(), UE = EngineUnitCount();
+        if (UE == U) {
+            check(hbk_get_recorded(_e, slot, set, out));
+            return;
+        }
+        vector<double> buf((size_t)_nSteps * UE);
+        check(hbk_get_recorded(_e, slot, set, buf.data()));
+        for (int t = 0; t < _nSteps; ++t)
+            for (int u = 0; u < U; ++u) {
+                const int col = twinLabel ? _twinCol[u] : u;
+                out[(size_t)t * U + u] = col < 0 ? std::nan("") : buf[(size_t)t * UE + col];
+            }
+    }
     int SetCount() const { return _nSets; }
     void GetOutlet(int first, int n, double* out) { check(hbk_get_outlet(_e, first, n, out)); }
     vector<string> GetRecordedHydroUnitLabels() const { return _labels; }
@@ -1550,7 +1626,7 @@ class ModelHydro {
     void GetHydroUnitValues(const string& label, int set, double* out) {
         auto it = _c->labels.find(label);
         if (it == _c->labels.end()) throw std::runtime_error("Label '" + label + "' is not recorded.");
-        check(hbk_get_recorded(_e, it->second, set, out));
+        gatherRecorded(it->second, set, _c->twinLabels.count(label) > 0, out);
     }
     void GetHydroUnitFractions(const string& label, double* out) {
         int slot;
@@ -1558,10 +1634,12 @@ class ModelHydro {
             slot = HBK_R_FRACTION_GROUND;
         } else if (!_c->glacierName.empty() && label == _c->glacierName) {
             slot = HBK_R_FRACTION_GLACIER;
+        } else if (!_c->glacier2Name.empty() && label == _c->glacier2Name) {
+            slot = HBK_R_FRACTION_GLACIER;  // of the twin units
         } else {
             throw std::runtime_error("Fraction label '" + label + "' is not recorded.");
         }
-        check(hbk_get_recorded(_e, slot, 0, out));
+        gatherRecorded(slot, 0, !_c->glacier2Name.empty() && label == _c->glacier2Name, out);
     }
     vector<int> GetHydroUnitIds() const {
         vector<int> ids;
@@ -1586,14 +1664,28 @@ class ModelHydro {
     const Compiled& compiled() const { return *_c; }
     const vector<UnitSettings>& units() const { return _units; }
     hbk_engine* engine() { return _e; }
+    // initial land-cover fractions and basin weights (area / basin area) per ENGINE unit: a twin has no ground, the
+    // second glacier cover's fraction, and its unit's weight
     void fractions(vector<double>& g, vector<double>& gl) const {
-        g.assign(_units.size(), 1.0);
-        gl.assign(_units.size(), 0.0);
-        for (size_t u = 0; u < _units.size(); ++u)
-            for (auto& lc : _units[u].landCovers) {
-                if (lc.first == _c->groundName) g[u] = lc.second;
-                if (!_c->glacierName.empty() && lc.first == _c->glacierName) gl[u] = lc.second;
+        const int UE = EngineUnitCount(), U = UnitCount();
+        g.assign(UE, 1.0);
+        gl.assign(UE, 0.0);
+        for (int e = 0; e < UE; ++e) {
+            const bool twin = e >= U;
+            if (twin) g[e] = 0.0;
+            for (auto& lc : _units[unitOf(e)].landCovers) {
+                if (!twin && lc.first == _c->groundName) g[e] = lc.second;
+                if (!twin && !_c->glacierName.empty() && lc.first == _c->glacierName) gl[e] = lc.second;
+                if (twin && lc.first == _c->glacier2Name) gl[e] = lc.second;
             }
+        }
+    }
+    vector<double> EngineUnitWeights() const {
+        double total = 0;
+        for (auto& u : _units) total += u.area;
+        vector<double> w(EngineUnitCount());
+        for (int e = 0; e < (int)w.size(); ++e) w[e] = _units[unitOf(e)].area / total;
+        return w;
     }
 
   private:
@@ -1605,6 +1697,7 @@ class ModelHydro {
     std::unique_ptr<Compiled> _c;
     SettingsModel* _settings = nullptr;  // non-owning, like Process parameter pointers into the SettingsModel
     vector<UnitSettings> _units;
+    vector<int> _twinOf, _twinCol;  // engine unit -> basin unit (-1 for the units themselves); basin unit -> twin column
     std::map<int, Series> _series;
     std::set<int> _stationVars;
     bool _forcingLoaded = false;

@@ -293,4 +293,11 @@ class Socont:
 
         if hasattr(self.model, "_engine"):
             return self.model._engine
-        return _engine.Engine.from_handle(self.model.engine_handle(), len(self.units), self._n_steps, n_sets)
+        n_engine = self.model.engine_unit_count() if hasattr(self.model, "engine_unit_count") else len(self.units)
+        eng = _engine.Engine.from_handle(self.model.engine_handle(), n_engine, self._n_steps, n_sets)
+        if n_engine > len(self.units):  # twin units carrying a second glacier cover (hbk_set_unit_twins)
+            from . import structure as _structure
+
+            twin_of = list(self.model.twin_of())
+            eng.layout = _structure.UnitLayout(len(self.units), twin_of[len(self.units):])
+        return eng

@@ -120,7 +120,7 @@ def test_structure_variant_assignment():
     assert gv == expect and 0 < sum(gv) < len(gv)
 
 
-COMPILER_CASES = [b for b in gu.bundles() if not b.startswith(("c1_", "kat_", "two_glaciers_"))]
+COMPILER_CASES = [b for b in gu.bundles() if not b.startswith(("c1_", "kat_"))]
 
 
 @pytest.mark.parametrize("name", COMPILER_CASES)
@@ -139,9 +139,10 @@ def test_cpp_and_python_structure_compilers_agree(name):
     py = structure.CompiledStructure(meta["structures"], meta["solver"], 1.0, 44605.0)
     for field in ("solver", "n_soil_stores", "quick_kind", "slow_process_order", "splitter_kind", "has_glacier",
                   "glacier_infinite_storage", "glacier_no_melt_when_snow_cover", "time_step_days", "snow_ice_kind",
-                  "north_hemisphere", "start_mjd", "sublimation_kind"):
+                  "north_hemisphere", "start_mjd", "sublimation_kind", "melt_kind", "snow_slide_kind"):
         assert cpp["structure"][field] == getattr(py.hbk, field), field
     assert np.array_equal(np.asarray(cpp["params"], dtype=np.float32), py.parameter_vector())
     assert {k: v for k, v in cpp["labels"].items()} == {k: engine.RECORD_SLOTS.index(v) for k, v in py.labels.items()}
     assert {tuple(k): v for k, v in cpp["param_index"].items()} == {tuple(k): v for k, v in py.param_index.items()}
     assert cpp["ground_name"] == py.ground_name and (cpp["glacier_name"] or None) == py.glacier_name
+    assert sorted(cpp["twin_labels"]) == sorted(py.twin_labels)
