@@ -465,7 +465,7 @@ class SettingsModel:
             if kind == "glacier":
                 self.add_brick_process("snow_ice_transfo", transformation_process, name + ":ice")
 
-    def add_snow_redistribution(self, redistribution_process="transport:snow_slide", skip_glaciers=True):
+    def add_snow_redistribution(self, redistribution_process="transport:snow_slide", skip_glaciers=False):  # SettingsModel.h:391
         """SettingsModel::AddSnowRedistribution (SettingsModel.cpp:560-572): on the snowpack of every land cover (the
         glacier covers only without skip_glaciers), a lateral process whose instantaneous snow fluxes go to the
         snowpacks of the connected units."""

@@ -130,7 +130,7 @@ PYBIND11_MODULE(_hydrobricks, m) {
         .def("add_snow_ice_transformation", &hb::SettingsModel::AddSnowIceTransformation,
              "transformation_process"_a = "transform:snow_ice_swat")
         .def("add_snow_redistribution", &hb::SettingsModel::AddSnowRedistribution,
-             "redistribution_process"_a = "transport:snow_slide", "skip_glaciers"_a = true)
+             "redistribution_process"_a = "transport:snow_slide", "skip_glaciers"_a = false)
         .def("set_process_outputs_as_instantaneous", &hb::SettingsModel::SetProcessOutputsAsInstantaneous)
         .def("set_process_outputs_as_static", &hb::SettingsModel::SetProcessOutputsAsStatic)
         .def("get_structure", [](hb::SettingsModel& s) { return structureList(s); })

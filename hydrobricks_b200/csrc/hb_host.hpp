@@ -315,7 +315,7 @@ class SettingsModel {
     }
     // SettingsModel::AddSnowRedistribution (SettingsModel.cpp:560-572): a lateral process on the snowpack of every land
     // cover (the glacier covers only without skipGlaciers), instantaneous snow fluxes to the connected units' snowpacks
-    void AddSnowRedistribution(const string& redistributionProcess = "transport:snow_slide", bool skipGlaciers = true) {
+    void AddSnowRedistribution(const string& redistributionProcess = "transport:snow_slide", bool skipGlaciers = false) {  // default as SettingsModel.h:391
         if (redistributionProcess != "transport:snow_slide")
             throw std::runtime_error("Process type '" + redistributionProcess + "' is not available in the B200 engine.");
         vector<std::pair<string, string>> covers;

@@ -37,7 +37,7 @@ class Socont:
     def __init__(self, solver="crank_nicolson", soil_storage_nb=1, surface_runoff="socont_runoff",
                  land_cover_names=None, land_cover_types=None, record_all=False, glacier_infinite_storage=True,
                  snow_melt_process="melt:degree_day", snow_ice_transformation=None, snow_sublimation_process=None,
-                 snow_redistribution=None, snow_redistribution_skip_glaciers=True, snow_rain_process=None,
+                 snow_redistribution=None, snow_redistribution_skip_glaciers=False, snow_rain_process=None,
                  backend=None):
         self.backend = resolve_backend(backend)
         self.solver = solver

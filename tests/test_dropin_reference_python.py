@@ -46,6 +46,18 @@ def _structure(backend, **kw):
     dict(solver="heun_explicit", soil_storage_nb=2, land_cover_names=["ground", "glacier"],
          land_cover_types=["ground", "glacier"], record_all=True, snow_ice_transformation="transform:snow_ice_swat",
          snow_sublimation_process="sublimation:pet"),
+    # round 2: the other melt processes, the lateral snow slide (with and without the glacier snowpacks), two glacier covers
+    dict(solver="rk4", soil_storage_nb=1, land_cover_names=["ground", "glacier"], land_cover_types=["ground", "glacier"],
+         record_all=True, snow_melt_process="melt:degree_day_aspect"),
+    dict(solver="heun_explicit", soil_storage_nb=2, land_cover_names=["ground", "glacier"],
+         land_cover_types=["ground", "glacier"], record_all=True, snow_melt_process="melt:temperature_index"),
+    dict(solver="rk4", soil_storage_nb=1, land_cover_names=["ground", "glacier"], land_cover_types=["ground", "glacier"],
+         record_all=True, snow_redistribution="transport:snow_slide"),
+    dict(solver="rk4", soil_storage_nb=2, land_cover_names=["ground", "glacier"], land_cover_types=["ground", "glacier"],
+         record_all=True, snow_redistribution="transport:snow_slide", snow_ice_transformation="transform:snow_ice_swat",
+         glacier_infinite_storage=False),
+    dict(solver="rk4", soil_storage_nb=1, land_cover_names=["ground", "glacier_ice", "glacier_debris"],
+         land_cover_types=["ground", "glacier", "glacier"], glacier_infinite_storage=False, record_all=True),
 ])
 @pytest.mark.parametrize("backend", ["b200", "b200-native"])
 def test_reference_socont_builds_same_structure_on_both_backends(kw, backend):
@@ -54,7 +66,7 @@ def test_reference_socont_builds_same_structure_on_both_backends(kw, backend):
     assert b200_st == ref_st
     # and the parameter plumbing of the reference layer works on the mirror
     params = socont.generate_parameters()
-    params.set_values({"a_snow": 3, "A": 200})
+    params.set_values({"A": 200})
     for _, p in params.get_model_parameters().iterrows():
         if p["value"] is None:
             continue
