@@ -698,15 +698,32 @@ class ModelHydro:
         dt = self._cs.hbk.time_step_days
         pos = {u["id"]: i for i, u in enumerate(self._units)}
         glacier = self._cs.glacier_name
+        layout = self._cs.layout
+
+        def cover_index(name, what):
+            """0 for the first glacier cover, 1 for the second (carried by the twin units)."""
+            if name == glacier:
+                return 0
+            if name is not None and name == self._cs.glacier2_name:
+                return 1
+            raise ValueError(f"{what}: land cover '{name}' is not a glacier cover")
+
+        def engine_unit(u, cover):
+            if cover == 0:
+                return u
+            if layout.twin_col[u] < 0:
+                raise ValueError(f"The land cover '{self._cs.glacier2_name}' was not found in hydro unit "
+                                 f"{self._units[u]['id']}")
+            return layout.twin_col[u]
+
         events = []  # (step, order, callable)
         sporadic = []
         have_tables = False
         for order, action in enumerate(self._actions):
             if isinstance(action, ActionGlacierSnowToIceTransformation):
-                if action.land_cover != glacier:
-                    raise ValueError(f"snow-to-ice: land cover '{action.land_cover}' is not the glacier cover")
+                c = cover_index(action.land_cover, "snow-to-ice")
                 for k in _schedule.recursive_steps(self._mjd0, self._n_steps, action.month, action.day, dt):
-                    events.append((k, order, lambda k=k: eng.add_snow_to_ice(k)))
+                    events.append((k, order, lambda k=k, c=c: eng.add_snow_to_ice(k, c)))
             elif isinstance(action, ActionGlacierEvolutionDeltaH):
                 # ActionGlacierEvolutionAreaScaling shares the lookup-table interface and Init of the delta-h action
                 # (ActionGlacierEvolutionAreaScaling.cpp:9-68); only its Apply rule differs
@@ -714,8 +731,7 @@ class ModelHydro:
                 if have_tables:
                     raise ValueError("only one glacier-evolution action per model")
                 have_tables = True
-                if action.land_cover != glacier:
-                    raise ValueError(f"delta-h: land cover '{action.land_cover}' is not the glacier cover")
+                c = cover_index(action.land_cover, "delta-h")
                 if self._shard:
                     # this block's columns of the lookup tables; the row sums of the whole table, summed in table order
                     # like ActionGlacierEvolutionDeltaH.cpp:123-126, come with them
@@ -726,7 +742,7 @@ class ModelHydro:
                     eng.set_delta_h_shard_totals(np.cumsum(vol, axis=1)[:, -1])
                 else:
                     try:
-                        units = [pos[int(i)] for i in action.hu_ids]
+                        units = [engine_unit(pos[int(i)], c) for i in action.hu_ids]
                     except KeyError as err:
                         raise ValueError(f"The hydro unit {err} was not found") from err
                     eng.set_delta_h_tables(units, action.areas, action.volumes)
@@ -746,14 +762,15 @@ class ModelHydro:
                     continue
                 raise ValueError(f"The hydro unit {unit_id} was not found")
             u = pos[unit_id]
-            if cover != glacier:
+            if cover not in (glacier, self._cs.glacier2_name) or cover is None:
                 # changing the generic cover itself is undone by FixLandCoverFractionsTotal (HydroUnit.cpp:459-490)
                 if cover == self._cs.ground_name:
                     continue
                 raise ValueError(f"Land cover '{cover}' was not found.")
             fraction = _schedule.check_fraction(area / self._units[u]["area"])
             k = _schedule.sporadic_step(self._mjd0, date, dt)
-            events.append((k, 10000 + n, lambda k=k, u=u, f=fraction: eng.add_land_cover_change(k, u, f)))
+            ue = engine_unit(u, cover_index(cover, "land cover change"))
+            events.append((k, 10000 + n, lambda k=k, u=ue, f=fraction: eng.add_land_cover_change(k, u, f)))
         for _, _, add in sorted(events, key=lambda e: (e[0], e[1])):
             add()
 

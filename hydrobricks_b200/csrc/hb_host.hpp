@@ -1729,23 +1729,36 @@ class ModelHydro {
         };
         vector<Sp> sporadic;
         bool haveTables = false;
+        // 0 for the first glacier cover, 1 for the second (carried by the twin units); engine unit of (unit, cover)
+        auto coverIndex = [&](const string& name, const char* what) -> int {
+            if (!_c->glacierName.empty() && name == _c->glacierName) return 0;
+            if (!_c->glacier2Name.empty() && name == _c->glacier2Name) return 1;
+            throw std::invalid_argument(string(what) + ": land cover '" + name + "' is not a glacier cover");
+        };
+        auto engineUnit = [&](int u, int cover) -> int {
+            if (cover == 0) return u;
+            if (_twinCol[u] < 0)
+                throw std::invalid_argument("The land cover '" + _c->glacier2Name + "' was not found in hydro unit " +
+                                            std::to_string(_units[u].id));
+            return _twinCol[u];
+        };
         for (int order = 0; order < (int)_actions.size(); ++order) {
             Action* a = _actions[order];
             if (auto* s2i = dynamic_cast<ActionGlacierSnowToIceTransformation*>(a)) {
-                if (s2i->cover != _c->glacierName) throw std::invalid_argument("snow-to-ice: land cover is not the glacier cover");
-                for (int k : recursiveSteps(_mjd0, _nSteps, s2i->month, s2i->day, _dt)) events.push_back({k, order, 1, -1, 0});
+                const int c = coverIndex(s2i->cover, "snow-to-ice");
+                for (int k : recursiveSteps(_mjd0, _nSteps, s2i->month, s2i->day, _dt)) events.push_back({k, order, 1, c, 0});
             } else if (auto* dh = dynamic_cast<ActionGlacierEvolutionDeltaH*>(a)) {
                 // ActionGlacierEvolutionAreaScaling shares the lookup-table interface and Init of the delta-h action
                 // (…AreaScaling.cpp:9-68); only its Apply rule differs (event kind 3)
                 const bool areaScaling = dynamic_cast<ActionGlacierEvolutionAreaScaling*>(a) != nullptr;
                 if (haveTables) throw std::invalid_argument("only one glacier-evolution action per model");
                 haveTables = true;
-                if (dh->cover != _c->glacierName) throw std::invalid_argument("delta-h: land cover is not the glacier cover");
+                const int c = coverIndex(dh->cover, "delta-h");
                 vector<int32_t> units;
                 for (int id : dh->unitIds) {
                     auto it = pos.find(id);
                     if (it == pos.end()) throw std::invalid_argument("The hydro unit " + std::to_string(id) + " was not found");
-                    units.push_back(it->second);
+                    units.push_back(engineUnit(it->second, c));
                 }
                 check(hbk_set_delta_h_tables(_e, (int)units.size(), units.data(), dh->rows, dh->areas.data(), dh->volumes.data()));
                 for (int k : recursiveSteps(_mjd0, _nSteps, dh->month, 1, _dt))
@@ -1761,12 +1774,12 @@ class ModelHydro {
         for (auto& s : sporadic) {
             auto it = pos.find(s.unitId);
             if (it == pos.end()) throw std::invalid_argument("The hydro unit " + std::to_string(s.unitId) + " was not found");
-            if (s.cover != _c->glacierName) {
-                if (s.cover == _c->groundName) continue;  // undone by FixLandCoverFractionsTotal (HydroUnit.cpp:459-490)
+            if (s.cover == _c->groundName) continue;  // undone by FixLandCoverFractionsTotal (HydroUnit.cpp:459-490)
+            if (s.cover != _c->glacierName && (_c->glacier2Name.empty() || s.cover != _c->glacier2Name))
                 throw std::invalid_argument("Land cover '" + s.cover + "' was not found.");
-            }
             double fraction = checkFraction(s.area / _units[it->second].area);
-            events.push_back({sporadicStep(_mjd0, s.date, _dt), 10000 + n++, 0, it->second, fraction});
+            events.push_back({sporadicStep(_mjd0, s.date, _dt), 10000 + n++, 0,
+                              engineUnit(it->second, coverIndex(s.cover, "land cover change")), fraction});
         }
         std::stable_sort(events.begin(), events.end(), [](const Ev& a, const Ev& b) {
             return a.step != b.step ? a.step < b.step : a.order < b.order;
@@ -1775,7 +1788,7 @@ class ModelHydro {
             if (ev.kind == 0) {
                 check(hbk_add_land_cover_change(_e, ev.step, ev.unit, ev.value));
             } else if (ev.kind == 1) {
-                check(hbk_add_snow_to_ice(_e, ev.step));
+                check(hbk_add_snow_to_ice_on(_e, ev.step, ev.unit));
             } else if (ev.kind == 3) {
                 check(hbk_add_area_scaling_update(_e, ev.step));
             } else {

@@ -1010,6 +1010,10 @@ struct ActArgs {
     int ldu;
     int iceInfinite;
     int* err;
+    // twin units (hbk_set_unit_twins): twinOf[u] = unit whose second glacier cover u carries (-1: an ordinary unit),
+    // twinCol[u] = the twin of unit u (-1: none); nullptr without twins
+    const int* twinOf;
+    const int* twinCol;
 };
 
 __device__ __forceinline__ double& stateAt(const ActArgs& a, int slot, int p, int u) {
@@ -1020,9 +1024,14 @@ __device__ __forceinline__ double& stateAt(const ActArgs& a, int slot, int p, in
 // cover absorbs the area difference and the water / snow column of the strip that changes hands moves with it
 // (HydroUnit.cpp:332-374 ChangeLandCoverAreaFraction, :384-451 TransferLandCoverContent, :459-490 FixLandCoverFractionsTotal).
 __device__ void changeGlacierFraction(const ActArgs& a, int p, int u, double fraction) {
-    const size_t fi = (size_t)p * a.U + u;
-    double& fG = a.frac[fi];
-    double& fGl = a.frac[(size_t)a.P * a.U + fi];
+    // With twin units the glacier cover being changed lives in u (an ordinary unit: the first glacier cover; a twin: the
+    // second), the generic cover that absorbs the difference in the unit itself (uGen), and the unit's other glacier
+    // cover (uOther, -1: none) only enters the total of FixLandCoverFractionsTotal.
+    const int uGen = (a.twinOf && a.twinOf[u] >= 0) ? a.twinOf[u] : u;
+    const int uOther = !a.twinOf ? -1 : (uGen != u ? uGen : a.twinCol[u]);
+    const size_t PU = (size_t)a.P * a.U;
+    double& fG = a.frac[(size_t)p * a.U + uGen];
+    double& fGl = a.frac[PU + (size_t)p * a.U + u];
     if (fraction < 0 || fraction > 1 || !(a.hruFlags[u] & 1)) {
         atomicOr(a.err, kErrActionFraction);
         return;
@@ -1036,9 +1045,9 @@ __device__ void changeGlacierFraction(const ActArgs& a, int p, int u, double fra
         return;
     }
     if (!nearlyZero(delta, kEpsD)) {
-        double& wG = stateAt(a, HBK_S_GROUND_WATER, p, u);
+        double& wG = stateAt(a, HBK_S_GROUND_WATER, p, uGen);
         double& wGl = stateAt(a, HBK_S_GLACIER_WATER, p, u);
-        double& snowG = stateAt(a, HBK_S_GROUND_SNOW, p, u);
+        double& snowG = stateAt(a, HBK_S_GROUND_SNOW, p, uGen);
         double& snowGl = stateAt(a, HBK_S_GLACIER_SNOW, p, u);
         double& ice = stateAt(a, HBK_S_ICE, p, u);
         if (delta > 0) {  // the glacier grows, taking land (and its water column) from the generic cover
@@ -1066,9 +1075,19 @@ __device__ void changeGlacierFraction(const ActArgs& a, int p, int u, double fra
         }
     }
     fGl = fraction;
+    // HydroUnit::FixLandCoverFractionsTotal (HydroUnit.cpp:459-490): the covers in brick order — generic, first glacier,
+    // second glacier
     double total = 0;
     total += fG;
-    total += fGl;
+    if (uOther < 0) {
+        total += fGl;
+    } else if (uGen == u) {
+        total += fGl;
+        total += a.frac[PU + (size_t)p * a.U + uOther];
+    } else {
+        total += a.frac[PU + (size_t)p * a.U + uOther];
+        total += fGl;
+    }
     if (!(fabs(total - 1.0) <= kEpsD)) {
         const double diff = total - 1.0;
         if (fG < diff - kEpsD) {
@@ -1085,11 +1104,12 @@ __global__ void hbkActLandCoverChange(const ActArgs a, int u, double fraction) {
 }
 
 // ActionGlacierSnowToIceTransformation::Apply (ActionGlacierSnowToIceTransformation.cpp:41-74)
-__global__ void hbkActSnowToIce(const ActArgs a) {
+__global__ void hbkActSnowToIce(const ActArgs a, int cover) {  // cover: 0 the first glacier cover, 1 the second (twins)
     const long long n = (long long)a.P * a.U;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int p = (int)(i / a.U), u = (int)(i % a.U);
         if (!(a.hruFlags[u] & 1)) continue;
+        if (((a.hruFlags[u] >> 3) & 1) != cover) continue;
         if (nearlyZero(a.frac[(size_t)a.P * a.U + i], kPrecision)) continue;
         double& snow = stateAt(a, HBK_S_GLACIER_SNOW, p, u);
         if (snow <= 0) continue;
@@ -1398,6 +1418,8 @@ struct hbk_engine {
     int nVars() const { return st.melt_kind == HBK_MELT_TEMPERATURE_INDEX ? 4 : 3; }
     std::vector<int> hAspect;  // HBK_ASPECT_* per unit (hbk_set_unit_aspect); empty = not given
     std::vector<int> hTwinOf;  // unit a twin (second glacier cover) belongs to, -1 = ordinary unit; empty = no twins
+    int* dTwinOf = nullptr;    // [U] device copies for the action kernels (nullptr without twins)
+    int* dTwinCol = nullptr;   // [U] twin of a unit, -1 = none
     bool hasTwins = false;
     // bit 0: the unit carries the glacier bricks; bits 1-2: HBK_ASPECT_*; bit 3: twin (second glacier cover)
     int unitFlags(int u) const {
@@ -1851,6 +1873,8 @@ void hbk_engine_destroy(hbk_engine* e) {
     freeDev(e->dUnconv);
     freeDev(e->dUnconvSet);
     freeDev(e->dQueue);
+    freeDev(e->dTwinOf);
+    freeDev(e->dTwinCol);
     freeDev(e->dLatOff);
     freeDev(e->dLatRecv);
     freeDev(e->dLatWeight);
@@ -1939,6 +1963,21 @@ int hbk_set_unit_twins(hbk_engine* e, const int32_t* twin_of) {
     }
     e->hTwinOf.assign(twin_of, twin_of + e->U);
     e->hasTwins = any;
+    HBK_CUDA(cudaSetDevice(e->device));
+    freeDev(e->dTwinOf);
+    freeDev(e->dTwinCol);
+    if (any) {
+        std::vector<int> col(e->U, -1);
+        for (int u = 0; u < e->U; ++u) {
+            if (twin_of[u] < 0) continue;
+            if (col[twin_of[u]] >= 0) return fail(e, HBK_E_UNSUPPORTED, "at most one twin (two glacier covers) per unit");
+            col[twin_of[u]] = u;
+        }
+        HBK_CUDA(cudaMalloc(&e->dTwinOf, sizeof(int) * e->U));
+        HBK_CUDA(cudaMalloc(&e->dTwinCol, sizeof(int) * e->U));
+        HBK_CUDA(cudaMemcpy(e->dTwinOf, twin_of, sizeof(int) * e->U, cudaMemcpyHostToDevice));
+        HBK_CUDA(cudaMemcpy(e->dTwinCol, col.data(), sizeof(int) * e->U, cudaMemcpyHostToDevice));
+    }
     e->unitsSet = false;  // hbk_set_units computes the basin area and the unit flags from it
     return HBK_OK;
 }
@@ -2193,12 +2232,16 @@ int hbk_add_land_cover_change(hbk_engine* e, int32_t step, int32_t unit, double 
     return HBK_OK;
 }
 
-int hbk_add_snow_to_ice(hbk_engine* e, int32_t step) {
+int hbk_add_snow_to_ice_on(hbk_engine* e, int32_t step, int32_t glacier_cover) {
     if (!e || step < 1) return HBK_E_ARG;
     if (!e->st.has_glacier) return fail(e, HBK_E_MODEL, "snow-to-ice transformation needs a glacier cover");
-    e->events.push_back({step, 1, -1, 0.0});
+    if (glacier_cover < 0 || glacier_cover > 1 || (glacier_cover == 1 && !e->hasTwins))
+        return fail(e, HBK_E_ARG, "snow to ice: glacier cover 0, or 1 with twin units (hbk_set_unit_twins)");
+    e->events.push_back({step, 1, glacier_cover, 0.0});  // Event::unit carries the glacier cover index
     return HBK_OK;
 }
+
+int hbk_add_snow_to_ice(hbk_engine* e, int32_t step) { return hbk_add_snow_to_ice_on(e, step, 0); }
 
 int hbk_add_delta_h_update(hbk_engine* e, int32_t step) {
     if (!e || step < 1) return HBK_E_ARG;
@@ -2236,7 +2279,9 @@ int hbk_set_delta_h_tables(hbk_engine* e, int32_t n, const int32_t* units, int32
             if (std::fabs(fraction) <= 1e-8) fraction = 0.0;
             if (std::fabs(1 - fraction) <= 1e-8) fraction = 1.0;
             if (fraction < 0 || fraction > 1) return fail(e, HBK_E_MODEL, "delta-h: initial fraction not in [0 .. 1]");
-            e->hFracG[u] -= fraction - e->hFracGl[u];
+            // the generic cover that gives the area: the unit's own (a twin carries only the second glacier cover)
+            const int uGen = (e->hasTwins && e->hTwinOf[u] >= 0) ? e->hTwinOf[u] : u;
+            e->hFracG[uGen] -= fraction - e->hFracGl[u];
             e->hFracGl[u] = fraction;
         } else if (std::fabs(areaInModel - areaRef) > 1e-8) {
             return fail(e, HBK_E_MODEL, "The glacier area fraction of a hydro unit does not match the lookup table "
@@ -2346,6 +2391,8 @@ static int applyEvents(hbk_engine* e, int step) {
     a.ldu = e->ldu;
     a.iceInfinite = e->st.glacier_infinite_storage;
     a.err = e->dErr;
+    a.twinOf = e->dTwinOf;
+    a.twinCol = e->dTwinCol;
     const int pBlocks = (e->P + 127) / 128;
     for (const auto& ev : e->events) {
         if (ev.step != step) continue;
@@ -2353,7 +2400,7 @@ static int applyEvents(hbk_engine* e, int step) {
             if (ev.unit < 0) continue;  // an edit in another block of the basin (unit shard): boundary only
             hbkActLandCoverChange<<<pBlocks, 128, 0, e->stream>>>(a, ev.unit, ev.value);
         } else if (ev.kind == 1) {
-            hbkActSnowToIce<<<148 * 2, 256, 0, e->stream>>>(a);
+            hbkActSnowToIce<<<148 * 2, 256, 0, e->stream>>>(a, ev.unit);  // ev.unit: glacier cover index
         } else if (ev.kind == 3) {
             if (e->dhUnits == 0) continue;  // a unit shard without any unit of the table: nothing to scale here
             const long long n = (long long)e->P * e->dhUnits;
@@ -2691,9 +2738,9 @@ int hbk_run(hbk_engine* e) {
                                             "(hbk_set_delta_h_shard_totals)");
     }
     e->shardSegments.clear();
-    if (e->hasTwins && (!e->events.empty() || e->st.snow_slide_kind != HBK_SNOW_SLIDE_NONE || e->shard))
-        return fail(e, HBK_E_UNSUPPORTED, "units with a second glacier cover (hbk_set_unit_twins) run neither dated actions "
-                                          "nor lateral connections nor unit shards");
+    if (e->hasTwins && (e->st.snow_slide_kind != HBK_SNOW_SLIDE_NONE || e->shard))
+        return fail(e, HBK_E_UNSUPPORTED, "units with a second glacier cover (hbk_set_unit_twins) run neither lateral "
+                                          "connections nor unit shards");
     const bool lateral = e->st.snow_slide_kind != HBK_SNOW_SLIDE_NONE;
     if (lateral) {
         if (!e->dLatOff)

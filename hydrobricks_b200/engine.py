@@ -121,6 +121,7 @@ def load_library():
     L.hbk_clear_actions.argtypes = [vp]
     L.hbk_add_land_cover_change.argtypes = [vp, i32, i32, dbl]
     L.hbk_add_snow_to_ice.argtypes = [vp, i32]
+    L.hbk_add_snow_to_ice_on.argtypes = [vp, i32, i32]
     L.hbk_set_delta_h_tables.argtypes = [vp, i32, ip, i32, dp, dp]
     L.hbk_add_delta_h_update.argtypes = [vp, i32]
     L.hbk_add_area_scaling_update.argtypes = [vp, i32]
@@ -311,8 +312,9 @@ class Engine:
     def add_land_cover_change(self, step, unit, glacier_fraction):
         self._check(self.L.hbk_add_land_cover_change(self.h, int(step), int(unit), float(glacier_fraction)))
 
-    def add_snow_to_ice(self, step):
-        self._check(self.L.hbk_add_snow_to_ice(self.h, int(step)))
+    def add_snow_to_ice(self, step, glacier_cover=0):
+        """glacier_cover 1 = the units' second glacier cover (twin units)."""
+        self._check(self.L.hbk_add_snow_to_ice_on(self.h, int(step), int(glacier_cover)))
 
     def set_delta_h_tables(self, units, areas, volumes):
         u = np.ascontiguousarray(units, dtype=np.int32)

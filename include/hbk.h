@@ -225,6 +225,11 @@ int hbk_clear_actions(hbk_engine* e);
 /* unit = -1 (unit shards only): the edit concerns a unit of another block; this block just cuts its run at `step`. */
 int hbk_add_land_cover_change(hbk_engine* e, int32_t step, int32_t unit, double glacier_fraction);
 int hbk_add_snow_to_ice(hbk_engine* e, int32_t step);
+/* ... of the units' second glacier cover (glacier_cover = 1, twin units) or the first (0 = hbk_add_snow_to_ice). With twin
+ * units, hbk_add_land_cover_change / hbk_set_delta_h_tables take ENGINE unit indices: an ordinary unit stands for its first
+ * glacier cover, its twin for the second; the generic cover that absorbs an area change is the unit's
+ * (HydroUnit::ChangeLandCoverAreaFraction, HydroUnit.cpp:332-490, with all three covers in FixLandCoverFractionsTotal). */
+int hbk_add_snow_to_ice_on(hbk_engine* e, int32_t step, int32_t glacier_cover);
 int hbk_set_delta_h_tables(hbk_engine* e, int32_t n_units, const int32_t* units, int32_t n_rows, const double* areas,
                            const double* volumes);
 int hbk_add_delta_h_update(hbk_engine* e, int32_t step);

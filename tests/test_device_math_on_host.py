@@ -20,7 +20,7 @@ HERE = Path(__file__).resolve().parent
 ROOT = HERE.parent
 EMUL = HERE / "host_emul"
 RTOL, ATOL = 1e-10, 1e-12
-CASES = [b for b in gu.bundles() if not b.startswith(("c1_", "kat_linear", "actions_", "melt_", "snow_slide_", "two_glaciers_"))]
+CASES = [b for b in gu.bundles() if not b.startswith(("c1_", "kat_linear", "actions_", "actions2_", "melt_", "snow_slide_", "two_glaciers_"))]
 
 
 def build_emul(name="libhbkemul.so", defines=()):

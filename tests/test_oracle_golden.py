@@ -9,7 +9,7 @@ import pytest
 
 import golden_utils as gu
 
-CASES = [b for b in gu.bundles() if not b.startswith(("c1_", "actions_"))]
+CASES = [b for b in gu.bundles() if not b.startswith(("c1_", "actions_", "actions2_"))]
 
 
 @pytest.mark.parametrize("name", CASES)

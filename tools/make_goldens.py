@@ -257,6 +257,24 @@ def two_glaciers_bundles(ref):
         save(f"two_glaciers_{solver}_{name}", meta, forcing, q, rec)
 
 
+def two_glaciers_action_bundles(ref):
+    """Dated actions on glacier_ice + glacier_debris units: delta-h on the clean ice, land-cover edits of the debris cover,
+    snow -> ice on both (tools/ref_two_glaciers_actions_case.py)."""
+    import ref_two_glaciers_actions_case as rt
+
+    for solver in ("rk4", "heun_explicit"):
+        meta, forcing, q, rec, frac, areas, volumes = rt.run_reference(ref, solver)
+        extra = {"spatial_dh_areas": areas, "spatial_dh_volumes": volumes}
+        for k, v in frac.items():
+            extra["spatial_fraction_" + k] = v
+        keep = ["glacier_ice:ice_content", "glacier_debris:ice_content", "glacier_ice:water_content", "ground:water_content",
+                "glacier_ice_snowpack:snow_content", "glacier_debris_snowpack:snow_content", "ground_snowpack:snow_content",
+                "slow_reservoir:water_content", "glacier_ice:melt:output", "glacier_debris:melt:output",
+                "glacier_debris:outflow_rain_snowmelt:output"]
+        meta["labels"] = keep
+        save(f"actions2_{solver}_two_glaciers", meta, forcing, q, {k: rec[k] for k in keep}, extra=extra)
+
+
 def slow_order_bundles(ref):
     """hbk_structure.slow_process_order = 1 (the process order of core/tests/src/helpers.cpp), two soil stores."""
     import ref_slow_order_case as ro
@@ -280,6 +298,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "threshold":
         threshold_splitter_bundles(ref)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "two_glaciers_actions":
+        two_glaciers_action_bundles(ref)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "two_glaciers":
         two_glaciers_bundles(ref)
@@ -352,6 +373,7 @@ def main():
     threshold_splitter_bundles(ref)
     rain_only_bundles(ref)
     two_glaciers_bundles(ref)
+    two_glaciers_action_bundles(ref)
     slow_order_bundles(ref)
 
 
