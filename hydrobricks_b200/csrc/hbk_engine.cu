@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
     double* accb = qbuf + (size_t)NQ * TC * nThreads;                  // cluster mode only: [2][NQ][TC][PB]
 
     // per-parameter-set constants: shared memory [field][PB] (or registers, HBK_PAR_SHARED=0)
-    double* sPar = accb + (size_t)(clusterMode ? 2 : 0) * NQ * TC * PB;
+    [[maybe_unused]] double* sPar = accb + (size_t)(clusterMode ? 2 : 0) * NQ * TC * PB;
     Par par;
     double quickBase = 0, gT = 0, gP = 0, corr = 1;
     auto setBlock = [&](int vb) {
@@ -723,6 +723,10 @@ struct LatArgs {
 
 template <int SOLVER, int NSOIL, bool GLACIER>
 __global__ void __launch_bounds__(128) hbkRunLateral(const KArgs a, const LatArgs L) {
+#if HBK_PAR_SHARED  // tuning builds with the parameters in shared memory have no lateral kernel (refused at engine creation)
+    (void)a;
+    (void)L;
+#else
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.P) return;
     const int pOut = a.perm ? a.perm[p] : p;
@@ -937,6 +941,7 @@ __global__ void __launch_bounds__(128) hbkRunLateral(const KArgs a, const LatArg
         atomicAdd(a.unconverged, (unsigned long long)unconverged);
         atomicAdd(&a.unconvergedPerSet[p], unconverged);
     }
+#endif
 }
 
 // Sum the unit-tile partials in tile order: out[p][t] = sum_tiles part[tile][p][t]  (only when nUTiles > 1).
