@@ -102,6 +102,22 @@ WORKLOADS = {
 }
 
 
+def block_shape_text(shape):
+    """The launch shape of the timed runs in words, from hbk_last_run_shape."""
+    sp, ub = shape["sets_per_block"], shape["units_per_block"]
+    lanes = "parameter sets (lanes)" if sp == 32 else "parameter set(s)"
+    text = f"{sp} {lanes} x {ub} units per block, {shape['unit_tiles']} unit tiles, {shape['tiles_per_block']} tiles " \
+           f"time-multiplexed per block, {shape['steps_per_chunk']} steps per chunk"
+    if shape["tile_groups"] > 1:
+        text += f"; {shape['tile_groups']} tile groups write partial outlet series, summed in group order (hbkReduceTiles)"
+    if shape["launches_per_segment"] > 1:
+        text += f"; {shape['launches_per_segment']} unit-kernel launches per run segment: the {shape['plain_variant_tiles']} " \
+                "tiles without glacier units run the plain kernel variant"
+    if sp == 32:
+        text += "; parameter sets ordered inside the engine so that warps hold similar sets"
+    return text
+
+
 def parameter_sets(P, seed=44):
     """Uniform in the reference ranges (parameters.py:66-174, 736-738), transition_start < transition_end."""
     rng = np.random.Generator(np.random.MT19937(seed))
@@ -576,6 +592,7 @@ def run_engine_arm(args):
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
     unconverged_sweeps = eng.last_run_stats()["unconverged_sweeps"]
+    shape = eng.last_run_shape()
     unconverged_sets = int((eng.unconverged_per_set() > 0).sum())
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([dev_ms, wall * 1e3, sum(kernel_ms)], dtype=torch.float64, device="cuda")
@@ -673,10 +690,9 @@ def run_engine_arm(args):
                        "timesteps": T, "solver": args.solver,
                        "structure": f"socont {wl['soil']} soil store(s), runoff:socont" + (", glacier (GSM)" if wl["glacier"] else ""),
                        "forcing": "station series + fused elevation-gradient spatialisation",
-                       "l2": "256 MiB flush between timed iterations; per-step output 8.8 GB >> L2",
-                       "block_shape": "32 parameter sets (lanes) x 4 units per block, all unit tiles time-multiplexed "
-                                      "on the block, 16 steps per chunk; parameter sets ordered inside the engine "
-                                      "so that warps hold similar sets",
+                       "l2": "256 MiB flush between timed iterations; per-step output %.3g GB" % (P * T * 8 / 1e9),
+                       "block_shape": block_shape_text(shape),
+                       "launch_shape": shape,
                        "arithmetic": "every quotient of the reference correctly rounded, verification sweep kept "
                                      "(bit-identical to the division-for-division build, DESIGN.md §4)"},
             "wall_ms_per_step": wall_ms / args.steps,

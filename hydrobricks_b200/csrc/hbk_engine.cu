@@ -44,6 +44,12 @@ namespace hbk {
 #ifndef HBK_MIN_BLOCKS
 #define HBK_MIN_BLOCKS 6  // register budget = 65536 / (HBK_MAX_THREADS * HBK_MIN_BLOCKS)
 #endif
+#ifndef HBK_MIN_BLOCKS_SOIL2
+#define HBK_MIN_BLOCKS_SOIL2 HBK_MIN_BLOCKS  // two soil stores without glacier
+#endif
+#ifndef HBK_ENS_TC_GLACIER
+#define HBK_ENS_TC_GLACIER HBK_ENS_TC  // glacier variants: three outlet quantities per step in the chunk slots
+#endif
 #ifndef HBK_MIN_BLOCKS_GLACIER
 #define HBK_MIN_BLOCKS_GLACIER 4  // the glacier variants carry ~60 more live registers: 128 regs x 16 warps (C3: +8.5 % over 6)
 #endif
@@ -52,6 +58,9 @@ constexpr int kNH = 4;  // per-unit constants: area fraction of basin, area [m2]
 
 struct KArgs {
     int P, U, tBegin, tEnd, PB, UB, TC, nUTiles, G, nGroups;
+    // the unit tiles [tile0, tile1) of this launch, cut into nGroups groups of G tiles; grpBase = index of its first group
+    // among the partial buffers (one launch covers all tiles unless the tiles without glacier units run the plain kernel)
+    int tile0, tile1, grpBase;
     int clusterMode;  // 1: one thread-block cluster per parameter-set group, one CTA per unit tile, DSMEM reduction
     Flags flags;
     double dt;
@@ -257,6 +266,13 @@ __device__ __forceinline__ void recordStep(const KArgs& a, int pOut, int t, int 
 #undef HBK_REC
 }
 
+// resident blocks per multiprocessor a kernel variant is compiled for (= its register budget) and the chunk length of
+// the compile-time ensemble shape
+__host__ __device__ constexpr int hbkMinBlocks(int nSoil, bool glacier) {
+    return glacier ? HBK_MIN_BLOCKS_GLACIER : (nSoil == 2 ? HBK_MIN_BLOCKS_SOIL2 : HBK_MIN_BLOCKS);
+}
+__host__ __device__ constexpr int hbkEnsTC(bool glacier) { return glacier ? HBK_ENS_TC_GLACIER : HBK_ENS_TC; }
+
 // ---- main kernel ------------------------------------------------------------------------------------
 // Block = PB parameter sets x UB units (threads), time-multiplexed over a GROUP of G consecutive unit tiles:
 //   for each chunk of TC steps: for each tile of the group: [load state] TC steps [store state], add the tile's
@@ -266,14 +282,14 @@ __device__ __forceinline__ void recordStep(const KArgs& a, int pOut, int t, int 
 // DAILY: the time step is exactly one day (the reference's usual case); x * 1.0 and x / 1.0 are exact, so the
 // multiplications by dt fold away without changing a bit.
 template <int SOLVER, int NSOIL, bool GLACIER, bool DAILY, bool ENS>
-__global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLACIER : HBK_MIN_BLOCKS)
+__global__ void __launch_bounds__(HBK_MAX_THREADS, hbkMinBlocks(NSOIL, GLACIER))
     hbkRunUnits(const KArgs a) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     constexpr int NQ = GLACIER ? 3 : 1;
     // ENS: the block shape of calibration ensembles fixed at compile time — 32 parameter sets (lanes) x 4 units, 16 steps per
     // chunk, station forcing with fused spatialisation, no cluster — so that the address arithmetic of the time loop
     // folds into immediates (at 80 registers ptxas otherwise re-derives it from the kernel arguments at every step)
-    const int PB = ENS ? 32 : a.PB, UB = ENS ? 4 : a.UB, TC = ENS ? HBK_ENS_TC : a.TC;
+    const int PB = ENS ? 32 : a.PB, UB = ENS ? 4 : a.UB, TC = ENS ? hbkEnsTC(GLACIER) : a.TC;
     const int forcingMode = ENS ? 1 : a.forcingMode;
     const int NV = ENS ? 3 : a.nVars;  // staged forcing variables (the ensemble shape never carries the radiation)
     const bool clusterMode = ENS ? false : (a.clusterMode != 0);
@@ -308,8 +324,8 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
         p = pg * PB + pl;
         validP = p < a.P;
         pOut = (validP && a.perm) ? a.perm[p] : p;  // the caller's index of this parameter set
-        tileBegin = clusterMode ? crank : grp * a.G;
-        tileEnd = clusterMode ? crank + 1 : min(tileBegin + a.G, a.nUTiles);
+        tileBegin = clusterMode ? crank : a.tile0 + grp * a.G;
+        tileEnd = clusterMode ? crank + 1 : min(tileBegin + a.G, a.tile1);
         multi = !clusterMode && a.G > 1;
 #if HBK_PAR_SHARED
         double* pv = sPar + pl;
@@ -667,7 +683,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, GLACIER ? HBK_MIN_BLOCKS_GLAC
                         double* dst = (qi == 0) ? a.outQ : (qi == 1 ? a.outD1 : a.outD2);
                         const int row = (qi == 0 && a.outQFinal && a.perm) ? a.perm[gp] : gp;
                         // streaming store: the 8.8 GB outlet must not evict the L2-resident unit state
-                        __stcs(&dst[((size_t)grp * a.P + row) * a.ldt + (t0 + tc)], s);
+                        __stcs(&dst[((size_t)(a.grpBase + grp) * a.P + row) * a.ldt + (t0 + tc)], s);
                     }
                 }
             }
@@ -1499,6 +1515,16 @@ struct hbk_engine {
     double* dObs = nullptr;     // [T] + 3 stats
     double* dStale = nullptr;  // [P][2] stale deposit amounts of null glacier bricks (actions only)
     int dhUnits = 0, dhRows = 0;
+    std::vector<int> hDhUnits;  // the lookup tables' units (host copy: they may gain ice at an update)
+    // Unit tiles of a glacier structure whose units can never carry ice (glacier fraction 0, untouched by any action) run
+    // the plain kernel variant (80 instead of 128 registers): the launches of one run segment (planRuns)
+    struct TileRun {
+        int tile0, tile1;  // unit tiles [tile0, tile1)
+        bool glacier;      // kernel variant
+        int TC, G, nGroups, grpBase;
+    };
+    std::vector<TileRun> runs;
+    int totalGroups = 1, glacierGroups = 1;
     bool dhTablesSet = false;  // since the last hbk_clear_actions (dhUnits may be 0 on a unit shard)
     double dhInitialWE = 0;
     std::vector<double> hArea;
@@ -1550,6 +1576,9 @@ void freeDev(T*& p) {
 }
 
 // Thread-block shape: parameter axis on the lanes when there are enough sets, else the unit axis.
+int chunkSteps(const hbk_engine* e, bool glacier);
+int tilesPerBlock(const hbk_engine* e, int nTiles, bool glacier);
+
 void chooseShape(hbk_engine* e) {
     int pb = 1;
     while (pb < 32 && pb < e->P) pb *= 2;
@@ -1573,17 +1602,7 @@ void chooseShape(hbk_engine* e) {
     }
     e->UB = best;
     e->nUTiles = (e->U + e->UB - 1) / e->UB;
-    // tiles per block: enough blocks to fill the machine several times, otherwise as many tiles per block as
-    // possible (G = all tiles: the block sums every unit of its sets itself, no partial buffers)
-    const long long nPGroups = (e->P + e->PB - 1) / e->PB;
-    const int minBlocks = e->st.has_glacier ? HBK_MIN_BLOCKS_GLACIER : HBK_MIN_BLOCKS;
-    const long long wantBlocks = 148LL * minBlocks * 2;
-    long long groups = std::min<long long>(e->nUTiles, std::max<long long>(1, (wantBlocks + nPGroups - 1) / nPGroups));
-    e->G = (int)((e->nUTiles + groups - 1) / groups);
-    if (const char* force = std::getenv("HBK_TILES_PER_BLOCK")) {  // testing / tuning knob
-        const int g = std::atoi(force);
-        if (g > 0) e->G = std::min(g, e->nUTiles);
-    }
+    e->G = tilesPerBlock(e, e->nUTiles, e->st.has_glacier != 0);
     e->nGroups = (e->nUTiles + e->G - 1) / e->G;
     // Optional (HBK_CLUSTER=1): one thread-block cluster per parameter-set group when all unit tiles fit in one
     // cluster (<= 16 CTAs, opt-in size): state stays in registers, the outlet is reduced through distributed shared
@@ -1604,13 +1623,25 @@ void chooseShape(hbk_engine* e) {
         e->nGroups = 1;
         e->clusterMode = false;
     }
-    const int nq = e->st.has_glacier ? 3 : 1;
-    // chunk length: shared memory per block small enough for HBK_MIN_BLOCKS blocks per SM
+    e->TC = chunkSteps(e, e->st.has_glacier != 0);
+}
+
+size_t smemBytes(const hbk_engine* e, bool tiled, bool glacier, int TC) {
+    const int nq = glacier ? 3 : 1;
+    const size_t fRow = tiled ? (size_t)TC * e->UB : (size_t)TC + 2;
+    return 128 + 2 * e->nVars() * fRow * 8 + (size_t)nq * TC * (e->PB * e->UB + (e->clusterMode ? 2 * e->PB : 0)) * 8 +
+           (HBK_PAR_SHARED ? (size_t)hbk::kParFields * e->PB * 8 : 0);
+}
+
+// Steps per chunk of a kernel variant: shared memory per block small enough for its resident blocks per SM
+int chunkSteps(const hbk_engine* e, bool glacier) {
+    const int minBlocks = hbk::hbkMinBlocks(e->st.n_soil_stores, glacier);
+    const int nq = glacier ? 3 : 1;
     const size_t budget = (size_t)(220 * 1024) / minBlocks - 1024;
     // (measured: the shared-memory carve-out shrinks the L1 that serves the register spills; with one block
     // barrier per chunk, 16 steps per chunk is the optimum on C2: 4 -> 2.07e10, 8 -> 2.14e10, 16 -> 2.18e10,
     // profiles/r01_tuning.md)
-    int tc = HBK_ENS_TC;
+    int tc = hbk::hbkEnsTC(glacier);
     for (;;) {
         const size_t fRow = (e->haveRaw[0] ? (size_t)tc * e->UB : (size_t)tc + 2);
         const size_t bytes = 128 + 2 * e->nVars() * fRow * 8 + (size_t)nq * tc * (e->PB * e->UB + 2 * e->PB) * 8;
@@ -1621,14 +1652,80 @@ void chooseShape(hbk_engine* e) {
         const int v = std::atoi(force);
         if (v >= 2 && v <= 64 && (v & (v - 1)) == 0) tc = v;
     }
-    e->TC = tc;
+    return tc;
 }
 
-size_t smemBytes(const hbk_engine* e, bool tiled) {
-    const int nq = e->st.has_glacier ? 3 : 1;
-    const size_t fRow = tiled ? (size_t)e->TC * e->UB : (size_t)e->TC + 2;
-    return 128 + 2 * e->nVars() * fRow * 8 + (size_t)nq * e->TC * (e->PB * e->UB + (e->clusterMode ? 2 * e->PB : 0)) * 8 +
-           (HBK_PAR_SHARED ? (size_t)hbk::kParFields * e->PB * 8 : 0);
+// Tiles per block for `nTiles` unit tiles run by a kernel variant: enough blocks to fill the machine several times,
+// otherwise as many tiles per block as possible (G = all tiles: the block sums every unit of its sets itself)
+int tilesPerBlock(const hbk_engine* e, int nTiles, bool glacier) {
+    const long long nPGroups = (e->P + e->PB - 1) / e->PB;
+    const int minBlocks = hbk::hbkMinBlocks(e->st.n_soil_stores, glacier);
+    const long long wantBlocks = 148LL * minBlocks * 2;
+    const long long groups = std::min<long long>(nTiles, std::max<long long>(1, (wantBlocks + nPGroups - 1) / nPGroups));
+    int G = (int)((nTiles + groups - 1) / groups);
+    if (const char* force = std::getenv("HBK_TILES_PER_BLOCK")) {  // testing / tuning knob
+        const int g = std::atoi(force);
+        if (g > 0) G = std::min(g, nTiles);
+    }
+    return G;
+}
+
+// The launches of a run segment. A glacier structure compiles the glacier variant of the unit kernel (three outlet
+// quantities, the glacier cover's state and parameters live: 128 registers, 4 blocks per SM), and that variant costs the
+// same on a unit without ice (measured on C3 / C4: 46 % / 36 % more than the plain variant on the same units). Units whose
+// glacier cover is empty and can never gain area — fraction exactly 0 (ground exactly 1), in no delta-h table, never
+// named by a land-cover change — compute exactly what the plain variant computes (LandCover.h:91-93: a null brick is
+// skipped), so runs of unit tiles that hold only such units are launched with the plain variant; their deposits into
+// the sub-basin stores are zero. Every launch writes partial outlet series per tile group, summed in group order by
+// hbkReduceTiles. Not with a recorder (the plain variant has no glacier labels), clusters, or the lateral kernel.
+void planRuns(hbk_engine* e) {
+    e->runs.clear();
+    const bool glacier = e->st.has_glacier != 0;
+    auto single = [&]() {
+        e->runs.push_back({0, e->nUTiles, glacier, e->TC, e->G, e->nGroups, 0});
+        e->totalGroups = e->nGroups;
+        e->glacierGroups = glacier ? e->nGroups : 0;
+    };
+    const char* knob = std::getenv("HBK_SPLIT_GLACIER");
+    if (!glacier || e->clusterMode || e->st.snow_slide_kind != HBK_SNOW_SLIDE_NONE || e->recordMask != 0 ||
+        (knob && knob[0] == '0') || HBK_PAR_SHARED)
+        return single();
+    std::vector<char> ice(e->U, 0);  // the unit may carry ice at some time of the run
+    for (int u = 0; u < e->U; ++u)
+        ice[u] = e->hGlacierVariant[u] && !(e->hFracGl[u] == 0.0 && e->hFracG[u] == 1.0);
+    for (const auto& ev : e->events)
+        if (ev.kind == 0 && ev.unit >= 0 && ev.unit < e->U) ice[ev.unit] = 1;
+    for (int u : e->hDhUnits)
+        if (u >= 0 && u < e->U) ice[u] = 1;
+    if (e->hasTwins)
+        for (int u = 0; u < e->U; ++u)
+            if (e->hTwinOf[u] >= 0) ice[u] = ice[e->hTwinOf[u]] = 1;
+    std::vector<char> tileIce(e->nUTiles, 0);
+    for (int u = 0; u < e->U; ++u)
+        if (ice[u]) tileIce[u / e->UB] = 1;
+    std::vector<hbk_engine::TileRun> runs;
+    for (int t = 0; t < e->nUTiles; ++t) {
+        if (runs.empty() || runs.back().glacier != (tileIce[t] != 0)) runs.push_back({t, t, tileIce[t] != 0, 0, 0, 0, 0});
+        runs.back().tile1 = t + 1;
+    }
+    bool anyIce = false, anyPlain = false;
+    for (const auto& r : runs) (r.glacier ? anyIce : anyPlain) = true;
+    // a handful of launches at most (glacier units sit together in an elevation-sorted basin); a basin without any ice keeps
+    // the glacier variant, which writes the (zero) deposits the sub-basin stores read
+    if (!anyIce || !anyPlain || runs.size() > 6) return single();
+    int base = 0;
+    for (int pass = 0; pass < 2; ++pass)  // glacier groups first: the deposits are summed over those only
+        for (auto& r : runs) {
+            if (r.glacier != (pass == 0)) continue;
+            r.TC = r.glacier ? e->TC : chunkSteps(e, false);
+            r.G = tilesPerBlock(e, r.tile1 - r.tile0, r.glacier);
+            r.nGroups = (r.tile1 - r.tile0 + r.G - 1) / r.G;
+            r.grpBase = base;
+            base += r.nGroups;
+            if (pass == 0) e->glacierGroups = base;
+        }
+    e->totalGroups = base;
+    e->runs = runs;
 }
 
 using KernelFn = void (*)(const KArgs);
@@ -1657,8 +1754,8 @@ KernelFn pickSoil(int nSoil, bool glacier, bool daily, bool ens) {
 // template instantiation, i.e. which process device functions are compiled into the time loop. ens: the launch has the
 // ensemble block shape (32 sets x 4 units, 16-step chunks, station forcing, no cluster) that one instantiation per
 // structure fixes at compile time.
-KernelFn pickKernel(const hbk_structure& st, bool ens) {
-    const bool daily = st.time_step_days == 1.0, glacier = st.has_glacier != 0;
+KernelFn pickKernel(const hbk_structure& st, bool glacier, bool ens) {
+    const bool daily = st.time_step_days == 1.0;
     switch (st.solver) {
         case HBK_SOLVER_EULER: return pickSoil<0>(st.n_soil_stores, glacier, daily, ens);
         case HBK_SOLVER_HEUN: return pickSoil<1>(st.n_soil_stores, glacier, daily, ens);
@@ -2221,6 +2318,7 @@ int hbk_clear_actions(hbk_engine* e) {
     if (!e) return HBK_E_ARG;
     e->events.clear();
     e->dhUnits = 0;
+    e->hDhUnits.clear();
     e->dhTablesSet = false;
     return HBK_OK;
 }
@@ -2313,6 +2411,7 @@ int hbk_set_delta_h_tables(hbk_engine* e, int32_t n, const int32_t* units, int32
         HBK_CUDA(cudaMemcpy(e->dDhVolumes, volumes, sizeof(double) * (size_t)n * nRows, cudaMemcpyHostToDevice));
     }
     e->dhUnits = n;
+    e->hDhUnits.assign(units, units + n);
     e->dhRows = nRows;
     e->dhTablesSet = true;
     double initialVolume = 0;
@@ -2450,14 +2549,20 @@ static void launchBasinStores(hbk_engine* e, int tBegin, int tEnd, const double*
 }
 
 // The tiled unit kernel (hbkRunUnits) over one segment.
-static int launchUnitKernel(hbk_engine* e, KArgs& a, bool tiled, int tBegin, int tEnd) {
-    const bool ens = e->PB == 32 && e->UB == 4 && e->TC == HBK_ENS_TC && !tiled && !e->clusterMode && a.nVars == 3 &&
-                     !std::getenv("HBK_NO_ENS_SHAPE");
-    KernelFn fn = pickKernel(e->st, ens);
-    const size_t smem = smemBytes(e, tiled);
+static int launchUnitKernel(hbk_engine* e, KArgs& a, bool tiled, int tBegin, int tEnd, const hbk_engine::TileRun& run) {
+    a.TC = run.TC;
+    a.G = run.G;
+    a.nGroups = run.nGroups;
+    a.tile0 = run.tile0;
+    a.tile1 = run.tile1;
+    a.grpBase = run.grpBase;
+    const bool ens = e->PB == 32 && e->UB == 4 && run.TC == hbk::hbkEnsTC(run.glacier) && !tiled && !e->clusterMode &&
+                     a.nVars == 3 && !std::getenv("HBK_NO_ENS_SHAPE");
+    KernelFn fn = pickKernel(e->st, run.glacier, ens);
+    const size_t smem = smemBytes(e, tiled, run.glacier, run.TC);
     HBK_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int nPGroups = (e->P + e->PB - 1) / e->PB;
-    const long long grid = (long long)nPGroups * (e->clusterMode ? e->nUTiles : e->nGroups);
+    const long long grid = (long long)nPGroups * (e->clusterMode ? e->nUTiles : run.nGroups);
     if (grid > 2147483647LL) return fail(e, HBK_E_UNSUPPORTED, "grid too large");
     // tuning aid: HBK_BLOCK_TIMES=<file> dumps start / end time and SM of every block of the (last) unit launch
     unsigned long long* dTimes = nullptr;
@@ -2481,7 +2586,7 @@ static int launchUnitKernel(hbk_engine* e, KArgs& a, bool tiled, int tBegin, int
             const long long v = std::atoll(forced);
             if (v > 0) slots = std::min(slots, v);
         }
-        const int nChunks = (tEnd - tBegin + e->TC - 1) / e->TC;
+        const int nChunks = (tEnd - tBegin + run.TC - 1) / run.TC;
         const char* q = std::getenv("HBK_QUEUE");
         const bool want = !(q && q[0] == '0') && !e->clusterMode && slots > 0 && grid > slots && nChunks >= 8;
         if (want) {
@@ -2612,7 +2717,7 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
     a.lds = (long long)e->P * e->U;
     a.sP = e->stateLaneP ? 1 : e->U;
     a.sU = e->stateLaneP ? e->P : 1;
-    const bool multi = e->nGroups > 1;
+    const bool multi = e->totalGroups > 1;
     a.outQ = multi ? e->dPartQ : e->dOutlet;
     a.outD1 = multi ? e->dPartD1 : e->dD1;
     a.outD2 = multi ? e->dPartD2 : e->dD2;
@@ -2631,26 +2736,28 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
         int rc = launchLateralKernel(e, a);
         if (rc) return rc;
     } else {
-        int rc = launchUnitKernel(e, a, tiled, tBegin, tEnd);
-        if (rc) return rc;
+        for (const auto& run : e->runs) {
+            int rc = launchUnitKernel(e, a, tiled, tBegin, tEnd, run);
+            if (rc) return rc;
+        }
     }
 
     if (writeOutputs && multi) {
         const long long n = (long long)e->P * (tEnd - tBegin);
         const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
-        hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartQ, e->dOutlet, e->nGroups, e->P, e->ldt, tBegin, tEnd, e->dPerm);
+        hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartQ, e->dOutlet, e->totalGroups, e->P, e->ldt, tBegin, tEnd, e->dPerm);
         e->lastLaunches++;
         if (e->st.has_glacier) {
-            hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD1, e->dD1, e->nGroups, e->P, e->ldt, tBegin, tEnd, nullptr);
-            hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD2, e->dD2, e->nGroups, e->P, e->ldt, tBegin, tEnd, nullptr);
+            hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD1, e->dD1, e->glacierGroups, e->P, e->ldt, tBegin, tEnd, nullptr);
+            hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD2, e->dD2, e->glacierGroups, e->P, e->ldt, tBegin, tEnd, nullptr);
             e->lastLaunches += 2;
         }
     } else if (!writeOutputs && multi && e->st.has_glacier) {
         // spin-up: the deposits are still needed by the sub-basin stores
         const long long n = (long long)e->P * (tEnd - tBegin);
         const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
-        hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD1, e->dD1, e->nGroups, e->P, e->ldt, tBegin, tEnd, nullptr);
-        hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD2, e->dD2, e->nGroups, e->P, e->ldt, tBegin, tEnd, nullptr);
+        hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD1, e->dD1, e->glacierGroups, e->P, e->ldt, tBegin, tEnd, nullptr);
+        hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD2, e->dD2, e->glacierGroups, e->P, e->ldt, tBegin, tEnd, nullptr);
         e->lastLaunches += 2;
     }
     if (e->st.has_glacier && e->shard && e->shardReduce && writeOutputs) {
@@ -2769,20 +2876,21 @@ int hbk_run(hbk_engine* e) {
     }
 
     // (re)allocate shape-dependent buffers
-    const bool multi = e->nGroups > 1;
+    planRuns(e);
+    const bool multi = e->totalGroups > 1;
     const size_t outN = (size_t)e->P * e->ldt;
-    if (e->partGroups != e->nGroups) {
+    if (e->partGroups != e->totalGroups) {
         freeDev(e->dPartQ);
         freeDev(e->dPartD1);
         freeDev(e->dPartD2);
-        e->partGroups = e->nGroups;
+        e->partGroups = e->totalGroups;
     }
-    if (multi && !e->dPartQ) HBK_CUDA(cudaMalloc(&e->dPartQ, sizeof(double) * outN * e->nGroups));
+    if (multi && !e->dPartQ) HBK_CUDA(cudaMalloc(&e->dPartQ, sizeof(double) * outN * e->totalGroups));
     if (e->st.has_glacier) {
         if (!e->dD1) HBK_CUDA(cudaMalloc(&e->dD1, sizeof(double) * outN));
         if (!e->dD2) HBK_CUDA(cudaMalloc(&e->dD2, sizeof(double) * outN));
-        if (multi && !e->dPartD1) HBK_CUDA(cudaMalloc(&e->dPartD1, sizeof(double) * outN * e->nGroups));
-        if (multi && !e->dPartD2) HBK_CUDA(cudaMalloc(&e->dPartD2, sizeof(double) * outN * e->nGroups));
+        if (multi && !e->dPartD1) HBK_CUDA(cudaMalloc(&e->dPartD1, sizeof(double) * outN * e->totalGroups));
+        if (multi && !e->dPartD2) HBK_CUDA(cudaMalloc(&e->dPartD2, sizeof(double) * outN * e->totalGroups));
     }
     const int nRec = __builtin_popcountll(e->recordMask);
     const size_t recBytes = sizeof(double) * (size_t)nRec * e->P * e->T * e->U;
@@ -3074,6 +3182,18 @@ int hbk_last_run_stats(hbk_engine* e, double* ms, int32_t* launches, int64_t* un
     if (ms) *ms = e->lastMs;
     if (launches) *launches = e->lastLaunches;
     if (unconverged) *unconverged = e->lastUnconverged;
+    return HBK_OK;
+}
+
+int hbk_last_run_shape(hbk_engine* e, int32_t* out) {
+    if (!e || !out) return HBK_E_ARG;
+    if (e->runs.empty()) return fail(e, HBK_E_STATE, "hbk_last_run_shape needs a run");
+    int plainTiles = 0;
+    for (const auto& r : e->runs)
+        if (e->st.has_glacier && !r.glacier) plainTiles += r.tile1 - r.tile0;
+    const int32_t v[8] = {e->PB, e->UB, e->nUTiles, (int32_t)e->runs.size(), e->runs[0].TC, e->runs[0].G, e->totalGroups,
+                          plainTiles};
+    std::copy(v, v + 8, out);
     return HBK_OK;
 }
 

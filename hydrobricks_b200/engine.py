@@ -134,6 +134,7 @@ def load_library():
     L.hbk_get_basin_state.argtypes = [vp, dp]
     L.hbk_outlet_dev.argtypes = [vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(i64)]
     L.hbk_last_run_stats.argtypes = [vp, dp, ip, ctypes.POINTER(i64)]
+    L.hbk_last_run_shape.argtypes = [vp, ip]
     L.hbk_get_unconverged.argtypes = [vp, ip]
     L.hbk_stream.argtypes = [vp]
     L.hbk_stream.restype = ctypes.c_void_p
@@ -434,6 +435,14 @@ class Engine:
         ms, n, unc = ctypes.c_double(), ctypes.c_int32(), ctypes.c_int64()
         self._check(self.L.hbk_last_run_stats(self.h, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(unc)))
         return {"kernel_ms": ms.value, "launches": n.value, "unconverged_sweeps": unc.value}
+
+    def last_run_shape(self):
+        """Launch shape of the last run (hbk_last_run_shape)."""
+        v = (ctypes.c_int32 * 8)()
+        self._check(self.L.hbk_last_run_shape(self.h, v))
+        keys = ("sets_per_block", "units_per_block", "unit_tiles", "launches_per_segment", "steps_per_chunk",
+                "tiles_per_block", "tile_groups", "plain_variant_tiles")
+        return dict(zip(keys, (int(x) for x in v)))
 
     def unconverged_per_set(self):
         """Constraint passes per parameter set that did not stabilise within 10 sweeps (hbk_get_unconverged)."""

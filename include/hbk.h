@@ -294,6 +294,11 @@ int hbk_get_basin_state(hbk_engine* e, double* out);
 int hbk_outlet_dev(hbk_engine* e, const double** ptr, int64_t* ld);
 /* Device time of the last hbk_run (CUDA events on the engine's stream), and kernel launch count. */
 int hbk_last_run_stats(hbk_engine* e, double* kernel_ms, int32_t* n_launches, int64_t* unconverged_sweeps);
+/* Launch shape of the last hbk_run (what a bench line reports as its block shape), out[8]: parameter sets per block (lanes),
+ * hydro units per block, unit tiles, unit-kernel launches per run segment (2+: the tiles without glacier units run the
+ * plain kernel variant), time steps per chunk and tiles per block of the first launch, tile groups in total (> 1: partial
+ * outlet series + hbkReduceTiles), unit tiles run by the plain variant of a glacier structure. */
+int hbk_last_run_shape(hbk_engine* e, int32_t* out);
 /* Per parameter set: number of constraint passes of its hydro units in the last run that ended with the reference's
  * "The storage constraints did not stabilize after 10 sweeps" (Processor.cpp:191-209) — the ill-conditioned small-capacity
  * regime in which the reference's own result hangs on the last bit. out[n_sets], caller's set order. */

@@ -29,6 +29,9 @@ def main():
     ap.add_argument("--solver", default="rk4")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--tag", default=os.environ.get("HBK_LIB", "default"))
+    # experiments on glacier workloads: no unit carries ice (the glacier kernel on plain units) / the plain structure
+    ap.add_argument("--no-ice", action="store_true", help="glacier structure, glacier fraction 0 on every unit")
+    ap.add_argument("--plain", action="store_true", help="same units and soil stores without the glacier cover")
     args = ap.parse_args()
 
     import bench
@@ -36,17 +39,21 @@ def main():
 
     wl = bench.WORKLOADS[args.workload]
     P, U, T = args.sets, args.units or wl["units"], args.timesteps
-    units = bench.hydro_units(U, area=wl["area"], glacier=wl["glacier"])
+    glacier = wl["glacier"] and not args.plain
+    units = bench.hydro_units(U, area=wl["area"], glacier=glacier)
+    if args.no_ice and glacier:
+        for u in units:
+            u["land_covers"] = [("ground", 1.0), ("glacier", 0.0)]
     precip, temp, pet = bench.station_series(T)
     ps = bench.parameter_sets(P)
-    if wl["glacier"]:
+    if glacier:
         rng = np.random.Generator(np.random.MT19937(91))
         ps.update({"a_ice": ps["a_snow"] + rng.uniform(0.5, 6, P), "k_snow": rng.uniform(0.05, 0.6, P),
                    "k_ice": rng.uniform(0.05, 0.6, P)})
     if wl["soil"] == 2:
         rng = np.random.Generator(np.random.MT19937(92))
         ps.update({"percol": rng.uniform(0, 10, P), "k_slow_2": ps["k_slow_1"] * rng.uniform(0.05, 0.9, P)})
-    covers = ["ground", "glacier"] if wl["glacier"] else ["ground"]
+    covers = ["ground", "glacier"] if glacier else ["ground"]
     m = models.Socont(solver=args.solver, soil_storage_nb=wl["soil"], surface_runoff="socont_runoff",
                       land_cover_names=covers, land_cover_types=covers,
                       glacier_infinite_storage=not wl.get("finite_ice", False), backend="python")
