@@ -45,10 +45,14 @@ namespace hbk {
 #define HBK_MIN_BLOCKS 6  // register budget = 65536 / (HBK_MAX_THREADS * HBK_MIN_BLOCKS)
 #endif
 #ifndef HBK_MIN_BLOCKS_SOIL2
-#define HBK_MIN_BLOCKS_SOIL2 HBK_MIN_BLOCKS  // two soil stores without glacier
+// two soil stores without glacier: at 6 blocks (80 registers) the spill frames (312 B x 768 threads) overflow the L1 left
+// beside the shared memory; 5 blocks (96 registers, 240 B) measured +4 % on C4's plain tiles, 4 blocks no better
+#define HBK_MIN_BLOCKS_SOIL2 5
 #endif
 #ifndef HBK_ENS_TC_GLACIER
-#define HBK_ENS_TC_GLACIER HBK_ENS_TC  // glacier variants: three outlet quantities per step in the chunk slots
+// glacier variants: three outlet quantities per step in the chunk slots. 16 steps x 4 blocks = 200 KB of shared memory
+// leave 23 KB of L1 for 143 KB of spill frames (ncu r02s: 5 % local-load hit rate); 8 steps measured +4 % on C3 and C4
+#define HBK_ENS_TC_GLACIER 8
 #endif
 #ifndef HBK_MIN_BLOCKS_GLACIER
 #define HBK_MIN_BLOCKS_GLACIER 4  // the glacier variants carry ~60 more live registers: 128 regs x 16 warps (C3: +8.5 % over 6)
@@ -670,6 +674,28 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, hbkMinBlocks(NSOIL, GLACIER))
             const bool last = (tl == nTilesHere - 1);
             if (last) {
                 __syncthreads();
+                if (!ENS && UB >= 32) {
+                    // few sets, many units per block (distributed basins): one WARP per (quantity, step, set) row — the
+                    // lanes add strided slices of the row's UB values in unit order, then a butterfly over the lanes
+                    // (a single thread per row would walk up to 128 dependent additions while the block waits)
+                    const int lane = tid & 31;
+                    for (int row = tid >> 5; row < NQ * n * PB; row += nThreads >> 5) {
+                        const int qi = row / (n * PB);
+                        const int rem = row - qi * n * PB;
+                        const int tc = rem / PB;
+                        const int lp = rem - tc * PB;
+                        const double* src = qbuf + ((size_t)qi * TC + tc) * nThreads + lp;
+                        double s = 0.0;
+                        for (int k = lane; k < UB; k += 32) s += src[(size_t)k * PB];
+                        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                        const int gp = pg * PB + lp;
+                        if (lane == 0 && gp < a.P && (a.writeOutputs || qi > 0)) {
+                            double* dst = (qi == 0) ? a.outQ : (qi == 1 ? a.outD1 : a.outD2);
+                            const int orow = (qi == 0 && a.outQFinal && a.perm) ? a.perm[gp] : gp;
+                            __stcs(&dst[((size_t)(a.grpBase + grp) * a.P + orow) * a.ldt + (t0 + tc)], s);
+                        }
+                    }
+                } else
                 for (int idx = tid; idx < NQ * n * PB; idx += nThreads) {
                     const int qi = idx / (n * PB);
                     const int rem = idx - qi * n * PB;
@@ -1493,8 +1519,13 @@ struct hbk_engine {
     int* dErr = nullptr;
     unsigned long long* dUnconv = nullptr;
     int* dUnconvSet = nullptr;  // [P]
-    int* dQueue = nullptr;      // work queue of the unit kernel: [0] item counter, [1 + vb] slices done per virtual block
-    size_t queueInts = 0;
+    // work queue of a unit-kernel launch: [0] item counter, [1 + vb] slices done per virtual block; one per launch of a
+    // run segment (the launches of a split glacier structure run concurrently, each on its own stream)
+    static constexpr int kMaxRuns = 6;
+    int* dQueue[kMaxRuns] = {};
+    size_t queueInts[kMaxRuns] = {};
+    cudaStream_t auxStream[kMaxRuns] = {};  // [0] unused: the first launch runs on `stream`
+    cudaEvent_t evFork = nullptr, evJoin[kMaxRuns] = {};
     int spinupSteps = 0;
     bool unitsSet = false, ran = false;
     // dated actions
@@ -1712,7 +1743,7 @@ void planRuns(hbk_engine* e) {
     for (const auto& r : runs) (r.glacier ? anyIce : anyPlain) = true;
     // a handful of launches at most (glacier units sit together in an elevation-sorted basin); a basin without any ice keeps
     // the glacier variant, which writes the (zero) deposits the sub-basin stores read
-    if (!anyIce || !anyPlain || runs.size() > 6) return single();
+    if (!anyIce || !anyPlain || (int)runs.size() > hbk_engine::kMaxRuns) return single();
     int base = 0;
     for (int pass = 0; pass < 2; ++pass)  // glacier groups first: the deposits are summed over those only
         for (auto& r : runs) {
@@ -1974,7 +2005,12 @@ void hbk_engine_destroy(hbk_engine* e) {
     freeDev(e->dErr);
     freeDev(e->dUnconv);
     freeDev(e->dUnconvSet);
-    freeDev(e->dQueue);
+    for (auto& q : e->dQueue) freeDev(q);
+    for (auto& st : e->auxStream)
+        if (st) cudaStreamDestroy(st);
+    for (auto& ev : e->evJoin)
+        if (ev) cudaEventDestroy(ev);
+    if (e->evFork) cudaEventDestroy(e->evFork);
     freeDev(e->dTwinOf);
     freeDev(e->dTwinCol);
     freeDev(e->dLatOff);
@@ -2549,7 +2585,8 @@ static void launchBasinStores(hbk_engine* e, int tBegin, int tEnd, const double*
 }
 
 // The tiled unit kernel (hbkRunUnits) over one segment.
-static int launchUnitKernel(hbk_engine* e, KArgs& a, bool tiled, int tBegin, int tEnd, const hbk_engine::TileRun& run) {
+static int launchUnitKernel(hbk_engine* e, KArgs& a, bool tiled, int tBegin, int tEnd, const hbk_engine::TileRun& run,
+                            cudaStream_t stream, int slot) {
     a.TC = run.TC;
     a.G = run.G;
     a.nGroups = run.nGroups;
@@ -2598,14 +2635,14 @@ static int launchUnitKernel(hbk_engine* e, KArgs& a, bool tiled, int tBegin, int
             if (nItems < 2000000000LL) {
                 a.nItems = (int)nItems;
                 const size_t need = 1 + (size_t)grid;
-                if (need > e->queueInts) {
-                    freeDev(e->dQueue);
-                    HBK_CUDA(cudaMalloc(&e->dQueue, sizeof(int) * need));
-                    e->queueInts = need;
+                if (need > e->queueInts[slot]) {
+                    freeDev(e->dQueue[slot]);
+                    HBK_CUDA(cudaMalloc(&e->dQueue[slot], sizeof(int) * need));
+                    e->queueInts[slot] = need;
                 }
-                HBK_CUDA(cudaMemsetAsync(e->dQueue, 0, sizeof(int) * need, e->stream));
-                a.workCounter = e->dQueue;
-                a.progress = e->dQueue + 1;
+                HBK_CUDA(cudaMemsetAsync(e->dQueue[slot], 0, sizeof(int) * need, stream));
+                a.workCounter = e->dQueue[slot];
+                a.progress = e->dQueue[slot] + 1;
                 launchGrid = (unsigned)slots;
             }
         }
@@ -2617,7 +2654,7 @@ static int launchUnitKernel(hbk_engine* e, KArgs& a, bool tiled, int tBegin, int
         cfg.gridDim = dim3((unsigned)grid);
         cfg.blockDim = dim3(e->PB * e->UB);
         cfg.dynamicSmemBytes = smem;
-        cfg.stream = e->stream;
+        cfg.stream = stream;
         cudaLaunchAttribute attr{};
         attr.id = cudaLaunchAttributeClusterDimension;
         attr.val.clusterDim.x = (unsigned)e->nUTiles;
@@ -2627,12 +2664,12 @@ static int launchUnitKernel(hbk_engine* e, KArgs& a, bool tiled, int tBegin, int
         cfg.numAttrs = 1;
         HBK_CUDA(cudaLaunchKernelExC(&cfg, (const void*)fn, args));
     } else {
-        HBK_CUDA(cudaLaunchKernel((const void*)fn, dim3(launchGrid), dim3(e->PB * e->UB), args, smem, e->stream));
+        HBK_CUDA(cudaLaunchKernel((const void*)fn, dim3(launchGrid), dim3(e->PB * e->UB), args, smem, stream));
     }
     e->lastLaunches++;
     if (dTimes) {
         std::vector<unsigned long long> h(3 * (size_t)grid);
-        if (cudaStreamSynchronize(e->stream) == cudaSuccess &&
+        if (cudaStreamSynchronize(stream) == cudaSuccess &&
             cudaMemcpy(h.data(), dTimes, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost) == cudaSuccess) {
             if (FILE* f = std::fopen(timesPath, "wb")) {
                 std::fwrite(h.data(), sizeof(unsigned long long), h.size(), f);
@@ -2736,9 +2773,28 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
         int rc = launchLateralKernel(e, a);
         if (rc) return rc;
     } else {
-        for (const auto& run : e->runs) {
-            int rc = launchUnitKernel(e, a, tiled, tBegin, tEnd, run);
+        // the launches of a split glacier structure are independent (their own units, partial buffers and work queues):
+        // they run side by side, the second and later ones on auxiliary streams forked from / joined to the engine's
+        const char* serial = std::getenv("HBK_SPLIT_SERIAL");
+        const bool fork = e->runs.size() > 1 && !(serial && serial[0] == '1');
+        if (fork) {
+            if (!e->evFork) HBK_CUDA(cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming));
+            HBK_CUDA(cudaEventRecord(e->evFork, e->stream));
+        }
+        for (size_t i = 0; i < e->runs.size(); ++i) {
+            cudaStream_t stream = e->stream;
+            if (fork && i > 0) {
+                if (!e->auxStream[i]) HBK_CUDA(cudaStreamCreateWithFlags(&e->auxStream[i], cudaStreamNonBlocking));
+                if (!e->evJoin[i]) HBK_CUDA(cudaEventCreateWithFlags(&e->evJoin[i], cudaEventDisableTiming));
+                stream = e->auxStream[i];
+                HBK_CUDA(cudaStreamWaitEvent(stream, e->evFork, 0));
+            }
+            int rc = launchUnitKernel(e, a, tiled, tBegin, tEnd, e->runs[i], stream, (int)i);
             if (rc) return rc;
+            if (fork && i > 0) {
+                HBK_CUDA(cudaEventRecord(e->evJoin[i], stream));
+                HBK_CUDA(cudaStreamWaitEvent(e->stream, e->evJoin[i], 0));
+            }
         }
     }
 
