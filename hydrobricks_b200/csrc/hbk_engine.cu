@@ -285,15 +285,18 @@ __host__ __device__ constexpr int hbkEnsTC(bool glacier) { return glacier ? HBK_
 // buffers, no second pass. With G = 1 (few sets, many units) the state never leaves the registers.
 // DAILY: the time step is exactly one day (the reference's usual case); x * 1.0 and x / 1.0 are exact, so the
 // multiplications by dt fold away without changing a bit.
-template <int SOLVER, int NSOIL, bool GLACIER, bool DAILY, bool ENS>
+template <int SOLVER, int NSOIL, bool GLACIER, bool DAILY, int SHAPE>
 __global__ void __launch_bounds__(HBK_MAX_THREADS, hbkMinBlocks(NSOIL, GLACIER))
     hbkRunUnits(const KArgs a) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     constexpr int NQ = GLACIER ? 3 : 1;
-    // ENS: the block shape of calibration ensembles fixed at compile time — 32 parameter sets (lanes) x 4 units, 16 steps per
-    // chunk, station forcing with fused spatialisation, no cluster — so that the address arithmetic of the time loop
-    // folds into immediates (at 80 registers ptxas otherwise re-derives it from the kernel arguments at every step)
-    const int PB = ENS ? 32 : a.PB, UB = ENS ? 4 : a.UB, TC = ENS ? hbkEnsTC(GLACIER) : a.TC;
+    // SHAPE 1 / 2: a block shape fixed at compile time — 1: calibration ensembles, 32 parameter sets (lanes) x 4 units;
+    // 2: distributed basins, one parameter set x 128 units (lanes = units) — with the variant's chunk length, station
+    // forcing with fused spatialisation, no cluster, so that the address arithmetic of the time loop folds into
+    // immediates (at 80 registers ptxas otherwise re-derives it from the kernel arguments at every step). 0: any shape.
+    constexpr bool ENS = SHAPE != 0;
+    const int PB = SHAPE == 1 ? 32 : (SHAPE == 2 ? 1 : a.PB), UB = SHAPE == 1 ? 4 : (SHAPE == 2 ? 128 : a.UB);
+    const int TC = ENS ? hbkEnsTC(GLACIER) : a.TC;
     const int forcingMode = ENS ? 1 : a.forcingMode;
     const int NV = ENS ? 3 : a.nVars;  // staged forcing variables (the ensemble shape never carries the radiation)
     const bool clusterMode = ENS ? false : (a.clusterMode != 0);
@@ -674,7 +677,7 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, hbkMinBlocks(NSOIL, GLACIER))
             const bool last = (tl == nTilesHere - 1);
             if (last) {
                 __syncthreads();
-                if (!ENS && UB >= 32) {
+                if (SHAPE != 1 && UB >= 32) {
                     // few sets, many units per block (distributed basins): one WARP per (quantity, step, set) row — the
                     // lanes add strided slices of the row's UB values in unit order, then a butterfly over the lanes
                     // (a single thread per row would walk up to 128 dependent additions while the block waits)
@@ -1762,36 +1765,37 @@ void planRuns(hbk_engine* e) {
 using KernelFn = void (*)(const KArgs);
 
 template <int SOLVER, int NSOIL, bool GLACIER>
-KernelFn pickDaily(bool daily, bool ens) {
+KernelFn pickDaily(bool daily, int shape) {
     // the sequential solvers (SOLVER 3) are not the throughput path: one instantiation, dt read at run time
     if constexpr (SOLVER == 3) {
-        return (KernelFn)hbkRunUnits<SOLVER, NSOIL, GLACIER, false, false>;
+        return (KernelFn)hbkRunUnits<SOLVER, NSOIL, GLACIER, false, 0>;
     } else {
-        // the compile-time ensemble shape exists for daily steps only (the case ensembles are run in)
-        if (daily && ens) return (KernelFn)hbkRunUnits<SOLVER, NSOIL, GLACIER, true, true>;
-        return daily ? (KernelFn)hbkRunUnits<SOLVER, NSOIL, GLACIER, true, false>
-                     : (KernelFn)hbkRunUnits<SOLVER, NSOIL, GLACIER, false, false>;
+        // the compile-time shapes exist for daily steps only (the case ensembles and distributed basins are run in)
+        if (daily && shape == 1) return (KernelFn)hbkRunUnits<SOLVER, NSOIL, GLACIER, true, 1>;
+        if (daily && shape == 2) return (KernelFn)hbkRunUnits<SOLVER, NSOIL, GLACIER, true, 2>;
+        return daily ? (KernelFn)hbkRunUnits<SOLVER, NSOIL, GLACIER, true, 0>
+                     : (KernelFn)hbkRunUnits<SOLVER, NSOIL, GLACIER, false, 0>;
     }
 }
 template <int SOLVER, int NSOIL>
-KernelFn pickGlacier(bool glacier, bool daily, bool ens) {
-    return glacier ? pickDaily<SOLVER, NSOIL, true>(daily, ens) : pickDaily<SOLVER, NSOIL, false>(daily, ens);
+KernelFn pickGlacier(bool glacier, bool daily, int shape) {
+    return glacier ? pickDaily<SOLVER, NSOIL, true>(daily, shape) : pickDaily<SOLVER, NSOIL, false>(daily, shape);
 }
 template <int SOLVER>
-KernelFn pickSoil(int nSoil, bool glacier, bool daily, bool ens) {
-    return nSoil == 2 ? pickGlacier<SOLVER, 2>(glacier, daily, ens) : pickGlacier<SOLVER, 1>(glacier, daily, ens);
+KernelFn pickSoil(int nSoil, bool glacier, bool daily, int shape) {
+    return nSoil == 2 ? pickGlacier<SOLVER, 2>(glacier, daily, shape) : pickGlacier<SOLVER, 1>(glacier, daily, shape);
 }
 // "Device functions selected from a per-structure process table": the table (hbk_structure) picks the
 // template instantiation, i.e. which process device functions are compiled into the time loop. ens: the launch has the
 // ensemble block shape (32 sets x 4 units, 16-step chunks, station forcing, no cluster) that one instantiation per
 // structure fixes at compile time.
-KernelFn pickKernel(const hbk_structure& st, bool glacier, bool ens) {
+KernelFn pickKernel(const hbk_structure& st, bool glacier, int shape) {
     const bool daily = st.time_step_days == 1.0;
     switch (st.solver) {
-        case HBK_SOLVER_EULER: return pickSoil<0>(st.n_soil_stores, glacier, daily, ens);
-        case HBK_SOLVER_HEUN: return pickSoil<1>(st.n_soil_stores, glacier, daily, ens);
-        case HBK_SOLVER_RK4: return pickSoil<2>(st.n_soil_stores, glacier, daily, ens);
-        default: return pickSoil<3>(st.n_soil_stores, glacier, false, false);  // sequential family
+        case HBK_SOLVER_EULER: return pickSoil<0>(st.n_soil_stores, glacier, daily, shape);
+        case HBK_SOLVER_HEUN: return pickSoil<1>(st.n_soil_stores, glacier, daily, shape);
+        case HBK_SOLVER_RK4: return pickSoil<2>(st.n_soil_stores, glacier, daily, shape);
+        default: return pickSoil<3>(st.n_soil_stores, glacier, false, 0);  // sequential family
     }
 }
 
@@ -2593,9 +2597,10 @@ static int launchUnitKernel(hbk_engine* e, KArgs& a, bool tiled, int tBegin, int
     a.tile0 = run.tile0;
     a.tile1 = run.tile1;
     a.grpBase = run.grpBase;
-    const bool ens = e->PB == 32 && e->UB == 4 && run.TC == hbk::hbkEnsTC(run.glacier) && !tiled && !e->clusterMode &&
-                     a.nVars == 3 && !std::getenv("HBK_NO_ENS_SHAPE");
-    KernelFn fn = pickKernel(e->st, run.glacier, ens);
+    const bool fixedShape = run.TC == hbk::hbkEnsTC(run.glacier) && !tiled && !e->clusterMode && a.nVars == 3 &&
+                            !std::getenv("HBK_NO_ENS_SHAPE");
+    const int shape = !fixedShape ? 0 : ((e->PB == 32 && e->UB == 4) ? 1 : ((e->PB == 1 && e->UB == 128) ? 2 : 0));
+    KernelFn fn = pickKernel(e->st, run.glacier, shape);
     const size_t smem = smemBytes(e, tiled, run.glacier, run.TC);
     HBK_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int nPGroups = (e->P + e->PB - 1) / e->PB;
