@@ -38,6 +38,7 @@ class Socont:
                  land_cover_names=None, land_cover_types=None, record_all=False, glacier_infinite_storage=True,
                  snow_melt_process="melt:degree_day", snow_ice_transformation=None, snow_sublimation_process=None,
                  snow_redistribution=None, snow_redistribution_skip_glaciers=False, snow_rain_process=None,
+                 snow_water_retention_process=None, snow_refreezing_process=None, rain_to_snowpack=False,
                  backend=None):
         self.backend = resolve_backend(backend)
         self.solver = solver
@@ -47,7 +48,16 @@ class Socont:
                         "snow_sublimation_process": snow_sublimation_process,
                         "snow_redistribution": snow_redistribution,
                         "snow_rain_process": snow_rain_process,  # model_settings.py:194-200; None -> snow_rain:linear
-                        "snow_redistribution_skip_glaciers": snow_redistribution_skip_glaciers}
+                        "snow_redistribution_skip_glaciers": snow_redistribution_skip_glaciers,
+                        # models/model.py:1184-1217 -> model_settings.py:139-141: liquid water kept in the snowpack
+                        # ('outflow:snow_holding'), refrozen ('refreeze:degree_day'), rain routed through the snowpack
+                        "snow_water_retention_process": snow_water_retention_process,
+                        "snow_refreezing_process": snow_refreezing_process,
+                        "rain_to_snowpack": rain_to_snowpack}
+        if snow_refreezing_process and not snow_water_retention_process:  # model_settings.py:233-239
+            raise ValueError("Snow refreezing requires a snow water retention process.")
+        if rain_to_snowpack and not snow_water_retention_process:  # model_settings.py:240-247
+            raise ValueError("Routing the rain to the snowpacks requires a snow water retention process.")
         self.land_cover_names = list(land_cover_names or ["open"])
         self.land_cover_types = list(land_cover_types or ["open"])
         self.record_all = record_all
@@ -116,7 +126,14 @@ class Socont:
             for t, n in zip(types, names):
                 s.add_land_cover_brick(n, "generic_land_cover" if t in ("ground", "generic_land_cover", "open",
                                                                         "forest", "lake") else t)
-            s.generate_snowpacks(self.options["snow_melt_process"])
+            if self.options["snow_water_retention_process"]:  # model_settings.py:248-255
+                s.generate_snowpacks_with_water_retention(self.options["snow_melt_process"],
+                                                          self.options["snow_water_retention_process"],
+                                                          self.options["rain_to_snowpack"])
+                if self.options["snow_refreezing_process"]:
+                    s.add_snowpack_refreezing(self.options["snow_refreezing_process"])
+            else:
+                s.generate_snowpacks(self.options["snow_melt_process"])
             if self.options["snow_ice_transformation"]:  # model_settings.py:258-259
                 s.add_snow_ice_transformation(self.options["snow_ice_transformation"])
             if self.options["snow_redistribution"]:  # model_settings.py:260-261
@@ -183,6 +200,10 @@ class Socont:
         elif self.options["snow_sublimation_process"] == "sublimation:pet":
             a["sublimation_pet_factor"] = ("type:snowpack", "sublimation_pet_factor")
             a["sublimation_factor"] = ("type:snowpack", "sublimation_pet_factor")
+        if self.options["snow_water_retention_process"]:  # models/hbv.py:367: cwh / whc, cfr
+            a["whc"] = a["cwh"] = ("type:snowpack", "water_holding_capacity")
+        if self.options["snow_refreezing_process"]:
+            a["cfr"] = ("type:snowpack", "refreezing_factor")
         if self._glacier_names:
             a.update({"k_snow": (RAIN_SNOWMELT_STORAGE, "response_factor"),
                       "k_ice": (ICEMELT_STORAGE, "response_factor")})

@@ -560,6 +560,43 @@ void GetRates(hbo_model& m, Process& p) {
             StoreRates1(p, static_cast<double>(p.params[0]));
             return;
         }
+        case HBO_P_OUTFLOW_SNOW_HOLDING: {  // ProcessOutflowSnowHolding.cpp:37-57
+            const Brick& b = m.bricks[p.brick];
+            if (b.kind != HBO_BRICK_SNOWPACK) {
+                StoreRates1(p, 0);
+                return;
+            }
+            const float whc = p.params[0];
+            double swe = ContentWithChanges(m.containers[b.second]);
+            double excess = ContentWithChanges(c) - whc * swe;
+            if (excess <= 0) {
+                StoreRates1(p, 0);
+                return;
+            }
+            StoreRates1(p, excess / m.dt);  // the time machine is wired to every process (ModelBuilder.cpp:126, 229)
+            return;
+        }
+        case HBO_P_REFREEZE_DEGREE_DAY: {  // ProcessRefreezeDegreeDay.cpp:72-87
+            const Process* melt = nullptr;  // FindSiblingMeltProcess (:52-64): the first melt:degree_day of the brick
+            for (int ip : m.bricks[p.brick].processes)
+                if (m.processes[ip].type == HBO_P_MELT_DEGREE_DAY) {
+                    melt = &m.processes[ip];
+                    break;
+                }
+            if (melt == nullptr) {
+                StoreRates1(p, 0);
+                return;
+            }
+            const float cfr = p.params[0];
+            const double ddf = melt->params[0], meltingTemperature = melt->params[1];
+            const double t = m.Forcing(HBO_V_TEMPERATURE, unit);
+            if (t >= meltingTemperature) {
+                StoreRates1(p, 0);
+                return;
+            }
+            StoreRates1(p, cfr * ddf * (meltingTemperature - t));
+            return;
+        }
         case HBO_P_SUBLIMATION_PET: {  // ProcessSublimationPET.cpp:46-51
             if (!ContentAccessible(m, c)) {
                 StoreRates1(p, 0);

@@ -43,7 +43,14 @@ enum {
     HBO_P_MELT_TEMPERATURE_INDEX = 13,
     /* transport:snow_slide (ProcessLateralSnowSlide.cpp): params coeff, exp, min_slope, max_slope,
      * min_snow_holding_depth, max_snow_depth; one instantaneous snow flux per (lateral connection, receiving snowpack) */
-    HBO_P_LATERAL_SNOW_SLIDE = 14
+    HBO_P_LATERAL_SNOW_SLIDE = 14,
+    /* outflow:snow_holding (ProcessOutflowSnowHolding.cpp): params water_holding_capacity; on the snowpack's water
+     * container, drains what exceeds the capacity x snow water equivalent */
+    HBO_P_OUTFLOW_SNOW_HOLDING = 15,
+    /* refreeze:degree_day (ProcessRefreezeDegreeDay.cpp): params refreezing_factor; on the snowpack's water container,
+     * instantaneous snow flux back to the same snowpack; degree-day factor and melting temperature of the sibling
+     * melt:degree_day process; forcing temperature */
+    HBO_P_REFREEZE_DEGREE_DAY = 16
 };
 enum {
     HBO_F_TO_BRICK = 0, HBO_F_TO_BRICK_INSTANT = 1, HBO_F_TO_OUTLET = 2, HBO_F_TO_ATMOSPHERE = 3,

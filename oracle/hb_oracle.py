@@ -41,6 +41,8 @@ PROC_KIND = {
     "melt:degree_day_aspect": 0,  # the degree-day factor of the unit's aspect class (ProcessMeltDegreeDayAspect.cpp:38-58)
     "melt:temperature_index": 13,
     "transport:snow_slide": 14,
+    "outflow:snow_holding": 15,
+    "refreeze:degree_day": 16,
 }
 PROC_PARAMS = {
     0: ["degree_day_factor", "melting_temperature"],
@@ -53,6 +55,8 @@ PROC_PARAMS = {
     12: ["sublimation_pet_factor"],
     13: ["melt_factor", "melting_temperature", "radiation_coefficient"],
     14: ["coeff", "exp", "min_slope", "max_slope", "min_snow_holding_depth", "max_snow_depth"],
+    15: ["water_holding_capacity"],
+    16: ["refreezing_factor"],
 }
 ASPECT_DDF = {"north": "degree_day_factor_n", "N": "degree_day_factor_n", "south": "degree_day_factor_s",
               "S": "degree_day_factor_s", "east": "degree_day_factor_ew", "west": "degree_day_factor_ew",

@@ -21,7 +21,7 @@ OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
 
 
 def save(name, meta, forcing, outlet, records, extra=None):
-    OUT.mkdir(parents=True, exist_ok=True)
+    (OUT / name).parent.mkdir(parents=True, exist_ok=True)
     arrays = {"meta": np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8), "outlet": np.asarray(outlet)}
     for k, v in forcing.items():
         arrays["forcing_" + k] = np.asarray(v, dtype=np.float64)
@@ -246,6 +246,24 @@ def rain_only_bundles(ref):
         save(f"splitter_rain_{solver}_nosnow_{name}", meta, forcing, q, rec)
 
 
+def snow_retention_bundles(ref):
+    """Snowpack liquid-water retention (outflow:snow_holding), refreezing (refreeze:degree_day) and the rain routed through
+    the snowpack (tools/ref_retention_case.py)."""
+    import ref_retention_case as rr
+
+    for solver, kw, name in (("rk4", dict(glacier=True, nsoil=2), "refreeze_glacier_2store"),
+                             ("rk4", dict(glacier=False, nsoil=1, refreeze=False), "holding_1store"),
+                             ("heun_explicit", dict(glacier=True, nsoil=1, rain_to_snowpack=True), "rain_glacier_1store"),
+                             ("euler_explicit", dict(glacier=False, nsoil=2, rain_to_snowpack=True), "rain_2store"),
+                             ("crank_nicolson", dict(glacier=True, nsoil=1), "refreeze_glacier_1store"),
+                             ("rk4", dict(glacier=True, nsoil=1, rain_to_snowpack=True,
+                                          extras=dict(snow_ice_transformation="transform:snow_ice_constant",
+                                                      snow_sublimation_process="sublimation:pet")), "rain_snowice_sublim_1store")):
+        meta, forcing, q, rec = rr.run_reference(ref, solver, **kw)
+        # tests/golden/next: pinned in the oracle, not in the CUDA engine yet (outside the engine's parity lists)
+        save(f"next/snow_retention_{solver}_{name}", meta, forcing, q, rec)
+
+
 def two_glaciers_bundles(ref):
     """glacier_ice + glacier_debris in one unit (the engine's twin units, hbk_set_unit_twins)."""
     import ref_two_glaciers_case as rt
@@ -307,6 +325,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "rain_only":
         rain_only_bundles(ref)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "snow_retention":
+        snow_retention_bundles(ref)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "snow_slide":
         snow_slide_bundles(ref)
@@ -372,6 +393,7 @@ def main():
     snow_slide_bundles(ref)
     threshold_splitter_bundles(ref)
     rain_only_bundles(ref)
+    snow_retention_bundles(ref)
     two_glaciers_bundles(ref)
     two_glaciers_action_bundles(ref)
     slow_order_bundles(ref)
