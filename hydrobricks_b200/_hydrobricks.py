@@ -53,6 +53,9 @@ _PROCESS_REGISTRY = {
     # ProcessSublimation{Constant,PET}::RegisterProcessSettings
     "sublimation:constant": ([("sublimation_rate", 0.1)], []),
     "sublimation:pet": ([("sublimation_pet_factor", 0.2)], ["pet"]),
+    # ProcessOutflowSnowHolding.cpp:15-17, ProcessRefreezeDegreeDay.cpp:14-17
+    "outflow:snow_holding": ([("water_holding_capacity", 0.1)], []),
+    "refreeze:degree_day": ([("refreezing_factor", 0.05)], ["temperature"]),
 }
 
 _log_level = "message"
@@ -439,14 +442,41 @@ class SettingsModel:
     def _unsupported(self, what):
         raise RuntimeError(f"{what} is not available in the B200 engine (SURVEY.md §8f lists it as next).")
 
-    def generate_snowpacks_with_water_retention(self, *a, **k):
-        self._unsupported("snowpack water retention")
+    def generate_snowpacks_with_water_retention(self, snow_melt_process, outflow_process, rain_to_snowpack=False):
+        """SettingsModel::GenerateSnowpacksWithWaterRetention (SettingsModel.cpp:608-634): the melt goes to the snowpack's
+        own water container (instantaneous), `outflow_process` (outflow:snow_holding) releases it to the land cover, and
+        with rain_to_snowpack the rain splitter feeds the snowpack instead of the cover."""
+        covers = [b["name"] for b in self._sel_structure["hydro_unit_bricks"] if b["is_land_cover"]]
+        for cover in covers:
+            if not self._select_splitter_if_found("snow_splitter"):
+                raise RuntimeError("The hydro unit splitter 'snow_splitter' was not found")
+            self._add_splitter_output(cover + "_snowpack", "snow")
+            self._add_surface_component_brick(cover + "_snowpack", "snowpack")
+            self._sel_brick["parent"] = cover
+            self.add_brick_process("melt", snow_melt_process)
+            self._sel_process["outputs"].append({"target": cover + "_snowpack", "flux_type": "water",
+                                                 "instantaneous": True, "static": False})  # OutputProcessToSameBrick
+            self.add_brick_process("meltwater", outflow_process)
+            self.add_process_output(cover)
+            if rain_to_snowpack:
+                if not self._select_splitter_if_found("rain_splitter"):
+                    raise RuntimeError("The hydro unit splitter 'rain_splitter' was not found")
+                for out in self._sel_splitter["outputs"]:  # ChangeSplitterOutputTargetIfFound
+                    if out["target"] == cover:
+                        out["target"] = cover + "_snowpack"
+                        break
 
     def generate_canopy_interception(self, *a, **k):
         self._unsupported("canopy interception")
 
-    def add_snowpack_refreezing(self, *a, **k):
-        self._unsupported("snowpack refreezing")
+    def add_snowpack_refreezing(self, refreezing_process="refreeze:degree_day"):
+        """SettingsModel::AddSnowpackRefreezing (SettingsModel.cpp:574-590): on every snowpack, from its water container back
+        to its snow container, instantaneous."""
+        covers = [b["name"] for b in self._sel_structure["hydro_unit_bricks"] if b["is_land_cover"]]
+        for name in covers:
+            self.select_hydro_unit_brick(name + "_snowpack")
+            self.add_brick_process("refreeze", refreezing_process, name + "_snowpack:snow")
+            self.set_process_outputs_as_instantaneous()
 
     def add_snowpack_sublimation(self, sublimation_process):
         """SettingsModel::AddSnowpackSublimation (SettingsModel.cpp:586-598): on every snowpack, from the snow

@@ -121,11 +121,12 @@ PYBIND11_MODULE(_hydrobricks, m) {
         .def("generate_precipitation_splitters", &hb::SettingsModel::GeneratePrecipitationSplitters, "with_snow"_a = true,
              "splitter_type"_a = "snow_rain:linear")
         .def("generate_snowpacks", &hb::SettingsModel::GenerateSnowpacks, "snow_melt_process"_a)
-        .def("generate_snowpacks_with_water_retention",
-             [](hb::SettingsModel& s, py::args, py::kwargs) { s.Unsupported("snowpack water retention"); })
+        .def("generate_snowpacks_with_water_retention", &hb::SettingsModel::GenerateSnowpacksWithWaterRetention,
+             "snow_melt_process"_a, "outflow_process"_a, "rain_to_snowpack"_a = false)
         .def("generate_canopy_interception",
              [](hb::SettingsModel& s, py::args, py::kwargs) { s.Unsupported("canopy interception"); })
-        .def("add_snowpack_refreezing", [](hb::SettingsModel& s, py::args, py::kwargs) { s.Unsupported("snowpack refreezing"); })
+        .def("add_snowpack_refreezing", &hb::SettingsModel::AddSnowpackRefreezing,
+             "refreezing_process"_a = "refreeze:degree_day")
         .def("add_snowpack_sublimation", &hb::SettingsModel::AddSnowpackSublimation, "sublimation_process"_a)
         .def("add_snow_ice_transformation", &hb::SettingsModel::AddSnowIceTransformation,
              "transformation_process"_a = "transform:snow_ice_swat")

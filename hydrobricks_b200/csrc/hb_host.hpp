@@ -115,6 +115,9 @@ inline const std::map<string, ProcessDefaults>& processRegistry() {
         // ProcessSublimation{Constant,PET}::RegisterProcessSettings
         {"sublimation:constant", {{{"sublimation_rate", 0.1f}}, {}}},
         {"sublimation:pet", {{{"sublimation_pet_factor", 0.2f}}, {"pet"}}},
+        // ProcessOutflowSnowHolding.cpp:15-17, ProcessRefreezeDegreeDay.cpp:14-17
+        {"outflow:snow_holding", {{{"water_holding_capacity", 0.1f}}, {}}},
+        {"refreeze:degree_day", {{{"refreezing_factor", 0.05f}}, {"temperature"}}},
     };
     return r;
 }
@@ -301,6 +304,51 @@ class SettingsModel {
             brick().isSurfaceComponent = true;
             brick().parent = cover;
             AddBrickProcess("melt", meltProcess, cover);
+        }
+    }
+    // SettingsModel::GenerateSnowpacksWithWaterRetention (SettingsModel.cpp:608-634): the melt goes to the snowpack's own
+    // water container (instantaneous), outflowProcess (outflow:snow_holding) releases it to the land cover; with
+    // rainToSnowpack the rain splitter feeds the snowpack instead of the cover
+    void GenerateSnowpacksWithWaterRetention(const string& meltProcess, const string& outflowProcess,
+                                             bool rainToSnowpack = false) {
+        vector<string> covers;
+        for (auto& b : sel().hydroUnitBricks)
+            if (b.isLandCover) covers.push_back(b.name);
+        for (auto& cover : covers) {
+            if (!selectSplitterIfFound("snow_splitter"))
+                throw std::runtime_error("The hydro unit splitter 'snow_splitter' was not found");
+            addSplitterOutput(cover + "_snowpack", "snow");
+            addBrick(false, cover + "_snowpack", "snowpack");
+            brick().isSurfaceComponent = true;
+            brick().parent = cover;
+            AddBrickProcess("melt", meltProcess);
+            Output same;  // OutputProcessToSameBrick (SettingsModel.cpp:295-303)
+            same.target = cover + "_snowpack";
+            same.instantaneous = true;
+            process().outputs.push_back(same);
+            AddBrickProcess("meltwater", outflowProcess);
+            AddProcessOutput(cover);
+            if (rainToSnowpack) {
+                if (!selectSplitterIfFound("rain_splitter"))
+                    throw std::runtime_error("The hydro unit splitter 'rain_splitter' was not found");
+                for (auto& o : splitter().outputs)  // ChangeSplitterOutputTargetIfFound (SettingsModel.cpp:401-412)
+                    if (o.target == cover) {
+                        o.target = cover + "_snowpack";
+                        break;
+                    }
+            }
+        }
+    }
+    // SettingsModel::AddSnowpackRefreezing (SettingsModel.cpp:574-590): from the snowpack's water container back to its
+    // snow container, instantaneous
+    void AddSnowpackRefreezing(const string& refreezingProcess = "refreeze:degree_day") {
+        vector<string> covers;
+        for (auto& b : sel().hydroUnitBricks)
+            if (b.isLandCover) covers.push_back(b.name);
+        for (auto& c : covers) {
+            SelectHydroUnitBrickByName(c + "_snowpack");
+            AddBrickProcess("refreeze", refreezingProcess, c + "_snowpack:snow");
+            SetProcessOutputsAsInstantaneous();
         }
     }
     // SettingsModel::AddSnowIceTransformation (SettingsModel.cpp:547-559)
@@ -590,7 +638,11 @@ inline const std::map<string, int>& recordSlots() {
         {"quick_runoff", HBK_R_QUICK_RUNOFF}, {"fraction_ground", HBK_R_FRACTION_GROUND},
         {"fraction_glacier", HBK_R_FRACTION_GLACIER}, {"glacier_snowpack_transfo", HBK_R_GLACIER_SNOWPACK_TRANSFO},
         {"ground_snowpack_sublimation", HBK_R_GROUND_SNOWPACK_SUBLIMATION},
-        {"glacier_snowpack_sublimation", HBK_R_GLACIER_SNOWPACK_SUBLIMATION}};
+        {"glacier_snowpack_sublimation", HBK_R_GLACIER_SNOWPACK_SUBLIMATION},
+        {"ground_snowpack_meltwater", HBK_R_GROUND_SNOWPACK_MELTWATER},
+        {"glacier_snowpack_meltwater", HBK_R_GLACIER_SNOWPACK_MELTWATER},
+        {"ground_snowpack_refreeze", HBK_R_GROUND_SNOWPACK_REFREEZE},
+        {"glacier_snowpack_refreeze", HBK_R_GLACIER_SNOWPACK_REFREEZE}};
     return m;
 }
 
@@ -626,6 +678,7 @@ struct Compiled {
         throw std::invalid_argument("Invalid aspect: " + a);
     }
     bool noSnow = false;
+    bool rainToSnowpack = false;  // the rain splitter feeds the snowpacks (GenerateSnowpacksWithWaterRetention)
     // The melt process of a snowpack or of the glacier ice: its kind (one per structure) and its parameters.
     void setMelt(const string& component, const Process& proc, int slotA, int slotTm, int slotB, int slotC) {
         const int kind = meltKindOf(proc.kind);
@@ -822,7 +875,12 @@ struct Compiled {
             if (glacier2) want.push_back(glacier2->name);
             std::sort(want.begin(), want.end());
             std::sort(rainTargets.begin(), rainTargets.end());
-            if (want != rainTargets) throw Unsupported("rain must go to every land cover");
+            // ... or, with rain_to_snowpack, to the snowpack of every land cover (SettingsModel.cpp:624-632)
+            vector<string> wantSnowpacks;
+            for (auto& w : want) wantSnowpacks.push_back(w + "_snowpack");
+            std::sort(wantSnowpacks.begin(), wantSnowpacks.end());
+            rainToSnowpack = rainTargets == wantSnowpacks;
+            if (!rainToSnowpack && want != rainTargets) throw Unsupported("rain must go to every land cover");
         }
         if (kinds(*ground) != vector<string>{"infiltration:socont", "outflow:rest"})
             throw Unsupported("land cover " + ground->name + ": expected infiltration:socont + outflow:rest");
@@ -839,6 +897,8 @@ struct Compiled {
             const Process* transfo;
             const Process* sublim;
             const Process* slide = nullptr;
+            const Process* holding = nullptr;   // outflow:snow_holding (liquid water kept in the snowpack)
+            const Process* refreeze = nullptr;  // refreeze:degree_day
         };
         auto snowpackOf = [&](const Brick& cover) -> SnowpackInfo {
             const Brick* sp = nullptr;
@@ -849,11 +909,31 @@ struct Compiled {
                 }
             }
             SnowpackInfo info{sp, nullptr, nullptr};
-            bool ok = sp && !sp->processes.empty() && meltKindOf(sp->processes[0].kind) >= 0 &&
-                      target(sp->processes[0]) == cover.name;
+            bool ok = sp && !sp->processes.empty() && meltKindOf(sp->processes[0].kind) >= 0;
             if (ok) {
                 size_t i = 1;
-                if (i < sp->processes.size() && cover.kind == "glacier" && snowIceKindOf(sp->processes[i].kind)) {
+                if (target(sp->processes[0]) == sp->name) {
+                    // SettingsModel::GenerateSnowpacksWithWaterRetention (SettingsModel.cpp:608-634): the melt stays in the
+                    // snowpack (instantaneous flux to its own water container), outflow:snow_holding feeds the cover
+                    const auto& mo = sp->processes[0].outputs;
+                    ok = mo.size() == 1 && mo[0].instantaneous && mo[0].fluxType == "water" && i < sp->processes.size() &&
+                         sp->processes[i].kind == "outflow:snow_holding";
+                    if (ok) {
+                        info.holding = &sp->processes[i++];
+                        const auto& out = info.holding->outputs;
+                        ok = out.size() == 1 && out[0].target == cover.name && out[0].fluxType == "water" &&
+                             !out[0].instantaneous && !out[0].isStatic;
+                    }
+                    if (ok && i < sp->processes.size() && sp->processes[i].kind == "refreeze:degree_day") {
+                        // SettingsModel::AddSnowpackRefreezing (SettingsModel.cpp:574-590)
+                        info.refreeze = &sp->processes[i++];
+                        const auto& out = info.refreeze->outputs;
+                        ok = out.size() == 1 && out[0].target == sp->name && out[0].fluxType == "snow" && out[0].instantaneous;
+                    }
+                } else {
+                    ok = target(sp->processes[0]) == cover.name;
+                }
+                if (ok && i < sp->processes.size() && cover.kind == "glacier" && snowIceKindOf(sp->processes[i].kind)) {
                     // SettingsModel::AddSnowIceTransformation: snow -> the glacier's ice container, a regular flux
                     info.transfo = &sp->processes[i++];
                     const auto& out = info.transfo->outputs;
@@ -874,8 +954,23 @@ struct Compiled {
             }
             if (!ok)
                 throw Unsupported("cover " + cover.name + ": expected one snowpack with melt:degree_day"
-                                  "|degree_day_aspect|temperature_index [+ transform:snow_ice_constant|swat on a glacier] [+ sublimation:constant|pet]");
+                                  "|degree_day_aspect|temperature_index [+ outflow:snow_holding [+ refreeze:degree_day]] "
+                                  "[+ transform:snow_ice_constant|swat on a glacier] [+ sublimation:constant|pet]");
             return info;
+        };
+        // water_holding_capacity / refreezing_factor of a snowpack with liquid-water retention and its labels
+        int nHolding = 0, nRefreeze = 0;
+        auto setRetention = [&](const SnowpackInfo& info, int whcSlot, int cfrSlot, const string& prefix) {
+            if (!info.holding) return;
+            const Brick& sp = *info.brick;
+            nHolding++;
+            set(whcSlot, sp.name, "water_holding_capacity", paramOf(info.holding->parameters, "water_holding_capacity"));
+            label(sp.name + ":" + info.holding->name + ":output", prefix + "_meltwater");
+            if (info.refreeze) {
+                nRefreeze++;
+                set(cfrSlot, sp.name, "refreezing_factor", paramOf(info.refreeze->parameters, "refreezing_factor"));
+                label(sp.name + ":" + info.refreeze->name + ":output", prefix + "_refreeze");
+            }
         };
         auto setSublimation = [&](const Brick& sp, const Process& proc, int slot, const char* record) {
             const int kind = sublimationKindOf(proc.kind);
@@ -902,6 +997,7 @@ struct Compiled {
             snowpacks.push_back(gsp.name);
             known.insert(gsp.name);
             if (gInfo.slide) slideOn.push_back({gsp.name, gInfo.slide});
+            setRetention(gInfo, HBK_P_GROUND_SNOW_WHC, HBK_P_GROUND_SNOW_CFR, "ground_snowpack");
         }
 
         string b1, b2;
@@ -970,6 +1066,7 @@ struct Compiled {
             snowpacks.push_back(glsp.name);
             known.insert(glsp.name);
             if (glInfo.slide) slideOn.push_back({glsp.name, glInfo.slide});
+            setRetention(glInfo, HBK_P_GLACIER_SNOW_WHC, HBK_P_GLACIER_SNOW_CFR, "glacier_snowpack");
             const int kind = glInfo.transfo ? snowIceKindOf(glInfo.transfo->kind) : HBK_SNOW_ICE_NONE;
             if (second && kind != st.snow_ice_kind)
                 throw Unsupported("the snow -> ice transformation must be the same on every glacier snowpack");
@@ -1009,6 +1106,21 @@ struct Compiled {
             std::sort(a.begin(), a.end());
             std::sort(b.begin(), b.end());
             if (a != b) throw Unsupported("snow must go to the snowpack of every land cover");
+        }
+        // liquid water in the snowpacks: the same processes on every snowpack (model_settings.py:248-255)
+        st.snow_retention = 0;
+        if (nHolding > 0) {
+            if (nHolding != (int)snowpacks.size() || (nRefreeze != 0 && nRefreeze != nHolding))
+                throw Unsupported("outflow:snow_holding / refreeze:degree_day must be on every snowpack or on none");
+            st.snow_retention = HBK_RETENTION_HOLDING | (nRefreeze ? HBK_RETENTION_REFREEZE : 0) |
+                                (rainToSnowpack ? HBK_RETENTION_RAIN_TO_SNOWPACK : 0);
+            if (nRefreeze && st.melt_kind != HBK_MELT_DEGREE_DAY)  // ProcessRefreezeDegreeDay::IsValid (:19-37)
+                throw Unsupported("The refreeze:degree_day process requires a melt:degree_day process on the same brick.");
+            if (glacier2 || !slideOn.empty())
+                throw Unsupported("liquid water in the snowpacks runs neither with a second glacier cover nor with "
+                                  "transport:snow_slide");
+        } else if (rainToSnowpack) {
+            throw Unsupported("rain routed to the snowpacks needs a snow water retention process");
         }
         st.snow_slide_kind = HBK_SNOW_SLIDE_NONE;
         if (!slideOn.empty()) {

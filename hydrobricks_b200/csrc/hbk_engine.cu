@@ -227,10 +227,30 @@ __device__ __forceinline__ void fillPar(double* pv, int ps, const float* pp, int
     pv[16 * ps] = pp[HBK_P_SNOW_ICE * ldp];
 }
 
+// HBK_RETENTION_*: where the extra state of one (set, unit) lives and its four parameters (read at use, like the options above)
+__device__ __noinline__ RetentionCtx retentionCtx(double* state, long long lds, long long si, const float* params, int ldp,
+                                                  int p, int bits) {
+    RetentionCtx c;
+    const float* pp = params + p;
+    c.g.water = state + HBK_S_GROUND_SNOWPACK_WATER * lds + si;
+    c.g.refreeze = state + HBK_S_AMT_REFREEZE_GROUND * lds + si;
+    c.g.snowmelt = state + HBK_S_AMT_SNOWMELT_GROUND * lds + si;
+    c.g.whc = pp[(size_t)HBK_P_GROUND_SNOW_WHC * ldp];
+    c.g.cfr = pp[(size_t)HBK_P_GROUND_SNOW_CFR * ldp];
+    c.gl.water = state + HBK_S_GLACIER_SNOWPACK_WATER * lds + si;
+    c.gl.refreeze = state + HBK_S_AMT_REFREEZE_GLACIER * lds + si;
+    c.gl.snowmelt = state + HBK_S_AMT_SNOWMELT_GLACIER * lds + si;
+    c.gl.whc = pp[(size_t)HBK_P_GLACIER_SNOW_WHC * ldp];
+    c.gl.cfr = pp[(size_t)HBK_P_GLACIER_SNOW_CFR * ldp];
+    c.refreeze = (bits & HBK_RETENTION_REFREEZE) != 0;
+    c.rainToSnowpack = (bits & HBK_RETENTION_RAIN_TO_SNOWPACK) != 0;
+    return c;
+}
+
 // Logger::Record (Logger.cpp:93-120) of one (set, unit, step): contents after Finalize and flux amounts, into the slots
 // of the record mask [slot][P][T][U]; NaN where the unit's structure variant has no such brick.
 __device__ __forceinline__ void recordStep(const KArgs& a, int pOut, int t, int u, const Hru& h, const StepOut& o, double fG,
-                                           double fGl, bool gv) {
+                                           double fGl, bool gv, const RetentionCtx* ret = nullptr) {
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     double* base = a.rec + ((size_t)pOut * a.T + t) * a.U + u;
     const size_t stride = (size_t)a.P * a.T * a.U;
@@ -247,12 +267,14 @@ __device__ __forceinline__ void recordStep(const KArgs& a, int pOut, int t, int 
     HBK_REC(HBK_R_GLACIER_ICE, gv ? h.ice : nan)
     HBK_REC(HBK_R_GLACIER_OUTFLOW, gv ? h.amtDep1 : nan)
     HBK_REC(HBK_R_GLACIER_MELT, gv ? h.amtDep2 : nan)
-    HBK_REC(HBK_R_GROUND_SNOWPACK_WATER, 0.0)
+    // with liquid water in the snowpacks h.amtMelt* are the melt WATER released to the covers; content, melt and refreeze
+    // amounts are in the state arrays (RetentionCtx)
+    HBK_REC(HBK_R_GROUND_SNOWPACK_WATER, ret ? *ret->g.water : 0.0)
     HBK_REC(HBK_R_GROUND_SNOWPACK_SNOW, h.snowG)
-    HBK_REC(HBK_R_GROUND_SNOWPACK_MELT, h.amtMeltG)
-    HBK_REC(HBK_R_GLACIER_SNOWPACK_WATER, gv ? 0.0 : nan)
+    HBK_REC(HBK_R_GROUND_SNOWPACK_MELT, ret ? *ret->g.snowmelt : h.amtMeltG)
+    HBK_REC(HBK_R_GLACIER_SNOWPACK_WATER, gv ? (ret ? *ret->gl.water : 0.0) : nan)
     HBK_REC(HBK_R_GLACIER_SNOWPACK_SNOW, gv ? h.snowGl : nan)
-    HBK_REC(HBK_R_GLACIER_SNOWPACK_MELT, gv ? h.amtMeltGl : nan)
+    HBK_REC(HBK_R_GLACIER_SNOWPACK_MELT, gv ? (ret ? *ret->gl.snowmelt : h.amtMeltGl) : nan)
     HBK_REC(HBK_R_SLOW_WATER, h.slow)
     HBK_REC(HBK_R_SLOW_ET, o.amtEt)
     HBK_REC(HBK_R_SLOW_OUTFLOW, o.amtOut)
@@ -267,6 +289,10 @@ __device__ __forceinline__ void recordStep(const KArgs& a, int pOut, int t, int 
     HBK_REC(HBK_R_GLACIER_SNOWPACK_TRANSFO, gv ? h.amtSnowIce : nan)
     HBK_REC(HBK_R_GROUND_SNOWPACK_SUBLIMATION, o.amtSubG)
     HBK_REC(HBK_R_GLACIER_SNOWPACK_SUBLIMATION, gv ? o.amtSubGl : nan)
+    HBK_REC(HBK_R_GROUND_SNOWPACK_MELTWATER, h.amtMeltG)
+    HBK_REC(HBK_R_GLACIER_SNOWPACK_MELTWATER, gv ? h.amtMeltGl : nan)
+    HBK_REC(HBK_R_GROUND_SNOWPACK_REFREEZE, ret ? *ret->g.refreeze : 0.0)
+    HBK_REC(HBK_R_GLACIER_SNOWPACK_REFREEZE, gv ? (ret ? *ret->gl.refreeze : 0.0) : nan)
 #undef HBK_REC
 }
 
@@ -607,15 +633,23 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, hbkMinBlocks(NSOIL, GLACIER))
                         sublimG = su.x;
                         sublimGl = su.y;
                     }
+                    RetentionCtx rc;
+                    const RetentionCtx* ret = nullptr;
+                    if (!ENS && a.flags.retention) {  // liquid water kept in the snowpacks: generic-shape kernels only
+                        rc = retentionCtx(a.state, a.lds, (long long)p * a.sP + (long long)u * a.sU, a.params, a.ldp, p,
+                                          a.flags.retention);
+                        ret = &rc;
+                    }
                     directPhase<GLACIER>(h, par, precip, temp, dt, invDt, fa, fG, fGl, glacierVariant, a.flags, o, err,
-                                         (GLACIER && a.swatFactor) ? a.swatFactor[t0 + tc] : 0.0, sublimG, sublimGl);
+                                         (GLACIER && a.swatFactor) ? a.swatFactor[t0 + tc] : 0.0, sublimG, sublimGl, 0.0, 0.0,
+                                         NoSlide(), NoSlide(), ret);
                     if constexpr (SOLVER == 3) {
                         solveUnitSequential<NSOIL>(h, par, pet, faW, dt, invDt, a.flags, o, err);
                     } else {
                         solveUnit<SOLVER, NSOIL>(h, par, pet, faW, dt, invDt, a.flags, o, err, unconverged);
                     }
 
-                    if (nRec && a.writeOutputs) recordStep(a, pOut, t0 + tc, u, h, o, fG, fGl, glacierVariant);
+                    if (nRec && a.writeOutputs) recordStep(a, pOut, t0 + tc, u, h, o, fG, fGl, glacierVariant, ret);
                 }
                 // this thread's slot accumulates its units of the group's tiles in tile order (no race: own slot)
                 double* slot = slotCol + (size_t)tc * nThreads;
@@ -1466,6 +1500,8 @@ struct hbk_engine {
     double* dStation[HBK_N_VARS] = {};       // [tld]
     bool haveRaw[HBK_N_VARS] = {}, haveStation[HBK_N_VARS] = {};
     int nVars() const { return st.melt_kind == HBK_MELT_TEMPERATURE_INDEX ? 4 : 3; }
+    // state slots in use: the six of the snowpacks' liquid water only with HBK_RETENTION_*
+    int nStates() const { return st.snow_retention ? HBK_N_STATES : HBK_S_AMT_REFREEZE_GROUND; }
     std::vector<int> hAspect;  // HBK_ASPECT_* per unit (hbk_set_unit_aspect); empty = not given
     std::vector<int> hTwinOf;  // unit a twin (second glacier cover) belongs to, -1 = ordinary unit; empty = no twins
     int* dTwinOf = nullptr;    // [U] device copies for the action kernels (nullptr without twins)
@@ -1879,7 +1915,7 @@ int ensureSetBuffers(hbk_engine* e, int P) {
     e->ldp = (P + 31) / 32 * 32;
     e->ldt = (e->T + 15) / 16 * 16;
     HBK_CUDA(cudaMalloc(&e->dParams, sizeof(float) * HBK_N_PARAMS * e->ldp));
-    HBK_CUDA(cudaMalloc(&e->dState, sizeof(double) * HBK_N_STATES * (size_t)P * e->U));
+    HBK_CUDA(cudaMalloc(&e->dState, sizeof(double) * e->nStates() * (size_t)P * e->U));
     HBK_CUDA(cudaMalloc(&e->dBasinState, sizeof(double) * 2 * P));
     HBK_CUDA(cudaMalloc(&e->dBasinInit, sizeof(double) * 2 * P));
     HBK_CUDA(cudaMemsetAsync(e->dBasinInit, 0, sizeof(double) * 2 * P, e->stream));
@@ -2311,6 +2347,7 @@ int hbk_set_station_forcing(hbk_engine* e, int32_t var, const double* series, do
 
 int hbk_set_initial_state(hbk_engine* e, int32_t slot, const double* values) {
     if (!e || slot < 0 || slot >= HBK_N_STATES) return HBK_E_ARG;
+    if (slot >= e->nStates()) return fail(e, HBK_E_ARG, "this state slot exists only with liquid water in the snowpacks");
     HBK_CUDA(cudaSetDevice(e->device));
     if (values) {
         HBK_CUDA(cudaMemcpyAsync(e->dInitUnit + (size_t)slot * e->U, values, sizeof(double) * e->U, cudaMemcpyHostToDevice,
@@ -2331,7 +2368,7 @@ int hbk_set_initial_state(hbk_engine* e, int32_t slot, const double* values) {
 int hbk_save_as_initial_state(hbk_engine* e) {
     if (!e || !e->ran) return fail(e, HBK_E_STATE, "save_as_initial_state needs a completed run");
     HBK_CUDA(cudaSetDevice(e->device));
-    const size_t n = sizeof(double) * HBK_N_STATES * (size_t)e->P * e->U;
+    const size_t n = sizeof(double) * e->nStates() * (size_t)e->P * e->U;
     if (!e->dInitFull) HBK_CUDA(cudaMalloc(&e->dInitFull, n));
     // on the engine's stream (created non-blocking: the legacy default stream is NOT ordered against it), then drained,
     // so that the next hbk_run's restore copy can never overlap this save
@@ -2598,7 +2635,7 @@ static int launchUnitKernel(hbk_engine* e, KArgs& a, bool tiled, int tBegin, int
     a.tile1 = run.tile1;
     a.grpBase = run.grpBase;
     const bool fixedShape = run.TC == hbk::hbkEnsTC(run.glacier) && !tiled && !e->clusterMode && a.nVars == 3 &&
-                            !std::getenv("HBK_NO_ENS_SHAPE");
+                            !e->st.snow_retention && !std::getenv("HBK_NO_ENS_SHAPE");
     const int shape = !fixedShape ? 0 : ((e->PB == 32 && e->UB == 4) ? 1 : ((e->PB == 1 && e->UB == 128) ? 2 : 0));
     KernelFn fn = pickKernel(e->st, run.glacier, shape);
     const size_t smem = smemBytes(e, tiled, run.glacier, run.TC);
@@ -2732,6 +2769,7 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
     a.flags.seqKind = e->st.solver >= HBK_SOLVER_CRANK_NICOLSON ? e->st.solver - HBK_SOLVER_CRANK_NICOLSON : 0;
     a.flags.meltKind = e->st.melt_kind;
     a.flags.hasTwins = e->hasTwins ? 1 : 0;
+    a.flags.retention = e->st.snow_retention;
     a.nVars = e->nVars();
     a.swatFactor = (a.flags.snowIceKind == HBK_SNOW_ICE_SWAT) ? e->dSwatFactor : nullptr;
     a.flags.noMeltWhenSnow = e->st.glacier_no_melt_when_snow_cover;
@@ -2911,6 +2949,10 @@ int hbk_run(hbk_engine* e) {
                                             "(hbk_set_delta_h_shard_totals)");
     }
     e->shardSegments.clear();
+    if (e->st.snow_retention && (e->hasTwins || e->st.snow_slide_kind != HBK_SNOW_SLIDE_NONE || !e->events.empty()))
+        return fail(e, HBK_E_UNSUPPORTED, "liquid water in the snowpacks (outflow:snow_holding / refreeze:degree_day) runs "
+                                          "neither with a second glacier cover, nor with lateral connections, nor with "
+                                          "dated actions");
     if (e->hasTwins && (e->st.snow_slide_kind != HBK_SNOW_SLIDE_NONE || e->shard))
         return fail(e, HBK_E_UNSUPPORTED, "units with a second glacier cover (hbk_set_unit_twins) run neither lateral "
                                           "connections nor unit shards");
@@ -2985,18 +3027,20 @@ int hbk_run(hbk_engine* e) {
     // ModelHydro::Reset (ModelHydro.cpp:183-193): containers back to their initial state, fluxes to 0.
     const size_t nPU = (size_t)e->P * e->U;
     if (e->initPerSet) {
-        HBK_CUDA(cudaMemcpyAsync(e->dState, e->dInitFull, sizeof(double) * HBK_N_STATES * nPU, cudaMemcpyDeviceToDevice,
+        HBK_CUDA(cudaMemcpyAsync(e->dState, e->dInitFull, sizeof(double) * e->nStates() * nPU, cudaMemcpyDeviceToDevice,
                                  e->stream));
+        // flux amounts back to 0 (the slots between the storages and the two snowpack water storages at the end)
         HBK_CUDA(cudaMemsetAsync(e->dState + (size_t)HBK_S_AMT_INFILTRATION * nPU, 0,
-                                 sizeof(double) * (HBK_N_STATES - HBK_S_AMT_INFILTRATION) * nPU, e->stream));
+                                 sizeof(double) * (std::min<int>(e->nStates(), HBK_S_GROUND_SNOWPACK_WATER) - HBK_S_AMT_INFILTRATION) * nPU,
+                                 e->stream));
     } else {
-        for (int s = 0; s < HBK_N_STATES; ++s) {
-            const bool storage = s < HBK_S_AMT_INFILTRATION;
+        for (int s = 0; s < e->nStates(); ++s) {
+            const bool storage = s < HBK_S_AMT_INFILTRATION || s >= HBK_S_GROUND_SNOWPACK_WATER;
             hbkBroadcastState<<<148 * 2, 256, 0, e->stream>>>(e->dState + (size_t)s * nPU,
                                                               storage ? e->dInitUnit + (size_t)s * e->U : nullptr, 0.0,
                                                               e->P, e->U, e->stateLaneP ? 1 : 0);
         }
-        e->lastLaunches += HBK_N_STATES;
+        e->lastLaunches += e->nStates();
     }
     HBK_CUDA(cudaMemcpyAsync(e->dBasinState, e->dBasinInit, sizeof(double) * 2 * e->P, cudaMemcpyDeviceToDevice, e->stream));
     HBK_CUDA(cudaMemcpyAsync(e->dFrac, e->dFracInit, sizeof(double) * 2 * e->U, cudaMemcpyDeviceToDevice, e->stream));
@@ -3197,6 +3241,7 @@ int hbk_get_recorded(hbk_engine* e, int32_t slot, int32_t set, double* out) {
 
 int hbk_get_state(hbk_engine* e, int32_t slot, double* out) {
     if (!e || !out || slot < 0 || slot >= HBK_N_STATES) return HBK_E_ARG;
+    if (slot >= e->nStates()) return fail(e, HBK_E_ARG, "this state slot exists only with liquid water in the snowpacks");
     if (!e->ran) return fail(e, HBK_E_STATE, "no completed run");
     HBK_CUDA(cudaSetDevice(e->device));
     const size_t n = (size_t)e->P * e->U;

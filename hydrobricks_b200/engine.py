@@ -25,6 +25,7 @@ SPLIT_LINEAR, SPLIT_THRESHOLD = 0, 1
 SNOW_ICE_NONE, SNOW_ICE_CONSTANT, SNOW_ICE_SWAT = 0, 1, 2
 SUBLIMATION_NONE, SUBLIMATION_CONSTANT, SUBLIMATION_PET = 0, 1, 2
 SNOW_SLIDE_NONE, SNOW_SLIDE_SKIP_GLACIERS, SNOW_SLIDE_ALL = 0, 1, 2
+RETENTION_HOLDING, RETENTION_REFREEZE, RETENTION_RAIN_TO_SNOWPACK = 1, 2, 4
 MELT_DEGREE_DAY, MELT_DEGREE_DAY_ASPECT, MELT_TEMPERATURE_INDEX = 0, 1, 2
 MELT_KIND = {"melt:degree_day": 0, "melt:degree_day_aspect": 1, "melt:temperature_index": 2}
 # HydroUnit property "aspect_class" (ProcessMeltDegreeDayAspect.cpp:38-58) -> HBK_ASPECT_*
@@ -40,6 +41,7 @@ PARAM_SLOTS = [
     "slide_coeff", "slide_exp", "slide_min_slope", "slide_max_slope", "slide_min_holding_depth", "slide_max_snow_depth",
     "glacier2_snow_ddf", "glacier2_snow_tmelt", "ice2_ddf", "ice2_tmelt", "snow_ice2", "glacier2_sublimation",
     "glacier2_snow_melt_b", "glacier2_snow_melt_c", "ice2_melt_b", "ice2_melt_c",
+    "ground_snow_whc", "glacier_snow_whc", "ground_snow_cfr", "glacier_snow_cfr",
 ]
 N_PARAMS = len(PARAM_SLOTS)
 RECORD_SLOTS = [
@@ -49,11 +51,14 @@ RECORD_SLOTS = [
     "slow_outflow", "slow_overflow", "slow_percolation", "slow2_water", "slow2_outflow", "quick_water",
     "quick_runoff", "fraction_ground", "fraction_glacier", "glacier_snowpack_transfo",
     "ground_snowpack_sublimation", "glacier_snowpack_sublimation",
+    "ground_snowpack_meltwater", "glacier_snowpack_meltwater", "ground_snowpack_refreeze", "glacier_snowpack_refreeze",
 ]
 STATE_SLOTS = [
     "ground_snow", "glacier_snow", "ground_water", "glacier_water", "ice", "slow", "slow2", "quick",
     "amt_infiltration", "amt_rest", "amt_melt_ground", "amt_melt_glacier", "amt_deposit_rain_snowmelt",
     "amt_deposit_icemelt", "amt_snow_ice",
+    "amt_refreeze_ground", "amt_refreeze_glacier", "amt_snowmelt_ground", "amt_snowmelt_glacier",
+    "ground_snowpack_water", "glacier_snowpack_water",
 ]
 
 
@@ -74,7 +79,7 @@ class HbkStructure(ctypes.Structure):
         ("sublimation_kind", ctypes.c_int32),
         ("melt_kind", ctypes.c_int32),
         ("snow_slide_kind", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("snow_retention", ctypes.c_int32),
     ]
 
 

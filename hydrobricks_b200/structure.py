@@ -161,7 +161,10 @@ class CompiledStructure:
         self.glacier_name = glacier["name"] if glacier else None
         self.glacier2_name = glacier2["name"] if glacier2 else None
         self.twin_labels = set()  # log labels of the second glacier cover: recorded in the twin units' columns
-        if sorted(rain_targets or []) != sorted(c["name"] for c in covers):
+        # rain goes to every land cover — or, with rain_to_snowpack, to the snowpack of every land cover (checked once
+        # the snowpacks are known, SettingsModel.cpp:624-632)
+        rain_to_snowpack = sorted(rain_targets or []) == sorted(c["name"] + "_snowpack" for c in covers)
+        if not rain_to_snowpack and sorted(rain_targets or []) != sorted(c["name"] for c in covers):
             raise UnsupportedStructure("rain must go to every land cover")
         if _proc_kinds(ground) != ["infiltration:socont", "outflow:rest"]:
             raise UnsupportedStructure(f"land cover {ground['name']}: expected infiltration:socont + outflow:rest")
@@ -209,16 +212,40 @@ class CompiledStructure:
                 self._set(slot_a, component, "melt_factor", pp["melt_factor"])
                 self._set(slot_b, component, "radiation_coefficient", pp["radiation_coefficient"])
 
+        retention = {}  # snowpack name -> (outflow:snow_holding process, refreeze:degree_day process or None)
+
         def snowpack_of(cover):
-            """One snowpack per cover: melt:degree_day [, snow -> ice transformation on a glacier] [, sublimation], in
-            the order model_settings.py:255-263 adds them. Returns (brick, transformation process, sublimation process)."""
+            """One snowpack per cover: melt:degree_day [, outflow:snow_holding [, refreeze:degree_day]] [, snow -> ice
+            transformation on a glacier] [, snow slide] [, sublimation], in the order model_settings.py:248-263 adds them.
+            Returns (brick, transformation process, sublimation process)."""
             sps = [b for b in full["hydro_unit_bricks"] if b["kind"] == "snowpack" and b.get("parent") == cover["name"]]
-            ok = len(sps) == 1 and sps[0]["processes"] and sps[0]["processes"][0]["kind"] in _e.MELT_KIND and \
-                _target(sps[0]["processes"][0]) == cover["name"]
+            ok = len(sps) == 1 and sps[0]["processes"] and sps[0]["processes"][0]["kind"] in _e.MELT_KIND
             transfo = sublim = None
             if ok:
+                sp_name = sps[0]["name"]
+                melt_out = sps[0]["processes"][0]["outputs"]
                 rest = list(sps[0]["processes"][1:])
-                if rest and rest[0]["kind"] in transfo_kinds and cover["kind"] == "glacier":
+                if _target(sps[0]["processes"][0]) == sp_name:
+                    # SettingsModel::GenerateSnowpacksWithWaterRetention (SettingsModel.cpp:608-634): the melt stays in the
+                    # snowpack (instantaneous flux to its own water container), outflow:snow_holding feeds the cover
+                    ok = len(melt_out) == 1 and melt_out[0]["instantaneous"] and melt_out[0]["flux_type"] == "water" and \
+                        bool(rest) and rest[0]["kind"] == "outflow:snow_holding"
+                    if ok:
+                        holding = rest.pop(0)
+                        out = holding["outputs"]
+                        ok = len(out) == 1 and out[0]["target"] == cover["name"] and out[0]["flux_type"] == "water" and \
+                            not out[0]["instantaneous"] and not out[0]["static"]
+                        refreeze = None
+                        if ok and rest and rest[0]["kind"] == "refreeze:degree_day":
+                            # SettingsModel::AddSnowpackRefreezing (SettingsModel.cpp:574-590)
+                            refreeze = rest.pop(0)
+                            out = refreeze["outputs"]
+                            ok = len(out) == 1 and out[0]["target"] == sp_name and out[0]["flux_type"] == "snow" and \
+                                out[0]["instantaneous"]
+                        retention[sp_name] = (holding, refreeze)
+                else:
+                    ok = _target(sps[0]["processes"][0]) == cover["name"]
+                if ok and rest and rest[0]["kind"] in transfo_kinds and cover["kind"] == "glacier":
                     # SettingsModel::AddSnowIceTransformation (SettingsModel.cpp:547-559): snow -> the glacier's ice
                     transfo = rest.pop(0)
                     out = transfo["outputs"]
@@ -239,8 +266,21 @@ class CompiledStructure:
                 ok = ok and not rest
             if not ok:
                 raise UnsupportedStructure(f"cover {cover['name']}: expected one snowpack with melt:degree_day"
-                                           "|degree_day_aspect|temperature_index [+ transform:snow_ice_constant|swat on a glacier] [+ sublimation:constant|pet]")
+                                           "|degree_day_aspect|temperature_index [+ outflow:snow_holding [+ refreeze:"
+                                           "degree_day]] [+ transform:snow_ice_constant|swat on a glacier] "
+                                           "[+ sublimation:constant|pet]")
             return sps[0], transfo, sublim
+
+        def set_retention(sp, whc_slot, cfr_slot, prefix):
+            """water_holding_capacity / refreezing_factor of a snowpack with liquid-water retention and its labels."""
+            if sp["name"] not in retention:
+                return
+            holding, refreeze = retention[sp["name"]]
+            self._set(whc_slot, sp["name"], "water_holding_capacity", _params(holding)["water_holding_capacity"])
+            self.labels[f"{sp['name']}:{holding['name']}:output"] = prefix + "_meltwater"
+            if refreeze is not None:
+                self._set(cfr_slot, sp["name"], "refreezing_factor", _params(refreeze)["refreezing_factor"])
+                self.labels[f"{sp['name']}:{refreeze['name']}:output"] = prefix + "_refreeze"
 
         def set_sublimation(sp, proc, slot, record):
             kind = sublim_kinds[proc["kind"]]
@@ -263,6 +303,7 @@ class CompiledStructure:
                                 f"{gsp['name']}:snow_content": "ground_snowpack_snow",
                                 f"{gsp['name']}:{gsp['processes'][0]['name']}:output": "ground_snowpack_melt"})
             snowpacks = [gsp["name"]]
+            set_retention(gsp, "ground_snow_whc", "ground_snow_cfr", "ground_snowpack")
 
         # --- glacier
         st.has_glacier = 0
@@ -325,6 +366,7 @@ class CompiledStructure:
                 label(f"{glsp['name']}:snow_content", "glacier_snowpack_snow")
                 label(f"{glsp['name']}:{glsp['processes'][0]['name']}:output", "glacier_snowpack_melt")
                 snowpacks.append(glsp["name"])
+                set_retention(glsp, "glacier_snow_whc", "glacier_snow_cfr", "glacier_snowpack")
                 kind = transfo_kinds[gltr["kind"]] if gltr is not None else _e.SNOW_ICE_NONE
                 if second and kind != st.snow_ice_kind:
                     raise UnsupportedStructure("the snow -> ice transformation must be the same on every glacier snowpack")
@@ -349,6 +391,22 @@ class CompiledStructure:
                 self._set(slot, name, "response_factor", _params(bb["processes"][0])["response_factor"])
         if sorted(snow_targets or []) != sorted(snowpacks):
             raise UnsupportedStructure("snow must go to the snowpack of every land cover")
+        # liquid water in the snowpacks: the same processes on every snowpack (model_settings.py:248-255)
+        st.snow_retention = 0
+        if retention:
+            kinds = {(True, r is not None) for _, r in retention.values()}
+            if len(retention) != len(snowpacks) or len(kinds) != 1:
+                raise UnsupportedStructure("outflow:snow_holding / refreeze:degree_day must be on every snowpack or on none")
+            st.snow_retention = _e.RETENTION_HOLDING | (_e.RETENTION_REFREEZE if kinds.pop()[1] else 0) | \
+                (_e.RETENTION_RAIN_TO_SNOWPACK if rain_to_snowpack else 0)
+            if (st.snow_retention & _e.RETENTION_REFREEZE) and st.melt_kind != _e.MELT_DEGREE_DAY:
+                # ProcessRefreezeDegreeDay::IsValid (ProcessRefreezeDegreeDay.cpp:19-37)
+                raise UnsupportedStructure("The refreeze:degree_day process requires a melt:degree_day process on the same brick.")
+            if glacier2 is not None or slide_on:
+                raise UnsupportedStructure("liquid water in the snowpacks runs neither with a second glacier cover nor with "
+                                           "transport:snow_slide")
+        elif rain_to_snowpack:
+            raise UnsupportedStructure("rain routed to the snowpacks needs a snow water retention process")
         if slide_on:
             # the snowpacks of the generic cover always slide, those of the glacier unless skipGlaciers; one set of
             # parameters for every sliding snowpack (ProcessLateralSnowSlide.cpp:24-31)

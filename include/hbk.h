@@ -58,6 +58,11 @@ enum { HBK_ASPECT_NORTH = 0, HBK_ASPECT_SOUTH = 1, HBK_ASPECT_EAST_WEST = 2 };
  * ProcessLateralSnowSlide.cpp:46-134: snow above a slope-dependent holding depth slides, within the step, onto the
  * snowpacks of the units the giving unit is laterally connected to (hbk_set_lateral_connections). */
 enum { HBK_SNOW_SLIDE_NONE = 0, HBK_SNOW_SLIDE_SKIP_GLACIERS = 1, HBK_SNOW_SLIDE_ALL = 2 };
+/* snowpack liquid water: the melt water stays in the snowpack's water container and outflow:snow_holding releases what
+ * exceeds water_holding_capacity x snow water equivalent (ProcessOutflowSnowHolding.cpp:37-57) | + refreeze:degree_day
+ * moves it back to the snow (ProcessRefreezeDegreeDay.cpp:72-87) | + the rain goes through the snowpack
+ * (ChangeSplitterOutputTargetIfFound, SettingsModel.cpp:626-632) */
+enum { HBK_RETENTION_HOLDING = 1, HBK_RETENTION_REFREEZE = 2, HBK_RETENTION_RAIN_TO_SNOWPACK = 4 };
 
 /* The per-structure process table for the Socont family, as the structure compiler
  * (hydrobricks_b200/csrc/hb_host.hpp, hb::Compiled) derives it from a SettingsModel. */
@@ -82,7 +87,9 @@ typedef struct {
     int32_t sublimation_kind;
     int32_t melt_kind;                /* HBK_MELT_*, the same process on every snowpack and on the glacier ice */
     int32_t snow_slide_kind;          /* HBK_SNOW_SLIDE_* */
-    int32_t reserved;
+    /* liquid water in the snowpacks (SettingsModel::GenerateSnowpacksWithWaterRetention, SettingsModel.cpp:608-634;
+     * AddSnowpackRefreezing :574-590), bits HBK_RETENTION_*: 0 = melt water goes straight to the land cover */
+    int32_t snow_retention;
 } hbk_structure;
 
 /* Parameter slots of one parameter set: float32 like the reference (Parameter.h:121). */
@@ -119,6 +126,8 @@ enum {
      * parameters.py:1766-1835): its snowpack's and its ice's melt parameters, snow -> ice transformation, sublimation */
     HBK_P_GLACIER2_SNOW_DDF, HBK_P_GLACIER2_SNOW_TMELT, HBK_P_ICE2_DDF, HBK_P_ICE2_TMELT, HBK_P_SNOW_ICE2,
     HBK_P_GLACIER2_SUBLIMATION, HBK_P_GLACIER2_SNOW_MELT_B, HBK_P_GLACIER2_SNOW_MELT_C, HBK_P_ICE2_MELT_B, HBK_P_ICE2_MELT_C,
+    /* <cover>_snowpack:water_holding_capacity and :refreezing_factor (HBK_RETENTION_*) */
+    HBK_P_GROUND_SNOW_WHC, HBK_P_GLACIER_SNOW_WHC, HBK_P_GROUND_SNOW_CFR, HBK_P_GLACIER_SNOW_CFR,
     HBK_N_PARAMS
 };
 
@@ -135,6 +144,9 @@ enum {
     HBK_R_GLACIER_SNOWPACK_TRANSFO,                /* glacier_snowpack:snow_ice_transfo:output */
     HBK_R_GROUND_SNOWPACK_SUBLIMATION, HBK_R_GLACIER_SNOWPACK_SUBLIMATION, /* <cover>_snowpack:sublimation:output;
                                                       0 while the cover is null (the reference keeps the last amount) */
+    /* <cover>_snowpack:meltwater:output and :refreeze:output (HBK_RETENTION_*) */
+    HBK_R_GROUND_SNOWPACK_MELTWATER, HBK_R_GLACIER_SNOWPACK_MELTWATER,
+    HBK_R_GROUND_SNOWPACK_REFREEZE, HBK_R_GLACIER_SNOWPACK_REFREEZE,
     HBK_N_RECORDS
 };
 
@@ -144,6 +156,11 @@ enum {
     HBK_S_SLOW, HBK_S_SLOW2, HBK_S_QUICK,
     HBK_S_AMT_INFILTRATION, HBK_S_AMT_REST, HBK_S_AMT_MELT_GROUND, HBK_S_AMT_MELT_GLACIER,
     HBK_S_AMT_DEPOSIT_RAIN_SNOWMELT, HBK_S_AMT_DEPOSIT_ICEMELT, HBK_S_AMT_SNOW_ICE,
+    /* HBK_RETENTION_*: the refreeze fluxes' last amounts (they count as static inputs of the snow containers until the
+     * next refreeze, WaterContainer.cpp:98-101) and the melt amounts (with retention HBK_S_AMT_MELT_* are the melt WATER
+     * released to the covers); then two more storages, the snowpacks' liquid water */
+    HBK_S_AMT_REFREEZE_GROUND, HBK_S_AMT_REFREEZE_GLACIER, HBK_S_AMT_SNOWMELT_GROUND, HBK_S_AMT_SNOWMELT_GLACIER,
+    HBK_S_GROUND_SNOWPACK_WATER, HBK_S_GLACIER_SNOWPACK_WATER,
     HBK_N_STATES
 };
 

@@ -62,7 +62,16 @@ def settings_from_structures(hb, meta, n_steps, solver=None):
         for b in st["hydro_unit_bricks"]:
             if b["is_land_cover"]:
                 s.add_land_cover_brick(b["name"], b["kind"])
-        if tr is not None:
+        snowpack_bricks = [b for b in st["hydro_unit_bricks"] if b["is_surface_component"]]
+        holding = next((p["kind"] for b in snowpack_bricks for p in b["processes"] if p["name"] == "meltwater"), None)
+        if tr is not None and holding:  # GenerateSnowpacksWithWaterRetention / AddSnowpackRefreezing (model_settings.py:248-255)
+            rain_splitter = next(sp for sp in st["hydro_unit_splitters"] if sp["name"] == "rain_splitter")
+            rain_to_snowpack = any(o["target"].endswith("_snowpack") for o in rain_splitter["outputs"])
+            s.generate_snowpacks_with_water_retention(snowpack_bricks[0]["processes"][0]["kind"], holding, rain_to_snowpack)
+            refreeze = next((p["kind"] for b in snowpack_bricks for p in b["processes"] if p["name"] == "refreeze"), None)
+            if refreeze:
+                s.add_snowpack_refreezing(refreeze)
+        elif tr is not None:
             s.generate_snowpacks(next(b["processes"][0]["kind"] for b in st["hydro_unit_bricks"]
                                       if b["is_surface_component"]))
         extras = {}  # AddSnowIceTransformation / AddSnowpackSublimation, in the order of model_settings.py:258-263

@@ -29,6 +29,7 @@ int runSet(const hbk_structure& st, int U, int T, const double* area, const floa
     f.snowIceKind = st.has_glacier ? st.snow_ice_kind : 0;
     f.sublimKind = st.sublimation_kind;
     f.seqKind = st.solver >= HBK_SOLVER_CRANK_NICOLSON ? st.solver - HBK_SOLVER_CRANK_NICOLSON : 0;
+    f.retention = st.snow_retention;
     const double dt = st.time_step_days, invDt = 1.0 / st.time_step_days;
 
     // parameter promotion as in hbkRunUnits (float32 -> double where the reference's expressions promote)
@@ -82,6 +83,15 @@ int runSet(const hbk_structure& st, int U, int T, const double* area, const floa
             par.v[7] = pp[a == 0 ? HBK_P_GLACIER_SNOW_DDF : (a == 1 ? HBK_P_GLACIER_SNOW_MELT_B : HBK_P_GLACIER_SNOW_MELT_C)];
             par.v[9] = pp[a == 0 ? HBK_P_ICE_DDF : (a == 1 ? HBK_P_ICE_MELT_B : HBK_P_ICE_MELT_C)];
         }
+        // liquid water in the snowpacks (HBK_RETENTION_*): the unit's six extra state values, as retentionCtx of
+        // hbk_engine.cu points them into the state arrays
+        double extra[6] = {0, 0, 0, 0, 0, 0};
+        RetentionCtx rc{};
+        rc.g = {&extra[0], &extra[1], &extra[2], (double)pp[HBK_P_GROUND_SNOW_WHC], (double)pp[HBK_P_GROUND_SNOW_CFR]};
+        rc.gl = {&extra[3], &extra[4], &extra[5], (double)pp[HBK_P_GLACIER_SNOW_WHC], (double)pp[HBK_P_GLACIER_SNOW_CFR]};
+        rc.refreeze = (st.snow_retention & HBK_RETENTION_REFREEZE) != 0;
+        rc.rainToSnowpack = (st.snow_retention & HBK_RETENTION_RAIN_TO_SNOWPACK) != 0;
+        const RetentionCtx* ret = st.snow_retention ? &rc : nullptr;
         for (int t = 0; t < T; ++t) {
             StepOut o{};
             const double p = precip[(size_t)t * U + u], tt = temp[(size_t)t * U + u], e = pet[(size_t)t * U + u];
@@ -98,7 +108,7 @@ int runSet(const hbk_structure& st, int U, int T, const double* area, const floa
                 if (GLACIER) sublimGl = scale * (double)pp[HBK_P_GLACIER_SUBLIMATION];
             }
             directPhase<GLACIER>(h, par, p, tt, dt, invDt, fa, fG, fGl, gv, f, o, err, (GLACIER && swat) ? swat[t] : 0.0,
-                                 sublimG, sublimGl);
+                                 sublimG, sublimGl, 0.0, 0.0, NoSlide(), NoSlide(), ret);
             if (SOLVER == 3) {
                 solveUnitSequential<NSOIL>(h, par, e, faW, dt, invDt, f, o, err);
             } else {

@@ -97,7 +97,7 @@ def test_unsupported_structures_are_refused():
             s.add_hydro_unit_brick("x", "storage")
             s.add_brick_process("p", "et:hbv")
         with pytest.raises(RuntimeError):
-            s.add_snowpack_refreezing("refreeze:degree_day")
+            s.generate_canopy_interception("forest", "forest")
         with pytest.raises(RuntimeError):
             s.add_snow_redistribution("transport:wind_drift")
     meta, _, _, _, _ = gu.load("kat_linear_storage_runge_kutta")

@@ -26,11 +26,9 @@ NEXT_CASES = sorted("next/" + p.stem for p in (gu.GOLDEN / "next").glob("*.npz")
 
 @pytest.mark.parametrize("name", NEXT_CASES)
 def test_oracle_matches_reference_on_options_the_engine_lacks(name):
-    """Snowpack liquid-water retention (outflow:snow_holding, ProcessOutflowSnowHolding.cpp:37-57), refreezing
-    (refreeze:degree_day, ProcessRefreezeDegreeDay.cpp:72-87) and the rain routed through the snowpack
-    (SettingsModel.cpp:608-634) — options of the reference's HBV / custom models, not of its Socont: the oracle is pinned
-    bit for bit against the unmodified reference (tools/ref_retention_case.py); the CUDA engine does not implement them
-    and its structure compiler refuses such structures (tests/golden/next is outside the engine's parity lists)."""
+    """tests/golden/next: options pinned bit for bit in the oracle that the CUDA engine does not implement yet — its
+    structure compiler refuses such structures (outside the engine's parity lists). Empty at the moment: the last
+    occupants, snowpack water retention / refreezing, moved to tests/golden when the engine learnt them."""
     from hydrobricks_b200 import structure
 
     meta, forcing, outlet, records, _ = gu.load(name)

@@ -260,8 +260,7 @@ def snow_retention_bundles(ref):
                                           extras=dict(snow_ice_transformation="transform:snow_ice_constant",
                                                       snow_sublimation_process="sublimation:pet")), "rain_snowice_sublim_1store")):
         meta, forcing, q, rec = rr.run_reference(ref, solver, **kw)
-        # tests/golden/next: pinned in the oracle, not in the CUDA engine yet (outside the engine's parity lists)
-        save(f"next/snow_retention_{solver}_{name}", meta, forcing, q, rec)
+        save(f"snow_retention_{solver}_{name}", meta, forcing, q, rec)
 
 
 def two_glaciers_bundles(ref):
