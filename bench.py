@@ -458,8 +458,12 @@ def run_engine_arm(args):
     if unit_sharded:
         P = args.sets
         U_total = U if strong else world * U
-        u0, u1 = parallel.shard_bounds(U_total, rank, world)
-        units = hydro_units(U_total, area=wl["area"], glacier=wl["glacier"])[u0:u1]
+        # blocks of equal integration cost, not of equal unit count: the units with ice (the upper third, at one end of
+        # the elevation-sorted basin) run the glacier kernel variant (parallel.GLACIER_UNIT_COST)
+        all_units = hydro_units(U_total, area=wl["area"], glacier=wl["glacier"])
+        u0, u1 = parallel.weighted_shard_bounds(parallel.unit_costs(all_units), rank, world)
+        units = all_units[u0:u1]
+        del all_units
         U = u1 - u0
         set_seed = 0  # unit shards integrate the SAME parameter sets
         ps = parameter_sets(P, seed=44)
@@ -683,9 +687,10 @@ def run_engine_arm(args):
             "evals_per_s": P_total * args.steps / (dev_ms * 1e-3),
             "config": {"workload": wl["name"], "sets_per_gpu": P, "sets_total": P_total, "hydro_units": U_total,
                        "hydro_units_per_gpu": U,
-                       "multi_gpu": ("one basin of %d units, a block of %d per GPU; per step one all-reduce of the "
-                                     "partial outlet and the two sub-basin deposit series [T], then the sub-basin "
-                                     "stores" % (U_total, U)) if unit_sharded else
+                       "multi_gpu": ("one basin of %d units in contiguous blocks of equal integration cost (units with ice "
+                                     "weigh %.2f; rank 0 holds %d); per step one all-reduce of the partial outlet and the "
+                                     "two sub-basin deposit series [T], then the sub-basin stores"
+                                     % (U_total, parallel.GLACIER_UNIT_COST, U)) if unit_sharded else
                                     "parameter axis sharded, no collective on the path, one all_gather of scores",
                        "timesteps": T, "solver": args.solver,
                        "structure": f"socont {wl['soil']} soil store(s), runoff:socont" + (", glacier (GSM)" if wl["glacier"] else ""),

@@ -20,6 +20,32 @@ def shard_bounds(n_sets: int, rank: int, world: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+# Relative cost of a hydro unit that carries ice (the glacier kernel variant, 128 registers) against a unit that never does
+# (the plain variant): 51.5 ms / 35.3 ms on the same 1 M units x 730 steps (profiles/r02s_kbench.jsonl)
+GLACIER_UNIT_COST = 1.46
+
+
+def unit_costs(units):
+    """Relative integration cost per hydro unit, for a cost-balanced split of a basin over the ranks."""
+    return [GLACIER_UNIT_COST if any(abs(f) > 0 for n, f in u["land_covers"] if "glacier" in n) else 1.0 for u in units]
+
+
+def weighted_shard_bounds(weights, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous split with (nearly) equal summed weight per rank: boundary r sits where the prefix sum of the weights
+    first reaches r/world of the total. A basin sorted by elevation has its glacier units — the expensive ones — at
+    one end, so equal unit counts leave the rank with the glaciers 40 % behind (2xB200, C3: x1.58 instead of x1.85)."""
+    import numpy as np
+
+    w = np.asarray(weights, dtype=np.float64)
+    if len(w) == 0 or world <= 1:
+        return 0, len(w)
+    csum = np.cumsum(w)
+    cuts = [0] + [int(np.searchsorted(csum, csum[-1] * r / world, side="left")) for r in range(1, world)] + [len(w)]
+    for i in range(1, len(cuts)):  # monotone, and no empty block while units are left
+        cuts[i] = max(cuts[i], cuts[i - 1])
+    return cuts[rank], cuts[rank + 1]
+
+
 def shard_rows(matrix, rank: int, world: int):
     lo, hi = shard_bounds(len(matrix), rank, world)
     return matrix[lo:hi]
@@ -135,15 +161,18 @@ class ShardedBasin:
     inside the run — which is what spin-up (ModelHydro::RunSpinup) and dated actions (the delta-h water equivalent of the
     whole glacier at every update) need — and run() goes through the model's own run(), so that actions registered on
     the model (tables / changes of the WHOLE basin, the same on every rank) are scheduled. Needs the Python host.
+
+    balance_cost=True cuts the blocks by integration cost (units with ice cost GLACIER_UNIT_COST) instead of unit count.
     """
 
-    def __init__(self, make_model, units, group=None, in_run_reduce=False):
+    def __init__(self, make_model, units, group=None, in_run_reduce=False, balance_cost=False):
         import torch.distributed as dist
 
         self.group = group
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         units = sorted(units, key=lambda u: -u["elevation"])
-        lo, hi = shard_bounds(len(units), rank, world)
+        lo, hi = weighted_shard_bounds(unit_costs(units), rank, world) if balance_cost else \
+            shard_bounds(len(units), rank, world)
         self.bounds = (lo, hi)
         self.total_area = basin_area([u["area"] for u in units])
         self.model = make_model(units[lo:hi])

@@ -101,3 +101,21 @@ def test_basin_area_is_the_running_sum_in_unit_order():
     for a in areas:
         total += float(a)
     assert parallel.basin_area(areas) == total
+
+
+def test_weighted_shard_bounds_balance_the_cost():
+    """Unit shards cut by integration cost (parallel.weighted_shard_bounds): contiguous, covering, and no block more than
+    one unit's weight away from the mean — for a basin whose expensive (glacier) units sit at one end."""
+    import bench
+
+    units = bench.hydro_units(997, glacier=True)
+    costs = parallel.unit_costs(units)
+    assert set(costs) == {1.0, parallel.GLACIER_UNIT_COST}
+    for world in (1, 2, 3, 4, 8):
+        spans = [parallel.weighted_shard_bounds(costs, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == len(units)
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sums = [sum(costs[lo:hi]) for lo, hi in spans]
+        assert max(sums) - min(sums) <= 2 * parallel.GLACIER_UNIT_COST
+    assert parallel.weighted_shard_bounds([], 0, 4) == (0, 0)
+    assert parallel.weighted_shard_bounds([1.0] * 10, 1, 1) == (0, 10)
