@@ -1093,6 +1093,7 @@ struct ActArgs {
     const int* hruFlags;
     int ldu;
     int iceInfinite;
+    int retention;  // HBK_RETENTION_*: the snowpacks hold liquid water, which moves with the land like the snow
     int* err;
     // twin units (hbk_set_unit_twins): twinOf[u] = unit whose second glacier cover u carries (-1: an ordinary unit),
     // twinCol[u] = the twin of unit u (-1: none); nullptr without twins
@@ -1134,15 +1135,21 @@ __device__ void changeGlacierFraction(const ActArgs& a, int p, int u, double fra
         double& snowG = stateAt(a, HBK_S_GROUND_SNOW, p, uGen);
         double& snowGl = stateAt(a, HBK_S_GLACIER_SNOW, p, u);
         double& ice = stateAt(a, HBK_S_ICE, p, u);
+        // the snowpacks' liquid water (CoverRole::SnowpackWater, HydroUnit.cpp:42-46): a storage only with HBK_RETENTION_*
+        double none = 0.0;
+        double& swG = a.retention ? stateAt(a, HBK_S_GROUND_SNOWPACK_WATER, p, uGen) : none;
+        double& swGl = a.retention ? stateAt(a, HBK_S_GLACIER_SNOWPACK_WATER, p, u) : none;
         if (delta > 0) {  // the glacier grows, taking land (and its water column) from the generic cover
             const double fRO = oldFraction, fRN = fraction, fDN = genericNew, strip = delta;
             if (!nearlyZero(fRN, kEpsD)) {
                 wGl = (wGl * fRO + wG * strip) / fRN;
                 if (!a.iceInfinite) ice = (ice * fRO + 0.0 * strip) / fRN;
                 snowGl = (snowGl * fRO + snowG * strip) / fRN;
+                if (a.retention) swGl = (swGl * fRO + swG * strip) / fRN;
                 if (nearlyZero(fDN, kEpsD)) {
                     wG = 0;
                     snowG = 0;
+                    swG = 0;
                 }
             }
         } else {  // the glacier shrinks, giving land to the generic cover; the ice stays with the glacier
@@ -1150,10 +1157,12 @@ __device__ void changeGlacierFraction(const ActArgs& a, int p, int u, double fra
             if (!nearlyZero(fRN, kEpsD)) {
                 wG = (wG * fRO + wGl * strip) / fRN;
                 snowG = (snowG * fRO + snowGl * strip) / fRN;
+                if (a.retention) swG = (swG * fRO + swGl * strip) / fRN;
                 if (nearlyZero(fDN, kEpsD)) {
                     wGl = 0;
                     if (!a.iceInfinite) ice = 0;
                     snowGl = 0;
+                    swGl = 0;
                 }
             }
         }
@@ -1778,11 +1787,12 @@ void planRuns(hbk_engine* e) {
         if (runs.empty() || runs.back().glacier != (tileIce[t] != 0)) runs.push_back({t, t, tileIce[t] != 0, 0, 0, 0, 0});
         runs.back().tile1 = t + 1;
     }
-    bool anyIce = false, anyPlain = false;
-    for (const auto& r : runs) (r.glacier ? anyIce : anyPlain) = true;
-    // a handful of launches at most (glacier units sit together in an elevation-sorted basin); a basin without any ice keeps
-    // the glacier variant, which writes the (zero) deposits the sub-basin stores read
-    if (!anyIce || !anyPlain || (int)runs.size() > hbk_engine::kMaxRuns) return single();
+    bool anyPlain = false;
+    for (const auto& r : runs) anyPlain = anyPlain || !r.glacier;
+    // a handful of launches at most (glacier units sit together in an elevation-sorted basin). A basin — or a unit shard of
+    // one — without any ice runs the plain variant alone: its deposits into the sub-basin stores are zeroed by hbk_run
+    if (!anyPlain || (int)runs.size() > hbk_engine::kMaxRuns) return single();
+    e->glacierGroups = 0;
     int base = 0;
     for (int pass = 0; pass < 2; ++pass)  // glacier groups first: the deposits are summed over those only
         for (auto& r : runs) {
@@ -1802,8 +1812,10 @@ using KernelFn = void (*)(const KArgs);
 
 template <int SOLVER, int NSOIL, bool GLACIER>
 KernelFn pickDaily(bool daily, int shape) {
-    // the sequential solvers (SOLVER 3) are not the throughput path: one instantiation, dt read at run time
+    // the sequential solvers (SOLVER 3): the generic instantiation (dt read at run time) and, for calibration ensembles with
+    // daily steps — crank_nicolson is the default of the reference's Python layer —, the compile-time ensemble shape
     if constexpr (SOLVER == 3) {
+        if (daily && shape == 1) return (KernelFn)hbkRunUnits<SOLVER, NSOIL, GLACIER, true, 1>;
         return (KernelFn)hbkRunUnits<SOLVER, NSOIL, GLACIER, false, 0>;
     } else {
         // the compile-time shapes exist for daily steps only (the case ensembles and distributed basins are run in)
@@ -1831,7 +1843,7 @@ KernelFn pickKernel(const hbk_structure& st, bool glacier, int shape) {
         case HBK_SOLVER_EULER: return pickSoil<0>(st.n_soil_stores, glacier, daily, shape);
         case HBK_SOLVER_HEUN: return pickSoil<1>(st.n_soil_stores, glacier, daily, shape);
         case HBK_SOLVER_RK4: return pickSoil<2>(st.n_soil_stores, glacier, daily, shape);
-        default: return pickSoil<3>(st.n_soil_stores, glacier, false, 0);  // sequential family
+        default: return pickSoil<3>(st.n_soil_stores, glacier, daily, shape == 1 ? 1 : 0);  // sequential family
     }
 }
 
@@ -2571,6 +2583,7 @@ static int applyEvents(hbk_engine* e, int step) {
     a.hruFlags = e->dHruFlags;
     a.ldu = e->ldu;
     a.iceInfinite = e->st.glacier_infinite_storage;
+    a.retention = e->st.snow_retention;
     a.err = e->dErr;
     a.twinOf = e->dTwinOf;
     a.twinCol = e->dTwinCol;
@@ -2846,12 +2859,12 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
         const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
         hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartQ, e->dOutlet, e->totalGroups, e->P, e->ldt, tBegin, tEnd, e->dPerm);
         e->lastLaunches++;
-        if (e->st.has_glacier) {
+        if (e->st.has_glacier && e->glacierGroups > 0) {
             hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD1, e->dD1, e->glacierGroups, e->P, e->ldt, tBegin, tEnd, nullptr);
             hbkReduceTiles<<<blocks, 256, 0, e->stream>>>(e->dPartD2, e->dD2, e->glacierGroups, e->P, e->ldt, tBegin, tEnd, nullptr);
             e->lastLaunches += 2;
         }
-    } else if (!writeOutputs && multi && e->st.has_glacier) {
+    } else if (!writeOutputs && multi && e->st.has_glacier && e->glacierGroups > 0) {
         // spin-up: the deposits are still needed by the sub-basin stores
         const long long n = (long long)e->P * (tEnd - tBegin);
         const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
@@ -2949,10 +2962,9 @@ int hbk_run(hbk_engine* e) {
                                             "(hbk_set_delta_h_shard_totals)");
     }
     e->shardSegments.clear();
-    if (e->st.snow_retention && (e->hasTwins || e->st.snow_slide_kind != HBK_SNOW_SLIDE_NONE || !e->events.empty()))
+    if (e->st.snow_retention && (e->hasTwins || e->st.snow_slide_kind != HBK_SNOW_SLIDE_NONE))
         return fail(e, HBK_E_UNSUPPORTED, "liquid water in the snowpacks (outflow:snow_holding / refreeze:degree_day) runs "
-                                          "neither with a second glacier cover, nor with lateral connections, nor with "
-                                          "dated actions");
+                                          "neither with a second glacier cover nor with lateral connections");
     if (e->hasTwins && (e->st.snow_slide_kind != HBK_SNOW_SLIDE_NONE || e->shard))
         return fail(e, HBK_E_UNSUPPORTED, "units with a second glacier cover (hbk_set_unit_twins) run neither lateral "
                                           "connections nor unit shards");
@@ -2994,6 +3006,10 @@ int hbk_run(hbk_engine* e) {
         if (!e->dD2) HBK_CUDA(cudaMalloc(&e->dD2, sizeof(double) * outN));
         if (multi && !e->dPartD1) HBK_CUDA(cudaMalloc(&e->dPartD1, sizeof(double) * outN * e->totalGroups));
         if (multi && !e->dPartD2) HBK_CUDA(cudaMalloc(&e->dPartD2, sizeof(double) * outN * e->totalGroups));
+        if (e->glacierGroups == 0) {  // no unit with ice: nothing ever deposits into the sub-basin stores
+            HBK_CUDA(cudaMemsetAsync(e->dD1, 0, sizeof(double) * outN, e->stream));
+            HBK_CUDA(cudaMemsetAsync(e->dD2, 0, sizeof(double) * outN, e->stream));
+        }
     }
     const int nRec = __builtin_popcountll(e->recordMask);
     const size_t recBytes = sizeof(double) * (size_t)nRec * e->P * e->T * e->U;

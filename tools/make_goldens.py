@@ -192,7 +192,7 @@ def action_bundles(ref, only_new=False):
              ("heun_explicit", (True, True, True), False), ("euler_explicit", (True, True, True), False)]
     new = [("rk4", (True, False, False), True), ("heun_explicit", (True, True, True), True),
            ("crank_nicolson", (True, True, True), False)]
-    for solver, flags, area_scaling in (new if only_new else cases + new):
+    for solver, flags, area_scaling in ([] if only_new is None else new if only_new else cases + new):
         meta, forcing, q, rec, frac, areas, volumes = rc.run_reference(ref, solver, *flags, area_scaling=area_scaling)
         tag = "".join(n for n, f in zip(("as" if area_scaling else "dh", "lc", "s2i"), flags) if f)
         extra = {"spatial_dh_areas": areas, "spatial_dh_volumes": volumes}
@@ -203,6 +203,19 @@ def action_bundles(ref, only_new=False):
                 "surface_runoff:water_content", "glacier:melt:output", "glacier:outflow_rain_snowmelt:output"]
         meta["labels"] = keep
         save(f"actions_{solver}_{tag}", meta, forcing, q, {k: rec[k] for k in keep}, extra=extra)
+    # the same actions with liquid water in the snowpacks: the land-cover transfer moves it like the snow
+    retention = dict(snow_water_retention_process="outflow:snow_holding", snow_refreezing_process="refreeze:degree_day",
+                     rain_to_snowpack=True, _parameters=[("type:snowpack", "water_holding_capacity", 0.15),
+                                                         ("type:snowpack", "refreezing_factor", 0.06)])
+    meta, forcing, q, rec, frac, areas, volumes = rc.run_reference(ref, "rk4", True, True, True, options=retention)
+    extra = {"spatial_dh_areas": areas, "spatial_dh_volumes": volumes}
+    for k, v in frac.items():
+        extra["spatial_fraction_" + k] = v
+    keep = ["glacier:ice_content", "glacier:water_content", "ground:water_content", "glacier_snowpack:snow_content",
+            "ground_snowpack:snow_content", "glacier_snowpack:water_content", "ground_snowpack:water_content",
+            "ground_snowpack:meltwater:output", "glacier_snowpack:refreeze:output", "slow_reservoir:water_content"]
+    meta["labels"] = keep
+    save("actions_rk4_dhlcs2i_retention", meta, forcing, q, {k: rec[k] for k in keep}, extra=extra)
 
 
 def melt_variant_bundles(ref):
@@ -330,6 +343,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "snow_slide":
         snow_slide_bundles(ref)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "actions_retention":
+        action_bundles(ref, only_new=None)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "actions_new":
         action_bundles(ref, only_new=True)

@@ -57,10 +57,12 @@ def synthetic_case(n_units=10, n_years=6, seed=11):
     return units, forcing, T, gl, areas, volumes
 
 
-def build_settings(backend, solver):
+def build_settings(backend, solver, **options):
+    """options: further models.Socont options, e.g. the snowpack liquid-water retention of tools/ref_retention_case.py."""
     m = models.Socont(solver=solver, soil_storage_nb=2, surface_runoff="socont_runoff", record_all=True,
                       land_cover_names=["ground", "glacier"], land_cover_types=["ground", "glacier"],
-                      glacier_infinite_storage=False, backend=backend)
+                      glacier_infinite_storage=False, backend=backend,
+                      **{k: v for k, v in options.items() if not k.startswith("_")})
     for comp, name, v in [("type:snowpack", "degree_day_factor", 4.0), ("slow_reservoir", "capacity", 150),
                           ("slow_reservoir", "response_factor", 0.03), ("surface_runoff", "beta", 900),
                           ("glacier", "degree_day_factor", 8.5),
@@ -76,9 +78,12 @@ CHANGES = [  # (days after start, unit position in basin order, new glacier area
     (400, 1, 0.90), (800, 2, 0.75), (800.0, 0, 1.05), (1300, 3, 0.0), (1700, 1, 0.60)]
 
 
-def run_reference(ref, solver, with_delta_h=True, with_changes=True, with_snow_to_ice=True, area_scaling=False):
+def run_reference(ref, solver, with_delta_h=True, with_changes=True, with_snow_to_ice=True, area_scaling=False,
+                  options=None):
     units, forcing, T, gl, areas, volumes = synthetic_case()
-    m = build_settings(ref, solver)
+    m = build_settings(ref, solver, **(options or {}))
+    for comp, name, v in (options or {}).get("_parameters", []):
+        assert m.settings.set_parameter_value(comp, name, v), (comp, name)
     end = str(np.datetime64("1981-01-01") + np.timedelta64(T - 1, "D"))
     m.setup(units, "1981-01-01", end)
     model = m.model
