@@ -2831,6 +2831,13 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
     } else {
         // the launches of a split glacier structure are independent (their own units, partial buffers and work queues):
         // they run side by side, the second and later ones on auxiliary streams forked from / joined to the engine's
+        if (e->st.has_glacier && e->glacierGroups == 0) {
+            // no unit with ice: nothing deposits into the sub-basin stores in this segment (the series may hold the sums
+            // of an earlier reduction over the shards, e.g. of the spin-up over the same steps)
+            const size_t width = sizeof(double) * (size_t)(tEnd - tBegin), pitch = sizeof(double) * (size_t)e->ldt;
+            HBK_CUDA(cudaMemset2DAsync(e->dD1 + tBegin, pitch, 0, width, e->P, e->stream));
+            HBK_CUDA(cudaMemset2DAsync(e->dD2 + tBegin, pitch, 0, width, e->P, e->stream));
+        }
         const char* serial = std::getenv("HBK_SPLIT_SERIAL");
         const bool fork = e->runs.size() > 1 && !(serial && serial[0] == '1');
         if (fork) {
@@ -3006,10 +3013,7 @@ int hbk_run(hbk_engine* e) {
         if (!e->dD2) HBK_CUDA(cudaMalloc(&e->dD2, sizeof(double) * outN));
         if (multi && !e->dPartD1) HBK_CUDA(cudaMalloc(&e->dPartD1, sizeof(double) * outN * e->totalGroups));
         if (multi && !e->dPartD2) HBK_CUDA(cudaMalloc(&e->dPartD2, sizeof(double) * outN * e->totalGroups));
-        if (e->glacierGroups == 0) {  // no unit with ice: nothing ever deposits into the sub-basin stores
-            HBK_CUDA(cudaMemsetAsync(e->dD1, 0, sizeof(double) * outN, e->stream));
-            HBK_CUDA(cudaMemsetAsync(e->dD2, 0, sizeof(double) * outN, e->stream));
-        }
+
     }
     const int nRec = __builtin_popcountll(e->recordMask);
     const size_t recBytes = sizeof(double) * (size_t)nRec * e->P * e->T * e->U;

@@ -121,6 +121,9 @@ def run_reference(ref, solver, with_delta_h=True, with_changes=True, with_snow_t
                         if with_changes else [],
                         "snow_to_ice": [9, 30] if with_snow_to_ice else None, "start_mjd": START_MJD},
             "source": "reference core driven directly (tools/ref_actions_case.py)"}
+    if options:  # what build_settings needs to rebuild this model on another host
+        meta["model_options"] = {k: v for k, v in options.items() if not k.startswith("_")}
+        meta["model_parameters"] = [list(x) for x in options.get("_parameters", [])]
     return meta, forcing, model.get_outlet_discharge(), rec, frac, areas, volumes
 
 
