@@ -644,7 +644,10 @@ __global__ void __launch_bounds__(HBK_MAX_THREADS, hbkMinBlocks(NSOIL, GLACIER))
                                          (GLACIER && a.swatFactor) ? a.swatFactor[t0 + tc] : 0.0, sublimG, sublimGl, 0.0, 0.0,
                                          NoSlide(), NoSlide(), ret);
                     if constexpr (SOLVER == 3) {
-                        solveUnitSequential<NSOIL>(h, par, pet, faW, dt, invDt, a.flags, o, err);
+                        // the ensemble-shape instantiation of the sequential family is crank_nicolson's (the default of the
+                        // reference's Python layer): the other members run the generic instantiation
+                        solveUnitSequential<NSOIL, (SHAPE == 1 ? (int)kSeqCrank : -1)>(h, par, pet, faW, dt, invDt, a.flags, o,
+                                                                                         err);
                     } else {
                         solveUnit<SOLVER, NSOIL>(h, par, pet, faW, dt, invDt, a.flags, o, err, unconverged);
                     }
@@ -1843,7 +1846,8 @@ KernelFn pickKernel(const hbk_structure& st, bool glacier, int shape) {
         case HBK_SOLVER_EULER: return pickSoil<0>(st.n_soil_stores, glacier, daily, shape);
         case HBK_SOLVER_HEUN: return pickSoil<1>(st.n_soil_stores, glacier, daily, shape);
         case HBK_SOLVER_RK4: return pickSoil<2>(st.n_soil_stores, glacier, daily, shape);
-        default: return pickSoil<3>(st.n_soil_stores, glacier, daily, shape == 1 ? 1 : 0);  // sequential family
+        default:  // sequential family: the compile-time ensemble shape exists for crank_nicolson only
+            return pickSoil<3>(st.n_soil_stores, glacier, daily, (shape == 1 && st.solver == HBK_SOLVER_CRANK_NICOLSON) ? 1 : 0);
     }
 }
 
