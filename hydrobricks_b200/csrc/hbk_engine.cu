@@ -1529,6 +1529,8 @@ struct hbk_engine {
     std::vector<double> hLatWeight;
     std::vector<float> hSlopeDeg;
     std::vector<float> hParamsT;  // [HBK_N_PARAMS][ldp], the device layout (internal set order)
+    float* hParamStage = nullptr;  // page-locked staging of the same layout for hbk_set_parameters
+    size_t paramStageN = 0;
     int* dLatOff = nullptr;
     int* dLatRecv = nullptr;
     double* dLatWeight = nullptr;
@@ -1732,7 +1734,8 @@ int chunkSteps(const hbk_engine* e, bool glacier) {
     }
     if (const char* force = std::getenv("HBK_CHUNK_STEPS")) {  // tuning knob
         const int v = std::atoi(force);
-        if (v >= 2 && v <= 64 && (v & (v - 1)) == 0) tc = v;
+        // station series are padded for chunks of up to 16 steps (tld = ceil16(T) + 32 >= T + TC + 2)
+        if (v >= 2 && v <= (e->haveRaw[0] ? 64 : 16) && (v & (v - 1)) == 0) tc = v;
     }
     return tc;
 }
@@ -2062,6 +2065,7 @@ void hbk_engine_destroy(hbk_engine* e) {
     freeDev(e->dUnconv);
     freeDev(e->dUnconvSet);
     for (auto& q : e->dQueue) freeDev(q);
+    if (e->hParamStage) cudaFreeHost(e->hParamStage);
     for (auto& st : e->auxStream)
         if (st) cudaStreamDestroy(st);
     for (auto& ev : e->evJoin)
@@ -2195,17 +2199,51 @@ int hbk_set_parameters(hbk_engine* e, int32_t n_sets, const float* values) {
         e->perm.resize(n_sets);
         for (int p = 0; p < n_sets; ++p) e->perm[p] = p;
         if (wantSort && !e->initPerSet) {
-            auto val = [&](int p, int k) { return values[(size_t)p * HBK_N_PARAMS + k]; };
+            // (the two keys gathered into contiguous arrays first: the comparators of a 100 000-set ensemble then stay in
+            // cache — this runs inside the end-to-end step)
+            std::vector<float> kSlow(n_sets), capacity(n_sets);
+            for (int p = 0; p < n_sets; ++p) {
+                kSlow[p] = values[(size_t)p * HBK_N_PARAMS + HBK_P_K_SLOW_1];
+                capacity[p] = values[(size_t)p * HBK_N_PARAMS + HBK_P_CAPACITY];
+            }
             std::vector<int> byK(e->perm);
-            std::stable_sort(byK.begin(), byK.end(),
-                             [&](int x, int y) { return val(x, HBK_P_K_SLOW_1) < val(y, HBK_P_K_SLOW_1); });
+            std::stable_sort(byK.begin(), byK.end(), [&](int x, int y) { return kSlow[x] < kSlow[y]; });
             const int nWarps = (n_sets + 31) / 32;
-            const int nBuckets = std::max(1, std::min(64, (int)std::lround(std::sqrt((double)nWarps / 3.0))));
+            int nBuckets = std::max(1, std::min(64, (int)std::lround(std::sqrt((double)nWarps / 3.0))));
             std::vector<int> bucket(n_sets);
-            for (int r = 0; r < n_sets; ++r) bucket[byK[r]] = (int)((long long)r * nBuckets / n_sets);
+            // tuning knob HBK_SORT_MODE=<second key slot>:<its buckets>[:<k_slow buckets>]: a second bucket level (e.g. the
+            // snow degree-day factor or the quick-flow coefficient) between the k_slow buckets and the capacity order
+            int key2 = -1, nB2 = 1;
+            if (const char* mode = std::getenv("HBK_SORT_MODE")) {
+                int b1 = 0;
+                if (std::sscanf(mode, "%d:%d:%d", &key2, &nB2, &b1) >= 2 && key2 >= 0 && key2 < HBK_N_PARAMS && nB2 >= 1) {
+                    if (b1 > 0) nBuckets = b1;
+                } else {
+                    key2 = -1;
+                    nB2 = 1;
+                }
+            }
+            for (int r = 0; r < n_sets; ++r) bucket[byK[r]] = (int)((long long)r * nBuckets / n_sets) * nB2;
+            if (key2 >= 0 && nB2 > 1) {
+                std::vector<float> k2(n_sets);
+                for (int p = 0; p < n_sets; ++p) k2[p] = values[(size_t)p * HBK_N_PARAMS + key2];
+                std::vector<int> by2(e->perm);
+                std::stable_sort(by2.begin(), by2.end(), [&](int x, int y) {
+                    if (bucket[x] != bucket[y]) return bucket[x] < bucket[y];
+                    return k2[x] < k2[y];
+                });
+                // within every k_slow bucket: rank by the second key -> sub-bucket
+                int start = 0;
+                while (start < n_sets) {
+                    int end = start;
+                    while (end < n_sets && bucket[by2[end]] == bucket[by2[start]]) ++end;
+                    for (int r = start; r < end; ++r) bucket[by2[r]] += (int)((long long)(r - start) * nB2 / (end - start));
+                    start = end;
+                }
+            }
             std::stable_sort(e->perm.begin(), e->perm.end(), [&](int x, int y) {
                 if (bucket[x] != bucket[y]) return bucket[x] < bucket[y];
-                return val(x, HBK_P_CAPACITY) < val(y, HBK_P_CAPACITY);
+                return capacity[x] < capacity[y];
             });
         }
         bool identity = true;
@@ -2218,15 +2256,27 @@ int hbk_set_parameters(hbk_engine* e, int32_t n_sets, const float* values) {
         }
     }
     // [n_sets][N] -> [N][ldp]: the parameter axis is the fastest one on the device
-    std::vector<float> t((size_t)HBK_N_PARAMS * e->ldp, 0.0f);
+    // staged in page-locked memory kept by the engine (no 18 MB allocation + pageable copy per end-to-end step)
+    const size_t nT = (size_t)HBK_N_PARAMS * e->ldp;
+    if (e->paramStageN != nT) {
+        if (e->hParamStage) cudaFreeHost(e->hParamStage);
+        e->hParamStage = nullptr;
+        e->paramStageN = 0;
+        HBK_CUDA(cudaHostAlloc((void**)&e->hParamStage, sizeof(float) * nT, cudaHostAllocDefault));
+        e->paramStageN = nT;
+        std::fill(e->hParamStage, e->hParamStage + nT, 0.0f);
+    }
+    float* t = e->hParamStage;
+    for (int k = 0; k < HBK_N_PARAMS; ++k)
+        for (int p = n_sets; p < e->ldp; ++p) t[(size_t)k * e->ldp + p] = 0.0f;  // padding lanes
     for (int p = 0; p < n_sets; ++p) {
         const float* src = values + (size_t)e->perm[p] * HBK_N_PARAMS;
         for (int k = 0; k < HBK_N_PARAMS; ++k) t[(size_t)k * e->ldp + p] = src[k];
     }
-    HBK_CUDA(cudaMemcpyAsync(e->dParams, t.data(), sizeof(float) * t.size(), cudaMemcpyHostToDevice, e->stream));
+    HBK_CUDA(cudaMemcpyAsync(e->dParams, t, sizeof(float) * nT, cudaMemcpyHostToDevice, e->stream));
     HBK_CUDA(cudaStreamSynchronize(e->stream));
     if (e->st.snow_slide_kind != HBK_SNOW_SLIDE_NONE) {
-        e->hParamsT.swap(t);
+        e->hParamsT.assign(t, t + nT);
         e->latThrDirty = true;
     }
     return HBK_OK;
