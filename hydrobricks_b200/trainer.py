@@ -21,6 +21,8 @@ SOCONT_RANGES = {
     "a_snow": (2.0, 20.0), "a_ice": (2.0, 20.0), "A": (0.0, 3000.0), "k_slow_1": (1e-4, 1.0), "k_slow_2": (1e-4, 1.0),
     "k_quick": (1e-4, 1.0), "beta": (100.0, 30000.0), "percol": (0.0, 10.0), "k_snow": (1e-4, 1.0),
     "k_ice": (1e-4, 1.0), "prec_t_start": (-2.0, 2.0), "prec_t_end": (0.0, 4.0),
+    # liquid water in the snowpacks (parameters.py:444-467): refreezing factor, water holding capacity
+    "cfr": (0.0, 0.1), "whc": (0.0, 0.2), "cwh": (0.0, 0.2),
 }
 # models/socont.py:280-285 plus the splitter's transition_start < transition_end
 SOCONT_CONSTRAINTS = [("a_snow", "<", "a_ice"), ("k_slow_1", "<", "k_quick"), ("k_slow_2", "<", "k_quick"),
