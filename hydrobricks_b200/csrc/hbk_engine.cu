@@ -2991,8 +2991,27 @@ static int launchSegment(hbk_engine* e, int tBegin, int tEnd, bool writeOutputs)
     return HBK_OK;
 }
 
+static int runImpl(hbk_engine* e, bool& enqueued);
+
 int hbk_run(hbk_engine* e) {
     if (!e) return HBK_E_ARG;
+    bool enqueued = false;  // work has been put on the engine's streams and the final synchronisation was not reached
+    const int rc = runImpl(e, enqueued);
+    if (rc != HBK_OK && enqueued) {
+        // a launch / allocation error in the middle of a run: drain what is already on the streams (the getters must not
+        // read a half-written run, the next call must not race with it) and forget the run
+        const std::string msg = e->error;
+        cudaStreamSynchronize(e->stream);
+        for (auto& st : e->auxStream)
+            if (st) cudaStreamSynchronize(st);
+        cudaGetLastError();
+        e->error = msg;
+        e->ran = false;
+    }
+    return rc;
+}
+
+static int runImpl(hbk_engine* e, bool& enqueued) {
     if (!e->unitsSet) return fail(e, HBK_E_STATE, "hbk_set_units has not been called");
     if (e->P <= 0) return fail(e, HBK_E_STATE, "hbk_set_parameters has not been called");
     bool tiled = true, station = true;
@@ -3097,6 +3116,7 @@ int hbk_run(hbk_engine* e) {
         e->tiledUB = e->UB;
     }
 
+    enqueued = true;
     HBK_CUDA(cudaEventRecord(e->ev0, e->stream));
     // ModelHydro::Reset (ModelHydro.cpp:183-193): containers back to their initial state, fluxes to 0.
     const size_t nPU = (size_t)e->P * e->U;
@@ -3185,6 +3205,7 @@ int hbk_run(hbk_engine* e) {
     }
     HBK_CUDA(cudaEventRecord(e->ev1, e->stream));
     HBK_CUDA(cudaStreamSynchronize(e->stream));
+    enqueued = false;  // the run is complete: errors from here on are findings about its results
     float ms = 0;
     cudaEventElapsedTime(&ms, e->ev0, e->ev1);
     e->lastMs = ms;
