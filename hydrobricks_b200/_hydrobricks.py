@@ -984,6 +984,8 @@ class ModelHydro:
         one = np.ones_like(g)
         total = self._storage_total([("ground_water", g), ("glacier_water", gl), ("slow", one), ("slow2", one),
                                      ("quick", one)])
+        if self._cs.hbk.snow_retention:  # liquid water kept in the snowpacks: '<cover>_snowpack:water_content'
+            total += self._storage_total([("ground_snowpack_water", g), ("glacier_snowpack_water", gl)])
         if self._cs.hbk.has_glacier:
             total += float(self._engine.get_basin_state()[0].sum())
         return total

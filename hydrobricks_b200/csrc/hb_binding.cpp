@@ -381,6 +381,13 @@ PYBIND11_MODULE(_hydrobricks, m) {
                 mh.GetState(slots[k], buf.data());
                 for (int u = 0; u < U; ++u) sum += buf[u] * (k == 0 ? g[u] : (k == 1 ? gl[u] : 1.0)) * w[u];
             }
+            if (mh.compiled().st.snow_retention) {  // liquid water kept in the snowpacks: '<cover>_snowpack:water_content'
+                const int more[2] = {HBK_S_GROUND_SNOWPACK_WATER, HBK_S_GLACIER_SNOWPACK_WATER};
+                for (int k = 0; k < 2; ++k) {
+                    mh.GetState(more[k], buf.data());
+                    for (int u = 0; u < U; ++u) sum += buf[u] * (k == 0 ? g[u] : gl[u]) * w[u];
+                }
+            }
             if (mh.compiled().st.has_glacier) {
                 std::vector<double> b((size_t)P * 2);
                 mh.GetBasinState(b.data());
