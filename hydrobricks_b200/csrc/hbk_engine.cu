@@ -1410,22 +1410,42 @@ __global__ void hbkScores(const double* __restrict__ outlet, long long ldt, cons
     const int p = blockIdx.x;
     const double* q = outlet + (size_t)p * ldt;
     const double n = stats[0], mo = stats[1], sso = stats[2];
-    double a = 0, b = 0;
+    double a = 0, b = 0, ab = 0;
     for (int t = t0 + threadIdx.x; t < T; t += blockDim.x) {
         const double o = obs[t];
         if (o == o) {
             const double s = q[t];
             a += s;
             b += (s - o) * (s - o);
+            ab += fabs(s - o);
         }
     }
     const double sumS = blockSum(a, sh);
     const double sse = blockSum(b, sh);
-    if (metric == HBK_SCORE_NSE) {
-        if (threadIdx.x == 0) out[p] = 1 - sse / sso;
-        return;
-    }
+    const double sae = blockSum(ab, sh);
     const double ms = sumS / n;
+    switch (metric) {  // metrics of the first pass
+        case HBK_SCORE_NSE:
+            if (threadIdx.x == 0) out[p] = 1 - sse / sso;
+            return;
+        case HBK_SCORE_ME:
+            if (threadIdx.x == 0) out[p] = ms - mo;  // mean(s - o) over the same steps
+            return;
+        case HBK_SCORE_MAE:
+            if (threadIdx.x == 0) out[p] = sae / n;
+            return;
+        case HBK_SCORE_MSE:
+            if (threadIdx.x == 0) out[p] = sse / n;
+            return;
+        case HBK_SCORE_RMSE:
+            if (threadIdx.x == 0) out[p] = sqrt(sse / n);
+            return;
+        case HBK_SCORE_NRMSE_MEAN:
+            if (threadIdx.x == 0) out[p] = sqrt(sse / n) / mo;
+            return;
+        default:
+            break;
+    }
     double c = 0, d = 0;
     for (int t = t0 + threadIdx.x; t < T; t += blockDim.x) {
         const double o = obs[t];
@@ -1439,10 +1459,18 @@ __global__ void hbkScores(const double* __restrict__ outlet, long long ldt, cons
     const double sso2 = blockSum(d, sh);
     if (threadIdx.x == 0) {
         const double r = sso2 / sqrt(sss * sso);
-        const double cvS = sqrt(sss / (n - 1)) / ms;
-        const double cvO = sqrt(sso / (n - 1)) / mo;
-        const double g = cvS / cvO, be = ms / mo;
-        out[p] = 1 - sqrt((r - 1) * (r - 1) + (g - 1) * (g - 1) + (be - 1) * (be - 1));
+        const double be = ms / mo;
+        if (metric == HBK_SCORE_R_SQUARED) {
+            out[p] = r * r;
+        } else if (metric == HBK_SCORE_KGE_2009) {
+            const double al = sqrt(sss / (n - 1)) / sqrt(sso / (n - 1));
+            out[p] = 1 - sqrt((r - 1) * (r - 1) + (al - 1) * (al - 1) + (be - 1) * (be - 1));
+        } else {
+            const double cvS = sqrt(sss / (n - 1)) / ms;
+            const double cvO = sqrt(sso / (n - 1)) / mo;
+            const double g = cvS / cvO;
+            out[p] = 1 - sqrt((r - 1) * (r - 1) + (g - 1) * (g - 1) + (be - 1) * (be - 1));
+        }
     }
 }
 
@@ -3411,7 +3439,7 @@ int hbk_get_unconverged(hbk_engine* e, int32_t* out) {
 void* hbk_stream(hbk_engine* e) { return e ? (void*)e->stream : nullptr; }
 
 int hbk_compute_scores(hbk_engine* e, int32_t metric, const double* observed, int32_t warmup, double* out) {
-    if (!e || !observed || warmup < 0 || warmup >= e->T || (metric != HBK_SCORE_NSE && metric != HBK_SCORE_KGE_2012))
+    if (!e || !observed || warmup < 0 || warmup >= e->T || metric < 0 || metric >= HBK_N_SCORES)
         return HBK_E_ARG;
     if (!e->ran) return fail(e, HBK_E_STATE, "no completed run");
     HBK_CUDA(cudaSetDevice(e->device));

@@ -26,6 +26,8 @@ SNOW_ICE_NONE, SNOW_ICE_CONSTANT, SNOW_ICE_SWAT = 0, 1, 2
 SUBLIMATION_NONE, SUBLIMATION_CONSTANT, SUBLIMATION_PET = 0, 1, 2
 SNOW_SLIDE_NONE, SNOW_SLIDE_SKIP_GLACIERS, SNOW_SLIDE_ALL = 0, 1, 2
 RETENTION_HOLDING, RETENTION_REFREEZE, RETENTION_RAIN_TO_SNOWPACK = 1, 2, 4
+# HBK_SCORE_*: HydroErr's names of the batched objective functions of hbk_compute_scores
+SCORES = ["nse", "kge_2012", "kge_2009", "me", "mae", "mse", "rmse", "nrmse_mean", "r_squared"]
 MELT_DEGREE_DAY, MELT_DEGREE_DAY_ASPECT, MELT_TEMPERATURE_INDEX = 0, 1, 2
 MELT_KIND = {"melt:degree_day": 0, "melt:degree_day_aspect": 1, "melt:temperature_index": 2}
 # HydroUnit property "aspect_class" (ProcessMeltDegreeDayAspect.cpp:38-58) -> HBK_ASPECT_*
@@ -372,11 +374,12 @@ class Engine:
         return out
 
     def compute_scores(self, metric, observed, warmup=0, out=None, to_host=True):
-        """Batched NSE ("nse") / KGE-2012 ("kge_2012") of the last run on the device; returns float64[n_sets]
+        """Batched objective function of the last run on the device (SCORES: "nse", "kge_2012", "kge_2009", "me", "mae",
+        "mse", "rmse", "nrmse_mean", "r_squared"); returns float64[n_sets]
         (to_host=False leaves them on the device only: scores_device_pointer())."""
         obs = np.ascontiguousarray(observed, dtype=np.float64)
         assert obs.shape == (self.n_steps,)
-        kind = {"nse": 0, "kge_2012": 1}[metric] if isinstance(metric, str) else int(metric)
+        kind = SCORES.index(metric.lower()) if isinstance(metric, str) else int(metric)
         if not to_host:
             self._check(self.L.hbk_compute_scores(self.h, kind, _dptr(obs), int(warmup), None))
             return None

@@ -304,7 +304,7 @@ class Socont:
         return self.model.run_batch(matrix)
 
     def evaluate_batch(self, metric, observations, warmup=0):
-        """Objective score ("nse" | "kge_2012") of every parameter set of the last run_batch against the observed
+        """Objective score (engine.SCORES: "nse", "kge_2012", "kge_2009", "rmse", "mae", ...) of every parameter set of the last run_batch against the observed
         outlet discharge, computed on the device (python evaluation/metrics.py:40-62, trainer.py:1091-1141)."""
         return self.engine(getattr(self, "_last_batch", 1)).compute_scores(metric, observations, warmup)
 

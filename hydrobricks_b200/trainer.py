@@ -29,7 +29,10 @@ SOCONT_CONSTRAINTS = [("a_snow", "<", "a_ice"), ("k_slow_1", "<", "k_quick"), ("
                       ("k_slow_2", "<", "k_slow_1"), ("prec_t_start", "<", "prec_t_end")]
 _OPS = {"<": np.less, "lt": np.less, "<=": np.less_equal, "le": np.less_equal, ">": np.greater, "gt": np.greater,
         ">=": np.greater_equal, "ge": np.greater_equal}
-HIGHER_IS_BETTER = {"nse": True, "kge_2012": True}
+# the objective functions hbk_compute_scores has on the device (HydroErr's names) and their orientation
+# (evaluation/metrics.py:9-38: the error metrics are the ones where lower is better)
+HIGHER_IS_BETTER = {"nse": True, "kge_2012": True, "kge_2009": True, "r_squared": True, "mae": False, "mse": False,
+                    "rmse": False, "nrmse_mean": False}
 
 
 class ParameterSpace:
@@ -110,12 +113,13 @@ class BatchedMonteCarlo:
 
     model: a set-up hydrobricks_b200.models.Socont with its forcing attached; observations: observed outlet
     discharge [T] (NaN = missing); warmup: leading steps left out of the score (trainer.py `warmup`);
-    objective: "nse" | "kge_2012" (evaluation/metrics.py:40-62).
+    objective: "nse" | "kge_2012" | "kge_2009" | "r_squared" | "mae" | "mse" | "rmse" | "nrmse_mean"
+    (evaluation/metrics.py:40-62; the error metrics are minimised).
     """
 
     def __init__(self, model, space, observations, warmup=0, objective="nse", fixed=None):
         if objective not in HIGHER_IS_BETTER:
-            raise ValueError(f"objective {objective!r} is not available on the device (nse, kge_2012)")
+            raise ValueError(f"objective {objective!r} is not available on the device ({', '.join(HIGHER_IS_BETTER)})")
         self.model, self.space, self.objective, self.warmup = model, space, objective, int(warmup)
         self.observations = np.ascontiguousarray(observations, dtype=np.float64)
         self.fixed = dict(fixed or {})

@@ -326,9 +326,15 @@ void* hbk_stream(hbk_engine* e);
 /* Batched objective functions on the device (python evaluation/metrics.py:40-62 via HydroErr):
  * one score per parameter set of the last run against observed[n_steps] (NaN = missing, dropped), skipping the first
  * `warmup` steps (trainer.py:1091-1141). HBK_SCORE_NSE = 1 - sum((s-o)^2)/sum((o-mean o)^2);
- * HBK_SCORE_KGE_2012 = 1 - sqrt((r-1)^2 + (CVs/CVo-1)^2 + (mean s/mean o-1)^2), std with ddof=1.
+ * HBK_SCORE_KGE_2012 = 1 - sqrt((r-1)^2 + (CVs/CVo-1)^2 + (mean s/mean o-1)^2), std with ddof=1;
+ * HBK_SCORE_KGE_2009 the same with the ratio of the standard deviations in place of the CV ratio; the error metrics
+ * me = mean(s-o), mae = mean|s-o|, mse, rmse = sqrt(mse), nrmse_mean = rmse/mean(o); r_squared = Pearson r^2
+ * (HydroErr's names; published formulas: parity against HydroErr itself is unpinned, the package is absent).
  * out[n_sets] on the host; hbk_scores_dev gives the device copy (for NCCL gathers). */
-enum { HBK_SCORE_NSE = 0, HBK_SCORE_KGE_2012 = 1 };
+enum {
+    HBK_SCORE_NSE = 0, HBK_SCORE_KGE_2012 = 1, HBK_SCORE_KGE_2009, HBK_SCORE_ME, HBK_SCORE_MAE, HBK_SCORE_MSE, HBK_SCORE_RMSE,
+    HBK_SCORE_NRMSE_MEAN, HBK_SCORE_R_SQUARED, HBK_N_SCORES
+};
 int hbk_compute_scores(hbk_engine* e, int32_t metric, const double* observed, int32_t warmup, double* out);
 int hbk_scores_dev(hbk_engine* e, const double** ptr);
 

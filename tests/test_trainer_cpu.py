@@ -65,7 +65,7 @@ def test_monte_carlo_batches_scores_and_best():
     s = mc.evaluate({"x": np.array([0.2, 0.9, 0.1, 1.5]), "y": np.array([0.5, 0.1, 0.4, 2.0])})
     assert model.runs[-1] == 2 and np.isneginf(s[[1, 3]]).all() and np.isfinite(s[[0, 2]]).all()
     with pytest.raises(ValueError):
-        trainer.BatchedMonteCarlo(model, space, np.zeros(10), objective="rmse")
+        trainer.BatchedMonteCarlo(model, space, np.zeros(10), objective="mape")  # not on the device
 
 
 @pytest.mark.skipif(not Path("/root/reference/python/src/hydrobricks").exists(), reason="reference sources not available")
