@@ -21,6 +21,7 @@ extern "C" void hbo_flop_counts(unsigned long long* out7, int reset) {
 
 #include <algorithm>
 #include <cmath>
+#include <numeric>
 #include <cstdio>
 #include <limits>
 #include <string>
@@ -77,6 +78,12 @@ struct Process {
     float slope = 0;
     std::vector<int> outputs;
     std::vector<double> rates;
+    // capillary:hbv (ProcessCapillaryHBV.h:66-69): target soil stores and, per target, the land covers feeding it
+    std::vector<int> capTargets;
+    std::vector<std::vector<int>> capWeights;
+    // routing:hbv (ProcessRoutingHBV.h): unit-hydrograph ordinates and the delivery schedule
+    std::vector<double> uhOrd, stuh;
+    double lastMaxbas = 0, previousContent = 0, processStorage = 0;
 };
 
 struct Brick {
@@ -378,9 +385,11 @@ void BrickApplyConstraints(hbo_model& m, Brick& b, double dt) {
 }
 
 // Brick.cpp:127-135, Snowpack.cpp:58-67, Glacier.cpp:71-74
+void ProcessFinalize(hbo_model& m, Process& p);
 void BrickFinalize(hbo_model& m, Brick& b) {
     if (b.second >= 0) FinalizeContainer(m.containers[b.second]);
     FinalizeContainer(m.containers[b.water]);
+    for (int ip : b.processes) ProcessFinalize(m, m.processes[ip]);  // Brick.cpp:130-134
 }
 
 // ---- processes --------------------------------------------------------------------------------
@@ -405,6 +414,39 @@ int DayOfYear(double mjd) {
 }
 
 void StoreRates1(Process& p, double v) { p.rates.assign(1, v); }
+
+// ProcessRoutingHBV::_cumulativeWeight / _recomputeUH (ProcessRoutingHBV.cpp:118-151): triangular weighting function
+double CumulativeWeightHBV(double t, double maxbas) {
+    if (t <= 0.0) return 0.0;
+    if (t >= maxbas) return 1.0;
+    double ratio = t / maxbas;
+    if (ratio <= 0.5) return 2.0 * ratio * ratio;
+    return 1.0 - 2.0 * (1.0 - ratio) * (1.0 - ratio);
+}
+void RecomputeUH(Process& p) {
+    double maxbas = p.params[0];
+    if (maxbas < 1.0) maxbas = 1.0;  // shorter than the timestep: pass-through
+    p.lastMaxbas = p.params[0];
+    int n = static_cast<int>(std::ceil(maxbas));
+    p.uhOrd.resize(n);
+    for (int j = 1; j <= n; ++j)
+        p.uhOrd[j - 1] = CumulativeWeightHBV(static_cast<double>(j), maxbas) - CumulativeWeightHBV(static_cast<double>(j - 1), maxbas);
+    p.stuh.resize(n, 0.0);
+}
+// ProcessRoutingHBV::Finalize (ProcessRoutingHBV.cpp:85-116), after the container has been finalized
+void ProcessFinalize(hbo_model& m, Process& p) {
+    if (p.type != HBO_P_ROUTING_HBV) return;
+    Container& c = m.containers[p.container];
+    double delivered = m.fluxes[p.outputs[0]].amount;
+    double content = c.content;
+    double inflow = content - p.previousContent + delivered;
+    p.previousContent = content;
+    double carryOver = p.stuh[0] + p.uhOrd[0] * inflow - delivered;
+    for (int j = 0; j < static_cast<int>(p.stuh.size()) - 1; ++j) p.stuh[j] = p.stuh[j + 1] + p.uhOrd[j + 1] * inflow;
+    p.stuh.back() = 0.0;
+    p.stuh[0] += carryOver;
+    p.processStorage = std::accumulate(p.stuh.begin(), p.stuh.end(), 0.0);
+}
 
 void GetRates(hbo_model& m, Process& p) {
     Container& c = m.containers[p.container];
@@ -597,6 +639,57 @@ void GetRates(hbo_model& m, Process& p) {
             StoreRates1(p, cfr * ddf * (meltingTemperature - t));
             return;
         }
+        case HBO_P_INFILTRATION_HBV: {  // ProcessInfiltrationHBV.cpp:36-46
+            Container& target = m.containers[m.bricks[p.targetBrick].water];
+            double in = ContentWithChanges(c);
+            double fc = static_cast<double>(target.capacity);
+            if (in <= 0 || !(fc > 0)) {
+                StoreRates1(p, 0);
+                return;
+            }
+            double ratio = std::clamp(TargetFillingRatio(target), 0.0, 1.0);
+            StoreRates1(p, in * (1.0 - std::pow(ratio, static_cast<double>(p.params[0]))));
+            return;
+        }
+        case HBO_P_ET_HBV: {  // ProcessETHBV.cpp:47-58; params lp, et_correction_factor
+            double pet = static_cast<double>(p.params[1]) * m.Forcing(HBO_V_PET, unit);
+            double threshold = static_cast<double>(p.params[0]) * static_cast<double>(c.capacity);
+            if (threshold <= 0) {
+                StoreRates1(p, pet);
+                return;
+            }
+            double ratio = std::min(1.0, ContentWithChanges(c) / threshold);
+            StoreRates1(p, pet * ratio);
+            return;
+        }
+        case HBO_P_CAPILLARY_HBV: {  // ProcessCapillaryHBV.cpp:66-96
+            p.rates.assign(p.capTargets.size(), 0.0);
+            for (size_t i = 0; i < p.capTargets.size(); ++i) {
+                Container& target = m.containers[m.bricks[p.capTargets[i]].water];
+                if (!(static_cast<double>(target.capacity) > 0)) continue;
+                double weight = 0.0;
+                for (int ib : p.capWeights[i]) weight += m.bricks[ib].areaFraction;
+                if (p.capWeights[i].empty()) weight = 1.0;
+                double deficit = 1.0 - std::clamp(TargetFillingRatio(target), 0.0, 1.0);
+                p.rates[i] = p.params[0] * weight * deficit;
+            }
+            return;
+        }
+        case HBO_P_RUNOFF_HBV: {  // ProcessRunoffHBV.cpp:40-47; params response_factor, alpha
+            double uz = ContentWithChanges(c);
+            if (uz <= 0) {
+                StoreRates1(p, 0);
+                return;
+            }
+            StoreRates1(p, p.params[0] * std::pow(uz, 1.0 + static_cast<double>(p.params[1])));
+            return;
+        }
+        case HBO_P_ROUTING_HBV: {  // ProcessRoutingHBV.cpp:69-83
+            if (p.params[0] != p.lastMaxbas) RecomputeUH(p);
+            double in = SumIncomingFluxes(m, c);
+            StoreRates1(p, std::max(0.0, p.stuh[0]) + p.uhOrd[0] * in);
+            return;
+        }
         case HBO_P_SUBLIMATION_PET: {  // ProcessSublimationPET.cpp:46-51
             if (!ContentAccessible(m, c)) {
                 StoreRates1(p, 0);
@@ -612,7 +705,8 @@ void GetRates(hbo_model& m, Process& p) {
 
 // Process.cpp:480-487
 const std::vector<double>& GetChangeRates(hbo_model& m, Process& p) {
-    if (LessThanOrEqual(ContentWithChanges(m.containers[p.container]), 0, PRECISION)) {
+    // routing:hbv bypasses the empty-container shortcut (ProcessRoutingHBV.h:62-72)
+    if (p.type != HBO_P_ROUTING_HBV && LessThanOrEqual(ContentWithChanges(m.containers[p.container]), 0, PRECISION)) {
         p.rates.assign(p.outputs.size(), 0.0);
         return p.rates;
     }
@@ -1378,6 +1472,10 @@ void hbo_set_cover_links(hbo_model* m, int cover_brick, int generic_cover_brick,
 }
 void hbo_set_parent(hbo_model* m, int brick, int parent_brick) { m->bricks[brick].parent = parent_brick; }
 void hbo_set_target_brick(hbo_model* m, int process, int target_brick) { m->processes[process].targetBrick = target_brick; }
+void hbo_add_capillary_target(hbo_model* m, int process, int target_brick, int n_weights, const int* weight_bricks) {
+    m->processes[process].capTargets.push_back(target_brick);
+    m->processes[process].capWeights.emplace_back(weight_bricks, weight_bricks + n_weights);
+}
 // ProcessLateralSnowSlide::SetHydroUnitProperties (slope in degrees, float) + ProcessLateral::AttachFluxOutWithWeight:
 // call once per output, in output order, after hbo_process_add_output.
 void hbo_set_lateral_slope(hbo_model* m, int process, float slope_deg) { m->processes[process].slopeDeg = slope_deg; }
@@ -1517,6 +1615,13 @@ int hbo_run(hbo_model* m, double* outlet, double* records) {
         for (Flux& f : m->fluxes) {
             f.amount = 0;
             f.changeRate = nullptr;
+        }
+        for (Process& p : m->processes) {  // ProcessRoutingHBV::Reset (ProcessRoutingHBV.cpp:43-49)
+            if (p.type != HBO_P_ROUTING_HBV) continue;
+            RecomputeUH(p);
+            std::fill(p.stuh.begin(), p.stuh.end(), 0.0);
+            p.previousContent = 0.0;
+            p.processStorage = 0.0;
         }
         // LandCover::Reset (LandCover.cpp:13-19): extents back to the initial ones; ActionsManager::Reset
         for (Brick& b : m->bricks) {

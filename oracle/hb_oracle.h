@@ -50,7 +50,18 @@ enum {
     /* refreeze:degree_day (ProcessRefreezeDegreeDay.cpp): params refreezing_factor; on the snowpack's water container,
      * instantaneous snow flux back to the same snowpack; degree-day factor and melting temperature of the sibling
      * melt:degree_day process; forcing temperature */
-    HBO_P_REFREEZE_DEGREE_DAY = 16
+    HBO_P_REFREEZE_DEGREE_DAY = 16,
+    /* HBV-96 (models/hbv.py, hbv_96.py; ORACLE ONLY — the CUDA engine does not run this family):
+     * infiltration:hbv (ProcessInfiltrationHBV.cpp) params beta; et:hbv (ProcessETHBV.cpp) params lp, et_correction_factor,
+     * forcing pet; capillary:hbv (ProcessCapillaryHBV.cpp) params max_capillary_flux, one output per target soil store,
+     * weighted by the area fractions of the land covers that feed it; runoff:hbv (ProcessRunoffHBV.cpp) params
+     * response_factor, alpha; routing:hbv (ProcessRoutingHBV.cpp) params maxbas, a triangular unit hydrograph with its
+     * delivery schedule as process state */
+    HBO_P_INFILTRATION_HBV = 17,
+    HBO_P_ET_HBV = 18,
+    HBO_P_CAPILLARY_HBV = 19,
+    HBO_P_RUNOFF_HBV = 20,
+    HBO_P_ROUTING_HBV = 21
 };
 enum {
     HBO_F_TO_BRICK = 0, HBO_F_TO_BRICK_INSTANT = 1, HBO_F_TO_OUTLET = 2, HBO_F_TO_ATMOSPHERE = 3,
@@ -72,6 +83,8 @@ int hbo_add_brick(hbo_model* m, int kind, int unit /* -1 = sub-basin */, int nee
 void hbo_set_area_fraction(hbo_model* m, int brick, double fraction);
 void hbo_set_parent(hbo_model* m, int brick, int parent_brick);
 void hbo_set_target_brick(hbo_model* m, int process, int target_brick);
+/* capillary:hbv: one more target soil store of the process; weight_bricks = the land covers feeding that store */
+void hbo_add_capillary_target(hbo_model* m, int process, int target_brick, int n_weights, const int* weight_bricks);
 /* capacity: NaN = no capacity. related_snow_container: -1 = none. */
 int hbo_add_container(hbo_model* m, int brick, int content_kind, float capacity, int infinite_storage,
                       int no_melt_when_snow_cover, double initial_state);

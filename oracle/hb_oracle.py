@@ -43,6 +43,12 @@ PROC_KIND = {
     "transport:snow_slide": 14,
     "outflow:snow_holding": 15,
     "refreeze:degree_day": 16,
+    # HBV-96 (oracle only)
+    "infiltration:hbv": 17,
+    "et:hbv": 18,
+    "capillary:hbv": 19,
+    "runoff:hbv": 20,
+    "routing:hbv": 21,
 }
 PROC_PARAMS = {
     0: ["degree_day_factor", "melting_temperature"],
@@ -57,6 +63,11 @@ PROC_PARAMS = {
     14: ["coeff", "exp", "min_slope", "max_slope", "min_snow_holding_depth", "max_snow_depth"],
     15: ["water_holding_capacity"],
     16: ["refreezing_factor"],
+    17: ["beta"],
+    18: ["lp", "et_correction_factor"],
+    19: ["max_capillary_flux"],
+    20: ["response_factor", "alpha"],
+    21: ["maxbas"],
 }
 ASPECT_DDF = {"north": "degree_day_factor_n", "N": "degree_day_factor_n", "south": "degree_day_factor_s",
               "S": "degree_day_factor_s", "east": "degree_day_factor_ew", "west": "degree_day_factor_ew",
@@ -102,6 +113,7 @@ def lib():
         L.hbo_set_related_snowpack.argtypes = [c_vp, c_int, c_int]
         L.hbo_set_parent.argtypes = [c_vp, c_int, c_int]
         L.hbo_set_target_brick.argtypes = [c_vp, c_int, c_int]
+        L.hbo_add_capillary_target.argtypes = [c_vp, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int)]
         L.hbo_add_process.argtypes = [c_vp, c_int, c_int, c_int, fp, c_int, c_int, c_dbl, c_flt]
         L.hbo_add_flux.argtypes = [c_vp, c_int, c_int, c_int, c_dbl, c_int, c_int, c_int]
         L.hbo_process_add_output.argtypes = [c_vp, c_int, c_int]
@@ -403,10 +415,19 @@ class OracleModel:
             for proc in brick["processes"]:
                 ps = proc["settings"]
                 # LinkHydroUnitProcessesTargetBricks (infiltration needs its target)
-                if proc["type"] == 2:
+                if proc["type"] in (2, 17):
                     target, _ = self._find_brick(ps["outputs"][0]["target"], unit)
                     L.hbo_set_target_brick(h, proc["id"], target["id"])
-                if proc["type"] in (1, 11, 12):  # ToAtmosphere (ET, sublimation)
+                if proc["type"] == 19:
+                    # capillary:hbv links every output's target with the land covers that feed it
+                    # (ModelBuilder::LinkHydroUnitProcessesTargetBricks / FindLandCoversFeeding, ModelBuilder.cpp:340-348)
+                    for out in ps["outputs"]:
+                        target, _ = self._find_brick(out["target"], unit)
+                        feeding = [self._bricks[(b["name"], unit)]["id"] for b in brick_settings if b["is_land_cover"] and
+                                   any(o["target"] == out["target"] for pp in b["processes"] for o in pp["outputs"])]
+                        arr = (ctypes.c_int * max(len(feeding), 1))(*feeding)
+                        L.hbo_add_capillary_target(h, proc["id"], target["id"], len(feeding), arr)
+                if proc["type"] in (1, 11, 12, 18):  # ToAtmosphere (ET, sublimation)
                     fl = L.hbo_add_flux(h, F_TO_ATMOSPHERE, 0, 0, 1.0, -1, -1, unit)
                     L.hbo_process_add_output(h, proc["id"], fl)
                     self._flux_of[(bs["name"], ps["name"], unit)] = fl

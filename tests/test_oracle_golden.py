@@ -26,9 +26,11 @@ NEXT_CASES = sorted("next/" + p.stem for p in (gu.GOLDEN / "next").glob("*.npz")
 
 @pytest.mark.parametrize("name", NEXT_CASES)
 def test_oracle_matches_reference_on_options_the_engine_lacks(name):
-    """tests/golden/next: options pinned bit for bit in the oracle that the CUDA engine does not implement yet — its
-    structure compiler refuses such structures (outside the engine's parity lists). Empty at the moment: the last
-    occupants, snowpack water retention / refreezing, moved to tests/golden when the engine learnt them."""
+    """tests/golden/next: what is pinned bit for bit in the oracle but not built in the CUDA engine — its structure
+    compiler refuses such structures (outside the engine's parity lists). At the moment HBV-96 (models/hbv.py, hbv_96.py:
+    infiltration:hbv, et:hbv, capillary:hbv, runoff:hbv, routing:hbv with its unit-hydrograph schedule), generated through
+    the reference's own Python class (tools/ref_hbv_case.py); the previous occupants — snowpack water retention and
+    refreezing, HBV's snow routine — moved to tests/golden when the engine learnt them."""
     from hydrobricks_b200 import structure
 
     meta, forcing, outlet, records, _ = gu.load(name)

@@ -276,6 +276,17 @@ def snow_retention_bundles(ref):
         save(f"snow_retention_{solver}_{name}", meta, forcing, q, rec)
 
 
+def hbv_bundles(ref):
+    """HBV-96 through the reference's own Python class (tools/ref_hbv_case.py): ORACLE ONLY — the engine does not run this
+    family; the vectors go to tests/golden/next (outside the engine's parity lists)."""
+    import ref_hbv_case as rh
+
+    hbpy = refpy.load_reference_python(backend="ref")
+    for solver in ("rk4", "crank_nicolson", "euler_explicit"):
+        meta, forcing, q, rec = rh.run_reference(hbpy, ref, solver, n_units=4, n_steps=600, seed=9)
+        save(f"next/hbv96_{solver}_open", meta, forcing, q, rec)
+
+
 def two_glaciers_bundles(ref):
     """glacier_ice + glacier_debris in one unit (the engine's twin units, hbk_set_unit_twins)."""
     import ref_two_glaciers_case as rt
@@ -337,6 +348,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "rain_only":
         rain_only_bundles(ref)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "hbv":
+        hbv_bundles(ref)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "snow_retention":
         snow_retention_bundles(ref)
@@ -409,6 +423,7 @@ def main():
     threshold_splitter_bundles(ref)
     rain_only_bundles(ref)
     snow_retention_bundles(ref)
+    hbv_bundles(ref)
     two_glaciers_bundles(ref)
     two_glaciers_action_bundles(ref)
     slow_order_bundles(ref)
