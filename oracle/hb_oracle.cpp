@@ -61,6 +61,7 @@ struct Container {  // containers/WaterContainer.h:342-353
     float capacity = 0;
     bool infinite = false;
     bool noMeltWhenSnowCover = false;
+    bool allowNegative = false;  // WaterContainer::SetAllowNegativeContent (routing:gr6j's bottomless store)
     int relatedSnowpackBrick = -1;
     int overflowProcess = -1;
     std::vector<int> inputs;
@@ -84,6 +85,9 @@ struct Process {
     // routing:hbv (ProcessRoutingHBV.h): unit-hydrograph ordinates and the delivery schedule
     std::vector<double> uhOrd, stuh;
     double lastMaxbas = 0, previousContent = 0, processStorage = 0;
+    // routing:gr4j (ProcessRoutingGR4J.h): the two unit hydrographs, the routing store, the last two discharges
+    std::vector<double> uh1Ord, uh2Ord, stuh1, stuh2;
+    double gr_r = 0, gr_qr = 0, gr_qd = 0, gr_rexp = 0, gr_qrexp = 0;  // + routing:gr6j's exponential store
 };
 
 struct Brick {
@@ -148,7 +152,12 @@ struct hbo_model {
     long unconverged = 0;
     std::string error;
 
+    // interception:gr4j publishes the NET evaporative demand through the unit's PET forcing object (Forcing::UpdateValue,
+    // ProcessInterceptionGR4J.cpp:29-34) until ModelHydro::UpdateForcing refreshes it at the next step
+    std::vector<double> petOverride;
+    std::vector<int> petOverrideStep;
     double Forcing(int var, int unit) const {  // base/Forcing.cpp:12-16, TimeSeriesData.cpp:57-60
+        if (var == 2 && !petOverrideStep.empty() && petOverrideStep[unit] == cursor) return petOverride[unit];
         return forcing[var][static_cast<size_t>(cursor) * nUnits + unit];
     }
 };
@@ -298,8 +307,8 @@ void ApplyConstraints(hbo_model& m, int containerId, double timeStep) {
     double change = inputs - outputs;
     double content = ContentWithDynamicChanges(c);
 
-    // Avoid negative content
-    if (change < 0 && content + inputsStatic + change * timeStep < 0) {
+    // Avoid negative content (unless the container is allowed to go negative, WaterContainer.cpp:116-118)
+    if (!c.allowNegative && change < 0 && content + inputsStatic + change * timeStep < 0) {
         double diff = (content + inputsStatic + change * timeStep) / timeStep;
         for (double* rate : outgoingRates) {
             if (NearlyZero(*rate, EPSILON_D)) continue;
@@ -340,6 +349,7 @@ void FinalizeContainer(Container& c) {
     c.content += c.dyn + c.stat;
     c.dyn = 0;
     c.stat = 0;
+    if (c.allowNegative) return;  // WaterContainer.cpp:201-203
     if (NearlyZero(c.content, PRECISION)) {
         c.content = 0;
         return;
@@ -433,8 +443,108 @@ void RecomputeUH(Process& p) {
         p.uhOrd[j - 1] = CumulativeWeightHBV(static_cast<double>(j), maxbas) - CumulativeWeightHBV(static_cast<double>(j - 1), maxbas);
     p.stuh.resize(n, 0.0);
 }
+// helpers/GR4JFormulas.h (Perrin et al., 2003)
+double Gr4jInfiltration(double S, double Pn, double X1) {
+    if (Pn <= 0.0 || X1 <= 0.0) return 0.0;
+    double Sr = S / X1;
+    double tws = std::tanh(std::min(Pn / X1, 13.0));
+    return X1 * (1.0 - Sr * Sr) * tws / (1.0 + Sr * tws);
+}
+double Gr4jEvaporation(double S, double En, double X1) {
+    if (En <= 0.0 || X1 <= 0.0) return 0.0;
+    double Sr = S / X1;
+    double tws = std::tanh(std::min(En / X1, 13.0));
+    return S * (2.0 - Sr) * tws / (1.0 + (1.0 - Sr) * tws);
+}
+double Gr4jPercolation(double S, double X1) {
+    if (X1 <= 0.0) return 0.0;
+    double ratio = S / X1;
+    return S * (1.0 - std::pow(1.0 + (ratio * ratio * ratio * ratio) / 25.62890625, -0.25));
+}
+// ProcessRoutingGR4J::_sh1 / _sh2 / _recomputeUH (ProcessRoutingGR4J.cpp:176-216)
+double Gr4jSh1(double t, double x4) {
+    if (t <= 0.0) return 0.0;
+    if (t >= x4) return 1.0;
+    return std::pow(t / x4, 2.5);
+}
+double Gr4jSh2(double t, double x4) {
+    if (t <= 0.0) return 0.0;
+    if (t >= 2.0 * x4) return 1.0;
+    if (t < x4) return 0.5 * std::pow(t / x4, 2.5);
+    return 1.0 - 0.5 * std::pow(2.0 - t / x4, 2.5);
+}
+// helpers/GR6JFormulas.h
+double Gr6jExponentialStoreOutflow(double Rexp, double X6) {
+    if (X6 <= 0.0) return std::max(0.0, Rexp);
+    double ar = std::max(-33.0, std::min(33.0, Rexp / X6));
+    if (ar > 7.0) return Rexp + X6 / std::exp(ar);
+    if (ar < -7.0) return X6 * std::exp(ar);
+    return X6 * std::log(std::exp(ar) + 1.0);
+}
+void RecomputeUHGr4j(Process& p) {
+    double X4 = p.params[2];
+    if (X4 <= 0) X4 = 0.5;
+    int n1 = static_cast<int>(std::ceil(X4));
+    int n2 = static_cast<int>(std::ceil(2.0 * X4));
+    p.uh1Ord.resize(n1);
+    for (int j = 1; j <= n1; ++j) p.uh1Ord[j - 1] = Gr4jSh1(static_cast<double>(j), X4) - Gr4jSh1(static_cast<double>(j - 1), X4);
+    p.uh2Ord.resize(n2);
+    for (int j = 1; j <= n2; ++j) p.uh2Ord[j - 1] = Gr4jSh2(static_cast<double>(j), X4) - Gr4jSh2(static_cast<double>(j - 1), X4);
+    p.stuh1.resize(n1, 0.0);
+    p.stuh2.resize(n2, 0.0);
+}
 // ProcessRoutingHBV::Finalize (ProcessRoutingHBV.cpp:85-116), after the container has been finalized
 void ProcessFinalize(hbo_model& m, Process& p) {
+    if (p.type == HBO_P_ROUTING_GR4J) {  // ProcessRoutingGR4J::Finalize (ProcessRoutingGR4J.cpp:130-174)
+        double X2 = p.params[0], X3 = p.params[1];
+        double PR = SumIncomingFluxes(m, m.containers[p.container]);
+        double prhu1 = 0.9 * PR, prhu2 = 0.1 * PR;
+        for (int j = 0; j < static_cast<int>(p.stuh1.size()) - 1; ++j) p.stuh1[j] = p.stuh1[j + 1] + p.uh1Ord[j] * prhu1;
+        p.stuh1.back() = p.uh1Ord.back() * prhu1;
+        for (int j = 0; j < static_cast<int>(p.stuh2.size()) - 1; ++j) p.stuh2[j] = p.stuh2[j + 1] + p.uh2Ord[j] * prhu2;
+        p.stuh2.back() = p.uh2Ord.back() * prhu2;
+        double F = 0.0;
+        if (X3 > 0) {
+            double rr = p.gr_r / X3;
+            F = X2 * rr * rr * rr * std::sqrt(rr);
+        }
+        p.gr_r = std::max(0.0, p.gr_r + p.stuh1[0] + F);
+        double rr4 = 0.0;
+        if (X3 > 0) {
+            double ratio = p.gr_r / X3;
+            rr4 = ratio * ratio * ratio * ratio;
+        }
+        p.gr_qr = p.gr_r * (1.0 - std::pow(1.0 + rr4, -0.25));
+        p.gr_r -= p.gr_qr;
+        p.gr_qd = std::max(0.0, p.stuh2[0] + F);
+        return;
+    }
+    if (p.type == HBO_P_ROUTING_GR6J) {  // ProcessRoutingGR6J::Finalize (ProcessRoutingGR6J.cpp:152-212)
+        double X2 = p.params[0], X3 = p.params[1], X5 = p.params[3], X6 = p.params[4];
+        double PR = SumIncomingFluxes(m, m.containers[p.container]);
+        double prhu1 = 0.9 * PR, prhu2 = 0.1 * PR;
+        for (int j = 0; j < static_cast<int>(p.stuh1.size()) - 1; ++j) p.stuh1[j] = p.stuh1[j + 1] + p.uh1Ord[j] * prhu1;
+        if (!p.stuh1.empty()) p.stuh1.back() = p.uh1Ord.back() * prhu1;
+        for (int j = 0; j < static_cast<int>(p.stuh2.size()) - 1; ++j) p.stuh2[j] = p.stuh2[j + 1] + p.uh2Ord[j] * prhu2;
+        if (!p.stuh2.empty()) p.stuh2.back() = p.uh2Ord.back() * prhu2;
+        double F = 0.0;
+        if (X3 > 0) F = X2 * (p.gr_r / X3 - X5);
+        double uh1_out = p.stuh1.empty() ? 0.0 : p.stuh1[0];
+        double uh2_out = p.stuh2.empty() ? 0.0 : p.stuh2[0];
+        p.gr_r = std::max(0.0, p.gr_r + 0.6 * uh1_out + F);
+        double rr4 = 0.0;
+        if (X3 > 0) {
+            double ratio = p.gr_r / X3;
+            rr4 = ratio * ratio * ratio * ratio;
+        }
+        p.gr_qr = p.gr_r * (1.0 - std::pow(1.0 + rr4, -0.25));
+        p.gr_r -= p.gr_qr;
+        p.gr_rexp = p.gr_rexp + 0.4 * uh1_out + F;
+        p.gr_qrexp = Gr6jExponentialStoreOutflow(p.gr_rexp, X6);
+        p.gr_rexp -= p.gr_qrexp;
+        p.gr_qd = std::max(0.0, uh2_out + F);
+        return;
+    }
     if (p.type != HBO_P_ROUTING_HBV) return;
     Container& c = m.containers[p.container];
     double delivered = m.fluxes[p.outputs[0]].amount;
@@ -690,6 +800,94 @@ void GetRates(hbo_model& m, Process& p) {
             StoreRates1(p, std::max(0.0, p.stuh[0]) + p.uhOrd[0] * in);
             return;
         }
+        case HBO_P_INTERCEPTION_GR4J: {  // ProcessInterceptionGR4J.cpp:29-34
+            double P = ContentWithChanges(c);
+            double E = m.Forcing(HBO_V_PET, unit);
+            m.petOverride[unit] = std::max(0.0, E - P);
+            m.petOverrideStep[unit] = m.cursor;
+            StoreRates1(p, std::min(P, E));
+            return;
+        }
+        case HBO_P_PRODUCTION_GR4J: {  // ProcessProductionGR4J.cpp:29-63
+            double X1 = static_cast<double>(c.capacity);
+            if (!(X1 > 0)) {
+                StoreRates1(p, 0);
+                return;
+            }
+            double S0 = c.content;
+            double Pn = ContentWithChanges(c) - ContentWithDynamicChanges(c);
+            double En = m.Forcing(HBO_V_PET, unit);
+            double Ps = Gr4jInfiltration(S0, Pn, X1);
+            double S1 = S0 + Ps;
+            double Es = Gr4jEvaporation(S1, En, X1);
+            double S2 = S1 - Es;
+            double Perc = Gr4jPercolation(S2, X1);
+            StoreRates1(p, (Pn - Ps) + Perc);
+            return;
+        }
+        case HBO_P_ET_GR4J: {  // ProcessETGR4J.cpp:30-55
+            double En = m.Forcing(HBO_V_PET, unit);
+            double X1 = static_cast<double>(c.capacity);
+            if (En <= 0 || !(X1 > 0)) {
+                StoreRates1(p, 0);
+                return;
+            }
+            double S0 = c.content;
+            double Pn = ContentWithChanges(c) - ContentWithDynamicChanges(c);
+            double S1 = S0 + Gr4jInfiltration(S0, Pn, X1);
+            StoreRates1(p, Gr4jEvaporation(S1, En, X1));
+            return;
+        }
+        case HBO_P_ROUTING_GR4J: {  // ProcessRoutingGR4J.cpp:61-128
+            double X2 = p.params[0], X3 = p.params[1];
+            RecomputeUHGr4j(p);  // (the reference's size test always fires: harmless, the buffers keep their state)
+            double PR = SumIncomingFluxes(m, c);
+            double prhu1 = 0.9 * PR, prhu2 = 0.1 * PR;
+            double uh1_out = (p.stuh1.size() > 1 ? p.stuh1[1] : 0.0) + p.uh1Ord[0] * prhu1;
+            double uh2_out = (p.stuh2.size() > 1 ? p.stuh2[1] : 0.0) + p.uh2Ord[0] * prhu2;
+            double F = 0.0;
+            if (X3 > 0) {
+                double rr = p.gr_r / X3;
+                F = X2 * rr * rr * rr * std::sqrt(rr);
+            }
+            double r_pred = std::max(0.0, p.gr_r + uh1_out + F);
+            double rr4 = 0.0;
+            if (X3 > 0) {
+                double ratio = r_pred / X3;
+                rr4 = ratio * ratio * ratio * ratio;
+            }
+            p.gr_qr = r_pred * (1.0 - std::pow(1.0 + rr4, -0.25));
+            p.gr_qd = std::max(0.0, uh2_out + F);
+            double exchangeToStore = r_pred - (p.gr_r + uh1_out);
+            double exchangeToDirect = p.gr_qd - uh2_out;
+            double netExchange = exchangeToStore + exchangeToDirect;
+            if (netExchange != 0.0) c.stat += netExchange * m.dt;  // AddAmountToStaticContentChange
+            StoreRates1(p, p.gr_qr + p.gr_qd);
+            return;
+        }
+        case HBO_P_ROUTING_GR6J: {  // ProcessRoutingGR6J.cpp:98-150
+            double X2 = p.params[0], X3 = p.params[1], X5 = p.params[3], X6 = p.params[4];
+            double clampedX4 = p.params[2] <= 0.0 ? 0.5 : static_cast<double>(p.params[2]);
+            if (static_cast<int>(std::ceil(clampedX4)) != static_cast<int>(p.uh1Ord.size())) RecomputeUHGr4j(p);
+            double PR = SumIncomingFluxes(m, c);
+            double prhu1 = 0.9 * PR, prhu2 = 0.1 * PR;
+            double uh1_out = (p.stuh1.size() > 1 ? p.stuh1[1] : 0.0) + (p.uh1Ord.empty() ? 0.0 : p.uh1Ord[0]) * prhu1;
+            double uh2_out = (p.stuh2.size() > 1 ? p.stuh2[1] : 0.0) + (p.uh2Ord.empty() ? 0.0 : p.uh2Ord[0]) * prhu2;
+            double F = 0.0;
+            if (X3 > 0) F = X2 * (p.gr_r / X3 - X5);
+            double r_pred = std::max(0.0, p.gr_r + 0.6 * uh1_out + F);
+            double rr4 = 0.0;
+            if (X3 > 0) {
+                double ratio = r_pred / X3;
+                rr4 = ratio * ratio * ratio * ratio;
+            }
+            p.gr_qr = r_pred * (1.0 - std::pow(1.0 + rr4, -0.25));
+            double rexp_pred = p.gr_rexp + 0.4 * uh1_out + F;
+            p.gr_qrexp = Gr6jExponentialStoreOutflow(rexp_pred, X6);
+            p.gr_qd = std::max(0.0, uh2_out + F);
+            StoreRates1(p, std::max(0.0, p.gr_qr + p.gr_qrexp + p.gr_qd));
+            return;
+        }
         case HBO_P_SUBLIMATION_PET: {  // ProcessSublimationPET.cpp:46-51
             if (!ContentAccessible(m, c)) {
                 StoreRates1(p, 0);
@@ -705,8 +903,8 @@ void GetRates(hbo_model& m, Process& p) {
 
 // Process.cpp:480-487
 const std::vector<double>& GetChangeRates(hbo_model& m, Process& p) {
-    // routing:hbv bypasses the empty-container shortcut (ProcessRoutingHBV.h:62-72)
-    if (p.type != HBO_P_ROUTING_HBV && LessThanOrEqual(ContentWithChanges(m.containers[p.container]), 0, PRECISION)) {
+    // routing:hbv and routing:gr6j bypass the empty-container shortcut (ProcessRoutingHBV.h:62-72, ProcessRoutingGR6J.cpp:91-96)
+    if (p.type != HBO_P_ROUTING_HBV && p.type != HBO_P_ROUTING_GR6J && LessThanOrEqual(ContentWithChanges(m.containers[p.container]), 0, PRECISION)) {
         p.rates.assign(p.outputs.size(), 0.0);
         return p.rates;
     }
@@ -1615,6 +1813,16 @@ int hbo_run(hbo_model* m, double* outlet, double* records) {
         for (Flux& f : m->fluxes) {
             f.amount = 0;
             f.changeRate = nullptr;
+        }
+        m->petOverride.assign(m->nUnits, 0.0);
+        m->petOverrideStep.assign(m->nUnits, -1);
+        for (Process& p : m->processes) {  // ProcessRoutingGR4J::Reset (ProcessRoutingGR4J.cpp:33-42)
+            if (p.type != HBO_P_ROUTING_GR4J && p.type != HBO_P_ROUTING_GR6J) continue;
+            RecomputeUHGr4j(p);
+            std::fill(p.stuh1.begin(), p.stuh1.end(), 0.0);
+            std::fill(p.stuh2.begin(), p.stuh2.end(), 0.0);
+            p.gr_r = p.gr_qr = p.gr_qd = p.gr_rexp = p.gr_qrexp = 0.0;
+            if (p.type == HBO_P_ROUTING_GR6J) m->containers[p.container].allowNegative = true;  // ProcessRoutingGR6J.cpp:28
         }
         for (Process& p : m->processes) {  // ProcessRoutingHBV::Reset (ProcessRoutingHBV.cpp:43-49)
             if (p.type != HBO_P_ROUTING_HBV) continue;

@@ -61,7 +61,19 @@ enum {
     HBO_P_ET_HBV = 18,
     HBO_P_CAPILLARY_HBV = 19,
     HBO_P_RUNOFF_HBV = 20,
-    HBO_P_ROUTING_HBV = 21
+    HBO_P_ROUTING_HBV = 21,
+    /* GR4J (models/gr4j.py; ORACLE ONLY): interception:gr4j (publishes the net evaporative demand through the unit's PET
+     * forcing, ProcessInterceptionGR4J.cpp), production:gr4j and et:gr4j on the production store (helpers/GR4JFormulas.h),
+     * routing:gr4j params exchange_factor, routing_capacity, uh_base_time (two unit hydrographs, the routing store and the
+     * groundwater exchange as process state, ProcessRoutingGR4J.cpp) */
+    HBO_P_INTERCEPTION_GR4J = 22,
+    HBO_P_PRODUCTION_GR4J = 23,
+    HBO_P_ET_GR4J = 24,
+    HBO_P_ROUTING_GR4J = 25,
+    /* GR6J (models/gr6j.py): routing:gr6j params exchange_factor, routing_capacity, uh_base_time, exchange_threshold,
+     * exp_store_coeff — GR4J's routing with a 60/40 split into the routing store and a bottomless exponential store
+     * (ProcessRoutingGR6J.cpp, helpers/GR6JFormulas.h); its container may go negative */
+    HBO_P_ROUTING_GR6J = 26
 };
 enum {
     HBO_F_TO_BRICK = 0, HBO_F_TO_BRICK_INSTANT = 1, HBO_F_TO_OUTLET = 2, HBO_F_TO_ATMOSPHERE = 3,

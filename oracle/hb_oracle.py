@@ -49,6 +49,12 @@ PROC_KIND = {
     "capillary:hbv": 19,
     "runoff:hbv": 20,
     "routing:hbv": 21,
+    # GR4J (oracle only)
+    "interception:gr4j": 22,
+    "production:gr4j": 23,
+    "et:gr4j": 24,
+    "routing:gr4j": 25,
+    "routing:gr6j": 26,
 }
 PROC_PARAMS = {
     0: ["degree_day_factor", "melting_temperature"],
@@ -68,6 +74,8 @@ PROC_PARAMS = {
     19: ["max_capillary_flux"],
     20: ["response_factor", "alpha"],
     21: ["maxbas"],
+    25: ["exchange_factor", "routing_capacity", "uh_base_time"],
+    26: ["exchange_factor", "routing_capacity", "uh_base_time", "exchange_threshold", "exp_store_coeff"],
 }
 ASPECT_DDF = {"north": "degree_day_factor_n", "N": "degree_day_factor_n", "south": "degree_day_factor_s",
               "S": "degree_day_factor_s", "east": "degree_day_factor_ew", "west": "degree_day_factor_ew",
@@ -427,7 +435,7 @@ class OracleModel:
                                    any(o["target"] == out["target"] for pp in b["processes"] for o in pp["outputs"])]
                         arr = (ctypes.c_int * max(len(feeding), 1))(*feeding)
                         L.hbo_add_capillary_target(h, proc["id"], target["id"], len(feeding), arr)
-                if proc["type"] in (1, 11, 12, 18):  # ToAtmosphere (ET, sublimation)
+                if proc["type"] in (1, 11, 12, 18, 22, 24):  # ToAtmosphere (ET, sublimation, interception)
                     fl = L.hbo_add_flux(h, F_TO_ATMOSPHERE, 0, 0, 1.0, -1, -1, unit)
                     L.hbo_process_add_output(h, proc["id"], fl)
                     self._flux_of[(bs["name"], ps["name"], unit)] = fl

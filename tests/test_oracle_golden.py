@@ -28,8 +28,9 @@ NEXT_CASES = sorted("next/" + p.stem for p in (gu.GOLDEN / "next").glob("*.npz")
 def test_oracle_matches_reference_on_options_the_engine_lacks(name):
     """tests/golden/next: what is pinned bit for bit in the oracle but not built in the CUDA engine — its structure
     compiler refuses such structures (outside the engine's parity lists). At the moment HBV-96 (models/hbv.py, hbv_96.py:
-    infiltration:hbv, et:hbv, capillary:hbv, runoff:hbv, routing:hbv with its unit-hydrograph schedule), generated through
-    the reference's own Python class (tools/ref_hbv_case.py); the previous occupants — snowpack water retention and
+    infiltration:hbv, et:hbv, capillary:hbv, runoff:hbv, routing:hbv with its unit-hydrograph schedule) and GR4J / GR6J
+    (models/gr4j.py, gr6j.py: interception, production store, the two unit hydrographs, routing and exponential stores),
+    generated through the reference's own Python classes (tools/ref_hbv_case.py, ref_gr4j_case.py); the previous occupants — snowpack water retention and
     refreezing, HBV's snow routine — moved to tests/golden when the engine learnt them."""
     from hydrobricks_b200 import structure
 

@@ -287,6 +287,16 @@ def hbv_bundles(ref):
         save(f"next/hbv96_{solver}_open", meta, forcing, q, rec)
 
 
+def gr_bundles(ref):
+    """GR4J / GR6J through the reference's own Python classes (tools/ref_gr4j_case.py): ORACLE ONLY, tests/golden/next."""
+    import ref_gr4j_case as rg
+
+    hbpy = refpy.load_reference_python(backend="ref")
+    for model in ("GR4J", "GR6J"):
+        meta, forcing, q, rec = rg.run_reference(hbpy, ref, model=model, n_units=4, n_steps=600, seed=9)
+        save(f"next/{model.lower()}_open", meta, forcing, q, rec)
+
+
 def two_glaciers_bundles(ref):
     """glacier_ice + glacier_debris in one unit (the engine's twin units, hbk_set_unit_twins)."""
     import ref_two_glaciers_case as rt
@@ -351,6 +361,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "hbv":
         hbv_bundles(ref)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "gr":
+        gr_bundles(ref)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "snow_retention":
         snow_retention_bundles(ref)
@@ -424,6 +437,7 @@ def main():
     rain_only_bundles(ref)
     snow_retention_bundles(ref)
     hbv_bundles(ref)
+    gr_bundles(ref)
     two_glaciers_bundles(ref)
     two_glaciers_action_bundles(ref)
     slow_order_bundles(ref)
