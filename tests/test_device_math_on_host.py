@@ -267,3 +267,58 @@ def test_fast_bisection_replays_the_reference_halving(name, emul, emul_plain_bis
     assert (q_fast == q_plain).mean() > 0.99  # bit-identical but for the rare midpoint within round-off of the root
     assert n_plain > 2.5 * n_fast, (n_plain, n_fast)
     _close(q_fast, outlet)
+
+
+@pytest.mark.parametrize("kind", ["melt:degree_day_aspect", "melt:temperature_index"])
+@pytest.mark.parametrize("solver", ["rk4", "crank_nicolson"])
+def test_snow_retention_with_the_melt_variants_on_host(kind, solver, emul):
+    """Liquid water kept in the snowpacks (outflow:snow_holding, no refreezing: that one needs melt:degree_day) together
+    with melt:degree_day_aspect / melt:temperature_index, a combination no golden covers: the device's retention step
+    (snowpackStepRetention) takes its degree-day factor from the same per-unit / per-step slots as the plain step; against
+    the oracle restatement (pinned on each of the two features separately)."""
+    import sys
+    sys.path.insert(0, str(gu.GOLDEN.parent.parent / "tools"))
+    import ref_melt_cases as rm
+    from hydrobricks_b200 import engine as _e
+    from hydrobricks_b200 import models
+    from oracle import hb_oracle
+
+    m0, units, forcing = rm.build("python", kind, solver, glacier=True, nsoil=1, n_units=6, n_steps=500, seed=23)
+    covers = ["ground", "glacier"]
+    m = models.Socont(solver=solver, soil_storage_nb=1, surface_runoff="socont_runoff", land_cover_names=covers,
+                      land_cover_types=covers, snow_melt_process=kind, record_all=True, glacier_infinite_storage=False,
+                      snow_water_retention_process="outflow:snow_holding", rain_to_snowpack=True, backend="python")
+    s = m.settings
+    for st in m0.settings.get_structure():  # the melt-case tool's parameter values
+        for el in st["hydro_unit_bricks"] + st["sub_basin_bricks"] + st["hydro_unit_splitters"]:
+            for p in el.get("parameters", []):
+                if p["name"] not in ("infinite_storage", "no_melt_when_snow_cover"):
+                    assert s.set_parameter_value(el["name"], p["name"], p["value"])
+            for proc in el.get("processes", []):
+                for p in proc["parameters"]:
+                    assert s.set_parameter_value(el["name"], p["name"], p["value"])
+    assert s.set_parameter_value("type:snowpack", "water_holding_capacity", 0.18)
+    s.set_timer("1981-01-01", str(np.datetime64("1981-01-01") + np.timedelta64(499, "D")), 1, "day")
+    meta = {"structures": s.get_structure(), "units": units, "solver": solver}
+    om = hb_oracle.OracleModel(meta["structures"], units, solver, 500)
+    for k, v in forcing.items():
+        om.set_forcing(k, v)
+    for label in ("slow_reservoir:water_content", "ground_snowpack:snow_content", "glacier:ice_content"):
+        om.record(label)
+    q_ref = om.run()
+    forcing = dict(forcing)
+    radiation = forcing.pop("solar_radiation", None)
+    aspect = np.array([_e.ASPECT[u["aspect_class"]] for u in units], dtype=np.int32)
+    if radiation is not None:
+        radiation = np.ascontiguousarray(radiation, dtype=np.float64)
+    emul.hbk_emul_set_melt_inputs.argtypes = [ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double)]
+    emul.hbk_emul_set_melt_inputs.restype = None
+    emul.hbk_emul_set_melt_inputs(aspect.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                  radiation.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) if radiation is not None else None)
+    cs, q, rec, _ = run_emul(emul, meta, forcing)
+    assert cs.hbk.snow_retention == (_e.RETENTION_HOLDING | _e.RETENTION_RAIN_TO_SNOWPACK)
+    _close(q, q_ref)
+    _close(rec["slow"], om.records["slow_reservoir:water_content"])
+    _close(rec["snow"], om.records["ground_snowpack:snow_content"])
+    _close(rec["ice"], om.records["glacier:ice_content"])
+    assert q_ref.max() > 0
