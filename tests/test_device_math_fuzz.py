@@ -87,3 +87,23 @@ def test_fast_arithmetic_variant_loses_the_non_converging_regime(emul_fast):  # 
         else:
             beyond += worst > 1.0
     assert beyond > 0
+
+
+@pytest.mark.parametrize("solver", ["rk4", "heun_explicit", "euler_explicit", "crank_nicolson"])
+def test_snow_retention_fuzz(solver, emul):  # noqa: F811
+    """Liquid water in the snowpacks over the parameter space: holding capacity 0-0.2, refreezing factor 0-0.1 (two cases
+    out of three), the rain through the snowpack (one out of two), with / without a glacier cover, soil capacities down to
+    0 — snowpackStepRetention against the oracle's outflow:snow_holding / refreeze:degree_day (pinned on the reference's
+    goldens snow_retention_*). Same rule as above: inside the bar wherever the reference's sweep converges."""
+    converged = 0
+    for seed in range(24):
+        meta, forcing, om, vals = fuzz_cases.run_oracle(seed, solver, retention=True)
+        _, q, rec, _ = run_emul(emul, meta, forcing)
+        worst = max(_excess(q, om.outlet), _excess(rec["slow"], om.records["slow_reservoir:water_content"]),
+                    _excess(rec["snow"], om.records["ground_snowpack:snow_content"]))
+        if om.unconverged == 0:
+            converged += 1
+            assert worst <= 1.0, f"seed {seed} ({vals}): {worst:.3g} x the tolerance with a converged sweep"
+        else:
+            assert float(vals["A"]) < 50.0, f"seed {seed}: non-converged sweep at A = {vals['A']}"
+    assert converged >= 14

@@ -154,3 +154,22 @@ def test_oracle_two_day_step_bit_exact_against_compiled_reference(solver):
     assert np.array_equal(om.run(), q_ref)
     for label, r in rec.items():
         assert np.array_equal(om.records[label], r, equal_nan=True), label
+
+
+@pytest.mark.parametrize("solver", ["rk4", "crank_nicolson"])
+def test_oracle_snow_retention_fuzz_bit_exact_against_compiled_reference(solver):
+    """The randomised snowpack-retention cases of tests/test_device_math_fuzz.py (holding / refreezing / rain through the
+    snowpack, whc and cfr over their ranges, 1-2 soil stores, both quick-flow laws, soil capacities down to 0) through the
+    compiled reference core: the oracle those device-arithmetic checks lean on is bit-exact there too."""
+    import fuzz_cases
+    import make_goldens as mg
+    import refpy
+
+    ref = refpy.load_extension("ref")
+    ref.init()
+    for seed in range(12):
+        m, units, forcing, vals = fuzz_cases.case(seed, solver, backend=ref, retention=True)
+        m.settings.set_timer("1981-01-01", str(np.datetime64("1981-01-01") + np.timedelta64(fuzz_cases.T - 1, "D")), 1, "day")
+        q_ref, _ = mg.run_ref_module(ref, m.settings, units, forcing)
+        _, _, om, _ = fuzz_cases.run_oracle(seed, solver, retention=True)
+        assert np.array_equal(om.outlet, np.asarray(q_ref)), f"seed {seed} ({vals})"

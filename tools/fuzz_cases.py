@@ -18,7 +18,10 @@ sys.path.insert(0, str(ROOT))
 U, T = 5, 500
 
 
-def case(seed, solver, backend="python"):
+def case(seed, solver, backend="python", retention=False):
+    """`retention`: liquid water kept in the snowpacks (outflow:snow_holding), refrozen (refreeze:degree_day) for two
+    cases out of three and with the rain routed through the snowpack for one out of two, whc / cfr drawn over the
+    reference's HBV ranges (models/hbv.py:367-370)."""
     import bench
     from hydrobricks_b200 import models
 
@@ -31,7 +34,10 @@ def case(seed, solver, backend="python"):
     p2, t2, e2 = bench.spatialise(units, precip, temp, pet)
     covers = ["ground", "glacier"] if glacier else ["ground"]
     m = models.Socont(solver=solver, soil_storage_nb=nsoil, surface_runoff=quick, land_cover_names=covers,
-                      land_cover_types=covers, backend=backend)
+                      land_cover_types=covers, backend=backend,
+                      **({"snow_water_retention_process": "outflow:snow_holding",
+                          "snow_refreezing_process": "refreeze:degree_day" if seed % 3 else None,
+                          "rain_to_snowpack": (seed // 3) % 2 == 1} if retention else {}))
     vals = {"a_snow": rng.uniform(2, 20), "A": rng.choice([0.0, rng.uniform(0, 50), rng.uniform(0, 3000)]),
             "k_slow_1": 10 ** rng.uniform(-4, 0), "prec_t_start": rng.uniform(-2, 1)}
     vals["prec_t_end"] = vals["prec_t_start"] + rng.uniform(0.1, 3)
@@ -43,6 +49,10 @@ def case(seed, solver, backend="python"):
         vals.update({"percol": rng.uniform(0, 10), "k_slow_2": 10 ** rng.uniform(-4, 0)})
     if glacier:
         vals.update({"a_ice": rng.uniform(2, 20), "k_snow": 10 ** rng.uniform(-3, 0), "k_ice": 10 ** rng.uniform(-3, 0)})
+    if retention:
+        vals["whc"] = rng.uniform(0, 0.2)
+        if seed % 3:
+            vals["cfr"] = rng.uniform(0, 0.1)
     for alias, v in vals.items():
         comp, name = m.aliases[alias]
         assert m.settings.set_parameter_value(comp, name, float(v)), alias
@@ -50,15 +60,17 @@ def case(seed, solver, backend="python"):
     return m, units, forcing, vals
 
 
-def run_oracle(seed, solver):
+def run_oracle(seed, solver, retention=False):
     from oracle import hb_oracle
 
-    m, units, forcing, vals = case(seed, solver)
+    m, units, forcing, vals = case(seed, solver, retention=retention)
     structures = m.settings.get_structure()
     om = hb_oracle.OracleModel(structures, units, solver, T)
     for k, v in forcing.items():
         om.set_forcing(k, v)
     om.record("slow_reservoir:water_content")
+    if retention:
+        om.record("ground_snowpack:snow_content")
     om.run()
     return {"structures": structures, "units": units, "solver": solver}, forcing, om, vals
 
