@@ -8,8 +8,10 @@ ParameterSet's constraints and ranges hold (trainer.py:934-964), `simulation()` 
 Here the same three steps are batched: `ParameterSpace.sample()` draws n sets with the same rejection rule,
 `Socont.run_sets()` integrates them in one `hbk_run`, and the device scores every set (`hbk_compute_scores`), so only
 n scores travel back. SPOTPY itself is not in this image; its Monte-Carlo sampler — the one the reference's
-`examples/basics/analyse_mc_socont_parallel.py` uses — is what `BatchedMonteCarlo` restates. Samplers that propose
-one set from the previous score (SCE-UA, DREAM …) can use `evaluate()` with whatever population they hold.
+`examples/basics/analyse_mc_socont_parallel.py` uses — is what `BatchedMonteCarlo` restates. SCE-UA, the algorithm most of the reference's examples calibrate with
+(`calibrate(spot_setup, "sceua", …)`, examples/basics/calibrate_sceua_socont.py), is restated from the published algorithm
+in `BatchedSceUa`: its complexes evolve side by side, one launch per evolution step. Other samplers that propose sets from
+previous scores (DREAM …) can use `evaluate()` with whatever population they hold.
 """
 from __future__ import annotations
 
@@ -161,3 +163,117 @@ class BatchedMonteCarlo:
         finite = np.where(np.isnan(self.scores), -np.inf if HIGHER_IS_BETTER[self.objective] else np.inf, self.scores)
         i = int(np.argmax(finite) if HIGHER_IS_BETTER[self.objective] else np.argmin(finite))
         return {name: float(v[i]) for name, v in self.parameters.items()}, float(self.scores[i])
+
+
+class BatchedSceUa(BatchedMonteCarlo):
+    """Shuffled complex evolution (SCE-UA; Duan, Sorooshian & Gupta, Water Resour. Res. 28(4) 1992 and J. Hydrol. 158, 1994)
+    with its complexes evolved SIDE BY SIDE — what `calibrate(spot_setup, "sceua", repetitions, ngs=…)` does one model run
+    at a time through SPOTPY (reference trainer.py:1272-1401; SPOTPY is absent from this image, so this follows the
+    published algorithm with SPOTPY's argument names and defaults, not its code).
+
+    The `ngs` complexes of a shuffling loop are independent: at each of the 2n+1 evolution steps every complex proposes
+    its reflection point, its contraction point and a random point, and the engine integrates all of them in ONE launch
+    (3 x ngs sets); each complex then keeps the first of the three that the algorithm would have accepted. The trajectory
+    is the sequential algorithm's — `speculative=False` evaluates only what is needed, in up to three launches per step,
+    and gives the same result — and only the evaluations the sequential algorithm would have made count against
+    `repetitions`. On the batched engine a launch of 60 sets costs what a launch of one does, so `ngs` can be raised to
+    hundreds of complexes for the price of one.
+    """
+
+    ALPHA, BETA = 1.0, 0.5  # reflection and contraction coefficients of the competitive complex evolution
+
+    def _cost(self, values):
+        scores = self.evaluate(values)
+        for name in self.space.names:
+            self._drawn[name].append(np.asarray(values[name], dtype=np.float64))
+        self._scores.append(scores)
+        self.launches += 1
+        cost = -scores if HIGHER_IS_BETTER[self.objective] else scores.copy()
+        return np.where(np.isnan(cost), np.inf, cost)
+
+    def _as_values(self, x):
+        return {name: np.ascontiguousarray(x[:, j]) for j, name in enumerate(self.space.names)}
+
+    def run(self, repetitions, ngs=20, kstop=100, pcento=1e-7, peps=1e-7, seed=0, speculative=True):
+        """repetitions: evaluation budget; ngs: number of complexes; kstop / pcento: stop when the best cost changed by
+        less than pcento percent over kstop shuffling loops; peps: stop when the population's normalised geometric range
+        falls below it. Returns the best set and its score; `evaluations`, `launches`, `loops` and `stop_reason` say how
+        it got there, `parameters` / `scores` hold every set that was run (SPOTPY's database)."""
+        names = self.space.names
+        n = len(names)
+        lo = np.array([self.space.ranges[k][0] for k in names])
+        hi = np.array([self.space.ranges[k][1] for k in names])
+        span = np.where(hi > lo, hi - lo, 1.0)
+        ngs, npg, nps = int(ngs), 2 * n + 1, n + 1
+        nspl, npt = npg, int(ngs) * (2 * n + 1)
+        rng = np.random.default_rng(seed)
+        self._drawn, self._scores = {name: [] for name in names}, []
+        self.launches = self.loops = 0
+
+        first = self.space.sample(npt, rng)
+        x = np.column_stack([first[k] for k in names])
+        f = self._cost(first)
+        self.evaluations = npt
+        order = np.argsort(f, kind="stable")
+        x, f = x[order], f[order]
+        history = [f[0]]
+        self.stop_reason = "repetitions"
+        # sub-complex membership: the triangular distribution that favours the better points of a complex
+        weights = 2.0 * (npg - np.arange(npg)) / (npg * (npg + 1.0))
+        while self.evaluations < int(repetitions):
+            cx = np.stack([x[k::ngs] for k in range(ngs)])  # [ngs, npg, n]: complex k holds the points k, k + ngs, …
+            cf = np.stack([f[k::ngs] for k in range(ngs)])
+            for _ in range(nspl):
+                members = np.stack([np.sort(rng.choice(npg, size=nps, replace=False, p=weights)) for _ in range(ngs)])
+                k_idx = np.arange(ngs)
+                worst = members[:, -1]
+                sw, fw = cx[k_idx, worst], cf[k_idx, worst]
+                centroid = np.stack([cx[k, members[k, :-1]].mean(axis=0) for k in range(ngs)])
+                random_point = self.space.sample(ngs, rng)
+                random_point = np.column_stack([random_point[k] for k in names])
+                reflection = centroid + self.ALPHA * (centroid - sw)
+                outside = ((reflection < lo) | (reflection > hi)).any(axis=1)
+                reflection[outside] = random_point[outside]  # a reflection that leaves the feasible space: mutation
+                contraction = sw + self.BETA * (centroid - sw)
+                if speculative:
+                    cost = self._cost(self._as_values(np.concatenate([reflection, contraction, random_point])))
+                    f_refl, f_contr, f_rand = cost[:ngs], cost[ngs:2 * ngs], cost[2 * ngs:]
+                else:
+                    f_refl = self._cost(self._as_values(reflection))
+                    f_contr, f_rand = np.full(ngs, np.inf), np.full(ngs, np.inf)
+                    need = f_refl > fw
+                    if need.any():
+                        f_contr[need] = self._cost(self._as_values(contraction[need]))
+                        need = need & (f_contr > fw)
+                        if need.any():
+                            f_rand[need] = self._cost(self._as_values(random_point[need]))
+                take_refl = f_refl <= fw
+                take_contr = ~take_refl & (f_contr <= fw)
+                take_rand = ~take_refl & ~take_contr
+                new_x = np.where(take_refl[:, None], reflection, np.where(take_contr[:, None], contraction, random_point))
+                new_f = np.where(take_refl, f_refl, np.where(take_contr, f_contr, f_rand))
+                self.evaluations += int(ngs + (~take_refl).sum() + take_rand.sum())
+                cx[k_idx, worst], cf[k_idx, worst] = new_x, new_f
+                inner = np.argsort(cf, axis=1, kind="stable")
+                cx, cf = np.take_along_axis(cx, inner[:, :, None], axis=1), np.take_along_axis(cf, inner, axis=1)
+            for k in range(ngs):  # back into the population, then shuffle by sorting it as a whole
+                x[k::ngs], f[k::ngs] = cx[k], cf[k]
+            order = np.argsort(f, kind="stable")
+            x, f = x[order], f[order]
+            self.loops += 1
+            history.append(f[0])
+            spread = (x.max(axis=0) - x.min(axis=0)) / span
+            if np.exp(np.mean(np.log(np.maximum(spread, 1e-300)))) < peps:
+                self.stop_reason = "parameter space converged (peps)"
+                break
+            if len(history) > kstop:
+                recent = np.array(history[-kstop - 1:])
+                scale = np.mean(np.abs(recent))
+                if scale == 0 or abs(recent[-1] - recent[0]) * 100.0 / scale < pcento:
+                    self.stop_reason = "objective converged (kstop, pcento)"
+                    break
+        self.parameters = {name: np.concatenate(v) for name, v in self._drawn.items()}
+        self.scores = np.concatenate(self._scores)
+        del self._drawn, self._scores
+        best_score = -f[0] if HIGHER_IS_BETTER[self.objective] else f[0]
+        return {name: float(x[0, j]) for j, name in enumerate(names)}, float(best_score)

@@ -86,3 +86,70 @@ def test_space_from_the_reference_parameter_set():
     assert (v["k_slow_2"] < v["k_slow_1"]).all()
     for name in space.names:
         assert trainer.SOCONT_RANGES[name] == space.ranges[name]
+
+
+class _FakeModelN:
+    """A model whose score is an analytic function of its parameter sets (so the optimiser can be checked on CPU)."""
+
+    def __init__(self, names, score):
+        self.names, self.score, self.runs = list(names), score, []
+
+    def parameter_matrix(self, sets, n):
+        return np.column_stack([np.asarray(sets[k], dtype=np.float64) for k in self.names])
+
+    def run_sets(self, matrix):
+        self.runs.append(len(matrix))
+        self._m = matrix
+
+    def evaluate_batch(self, metric, obs, warmup):
+        return self.score(self._m)
+
+
+def test_sceua_evolves_its_complexes_side_by_side():
+    """Shuffled complex evolution on the batched engine: every evolution step of all complexes is ONE launch of 3 x ngs
+    candidate sets; the speculative launches change how many launches there are, not the trajectory."""
+    names = ["a", "b", "c", "d"]
+    target = np.array([0.3, 0.7, 0.45, 0.9])
+
+    def score(m):  # a curved valley (Rosenbrock-like) with its maximum 1 at `target`
+        z = (m - target) * 4
+        return 1.0 - np.sum((z[:, 1:] - z[:, :-1] ** 2) ** 2 + z[:, :-1] ** 2, axis=1) - z[:, -1] ** 2
+
+    space = trainer.ParameterSpace({k: (0.0, 1.0) for k in names}, [("a", "<", "b")])
+    ngs, n = 6, len(names)
+    model = _FakeModelN(names, score)
+    sce = trainer.BatchedSceUa(model, space, np.zeros(4), objective="nse")
+    best, best_score = sce.run(4000, ngs=ngs, seed=5)
+    assert best_score > 1 - 1e-4 and np.abs(np.array([best[k] for k in names]) - target).max() < 0.02
+    assert best["a"] < best["b"] and best_score == sce.scores.max()
+    npg = 2 * n + 1
+    assert model.runs[0] == ngs * npg  # the initial population in one launch
+    assert sce.launches == 1 + sce.loops * npg == len(model.runs)  # then one launch per evolution step
+    assert all(r <= 3 * ngs for r in model.runs[1:]) and max(model.runs[1:]) > 2 * ngs  # (sets outside the constraint do not run)
+    assert sce.evaluations <= len(sce.scores) and sce.evaluations >= ngs * npg + sce.loops * npg * ngs
+    assert len(sce.scores) == sum(len(v) for v in [sce.parameters["a"]]) == ngs * npg + sce.loops * npg * 3 * ngs
+
+    # the same trajectory without speculation: fewer sets run, up to three launches per step, same answer
+    model2 = _FakeModelN(names, score)
+    seq = trainer.BatchedSceUa(model2, space, np.zeros(4), objective="nse")
+    best2, score2 = seq.run(4000, ngs=ngs, seed=5, speculative=False)
+    assert best2 == best and score2 == best_score and seq.evaluations == sce.evaluations and seq.loops == sce.loops
+    assert seq.launches > sce.launches and len(seq.scores) <= seq.evaluations < len(sce.scores)
+
+
+def test_sceua_minimises_error_metrics_and_stops_on_convergence():
+    names = ["x", "y"]
+    model = _FakeModelN(names, lambda m: np.sqrt((m[:, 0] - 0.25) ** 2 + (m[:, 1] - 0.6) ** 2))
+    space = trainer.ParameterSpace({"x": (0.0, 1.0), "y": (0.0, 1.0)})
+    sce = trainer.BatchedSceUa(model, space, np.zeros(4), objective="rmse")
+    best, err = sce.run(100000, ngs=4, seed=1, peps=1e-4)
+    assert sce.stop_reason.startswith("parameter space converged") and sce.evaluations < 100000
+    assert err < 1e-3 and abs(best["x"] - 0.25) < 1e-3 and abs(best["y"] - 0.6) < 1e-3 and err == sce.scores.min()
+    # the budget ends the search when nothing converges first
+    sce2 = trainer.BatchedSceUa(_FakeModelN(names, model.score), space, np.zeros(4), objective="rmse")
+    sce2.run(60, ngs=4, seed=1)
+    assert sce2.stop_reason == "repetitions" and sce2.loops >= 1
+    # a flat objective stops on kstop / pcento
+    flat = trainer.BatchedSceUa(_FakeModelN(names, lambda m: np.ones(len(m))), space, np.zeros(4), objective="rmse")
+    flat.run(100000, ngs=2, seed=0, kstop=3, peps=0.0)
+    assert flat.stop_reason.startswith("objective converged")
