@@ -165,6 +165,23 @@ class BatchedMonteCarlo:
         return {name: float(v[i]) for name, v in self.parameters.items()}, float(self.scores[i])
 
 
+class BatchedLatinHypercube(BatchedMonteCarlo):
+    """Latin-hypercube sampling (SPOTPY's `lhs`): every parameter's range is cut into n_sets equal strata and each stratum
+    is used exactly once, the strata being paired at random between parameters. As in SPOTPY the design ignores the
+    constraints; a set that violates one is not run and gets the worst score (trainer.py:1007-1020, 1101-1108)."""
+
+    def run(self, n_sets, batch=65536, seed=0):
+        rng = np.random.default_rng(seed)
+        n = int(n_sets)
+        design = {}
+        for name in self.space.names:
+            lo, hi = self.space.ranges[name]
+            design[name] = lo + (hi - lo) * (rng.permutation(n) + rng.uniform(0.0, 1.0, n)) / n
+        scores = [self.evaluate({k: v[i:i + int(batch)] for k, v in design.items()}) for i in range(0, n, int(batch))]
+        self.parameters, self.scores = design, np.concatenate(scores) if scores else np.empty(0)
+        return self.best()
+
+
 class BatchedSceUa(BatchedMonteCarlo):
     """Shuffled complex evolution (SCE-UA; Duan, Sorooshian & Gupta, Water Resour. Res. 28(4) 1992 and J. Hydrol. 158, 1994)
     with its complexes evolved SIDE BY SIDE — what `calibrate(spot_setup, "sceua", repetitions, ngs=…)` does one model run
@@ -276,4 +293,27 @@ class BatchedSceUa(BatchedMonteCarlo):
         self.scores = np.concatenate(self._scores)
         del self._drawn, self._scores
         best_score = -f[0] if HIGHER_IS_BETTER[self.objective] else f[0]
-        return {name: float(x[0, j]) for j, name in enumerate(names)}, float(best_score)
+        self._result = ({name: float(x[0, j]) for j, name in enumerate(names)}, float(best_score))
+        return self._result
+
+    def best(self):
+        """The best point of the final population (the algorithm's answer, the same with and without speculation)."""
+        if not hasattr(self, "_result"):
+            raise RuntimeError("no evaluation yet")
+        return self._result
+
+
+ALGORITHMS = {"mc": BatchedMonteCarlo, "lhs": BatchedLatinHypercube, "sceua": BatchedSceUa}
+
+
+def calibrate(model, space, observations, algorithm, repetitions, warmup=0, objective="nse", fixed=None, seed=0,
+              **algorithm_kwargs):
+    """The reference's `calibrate(spot_setup, algorithm, repetitions, **algorithm_kwargs)` (trainer.py:1272-1401) on the
+    batched engine: `algorithm` is SPOTPY's name ("mc", "lhs", "sceua"), `algorithm_kwargs` its sample() arguments
+    (sceua: ngs, kstop, pcento, peps; mc / lhs: batch). Returns the sampler; `sampler.best()` is `get_best`
+    (trainer.py:1607-1650), `sampler.parameters` / `sampler.scores` the database of every set that was run."""
+    if algorithm not in ALGORITHMS:
+        raise ValueError(f"algorithm {algorithm!r} is not available on the batched engine ({', '.join(ALGORITHMS)})")
+    sampler = ALGORITHMS[algorithm](model, space, observations, warmup=warmup, objective=objective, fixed=fixed)
+    sampler.run(repetitions, seed=seed, **algorithm_kwargs)
+    return sampler

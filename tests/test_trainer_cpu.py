@@ -153,3 +153,27 @@ def test_sceua_minimises_error_metrics_and_stops_on_convergence():
     flat = trainer.BatchedSceUa(_FakeModelN(names, lambda m: np.ones(len(m))), space, np.zeros(4), objective="rmse")
     flat.run(100000, ngs=2, seed=0, kstop=3, peps=0.0)
     assert flat.stop_reason.startswith("objective converged")
+
+
+def test_latin_hypercube_uses_every_stratum_once_and_calibrate_dispatches():
+    names = ["x", "y"]
+    space = trainer.ParameterSpace({"x": (0.0, 1.0), "y": (2.0, 4.0)}, [])
+    model = _FakeModelN(names, lambda m: 1.0 - (m[:, 0] - 0.3) ** 2 - (m[:, 1] - 3.1) ** 2)
+    lhs = trainer.calibrate(model, space, np.zeros(4), "lhs", 500, batch=200)
+    assert isinstance(lhs, trainer.BatchedLatinHypercube) and model.runs == [200, 200, 100]
+    assert sorted(np.floor(lhs.parameters["x"] * 500).astype(int)) == list(range(500))
+    assert sorted(np.floor((lhs.parameters["y"] - 2.0) / 2.0 * 500).astype(int)) == list(range(500))
+    best, score = lhs.best()
+    assert score == lhs.scores.max() and abs(best["x"] - 0.3) < 0.1 and abs(best["y"] - 3.1) < 0.2
+    # a constraint is not part of the design: violating sets are not run and score worst
+    constrained = trainer.ParameterSpace({"x": (0.0, 1.0), "y": (0.0, 1.0)}, [("x", "<", "y")])
+    model2 = _FakeModelN(names, lambda m: -np.abs(m[:, 0] - 0.2))
+    lhs2 = trainer.calibrate(model2, constrained, np.zeros(4), "lhs", 400)
+    assert 100 < model2.runs[0] < 300 and np.isneginf(lhs2.scores).sum() == 400 - model2.runs[0]
+    assert lhs2.best()[0]["x"] < lhs2.best()[0]["y"]
+    sce = trainer.calibrate(model2, constrained, np.zeros(4), "sceua", 600, ngs=3, seed=2)
+    assert isinstance(sce, trainer.BatchedSceUa) and abs(sce.best()[0]["x"] - 0.2) < 0.01
+    mc = trainer.calibrate(model2, constrained, np.zeros(4), "mc", 300, batch=100)
+    assert isinstance(mc, trainer.BatchedMonteCarlo) and len(mc.scores) == 300
+    with pytest.raises(ValueError, match="not available on the batched engine"):
+        trainer.calibrate(model2, constrained, np.zeros(4), "dream", 10)
