@@ -1000,7 +1000,8 @@ class ModelHydro:
 
     def dump_outputs(self, path):
         """ModelHydro::DumpOutputs -> ResultWriter::WriteNetCDF (ResultWriter.cpp:8-87): the same variables under the
-        same names in <path>/results.npz (netCDF is absent from this image); read it back with results.Results."""
+        same names in <path>/results.nc (netCDF classic, through scipy.io) and <path>/results.npz; read either back with
+        results.Results."""
         from . import results
 
         return results.write_results(self, path, self._cs.assign_structure_variants_ids(

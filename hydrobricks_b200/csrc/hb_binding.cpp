@@ -418,8 +418,8 @@ PYBIND11_MODULE(_hydrobricks, m) {
             return sum;
         })
         // ModelHydro::DumpOutputs -> ResultWriter::WriteNetCDF (ResultWriter.cpp:8-87): the same variables under the same
-        // names in <path>/results.npz (netCDF is absent from this image), written by hydrobricks_b200/results.py from this
-        // object's getters
+        // names in <path>/results.nc (netCDF classic) and <path>/results.npz, written by hydrobricks_b200/results.py from
+        // this object's getters
         .def("dump_outputs", [](py::object self, const std::string& path) -> bool {
             return py::module_::import("hydrobricks_b200.results").attr("write_results")(self, path).cast<bool>();
         }, "path"_a)

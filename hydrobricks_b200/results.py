@@ -1,9 +1,11 @@
 """Results file of a model run from the device recorder: the variables of the reference's `results.nc`
-(core/src/base/ResultWriter.cpp:8-87, written by ModelHydro::DumpOutputs -> Logger::DumpOutputs) under the same names and
-with the same dimension order, in a numpy `.npz` container — netCDF is not available in this image —, and a reader with the
-surface of python/src/hydrobricks/results.py (`Results`) on top of it.
+(core/src/base/ResultWriter.cpp:8-87, written by ModelHydro::DumpOutputs -> Logger::DumpOutputs) under the same names, with
+the same dimension order and attributes, and a reader with the surface of python/src/hydrobricks/results.py (`Results`).
 
-    results.npz
+Two containers are written side by side: `results.nc` — netCDF classic (64-bit offset) through scipy.io, the one netCDF
+writer in this image; xarray, ncdump or the netCDF4 package open it like the reference's file — and `results.npz`, the
+same arrays for numpy alone.
+
       time                       [time]                       float64, days since 1858-11-17 (MJD)
       hydro_units_ids            [hydro_units]                int32
       hydro_units_structure_ids  [hydro_units]                int32
@@ -11,10 +13,13 @@ surface of python/src/hydrobricks/results.py (`Results`) on top of it.
       sub_basin_values           [aggregated_values][time]    float64 (mm)
       hydro_units_values         [distributed_values][hydro_units][time]
       land_cover_fractions       [land_covers][hydro_units][time]        (only when fractions were recorded)
-      labels_aggregated, labels_distributed, labels_land_covers          string arrays (global attributes of the .nc)
+      labels_aggregated, labels_distributed, labels_land_covers          global attributes
 
-Stated difference: the engine's sub-basin recorder holds the outlet discharge only, so `labels_aggregated` is ["outlet"]
-(the reference also logs the contents and outflows of the two glacier-area stores when log_all is set).
+Stated differences: (1) the engine's sub-basin recorder holds the outlet discharge only, so `labels_aggregated` is
+["outlet"] (the reference also logs the contents and outflows of the two glacier-area stores when log_all is set);
+(2) the classic format has no string-array attributes (the reference's netCDF-4 file stores the labels as NC_STRING
+arrays, ResultWriter.cpp:76-79): the label lists are comma-joined text attributes (no label contains a comma), and the
+variables are not compressed.
 """
 from __future__ import annotations
 
@@ -23,11 +28,23 @@ from pathlib import Path
 import numpy as np
 
 FILE_NAME = "results.npz"
+NC_FILE_NAME = "results.nc"
+_LONG_NAMES = {  # ResultWriter.cpp:41-72: variable -> (dimensions, long_name, units)
+    "time": (("time",), "time", "days since 1858-11-17 00:00:00.0"),
+    "hydro_units_ids": (("hydro_units",), "hydrological units ids", None),
+    "hydro_units_structure_ids": (("hydro_units",), "model structure id used by each hydrological unit", None),
+    "hydro_units_areas": (("hydro_units",), "hydrological units areas", None),
+    "sub_basin_values": (("aggregated_values", "time"), "aggregated values over the sub basin", "mm"),
+    "hydro_units_values": (("distributed_values", "hydro_units", "time"), "values for each hydrological units", "mm"),
+    "land_cover_fractions": (("land_covers", "hydro_units", "time"), "land cover fractions for each hydrological units",
+                             "percent"),
+}
 
 
-def write_results(model, path, structure_ids=None):
-    """ModelHydro::DumpOutputs(path) for either host module's ModelHydro (after run()): writes <path>/results.npz and
-    returns True; False when the directory does not exist (ResultWriter.cpp:13-16)."""
+def write_results(model, path, structure_ids=None, netcdf=True):
+    """ModelHydro::DumpOutputs(path) for either host module's ModelHydro (after run()): writes <path>/results.nc (unless
+    netcdf=False) and <path>/results.npz and returns True; False when the directory does not exist
+    (ResultWriter.cpp:13-16)."""
     directory = Path(path)
     if not directory.is_dir():
         return False
@@ -58,7 +75,48 @@ def write_results(model, path, structure_ids=None):
         arrays["land_cover_fractions"] = fractions
         arrays["labels_land_covers"] = np.array(fraction_labels, dtype=str)
     np.savez_compressed(directory / FILE_NAME, **arrays)
+    if netcdf:
+        _write_netcdf(directory / NC_FILE_NAME, arrays)
     return True
+
+
+def _write_netcdf(path, arrays):
+    """ResultWriter.cpp:21-87 in netCDF classic, 64-bit offset (a variable may hold up to 4 GiB)."""
+    from scipy.io import netcdf_file
+
+    with netcdf_file(str(path), "w", version=2) as nc:
+        for name, (dims, _, _) in _LONG_NAMES.items():
+            if name in arrays:
+                for dim, size in zip(dims, arrays[name].shape):
+                    if dim not in nc.dimensions:
+                        nc.createDimension(dim, int(size))
+        for name, (dims, long_name, units) in _LONG_NAMES.items():
+            if name not in arrays:
+                continue
+            var = nc.createVariable(name, "i" if arrays[name].dtype.kind == "i" else "d", dims)
+            var[:] = arrays[name]
+            var.long_name = long_name
+            if units:
+                var.units = units
+        for name in ("labels_aggregated", "labels_distributed", "labels_land_covers"):
+            if name in arrays:
+                labels = [str(x) for x in arrays[name]]
+                if any("," in x for x in labels):
+                    raise ValueError(f"a label with a comma cannot be stored in {NC_FILE_NAME}: {labels}")
+                setattr(nc, name, ",".join(labels))
+
+
+def _read_netcdf(path):
+    from scipy.io import netcdf_file
+
+    with netcdf_file(str(path), "r", mmap=False) as nc:
+        out = {name: np.array(var[:]) for name, var in nc.variables.items()}
+        for name in ("labels_aggregated", "labels_distributed", "labels_land_covers"):
+            text = getattr(nc, name, None)
+            if text is not None:
+                text = text.decode() if isinstance(text, bytes) else str(text)
+                out[name] = np.array(text.split(",") if text else [], dtype=str)
+    return out
 
 
 def _time_axis(model, n_steps):
@@ -80,16 +138,19 @@ def _structure_ids(model, n_units):
 
 
 class Results:
-    """python/src/hydrobricks/results.py `Results` on a results.npz: the same attribute and method names, numpy instead
+    """python/src/hydrobricks/results.py `Results` on a results.nc / results.npz: the same attribute and method names, numpy instead
     of xarray. Dates are 'YYYY-MM-DD' strings; time selections return views [hydro_units x time] (or [hydro_units] for a
     single date), like the reference's `.sel(time=slice(...))`."""
 
     def __init__(self, filename):
         p = Path(filename)
         if p.is_dir():
-            p = p / FILE_NAME
-        with np.load(p) as z:
-            self.results = {k: z[k] for k in z.files}
+            p = p / FILE_NAME if (p / FILE_NAME).exists() else p / NC_FILE_NAME
+        if p.suffix == ".nc":
+            self.results = _read_netcdf(p)
+        else:
+            with np.load(p) as z:
+                self.results = {k: z[k] for k in z.files}
         self.labels_distributed = [str(x) for x in self.results["labels_distributed"]]
         self.labels_aggregated = [str(x) for x in self.results["labels_aggregated"]]
         self.labels_land_cover = [str(x) for x in self.results["labels_land_covers"]] \

@@ -89,3 +89,41 @@ def test_write_then_read(tmp_path):
         w = np.array([0.4e6, 1.4e6, 3.0e6, 0.6e6, 0.6e6, 0.0])
         stacked = np.concatenate([g.T, np.nan_to_num(s.T)])
         assert np.allclose(mean_swe, (stacked * w[:, None]).sum(0) / w.sum())
+
+
+def test_results_nc_holds_the_reference_layout(tmp_path):
+    """results.nc (netCDF classic through scipy.io): dimensions, variables, attributes and units of ResultWriter.cpp:21-87,
+    the same numbers as results.npz, and the Results reader gives the same answers on either file."""
+    from scipy.io import netcdf_file
+
+    m = FakeModel()
+    assert results.write_results(m, tmp_path)
+    with netcdf_file(str(tmp_path / "results.nc"), "r", mmap=False) as nc:
+        assert {k: v for k, v in nc.dimensions.items()} == {"time": 20, "hydro_units": 3, "aggregated_values": 1,
+                                                            "distributed_values": 3, "land_covers": 2}
+        assert nc.variables["time"].units == b"days since 1858-11-17 00:00:00.0"
+        assert nc.variables["time"].long_name == b"time" and nc.variables["time"][0] == 44605.0
+        assert nc.variables["hydro_units_values"].dimensions == ("distributed_values", "hydro_units", "time")
+        assert nc.variables["hydro_units_values"].units == b"mm" and nc.variables["sub_basin_values"].units == b"mm"
+        assert nc.variables["land_cover_fractions"].dimensions == ("land_covers", "hydro_units", "time")
+        assert nc.variables["land_cover_fractions"].units == b"percent"
+        assert nc.variables["hydro_units_ids"].typecode() == "i" and list(nc.variables["hydro_units_ids"][:]) == [7, 8, 9]
+        assert nc.variables["hydro_units_structure_ids"].long_name == b"model structure id used by each hydrological unit"
+        assert nc.labels_distributed.decode().split(",") == m.labels and nc.labels_aggregated == b"outlet"
+    with results.Results(tmp_path / "results.nc") as a, results.Results(tmp_path / "results.npz") as b:
+        assert a.labels_distributed == b.labels_distributed and a.labels_land_cover == b.labels_land_cover
+        for key in b.results:
+            if not key.startswith("labels_"):
+                assert np.array_equal(a.results[key], b.results[key], equal_nan=True), key
+        assert np.array_equal(a.get_sub_basin_values("outlet"), m.q)
+        assert np.array_equal(a.get_mean_swe(), b.get_mean_swe())
+        assert np.array_equal(a.get_hydro_units_values("reservoir:water_content", "1981-01-03"),
+                              b.get_hydro_units_values("reservoir:water_content", "1981-01-03"))
+    # a directory is enough; the .npz can be left out
+    (tmp_path / "only_nc").mkdir()
+    assert results.write_results(m, tmp_path / "only_nc")
+    (tmp_path / "only_nc" / "results.npz").unlink()
+    with results.Results(tmp_path / "only_nc") as r:
+        assert r.labels_aggregated == ["outlet"]
+    (tmp_path / "no_nc").mkdir()
+    assert results.write_results(m, tmp_path / "no_nc", netcdf=False) and not (tmp_path / "no_nc" / "results.nc").exists()
