@@ -138,8 +138,8 @@ def _structure_ids(model, n_units):
 
 
 class Results:
-    """python/src/hydrobricks/results.py `Results` on a results.nc / results.npz: the same attribute and method names, numpy instead
-    of xarray. Dates are 'YYYY-MM-DD' strings; time selections return views [hydro_units x time] (or [hydro_units] for a
+    """python/src/hydrobricks/results.py `Results` on a results.nc / results.npz: the same attribute and method names,
+    numpy instead of xarray. Dates are 'YYYY-MM-DD' strings; time selections return views [hydro_units x time] (or [hydro_units] for a
     single date), like the reference's `.sel(time=slice(...))`."""
 
     def __init__(self, filename):

@@ -8,10 +8,11 @@ ParameterSet's constraints and ranges hold (trainer.py:934-964), `simulation()` 
 Here the same three steps are batched: `ParameterSpace.sample()` draws n sets with the same rejection rule,
 `Socont.run_sets()` integrates them in one `hbk_run`, and the device scores every set (`hbk_compute_scores`), so only
 n scores travel back. SPOTPY itself is not in this image; its Monte-Carlo sampler — the one the reference's
-`examples/basics/analyse_mc_socont_parallel.py` uses — is what `BatchedMonteCarlo` restates. SCE-UA, the algorithm most of the reference's examples calibrate with
-(`calibrate(spot_setup, "sceua", …)`, examples/basics/calibrate_sceua_socont.py), is restated from the published algorithm
-in `BatchedSceUa`: its complexes evolve side by side, one launch per evolution step. Other samplers that propose sets from
-previous scores (DREAM …) can use `evaluate()` with whatever population they hold.
+`examples/basics/analyse_mc_socont_parallel.py` uses — is what `BatchedMonteCarlo` restates. SCE-UA, the algorithm
+most of the reference's examples calibrate with (`calibrate(spot_setup, "sceua", …)`,
+examples/basics/calibrate_sceua_socont.py), is restated from the published algorithm in `BatchedSceUa`: its complexes
+evolve side by side, one launch per evolution step. Other samplers that propose sets from previous scores (DREAM …) can
+use `evaluate()` with whatever population they hold.
 """
 from __future__ import annotations
 
