@@ -30,6 +30,12 @@ SOCONT_RANGES = {
 # models/socont.py:280-285 plus the splitter's transition_start < transition_end
 SOCONT_CONSTRAINTS = [("a_snow", "<", "a_ice"), ("k_slow_1", "<", "k_quick"), ("k_slow_2", "<", "k_quick"),
                       ("k_slow_2", "<", "k_slow_1"), ("prec_t_start", "<", "prec_t_end")]
+# models/socont.py:287-321: the reference's Socont calibrates the slow reservoirs' response factors as lk = log(k [1/h]),
+# the original SOCONT formulation, k [1/d] = 24 k [1/h]: alias -> (real -> transformed, transformed -> real)
+SOCONT_TRANSFORMS = {
+    "k_slow_1": (lambda rf: np.log(np.asarray(rf) / 24.0), lambda lk: 24.0 * np.exp(lk)),
+    "k_slow_2": (lambda rf: np.log(np.asarray(rf) / 24.0), lambda lk: 24.0 * np.exp(lk)),
+}
 _OPS = {"<": np.less, "lt": np.less, "<=": np.less_equal, "le": np.less_equal, ">": np.greater, "gt": np.greater,
         ">=": np.greater_equal, "ge": np.greater_equal}
 # the objective functions hbk_compute_scores has on the device (HydroErr's names) and their orientation
@@ -42,7 +48,12 @@ class ParameterSpace:
     """The parameters allowed to change, their ranges and the constraints between them
     (ParameterSet.allow_changing / change_range / define_constraint, parameters.py:807-1078)."""
 
-    def __init__(self, ranges, constraints=()):
+    def __init__(self, ranges, constraints=(), transforms=None):
+        """transforms: {name: (to_transformed, to_real)} or objects with those two attributes (the reference's
+        ParameterTransform, parameters.py:43-56). The samplers then search that parameter in the transformed space —
+        uniform between the transformed bounds, like ParameterSet.get_for_spotpy (parameters.py:1492-1502) — and every
+        value that reaches the model, the constraints or the database is mapped back to the real one
+        (SpotpySetup.parameters(), trainer.py:955-956)."""
         self.ranges = {k: (float(lo), float(hi)) for k, (lo, hi) in ranges.items()}
         for name, (lo, hi) in self.ranges.items():
             if not lo <= hi:
@@ -52,20 +63,55 @@ class ParameterSpace:
             if op not in _OPS:
                 raise ValueError(f"unknown constraint operator {op!r}")
         self.names = list(self.ranges)
+        self.transforms = {}
+        for name, t in (transforms or {}).items():
+            if name not in self.ranges:
+                raise ValueError(f"transform of {name}: the parameter is not part of the space")
+            self.transforms[name] = (t.to_transformed, t.to_real) if hasattr(t, "to_real") else tuple(t)
+
+    def optimizer_bounds(self, name):
+        """The search interval of a parameter: its range, mapped through its transform if it has one (sorted: the map
+        may be decreasing)."""
+        lo, hi = self.ranges[name]
+        if name in self.transforms:
+            forward = self.transforms[name][0]
+            lo, hi = sorted([float(forward(lo)), float(forward(hi))])
+        return lo, hi
+
+    def to_real(self, name, values):
+        """Optimizer-space values of one parameter -> real values."""
+        values = np.asarray(values, dtype=np.float64)
+        if name not in self.transforms:
+            return values
+        inverse = self.transforms[name][1]
+        try:
+            real = np.asarray(inverse(values), dtype=np.float64)
+            if real.shape == values.shape:
+                return real
+        except (TypeError, ValueError):
+            pass
+        return np.array([float(inverse(float(v))) for v in values.ravel()]).reshape(values.shape)  # scalar-only callables
 
     @classmethod
-    def for_socont(cls, names, constraints=SOCONT_CONSTRAINTS):
+    def for_socont(cls, names, constraints=SOCONT_CONSTRAINTS, transforms="reference"):
+        """The reference's ranges, constraints and — unless transforms=None (search the real values) or an own table is
+        given — its log-space convention for the slow reservoirs' response factors (SOCONT_TRANSFORMS)."""
         unknown = [n for n in names if n not in SOCONT_RANGES]
         if unknown:
             raise ValueError(f"no reference range for {unknown}")
-        return cls({n: SOCONT_RANGES[n] for n in names}, constraints)
+        if isinstance(transforms, str):
+            if transforms != "reference":
+                raise ValueError(f"transforms: 'reference', None or a table, not {transforms!r}")
+            transforms = SOCONT_TRANSFORMS
+        transforms = {n: t for n, t in (transforms or {}).items() if n in names}
+        return cls({n: SOCONT_RANGES[n] for n in names}, constraints, transforms)
 
     @classmethod
     def from_parameter_set(cls, parameter_set, allow_changing=None):
         """From the reference's ParameterSet (its `parameters` table with aliases/min/max, its `constraints` and
         `allow_changing` lists), so that existing calibration scripts keep their parameter definitions."""
         names = list(allow_changing if allow_changing is not None else parameter_set.allow_changing)
-        ranges = {}
+        ranges, transforms = {}, {}
         for name in names:
             row = None
             for _, r in parameter_set.parameters.iterrows():
@@ -78,7 +124,10 @@ class ParameterSpace:
             if isinstance(row["min"], list):
                 raise ValueError("list parameters are not supported by the batched sampler")
             ranges[name] = (row["min"], row["max"])
-        return cls(ranges, [tuple(c) for c in parameter_set.constraints])
+            transform = row["transform"] if "transform" in row.index else None
+            if transform is not None and hasattr(transform, "to_real"):
+                transforms[name] = transform
+        return cls(ranges, [tuple(c) for c in parameter_set.constraints], transforms)
 
     def satisfied(self, values):
         """Mask [n] of the draws that satisfy every constraint whose two parameters are in the space
@@ -94,21 +143,31 @@ class ParameterSpace:
             ok &= (v >= lo) & (v <= hi)
         return ok
 
-    def sample(self, n, rng, max_attempts=1000):
-        """n uniform draws; a draw that violates a constraint is redrawn, at most `max_attempts` times, then the
-        sampler gives up like SpotpySetup.parameters() (trainer.py:948-964)."""
-        values = {name: rng.uniform(lo, hi, n) for name, (lo, hi) in self.ranges.items()}
-        bad = ~self.satisfied(values)
+    def sample_optimizer(self, n, rng, max_attempts=1000):
+        """n uniform draws in the optimizer space [n x parameters]; a draw whose real values violate a constraint or a
+        range is redrawn, at most `max_attempts` times, then the sampler gives up like SpotpySetup.parameters()
+        (trainer.py:948-964)."""
+        bounds = [self.optimizer_bounds(name) for name in self.names]
+        x = np.column_stack([rng.uniform(lo, hi, n) for lo, hi in bounds]) if self.names else np.empty((n, 0))
+        bad = ~self.satisfied(self.real_values(x))
         for _ in range(max_attempts):
             if not bad.any():
-                return values
+                return x
             k = int(bad.sum())
-            for name, (lo, hi) in self.ranges.items():
-                values[name][bad] = rng.uniform(lo, hi, k)
-            bad = ~self.satisfied(values)
+            for j, (lo, hi) in enumerate(bounds):
+                x[bad, j] = rng.uniform(lo, hi, k)
+            bad = ~self.satisfied(self.real_values(x))
         if bad.any():
             raise RuntimeError("The parameter constraints could not be satisfied.")
-        return values
+        return x
+
+    def real_values(self, x):
+        """Optimizer-space matrix [n x parameters] -> {name: real values [n]}."""
+        return {name: self.to_real(name, np.ascontiguousarray(x[:, j])) for j, name in enumerate(self.names)}
+
+    def sample(self, n, rng, max_attempts=1000):
+        """n draws as real values {name: [n]} (uniform in the optimizer space, constraints and ranges satisfied)."""
+        return self.real_values(self.sample_optimizer(n, rng, max_attempts))
 
 
 class BatchedMonteCarlo:
@@ -175,9 +234,9 @@ class BatchedLatinHypercube(BatchedMonteCarlo):
         rng = np.random.default_rng(seed)
         n = int(n_sets)
         design = {}
-        for name in self.space.names:
-            lo, hi = self.space.ranges[name]
-            design[name] = lo + (hi - lo) * (rng.permutation(n) + rng.uniform(0.0, 1.0, n)) / n
+        for name in self.space.names:  # strata of the optimizer space, values stored as real ones
+            lo, hi = self.space.optimizer_bounds(name)
+            design[name] = self.space.to_real(name, lo + (hi - lo) * (rng.permutation(n) + rng.uniform(0.0, 1.0, n)) / n)
         scores = [self.evaluate({k: v[i:i + int(batch)] for k, v in design.items()}) for i in range(0, n, int(batch))]
         self.parameters, self.scores = design, np.concatenate(scores) if scores else np.empty(0)
         return self.best()
@@ -210,7 +269,7 @@ class BatchedSceUa(BatchedMonteCarlo):
         return np.where(np.isnan(cost), np.inf, cost)
 
     def _as_values(self, x):
-        return {name: np.ascontiguousarray(x[:, j]) for j, name in enumerate(self.space.names)}
+        return self.space.real_values(x)
 
     def run(self, repetitions, ngs=20, kstop=100, pcento=1e-7, peps=1e-7, seed=0, speculative=True):
         """repetitions: evaluation budget; ngs: number of complexes; kstop / pcento: stop when the best cost changed by
@@ -219,8 +278,8 @@ class BatchedSceUa(BatchedMonteCarlo):
         it got there, `parameters` / `scores` hold every set that was run (SPOTPY's database)."""
         names = self.space.names
         n = len(names)
-        lo = np.array([self.space.ranges[k][0] for k in names])
-        hi = np.array([self.space.ranges[k][1] for k in names])
+        lo = np.array([self.space.optimizer_bounds(k)[0] for k in names])  # the population lives in the optimizer space
+        hi = np.array([self.space.optimizer_bounds(k)[1] for k in names])
         span = np.where(hi > lo, hi - lo, 1.0)
         ngs, npg, nps = int(ngs), 2 * n + 1, n + 1
         nspl, npt = npg, int(ngs) * (2 * n + 1)
@@ -228,9 +287,8 @@ class BatchedSceUa(BatchedMonteCarlo):
         self._drawn, self._scores = {name: [] for name in names}, []
         self.launches = self.loops = 0
 
-        first = self.space.sample(npt, rng)
-        x = np.column_stack([first[k] for k in names])
-        f = self._cost(first)
+        x = self.space.sample_optimizer(npt, rng)
+        f = self._cost(self._as_values(x))
         self.evaluations = npt
         order = np.argsort(f, kind="stable")
         x, f = x[order], f[order]
@@ -247,8 +305,7 @@ class BatchedSceUa(BatchedMonteCarlo):
                 worst = members[:, -1]
                 sw, fw = cx[k_idx, worst], cf[k_idx, worst]
                 centroid = np.stack([cx[k, members[k, :-1]].mean(axis=0) for k in range(ngs)])
-                random_point = self.space.sample(ngs, rng)
-                random_point = np.column_stack([random_point[k] for k in names])
+                random_point = self.space.sample_optimizer(ngs, rng)
                 reflection = centroid + self.ALPHA * (centroid - sw)
                 outside = ((reflection < lo) | (reflection > hi)).any(axis=1)
                 reflection[outside] = random_point[outside]  # a reflection that leaves the feasible space: mutation
@@ -294,7 +351,7 @@ class BatchedSceUa(BatchedMonteCarlo):
         self.scores = np.concatenate(self._scores)
         del self._drawn, self._scores
         best_score = -f[0] if HIGHER_IS_BETTER[self.objective] else f[0]
-        self._result = ({name: float(x[0, j]) for j, name in enumerate(names)}, float(best_score))
+        self._result = ({name: float(v[0]) for name, v in self._as_values(x[:1]).items()}, float(best_score))
         return self._result
 
     def best(self):

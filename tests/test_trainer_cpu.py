@@ -12,8 +12,18 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 def test_sample_respects_ranges_and_constraints():
-    space = trainer.ParameterSpace.for_socont(["a_snow", "a_ice", "k_slow_1", "k_slow_2", "k_quick", "A"])
+    space = trainer.ParameterSpace.for_socont(["a_snow", "a_ice", "k_slow_1", "k_slow_2", "k_quick", "A"], transforms=None)
+    assert not space.transforms
     v = space.sample(5000, np.random.default_rng(1))
+    # without transforms the draws are plain uniform ones in the order of the names, the rejected sets redrawn together
+    rng = np.random.default_rng(1)
+    plain = {name: rng.uniform(lo, hi, 5000) for name, (lo, hi) in space.ranges.items()}
+    bad = ~space.satisfied(plain)
+    while bad.any():
+        for name, (lo, hi) in space.ranges.items():
+            plain[name][bad] = rng.uniform(lo, hi, int(bad.sum()))
+        bad = ~space.satisfied(plain)
+    assert all(np.array_equal(v[name], plain[name]) for name in space.names)
     assert set(v) == set(space.names) and all(len(x) == 5000 for x in v.values())
     assert (v["a_snow"] < v["a_ice"]).all()  # models/socont.py:280-285
     assert (v["k_slow_2"] < v["k_slow_1"]).all() and (v["k_slow_1"] < v["k_quick"]).all()
@@ -86,6 +96,24 @@ def test_space_from_the_reference_parameter_set():
     assert (v["k_slow_2"] < v["k_slow_1"]).all()
     for name in space.names:
         assert trainer.SOCONT_RANGES[name] == space.ranges[name]
+    # a transform attached to the reference's ParameterSet (set_transform, parameters.py:948-988; scalar-only callables
+    # as in the reference's own tests) moves the search of that parameter to the transformed space
+    import math
+
+    # the reference's Socont searches the response factors as lk = log(k / 24) (models/socont.py:287-321): the same
+    # convention as SOCONT_TRANSFORMS
+    assert sorted(space.transforms) == ["k_slow_1", "k_slow_2"]
+    own = trainer.ParameterSpace.for_socont(["k_slow_1", "k_slow_2", "A"])
+    assert sorted(own.transforms) == ["k_slow_1", "k_slow_2"]
+    for name in own.transforms:
+        assert np.allclose(own.optimizer_bounds(name), space.optimizer_bounds(name), rtol=1e-15)
+        assert np.allclose(own.to_real(name, np.array([-9.0, -5.5])), space.to_real(name, np.array([-9.0, -5.5])), rtol=1e-15)
+    ps.set_transform("k_slow_1", math.log, math.exp)
+    space = trainer.ParameterSpace.from_parameter_set(ps, ["k_slow_1", "k_slow_2", "A"])
+    assert np.allclose(space.optimizer_bounds("k_slow_1"), sorted([math.log(space.ranges["k_slow_1"][0]), 0.0]))
+    assert space.optimizer_bounds("A") == (0.0, 3000.0)
+    v = space.sample(4000, np.random.default_rng(6))
+    assert space.satisfied(v).all() and (v["k_slow_2"] < v["k_slow_1"]).all()
 
 
 class _FakeModelN:
@@ -177,3 +205,34 @@ def test_latin_hypercube_uses_every_stratum_once_and_calibrate_dispatches():
     assert isinstance(mc, trainer.BatchedMonteCarlo) and len(mc.scores) == 300
     with pytest.raises(ValueError, match="not available on the batched engine"):
         trainer.calibrate(model2, constrained, np.zeros(4), "dream", 10)
+
+
+def test_transforms_move_the_search_to_the_transformed_space():
+    """ParameterTransform (parameters.py:43-56): uniform in log space = log-uniform real values (half of the draws below
+    the geometric mean of the range), real values everywhere outside the sampler, decreasing maps handled, and SCE-UA /
+    the Latin hypercube search the same space."""
+    space = trainer.ParameterSpace({"k": (1e-4, 1.0), "y": (0.0, 1.0)}, [],
+                                   transforms={"k": (np.log10, lambda t: 10.0 ** t)})
+    assert np.allclose(space.optimizer_bounds("k"), (-4.0, 0.0)) and space.optimizer_bounds("y") == (0.0, 1.0)
+    v = space.sample(20000, np.random.default_rng(0))
+    assert v["k"].min() >= 1e-4 and v["k"].max() <= 1.0 and abs(np.mean(v["k"] < 1e-2) - 0.5) < 0.02
+    assert abs(np.mean(v["y"] < 0.5) - 0.5) < 0.02
+    # a decreasing map (1 / k) and a constraint checked on the real values
+    inv = trainer.ParameterSpace({"k": (0.5, 4.0), "y": (0.0, 4.0)}, [("k", "<", "y")],
+                                 transforms={"k": (lambda r: 1.0 / r, lambda t: 1.0 / t)})
+    assert np.allclose(inv.optimizer_bounds("k"), (0.25, 2.0))
+    w = inv.sample(5000, np.random.default_rng(1))
+    assert (w["k"] < w["y"]).all() and w["k"].min() >= 0.5 and w["k"].max() <= 4.0
+    with pytest.raises(ValueError, match="not part of the space"):
+        trainer.ParameterSpace({"k": (0.0, 1.0)}, [], transforms={"z": (np.log, np.exp)})
+
+    # the optimum sits three decades below the top of the range: found in log space to a relative 1e-3
+    names = ["k", "y"]
+    model = _FakeModelN(names, lambda m: 1.0 - (np.log10(m[:, 0]) + 3.0) ** 2 - (m[:, 1] - 0.5) ** 2)
+    sce = trainer.calibrate(model, space, np.zeros(4), "sceua", 3000, ngs=4, seed=4)
+    best, score = sce.best()
+    assert abs(best["k"] / 1e-3 - 1.0) < 2e-2 and abs(best["y"] - 0.5) < 1e-2 and score > 1 - 1e-4
+    assert sce.parameters["k"].min() >= 1e-4 * (1 - 1e-12) and sce.parameters["k"].max() <= 1.0 + 1e-12  # real values
+    lhs = trainer.calibrate(model, space, np.zeros(4), "lhs", 1000)
+    strata = np.floor((np.log10(lhs.parameters["k"]) + 4.0) / 4.0 * 1000 + 1e-9).astype(int)
+    assert len(set(strata)) >= 998  # one draw per stratum of the LOG axis (up to rounding at the stratum edges)

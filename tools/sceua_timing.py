@@ -39,7 +39,7 @@ def main():
     truth = {"a_snow": 5.0, "A": 400.0, "k_slow_1": 0.05, "beta": 2000.0}
     m.run_sets(m.parameter_matrix({k: [v] for k, v in truth.items()}, 1))
     obs = m.model.get_outlet_discharge_batch()[0].copy()
-    space = trainer.ParameterSpace.for_socont(list(truth))
+    space = trainer.ParameterSpace.for_socont(list(truth), transforms=None)
     for ngs in a.ngs:
         sce = trainer.BatchedSceUa(m, space, obs, warmup=warm, objective="nse")
         t0 = time.perf_counter()
