@@ -375,3 +375,23 @@ def calibrate(model, space, observations, algorithm, repetitions, warmup=0, obje
     sampler = ALGORITHMS[algorithm](model, space, observations, warmup=warmup, objective=objective, fixed=fixed)
     sampler.run(repetitions, seed=seed, **algorithm_kwargs)
     return sampler
+
+
+def get_results(sampler):
+    """Every set that was run, as a table: `score` (the metric's own value, no optimiser sign) and one column of real
+    values per parameter — the reference's get_results(sampler) (trainer.py:1560-1605)."""
+    import pandas as pd
+
+    return pd.DataFrame({"score": np.asarray(sampler.scores, dtype=np.float64), **sampler.parameters})
+
+
+def get_best(sampler):
+    """{'score', 'parameters', 'index'}: the best row of get_results (highest skill, or lowest error for the error
+    metrics), like the reference's get_best(sampler) (trainer.py:1607-1672); raises when no run has a finite score."""
+    scores = np.asarray(sampler.scores, dtype=np.float64)
+    if not np.isfinite(scores).any():
+        raise RuntimeError("No finite objective values in the calibration results.")
+    higher = HIGHER_IS_BETTER[sampler.objective]
+    masked = np.where(np.isfinite(scores), scores, -np.inf if higher else np.inf)
+    i = int(np.argmax(masked) if higher else np.argmin(masked))
+    return {"score": float(scores[i]), "parameters": {k: float(v[i]) for k, v in sampler.parameters.items()}, "index": i}

@@ -236,3 +236,21 @@ def test_transforms_move_the_search_to_the_transformed_space():
     lhs = trainer.calibrate(model, space, np.zeros(4), "lhs", 1000)
     strata = np.floor((np.log10(lhs.parameters["k"]) + 4.0) / 4.0 * 1000 + 1e-9).astype(int)
     assert len(set(strata)) >= 998  # one draw per stratum of the LOG axis (up to rounding at the stratum edges)
+
+
+def test_get_results_and_get_best_read_the_database():
+    names = ["x", "y"]
+    space = trainer.ParameterSpace({"x": (0.0, 1.0), "y": (0.0, 1.0)}, [("x", "<", "y")])
+    model = _FakeModelN(names, lambda m: np.abs(m[:, 0] - 0.2))
+    lhs = trainer.calibrate(model, space, np.zeros(4), "lhs", 300, objective="mae")
+    df = trainer.get_results(lhs)
+    assert list(df.columns) == ["score", "x", "y"] and len(df) == 300
+    best = trainer.get_best(lhs)
+    assert best["score"] == df["score"].min() and df["x"].iloc[best["index"]] == best["parameters"]["x"]
+    assert np.isposinf(df["score"]).sum() > 50 and best["parameters"]["x"] < best["parameters"]["y"]  # rejected sets kept
+    sce = trainer.calibrate(_FakeModelN(names, lambda m: 1 - (m[:, 0] - 0.2) ** 2), space, np.zeros(4), "sceua", 300, ngs=2)
+    assert trainer.get_best(sce)["score"] >= sce.best()[1]  # the database also holds the speculative candidates
+    empty = trainer.BatchedMonteCarlo(model, space, np.zeros(4))
+    empty.scores, empty.parameters = np.array([np.nan, -np.inf]), {"x": np.zeros(2), "y": np.ones(2)}
+    with pytest.raises(RuntimeError, match="No finite objective"):
+        trainer.get_best(empty)
