@@ -91,3 +91,17 @@ def test_reference_setup_reaches_the_engine(backend):
         with pytest.raises(Exception) as err:
             socont.setup(spatial_structure=hu, output_path="/tmp", start_date="1981-01-01", end_date="1981-12-31")
         assert "CUDA" in str(err.value) or "hbk" in str(err.value)
+
+
+def test_the_reference_own_python_tests_pass_on_the_host_module():
+    """The reference's OWN test files that stop before a model run (parameters, binding surface, hydro units, ET process
+    structures, periods), with its
+    extension module replaced by this repo's: every test passes (the two skipped ones want SPOTPY)."""
+    import re
+    import subprocess
+
+    out = subprocess.run([sys.executable, str(ROOT / "tools" / "run_reference_tests.py"), "b200", "test_parameters.py",
+                          "test_binding.py", "test_hydro_units.py", "test_et_processes.py", "test_periods.py"], capture_output=True, text=True, timeout=600)
+    tail = out.stdout.strip().splitlines()[-1]
+    assert out.returncode == 0 and "failed" not in tail and "error" not in tail, out.stdout[-2000:]
+    assert int(re.search(r"(\d+) passed", tail).group(1)) >= 81
